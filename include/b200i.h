@@ -1,0 +1,234 @@
+/*
+ * b200i.h -- C ABI of the B200-native INSITE hot path (libb200insite.so).
+ *
+ * The reference (samholt/ODE-Discovery-for-Longitudinal-Heterogeneous-Treatment-Effects-Inference)
+ * is pure Python and has no FFI for this path; its boundary is the Python call signatures listed in
+ * SURVEY.md §8(b).  Each entry point below names the reference function it replaces (file:line under
+ * the reference root).  The Python host layer (package dir, `cancer_simulation.py`, `sindy.py`) keeps
+ * the reference signatures and calls these through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`; all arrays are row-major,
+ *    C-contiguous, float64 unless stated, exactly the numpy layout of the reference dicts
+ *    (SURVEY.md App. D), so `torch.from_numpy(a).cuda().data_ptr()` can be passed as is;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *    stream-ordered, nothing synchronises unless documented;
+ *  - caller owns every buffer; nothing is allocated inside except where a function takes a
+ *    workspace pointer + size;
+ *  - return value: 0 ok; <0 argument error (B200I_E_*); >0 a cudaError_t.  b200i_last_error()
+ *    returns a thread-local message for the last non-zero return.
+ */
+#ifndef B200I_H
+#define B200I_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200I_API __attribute__((visibility("default")))
+#else
+#define B200I_API
+#endif
+
+#define B200I_OK 0
+#define B200I_E_ARG (-1)        /* NULL pointer / negative size */
+#define B200I_E_UNSUPPORTED (-2)/* configuration outside the kernels' range (e.g. lag != 0) */
+#define B200I_E_ALIGN (-3)      /* pointer or row pitch not 16-byte aligned for the TMA path */
+#define B200I_E_WORKSPACE (-4)  /* workspace too small */
+#define B200I_E_DRIVER (-5)     /* cuTensorMapEncodeTiled unavailable / failed */
+
+#define B200I_NUM_PARAMS 10     /* rows of the parameter block, order below */
+/* parameter block `params` is (10, N) row-major, rows in this order (keys of the dict returned by
+ * generate_params, cancer_simulation.py:195-203, 84-88):
+ *   0 initial_volumes 1 alpha 2 rho 3 beta 4 beta_c 5 K
+ *   6 chemo_sigmoid_intercepts 7 radio_sigmoid_intercepts 8 chemo_sigmoid_betas 9 radio_sigmoid_betas */
+
+/* scalar constants of the simulator, computed by the host in float64 exactly as the reference
+ * does (cancer_simulation.py:34-44, 231-241) and passed by value. */
+typedef struct {
+    double death_threshold;   /* TUMOUR_DEATH_THRESHOLD = calc_volume(13)            :44  */
+    double cell_density;      /* TUMOUR_CELL_DENSITY = 5.8e8                          :43  */
+    double sphere_coef;       /* 4 / 3 * pi  (calc_diameter denominator)              :39  */
+    double chemo_amt;         /* 5.0                                                  :233 */
+    double radio_amt;         /* 2.0                                                  :231 */
+    double drug_decay;        /* exp(-log(2) / drug_half_life) = 0.5                  :338 */
+    int32_t window_size;      /* 1..15                                                :252 */
+    int32_t lag;              /* only 0 is supported by the CUDA path                 :253 */
+} b200i_sim_consts;
+
+B200I_API const char *b200i_last_error(void);
+B200I_API int b200i_version(void);
+/* number of SMs of the current device (grid sizing is done inside; exposed for reporting) */
+B200I_API int b200i_device_sms(int *sms_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  simulate_factual -- cancer_simulation.py:218-375 (loop :282-354).
+ * in : params (10,N); noise/recovery_rvs/chemo_rvs/radio_rvs (N,T) pre-drawn in the reference's
+ *      order (:275-279; noise already multiplied by 0.01); assigned_actions (N,T,2) or NULL (:317).
+ * out: nine (N,T) arrays + sequence_lengths (N,), keys of the dict at :356-367.  Every element of
+ *      every output is written (zeros included) -- buffers need not be pre-zeroed.
+ * variant: 0 = auto (TMA-tiled kernel when T is even and all (N,T) pointers are 16 B aligned, else the
+ *      generic kernel); 1 = generic thread-per-patient kernel; >=2 = explicit TMA tile shapes
+ *      (see csrc/sim_factual.cu), used by the tuning sweep in bench.py.
+ * gram_partials: NULL, or a workspace of b200i_gram_workspace_bytes() bytes: the kernel then also
+ *      accumulates the population statistics of K4 on the fly (fused theta_gram) and leaves the
+ *      reduced result in the first B200I_STATS_DOUBLES doubles of the workspace.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *consts,
+                      const double *params,
+                      const double *noise, const double *recovery_rvs,
+                      const double *chemo_rvs, const double *radio_rvs,
+                      const double *assigned_actions,
+                      double *cancer_volume, double *chemo_dosage, double *radio_dosage,
+                      double *chemo_application, double *radio_application,
+                      double *chemo_probabilities, double *radio_probabilities,
+                      double *death_flags, double *recovery_flags, double *sequence_lengths,
+                      const double *static_feature, double fd_dt, void *gram_workspace,
+                      int32_t variant, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  theta_gram -- the data reduction behind SINDY.fit: constant-treatment snippeting
+ * (pkpd/utils.py:433-462), order-1 finite differences and the [1,x0,u0,x0*u0] library of the
+ * pysindy call at sindy.py:203-213, reduced to per-treatment normal equations, plus the moments
+ * get_scaling_params needs (cancer_simulation.py:776-796).
+ * in : cancer_volume/chemo_application/radio_application (N,T), sequence_lengths (N,) float64,
+ *      static_feature (N,) float64 (the un-scaled patient type), chemo_dosage/radio_dosage (N,T) or
+ *      NULL (moments of those two are then left 0).
+ * out: stats[B200I_STATS_DOUBLES] (layout below), reduced over all N patients in a fixed order
+ *      (deterministic for a fixed N and launch shape).
+ * workspace: b200i_gram_workspace_bytes() bytes, 16 B aligned; stats live at its start.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200I_GRAM_PER_TREATMENT 15 /* 10 upper-triangular Gram entries (row-major: 00 01 02 03 11 12 13 22 23 33),
+                                       4 right-hand sides (Theta^T xdot), 1 sample count */
+#define B200I_MOMENTS 8             /* sum v, sum v^2, sum C, sum C^2, sum d, sum d^2 over active entries; active count; N */
+#define B200I_STATS_DOUBLES (4 * B200I_GRAM_PER_TREATMENT + B200I_MOMENTS)
+B200I_API int64_t b200i_gram_workspace_bytes(void);
+B200I_API int b200i_theta_gram(int64_t n, int32_t T, double fd_dt,
+                     const double *cancer_volume, const double *chemo_application,
+                     const double *radio_application, const double *sequence_lengths,
+                     const double *static_feature,
+                     const double *chemo_dosage, const double *radio_dosage,
+                     void *gram_workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  population STLSQ -- pysindy STLSQ(threshold, alpha, max_iter) + unbias refit, semantics of the
+ * vendored copy pkpd/utils.py:244-327 and of sindy.py:194,203-213: per treatment, on the 4x4 normal
+ * equations: repeat { solve (G[ind,ind] + alpha I) c = b[ind]; ind &= |c| >= threshold } until the
+ * support stops changing (<= max_iter), then OLS on the final support.
+ * in : stats (device, B200I_STATS_DOUBLES, e.g. after the cross-GPU all-reduce).
+ * out: coefs (4,4) device float64 = SINDY.joint_coefs (sindy.py:334); support (4,4) int32 device.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_stlsq_population(const double *stats, double threshold, double alpha, int32_t max_iter,
+                           double *coefs, int32_t *support, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  ode_rollout -- SINDY._get_non_fine_tuned_predictions (sindy.py:371-431) and
+ * predict_with_reduced_coefs (sindy.py:767-778) with the Euler integrator of pkpd/utils.py:68-90:
+ * open loop from x0, `substeps` explicit-Euler sub-steps of dt/substeps per interval, the ODE of the
+ * interval chosen by the treatment code (argmax of the one-hot, sindy.py:310,499).
+ * in : x0 (R,), static_feature (R,), codes (R,W) uint8 in 0..3, coefs (4,4) shared by all rows
+ *      (coefs_per_row == 0) or (R,4,4) (coefs_per_row == 1).  Terms with |c| <= drop_below are
+ *      dropped (1e-3 for the population path, pkpd/utils.py:388; pass a negative value to keep all).
+ * out: pred (R,W) un-scaled volumes.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t substeps,
+                      const double *x0, const double *static_feature, const uint8_t *codes,
+                      const double *coefs, int32_t coefs_per_row, double drop_below,
+                      double *pred, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * treatment codes: code = chemo + 2*radio of the (R,Wfull) application arrays, columns [0,W)
+ * (dataset.py:127-141: one-hot index of [none, chemo, radio, both]).
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_treatment_codes(int64_t rows, int32_t W, int32_t row_pitch,
+                          const double *chemo_application, const double *radio_application,
+                          uint8_t *codes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * masked squared-error sums for TimeVaryingCausalModel.get_normalised_masked_rmse /
+ * get_normalised_n_step_rmses (time_varying_model.py:236-313): for predictions and targets (R,W)
+ * in un-scaled units and integer active lengths (active_entries[i,:len]=1, dataset.py:162-164):
+ * out: sums (3*W + 2) doubles: se_col[W] (sum over rows of active squared error per column),
+ *      cnt_col[W] (active rows per column), se_last_col[W] (squared error at the last active
+ *      entry, binned by column), then total se_last and count_last.  W <= 128.
+ * workspace: b200i_masked_se_workspace_bytes() bytes (block partials; ordered, atomics-free sum).
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int64_t b200i_masked_se_workspace_bytes(void);
+B200I_API int b200i_masked_se(int64_t rows, int32_t W, const double *pred, const double *target,
+                    const int32_t *active_len, double *sums, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Counterfactual generators -- compact, device-resident representation.
+ *
+ * The reference materialises one dense row per (patient, t, option) (R ~ 227 N rows of width T for
+ * the one-step set, R ~ 562 N rows of width T+H for treatment sequences, cancer_simulation.py:423-430,
+ * :621-630): 0.9 TB at N = 1M.  Here a cohort is stored per patient:
+ *   factual       (N,T)    float64  clipped factual trajectory F (F[t+1] written at step t)
+ *   codes         (N,T)    uint8    factual option index at step t: 2*chemo + radio (reference option
+ *                                   order (0,0),(0,1),(1,0),(1,1), :513); 0 after the last step
+ *   n_steps       (N,)     int32    executed steps (t_last + 1)
+ *   one-step:  cf (N,T-1,4)   float64  un-clipped next volume under each of the 4 options (:536-538)
+ *   tr.-seq.:  cf (N,T-1,2H,H) float64 the H projected volumes of each of the 2H sliding options
+ *                                   (:721-743); valid (N,T-1) uint16 bit o set iff option o produced
+ *                                   a row (no NaN, :745-746)
+ *   n_rows        (N,)     int32    rows the reference would have emitted for this patient
+ *   row_offsets   (N+1,)   int64    exclusive prefix sum of n_rows = reference row index of the
+ *                                   patient's first row (test_idx at :432/:632)
+ * b200i_expand_* turn a row range of this into the reference's dense arrays.
+ *
+ * Cross-row window: the reference computes patient i's treatment probabilities from OUTPUT ROW i
+ * (cancer_simulation.py:471, :671), i.e. from a row emitted by an earlier patient j(i).  A cohort is
+ * therefore simulated in dependency levels (level k+1 = the patients whose row index falls into rows
+ * emitted by level k); the level loop runs inside these calls and synchronises the stream once per
+ * level (depth ~ log_227 N resp. log_562 N).  For a shard of a larger cohort pass `source`: the
+ * compact arrays of the global prefix of patients that own rows [0, global_base + n), simulated
+ * redundantly on every rank; then no level loop is needed.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n;                    /* patients in the source cohort (global indices 0..n-1) */
+    const double *factual;        /* (n,T) */
+    const uint8_t *codes;         /* (n,T) */
+    const double *cf;             /* (n,T-1,4) or (n,T-1,2H,H) */
+    const uint16_t *valid;        /* (n,T-1) treatment-seq only, else NULL */
+    const int64_t *row_offsets;   /* (n+1,) */
+} b200i_cf_source;
+
+/* K2  simulate_counterfactual_1_step -- cancer_simulation.py:378-563 (loop :435-552).
+ * draws: per-patient rows in the reference's order (:440-453): noise (N,T) [x0.01], recovery, chemo,
+ * radio (N,T).  total_rows_host (may be NULL) receives row_offsets[N] (synchronises). */
+B200I_API int b200i_sim_cf_one_step(int64_t n, int32_t T, const b200i_sim_consts *consts, const double *params,
+                          const double *noise, const double *recovery_rvs, const double *chemo_rvs,
+                          const double *radio_rvs, int64_t global_base, const b200i_cf_source *source,
+                          double *factual, uint8_t *codes, double *cf, int32_t *n_steps, int32_t *n_rows,
+                          int64_t *row_offsets, int64_t *total_rows_host, int32_t *levels_host, void *stream);
+
+/* K3  simulate_counterfactuals_treatment_seq, cf_seq_mode='sliding_treatment' --
+ * cancer_simulation.py:566-773 (loop :635-760).  noise is (N,T+H) [x0.01] (:640). */
+B200I_API int b200i_sim_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const b200i_sim_consts *consts,
+                               const double *params, const double *noise, const double *recovery_rvs,
+                               const double *chemo_rvs, const double *radio_rvs, int64_t global_base,
+                               const b200i_cf_source *source, double *factual, uint8_t *codes, double *cf,
+                               uint16_t *valid, int32_t *n_steps, int32_t *n_rows, int64_t *row_offsets,
+                               int64_t *total_rows_host, int32_t *levels_host, void *stream);
+
+/* dense reference rows [row_begin, row_end) of a compact cohort (keys of the dicts at :554-559 and
+ * :762-769).  Output arrays hold (row_end-row_begin) rows of width T (one-step) / T+H (sequences). */
+B200I_API int b200i_expand_cf_one_step(int64_t n, int32_t T, const double *factual, const uint8_t *codes,
+                             const double *cf, const int64_t *row_offsets, const double *patient_types,
+                             int64_t row_begin, int64_t row_end, double *cancer_volume,
+                             double *chemo_application, double *radio_application, double *sequence_lengths,
+                             double *patient_types_rows, void *stream);
+B200I_API int b200i_expand_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const double *factual,
+                                  const uint8_t *codes, const double *cf, const uint16_t *valid,
+                                  const int64_t *row_offsets, const double *patient_types, int64_t row_begin,
+                                  int64_t row_end, double *cancer_volume, double *chemo_application,
+                                  double *radio_application, double *sequence_lengths,
+                                  double *patient_types_rows, double *patient_ids, double *patient_current_t,
+                                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200I_H */

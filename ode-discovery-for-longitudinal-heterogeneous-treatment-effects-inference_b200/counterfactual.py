@@ -1,0 +1,141 @@
+"""Counterfactual cohorts: device-resident compact representation (K2 / K3) and the conversion to the
+reference's dense row layout for run.py-scale cohorts.
+
+Reference: simulate_counterfactual_1_step (cancer_simulation.py:378-563) and
+simulate_counterfactuals_treatment_seq (:566-773).  See include/b200i.h for the compact layout and the
+cross-row window semantics (:471, :671) that make the cohort a dependency wavefront.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from . import device as dev
+from ._native import CfSource
+
+
+class CompactCohort:
+    """Per-patient counterfactual cohort on the device."""
+
+    def __init__(self, kind, n, T, H, factual, codes, cf, valid, n_steps, n_rows, row_offsets, total_rows, levels,
+                 patient_types=None):
+        self.kind, self.n, self.T, self.H = kind, n, T, H
+        self.factual, self.codes, self.cf, self.valid = factual, codes, cf, valid
+        self.n_steps, self.n_rows, self.row_offsets = n_steps, n_rows, row_offsets
+        self.total_rows, self.levels = total_rows, levels
+        self.patient_types = patient_types
+
+    def as_source(self):
+        return CfSource(self.n, self.factual.data_ptr(), self.codes.data_ptr(), self.cf.data_ptr(),
+                        self.valid.data_ptr() if self.valid is not None else None, self.row_offsets.data_ptr())
+
+
+def sim_cf_one_step(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=None, global_base=0, source=None):
+    lib = _native.load()
+    n = params_dev.shape[1]
+    consts = consts or dev.sim_consts()
+    F = torch.empty((n, T), dtype=torch.float64, device='cuda')
+    codes = torch.empty((n, T), dtype=torch.uint8, device='cuda')
+    cf = torch.empty((n, T - 1, 4), dtype=torch.float64, device='cuda')
+    n_steps = torch.empty((n,), dtype=torch.int32, device='cuda')
+    n_rows = torch.empty((n,), dtype=torch.int32, device='cuda')
+    off = torch.empty((n + 1,), dtype=torch.int64, device='cuda')
+    total, levels = ctypes.c_int64(0), ctypes.c_int32(0)
+    src = source.as_source() if source is not None else None
+    rc = lib.b200i_sim_cf_one_step(n, T, ctypes.byref(consts), dev._ptr(params_dev), dev._ptr(noise),
+                                   dev._ptr(recovery), dev._ptr(chemo_rvs), dev._ptr(radio_rvs), int(global_base),
+                                   ctypes.byref(src) if src is not None else None,
+                                   dev._ptr(F), dev._ptr(codes), dev._ptr(cf), dev._ptr(n_steps), dev._ptr(n_rows),
+                                   dev._ptr(off), ctypes.byref(total), ctypes.byref(levels), dev._stream())
+    _native.check(rc, "b200i_sim_cf_one_step")
+    return CompactCohort('one_step', n, T, 0, F, codes, cf, None, n_steps, n_rows, off, total.value, levels.value)
+
+
+def sim_cf_treatment_seq(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, H, consts=None, global_base=0,
+                         source=None):
+    lib = _native.load()
+    n = params_dev.shape[1]
+    consts = consts or dev.sim_consts()
+    F = torch.empty((n, T), dtype=torch.float64, device='cuda')
+    codes = torch.empty((n, T), dtype=torch.uint8, device='cuda')
+    cf = torch.empty((n, T - 1, 2 * H, H), dtype=torch.float64, device='cuda')
+    valid = torch.empty((n, T - 1), dtype=torch.int16, device='cuda')   # bit mask, read as uint16
+    n_steps = torch.empty((n,), dtype=torch.int32, device='cuda')
+    n_rows = torch.empty((n,), dtype=torch.int32, device='cuda')
+    off = torch.empty((n + 1,), dtype=torch.int64, device='cuda')
+    total, levels = ctypes.c_int64(0), ctypes.c_int32(0)
+    src = source.as_source() if source is not None else None
+    rc = lib.b200i_sim_cf_treatment_seq(n, T, H, ctypes.byref(consts), dev._ptr(params_dev), dev._ptr(noise),
+                                        dev._ptr(recovery), dev._ptr(chemo_rvs), dev._ptr(radio_rvs),
+                                        int(global_base), ctypes.byref(src) if src is not None else None,
+                                        dev._ptr(F), dev._ptr(codes), dev._ptr(cf), dev._ptr(valid),
+                                        dev._ptr(n_steps), dev._ptr(n_rows), dev._ptr(off), ctypes.byref(total),
+                                        ctypes.byref(levels), dev._stream())
+    _native.check(rc, "b200i_sim_cf_treatment_seq")
+    return CompactCohort('treatment_seq', n, T, H, F, codes, cf, valid, n_steps, n_rows, off, total.value,
+                         levels.value)
+
+
+def expand(cohort, patient_types_dev, row_begin=0, row_end=None):
+    """Dense reference rows [row_begin,row_end) as a dict of device tensors (reference key names)."""
+    lib = _native.load()
+    row_end = cohort.total_rows if row_end is None else row_end
+    R = row_end - row_begin
+    W = cohort.T + cohort.H
+    f64 = dict(dtype=torch.float64, device='cuda')
+    out = {'cancer_volume': torch.empty((R, W), **f64), 'chemo_application': torch.empty((R, W), **f64),
+           'radio_application': torch.empty((R, W), **f64), 'sequence_lengths': torch.empty((R,), **f64),
+           'patient_types': torch.empty((R,), **f64)}
+    if cohort.kind == 'one_step':
+        rc = lib.b200i_expand_cf_one_step(cohort.n, cohort.T, dev._ptr(cohort.factual), dev._ptr(cohort.codes),
+                                          dev._ptr(cohort.cf), dev._ptr(cohort.row_offsets),
+                                          dev._ptr(patient_types_dev), row_begin, row_end,
+                                          dev._ptr(out['cancer_volume']), dev._ptr(out['chemo_application']),
+                                          dev._ptr(out['radio_application']), dev._ptr(out['sequence_lengths']),
+                                          dev._ptr(out['patient_types']), dev._stream())
+        _native.check(rc, "b200i_expand_cf_one_step")
+    else:
+        out['patient_ids_all_trajectories'] = torch.empty((R,), **f64)
+        out['patient_current_t'] = torch.empty((R,), **f64)
+        rc = lib.b200i_expand_cf_treatment_seq(cohort.n, cohort.T, cohort.H, dev._ptr(cohort.factual),
+                                               dev._ptr(cohort.codes), dev._ptr(cohort.cf), dev._ptr(cohort.valid),
+                                               dev._ptr(cohort.row_offsets), dev._ptr(patient_types_dev),
+                                               row_begin, row_end, dev._ptr(out['cancer_volume']),
+                                               dev._ptr(out['chemo_application']), dev._ptr(out['radio_application']),
+                                               dev._ptr(out['sequence_lengths']), dev._ptr(out['patient_types']),
+                                               dev._ptr(out['patient_ids_all_trajectories']),
+                                               dev._ptr(out['patient_current_t']), dev._stream())
+        _native.check(rc, "b200i_expand_cf_treatment_seq")
+    return out
+
+
+def _upload(simulation_params, draws):
+    params_dev = dev.to_device(dev.pack_params(simulation_params))
+    noise, rec, chemo, radio = (dev.to_device(a) for a in draws)
+    ptypes = dev.to_device(np.asarray(simulation_params['patient_types'], dtype=np.float64))
+    consts = dev.sim_consts(simulation_params['window_size'], simulation_params['lag'])
+    return params_dev, noise, rec, chemo, radio, ptypes, consts
+
+
+def one_step_dense(simulation_params, seq_length, draws):
+    """numpy-in / numpy-out body of simulate_counterfactual_1_step (dict keys of :554-559)."""
+    dev.require_cuda()
+    params_dev, noise, rec, chemo, radio, ptypes, consts = _upload(simulation_params, draws)
+    cohort = sim_cf_one_step(params_dev, noise, rec, chemo, radio, seq_length, consts)
+    dense = expand(cohort, ptypes)
+    torch.cuda.current_stream().synchronize()
+    return {k: dense[k].cpu().numpy() for k in
+            ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'patient_types')}
+
+
+def treatment_seq_dense(simulation_params, seq_length, projection_horizon, draws):
+    """numpy-in / numpy-out body of simulate_counterfactuals_treatment_seq (dict keys of :762-769)."""
+    dev.require_cuda()
+    params_dev, noise, rec, chemo, radio, ptypes, consts = _upload(simulation_params, draws)
+    cohort = sim_cf_treatment_seq(params_dev, noise, rec, chemo, radio, seq_length, projection_horizon, consts)
+    dense = expand(cohort, ptypes)
+    torch.cuda.current_stream().synchronize()
+    return {k: dense[k].cpu().numpy() for k in
+            ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'patient_types',
+             'patient_ids_all_trajectories', 'patient_current_t')}

@@ -1,0 +1,252 @@
+// fit_rollout.cu -- K5 (population STLSQ), K6 (closed-form ODE rollout), treatment codes and the
+// masked squared-error reductions of the RMSE metrics.
+#include "stats_reduce.cuh"
+#include "stlsq.cuh"
+
+namespace b200i {
+
+// ---- K5 ------------------------------------------------------------------------------------------
+__global__ void stlsq_population_kernel(const double *__restrict__ stats, double threshold, double alpha, int max_iter,
+                                        double *__restrict__ coefs, int *__restrict__ support)
+{
+    const int a = threadIdx.x;
+    if (a >= 4) return;
+    double G[4][4], b[4], c[4];
+    unpack_gram(stats + a * B200I_GRAM_PER_TREATMENT, G, b);
+    unsigned ind = 0;
+    if (stats[a * B200I_GRAM_PER_TREATMENT + 14] > 0.0)
+        ind = stlsq4(G, b, threshold, alpha, max_iter, 0xFu, c);
+    else
+        for (int j = 0; j < 4; ++j) c[j] = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        coefs[a * 4 + j] = c[j];
+        support[a * 4 + j] = (int)((ind >> j) & 1u);
+    }
+}
+
+// ---- K6 ------------------------------------------------------------------------------------------
+// thread per row; predictions staged in shared memory (odd pitch: conflict-free) and written back
+// as one contiguous, fully coalesced chunk per CTA.
+constexpr int RP = 128;
+
+__global__ void __launch_bounds__(RP)
+ode_rollout_kernel(int64_t rows, int W, double h, int substeps, const double *__restrict__ x0,
+                   const double *__restrict__ static_feature, const uint8_t *__restrict__ codes,
+                   const double *__restrict__ coefs, int per_row, double drop_below, double *__restrict__ pred)
+{
+    extern __shared__ double s_out[];  // [RP][W | 1]
+    __shared__ double s_coef[16];
+    const int pitch = W | 1;
+    const int tid = threadIdx.x;
+    if (!per_row && tid < 16) {
+        const double c = coefs[tid];
+        s_coef[tid] = (fabs(c) > drop_below) ? c : 0.0;
+    }
+    __syncthreads();
+    const int64_t ntiles = (rows + RP - 1) / RP;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * RP;
+        const int64_t r = first + tid;
+        if (r < rows) {
+            double c[4][4];
+            if (per_row) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const double v = coefs[r * 16 + j];
+                    c[j >> 2][j & 3] = (fabs(v) > drop_below) ? v : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) c[j >> 2][j & 3] = s_coef[j];
+            }
+            double v = x0[r];
+            const double u = static_feature[r];
+            const uint8_t *cr = codes + r * W;
+            for (int k = 0; k < W; ++k) {
+                const int a = cr[k] & 3;
+                // select the treatment's ODE (argmax of the one-hot, sindy.py:310 / :499)
+                const double c0 = a == 0 ? c[0][0] : a == 1 ? c[1][0] : a == 2 ? c[2][0] : c[3][0];
+                const double c1 = a == 0 ? c[0][1] : a == 1 ? c[1][1] : a == 2 ? c[2][1] : c[3][1];
+                const double c2 = a == 0 ? c[0][2] : a == 1 ? c[1][2] : a == 2 ? c[2][2] : c[3][2];
+                const double c3 = a == 0 ? c[0][3] : a == 1 ? c[1][3] : a == 2 ? c[2][3] : c[3][3];
+                const double c2u = __dmul_rn(c2, u);
+                for (int sidx = 0; sidx < substeps; ++sidx) {
+                    // y + (c0*1 + c1*y + c2*u + c3*(y*u)) * h   (pkpd/utils.py:68-71, sindy.py:491-496)
+                    double f = __dadd_rn(c0, __dmul_rn(c1, v));
+                    f = __dadd_rn(f, c2u);
+                    f = __dadd_rn(f, __dmul_rn(c3, __dmul_rn(v, u)));
+                    v = __dadd_rn(v, __dmul_rn(f, h));
+                }
+                s_out[tid * pitch + k] = v;
+            }
+        }
+        __syncthreads();
+        const int nrows = (int)((rows - first < RP) ? (rows - first) : RP);
+        double *dst = pred + first * W;
+        for (int e = tid; e < nrows * W; e += RP) dst[e] = s_out[(e / W) * pitch + (e % W)];
+        __syncthreads();
+    }
+}
+
+// ---- treatment codes -------------------------------------------------------------------------------
+__global__ void treatment_codes_kernel(int64_t rows, int W, int pitch, const double *__restrict__ chemo,
+                                       const double *__restrict__ radio, uint8_t *__restrict__ codes)
+{
+    const int64_t total = rows * W;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / W;
+        const int k = (int)(e - r * W);
+        const double c = chemo[r * pitch + k], d = radio[r * pitch + k];
+        codes[e] = (uint8_t)((c != 0.0 ? 1 : 0) + (d != 0.0 ? 2 : 0));
+    }
+}
+
+// ---- masked squared errors -------------------------------------------------------------------------
+// one warp per row, lanes over columns; per-lane column partials, block combine, ordered grid combine.
+constexpr int MSE_MAX_W = 128;
+struct MseWorkspaceHdr {
+    unsigned int ticket[32];
+};
+
+__global__ void __launch_bounds__(256)
+masked_se_kernel(int64_t rows, int W, const double *__restrict__ pred, const double *__restrict__ target,
+                 const int *__restrict__ active_len, double *__restrict__ sums, double *__restrict__ partials,
+                 unsigned int *__restrict__ ticket)
+{
+    __shared__ double s_acc[8][3 * MSE_MAX_W];
+    __shared__ unsigned int s_is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    constexpr int SL = MSE_MAX_W / 32;  // column slots per lane
+    double se[SL], cnt[SL], last[SL];
+#pragma unroll
+    for (int j = 0; j < SL; ++j) se[j] = cnt[j] = last[j] = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+        int L = active_len[r];
+        if (L > W) L = W;
+#pragma unroll
+        for (int j = 0; j < SL; ++j) {
+            const int k = lane + 32 * j;
+            if (k < L) {
+                const double d = pred[r * W + k] - target[r * W + k];
+                const double e = d * d;
+                se[j] += e;
+                cnt[j] += 1.0;
+                if (k == L - 1) last[j] += e;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SL; ++j) {
+        const int k = lane + 32 * j;
+        s_acc[warp][k] = se[j];
+        s_acc[warp][MSE_MAX_W + k] = cnt[j];
+        s_acc[warp][2 * MSE_MAX_W + k] = last[j];
+    }
+    __syncthreads();
+    const int nvals = 3 * MSE_MAX_W;
+    for (int j = tid; j < nvals; j += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < nwarps; ++w) v += s_acc[w][j];
+        partials[(size_t)blockIdx.x * nvals + j] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_is_last) {
+        __threadfence();
+        for (int j = tid; j < nvals; j += blockDim.x) {
+            double v = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * nvals + j]);
+            const int which = j / MSE_MAX_W, k = j % MSE_MAX_W;
+            if (k < W) sums[which * W + k] = v;
+            s_acc[0][j] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tl = 0.0, cl = 0.0;
+            for (int k = 0; k < W; ++k) tl += s_acc[0][2 * MSE_MAX_W + k];
+            // number of rows with a last active entry = rows with L >= 1 = active count of column 0
+            cl = s_acc[0][MSE_MAX_W + 0];
+            sums[3 * W] = tl;
+            sums[3 * W + 1] = cl;
+            *ticket = 0u;
+        }
+    }
+}
+
+}  // namespace b200i
+
+using namespace b200i;
+
+extern "C" int b200i_stlsq_population(const double *stats, double threshold, double alpha, int32_t max_iter,
+                                      double *coefs, int32_t *support, void *stream)
+{
+    B200I_REQUIRE(stats && coefs && support, B200I_E_ARG, "stlsq_population: NULL argument");
+    B200I_REQUIRE(threshold >= 0 && alpha >= 0 && max_iter >= 1, B200I_E_ARG,
+                  "stlsq_population: threshold/alpha must be >= 0 and max_iter >= 1");
+    stlsq_population_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, threshold, alpha, max_iter, coefs,
+                                                                             support);
+    return check_cuda(cudaGetLastError(), "stlsq_population launch");
+}
+
+extern "C" int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
+                                 const double *static_feature, const uint8_t *codes, const double *coefs,
+                                 int32_t coefs_per_row, double drop_below, double *pred, void *stream)
+{
+    B200I_REQUIRE(rows >= 0 && x0 && static_feature && codes && coefs && pred, B200I_E_ARG,
+                  "ode_rollout: NULL argument or negative rows");
+    B200I_REQUIRE(W >= 1 && W <= 2048 && substeps >= 1, B200I_E_UNSUPPORTED, "ode_rollout: W=%d substeps=%d", W, substeps);
+    if (rows == 0) return 0;
+    const size_t smem = (size_t)RP * (W | 1) * sizeof(double);
+    B200I_REQUIRE(smem <= 200 * 1024, B200I_E_UNSUPPORTED, "ode_rollout: W=%d too wide", W);
+    B200I_CUDA(cudaFuncSetAttribute(ode_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (rows + RP - 1) / RP;
+    const int64_t cap = (int64_t)num_sms() * 3;
+    if (grid > cap) grid = cap;
+    ode_rollout_kernel<<<(unsigned)grid, RP, smem, static_cast<cudaStream_t>(stream)>>>(
+        rows, W, dt / substeps, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, pred);
+    return check_cuda(cudaGetLastError(), "ode_rollout launch");
+}
+
+extern "C" int b200i_treatment_codes(int64_t rows, int32_t W, int32_t row_pitch, const double *chemo_application,
+                                     const double *radio_application, uint8_t *codes, void *stream)
+{
+    B200I_REQUIRE(rows >= 0 && W >= 1 && row_pitch >= W && chemo_application && radio_application && codes, B200I_E_ARG,
+                  "treatment_codes: bad argument");
+    if (rows == 0) return 0;
+    int64_t grid = (rows * W + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    treatment_codes_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows, W, row_pitch, chemo_application, radio_application, codes);
+    return check_cuda(cudaGetLastError(), "treatment_codes launch");
+}
+
+extern "C" int64_t b200i_masked_se_workspace_bytes(void)
+{
+    return (int64_t)(256 + (size_t)2048 * 3 * MSE_MAX_W * sizeof(double));
+}
+
+extern "C" int b200i_masked_se(int64_t rows, int32_t W, const double *pred, const double *target,
+                               const int32_t *active_len, double *sums, void *workspace, void *stream)
+{
+    B200I_REQUIRE(rows >= 0 && pred && target && active_len && sums && workspace, B200I_E_ARG,
+                  "masked_se: NULL argument or negative rows");
+    B200I_REQUIRE(W >= 1 && W <= MSE_MAX_W, B200I_E_UNSUPPORTED, "masked_se: W=%d outside [1,%d]", W, MSE_MAX_W);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200I_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (3 * W + 2), st));
+    B200I_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    if (rows == 0) return 0;
+    int64_t grid = (rows + 7) / 8;
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (cap > 2048) cap = 2048;
+    if (grid > cap) grid = cap;
+    unsigned int *ticket = static_cast<unsigned int *>(workspace);
+    double *partials = reinterpret_cast<double *>(static_cast<uint8_t *>(workspace) + 256);
+    masked_se_kernel<<<(unsigned)grid, 256, 0, st>>>(rows, W, pred, target, active_len, sums, partials, ticket);
+    return check_cuda(cudaGetLastError(), "masked_se launch");
+}

@@ -1,0 +1,99 @@
+// runtime.cu -- error reporting, device queries and tensor-map encoding shared by all kernels.
+#include <cuda.h>
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace b200i {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+int num_sms()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+    }
+    return fn;
+}
+
+int encode_tmap_2d_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, bool promote_256)
+{
+    encode_tiled_fn enc = get_encode();
+    B200I_REQUIRE(enc != nullptr, B200I_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    const uint32_t row_bytes = box_cols * 8u;
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+    else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    else if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    else {
+        set_error("tensor map: box of %u columns is not 32/64/128 bytes", box_cols);
+        return B200I_E_UNSUPPORTED;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 8u};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     promote_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u base=%p)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols, base);
+        return B200I_E_DRIVER;
+    }
+    return 0;
+}
+
+}  // namespace b200i
+
+extern "C" const char *b200i_last_error(void) { return b200i::g_err; }
+extern "C" int b200i_version(void) { return 100; }
+extern "C" int b200i_device_sms(int *sms_out)
+{
+    if (!sms_out) return B200I_E_ARG;
+    *sms_out = b200i::num_sms();
+    return 0;
+}

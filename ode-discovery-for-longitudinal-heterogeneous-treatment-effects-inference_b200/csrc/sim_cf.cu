@@ -1,0 +1,658 @@
+// sim_cf.cu -- K2 / K3: the two counterfactual generators of the cancer simulator in a compact,
+// per-patient representation (see include/b200i.h), plus the expanders to the reference's dense rows.
+//
+//   K2  simulate_counterfactual_1_step          cancer_simulation.py:435-552
+//   K3  simulate_counterfactuals_treatment_seq  cancer_simulation.py:635-760 ('sliding_treatment')
+//
+// One thread per patient.  Per step the factual recursion costs one log + one cbrt + one exp; K2 adds
+// four multiply-adds (all options share log(K/F[t])); K3 adds the 2H projected sequences, which share
+// their no-treatment prefix: 5 baseline + 15 chemo + 15 radio = 35 log-steps instead of 50 for H = 5.
+//
+// Cross-row window (cancer_simulation.py:471 / :671): patient i's treatment probabilities are
+// computed from output row i, a row emitted by an earlier patient j(i).  Its content is reconstructed
+// from j's compact arrays: a prefix of j's factual trajectory, then a short tail (the counterfactual
+// value(s) of that row), then zeros.  32 consecutive patients almost always share j, so the reads of
+// F_j broadcast within the warp.
+#include "sim_math.cuh"
+
+namespace b200i {
+
+struct SimC2 {
+    double death, density, sphere, chemo_amt, radio_amt, decay;
+    int window;
+};
+
+struct CfSrc {
+    int64_t n;  // patients whose row_offsets are known: off[0..n] valid
+    const double *F;
+    const uint8_t *codes;
+    const double *cf;
+    const uint16_t *valid;
+    const int64_t *off;
+};
+
+constexpr int MAXH = 8;
+
+// owner j of global row g: off[j] <= g < off[j+1]; -1 if g is beyond the known rows
+__device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, int64_t n, int64_t g)
+{
+    if (n <= 0 || g >= off[n]) return -1;
+    int64_t lo = 0, hi = n;  // off[lo] <= g < off[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// what output row `gi` looked like when patient gi read it
+struct WindowRow {
+    const double *F;   // owner's factual trajectory
+    int n_f;           // leading entries taken from F
+    int tail_len;      // then tail[0..tail_len), then zeros
+    double tail[MAXH];
+    bool self;         // patient 0: reads the row it writes itself at t = 0
+    __device__ __forceinline__ double at(int k) const
+    {
+        if (k < n_f) return F[k];
+        const int m = k - n_f;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < MAXH; ++q)
+            if (q == m && q < tail_len) v = tail[q];
+        return v;
+    }
+};
+
+struct CfFactual {
+    double F, Cprev;         // F[t], chemo dosage of t-1
+    double win[16];
+    int cnt;
+};
+
+// one factual step shared by K2 and K3: window -> probabilities -> assignment -> dosage.
+// Returns the factual option index 2*chemo + radio; C_t, D_t by reference.
+__device__ __forceinline__ int cf_assign(const SimC2 &c, const Patient &p, CfFactual &s, double w_t, double uchemo,
+                                         double uradio, int t, double &C_t, double &D_t)
+{
+    window_push(s.win, s.cnt, c.window + 1, calc_diameter(w_t, c.sphere));
+    const double metric = np_mean(s.win, s.cnt);
+    const double pr = sigmoid_prob(p.radio_beta, metric, p.radio_int);
+    const double pc = p.same_sigmoid ? pr : sigmoid_prob(p.chemo_beta, metric, p.chemo_int);
+    const bool ra = uradio < pr;   // NaN probability (negative volume in the window) -> no treatment
+    const bool ca = uchemo < pc;
+    D_t = ra ? c.radio_amt : 0.0;
+    const double prev = (t == 0) ? 0.0 : s.Cprev;
+    C_t = __dadd_rn(__dmul_rn(prev, c.decay), ca ? c.chemo_amt : 0.0);
+    return (ca ? 2 : 0) + (ra ? 1 : 0);
+}
+
+// V * (1 + rho*lg - beta_c*C - (alpha*d + beta*d^2) + noise) with lg supplied
+__device__ __forceinline__ double growth(const Patient &p, double V, double lg, double C, double D, double noise)
+{
+    double s = __dadd_rn(1.0, __dmul_rn(p.rho, lg));
+    s = __dsub_rn(s, __dmul_rn(p.beta_c, C));
+    s = __dsub_rn(s, __dadd_rn(__dmul_rn(p.alpha, D), __dmul_rn(p.beta, __dmul_rn(D, D))));
+    s = __dadd_rn(s, noise);
+    return __dmul_rn(V, s);
+}
+
+__device__ __forceinline__ double clip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const double *__restrict__ params,
+                   const double *__restrict__ noise, const double *__restrict__ rec,
+                   const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
+                   CfSrc src, int src_required, double *__restrict__ F_out, uint8_t *__restrict__ codes_out,
+                   double *__restrict__ cf_out, int *__restrict__ n_steps, int *__restrict__ n_rows,
+                   int *__restrict__ err)
+{
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const int64_t gi = base + i;
+    const Patient p = load_patient(params, n, i);
+    WindowRow w;
+    w.F = nullptr; w.n_f = 0; w.tail_len = 0; w.self = (gi == 0);
+#pragma unroll
+    for (int q = 0; q < MAXH; ++q) w.tail[q] = 0.0;
+    if (!w.self) {
+        const int64_t j = find_owner(src.off, src.n, gi);
+        if (j < 0) {
+            if (src_required) { atomicExch(err, 1); return; }
+            // row not written yet: the reference reads zeros
+        } else {
+            const int r = (int)(gi - src.off[j]);
+            const int ts = r >> 2, q = r & 3;
+            w.F = src.F + j * T;
+            if (q == 0) {
+                w.n_f = ts + 2;           // factual snapshot taken at step ts: F[:ts+2]
+            } else {
+                const int fo = src.codes[j * T + ts];
+                const int o = (q - 1) + ((q - 1) >= fo ? 1 : 0);   // q-th non-factual option
+                w.n_f = ts + 1;           // F[:ts+1] ++ [counterfactual volume]
+                w.tail_len = 1;
+                w.tail[0] = src.cf[(j * (T - 1) + ts) * 4 + o];
+            }
+        }
+    }
+    CfFactual s;
+    s.F = p.v0; s.Cprev = 0.0; s.cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s.win[q] = 0.0;
+    double *Fr = F_out + i * T;
+    uint8_t *cr = codes_out + i * T;
+    Fr[0] = p.v0;
+    double self_F1 = 0.0;
+    int steps = 0;
+    bool alive = true;
+    for (int t = 0; t < T - 1; ++t) {
+        if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; continue; }
+        double w_t;
+        if (w.self) {
+            // row 0 is this patient's own t=0 snapshot [F0, F1, 0, ...]; before it exists the row is 0
+            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, calc_diameter(p.v0, c.sphere)); }
+            w_t = (t == 1) ? self_F1 : 0.0;
+        } else {
+            w_t = w.at(t);
+        }
+        double C_t, D_t;
+        const int fo = cf_assign(c, p, s, w_t, chemo_rvs[i * T + t], radio_rvs[i * T + t], t, C_t, D_t);
+        const double lg = log(__ddiv_rn(p.K, s.F));
+        const double nz = noise[i * T + t + 1];
+        const double prevC = (t == 0) ? 0.0 : s.Cprev;
+        double Vf = 0.0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const double Co = __dadd_rn(__dmul_rn(prevC, c.decay), (o & 2) ? c.chemo_amt : 0.0);
+            const double Do = (o & 1) ? c.radio_amt : 0.0;
+            const double V = growth(p, s.F, lg, Co, Do, nz);
+            cf_out[(i * (T - 1) + t) * 4 + o] = V;
+            if (o == fo) Vf = V;
+        }
+        const double Fn = clip(Vf, 0.0, c.death);
+        Fr[t + 1] = Fn;
+        cr[t] = (uint8_t)fo;
+        if (t == 0) self_F1 = Fn;
+        steps = t + 1;
+        s.F = Fn;
+        s.Cprev = C_t;
+        if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
+    }
+    cr[T - 1] = 0;
+    n_steps[i] = steps;
+    n_rows[i] = 4 * steps;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+// one projected step, cancer_simulation.py:739-743 (note the two 1e-07 terms and no clipping)
+__device__ __forceinline__ double proj_step(const Patient &p, double V, double C, double D, double noise)
+{
+    const double lg = log(__dadd_rn(__ddiv_rn(p.K, __dadd_rn(V, 1e-07)), 1e-07));
+    return growth(p, V, lg, C, D, noise);
+}
+
+template <int H>
+__global__ void __launch_bounds__(128)
+cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const double *__restrict__ params,
+                        const double *__restrict__ noise, const double *__restrict__ rec,
+                        const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
+                        CfSrc src, int src_required, double *__restrict__ F_out, uint8_t *__restrict__ codes_out,
+                        double *__restrict__ cf_out, uint16_t *__restrict__ valid_out, int *__restrict__ n_steps,
+                        int *__restrict__ n_rows, int *__restrict__ err)
+{
+    static_assert(H >= 1 && H <= MAXH, "projection horizon");
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const int64_t gi = base + i;
+    const int NW = T + H;  // noise row width
+    const Patient p = load_patient(params, n, i);
+    WindowRow w;
+    w.F = nullptr; w.n_f = 0; w.tail_len = 0; w.self = (gi == 0);
+#pragma unroll
+    for (int q = 0; q < MAXH; ++q) w.tail[q] = 0.0;
+    if (!w.self) {
+        const int64_t j = find_owner(src.off, src.n, gi);
+        if (j < 0) {
+            if (src_required) { atomicExch(err, 1); return; }
+        } else {
+            int r = (int)(gi - src.off[j]);
+            int ts = 0, o = 0;
+            for (ts = 0; ts < T - 1; ++ts) {     // locate (step, option) of the patient's r-th emitted row
+                const unsigned m = src.valid[j * (T - 1) + ts];
+                const int cnt = __popc(m);
+                if (r < cnt) {
+                    unsigned mm = m;
+                    for (int q = 0; q < r; ++q) mm &= mm - 1;   // drop the r lowest set bits
+                    o = __ffs(mm) - 1;
+                    break;
+                }
+                r -= cnt;
+            }
+            w.F = src.F + j * T;
+            w.n_f = ts + 2;                      // F[:ts+2] ++ the H projected volumes
+            w.tail_len = H;
+#pragma unroll
+            for (int q = 0; q < H; ++q) w.tail[q] = src.cf[((j * (T - 1) + ts) * (2 * H) + o) * H + q];
+        }
+    }
+    CfFactual s;
+    s.F = p.v0; s.Cprev = 0.0; s.cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s.win[q] = 0.0;
+    double *Fr = F_out + i * T;
+    uint8_t *cr = codes_out + i * T;
+    Fr[0] = p.v0;
+    double self_F1 = 0.0, self_tail[H];
+#pragma unroll
+    for (int q = 0; q < H; ++q) self_tail[q] = 0.0;
+    int steps = 0, rows = 0;
+    bool alive = true;
+    for (int t = 0; t < T - 1; ++t) {
+        if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; valid_out[i * (T - 1) + t] = 0; continue; }
+        double w_t;
+        if (w.self) {
+            // row 0 = first row this patient emits at t = 0: [F0, F1, projections of that option, 0, ...]
+            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, calc_diameter(p.v0, c.sphere)); }
+            w_t = 0.0;
+            if (t == 1) w_t = self_F1;
+#pragma unroll
+            for (int q = 0; q < H; ++q)
+                if (t == q + 2) w_t = self_tail[q];
+        } else {
+            w_t = w.at(t);
+        }
+        double C_t, D_t;
+        const int fo = cf_assign(c, p, s, w_t, chemo_rvs[i * T + t], radio_rvs[i * T + t], t, C_t, D_t);
+        const double lg = log(__ddiv_rn(p.K, s.F));
+        const double Fn = clip(growth(p, s.F, lg, C_t, D_t, noise[i * NW + t + 1]), 0.0, c.death);
+        Fr[t + 1] = Fn;
+        cr[t] = (uint8_t)fo;
+
+        // ---- 2H sliding-treatment projections (:707-756); noise index of projected step k is t+2+k
+        const double *nz = noise + i * NW + t + 2;
+        double Vb[H + 1], Cb[H];
+        Vb[0] = Fn;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            Cb[k] = __dadd_rn(__dmul_rn(k == 0 ? C_t : Cb[k - 1], c.decay), 0.0);
+            Vb[k + 1] = proj_step(p, Vb[k], Cb[k], 0.0, nz[k]);
+        }
+        double *cfr = cf_out + (i * (T - 1) + t) * (2 * H) * H;
+        unsigned vmask = 0;
+        bool first_done = false;
+#pragma unroll
+        for (int sft = 0; sft < H; ++sft) {
+            // option sft: chemo at projected step sft
+            {
+                double V = Vb[sft];
+                double C = 0.0;
+                bool nan_any = false;
+                double outv[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    if (k < sft) {
+                        outv[k] = Vb[k + 1];
+                    } else {
+                        const double prev = (k == sft) ? (sft == 0 ? C_t : Cb[sft - 1]) : C;
+                        C = __dadd_rn(__dmul_rn(prev, c.decay), k == sft ? c.chemo_amt : 0.0);
+                        V = proj_step(p, V, C, 0.0, nz[k]);
+                        outv[k] = V;
+                    }
+                    nan_any |= isnan(outv[k]);
+                    cfr[sft * H + k] = outv[k];
+                }
+                if (!nan_any) {
+                    vmask |= 1u << sft;
+                    if (t == 0 && !first_done) {
+                        first_done = true;
+#pragma unroll
+                        for (int k = 0; k < H; ++k) self_tail[k] = outv[k];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int sft = 0; sft < H; ++sft) {
+            // option H + sft: radiotherapy at projected step sft
+            double V = Vb[sft];
+            bool nan_any = false;
+            double outv[H];
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                if (k < sft) {
+                    outv[k] = Vb[k + 1];
+                } else {
+                    V = proj_step(p, V, Cb[k], k == sft ? c.radio_amt : 0.0, nz[k]);
+                    outv[k] = V;
+                }
+                nan_any |= isnan(outv[k]);
+                cfr[(H + sft) * H + k] = outv[k];
+            }
+            if (!nan_any) {
+                vmask |= 1u << (H + sft);
+                if (t == 0 && !first_done) {
+                    first_done = true;
+#pragma unroll
+                    for (int k = 0; k < H; ++k) self_tail[k] = outv[k];
+                }
+            }
+        }
+        valid_out[i * (T - 1) + t] = (uint16_t)vmask;
+        rows += __popc(vmask);
+        if (t == 0) {
+            self_F1 = Fn;
+            if (w.self && vmask == 0) atomicExch(err, 2);   // row 0 would be written later: not modelled
+        }
+        steps = t + 1;
+        s.F = Fn;
+        s.Cprev = C_t;
+        if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
+    }
+    cr[T - 1] = 0;
+    n_steps[i] = steps;
+    n_rows[i] = rows;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of n_rows[lo..hi) continuing from off[lo]; single CTA
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_rows_kernel(const int *__restrict__ n_rows, int64_t *__restrict__ off,
+                                                         int64_t lo, int64_t hi)
+{
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = off[lo];
+    __syncthreads();
+    for (int64_t start = lo; start < hi; start += 1024) {
+        const int64_t i = start + tid;
+        int64_t v = (i < hi) ? (int64_t)n_rows[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t wv = s_warp[lane];
+            int64_t winc = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t up = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += up;
+            }
+            s_warp[lane] = winc - wv;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const int64_t carry = s_carry;
+        const int64_t total_incl = carry + s_warp[warp] + incl;
+        if (i < hi) off[i + 1] = total_incl;
+        __syncthreads();
+        if (tid == 1023) s_carry = total_incl;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expanders: one warp per reference row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+expand_one_step_kernel(int64_t n, int T, const double *__restrict__ F, const uint8_t *__restrict__ codes,
+                       const double *__restrict__ cf, const int64_t *__restrict__ off,
+                       const double *__restrict__ ptypes, int64_t row_begin, int64_t row_end,
+                       double *__restrict__ vol, double *__restrict__ chemo, double *__restrict__ radio,
+                       double *__restrict__ seq_len, double *__restrict__ pt_rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = row_begin + wid; g < row_end; g += nw) {
+        const int64_t j = find_owner(off, n, g);
+        if (j < 0) continue;
+        const int r = (int)(g - off[j]);
+        const int t = r >> 2, q = r & 3;
+        const int fo = codes[j * T + t];
+        const int o = (q == 0) ? fo : (q - 1) + ((q - 1) >= fo ? 1 : 0);
+        const double tail = (q == 0) ? F[j * T + t + 1] : cf[(j * (T - 1) + t) * 4 + o];
+        const int64_t orow = (g - row_begin) * T;
+        for (int k = lane; k < T; k += 32) {
+            double v = 0.0, ca = 0.0, ra = 0.0;
+            if (k <= t) v = F[j * T + k];
+            else if (k == t + 1) v = tail;
+            if (k < t) { const int cd = codes[j * T + k]; ca = (cd >> 1) & 1; ra = cd & 1; }
+            else if (k == t) { ca = (o >> 1) & 1; ra = o & 1; }
+            vol[orow + k] = v; chemo[orow + k] = ca; radio[orow + k] = ra;
+        }
+        if (lane == 0) { seq_len[g - row_begin] = (double)(t + 1); pt_rows[g - row_begin] = ptypes[j]; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+expand_treatment_seq_kernel(int64_t n, int T, int H, const double *__restrict__ F, const uint8_t *__restrict__ codes,
+                            const double *__restrict__ cf, const uint16_t *__restrict__ valid,
+                            const int64_t *__restrict__ off, const double *__restrict__ ptypes, int64_t row_begin,
+                            int64_t row_end, double *__restrict__ vol, double *__restrict__ chemo,
+                            double *__restrict__ radio, double *__restrict__ seq_len, double *__restrict__ pt_rows,
+                            double *__restrict__ pids, double *__restrict__ pcur)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int Wd = T + H;
+    for (int64_t g = row_begin + wid; g < row_end; g += nw) {
+        const int64_t j = find_owner(off, n, g);
+        if (j < 0) continue;
+        int r = (int)(g - off[j]);
+        int t = 0, o = 0;
+        for (t = 0; t < T - 1; ++t) {
+            const unsigned m = valid[j * (T - 1) + t];
+            const int cnt = __popc(m);
+            if (r < cnt) {
+                unsigned mm = m;
+                for (int q = 0; q < r; ++q) mm &= mm - 1;
+                o = __ffs(mm) - 1;
+                break;
+            }
+            r -= cnt;
+        }
+        const double *cfo = cf + ((j * (T - 1) + t) * (2 * H) + o) * H;
+        const int64_t orow = (g - row_begin) * Wd;
+        for (int k = lane; k < Wd; k += 32) {
+            double v = 0.0, ca = 0.0, ra = 0.0;
+            if (k <= t + 1) v = F[j * T + k];
+            else if (k <= t + 1 + H) v = cfo[k - t - 2];
+            if (k <= t) { const int cd = codes[j * T + k]; ca = (cd >> 1) & 1; ra = cd & 1; }
+            else if (k <= t + H) {
+                const int m = k - t - 1;
+                ca = (o < H && m == o) ? 1.0 : 0.0;
+                ra = (o >= H && m == o - H) ? 1.0 : 0.0;
+            }
+            vol[orow + k] = v; chemo[orow + k] = ca; radio[orow + k] = ra;
+        }
+        if (lane == 0) {
+            seq_len[g - row_begin] = (double)(t + H + 1);
+            pt_rows[g - row_begin] = ptypes[j];
+            pids[g - row_begin] = (double)j;
+            pcur[g - row_begin] = (double)t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: dependency-level driver
+// ------------------------------------------------------------------------------------------------
+template <typename Launch>
+static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, int *n_rows, int64_t *off,
+                      int64_t *total_rows_host, int *levels_host, cudaStream_t st, Launch launch)
+{
+    int *d_err = nullptr;
+    B200I_CUDA(cudaMallocAsync(&d_err, sizeof(int), st));
+    B200I_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    B200I_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t), st));
+    int levels = 0;
+    int64_t total = 0;
+    int rc = 0;
+    if (source != nullptr) {
+        rc = launch(0, n, true, d_err);
+        if (!rc) {
+            scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, 0, n);
+            rc = check_cuda(cudaGetLastError(), "scan_rows launch");
+        }
+        levels = 1;
+    } else {
+        B200I_REQUIRE(base == 0, B200I_E_ARG, "sim_cf: a shard (global_base > 0) needs a source cohort");
+        int64_t lo = 0, hi = (n > 0) ? 1 : 0;
+        while (lo < n && !rc) {
+            rc = launch(lo, hi, false, d_err);
+            if (rc) break;
+            scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, lo, hi);
+            rc = check_cuda(cudaGetLastError(), "scan_rows launch");
+            if (rc) break;
+            int64_t off_hi = 0;
+            rc = check_cuda(cudaMemcpyAsync(&off_hi, off + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, st), "copy off");
+            if (rc) break;
+            rc = check_cuda(cudaStreamSynchronize(st), "level sync");
+            if (rc) break;
+            ++levels;
+            lo = hi;
+            int64_t next = off_hi;          // patients whose row already exists
+            if (next <= lo) next = lo + 1;   // (row not written yet: the reference reads zeros)
+            hi = next < n ? next : n;
+        }
+    }
+    int h_err = 0;
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st), "copy err");
+    if (!rc && (total_rows_host || true))
+        rc = check_cuda(cudaMemcpyAsync(&total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st), "copy total");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "final sync");
+    cudaFreeAsync(d_err, st);
+    if (rc) return rc;
+    B200I_REQUIRE(h_err != 1, B200I_E_ARG, "sim_cf: source cohort does not cover the rows this shard reads");
+    B200I_REQUIRE(h_err != 2, B200I_E_UNSUPPORTED, "sim_cf: patient 0 emitted no row at t=0 (not modelled)");
+    if (total_rows_host) *total_rows_host = total;
+    if (levels_host) *levels_host = levels;
+    return 0;
+}
+
+static int check_consts(const b200i_sim_consts *k, int T, const char *who)
+{
+    B200I_REQUIRE(k != nullptr, B200I_E_ARG, "%s: consts is NULL", who);
+    B200I_REQUIRE(T >= 3 && T <= 4096, B200I_E_UNSUPPORTED, "%s: seq_length %d outside [3,4096]", who, T);
+    B200I_REQUIRE(k->lag == 0, B200I_E_UNSUPPORTED, "%s: lag=%d (only lag=0 is implemented)", who, k->lag);
+    B200I_REQUIRE(k->window_size >= 1 && k->window_size <= 15, B200I_E_UNSUPPORTED, "%s: window_size=%d outside [1,15]",
+                  who, k->window_size);
+    return 0;
+}
+
+}  // namespace b200i
+
+using namespace b200i;
+
+extern "C" int b200i_sim_cf_one_step(int64_t n, int32_t T, const b200i_sim_consts *k, const double *params,
+                                     const double *noise, const double *recovery_rvs, const double *chemo_rvs,
+                                     const double *radio_rvs, int64_t global_base, const b200i_cf_source *source,
+                                     double *factual, uint8_t *codes, double *cf, int32_t *n_steps, int32_t *n_rows,
+                                     int64_t *row_offsets, int64_t *total_rows_host, int32_t *levels_host, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && params && noise && recovery_rvs && chemo_rvs && radio_rvs && factual && codes && cf &&
+                      n_steps && n_rows && row_offsets,
+                  B200I_E_ARG, "sim_cf_one_step: NULL argument or negative n");
+    int rc = check_consts(k, T, "sim_cf_one_step");
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SimC2 c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay,
+            k->window_size};
+    auto launch = [&](int64_t lo, int64_t hi, bool required, int *d_err) -> int {
+        if (hi <= lo) return 0;
+        CfSrc src;
+        if (source) src = CfSrc{source->n, source->factual, source->codes, source->cf, nullptr, source->row_offsets};
+        else src = CfSrc{lo, factual, codes, cf, nullptr, row_offsets};
+        const unsigned grid = (unsigned)((hi - lo + 127) / 128);
+        cf_one_step_kernel<<<grid, 128, 0, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs, radio_rvs,
+                                                 global_base, src, required ? 1 : 0, factual, codes, cf, n_steps,
+                                                 n_rows, d_err);
+        return check_cuda(cudaGetLastError(), "cf_one_step launch");
+    };
+    return run_levels(n, global_base, source, n_rows, row_offsets, total_rows_host, levels_host, st, launch);
+}
+
+extern "C" int b200i_sim_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const b200i_sim_consts *k,
+                                          const double *params, const double *noise, const double *recovery_rvs,
+                                          const double *chemo_rvs, const double *radio_rvs, int64_t global_base,
+                                          const b200i_cf_source *source, double *factual, uint8_t *codes, double *cf,
+                                          uint16_t *valid, int32_t *n_steps, int32_t *n_rows, int64_t *row_offsets,
+                                          int64_t *total_rows_host, int32_t *levels_host, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && params && noise && recovery_rvs && chemo_rvs && radio_rvs && factual && codes && cf &&
+                      valid && n_steps && n_rows && row_offsets,
+                  B200I_E_ARG, "sim_cf_treatment_seq: NULL argument or negative n");
+    int rc = check_consts(k, T, "sim_cf_treatment_seq");
+    if (rc) return rc;
+    B200I_REQUIRE(H == 5, B200I_E_UNSUPPORTED,
+                  "sim_cf_treatment_seq: projection_horizon=%d (the kernel is instantiated for 5, the only value "
+                  "the reference configures: config/dataset/cancer_sim.yaml:16)", H);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SimC2 c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay,
+            k->window_size};
+    auto launch = [&](int64_t lo, int64_t hi, bool required, int *d_err) -> int {
+        if (hi <= lo) return 0;
+        CfSrc src;
+        if (source) src = CfSrc{source->n, source->factual, source->codes, source->cf, source->valid, source->row_offsets};
+        else src = CfSrc{lo, factual, codes, cf, valid, row_offsets};
+        const unsigned grid = (unsigned)((hi - lo + 127) / 128);
+        cf_treatment_seq_kernel<5><<<grid, 128, 0, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs,
+                                                         radio_rvs, global_base, src, required ? 1 : 0, factual, codes,
+                                                         cf, valid, n_steps, n_rows, d_err);
+        return check_cuda(cudaGetLastError(), "cf_treatment_seq launch");
+    };
+    return run_levels(n, global_base, source, n_rows, row_offsets, total_rows_host, levels_host, st, launch);
+}
+
+extern "C" int b200i_expand_cf_one_step(int64_t n, int32_t T, const double *factual, const uint8_t *codes,
+                                        const double *cf, const int64_t *row_offsets, const double *patient_types,
+                                        int64_t row_begin, int64_t row_end, double *cancer_volume,
+                                        double *chemo_application, double *radio_application,
+                                        double *sequence_lengths, double *patient_types_rows, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && factual && codes && cf && row_offsets && patient_types && cancer_volume &&
+                      chemo_application && radio_application && sequence_lengths && patient_types_rows &&
+                      row_end >= row_begin && row_begin >= 0,
+                  B200I_E_ARG, "expand_cf_one_step: bad argument");
+    if (row_end == row_begin) return 0;
+    int64_t grid = (row_end - row_begin + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    expand_one_step_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, T, factual, codes, cf, row_offsets, patient_types, row_begin, row_end, cancer_volume, chemo_application,
+        radio_application, sequence_lengths, patient_types_rows);
+    return check_cuda(cudaGetLastError(), "expand_one_step launch");
+}
+
+extern "C" int b200i_expand_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const double *factual,
+                                             const uint8_t *codes, const double *cf, const uint16_t *valid,
+                                             const int64_t *row_offsets, const double *patient_types,
+                                             int64_t row_begin, int64_t row_end, double *cancer_volume,
+                                             double *chemo_application, double *radio_application,
+                                             double *sequence_lengths, double *patient_types_rows,
+                                             double *patient_ids, double *patient_current_t, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && factual && codes && cf && valid && row_offsets && patient_types && cancer_volume &&
+                      chemo_application && radio_application && sequence_lengths && patient_types_rows &&
+                      patient_ids && patient_current_t && row_end >= row_begin && row_begin >= 0,
+                  B200I_E_ARG, "expand_cf_treatment_seq: bad argument");
+    if (row_end == row_begin) return 0;
+    int64_t grid = (row_end - row_begin + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    expand_treatment_seq_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, T, H, factual, codes, cf, valid, row_offsets, patient_types, row_begin, row_end, cancer_volume,
+        chemo_application, radio_application, sequence_lengths, patient_types_rows, patient_ids, patient_current_t);
+    return check_cuda(cudaGetLastError(), "expand_treatment_seq launch");
+}

@@ -1,0 +1,455 @@
+// sim_factual.cu -- K1: simulate_factual (cancer_simulation.py:218-375, loop :282-354) on sm_100a.
+//
+// One thread per patient walks the T columns sequentially.  Two kernels:
+//   * sim_factual_tma<P,TC,SIN,GRAM>: persistent CTAs of P threads; the four (N,T) random-draw arrays
+//     and the nine (N,T) outputs move as TMA boxes {TC columns, P patients} through swizzled shared
+//     memory tiles (conflict-free 16-byte LDS/STS per thread), loads tracked by mbarriers with SIN
+//     stages, stores by bulk async-groups.  HBM traffic = algorithmic bytes (each element touched once).
+//   * sim_factual_generic: the same per-column arithmetic with direct global accesses; covers odd T,
+//     unaligned buffers and the `assigned_actions` fixed policy, and cross-checks the TMA kernel.
+// With GRAM the population statistics of theta_gram (K4) are accumulated while simulating.
+#include "sim_math.cuh"
+#include "stats_reduce.cuh"
+#include "tma.cuh"
+#include <type_traits>
+
+namespace b200i {
+
+struct SimC {
+    double death, density, sphere, chemo_amt, radio_amt, decay, fd_dt;
+    int window;
+};
+
+struct FactualState {
+    double V, C, D;     // column t-1
+    double win[15];     // diameters of the last `window` volumes, oldest first
+    int cnt;
+    int code_prev;      // treatment code (chemo + 2*radio) of column t-1
+    int t_end;          // last simulated column
+    bool exists, alive;
+};
+
+struct Column {
+    double V, C, D, ca, ra, pc, pr, death, recov;
+};
+
+struct Moments {
+    double sv, svv, sc, scc, sd, sdd;
+    __device__ __forceinline__ void clear() { sv = svv = sc = scc = sd = sdd = 0.0; }
+    __device__ __forceinline__ void add(double v, double c, double d)
+    {
+        sv += v; svv += v * v; sc += c; scc += c * c; sd += d; sdd += d * d;
+    }
+};
+
+__device__ __forceinline__ void state_init(FactualState &s, bool exists)
+{
+    s.V = s.C = s.D = 0.0;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) s.win[j] = 0.0;
+    s.cnt = 0; s.code_prev = 0; s.t_end = 0;
+    s.exists = exists; s.alive = exists;
+}
+
+// produces column t of all nine outputs for one patient and advances the state
+// FULL: caller guarantees t > 0 and a completely filled 15-slot window (steady state, t >= 16)
+template <bool GRAM, bool FULL = false>
+__device__ __forceinline__ void factual_column(int t, int T, const SimC &c, const Patient &p, FactualState &s,
+                                               double noise, double urec, double uchemo, double uradio,
+                                               const double *assigned, Column &o, PatientGram &pg, Moments &mom)
+{
+    o.V = o.C = o.D = o.ca = o.ra = o.pc = o.pr = o.death = o.recov = 0.0;
+    if (!FULL && t == 0) {
+        if (s.exists) {
+            o.V = p.v0;
+            s.V = p.v0;
+            if (GRAM) mom.add(p.v0, 0.0, 0.0);
+        }
+        return;
+    }
+    if (!s.alive || t >= T - 1) return;
+
+    double Vn = gompertz_step(p, s.V, s.C, s.D, noise);
+    double metric;
+    if (FULL) {
+#pragma unroll
+        for (int j = 0; j < 14; ++j) s.win[j] = s.win[j + 1];
+        s.win[14] = calc_diameter(s.V, c.sphere);
+        metric = np_mean_full(s.win);
+    } else {
+        window_push(s.win, s.cnt, c.window, calc_diameter(s.V, c.sphere));
+        metric = np_mean(s.win, s.cnt);
+    }
+    double pr, pc;
+    if (assigned != nullptr) {
+        pc = assigned[0];
+        pr = assigned[1];
+    } else {
+        pr = sigmoid_prob(p.radio_beta, metric, p.radio_int);
+        pc = p.same_sigmoid ? pr : sigmoid_prob(p.chemo_beta, metric, p.chemo_int);
+    }
+    const bool ra = uradio < pr;
+    const bool ca = uchemo < pc;
+    const double D = ra ? c.radio_amt : 0.0;
+    const double C = __dadd_rn(__dmul_rn(s.C, c.decay), ca ? c.chemo_amt : 0.0);
+    const bool death = Vn > c.death;
+    if (death) Vn = c.death;
+    const bool recov = !death && recovery_test<true>(urec, Vn, c.density);
+    if (recov) Vn = 0.0;
+    const int code = (ca ? 1 : 0) + (ra ? 2 : 0);
+    if (GRAM) {
+        // sample k = t-1 of the SINDy regression (pkpd/utils.py:433-462 + FiniteDifference order 1)
+        const double xdot = __ddiv_rn(__dsub_rn(Vn, s.V), c.fd_dt);
+        pg.add(s.code_prev, s.V, xdot);
+        if (code != s.code_prev) pg.add(s.code_prev, Vn, xdot);  // snippet end-point: backward difference
+        mom.add(Vn, C, D);
+    }
+    o.V = Vn; o.C = C; o.D = D;
+    o.ca = ca ? 1.0 : 0.0; o.ra = ra ? 1.0 : 0.0;
+    o.pc = pc; o.pr = pr;
+    o.death = death ? 1.0 : 0.0; o.recov = recov ? 1.0 : 0.0;
+    s.V = Vn; s.C = C; s.D = D;
+    s.code_prev = code;
+    s.t_end = t;
+    if (death || recov) s.alive = false;
+}
+
+// last regression sample of a patient: x[L] is the never-simulated zero at column seq_len
+template <bool GRAM>
+__device__ __forceinline__ void factual_finish(const SimC &c, const FactualState &s, PatientGram &pg)
+{
+    if (GRAM && s.exists) {
+        const double xdot = __ddiv_rn(__dsub_rn(0.0, s.V), c.fd_dt);
+        pg.add(s.code_prev, s.V, xdot);
+        pg.add(s.code_prev, 0.0, xdot);
+    }
+}
+
+// folds one patient's statistics into the warp accumulators (all 32 lanes participate)
+__device__ __forceinline__ void fold_patient_stats(double *warp_acc, int lane, const PatientGram &pg,
+                                                   const Moments &mom, double u, bool exists, int seq_len)
+{
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double g[B200I_GRAM_PER_TREATMENT];
+        expand_gram(pg.s[a], u, g);
+#pragma unroll
+        for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j)
+            warp_acc_add(warp_acc, a * B200I_GRAM_PER_TREATMENT + j, exists ? g[j] : 0.0, lane);
+    }
+    const int m0 = 4 * B200I_GRAM_PER_TREATMENT;
+    warp_acc_add(warp_acc, m0 + 0, exists ? mom.sv : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 1, exists ? mom.svv : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 2, exists ? mom.sc : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 3, exists ? mom.scc : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 4, exists ? mom.sd : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 5, exists ? mom.sdd : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 6, exists ? (double)seq_len : 0.0, lane);
+    warp_acc_add(warp_acc, m0 + 7, exists ? 1.0 : 0.0, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: direct global accesses
+// ------------------------------------------------------------------------------------------------
+struct FactualPtrs {
+    const double *noise, *rec, *chemo_rvs, *radio_rvs, *assigned;
+    double *out[9];  // V C D ca ra pc pr death recov
+    double *seq_len;
+};
+
+template <bool GRAM>
+__global__ void __launch_bounds__(128) sim_factual_generic(int64_t n, int T, SimC c, const double *__restrict__ params,
+                                                           FactualPtrs io, const double *__restrict__ static_feature,
+                                                           StatsWorkspace *ws)
+{
+    __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (GRAM) {
+        for (int j = threadIdx.x; j < STATS_MAX_WARPS * STATS_PAD; j += blockDim.x) (&block_acc[0][0])[j] = 0.0;
+        __syncthreads();
+    }
+    const int64_t span = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = ((n + blockDim.x - 1) / blockDim.x) * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += span) {
+        const bool exists = i < n;
+        Patient p = load_patient(params, n, exists ? i : 0);
+        FactualState s;
+        state_init(s, exists);
+        PatientGram pg; Moments mom;
+        pg.clear(); mom.clear();
+        if (exists) {
+            const int64_t row = i * T;
+            for (int t = 0; t < T; ++t) {
+                Column o;
+                const double *aa = io.assigned ? io.assigned + (row + t) * 2 : nullptr;
+                factual_column<GRAM>(t, T, c, p, s, io.noise[row + t], io.rec[row + t], io.chemo_rvs[row + t],
+                                     io.radio_rvs[row + t], aa, o, pg, mom);
+                io.out[0][row + t] = o.V; io.out[1][row + t] = o.C; io.out[2][row + t] = o.D;
+                io.out[3][row + t] = o.ca; io.out[4][row + t] = o.ra; io.out[5][row + t] = o.pc;
+                io.out[6][row + t] = o.pr; io.out[7][row + t] = o.death; io.out[8][row + t] = o.recov;
+            }
+            factual_finish<GRAM>(c, s, pg);
+            io.seq_len[i] = (double)(s.t_end + 1);
+        }
+        if (GRAM) {
+            const double u = exists ? static_feature[i] : 0.0;
+            fold_patient_stats(block_acc[warp], lane, pg, mom, u, exists, s.t_end + 1);
+        }
+    }
+    if (GRAM) stats_block_finish(block_acc, blockDim.x >> 5, ws, &s_is_last);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-tiled kernel
+// ------------------------------------------------------------------------------------------------
+struct TmapPack {
+    CUtensorMap in[4];   // noise, recovery, chemo_rvs, radio_rvs
+    CUtensorMap out[9];  // V C D ca ra pc pr death recov
+};
+
+template <int P, int TC, int SIN>
+struct TileCfg {
+    static constexpr int ROW_BYTES = TC * 8;
+    static constexpr int TILE_BYTES = P * ROW_BYTES;
+    static constexpr int IN_BYTES = SIN * 4 * TILE_BYTES;
+    static constexpr int OUT_BYTES = 9 * TILE_BYTES;
+    static constexpr int SMEM_BYTES = IN_BYTES + OUT_BYTES + 1024;  // + alignment slack
+    static_assert(TILE_BYTES % 1024 == 0, "tiles must keep 1024-byte alignment");
+    static_assert(ROW_BYTES == 32 || ROW_BYTES == 64 || ROW_BYTES == 128, "row = swizzle span");
+};
+
+template <int P, int TC, int SIN, int MINB, bool GRAM>
+__global__ void __launch_bounds__(P, MINB)
+sim_factual_tma(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, const double *__restrict__ params,
+                double *__restrict__ seq_len_out, const double *__restrict__ static_feature, StatsWorkspace *ws)
+{
+    using Cfg = TileCfg<P, TC, SIN>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[SIN];
+    __shared__ double block_acc[GRAM ? STATS_MAX_WARPS : 1][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *in_tiles = smem;                    // [SIN][4][TILE]
+    uint8_t *out_tiles = smem + Cfg::IN_BYTES;   // [9][TILE]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = (T + TC - 1) / TC;
+    const int64_t ntiles = (n + P - 1) / P;
+    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SIN; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_prefetch_desc(&maps.in[a]);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) tma_prefetch_desc(&maps.out[a]);
+    }
+    if (GRAM) {
+        for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += P) (&block_acc[0][0])[j] = 0.0;
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int64_t g) {
+        const int stage = (int)(g % SIN);
+        const int64_t tile = blockIdx.x + (g / nchunks) * gridDim.x;
+        const int ch = (int)(g % nchunks);
+        mbar_arrive_expect_tx(&bars[stage], 4u * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            tma_load_2d(in_tiles + (stage * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TC, (int)(tile * P), &bars[stage]);
+    };
+
+    if (tid == 0) {
+        for (int64_t g = 0; g < SIN && g < total; ++g) issue_load(g);
+    }
+
+    Patient p;
+    FactualState s;
+    PatientGram pg;
+    Moments mom;
+    int64_t patient = 0;
+
+    for (int64_t g = 0; g < total; ++g) {
+        const int stage = (int)(g % SIN);
+        const uint32_t parity = (uint32_t)((g / SIN) & 1);
+        const int64_t tile = blockIdx.x + (g / nchunks) * gridDim.x;
+        const int ch = (int)(g % nchunks);
+        if (ch == 0) {
+            patient = tile * P + tid;
+            const bool exists = patient < n;
+            p = load_patient(params, n, exists ? patient : 0);
+            state_init(s, exists);
+            pg.clear(); mom.clear();
+        }
+        if (tid == 0) tma_store_wait_read();  // previous chunk's stores no longer read the out tiles
+        __syncthreads();
+        mbar_wait(&bars[stage], parity);
+
+        const uint8_t *in_base = in_tiles + stage * 4 * Cfg::TILE_BYTES;
+        auto run_chunk = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll 1
+            for (int q = 0; q < TC / 2; ++q) {
+                const uint32_t off = swz_off<Cfg::ROW_BYTES>(tid, q);
+                const double2 nz = *reinterpret_cast<const double2 *>(in_base + 0 * Cfg::TILE_BYTES + off);
+                const double2 ur = *reinterpret_cast<const double2 *>(in_base + 1 * Cfg::TILE_BYTES + off);
+                const double2 uc = *reinterpret_cast<const double2 *>(in_base + 2 * Cfg::TILE_BYTES + off);
+                const double2 ud = *reinterpret_cast<const double2 *>(in_base + 3 * Cfg::TILE_BYTES + off);
+                Column o0, o1;
+                const int t0 = ch * TC + 2 * q;
+                factual_column<GRAM, FULL>(t0, T, c, p, s, nz.x, ur.x, uc.x, ud.x, nullptr, o0, pg, mom);
+                factual_column<GRAM, FULL>(t0 + 1, T, c, p, s, nz.y, ur.y, uc.y, ud.y, nullptr, o1, pg, mom);
+                *reinterpret_cast<double2 *>(out_tiles + 0 * Cfg::TILE_BYTES + off) = make_double2(o0.V, o1.V);
+                *reinterpret_cast<double2 *>(out_tiles + 1 * Cfg::TILE_BYTES + off) = make_double2(o0.C, o1.C);
+                *reinterpret_cast<double2 *>(out_tiles + 2 * Cfg::TILE_BYTES + off) = make_double2(o0.D, o1.D);
+                *reinterpret_cast<double2 *>(out_tiles + 3 * Cfg::TILE_BYTES + off) = make_double2(o0.ca, o1.ca);
+                *reinterpret_cast<double2 *>(out_tiles + 4 * Cfg::TILE_BYTES + off) = make_double2(o0.ra, o1.ra);
+                *reinterpret_cast<double2 *>(out_tiles + 5 * Cfg::TILE_BYTES + off) = make_double2(o0.pc, o1.pc);
+                *reinterpret_cast<double2 *>(out_tiles + 6 * Cfg::TILE_BYTES + off) = make_double2(o0.pr, o1.pr);
+                *reinterpret_cast<double2 *>(out_tiles + 7 * Cfg::TILE_BYTES + off) = make_double2(o0.death, o1.death);
+                *reinterpret_cast<double2 *>(out_tiles + 8 * Cfg::TILE_BYTES + off) = make_double2(o0.recov, o1.recov);
+            }
+        };
+        // the 15-slot diameter window is full from column 16 on: whole chunks take the steady-state path
+        if (ch * TC >= 16 && c.window == 15)
+            run_chunk(std::true_type{});
+        else
+            run_chunk(std::false_type{});
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 0; a < 9; ++a)
+                tma_store_2d(&maps.out[a], ch * TC, (int)(tile * P), out_tiles + a * Cfg::TILE_BYTES);
+            tma_store_commit();
+            if (g + SIN < total) issue_load(g + SIN);
+        }
+        if (ch == nchunks - 1) {
+            factual_finish<GRAM>(c, s, pg);
+            if (s.exists) seq_len_out[patient] = (double)(s.t_end + 1);
+            if (GRAM) {
+                const double u = s.exists ? __ldg(static_feature + patient) : 0.0;
+                fold_patient_stats(block_acc[warp], lane, pg, mom, u, s.exists, s.t_end + 1);
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
+    if (GRAM) stats_block_finish(block_acc, P >> 5, ws, &s_is_last);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int P, int TC, int SIN, int MINB, bool GRAM>
+static int launch_tma(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
+                      double *const out[9], double *seq_len, const double *static_feature, StatsWorkspace *ws,
+                      cudaStream_t st)
+{
+    using Cfg = TileCfg<P, TC, SIN>;
+    TmapPack pack;
+    for (int a = 0; a < 4; ++a) {
+        int rc = encode_tmap_2d_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, P, TC, true);
+        if (rc) return rc;
+    }
+    for (int a = 0; a < 9; ++a) {
+        int rc = encode_tmap_2d_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, P, TC, false);
+        if (rc) return rc;
+    }
+    auto kern = sim_factual_tma<P, TC, SIN, MINB, GRAM>;
+    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int per_sm = 0;
+    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P, Cfg::SMEM_BYTES));
+    B200I_REQUIRE(per_sm >= 1, B200I_E_UNSUPPORTED, "sim_factual_tma<%d,%d,%d>: does not fit on an SM", P, TC, SIN);
+    const int64_t ntiles = (n + P - 1) / P;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
+    kern<<<(unsigned)grid, P, Cfg::SMEM_BYTES, st>>>(pack, n, T, c, params, seq_len, static_feature, ws);
+    return check_cuda(cudaGetLastError(), "sim_factual_tma launch");
+}
+
+template <bool GRAM>
+static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
+                        double *const out[9], double *seq_len, const double *sf, StatsWorkspace *ws, cudaStream_t st)
+{
+    switch (variant) {
+        case 2: return launch_tma<128, 8, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 3: return launch_tma<128, 4, 2, 3, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 4: return launch_tma<64, 16, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 5: return launch_tma<64, 8, 2, 3, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 6: return launch_tma<128, 4, 1, 4, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 7: return launch_tma<256, 4, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 8: return launch_tma<128, 16, 1, 1, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
+        default:
+            set_error("sim_factual: unknown variant %d", variant);
+            return B200I_E_ARG;
+    }
+}
+
+}  // namespace b200i
+
+using namespace b200i;
+
+extern "C" int64_t b200i_gram_workspace_bytes(void) { return (int64_t)sizeof(StatsWorkspace); }
+
+extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k, const double *params,
+                                 const double *noise, const double *recovery_rvs, const double *chemo_rvs,
+                                 const double *radio_rvs, const double *assigned_actions, double *cancer_volume,
+                                 double *chemo_dosage, double *radio_dosage, double *chemo_application,
+                                 double *radio_application, double *chemo_probabilities, double *radio_probabilities,
+                                 double *death_flags, double *recovery_flags, double *sequence_lengths,
+                                 const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
+                                 void *stream)
+{
+    B200I_REQUIRE(n >= 0 && k && params && noise && recovery_rvs && chemo_rvs && radio_rvs && cancer_volume &&
+                      chemo_dosage && radio_dosage && chemo_application && radio_application && chemo_probabilities &&
+                      radio_probabilities && death_flags && recovery_flags && sequence_lengths,
+                  B200I_E_ARG, "sim_factual: NULL argument or negative n");
+    B200I_REQUIRE(T >= 3 && T <= 4096, B200I_E_UNSUPPORTED, "sim_factual: seq_length %d outside [3,4096]", T);
+    B200I_REQUIRE(k->lag == 0, B200I_E_UNSUPPORTED, "sim_factual: lag=%d (only lag=0 is implemented)", k->lag);
+    B200I_REQUIRE(k->window_size >= 1 && k->window_size <= 15, B200I_E_UNSUPPORTED,
+                  "sim_factual: window_size=%d outside [1,15]", k->window_size);
+    B200I_REQUIRE(n < (int64_t)1 << 31, B200I_E_UNSUPPORTED, "sim_factual: n=%lld >= 2^31", (long long)n);
+    const bool gram = gram_workspace != nullptr;
+    B200I_REQUIRE(!gram || (static_feature && fd_dt > 0), B200I_E_ARG,
+                  "sim_factual: fused gram needs static_feature and fd_dt > 0");
+    if (n == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SimC c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay, fd_dt,
+           k->window_size};
+    const double *in[4] = {noise, recovery_rvs, chemo_rvs, radio_rvs};
+    double *out[9] = {cancer_volume, chemo_dosage, radio_dosage, chemo_application, radio_application,
+                      chemo_probabilities, radio_probabilities, death_flags, recovery_flags};
+    StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
+
+    bool tma_ok = (T % 2 == 0) && assigned_actions == nullptr;
+    for (int a = 0; a < 4; ++a) tma_ok = tma_ok && aligned16(in[a]);
+    for (int a = 0; a < 9; ++a) tma_ok = tma_ok && aligned16(out[a]);
+    if (variant == 0) variant = tma_ok ? 2 : 1;
+    if (variant >= 2) {
+        B200I_REQUIRE(assigned_actions == nullptr, B200I_E_UNSUPPORTED,
+                      "sim_factual: assigned_actions is only handled by the generic kernel (variant 1)");
+        B200I_REQUIRE(tma_ok, B200I_E_ALIGN, "sim_factual: TMA variant needs even T and 16-byte aligned arrays");
+        return gram ? dispatch_tma<true>(variant, n, T, c, params, in, out, sequence_lengths, static_feature, ws, st)
+                    : dispatch_tma<false>(variant, n, T, c, params, in, out, sequence_lengths, static_feature, ws, st);
+    }
+    FactualPtrs io;
+    io.noise = noise; io.rec = recovery_rvs; io.chemo_rvs = chemo_rvs; io.radio_rvs = radio_rvs;
+    io.assigned = assigned_actions;
+    for (int a = 0; a < 9; ++a) io.out[a] = out[a];
+    io.seq_len = sequence_lengths;
+    int64_t grid = (n + 127) / 128;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    if (gram)
+        sim_factual_generic<true><<<(unsigned)grid, 128, 0, st>>>(n, T, c, params, io, static_feature, ws);
+    else
+        sim_factual_generic<false><<<(unsigned)grid, 128, 0, st>>>(n, T, c, params, io, static_feature, ws);
+    return check_cuda(cudaGetLastError(), "sim_factual_generic launch");
+}

@@ -1,0 +1,220 @@
+// theta_gram.cu -- K4: the data reduction behind SINDY.fit for the cancer simulator.
+//
+// Reference semantics: process_sindy_training_data (pkpd/utils.py:433-462) cuts
+// every patient's trajectory x[0..L] (L = sequence_length, x[L] included) into maximal constant-
+// treatment snippets that share their end point with the next snippet; pysindy differentiates each
+// snippet with FiniteDifference(order=1) (forward difference, last point backward) and evaluates
+// PolynomialLibrary(degree=2, interaction_only=True) = [1, x0, u0, x0*u0]; the four per-treatment
+// regressions (sindy.py:203-213) only need Theta^T Theta and Theta^T xdot.  This kernel streams the
+// cohort once and reduces those normal equations in FP64; nothing tall is ever materialised.
+//
+// Mapping: CTA of 128 threads = 128 consecutive patients.  Their volume rows are one contiguous
+// chunk of 128*T doubles, fetched with a single 1-D bulk TMA copy (cp.async.bulk, SASS UBLKCP) into
+// shared memory; the two application arrays are read with coalesced 16-byte loads and packed to one
+// treatment-code byte per step.  Then one thread walks one patient.  HBM traffic = 3 arrays once.
+// The moments needed by get_scaling_params (cancer_simulation.py:776-796) come from a second,
+// element-parallel kernel over the same arrays (masked_moments).
+#include "sim_math.cuh"
+#include "stats_reduce.cuh"
+#include "tma.cuh"
+
+namespace b200i {
+
+constexpr int GP = 128;  // patients per CTA
+
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(GP)
+theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol, const double *__restrict__ chemo,
+                  const double *__restrict__ radio, const double *__restrict__ seq_len,
+                  const double *__restrict__ static_feature, StatsWorkspace *ws)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+    double *s_vol = reinterpret_cast<double *>(smem_raw);                         // [GP][T]
+    uint8_t *s_code = smem_raw + (size_t)GP * T * sizeof(double);                  // [GP][T]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += GP) (&block_acc[0][0])[j] = 0.0;
+    if (BULK && tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (n + GP - 1) / GP;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * GP;
+        const int rows = (int)((n - first < GP) ? (n - first) : GP);
+        const int64_t elems = (int64_t)rows * T;
+        const double *gv = vol + first * T;
+        if (BULK) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, (uint32_t)(elems * 8));
+                bulk_load_1d(s_vol, gv, (uint32_t)(elems * 8), &bar);
+            }
+        } else {
+            for (int64_t e = tid; e < elems; e += GP) s_vol[e] = gv[e];
+        }
+        // treatment codes: code = chemo + 2*radio (dataset.py:130-141 one-hot index)
+        const double *gc = chemo + first * T, *gr = radio + first * T;
+        if (BULK) {  // T even, 16-byte aligned: two steps per load
+            const double2 *gc2 = reinterpret_cast<const double2 *>(gc), *gr2 = reinterpret_cast<const double2 *>(gr);
+            for (int64_t e = tid; e < elems / 2; e += GP) {
+                const double2 a = __ldg(gc2 + e), b = __ldg(gr2 + e);
+                s_code[2 * e] = (uint8_t)((a.x != 0.0 ? 1 : 0) + (b.x != 0.0 ? 2 : 0));
+                s_code[2 * e + 1] = (uint8_t)((a.y != 0.0 ? 1 : 0) + (b.y != 0.0 ? 2 : 0));
+            }
+        } else {
+            for (int64_t e = tid; e < elems; e += GP)
+                s_code[e] = (uint8_t)((gc[e] != 0.0 ? 1 : 0) + (gr[e] != 0.0 ? 2 : 0));
+        }
+        __syncthreads();
+        if (BULK) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        }
+        const bool exists = tid < rows;
+        PatientGram pg;
+        pg.clear();
+        int L = 0;
+        double u = 0.0;
+        if (exists) {
+            L = (int)seq_len[first + tid];
+            if (L > T - 1) L = T - 1;
+            u = static_feature[first + tid];
+            const double *x = s_vol + (size_t)tid * T;
+            const uint8_t *a = s_code + (size_t)tid * T;
+            double x0 = x[0];
+            int a0 = a[0];
+            for (int k = 0; k < L; ++k) {
+                const double x1 = x[k + 1];
+                const int a1 = a[k + 1];
+                const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+                pg.add(a0, x0, xdot);
+                if (k == L - 1 || a1 != a0) pg.add(a0, x1, xdot);
+                x0 = x1;
+                a0 = a1;
+            }
+        }
+        // fold (Gram part only; moments are produced by masked_moments_kernel)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double g[B200I_GRAM_PER_TREATMENT];
+            expand_gram(pg.s[a], u, g);
+#pragma unroll
+            for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j)
+                warp_acc_add(block_acc[warp], a * B200I_GRAM_PER_TREATMENT + j, exists ? g[j] : 0.0, lane);
+        }
+        __syncthreads();  // smem tile is reused by the next iteration
+    }
+    stats_block_finish(block_acc, GP >> 5, ws, &s_is_last);
+}
+
+// sum x, sum x^2 over active entries [i, :seq_len[i]] of up to three (N,T) arrays; one warp per row.
+// Writes moments into a second StatsWorkspace-style partial area (slots 60..67 of the same layout).
+__global__ void __launch_bounds__(256)
+masked_moments_kernel(int64_t n, int T, const double *__restrict__ a0, const double *__restrict__ a1,
+                      const double *__restrict__ a2, const double *__restrict__ seq_len, StatsWorkspace *ws)
+{
+    __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += blockDim.x) (&block_acc[0][0])[j] = 0.0;
+    __syncthreads();
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    double cnt = 0.0, rows = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * nwarps + warp; i < n; i += (int64_t)gridDim.x * nwarps) {
+        int L = (int)seq_len[i];
+        if (L > T) L = T;
+        for (int k = lane; k < L; k += 32) {
+            const double v = a0[i * T + k];
+            s[0] += v; s[1] += v * v;
+            if (a1) { const double c = a1[i * T + k]; s[2] += c; s[3] += c * c; }
+            if (a2) { const double d = a2[i * T + k]; s[4] += d; s[5] += d * d; }
+        }
+        if (lane == 0) { cnt += (double)L; rows += 1.0; }
+    }
+    const int m0 = 4 * B200I_GRAM_PER_TREATMENT;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) warp_acc_add(block_acc[warp], m0 + j, s[j], lane);
+    warp_acc_add(block_acc[warp], m0 + 6, cnt, lane);
+    warp_acc_add(block_acc[warp], m0 + 7, rows, lane);
+    // reduce only the moment slots; Gram slots of this launch are zero and must not clobber stats[0..59]
+    __syncthreads();
+    if (tid < B200I_MOMENTS) {
+        double v = 0.0;
+        for (int w = 0; w < nwarps; ++w) v += block_acc[w][m0 + tid];
+        ws->partials[blockIdx.x][m0 + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&ws->ticket[1], 1u);
+        s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_is_last) {
+        __threadfence();
+        if (tid < B200I_MOMENTS) {
+            double v = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(&ws->partials[b][m0 + tid]);
+            ws->stats[m0 + tid] = v;
+        }
+        if (tid == 0) ws->ticket[1] = 0u;
+    }
+}
+
+}  // namespace b200i
+
+using namespace b200i;
+
+extern "C" int b200i_theta_gram(int64_t n, int32_t T, double fd_dt, const double *cancer_volume,
+                                const double *chemo_application, const double *radio_application,
+                                const double *sequence_lengths, const double *static_feature,
+                                const double *chemo_dosage, const double *radio_dosage, void *gram_workspace,
+                                void *stream)
+{
+    B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths &&
+                      static_feature && gram_workspace,
+                  B200I_E_ARG, "theta_gram: NULL argument or negative n");
+    B200I_REQUIRE(T >= 2 && T <= 1024, B200I_E_UNSUPPORTED, "theta_gram: T=%d outside [2,1024]", T);
+    B200I_REQUIRE(fd_dt > 0, B200I_E_ARG, "theta_gram: fd_dt must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
+    // stats + tickets start from zero for every call (partials are fully overwritten)
+    B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
+    if (n == 0) return 0;
+    const size_t smem = (size_t)GP * T * 9;
+    const bool bulk = (T % 2 == 0) && aligned16(cancer_volume) && aligned16(chemo_application) &&
+                      aligned16(radio_application);
+    auto kern = bulk ? theta_gram_kernel<true> : theta_gram_kernel<false>;
+    B200I_REQUIRE(smem <= 220 * 1024, B200I_E_UNSUPPORTED, "theta_gram: T=%d needs %zu bytes of shared memory", T, smem);
+    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (n + GP - 1) / GP;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
+    kern<<<(unsigned)grid, GP, smem, st>>>(n, T, fd_dt, cancer_volume, chemo_application, radio_application,
+                                           sequence_lengths, static_feature, ws);
+    B200I_CUDA(cudaGetLastError());
+    int64_t g2 = (n + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (g2 > cap) g2 = cap;
+    masked_moments_kernel<<<(unsigned)g2, 256, 0, st>>>(n, T, cancer_volume, chemo_dosage, radio_dosage,
+                                                        sequence_lengths, ws);
+    return check_cuda(cudaGetLastError(), "theta_gram launch");
+}

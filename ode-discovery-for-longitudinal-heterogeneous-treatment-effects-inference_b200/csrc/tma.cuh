@@ -1,0 +1,90 @@
+// tma.cuh -- minimal sm_100a TMA / mbarrier wrappers (inline PTX) and host-side tensor-map encoding.
+//
+// The (N,T) float64 arrays of the reference I/O contract are row-major with a 480-byte pitch, so a
+// thread-per-patient kernel cannot touch them directly without wasting 3/4 of every sector.  They are
+// moved as 2-D boxes {TC time steps, P patients} by the TMA unit (cp.async.bulk.tensor, SASS
+// UTMALDG/UTMASTG) into/out of swizzled shared-memory tiles, completion tracked by mbarriers
+// (loads) and bulk async-groups (stores).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace b200i {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// byte offset of (row p, 16-byte unit q) inside a tile whose rows are ROW_BYTES (32/64/128) long and
+// which TMA wrote/reads with the swizzle mode of the same span (address bits [4,4+b) ^= bits [7,7+b)).
+// Tile bases are 1024-byte aligned, so the row index supplies bits 7.. directly.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint32_t swz_off(uint32_t p, uint32_t q)
+{
+    constexpr uint32_t UNITS = ROW_BYTES / 16;
+    const uint32_t x = ((p * ROW_BYTES) >> 7) & (UNITS - 1);
+    return p * ROW_BYTES + ((q ^ x) << 4);
+}
+
+// ---- host side -------------------------------------------------------------------------------
+// Encodes a 2-D tiled map over a (rows, cols) float64 row-major array: box = {box_cols, box_rows}.
+int encode_tmap_2d_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows, uint32_t box_cols, bool promote_256);
+
+}  // namespace b200i

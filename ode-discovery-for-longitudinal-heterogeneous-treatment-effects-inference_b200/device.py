@@ -1,0 +1,196 @@
+"""Device-resident API of the INSITE hot path: thin, typed wrappers over the C ABI.
+
+PyTorch is used for device memory, streams and (in distributed.py) the process group only; every
+numeric kernel is hand-written CUDA inside libb200insite.so.  All tensors are float64, C-contiguous
+and on the current CUDA device unless stated.  Nothing here falls back to the CPU.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import SimConsts
+
+PARAM_KEYS = ('initial_volumes', 'alpha', 'rho', 'beta', 'beta_c', 'K', 'chemo_sigmoid_intercepts',
+              'radio_sigmoid_intercepts', 'chemo_sigmoid_betas', 'radio_sigmoid_betas')
+FACTUAL_OUT_KEYS = ('cancer_volume', 'chemo_dosage', 'radio_dosage', 'chemo_application', 'radio_application',
+                    'chemo_probabilities', 'radio_probabilities', 'death_flags', 'recovery_flags')
+
+# constants exactly as the reference computes them (cancer_simulation.py:34-44, 231-241)
+TUMOUR_CELL_DENSITY = 5.8 * 10 ** 8
+TUMOUR_DEATH_THRESHOLD = 4 / 3 * np.pi * (13 / 2) ** 3
+SPHERE_COEF = 4 / 3 * np.pi
+STANDARD_DT = 10.0 / int(60)          # pkpd/utils.py:48-53
+STEPS_FOR_DT = 5                      # pkpd/utils.py:40
+
+STATS_DOUBLES = 68
+GRAM_PER_TREATMENT = 15
+
+
+def sim_consts(window_size=15, lag=0):
+    return SimConsts(float(TUMOUR_DEATH_THRESHOLD), float(TUMOUR_CELL_DENSITY), float(SPHERE_COEF), 5.0, 2.0,
+                     float(np.exp(-np.log(2) / 1)), int(window_size), int(lag))
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors must be CUDA and contiguous"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200_insite needs a CUDA device (B200, sm_100a); there is no CPU path")
+    _native.load()
+
+
+def pack_params(params):
+    """dict of (N,) arrays (generate_params layout) -> (10,N) float64 numpy block."""
+    return np.ascontiguousarray(np.stack([np.asarray(params[k], dtype=np.float64) for k in PARAM_KEYS], axis=0))
+
+
+def to_device(a, dtype=torch.float64, pinned=False):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if pinned:
+        t = t.pin_memory()
+    return t.cuda(non_blocking=pinned)
+
+
+_workspaces = {}
+
+
+def gram_workspace(tag="default"):
+    """Per-device statistics workspace (stats live in its first 68 doubles)."""
+    lib = _native.load()
+    key = (torch.cuda.current_device(), tag)
+    if key not in _workspaces:
+        nbytes = lib.b200i_gram_workspace_bytes()
+        _workspaces[key] = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device='cuda')
+    return _workspaces[key]
+
+
+def sim_factual(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=None, assigned_actions=None,
+                out=None, variant=0, fused_static=None, fd_dt=STANDARD_DT):
+    """K1.  Returns (dict of nine (N,T) tensors + 'sequence_lengths' (N,), stats or None).
+
+    fused_static: (N,) un-scaled static feature (patient type); if given the population statistics of
+    theta_gram are accumulated inside the simulator kernel and returned as a (68,) tensor view."""
+    lib = _native.load()
+    n = params_dev.shape[1]
+    consts = consts or sim_consts()
+    if out is None:
+        out = {k: torch.empty((n, T), dtype=torch.float64, device='cuda') for k in FACTUAL_OUT_KEYS}
+        out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
+    ws = gram_workspace() if fused_static is not None else None
+    rc = lib.b200i_sim_factual(n, T, ctypes.byref(consts), _ptr(params_dev), _ptr(noise), _ptr(recovery),
+                               _ptr(chemo_rvs), _ptr(radio_rvs), _ptr(assigned_actions),
+                               *[_ptr(out[k]) for k in FACTUAL_OUT_KEYS], _ptr(out['sequence_lengths']),
+                               _ptr(fused_static), float(fd_dt), _ptr(ws), int(variant), _stream())
+    _native.check(rc, "b200i_sim_factual")
+    return out, (ws[:STATS_DOUBLES] if ws is not None else None)
+
+
+def theta_gram(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature,
+               chemo_dosage=None, radio_dosage=None, fd_dt=STANDARD_DT, tag="default"):
+    """K4.  Returns the (68,) packed statistics (view into the workspace)."""
+    lib = _native.load()
+    n, T = cancer_volume.shape
+    ws = gram_workspace(tag)
+    rc = lib.b200i_theta_gram(n, T, float(fd_dt), _ptr(cancer_volume), _ptr(chemo_application),
+                              _ptr(radio_application), _ptr(sequence_lengths), _ptr(static_feature),
+                              _ptr(chemo_dosage), _ptr(radio_dosage), _ptr(ws), _stream())
+    _native.check(rc, "b200i_theta_gram")
+    return ws[:STATS_DOUBLES]
+
+
+def stlsq_population(stats, threshold=1e-3, alpha=0.5, max_iter=100):
+    """K5.  stats (68,) device -> (coefs (4,4) float64, support (4,4) int32), both on device."""
+    lib = _native.load()
+    coefs = torch.empty((4, 4), dtype=torch.float64, device='cuda')
+    support = torch.empty((4, 4), dtype=torch.int32, device='cuda')
+    rc = lib.b200i_stlsq_population(_ptr(stats), float(threshold), float(alpha), int(max_iter), _ptr(coefs),
+                                    _ptr(support), _stream())
+    _native.check(rc, "b200i_stlsq_population")
+    return coefs, support
+
+
+def treatment_codes(chemo_application, radio_application, W):
+    lib = _native.load()
+    rows, pitch = chemo_application.shape
+    codes = torch.empty((rows, W), dtype=torch.uint8, device='cuda')
+    rc = lib.b200i_treatment_codes(rows, W, pitch, _ptr(chemo_application), _ptr(radio_application), _ptr(codes),
+                                   _stream())
+    _native.check(rc, "b200i_treatment_codes")
+    return codes
+
+
+def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS_FOR_DT, drop_below=1e-3, out=None):
+    """K6.  codes (R,W) uint8; coefs (4,4) or (R,4,4).  Returns (R,W) un-scaled predictions."""
+    lib = _native.load()
+    rows, W = codes.shape
+    per_row = 1 if coefs.dim() == 3 else 0
+    if out is None:
+        out = torch.empty((rows, W), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_ode_rollout(rows, W, float(dt), int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes),
+                               _ptr(coefs), per_row, float(drop_below), _ptr(out), _stream())
+    _native.check(rc, "b200i_ode_rollout")
+    return out
+
+
+_mse_ws = {}
+
+
+def masked_se(pred, target, active_len):
+    """(3W+2,) sums: se per column, active count per column, last-entry se per column, total last se, #rows."""
+    lib = _native.load()
+    rows, W = pred.shape
+    dev = torch.cuda.current_device()
+    if dev not in _mse_ws:
+        _mse_ws[dev] = torch.zeros((lib.b200i_masked_se_workspace_bytes() + 7) // 8, dtype=torch.float64, device='cuda')
+    sums = torch.empty(3 * W + 2, dtype=torch.float64, device='cuda')
+    rc = lib.b200i_masked_se(rows, W, _ptr(pred), _ptr(target), _ptr(active_len), _ptr(sums), _ptr(_mse_ws[dev]),
+                             _stream())
+    _native.check(rc, "b200i_masked_se")
+    return sums
+
+
+def unpack_stats(stats):
+    """(68,) host array -> dict with per-treatment G (4,4,4), b (4,4), counts (4,), moments."""
+    s = np.asarray(stats, dtype=np.float64)
+    G = np.zeros((4, 4, 4)); b = np.zeros((4, 4)); cnt = np.zeros(4)
+    for a in range(4):
+        g = s[a * GRAM_PER_TREATMENT:(a + 1) * GRAM_PER_TREATMENT]
+        k = 0
+        for i in range(4):
+            for j in range(i, 4):
+                G[a, i, j] = G[a, j, i] = g[k]
+                k += 1
+        b[a] = g[10:14]
+        cnt[a] = g[14]
+    m = s[4 * GRAM_PER_TREATMENT:]
+    return {'G': G, 'b': b, 'count': cnt,
+            'sum_v': m[0], 'sum_vv': m[1], 'sum_c': m[2], 'sum_cc': m[3], 'sum_d': m[4], 'sum_dd': m[5],
+            'active': m[6], 'patients': m[7]}
+
+
+def moments_to_scaling(stats):
+    """mean / std (ddof=0) of cancer_volume, chemo_dosage, radio_dosage over active entries
+    (get_scaling_params, cancer_simulation.py:776-796) from the packed statistics."""
+    u = unpack_stats(stats)
+    n = u['active']
+    out = {}
+    for name, s1, s2 in (('cancer_volume', 'sum_v', 'sum_vv'), ('chemo_dosage', 'sum_c', 'sum_cc'),
+                         ('radio_dosage', 'sum_d', 'sum_dd')):
+        mean = u[s1] / n
+        var = max(u[s2] / n - mean * mean, 0.0)
+        out[name] = (mean, math.sqrt(var))
+    return out

@@ -1,0 +1,146 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/sim_c/oracle_sim.c.
+
+Each function takes the simulation-parameter dict (reference layout) plus the
+pre-drawn random arrays and returns the reference's output dict (same keys / shapes / dtypes as
+cancer_simulation.py:356-367, :554-559, :762-769).
+"""
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle_sim.so")
+_lib = None
+
+TUMOUR_DEATH_THRESHOLD = 4 / 3 * np.pi * (13 / 2) ** 3   # cancer_simulation.py:34-35,44
+
+_PARAM_KEYS = ['initial_volumes', 'alpha', 'rho', 'beta', 'beta_c', 'K', 'chemo_sigmoid_intercepts',
+               'radio_sigmoid_intercepts', 'chemo_sigmoid_betas', 'radio_sigmoid_betas']
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, a second or two)."""
+    src = os.path.join(_HERE, "sim_c", "oracle_sim.c")
+    if force or not os.path.isfile(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "sim_c")])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.oracle_sim_factual.restype = ctypes.c_int
+        _lib.oracle_sim_cf_one_step.restype = ctypes.c_int64
+        _lib.oracle_sim_cf_treatment_seq.restype = ctypes.c_int64
+        _lib.oracle_np_mean.restype = ctypes.c_double
+        _lib.oracle_np_sum.restype = ctypes.c_double
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def np_mean(a):
+    a = _f64(a)
+    return lib().oracle_np_mean(_p(a), ctypes.c_int64(a.size))
+
+
+def sim_factual(params, T, draws, assigned_actions=None, n_threads=1):
+    L = lib()
+    n = params['initial_volumes'].shape[0]
+    pk = [_f64(params[k]) for k in _PARAM_KEYS]
+    dr = [_f64(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    aa = None if assigned_actions is None else _f64(assigned_actions)
+    names = ['cancer_volume', 'chemo_dosage', 'radio_dosage', 'chemo_application', 'radio_application',
+             'chemo_probabilities', 'radio_probabilities']
+    out = {k: np.empty((n, T)) for k in names}
+    out['sequence_lengths'] = np.empty(n)
+    out['death_flags'] = np.empty((n, T))
+    out['recovery_flags'] = np.empty((n, T))
+
+    def run(lo, hi):
+        args = [ctypes.c_int64(hi - lo), ctypes.c_int(T), ctypes.c_int(int(params['window_size'])),
+                ctypes.c_int(int(params['lag'])), ctypes.c_double(TUMOUR_DEATH_THRESHOLD)]
+        args += [_p(a[lo:hi]) for a in pk]
+        args += [_p(a[lo:hi]) for a in dr]
+        args += [None if aa is None else _p(aa[lo:hi])]
+        args += [_p(out[k][lo:hi]) for k in names]
+        args += [_p(out['sequence_lengths'][lo:hi]), _p(out['death_flags'][lo:hi]), _p(out['recovery_flags'][lo:hi])]
+        rc = L.oracle_sim_factual(*args)
+        assert rc == 0, rc
+
+    if n_threads <= 1 or n < 4 * n_threads:
+        run(0, n)
+    else:
+        bounds = np.linspace(0, n, n_threads + 1).astype(np.int64)
+        with ThreadPoolExecutor(n_threads) as ex:
+            list(ex.map(lambda b: run(int(b[0]), int(b[1])), zip(bounds[:-1], bounds[1:])))
+    out['patient_types'] = params['patient_types']
+    assert not np.any(np.isnan(out['cancer_volume'])), 'Cancer volume contains NaN'
+    return out
+
+
+def sim_cf_one_step(params, T, draws):
+    L = lib()
+    n = params['initial_volumes'].shape[0]
+    pk = [_f64(params[k]) for k in _PARAM_KEYS]
+    pt = _f64(params['patient_types'])
+    dr = [_f64(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    cap = 4 * n * T
+    cv, ca, ra = np.empty((cap, T)), np.empty((cap, T)), np.empty((cap, T))
+    sl, pta = np.empty(cap), np.empty(cap)
+    rows = L.oracle_sim_cf_one_step(ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(int(params['window_size'])),
+                                    ctypes.c_int(int(params['lag'])), ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
+                                    *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr],
+                                    _p(cv), _p(ca), _p(ra), _p(sl), _p(pta))
+    assert rows >= 0, rows
+    return {'cancer_volume': cv[:rows], 'chemo_application': ca[:rows], 'radio_application': ra[:rows],
+            'sequence_lengths': sl[:rows], 'patient_types': pta[:rows]}
+
+
+def sim_cf_treatment_seq(params, T, H, draws):
+    L = lib()
+    n = params['initial_volumes'].shape[0]
+    pk = [_f64(params[k]) for k in _PARAM_KEYS]
+    pt = _f64(params['patient_types'])
+    dr = [_f64(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    cap = 2 * H * n * T
+    W = T + H
+    cv, ca, ra = np.empty((cap, W)), np.empty((cap, W)), np.empty((cap, W))
+    sl, pta, pid, pct = np.empty(cap), np.empty(cap), np.empty(cap), np.empty(cap)
+    rows = L.oracle_sim_cf_treatment_seq(ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(H),
+                                         ctypes.c_int(int(params['window_size'])), ctypes.c_int(int(params['lag'])),
+                                         ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
+                                         *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr],
+                                         _p(cv), _p(ca), _p(ra), _p(sl), _p(pta), _p(pid), _p(pct))
+    assert rows >= 0, rows
+    return {'cancer_volume': cv[:rows], 'chemo_application': ca[:rows], 'radio_application': ra[:rows],
+            'sequence_lengths': sl[:rows], 'patient_types': pta[:rows],
+            'patient_ids_all_trajectories': pid[:rows], 'patient_current_t': pct[:rows]}
+
+
+def scaling_params(sim):
+    """get_scaling_params (:776-796) -> (means dict, stds dict)."""
+    L = lib()
+    sl = _f64(sim['sequence_lengths'])
+    n, T = sim['cancer_volume'].shape
+    scratch = np.empty(int(sl.sum()) + 1)
+    means, stds = {}, {}
+    for k in ['cancer_volume', 'chemo_dosage', 'radio_dosage']:
+        m, s = ctypes.c_double(), ctypes.c_double()
+        L.oracle_scaling_moments(ctypes.c_int64(n), ctypes.c_int(T), _p(_f64(sim[k])), _p(sl), _p(scratch),
+                                 ctypes.byref(m), ctypes.byref(s))
+        means[k], stds[k] = m.value, s.value
+    means['patient_types'] = np.mean(sim['patient_types'])
+    stds['patient_types'] = np.std(sim['patient_types'])
+    return means, stds

@@ -1,0 +1,273 @@
+"""TEST INFRASTRUCTURE ONLY.  numpy / sklearn restatement of the reference SINDy-INSITE path.
+
+The reference code (libs_m/ct/src/models/sindy.py, libs_m/ct/src/data/pkpd/utils.py) cannot be
+imported here: it needs pysindy, jax, sympy2jax, hydra, pytorch-lightning, none of which are
+installed (no network).  The arithmetic that lives in the un-vendored, *unpinned* dependency
+``pysindy`` (setup/requirements.txt:1; API usage + log dates imply 1.7.x) is restated from its
+published algorithm:
+
+  PolynomialLibrary(degree=2, interaction_only=True)  -> features [1, x0, u0, x0*u0]
+  FiniteDifference(order=1, is_uniform=True)          -> forward difference, last point backward
+  STLSQ(threshold, alpha, max_iter=100)               -> loop as in the vendored copy
+                                                         pkpd/utils.py:244-327 (ridge via
+                                                         sklearn.linear_model.ridge_regression
+                                                         :228) + pysindy's default unbias OLS refit
+  call sites: sindy.py:185-213.
+
+Parity pinning: tests/test_oracle.py checks this file against the reference's own committed run
+log results/2_main_table/final_with_insite.txt:6 (16 population coefficients, 3 one-step RMSEs,
+5 tau-step RMSEs for seed=1, gamma=2, 1000/100/100 patients) -- the only known-answer vectors the
+reference holds for this path.
+
+Other functions follow (file:line of the reference):
+  process_data                   dataset.py:92-192
+  process_sequential_test/multi  dataset.py:395-473, 533-552
+  de_format_snippets             pkpd/utils.py:433-462, 543-554, 607-637
+  equation_string                pkpd/utils.py:378-397
+  rollout                        sindy.py:371-431 + pkpd/utils.py:68-90 (5 Euler sub-steps)
+  masked_rmse / n_step_rmses     time_varying_model.py:236-313
+  slice_autoregressive           sindy.py:729-733
+  insite_objective / insite_bfgs sindy.py:587-631, 781-794 (scipy BFGS; iterate-level parity
+                                 with jax's BFGS is UNPINNED)
+"""
+import numpy as np
+
+STANDARD_DT = 10.0 / int(60)      # pkpd/utils.py:48-53
+STEPS_FOR_DT = 5                  # pkpd/utils.py:40
+TUMOUR_DEATH_THRESHOLD = 4 / 3 * np.pi * (13 / 2) ** 3
+
+
+# ------------------------------------------------------------------------------------------------
+# dataset transforms
+# ------------------------------------------------------------------------------------------------
+def process_data(sim, means, stds, treatment_mode='multiclass'):
+    """dataset.py:92-192.  ``sim`` = simulator output dict; returns a NEW dict with the added keys."""
+    d = dict(sim)
+    cv = (sim['cancer_volume'] - means['cancer_volume']) / stds['cancer_volume']
+    pt = (sim['patient_types'] - means['patient_types']) / stds['patient_types']
+    pt = np.stack([pt for _ in range(cv.shape[1])], axis=1)
+    chemo, radio, sl = sim['chemo_application'], sim['radio_application'], sim['sequence_lengths']
+    treatments = np.concatenate([chemo[:, :-1, None], radio[:, :-1, None]], axis=-1)
+    if treatment_mode == 'multiclass':
+        code = (treatments[..., 0] == 1) * 1 + (treatments[..., 1] == 1) * 2
+        known = ((treatments[..., 0] == 0) | (treatments[..., 0] == 1)) & \
+                ((treatments[..., 1] == 0) | (treatments[..., 1] == 1))
+        one_hot = np.zeros(treatments.shape[:2] + (4,))
+        for c in range(4):
+            one_hot[..., c] = ((code == c) & known) * 1.0
+        d['prev_treatments'] = one_hot[:, :-1, :]
+        d['current_treatments'] = one_hot
+    else:
+        d['prev_treatments'] = treatments[:, :-1, :]
+        d['current_treatments'] = treatments
+    cov = np.concatenate([cv[:, :-1, None], pt[:, :-1, None]], axis=-1)
+    outputs = cv[:, 1:, None]
+    active = np.zeros(outputs.shape)
+    for i in range(sl.shape[0]):
+        active[i, :int(sl[i]), :] = 1
+    d['current_covariates'] = cov
+    d['outputs'] = outputs
+    d['active_entries'] = active
+    d['unscaled_outputs'] = outputs * stds['cancer_volume'] + means['cancer_volume']
+    d['prev_outputs'] = cov[:, :, :1]
+    d['static_features'] = cov[:, 0, 1:]
+    zero = np.zeros((cov.shape[0], 1, d['prev_treatments'].shape[-1]))
+    d['prev_treatments'] = np.concatenate([zero, d['prev_treatments']], axis=1)
+    scaling = {'input_means': np.array([means['cancer_volume'], means['patient_types'], 0.0, 0.0]),
+               'inputs_stds': np.array([stds['cancer_volume'], stds['patient_types'], 1.0, 1.0]),
+               'output_means': means['cancer_volume'], 'output_stds': stds['cancer_volume']}
+    return d, scaling
+
+
+def process_sequential_test(data, scaling, H):
+    """dataset.py:395-473 (encoder_r=None): the last H steps of every row."""
+    sl, outputs = data['sequence_lengths'], data['outputs']
+    cur, prev = data['current_treatments'], data['prev_treatments'][:, 1:, :]
+    cov = data['current_covariates']
+    R = outputs.shape[0]
+    o = np.zeros((R, H, outputs.shape[-1])); ct = np.zeros((R, H, cur.shape[-1]))
+    pt = np.zeros((R, H, prev.shape[-1])); cc = np.zeros((R, H, cov.shape[-1]))
+    for i in range(R):
+        fl = int(sl[i]) - H
+        pt[i] = prev[i, fl - 1:fl + H - 1, :]
+        ct[i] = cur[i, fl:fl + H, :]
+        o[i] = outputs[i, fl:fl + H, :]
+        cc[i] = np.repeat([cov[i, fl - 1]], H, axis=0)
+    return {'prev_treatments': pt, 'current_treatments': ct, 'current_covariates': cc,
+            'prev_outputs': cc[:, :, :1], 'static_features': cc[:, 0, 1:], 'outputs': o,
+            'sequence_lengths': np.full(R, float(H)), 'active_entries': np.ones((R, H, 1)),
+            'unscaled_outputs': o * scaling['output_stds'] + scaling['output_means']}
+
+
+# ------------------------------------------------------------------------------------------------
+# population fit
+# ------------------------------------------------------------------------------------------------
+def de_format_snippets(data, scaling):
+    """pkpd/utils.py:543-554 + :433-462 + :620-637 (joint=False, CANCER_SIM).
+
+    Returns 4 lists (one per treatment) of (x (L,), u (L,)) constant-treatment snippets."""
+    prev = data['prev_outputs'] * scaling['output_stds'] + scaling['output_means']
+    static = data['static_features'] * scaling['inputs_stds'][1:2] + scaling['input_means'][1:2]
+    cur = np.squeeze(data['current_treatments'])
+    unscaled_outputs = np.squeeze(data['unscaled_outputs'])
+    sl = data['sequence_lengths'].astype(np.int64)
+    vol = np.concatenate((prev[:, 0].reshape(-1, 1), unscaled_outputs), axis=1)
+    buckets = ([], [], [], [])
+    for p in range(vol.shape[0]):
+        tr, x, L, u = cur[p], vol[p], int(sl[p]), static[p, 0]
+        cur_t, cur_x = [], []
+        for i in range(L):
+            if len(cur_t) >= 1 and (tr[i] != cur_t[-1]).any():
+                cur_t.append(cur_t[-1]); cur_x.append(x[i])
+                buckets[int(np.argmax(np.stack(cur_t).mean(0)))].append((np.array(cur_x), np.full(len(cur_x), u)))
+                cur_t, cur_x = [tr[i]], [x[i]]
+            else:
+                cur_t.append(tr[i]); cur_x.append(x[i])
+            if i == L - 1:
+                cur_t.append(tr[i]); cur_x.append(x[i + 1])
+                buckets[int(np.argmax(np.stack(cur_t).mean(0)))].append((np.array(cur_x), np.full(len(cur_x), u)))
+    return buckets
+
+
+def finite_difference_order1(x, dt):
+    """pysindy FiniteDifference(order=1, is_uniform=True): forward, last point backward."""
+    xd = np.empty_like(x)
+    xd[:-1] = (x[1:] - x[:-1]) / dt
+    xd[-1] = (x[-1] - x[-2]) / dt
+    return xd
+
+
+def library_p4(x, u):
+    """PolynomialLibrary(degree=2, interaction_only=True) on [x0, u0] -> [1, x0, u0, x0 u0]."""
+    return np.stack([np.ones_like(x), x, u, x * u], axis=1)
+
+
+def design_matrices(snippets, dt=STANDARD_DT):
+    th = np.concatenate([library_p4(x, u) for x, u in snippets], axis=0)
+    xd = np.concatenate([finite_difference_order1(x, dt) for x, _ in snippets], axis=0)
+    return th, xd
+
+
+def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True):
+    """pysindy STLSQ.  Loop: pkpd/utils.py:274-310 (vendored copy); ridge: :228; unbias: pysindy
+    BaseOptimizer._unbias (LinearRegression without intercept on the final support)."""
+    from sklearn.linear_model import ridge_regression, LinearRegression
+    n_feat = theta.shape[1]
+    ind = np.ones(n_feat, dtype=bool)
+    coef = np.linalg.lstsq(theta, xdot, rcond=None)[0]
+    history = [coef.copy()]
+    n_sel = n_feat
+    for _ in range(max_iter):
+        if np.count_nonzero(ind) == 0:
+            coef = np.zeros(n_feat)
+            break
+        c_i = ridge_regression(theta[:, ind], xdot, alpha, tol=1e-6)
+        c = np.zeros(n_feat)
+        c[ind] = c_i
+        big = np.abs(c) >= threshold
+        c[~big] = 0
+        coef, ind = c, big
+        history.append(coef.copy())
+        this, last = history[-1], history[-2] if len(history) > 1 else np.zeros_like(coef)
+        if np.sum(ind) == n_sel or all(bool(a) == bool(b) for a, b in zip(this, last)):
+            break
+        n_sel = np.sum(ind)
+    if unbias and np.any(ind):
+        c = np.zeros(n_feat)
+        c[ind] = LinearRegression(fit_intercept=False).fit(theta[:, ind], xdot).coef_
+        coef = c
+    return coef, ind
+
+
+def fit_population(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
+    """sindy.py:160-213, 332-336 -> joint_coefs (4,4), support (4,4) bool."""
+    buckets = de_format_snippets(data, scaling)
+    coefs, sup = np.zeros((4, 4)), np.zeros((4, 4), dtype=bool)
+    stats = []
+    for a in range(4):
+        th, xd = design_matrices(buckets[a], dt)
+        coefs[a], sup[a] = stlsq_fit(th, xd, threshold, alpha)
+        stats.append((len(buckets[a]), th.shape[0]))
+    return coefs, sup, stats
+
+
+def equation_string(coefs, names=('1', 'x0', 'u0', 'x0*u0')):
+    """pkpd/utils.py:386-391 + sindy.py:295."""
+    parts = []
+    for a in range(coefs.shape[0]):
+        s = ''
+        for i, c in enumerate(coefs[a]):
+            if np.abs(c) > 1e-3:
+                s += f'+{c}*' + names[i]
+        parts.append(f'Treatment {a}: x_dot = {s}')
+    return ' | '.join(parts)
+
+
+# ------------------------------------------------------------------------------------------------
+# rollout + metrics
+# ------------------------------------------------------------------------------------------------
+def rollout_unscaled(x0, codes, u, coefs, dt=STANDARD_DT, steps=STEPS_FOR_DT):
+    """sindy.py:413-431 / :767-778 with pkpd/utils.py:68-90: open loop, 5 Euler sub-steps per
+    interval.  x0 (R,), codes (R,W) int treatment index (argmax of the one-hot), u (R,),
+    coefs (4,4) or per-row (R,4,4).  Returns (R,W)."""
+    R, W = codes.shape
+    v = x0.astype(np.float64).copy()
+    out = np.empty((R, W))
+    h = dt / steps
+    rows = np.arange(R)
+    for k in range(W):
+        c = coefs[codes[:, k]] if coefs.ndim == 2 else coefs[rows, codes[:, k]]
+        for _ in range(steps):
+            v = v + (c[:, 0] * 1 + c[:, 1] * v + c[:, 2] * u + c[:, 3] * (v * u)) * h
+        out[:, k] = v
+    return out
+
+
+def effective_coefs(coefs):
+    """The sympy expression only keeps terms with |c| > 1e-3 (pkpd/utils.py:387-391)."""
+    return np.where(np.abs(coefs) > 1e-3, coefs, 0.0)
+
+
+def predictions_population(data, scaling, coefs):
+    """_get_non_fine_tuned_predictions sindy.py:371-431 -> scaled predictions (R,W,1)."""
+    prev = np.squeeze(data['prev_outputs'] * scaling['output_stds'] + scaling['output_means'], -1)
+    static = data['static_features'] * scaling['inputs_stds'][1:2] + scaling['input_means'][1:2]
+    codes = np.argmax(data['current_treatments'], axis=-1)
+    un = rollout_unscaled(prev[:, 0], codes, static[:, 0], effective_coefs(coefs))
+    return ((un - scaling['output_means']) / scaling['output_stds'])[..., None]
+
+
+def masked_rmse(pred_scaled, data, scaling, norm_const=TUMOUR_DEATH_THRESHOLD, one_step_counterfactual=True):
+    """time_varying_model.py:236-283 (unscale=True, percentage=True) -> (orig, all, last)."""
+    un = pred_scaled * scaling['output_stds'] + scaling['output_means']
+    act = data['active_entries']
+    mse = ((un - data['unscaled_outputs']) ** 2) * act
+    orig = (mse.sum(0).sum(-1) / act.sum(0).sum(-1)).mean()
+    rmse_orig = np.sqrt(orig) / norm_const * 100.0
+    rmse_all = np.sqrt(mse.sum() / act.sum()) / norm_const * 100.0
+    if not one_step_counterfactual:
+        return rmse_orig, rmse_all
+    R, _, od = act.shape
+    last = act - np.concatenate([act[:, 1:, :], np.zeros((R, 1, od))], axis=1)
+    mse_last = (((un - data['unscaled_outputs']) ** 2) * last).sum() / last.sum()
+    return rmse_orig, rmse_all, np.sqrt(mse_last) / norm_const * 100.0
+
+
+def slice_autoregressive(pred_scaled, sequence_lengths, H):
+    """sindy.py:729-733: dynamic_slice(preds, (i, max(1, sl-H), 0), (1,H,1)) (start is clamped
+    so that the slice fits, as lax.dynamic_slice does)."""
+    R, W, _ = pred_scaled.shape
+    sl = sequence_lengths.astype(np.int64)
+    lo = np.clip(np.maximum(1, sl - H), 0, W - H)
+    idx = lo[:, None] + np.arange(H)[None, :]
+    return pred_scaled[np.arange(R)[:, None], idx, :]
+
+
+def n_step_rmses(pred_seq_scaled, data_seq, scaling, norm_const=TUMOUR_DEATH_THRESHOLD):
+    """time_varying_model.py:285-313 -> (H,) percentages."""
+    un = pred_seq_scaled * scaling['output_stds'] + scaling['output_means']
+    mse = ((un - data_seq['unscaled_outputs']) ** 2) * data_seq['active_entries']
+    nan_idx = np.unique(np.where(np.isnan(data_seq['outputs']))[0])
+    keep = np.setdiff1d(np.arange(un.shape[0]), nan_idx)
+    mse_orig = mse[keep].sum(0).sum(-1) / data_seq['active_entries'][keep].sum(0).sum(-1)
+    return np.sqrt(mse_orig) / norm_const * 100.0
