@@ -1,0 +1,92 @@
+"""Device-resident cohort pipeline for the large configurations (1M+ patients per GPU).
+
+One process per GPU; patients are sharded contiguously over ranks (no data-path collective); the only
+exchange is a sum-allreduce of the 68 packed population statistics (NCCL over NVLink when a process
+group is initialised), after which every rank runs the identical tiny STLSQ and therefore holds
+bit-identical population coefficients.
+
+    FactualFitPipeline.step_device()  K1 simulate_factual -> K4 theta_gram (or fused) -> allreduce ->
+                                      K5 population STLSQ, inputs already resident in HBM
+    FactualFitPipeline.step_host()    the same through host buffers: pinned params + pre-drawn noise
+                                      are copied H2D, results (coefficients, support, scaling moments)
+                                      are copied back
+Reference path being replaced: SyntheticCancerDataset(mode='factual') -> get_scaling_params ->
+SINDY.fit (dataset.py:58-63, cancer_simulation.py:218-375/776-796, sindy.py:145-338).
+"""
+import numpy as np
+import torch
+
+from . import device as dev
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous patient range [lo, hi) of `rank`."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_stats(stats):
+    """Sum the packed statistics over ranks (no-op without a process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+class FactualFitPipeline:
+    def __init__(self, n_local, T=60, window_size=15, threshold=1e-3, alpha=0.5, max_iter=100, variant=0,
+                 fused=False):
+        dev.require_cuda()
+        self.n, self.T = int(n_local), int(T)
+        self.consts = dev.sim_consts(window_size, 0)
+        self.threshold, self.alpha, self.max_iter = threshold, alpha, max_iter
+        self.variant, self.fused = variant, fused
+        f64 = dict(dtype=torch.float64, device='cuda')
+        self.params = torch.empty((10, self.n), **f64)
+        self.static = torch.empty((self.n,), **f64)
+        self.draws = [torch.empty((self.n, self.T), **f64) for _ in range(4)]   # noise, recovery, chemo, radio
+        self.out = {k: torch.empty((self.n, self.T), **f64) for k in dev.FACTUAL_OUT_KEYS}
+        self.out['sequence_lengths'] = torch.empty((self.n,), **f64)
+        self.stats = torch.zeros(dev.STATS_DOUBLES, **f64)
+        self.coefs = None
+        self.support = None
+        self.launches_per_step = 3 if fused else 4   # sim (+gram +moments) + stlsq
+
+    # -- inputs ------------------------------------------------------------------------------------
+    def load_host(self, params_block, static, draws, non_blocking=True):
+        """H2D copy of one step's inputs from (pinned) host tensors."""
+        self.params.copy_(params_block, non_blocking=non_blocking)
+        self.static.copy_(static, non_blocking=non_blocking)
+        for d, h in zip(self.draws, draws):
+            d.copy_(h, non_blocking=non_blocking)
+
+    def h2d_bytes(self):
+        return (10 + 1 + 4 * self.T) * self.n * 8
+
+    # -- one pass of the hot path ------------------------------------------------------------------
+    def step_device(self):
+        out, stats = dev.sim_factual(self.params, *self.draws, self.T, self.consts, out=self.out,
+                                     variant=self.variant, fused_static=self.static if self.fused else None)
+        if not self.fused:
+            stats = dev.theta_gram(out['cancer_volume'], out['chemo_application'], out['radio_application'],
+                                   out['sequence_lengths'], self.static, out['chemo_dosage'], out['radio_dosage'])
+        self.stats.copy_(stats)
+        allreduce_stats(self.stats)
+        self.coefs, self.support = dev.stlsq_population(self.stats, self.threshold, self.alpha, self.max_iter)
+        return self.coefs
+
+    def step_host(self, params_block, static, draws, result_host):
+        """Host buffers in, host result out: result_host is a pinned (16 + 16 + 68,) float64 tensor that
+        receives coefficients, support and the packed statistics."""
+        self.load_host(params_block, static, draws)
+        self.step_device()
+        result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
+        result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
+        result_host[32:32 + dev.STATS_DOUBLES].copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return result_host
+
+    def executed_steps(self):
+        """Executed simulator loop iterations of the last step: sum(sequence_length - 1)."""
+        return float((self.out['sequence_lengths'] - 1.0).sum().item())

@@ -407,10 +407,12 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
                                  const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
                                  void *stream)
 {
-    B200I_REQUIRE(n >= 0 && k && params && noise && recovery_rvs && chemo_rvs && radio_rvs && cancer_volume &&
+    B200I_REQUIRE(n >= 0, B200I_E_ARG, "sim_factual: negative n");
+    if (n == 0) return 0;
+    B200I_REQUIRE(k && params && noise && recovery_rvs && chemo_rvs && radio_rvs && cancer_volume &&
                       chemo_dosage && radio_dosage && chemo_application && radio_application && chemo_probabilities &&
                       radio_probabilities && death_flags && recovery_flags && sequence_lengths,
-                  B200I_E_ARG, "sim_factual: NULL argument or negative n");
+                  B200I_E_ARG, "sim_factual: NULL argument");
     B200I_REQUIRE(T >= 3 && T <= 4096, B200I_E_UNSUPPORTED, "sim_factual: seq_length %d outside [3,4096]", T);
     B200I_REQUIRE(k->lag == 0, B200I_E_UNSUPPORTED, "sim_factual: lag=%d (only lag=0 is implemented)", k->lag);
     B200I_REQUIRE(k->window_size >= 1 && k->window_size <= 15, B200I_E_UNSUPPORTED,
@@ -419,7 +421,6 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
     const bool gram = gram_workspace != nullptr;
     B200I_REQUIRE(!gram || (static_feature && fd_dt > 0), B200I_E_ARG,
                   "sim_factual: fused gram needs static_feature and fd_dt > 0");
-    if (n == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SimC c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay, fd_dt,
            k->window_size};

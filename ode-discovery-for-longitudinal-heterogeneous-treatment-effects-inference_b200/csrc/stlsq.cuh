@@ -9,59 +9,68 @@
 
 namespace b200i {
 
-// Solve (A[idx,idx] + ridge*I) c = b[idx] for the m = popcount(mask) selected features by Cholesky
-// with Jacobi (diagonal) scaling; unselected coefficients are 0.  Optional prior: solves
-// (A + ridge*I) c = b + ridge*prior (ridge-to-prior).  Returns false if the matrix is not positive
-// definite.
+// Solve (G[S,S] + ridge*I) c[S] = b[S] (+ ridge*prior[S]) for the selected features S = mask by
+// Cholesky with Jacobi (diagonal) scaling; unselected coefficients are 0.  The system is kept 4x4:
+// unselected rows/columns are replaced by the identity, so every index is static (registers only).
+// Returns false if the matrix is not positive definite.
 __host__ __device__ inline bool solve_spd4(const double (&G)[4][4], const double (&b)[4], unsigned mask, double ridge,
                                            const double *prior, double (&c)[4])
 {
-    int idx[4], m = 0;
+    double A[4][4], r[4], sc[4];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool si = (mask >> i) & 1u;
+        const double d = si ? G[i][i] + ridge : 1.0;
+        ok = ok && (d > 0.0);
+        sc[i] = si ? 1.0 / sqrt(d > 0.0 ? d : 1.0) : 1.0;
+        r[i] = si ? (b[i] + (prior ? ridge * prior[i] : 0.0)) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool sel = ((mask >> i) & 1u) && ((mask >> j) & 1u);
+            const double g = G[i][j] + ((i == j) ? ridge : 0.0);
+            A[i][j] = sel ? g * sc[i] * sc[j] : ((i == j) ? 1.0 : 0.0);
+        }
+        r[i] *= sc[i];
+    }
+    // Cholesky A = L L^T, lower triangle in place
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
-        c[j] = 0.0;
-        if (mask & (1u << j)) idx[m++] = j;
-    }
-    if (m == 0) return true;
-    double A[4][4], r[4], s[4];
-    for (int i = 0; i < m; ++i) {
-        for (int j = 0; j < m; ++j) A[i][j] = G[idx[i]][idx[j]];
-        A[i][i] += ridge;
-        r[i] = b[idx[i]] + (prior ? ridge * prior[idx[i]] : 0.0);
-    }
-    for (int i = 0; i < m; ++i) {
-        if (!(A[i][i] > 0.0)) return false;
-        s[i] = 1.0 / sqrt(A[i][i]);
-    }
-    for (int i = 0; i < m; ++i) {
-        for (int j = 0; j < m; ++j) A[i][j] *= s[i] * s[j];
-        r[i] *= s[i];
-    }
-    // Cholesky A = L L^T (lower triangle in place)
-    for (int j = 0; j < m; ++j) {
         double d = A[j][j];
+#pragma unroll
         for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
-        if (!(d > 0.0)) return false;
-        d = sqrt(d);
+        ok = ok && (d > 0.0);
+        d = sqrt(d > 0.0 ? d : 1.0);
         A[j][j] = d;
-        for (int i = j + 1; i < m; ++i) {
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
             double v = A[i][j];
+#pragma unroll
             for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k];
             A[i][j] = v / d;
         }
     }
     double y[4];
-    for (int i = 0; i < m; ++i) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
         double v = r[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) v -= A[i][k] * y[k];
         y[i] = v / A[i][i];
     }
-    for (int i = m - 1; i >= 0; --i) {
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
         double v = y[i];
-        for (int k = i + 1; k < m; ++k) v -= A[k][i] * y[k];
+#pragma unroll
+        for (int k = i + 1; k < 4; ++k) v -= A[k][i] * y[k];
         y[i] = v / A[i][i];
     }
-    for (int i = 0; i < m; ++i) c[idx[i]] = y[i] * s[i];
-    return true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = ((mask >> i) & 1u) ? y[i] * sc[i] : 0.0;
+    return ok;
 }
 
 // full STLSQ + unbias on one 4-feature problem.  Returns the final support mask.

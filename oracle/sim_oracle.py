@@ -144,3 +144,48 @@ def scaling_params(sim):
     means['patient_types'] = np.mean(sim['patient_types'])
     stds['patient_types'] = np.std(sim['patient_types'])
     return means, stds
+
+
+def theta_gram(sim, static_feature, dt=10.0 / 60):
+    """Normal equations of the population fit in long double (C): (G (4,4,4), b (4,4), counts (4,))."""
+    L = lib()
+    vol = _f64(sim['cancer_volume'])
+    n, T = vol.shape
+    G, b, cnt = np.zeros((4, 4, 4)), np.zeros((4, 4)), np.zeros(4)
+    L.oracle_theta_gram(ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_double(dt), _p(vol),
+                        _p(_f64(sim['chemo_application'])), _p(_f64(sim['radio_application'])),
+                        _p(_f64(sim['sequence_lengths'])), _p(_f64(static_feature)), _p(G), _p(b), _p(cnt))
+    return G, b, cnt
+
+
+def stlsq_from_gram(G, b, threshold=1e-3, alpha=0.5, max_iter=100):
+    """pysindy STLSQ + unbias on normal equations (same loop as sindy_np.stlsq_fit; the ridge step is
+    what sklearn's 'cholesky' solver computes: solve(G + alpha I, b))."""
+    coefs, sup = np.zeros((4, 4)), np.zeros((4, 4), dtype=bool)
+    for a in range(4):
+        ind = np.ones(4, dtype=bool)
+        prev = np.ones(4, dtype=bool)
+        n0 = 4
+        c = np.zeros(4)
+        if G[a, 0, 0] == 0:
+            continue
+        for _ in range(max_iter):
+            if not ind.any():
+                c = np.zeros(4)
+                break
+            ci = np.linalg.solve(G[a][np.ix_(ind, ind)] + alpha * np.eye(ind.sum()), b[a][ind])
+            c = np.zeros(4)
+            c[ind] = ci
+            big = np.abs(c) >= threshold
+            c[~big] = 0
+            ind = big
+            pattern = c != 0
+            same = np.array_equal(pattern, prev)
+            prev = pattern
+            if ind.sum() == n0 or same:
+                break
+        if ind.any():
+            c = np.zeros(4)
+            c[ind] = np.linalg.solve(G[a][np.ix_(ind, ind)], b[a][ind])
+        coefs[a], sup[a] = c, ind
+    return coefs, sup

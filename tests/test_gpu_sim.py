@@ -1,0 +1,223 @@
+"""GPU parity tests of the simulators (K1, K2, K3) against the oracle and the reference fixtures.
+
+Tolerances (BASELINE.json north_star): treatment assignments, flags, sequence lengths and row counts
+bit-exact; float64 trajectories within 1e-6 relative -- asserted here at 1e-9 (measured ~1e-13)."""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_RTOL = 1e-9
+EXACT_F = ('chemo_application', 'radio_application', 'radio_dosage', 'death_flags', 'recovery_flags',
+           'sequence_lengths')
+FLOAT_F = ('cancer_volume', 'chemo_dosage', 'chemo_probabilities', 'radio_probabilities')
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from b200_insite import device
+    device.require_cuda()
+    return device
+
+
+def _run_factual(dev, params, draws, T=60, variant=0, assigned=None, fused=False):
+    import torch
+    pd_ = dev.to_device(dev.pack_params(params))
+    static = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64)) if fused else None
+    aa = None if assigned is None else dev.to_device(assigned)
+    consts = dev.sim_consts(params['window_size'], params['lag'])
+    out, stats = dev.sim_factual(pd_, dev.to_device(draws['noise']), dev.to_device(draws['recovery']),
+                                 dev.to_device(draws['chemo']), dev.to_device(draws['radio']), T, consts,
+                                 assigned_actions=aa, variant=variant, fused_static=static)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}, (stats.cpu().numpy() if stats is not None else None)
+
+
+def _check_factual(got, ref, tag):
+    for k in EXACT_F:
+        assert np.array_equal(got[k], ref[k]), f"{tag}: {k} not bit-exact ({np.count_nonzero(got[k] != ref[k])} diffs)"
+    for k in FLOAT_F:
+        np.testing.assert_allclose(got[k], ref[k], rtol=FLOAT_RTOL, atol=1e-13, err_msg=f"{tag}: {k}")
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_factual_variants_match_oracle(dev, variant):
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(3000, seed=5)   # ragged: last tile partial for every tile size
+    ref = so.sim_factual(params, 60, draws)
+    got, _ = _run_factual(dev, params, draws, variant=variant)
+    _check_factual(got, ref, f"variant {variant}")
+
+
+def test_factual_matches_reference_fixture(dev):
+    """Reference outputs themselves (tests/golden/ref_sim_small.npz), reference RNG order."""
+    g = h.load_npz('ref_sim_small.npz')
+    inputs = h.collection_inputs(7, 2.0, 192, 24, 24)
+    for name in ('train', 'val'):
+        got, _ = _run_factual(dev, *inputs[name])
+        ref = {k: g[f'{name}/out/{k}'] for k in EXACT_F + FLOAT_F}
+        _check_factual(got, ref, name)
+
+
+def test_factual_dropin_consumes_global_rng_like_reference(dev):
+    import b200_insite.cancer_simulation as cs
+    g = h.load_npz('ref_sim_small.npz')
+    np.random.seed(7)
+    p = cs.generate_params(192, 2.0, 2.0, 15, 0)
+    out = cs.simulate_factual(p, 60)
+    assert set(out) == {'cancer_volume', 'chemo_dosage', 'radio_dosage', 'chemo_application', 'radio_application',
+                        'chemo_probabilities', 'radio_probabilities', 'sequence_lengths', 'death_flags',
+                        'recovery_flags', 'patient_types'}
+    _check_factual(out, {k: g[f'train/out/{k}'] for k in EXACT_F + FLOAT_F}, 'drop-in train')
+    p2 = cs.generate_params(24, 2.0, 2.0, 15, 0)     # RNG stream continues: validation subset matches too
+    out2 = cs.simulate_factual(p2, 60)
+    _check_factual(out2, {k: g[f'val/out/{k}'] for k in EXACT_F + FLOAT_F}, 'drop-in val')
+    m, s = cs.get_scaling_params(out)
+    np.testing.assert_allclose(m.values, g['train/scaling_means'], rtol=1e-12)
+    np.testing.assert_allclose(s.values, g['train/scaling_stds'], rtol=1e-12)
+
+
+def test_factual_gamma10_and_assigned_actions_fixture(dev):
+    from oracle import rng_export as rx
+    g = h.load_npz('ref_sim_gamma10.npz')
+    np.random.seed(100)
+    p = rx.generate_params(128, 10.0, 10.0, 15, 0)
+    d = rx.draw_factual(128, 60)
+    got, _ = _run_factual(dev, p, d)
+    _check_factual(got, {k: g[f'out/{k}'] for k in EXACT_F + FLOAT_F}, 'gamma10')
+    d2 = rx.draw_factual(128, 60)
+    got2, _ = _run_factual(dev, p, d2, assigned=g['assigned_actions'])
+    _check_factual(got2, {k: g[f'out_assigned/{k}'] for k in EXACT_F + FLOAT_F}, 'assigned_actions')
+
+
+@pytest.mark.parametrize("n,T,window", [(1, 60, 15), (127, 60, 15), (129, 60, 15), (700, 30, 15), (333, 61, 15),
+                                        (500, 60, 7), (64, 4, 15)])
+def test_factual_edge_shapes(dev, n, T, window):
+    """Single patient, tile boundaries, short / odd horizons (odd T -> generic kernel), short window."""
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(n, seed=n + T, T=T)
+    params['window_size'] = window
+    ref = so.sim_factual(params, T, draws)
+    got, _ = _run_factual(dev, params, draws, T=T)
+    _check_factual(got, ref, f"n={n} T={T} w={window}")
+
+
+def test_factual_empty_cohort_and_bad_config(dev):
+    import torch
+    params, draws = h.random_cohort(4, seed=1)
+    for k in h.PARAM_KEYS:
+        params[k] = params[k][:0]
+    draws = {k: v[:0] for k, v in draws.items()}
+    got, _ = _run_factual(dev, params, draws)
+    assert got['cancer_volume'].shape == (0, 60)
+    params, draws = h.random_cohort(4, seed=1)
+    params['lag'] = 1
+    with pytest.raises(RuntimeError, match="lag"):
+        _run_factual(dev, params, draws)
+
+
+def test_factual_large_cohort_properties(dev):
+    """1M patients (BASELINE config C2 size): oracle parity on a strided sample + structural properties."""
+    import torch
+    from oracle import sim_oracle as so
+    n, T = 1_000_000, 60
+    params, draws = h.random_cohort(n, seed=2024)
+    got, _ = _run_factual(dev, params, draws)
+    sl = got['sequence_lengths'].astype(np.int64)
+    cols = np.arange(T)[None, :]
+    assert sl.min() >= 2 and sl.max() == T - 1
+    # nothing after the last simulated step, treatment never at t = 0, flags only at the last step
+    for k in ('cancer_volume', 'chemo_dosage', 'radio_dosage', 'chemo_application', 'radio_application',
+              'chemo_probabilities', 'radio_probabilities'):
+        assert not np.any(got[k][cols >= sl[:, None]]), k
+    assert not got['chemo_application'][:, 0].any() and not got['radio_application'][:, 0].any()
+    assert np.array_equal(got['radio_dosage'], 2.0 * got['radio_application'])
+    ended = got['death_flags'].sum(1) + got['recovery_flags'].sum(1)
+    assert np.array_equal(ended > 0, sl < T - 1) or np.all((ended > 0) <= (sl <= T - 1))
+    assert got['cancer_volume'].max() <= 1150.3465099894624
+    # chemo dosage recursion C[t] = C[t-1]/2 + 5*app[t] holds exactly
+    C, A = got['chemo_dosage'], got['chemo_application']
+    act = cols[:, 1:] < sl[:, None]
+    assert np.array_equal((C[:, 1:] == C[:, :-1] * 0.5 + 5.0 * A[:, 1:]) | ~act, np.ones_like(act))
+    # oracle on every 97th patient
+    idx = np.arange(0, n, 97)
+    sub_p = {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in params.items()}
+    sub_d = {k: v[idx] for k, v in draws.items()}
+    ref = so.sim_factual(sub_p, T, sub_d)
+    _check_factual({k: v[idx] for k, v in got.items()}, ref, "1M sample")
+
+
+# ---------------------------------------------------------------------------------------------------
+# counterfactual generators
+# ---------------------------------------------------------------------------------------------------
+CF1_EXACT = ('chemo_application', 'radio_application', 'sequence_lengths', 'patient_types')
+CFS_EXACT = CF1_EXACT + ('patient_ids_all_trajectories', 'patient_current_t')
+
+
+def _run_cf(dev, kind, params, draws, T=60, H=5):
+    from b200_insite import counterfactual as cf
+    d = (draws['noise'], draws['recovery'], draws['chemo'], draws['radio'])
+    if kind == 'one':
+        return cf.one_step_dense(params, T, d)
+    return cf.treatment_seq_dense(params, T, H, d)
+
+
+def _check_cf(got, ref, exact, tag):
+    assert got['cancer_volume'].shape == ref['cancer_volume'].shape, f"{tag}: row count"
+    for k in exact:
+        assert np.array_equal(got[k], ref[k]), f"{tag}: {k} not bit-exact"
+    np.testing.assert_allclose(got['cancer_volume'], ref['cancer_volume'], rtol=FLOAT_RTOL, atol=1e-12,
+                               err_msg=f"{tag}: cancer_volume")
+
+
+def test_cf_generators_match_reference_fixture(dev):
+    g = h.load_npz('ref_sim_small.npz')
+    inputs = h.collection_inputs(7, 2.0, 192, 24, 24)
+    got = _run_cf(dev, 'one', *inputs['one'])
+    _check_cf(got, {k: g[f'one/out/{k}'] for k in CF1_EXACT + ('cancer_volume',)}, CF1_EXACT, 'one-step fixture')
+    got = _run_cf(dev, 'seq', *inputs['seq'])
+    _check_cf(got, {k: g[f'seq/out/{k}'] for k in CFS_EXACT + ('cancer_volume',)}, CFS_EXACT, 'treatment-seq fixture')
+
+
+@pytest.mark.parametrize("n,seed", [(1, 3), (2, 4), (100, 1), (400, 9), (1500, 21)])
+def test_cf_one_step_matches_oracle_across_wavefront_levels(dev, n, seed):
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(n, seed=seed)
+    ref = so.sim_cf_one_step(params, 60, draws)
+    got = _run_cf(dev, 'one', params, draws)
+    _check_cf(got, ref, CF1_EXACT, f"one-step n={n}")
+
+
+@pytest.mark.parametrize("n,seed", [(1, 3), (3, 4), (100, 1), (700, 9)])
+def test_cf_treatment_seq_matches_oracle_across_wavefront_levels(dev, n, seed):
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(n, seed=seed, extra=5)
+    ref = so.sim_cf_treatment_seq(params, 60, 5, draws)
+    got = _run_cf(dev, 'seq', params, draws)
+    _check_cf(got, ref, CFS_EXACT, f"treatment-seq n={n}")
+
+
+def test_cf_dropin_entry_points_seed1_digests(dev):
+    """Log configuration through the drop-in entry points (global RNG): row counts and the bit-exact
+    arrays must reproduce the sha256 digests of the reference outputs."""
+    import hashlib
+    import b200_insite.cancer_simulation as cs
+    dig = h.load_json('ref_digests_seed1.json')
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    np.random.seed(1)
+    train = cs.simulate_factual(cs.generate_params(1000, 2.0, 2.0, 15, 0), 60)
+    val = cs.simulate_factual(cs.generate_params(100, 2.0, 2.0, 15, 0), 60)
+    one = cs.simulate_counterfactual_1_step(cs.generate_params(100, 2.0, 2.0, 15, 0), 60)
+    seq = cs.simulate_counterfactuals_treatment_seq(cs.generate_params(100, 2.0, 2.0, 15, 0), 60, 5)
+    for name, d in (('train', train), ('val', val), ('one', one), ('seq', seq)):
+        assert d['cancer_volume'].shape[0] == dig[name]['rows'], name
+        for k in ('chemo_application', 'radio_application', 'sequence_lengths'):
+            assert sha(d[k]) == dig[name]['out_sha256'][k], (name, k)
+        assert abs(d['cancer_volume'].sum() - dig[name]['cancer_volume_sum']) <= 1e-9 * abs(dig[name]['cancer_volume_sum'])
+    with pytest.raises(NotImplementedError):
+        cs.simulate_counterfactuals_treatment_seq(cs.generate_params(4, 2.0, 2.0, 15, 0), 60, 5, 'random_trajectories')

@@ -1,0 +1,152 @@
+"""CPU tests: the oracle against the reference's golden vectors (no GPU, no /root/reference needed).
+
+Fixtures in tests/golden/ were produced by oracle/make_golden.py from the UNMODIFIED reference."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import rng_export as rx
+from oracle import sim_oracle as so
+from oracle import sindy_np as sp
+from oracle.ref_loader import reference_available
+
+import helpers as h
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_np_mean_matches_numpy_bitwise():
+    rng = np.random.RandomState(0)
+    for _ in range(3000):
+        n = rng.randint(1, 40)
+        a = rng.rand(n) * 10 ** rng.uniform(-3, 3, size=n)
+        assert np.array(list(a)).mean() == so.np_mean(a)
+
+
+@pytest.fixture(scope="module")
+def small():
+    return h.load_npz('ref_sim_small.npz')
+
+
+@pytest.fixture(scope="module")
+def small_inputs():
+    return h.collection_inputs(7, 2.0, 192, 24, 24)
+
+
+def test_rng_replay_reproduces_reference_params(small, small_inputs):
+    for name in ('train', 'val', 'one', 'seq'):
+        p = small_inputs[name][0]
+        for k in h.PARAM_KEYS:
+            assert np.array_equal(p[k], small[f'{name}/params/{k}']), (name, k)
+        assert np.array_equal(p['initial_stages'], small[f'{name}/params/initial_stages'])
+
+
+def test_c_oracle_matches_reference_small(small, small_inputs):
+    o = h.oracle_collection(small_inputs)
+    exact = {'train': ['cancer_volume', 'chemo_dosage', 'radio_dosage', 'chemo_application', 'radio_application',
+                       'sequence_lengths', 'death_flags', 'recovery_flags'],
+             'one': ['chemo_application', 'radio_application', 'sequence_lengths', 'patient_types'],
+             'seq': ['chemo_application', 'radio_application', 'sequence_lengths', 'patient_types',
+                     'patient_ids_all_trajectories', 'patient_current_t']}
+    exact['val'] = exact['train']
+    for name, keys in exact.items():
+        for k in keys:
+            assert np.array_equal(o[name][k], small[f'{name}/out/{k}']), (name, k)
+    # floats that go through numpy's SIMD exp/log differ from libm by <= a few ulp
+    for name, k in (('train', 'chemo_probabilities'), ('train', 'radio_probabilities'), ('one', 'cancer_volume'),
+                    ('seq', 'cancer_volume')):
+        assert o[name][k].shape == small[f'{name}/out/{k}'].shape
+        np.testing.assert_allclose(o[name][k], small[f'{name}/out/{k}'], rtol=1e-13, atol=1e-15)
+
+
+def test_scaling_params_match_reference(small, small_inputs):
+    o = so.sim_factual(small_inputs['train'][0], 60, small_inputs['train'][1])
+    means, stds = so.scaling_params(o)
+    order = ['cancer_volume', 'chemo_dosage', 'radio_dosage', 'patient_types']
+    assert [means[k] for k in order] == list(small['train/scaling_means'])
+    assert [stds[k] for k in order] == list(small['train/scaling_stds'])
+
+
+def test_c_oracle_gamma10_and_assigned_actions():
+    g = h.load_npz('ref_sim_gamma10.npz')
+    np.random.seed(100)
+    p = rx.generate_params(128, 10.0, 10.0, 15, 0)
+    d = rx.draw_factual(128, 60)
+    for k in h.PARAM_KEYS:
+        assert np.array_equal(p[k], g[f'params/{k}'])
+    o = so.sim_factual(p, 60, d)
+    for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'death_flags',
+              'recovery_flags', 'chemo_dosage'):
+        assert np.array_equal(o[k], g[f'out/{k}']), k
+    d2 = rx.draw_factual(128, 60)
+    o2 = so.sim_factual(p, 60, d2, assigned_actions=g['assigned_actions'])
+    for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'chemo_probabilities'):
+        assert np.array_equal(o2[k], g[f'out_assigned/{k}']), k
+
+
+@pytest.fixture(scope="module")
+def seed1():
+    inputs = h.collection_inputs(1, 2.0, 1000, 100, 100)
+    return inputs, h.oracle_collection(inputs)
+
+
+def test_seed1_digests(seed1):
+    """Log configuration (seed 1, gamma 2, 1000/100/100): bit-exact arrays vs sha256 of the reference."""
+    inputs, o = seed1
+    dig = h.load_json('ref_digests_seed1.json')
+    for name in ('train', 'val', 'one', 'seq'):
+        for k in h.PARAM_KEYS:
+            assert _digest(inputs[name][0][k]) == dig[name]['params_sha256'][k], (name, k)
+        assert o[name]['cancer_volume'].shape[0] == dig[name]['rows']
+        for k in ('chemo_application', 'radio_application', 'sequence_lengths'):
+            assert _digest(o[name][k]) == dig[name]['out_sha256'][k], (name, k)
+    assert dig['one']['rows'] == 22748 and dig['seq']['rows'] == 56239
+    for k in ('cancer_volume', 'chemo_dosage', 'radio_dosage', 'death_flags', 'recovery_flags'):
+        assert _digest(o['train'][k]) == dig['train']['out_sha256'][k], k
+    assert _digest(o['one']['cancer_volume']) == dig['one']['out_sha256']['cancer_volume']
+    assert abs(o['seq']['cancer_volume'].sum() - dig['seq']['cancer_volume_sum']) < 1e-6
+
+
+def test_population_fit_and_metrics_reproduce_reference_log(seed1):
+    """Known-answer test: results/2_main_table/final_with_insite.txt:6 of the reference."""
+    _, o = seed1
+    log = h.load_json('ref_log_seed1.json')['sindy']
+    means, stds = so.scaling_params(o['train'])
+    dtr, sc = sp.process_data(o['train'], means, stds)
+    coefs, sup, stats = sp.fit_population(dtr, sc)
+    np.testing.assert_allclose(coefs, np.array(log['coefs']), rtol=1e-10)
+    assert sup.all()
+    assert [s[1] for s in stats] == [42092, 20567, 20850, 10471]
+    d1, _ = sp.process_data(o['one'], means, stds)
+    orig, all_, last = sp.masked_rmse(sp.predictions_population(d1, sc, coefs), d1, sc)
+    np.testing.assert_allclose([all_, orig, last], [log['encoder_test_rmse_all'], log['encoder_test_rmse_orig'],
+                                                    log['encoder_test_rmse_last']], rtol=1e-11)
+    d2, _ = sp.process_data(o['seq'], means, stds)
+    d2s = sp.process_sequential_test(d2, sc, 5)
+    ps = sp.slice_autoregressive(sp.predictions_population(d2, sc, coefs), d2['sequence_lengths'], 5)
+    np.testing.assert_allclose(sp.n_step_rmses(ps, d2s, sc), log['decoder_test_rmse_2_to_6_step'], rtol=1e-11)
+    assert sp.equation_string(coefs).startswith('Treatment 0: x_dot = +-0.0560145608')
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (GPU box)")
+def test_oracle_against_live_reference():
+    """In the build container the unmodified reference is importable: compare directly."""
+    import warnings
+    from oracle.ref_loader import load_reference_sim
+    warnings.filterwarnings('ignore')
+    m = load_reference_sim()
+    np.random.seed(3)
+    p = m.generate_params(40, 2.0, 2.0, 15, 0)
+    st = np.random.get_state()
+    ref = m.simulate_counterfactuals_treatment_seq(p, 60, 5)
+    np.random.set_state(st)
+    d = rx.draw_cf(40, 60, 5)
+    o = so.sim_cf_treatment_seq(p, 60, 5, d)
+    assert o['cancer_volume'].shape == ref['cancer_volume'].shape
+    for k in ('chemo_application', 'radio_application', 'sequence_lengths', 'patient_ids_all_trajectories',
+              'patient_current_t'):
+        assert np.array_equal(o[k], ref[k]), k
+    np.testing.assert_allclose(o['cancer_volume'], ref['cancer_volume'], rtol=1e-13, atol=1e-15)
