@@ -14,6 +14,10 @@ warnings.filterwarnings('ignore')
 from b200_insite import device as dev
 
 
+VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '2,5,10,11,12,13,14').split(',')]
+FUSED = [bool(int(v)) for v in os.environ.get('FUSED', '0').split(',')]
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -37,8 +41,8 @@ def main():
     out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
     bytes_alg = n * (4 * T * 8 + 9 * T * 8 + 10 * 8 + 8)
     res = []
-    for fused in (False, True):
-        for variant in (2, 3, 4, 5, 6, 7, 8, 9, 1):
+    for fused in FUSED:
+        for variant in VARIANTS:
             try:
                 for _ in range(2):
                     dev.sim_factual(params, noise, rec, chemo, radio, T, out=out, variant=variant,
