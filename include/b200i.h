@@ -228,6 +228,39 @@ B200I_API int b200i_expand_cf_treatment_seq(int64_t n, int32_t T, int32_t H, con
                                   double *patient_types_rows, double *patient_ids, double *patient_current_t,
                                   void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Individualisation of the population ODE.  Row interface shared by both estimators:
+ *   x (R,W) float64       un-scaled prev_outputs of the processed dataset (sindy.py:555-556)
+ *   codes (R,W) uint8     treatment index per step = argmax of the one-hot current_treatments
+ *                         (chemo + 2*radio; sindy.py:499)
+ *   the fit window of a row is its first n_fit = sequence_length - projection_horizon transitions
+ *   x[k] -> x[k+1] (mask of f_to_min_func, sindy.py:786)
+ *   output coefs (R,4,4): per-row coefficient matrix for b200i_ode_rollout(coefs_per_row = 1)
+ *
+ * K5b b200i_stlsq_batched: per row and treatment, sequentially thresholded ridge regression shrunk to
+ *   the population coefficients on the population support:
+ *     repeat { c = argmin (1/n)|Theta c - xdot|^2 + lam |c - prior|^2 on the support; drop |c| < threshold }
+ *   (normal equations from the same snippet / finite-difference / library rules as b200i_theta_gram; 4x4
+ *   Cholesky in registers).  Support = |prior| > support_tol.  Treatments that do not occur in the window
+ *   keep the prior.  fit_len (R,) int32 = n_fit, already clamped by the caller to [0, W-1].
+ *   Lineage: determine_individualized_equation_coefs, pkpd_simulation.py:791-836 (dormant in the reference).
+ *
+ * K7 b200i_insite_bfgs: the reference's live estimator, _fine_tuning_inner (sindy.py:587-631) with
+ *   f_to_min_func (:781-794): BFGS (strong-Wolfe line search) over all 16 coefficients from theta0.
+ *   Rows with sequence_length <= projection_horizon keep theta0 (:571-585).
+ *   status_out (R,) int32: low byte 0 converged / 1 max_iter / 3,5 line search exhausted / 4 perfect start /
+ *   6 no improvement (theta0 kept) / -2 skipped; bits 8.. = BFGS iterations.  fval_out (R,2) = objective at
+ *   theta0 and at the returned coefficients.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const double *x, const uint8_t *codes,
+                        const int32_t *fit_len, const double *static_feature, const double *prior,
+                        double support_tol, double lam, double threshold, int32_t max_iter,
+                        double *coefs_out, void *stream);
+B200I_API int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
+                      const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
+                      const double *static_feature, const double *theta0, double lam, double gtol,
+                      int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,398 @@
+// insite_fit.cu -- individualisation of the population ODE (the "I" of INSITE).
+//
+// Two estimators behind the same row interface (x = un-scaled prev_outputs (R,W), treatment codes
+// (R,W), fit window = the first n_fit = sequence_length - projection_horizon transitions of the row,
+// as create_mask(...) in f_to_min_func, sindy.py:786):
+//
+//  K5b  b200i_stlsq_batched   -- batched per-row sequentially-thresholded ridge regression shrunk to
+//       the population coefficients on the population support (the BASELINE north-star estimator;
+//       lineage: the reference's dormant per-patient STLSQ with warm start, pkpd_simulation.py:791-836
+//       + LSQIntialMask, pkpd/utils.py:96-335).  One thread per row, 4x4 Cholesky in registers.
+//
+//  K7   b200i_insite_bfgs     -- the reference's live path (sindy.py:587-631, 781-794): BFGS over the
+//       16 coefficients of  mean_{k<n_fit}(x[k+1]-xhat[k+1](theta*mask))^2 / (2.5*mse(theta0))
+//       + lam*mean((theta-theta0)^2), xhat = open-loop Euler rollout (5 sub-steps per interval).
+//       16 lanes per row: lane j owns coefficient j, its forward sensitivity d xhat / d theta_j and
+//       row j of the inverse-Hessian approximation; dot products and mat-vecs go through half-warp
+//       shuffles.  Line search: strong Wolfe (c1=1e-4, c2=0.9) with bracketing + zoom as in
+//       jax.scipy.optimize / scipy (Nocedal & Wright alg. 3.5/3.6).  jax's iterate-level behaviour
+//       (in particular how its line search fails at the FP64 noise floor) is NOT pinned: see DESIGN.md.
+#include "sim_math.cuh"
+#include "stlsq.cuh"
+
+namespace b200i {
+
+// ------------------------------------------------------------------------------------------------
+// K5b
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
+                     const int *__restrict__ fit_len, const double *__restrict__ static_u,
+                     const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
+                     double *__restrict__ coefs_out)
+{
+    __shared__ double s_prior[16];
+    if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int n = fit_len[r];
+    if (n > W - 1) n = W - 1;
+    const double u = static_u[r];
+    const double *xr = x + r * W;
+    const uint8_t *cr = codes + r * W;
+    PatientGram pg;
+    pg.clear();
+    if (n > 0) {
+        double x0 = xr[0];
+        int a0 = cr[0] & 3;
+        for (int k = 0; k < n; ++k) {
+            const double x1 = xr[k + 1];
+            const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
+            const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+            pg.add(a0, x0, xdot);
+            if (k == n - 1 || a1 != a0) pg.add(a0, x1, xdot);
+            x0 = x1;
+            a0 = a1;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double g15[B200I_GRAM_PER_TREATMENT], G[4][4], b[4], c[4], pr[4];
+        expand_gram(pg.s[a], u, g15);
+        unsigned ind = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            pr[j] = s_prior[a * 4 + j];
+            if (fabs(pr[j]) > support_tol) ind |= 1u << j;
+        }
+        const double cnt = g15[14];
+        if (cnt > 0.0 && ind != 0) {
+            const double inv = 1.0 / cnt;   // mean-normalised normal equations
+#pragma unroll
+            for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) g15[j] *= inv;
+            unpack_gram(g15, G, b);
+            for (int it = 0; it < max_iter; ++it) {
+                if (!solve_spd4(G, b, ind, lam, pr, c)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[j] = ((ind >> j) & 1u) ? pr[j] : 0.0;
+                    break;
+                }
+                unsigned big = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((ind >> j) & 1u) && fabs(c[j]) >= threshold) big |= 1u << j;
+                if (big == ind) break;
+                ind = big;
+                if (ind == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[j] = 0.0;
+                    break;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = pr[j];   // treatment never observed in the window: keep the prior
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) coefs_out[r * 16 + a * 4 + j] = c[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: cooperative BFGS, 16 lanes per row
+// ------------------------------------------------------------------------------------------------
+constexpr int BFGS_THREADS = 128;
+constexpr int BFGS_GROUPS = BFGS_THREADS / 16;
+constexpr int BFGS_MAXW = 80;
+
+struct RowData {
+    const double *x;       // shared memory: x[0..n_fit]
+    const uint8_t *codes;  // shared memory: codes[0..n_fit-1]
+    int n_fit;
+    double u, h, norm, lam;
+    int substeps;
+};
+
+__device__ __forceinline__ double shfl16(double v, int src, unsigned mask, int base)
+{
+    return __shfl_sync(mask, v, base + src);
+}
+__device__ __forceinline__ double sum16(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+__device__ __forceinline__ double max16(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+
+// objective and gradient component of this lane: f_to_min_func (sindy.py:781-794) with forward
+// sensitivities through the Euler rollout (predict_with_reduced_coefs :767-778, odeint pkpd/utils.py:68-90)
+__device__ __forceinline__ void eval_objective(const RowData &d, double theta, double theta0, double mask_j, int my_a,
+                                               int my_m, unsigned gmask, int gbase, double &f, double &g)
+{
+    const double tm = theta * mask_j;
+    double v = d.x[0], s = 0.0, acc = 0.0, gacc = 0.0;
+    for (int k = 0; k < d.n_fit; ++k) {
+        const int a = d.codes[k] & 3;
+        const double c0 = shfl16(tm, 4 * a + 0, gmask, gbase), c1 = shfl16(tm, 4 * a + 1, gmask, gbase);
+        const double c2 = shfl16(tm, 4 * a + 2, gmask, gbase), c3 = shfl16(tm, 4 * a + 3, gmask, gbase);
+        const double c2u = c2 * d.u, dfdv = c1 + c3 * d.u;
+        const bool mine = (a == my_a);
+        for (int q = 0; q < d.substeps; ++q) {
+            const double vu = v * d.u;
+            const double fval = ((c0 + c1 * v) + c2u) + c3 * vu;
+            const double basis = my_m == 0 ? 1.0 : (my_m == 1 ? v : (my_m == 2 ? d.u : vu));
+            const double dfj = mine ? basis * mask_j : 0.0;
+            s = s + d.h * (dfdv * s + dfj);
+            v = v + d.h * fval;
+        }
+        const double r = d.x[k + 1] - v;
+        acc += r * r;
+        gacc += -2.0 * r * s;
+    }
+    const double inv = 1.0 / (double)d.n_fit;
+    const double diff = theta - theta0;
+    const double pen = sum16(diff * diff, gmask) * (1.0 / 16.0);
+    f = acc * inv / d.norm + d.lam * pen;
+    g = gacc * inv / d.norm + d.lam * 2.0 * diff * (1.0 / 16.0);
+}
+
+// minimiser of the cubic through (a,fa,fpa), (b,fb), (c,fc); NaN if it does not exist (scipy _cubicmin)
+__device__ __forceinline__ double cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc)
+{
+    const double C = fpa, db = b - a, dc = c - a;
+    const double denom = (db * dc) * (db * dc) * (db - dc);
+    if (denom == 0.0) return nan("");
+    const double t0 = fb - fa - C * db, t1 = fc - fa - C * dc;
+    double A = (dc * dc * t0 - db * db * t1) / denom;
+    double B = (-dc * dc * dc * t0 + db * db * db * t1) / denom;
+    const double radical = B * B - 3.0 * A * C;
+    if (!(radical >= 0.0) || A == 0.0) return nan("");
+    return a + (-B + sqrt(radical)) / (3.0 * A);
+}
+__device__ __forceinline__ double quadmin(double a, double fa, double fpa, double b, double fb)
+{
+    const double db = b - a;
+    const double B = (fb - fa - fpa * db) / (db * db);
+    if (!(B > 0.0)) return nan("");
+    return a - fpa / (2.0 * B);
+}
+
+__global__ void __launch_bounds__(BFGS_THREADS)
+insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x,
+                   const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
+                   const double *__restrict__ static_u, const double *__restrict__ theta0_g, double lam, double gtol,
+                   int max_iter, double *__restrict__ coefs_out, int *__restrict__ status_out,
+                   double *__restrict__ fval_out)
+{
+    __shared__ double s_x[BFGS_GROUPS][BFGS_MAXW + 1];
+    __shared__ uint8_t s_c[BFGS_GROUPS][BFGS_MAXW];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 4, j = threadIdx.x & 15;
+    const int gbase = lane & 16;
+    const unsigned gmask = 0xFFFFu << gbase;
+    const int my_a = j >> 2, my_m = j & 3;
+    const double theta0 = theta0_g[j];
+    const double mask_j = fabs(theta0) > 1e-3 ? 1.0 : 0.0;   // coef_sparse_mask, sindy.py:589
+    const int64_t ngroups = (int64_t)gridDim.x * BFGS_GROUPS;
+    const int64_t iters = (rows + ngroups - 1) / ngroups;
+
+    for (int64_t itr = 0; itr < iters; ++itr) {
+        const int64_t r = itr * ngroups + (int64_t)blockIdx.x * BFGS_GROUPS + grp;
+        const bool valid = r < rows;
+        int n_fit = 0;
+        if (valid) {
+            n_fit = seq_len[r] - ph;
+            if (n_fit > W - 1) n_fit = W - 1;
+        }
+        __syncwarp(gmask);
+        if (valid && n_fit > 0) {
+            for (int k = j; k <= n_fit; k += 16) s_x[grp][k] = x[r * W + k];
+            for (int k = j; k < n_fit; k += 16) s_c[grp][k] = codes[r * W + k];
+        }
+        __syncwarp(gmask);
+        if (!valid) continue;
+        if (n_fit <= 0) {   // sequence_length <= projection_horizon: population coefficients (sindy.py:571-585)
+            coefs_out[r * 16 + j] = theta0;
+            if (j == 0) { status_out[r] = -2; fval_out[2 * r] = 0.0; fval_out[2 * r + 1] = 0.0; }
+            continue;
+        }
+        RowData d;
+        d.x = s_x[grp]; d.codes = s_c[grp]; d.n_fit = n_fit; d.u = static_u[r];
+        d.h = dt / substeps; d.substeps = substeps; d.norm = 1.0; d.lam = lam;
+
+        double theta = theta0, f, g;
+        eval_objective(d, theta, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+        const double start_res = f;                 // norm_const = 1 (sindy.py:591-603)
+        d.norm = 2.5 * start_res;                   // sindy.py:616
+        int status = 0, it = 0;
+        double f0 = 0.0;
+        if (!(d.norm > 0.0) || !isfinite(d.norm)) {
+            status = 4;                             // perfect fit already (or non-finite): keep theta0
+        } else {
+            eval_objective(d, theta, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+            f0 = f;
+            double Hrow[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Hrow[i] = (i == j) ? 1.0 : 0.0;
+            double old_old = f + sqrt(sum16(g * g, gmask)) * 0.5;   // jax: f_0 + ||g_0|| / 2
+            for (it = 0; it < max_iter; ++it) {
+                if (max16(fabs(g), gmask) < gtol) { status = 0; break; }
+                // p = -H g
+                double p = 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) p -= Hrow[i] * shfl16(g, i, gmask, gbase);
+                double dphi0 = sum16(g * p, gmask);
+                if (!(dphi0 < 0.0)) {               // not a descent direction: reset to steepest descent
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) Hrow[i] = (i == j) ? 1.0 : 0.0;
+                    p = -g;
+                    dphi0 = sum16(g * p, gmask);
+                    if (!(dphi0 < 0.0)) { status = 0; break; }
+                }
+                // ---- strong-Wolfe line search -------------------------------------------------------
+                const double c1 = 1e-4, c2 = 0.9, phi0 = f;
+                double a_prev = 0.0, phi_prev = phi0, dphi_prev = dphi0;
+                double cand = 1.01 * 2.0 * (phi0 - old_old) / dphi0;
+                double alpha = (cand > 1.0 || !(cand > 0.0)) ? 1.0 : cand;
+                double a_star = 0.0, f_star = f, g_star = g;
+                bool found = false, ls_failed = false;
+                double lo = 0, hi = 0, phi_lo = 0, dphi_lo = 0, phi_hi = 0;
+                bool need_zoom = false;
+                for (int i = 1; i <= 10; ++i) {
+                    double fi, gi;
+                    eval_objective(d, theta + alpha * p, theta0, mask_j, my_a, my_m, gmask, gbase, fi, gi);
+                    const double dphi_i = sum16(gi * p, gmask);
+                    if (!isfinite(fi) || fi > phi0 + c1 * alpha * dphi0 || (fi >= phi_prev && i > 1)) {
+                        lo = a_prev; phi_lo = phi_prev; dphi_lo = dphi_prev; hi = alpha; phi_hi = fi;
+                        need_zoom = true; break;
+                    }
+                    if (fabs(dphi_i) <= -c2 * dphi0) { a_star = alpha; f_star = fi; g_star = gi; found = true; break; }
+                    if (dphi_i >= 0.0) {
+                        lo = alpha; phi_lo = fi; dphi_lo = dphi_i; hi = a_prev; phi_hi = phi_prev;
+                        need_zoom = true; break;
+                    }
+                    a_prev = alpha; phi_prev = fi; dphi_prev = dphi_i;
+                    alpha *= 2.0;
+                    if (i == 10) ls_failed = true;
+                }
+                if (need_zoom) {
+                    double a_rec = 0.0, phi_rec = phi0;
+                    bool have_rec = false;
+                    ls_failed = true;
+                    for (int z = 0; z < 30; ++z) {
+                        const double dalpha = hi - lo;
+                        const double a_min = dalpha < 0 ? hi : lo, a_max = dalpha < 0 ? lo : hi;
+                        double aj = nan("");
+                        if (have_rec) {
+                            const double cchk = 0.2 * dalpha;
+                            aj = cubicmin(lo, phi_lo, dphi_lo, hi, phi_hi, a_rec, phi_rec);
+                            if (isnan(aj) || aj > a_max - fabs(cchk) || aj < a_min + fabs(cchk)) aj = nan("");
+                        }
+                        if (isnan(aj)) {
+                            const double qchk = 0.1 * dalpha;
+                            aj = quadmin(lo, phi_lo, dphi_lo, hi, phi_hi);
+                            if (isnan(aj) || aj > a_max - fabs(qchk) || aj < a_min + fabs(qchk)) aj = lo + 0.5 * dalpha;
+                        }
+                        double fj, gj;
+                        eval_objective(d, theta + aj * p, theta0, mask_j, my_a, my_m, gmask, gbase, fj, gj);
+                        const double dphi_j = sum16(gj * p, gmask);
+                        if (!isfinite(fj) || fj > phi0 + c1 * aj * dphi0 || fj >= phi_lo) {
+                            a_rec = hi; phi_rec = phi_hi; have_rec = true;
+                            hi = aj; phi_hi = fj;
+                        } else {
+                            if (fabs(dphi_j) <= -c2 * dphi0) {
+                                a_star = aj; f_star = fj; g_star = gj; found = true; ls_failed = false; break;
+                            }
+                            if (dphi_j * (hi - lo) >= 0.0) {
+                                a_rec = hi; phi_rec = phi_hi; hi = lo; phi_hi = phi_lo;
+                            } else {
+                                a_rec = lo; phi_rec = phi_lo;
+                            }
+                            have_rec = true;
+                            lo = aj; phi_lo = fj; dphi_lo = dphi_j;
+                            // remember the best sufficient-decrease point in case the curvature test never passes
+                            a_star = aj; f_star = fj; g_star = gj;
+                        }
+                        if (fabs(hi - lo) <= 1e-16 * fmax(1.0, fabs(lo))) break;
+                    }
+                }
+                if (!found) {
+                    // line search exhausted (typically at the FP64 noise floor of the objective): accept the
+                    // best sufficient-decrease point if it improves f, then stop
+                    if (a_star > 0.0 && f_star < f) { theta += a_star * p; f = f_star; g = g_star; }
+                    status = ls_failed ? 3 : 5;
+                    break;
+                }
+                // ---- BFGS update of the inverse Hessian ---------------------------------------------
+                const double s_k = a_star * p, y_k = g_star - g;
+                const double f_old = f;
+                theta += s_k; old_old = f; f = f_star; g = g_star;
+                const double sy = sum16(s_k * y_k, gmask);
+                double rho = 1.0 / sy;
+                if (!isfinite(rho)) rho = 1000.0;   // jax: rho_k = where(isinf(rho_k), 1000, rho_k)
+                double Hy = 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Hy += Hrow[i] * shfl16(y_k, i, gmask, gbase);
+                const double yHy = sum16(y_k * Hy, gmask);
+                const double coef = rho * rho * yHy + rho;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const double s_i = shfl16(s_k, i, gmask, gbase), Hy_i = shfl16(Hy, i, gmask, gbase);
+                    Hrow[i] = Hrow[i] - rho * (s_k * Hy_i + Hy * s_i) + coef * s_k * s_i;
+                }
+                if (fabs(f_old - f) <= 1e-15 * fmax(fabs(f), 1e-300)) { status = 0; ++it; break; }
+            }
+            if (it >= max_iter && status == 0) status = 1;
+            if (!(f <= f0) || !isfinite(f)) { theta = theta0; f = f0; status = 6; }   // never accept a worse point
+        }
+        coefs_out[r * 16 + j] = theta;
+        if (j == 0) { status_out[r] = status | (it << 8); fval_out[2 * r] = f0; fval_out[2 * r + 1] = f; }
+    }
+}
+
+}  // namespace b200i
+
+using namespace b200i;
+
+extern "C" int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const double *x, const uint8_t *codes,
+                                   const int32_t *fit_len, const double *static_feature, const double *prior,
+                                   double support_tol, double lam, double threshold, int32_t max_iter,
+                                   double *coefs_out, void *stream)
+{
+    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "stlsq_batched: negative rows");
+    if (rows == 0) return 0;
+    B200I_REQUIRE(x && codes && fit_len && static_feature && prior && coefs_out, B200I_E_ARG, "stlsq_batched: NULL argument");
+    B200I_REQUIRE(W >= 2 && fd_dt > 0 && lam > 0 && threshold >= 0 && max_iter >= 1, B200I_E_ARG,
+                  "stlsq_batched: need W >= 2, fd_dt > 0, lam > 0 (the per-row design is rank deficient), threshold >= 0");
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+    stlsq_batched_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold, max_iter, coefs_out);
+    return check_cuda(cudaGetLastError(), "stlsq_batched launch");
+}
+
+extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
+                                 const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
+                                 const double *static_feature, const double *theta0, double lam, double gtol,
+                                 int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out,
+                                 void *stream)
+{
+    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs: negative rows");
+    if (rows == 0) return 0;
+    B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
+                  B200I_E_ARG, "insite_bfgs: NULL argument");
+    B200I_REQUIRE(W >= 2 && W <= BFGS_MAXW, B200I_E_UNSUPPORTED, "insite_bfgs: W=%d outside [2,%d]", W, BFGS_MAXW);
+    B200I_REQUIRE(dt > 0 && substeps >= 1 && lam >= 0 && max_iter >= 1, B200I_E_ARG, "insite_bfgs: bad scalar argument");
+    int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    insite_bfgs_kernel<<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+        max_iter, coefs_out, status_out, fval_out);
+    return check_cuda(cudaGetLastError(), "insite_bfgs launch");
+}

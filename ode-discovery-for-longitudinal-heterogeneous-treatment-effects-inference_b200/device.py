@@ -146,6 +146,34 @@ def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS
     return out
 
 
+def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10,
+                  fd_dt=STANDARD_DT):
+    """K5b.  x (R,W) float64, codes (R,W) uint8, fit_len (R,) int32 -> per-row coefficients (R,4,4)."""
+    lib = _native.load()
+    rows, W = x.shape
+    out = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_stlsq_batched(rows, W, float(fd_dt), _ptr(x), _ptr(codes), _ptr(fit_len), _ptr(static_feature),
+                                 _ptr(prior), float(support_tol), float(lam), float(threshold), int(max_iter),
+                                 _ptr(out), _stream())
+    _native.check(rc, "b200i_stlsq_batched")
+    return out
+
+
+def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol=1e-12,
+                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT):
+    """K7.  Returns (coefs (R,4,4), status (R,) int32, fval (R,2))."""
+    lib = _native.load()
+    rows, W = x.shape
+    coefs = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
+    status = torch.empty((rows,), dtype=torch.int32, device='cuda')
+    fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_insite_bfgs(rows, W, float(dt), int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
+                               int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
+                               int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+    _native.check(rc, "b200i_insite_bfgs")
+    return coefs, status, fval
+
+
 _mse_ws = {}
 
 

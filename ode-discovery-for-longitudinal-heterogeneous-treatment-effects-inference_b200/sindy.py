@@ -1,0 +1,294 @@
+"""Host mirror of the reference model ``src.models.sindy.SINDY`` (libs_m/ct/src/models/sindy.py) for the
+cancer simulator: same constructor, ``fit`` / ``get_predictions`` / ``get_autoregressive_predictions`` and the
+two RMSE methods it inherits from TimeVaryingCausalModel (time_varying_model.py:236-313), same attributes
+(``joint_coefs``, ``global_equation_string``, ``feature_library_names``, ``feature_names``, ``insite`` ...).
+
+What runs where
+    fit                      K4 theta_gram + K5 population STLSQ (csrc/theta_gram.cu, fit_rollout.cu)
+                             <- process_dataset_into_de_format + 4x pysindy SINDy.fit (sindy.py:160-213)
+    population predictions   K6 ode_rollout <- _get_non_fine_tuned_predictions (sindy.py:371-431)
+    INSITE predictions       K7 insite_bfgs (reference estimator) or K5b stlsq_batched (north-star estimator)
+                             + K6 with per-row coefficients <- _get_fine_tuned_predictions (sindy.py:433-715)
+    tau-step slicing         get_autoregressive_predictions (sindy.py:717-760)
+    metrics                  numpy on the host, formulas of time_varying_model.py:236-313
+
+Not implemented (outside the cancer_sim hot path): Weak-SINDy, EQ_4/EQ_5 datasets, the joint
+11-term model, smoothing / quantisation options, ray-tune finetune.  They raise NotImplementedError.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import device as dev
+
+logger = logging.getLogger(__name__)
+
+FEATURE_LIBRARY_NAMES = ['1', 'x0', 'u0', 'x0 u0']      # PolynomialLibrary(degree=2, interaction_only=True)
+FEATURE_NAMES = ['x0', 'u0']
+
+
+def equation_string_core(feature_library_names, feature_names, coefs, quantize=False, quantize_round_to=3):
+    """convert_sindy_model_to_sympyjax_model_core (pkpd/utils.py:378-391): the logged equation format."""
+    names = [fn.replace(' ', '*') for fn in feature_library_names]
+    out = []
+    for fln in names:
+        for i in range(len(feature_names)):
+            fln = fln.replace(f'x{i}', feature_names[i])
+        out.append(fln)
+    s = ''
+    for i, coef in enumerate(coefs):
+        if np.abs(coef) > 1e-3:
+            if quantize:
+                coef = np.round(coef, quantize_round_to)
+            s += f'+{coef}*' + out[i]
+    return s
+
+
+class SINDY:
+    model_type = 'sindy_regressor'
+    tuning_criterion = 'rmse'
+
+    def __init__(self, args, dataset_collection=None, autoregressive=None, has_vitals=None, **kwargs):
+        self.dataset_collection = dataset_collection
+        if dataset_collection is not None:
+            self.autoregressive = dataset_collection.autoregressive
+            self.has_vitals = dataset_collection.has_vitals
+        else:
+            self.autoregressive, self.has_vitals = autoregressive, has_vitals
+        self.hparams = args
+        m = args.model
+        self.dim_treatments = m.dim_treatments
+        self.dim_vitals = m.dim_vitals
+        self.dim_static_features = m.dim_static_features
+        self.dim_outcome = m.dim_outcomes
+        self.lag_features = m.lag_features
+        self.input_size = self.dim_treatments + self.dim_static_features
+        self.input_size += self.dim_vitals if self.has_vitals else 0
+        self.input_size += self.dim_outcome if self.autoregressive else 0
+        self.output_size = self.dim_outcome
+        self.dt = dev.STANDARD_DT
+        self.insite_val_error_threshold = m.insite_val_error_threshold
+        self.global_equation_string = ''
+        self.sindy_threshold = m.sindy_threshold
+        self.sindy_alpha = m.sindy_alpha
+        self.smooth_input_data = m.smooth_input_data
+        self.sindy_quantize = m.sindy_quantize
+        self.sindy_quantize_global_model_round_to = m.sindy_quantize_global_model_round_to
+        self.lam = m.lam
+        self.joint_model = m.joint_model
+        self.insite = m.insite
+        self.wsindy = m.wsindy
+        self.use_smoothed_finite_difference = m.use_smoothed_finite_difference
+        self.dataset_name = str(m.dataset_name).upper()
+        self.ablation_more_complex_basis_functions = m.ablation_more_complex_basis_functions
+        self.insight_recover_parametric_dist = m.insight_recover_parametric_dist
+        self.treatment_mode = args.dataset.treatment_mode
+        self.dim_one_hot_treatments = self.dim_treatments
+        self.individualisation = getattr(m, 'individualisation', 'bfgs_rollout')
+        self.ridge_prior_lam = getattr(m, 'ridge_prior_lam', 1e4)
+        self.last_fit_info = {}
+        if self.dataset_name != 'CANCER_SIM':
+            raise NotImplementedError(f"dataset {m.dataset_name!r}: only cancer_sim is on the accelerated path")
+        for flag in ('wsindy', 'joint_model', 'smooth_input_data', 'use_smoothed_finite_difference', 'sindy_quantize',
+                     'ablation_more_complex_basis_functions'):
+            if getattr(self, flag):
+                raise NotImplementedError(f"model.{flag}=True is outside the accelerated INSITE path (SURVEY.md §8a/f)")
+        if self.treatment_mode != 'multiclass':
+            raise NotImplementedError("treatment_mode must be 'multiclass' for the per-treatment SINDy models")
+
+    @staticmethod
+    def set_hparams(model_args, new_args, input_size, model_type):
+        model_args.lam = new_args['lam']
+
+    def prepare_data(self):
+        if self.dataset_collection is not None and not self.dataset_collection.processed_data_multi:
+            self.dataset_collection.process_data_multi()
+
+    def finetune(self, resources_per_trial=None, args=None):
+        raise NotImplementedError("ray-tune hyper-parameter search is disabled in the reference (run.py:193)")
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _unscaled_inputs(self, dataset):
+        """Un-scaling exactly as the reference does it (sindy.py:387-399, 554-567)."""
+        sp = dataset.scaling_params
+        prev = np.squeeze(dataset.data['prev_outputs'] * sp['output_stds'] + sp['output_means'], axis=-1)
+        lo, hi = self.dim_outcome, self.dim_outcome + self.dim_static_features
+        static = dataset.data['static_features'] * sp['inputs_stds'][lo:hi] + sp['input_means'][lo:hi]
+        codes = np.argmax(dataset.data['current_treatments'], axis=-1).astype(np.uint8)
+        seq = dataset.data['sequence_lengths'].astype(np.int64)
+        return prev, static[:, 0], codes, seq
+
+    # -- fit (sindy.py:145-338) ----------------------------------------------------------------------
+    def fit(self, train_f, val_f=None):
+        self.prepare_data()
+        dev.require_cuda()
+        sp = train_f.scaling_params
+        prev, static, codes, seq = self._unscaled_inputs(train_f)
+        unscaled_outputs = np.squeeze(train_f.data['unscaled_outputs'], axis=-1)
+        # pkpd/utils.py:554: 60-long volume = [prev_outputs[:,0] | unscaled_outputs]
+        vol = np.concatenate((prev[:, 0].reshape(-1, 1), unscaled_outputs), axis=1)
+        n, T = vol.shape
+        chemo = np.zeros((n, T)); radio = np.zeros((n, T))
+        chemo[:, :T - 1] = (codes & 1)
+        radio[:, :T - 1] = (codes >> 1) & 1
+        stats = dev.theta_gram(dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio),
+                               dev.to_device(seq.astype(np.float64)), dev.to_device(static), fd_dt=self.dt)
+        coefs, support = dev.stlsq_population(stats, threshold=self.sindy_threshold, alpha=self.sindy_alpha, max_iter=100)
+        torch.cuda.current_stream().synchronize()
+        self.joint_coefs = coefs.cpu().numpy()
+        self.support_ = support.cpu().numpy().astype(bool)
+        self.population_stats_ = stats.cpu().numpy().copy()
+        self.feature_library_names = list(FEATURE_LIBRARY_NAMES)
+        self.feature_names = list(FEATURE_NAMES)
+        strs = [equation_string_core(self.feature_library_names, self.feature_names, self.joint_coefs[a],
+                                     quantize=self.sindy_quantize,
+                                     quantize_round_to=self.sindy_quantize_global_model_round_to) for a in range(4)]
+        self.global_equation_string = (f'Treatment 0: x_dot = {strs[0]} | Treatment 1: x_dot = {strs[1]} | '
+                                       f'Treatment 2: x_dot = {strs[2]} | Treatment 3: x_dot = {strs[3]}')
+        logger.info('[Model]: ' + self.global_equation_string)
+        return self
+
+    # -- predictions ---------------------------------------------------------------------------------
+    def get_predictions(self, dataset):
+        if not self.insite:
+            predictions = self._get_non_fine_tuned_predictions(dataset)
+        else:
+            predictions = self._get_fine_tuned_predictions(dataset)
+        assert not np.any(np.isnan(predictions)), 'Predictions contains NaN'
+        return predictions
+
+    def _rollout(self, prev, static, codes, coefs_dev, drop_below):
+        pred = dev.ode_rollout(dev.to_device(np.ascontiguousarray(prev[:, 0])), dev.to_device(static),
+                               dev.to_device(codes, dtype=torch.uint8), coefs_dev, dt=self.dt,
+                               substeps=dev.STEPS_FOR_DT, drop_below=drop_below)
+        torch.cuda.current_stream().synchronize()
+        return pred.cpu().numpy()
+
+    def _get_non_fine_tuned_predictions(self, dataset):
+        """Open-loop rollout of the population ODE (terms with |c| <= 1e-3 dropped, pkpd/utils.py:388)."""
+        sp = dataset.scaling_params
+        prev, static, codes, _ = self._unscaled_inputs(dataset)
+        un = self._rollout(prev, static, codes, dev.to_device(self.joint_coefs), 1e-3)
+        return ((un - sp['output_means']) / sp['output_stds'])[..., None]
+
+    def individualised_coefficients(self, dataset, projection_horizon=1):
+        """Per-row coefficient matrices (R,4,4) on the device + diagnostics."""
+        prev, static, codes, seq = self._unscaled_inputs(dataset)
+        x = dev.to_device(prev)
+        cd = dev.to_device(codes, dtype=torch.uint8)
+        st = dev.to_device(static)
+        theta0 = dev.to_device(self.joint_coefs)
+        W = prev.shape[1]
+        if self.individualisation == 'bfgs_rollout':
+            coefs, status, fval = dev.insite_bfgs(x, cd, dev.to_device(seq, dtype=torch.int32), projection_horizon,
+                                                  st, theta0, lam=self.lam, gtol=1e-12)
+            torch.cuda.current_stream().synchronize()
+            st_np = status.cpu().numpy()
+            self.last_fit_info = {'estimator': 'bfgs_rollout', 'status_low_byte': np.bincount(st_np[st_np >= 0] & 0xff, minlength=8),
+                                  'skipped': int((st_np < 0).sum()), 'iterations_mean': float((st_np[st_np >= 0] >> 8).mean()) if (st_np >= 0).any() else 0.0,
+                                  'objective_start_mean': float(fval[:, 0].mean().item()),
+                                  'objective_end_mean': float(fval[:, 1].mean().item())}
+        elif self.individualisation == 'ridge_prior_stlsq':
+            fit_len = np.clip(seq - projection_horizon, 0, W - 1).astype(np.int32)
+            coefs = dev.stlsq_batched(x, cd, dev.to_device(fit_len, dtype=torch.int32), st, theta0,
+                                      lam=self.ridge_prior_lam, threshold=self.sindy_threshold, support_tol=1e-3,
+                                      fd_dt=self.dt)
+            self.last_fit_info = {'estimator': 'ridge_prior_stlsq', 'lam': self.ridge_prior_lam}
+        else:
+            raise ValueError(f"unknown individualisation estimator {self.individualisation!r}")
+        return coefs, (prev, static, codes, seq)
+
+    def _get_fine_tuned_predictions(self, dataset, projection_horizon=1):
+        """INSITE: individualise per row, then roll out with the row's own coefficients (no 1e-3 term filter,
+        as predict_with_reduced_coefs, sindy.py:658)."""
+        sp = dataset.scaling_params
+        coefs, (prev, static, codes, _) = self.individualised_coefficients(dataset, projection_horizon)
+        un = self._rollout(prev, static, codes, coefs, -1.0)
+        scaled = (un - sp['output_means']) / sp['output_stds']
+        assert not np.any(np.isnan(scaled) | np.isinf(scaled)), 'Scaled_preds contains NaN or Inf'
+        return scaled[..., None]
+
+    def get_autoregressive_predictions(self, dataset):
+        H = self.hparams.dataset.projection_horizon
+        if not self.insite:
+            scaled = self._get_non_fine_tuned_predictions(dataset)
+        else:
+            scaled = self._get_fine_tuned_predictions(dataset, projection_horizon=H)
+        assert scaled.ndim == 3 and scaled.shape[2] == 1
+        seq = dataset.data['sequence_lengths'].astype(np.int64)
+        R, W, _ = scaled.shape
+        # dynamic_slice(preds, (i, max(1, sl-H), 0), (1,H,1)) -- start clamped so the slice fits (sindy.py:729-733)
+        lo = np.clip(np.maximum(1, seq - H), 0, W - H)
+        idx = lo[:, None] + np.arange(H)[None, :]
+        return scaled[np.arange(R)[:, None], idx, :]
+
+    # -- metrics (time_varying_model.py:236-313) -------------------------------------------------------
+    def get_normalised_masked_rmse(self, dataset, one_step_counterfactual=False):
+        outputs_scaled = self.get_predictions(dataset)
+        unscale = self.hparams.exp.unscale_rmse
+        percentage = self.hparams.exp.percentage_rmse
+        act = dataset.data['active_entries']
+        if unscale:
+            sp = dataset.scaling_params
+            err = outputs_scaled * sp['output_stds'] + sp['output_means'] - dataset.data['unscaled_outputs']
+        else:
+            err = outputs_scaled - dataset.data['outputs']
+        mse = (err ** 2) * act
+        mse_orig = (mse.sum(0).sum(-1) / act.sum(0).sum(-1)).mean()
+        rmse_orig = np.sqrt(mse_orig) / dataset.norm_const
+        rmse_all = np.sqrt(mse.sum() / act.sum()) / dataset.norm_const
+        if percentage:
+            rmse_orig *= 100.0
+            rmse_all *= 100.0
+        if one_step_counterfactual:
+            n, _, od = act.shape
+            last = act - np.concatenate([act[:, 1:, :], np.zeros((n, 1, od))], axis=1)
+            mse_last = ((err ** 2) * last).sum() / last.sum()
+            rmse_last = np.sqrt(mse_last) / dataset.norm_const
+            if percentage:
+                rmse_last *= 100.0
+            return rmse_orig, rmse_all, rmse_last
+        return rmse_orig, rmse_all
+
+    def get_normalised_n_step_rmses(self, dataset, datasets_mc=None):
+        assert hasattr(dataset, 'data_processed_seq')
+        unscale = self.hparams.exp.unscale_rmse
+        percentage = self.hparams.exp.percentage_rmse
+        outputs_scaled = self.get_autoregressive_predictions(dataset if datasets_mc is None else datasets_mc)
+        seq = dataset.data_processed_seq
+        if unscale:
+            sp = dataset.scaling_params
+            mse = ((outputs_scaled * sp['output_stds'] + sp['output_means'] - seq['unscaled_outputs']) ** 2) \
+                * seq['active_entries']
+        else:
+            mse = ((outputs_scaled - seq['outputs']) ** 2) * seq['active_entries']
+        nan_idx = np.unique(np.where(np.isnan(seq['outputs']))[0])
+        not_nan = np.setdiff1d(np.arange(outputs_scaled.shape[0]), nan_idx)
+        mse_orig = mse[not_nan].sum(0).sum(-1) / seq['active_entries'][not_nan].sum(0).sum(-1)
+        rmses = np.sqrt(mse_orig) / dataset.norm_const
+        if percentage:
+            rmses *= 100.0
+        return rmses
+
+
+def run_experiment(args, dataset_collection=None):
+    """Body of runnables/train_sindy.py::main (:38-113) without hydra / MLflow: returns the same result dict."""
+    from .dataset import SyntheticCancerDatasetCollection
+    if dataset_collection is None:
+        d = args.dataset
+        dataset_collection = SyntheticCancerDatasetCollection(
+            d.chemo_coeff, d.radio_coeff, {'train': d.num_patients.train, 'val': d.num_patients.val,
+                                           'test': d.num_patients.test}, seed=d.seed, window_size=d.window_size,
+            max_seq_length=d.max_seq_length, projection_horizon=d.projection_horizon, lag=d.lag,
+            cf_seq_mode=d.cf_seq_mode, treatment_mode=d.treatment_mode)
+    dataset_collection.process_data_multi()
+    model = SINDY(args, dataset_collection)
+    model.fit(dataset_collection.train_f, dataset_collection.val_f)
+    results = {}
+    orig, all_, last = model.get_normalised_masked_rmse(dataset_collection.test_cf_one_step, one_step_counterfactual=True)
+    results.update({'encoder_test_rmse_all': all_, 'encoder_test_rmse_orig': orig, 'encoder_test_rmse_last': last})
+    rmses = model.get_normalised_n_step_rmses(dataset_collection.test_cf_treatment_seq)
+    results.update({f'decoder_test_rmse_{k + 2}-step': v for k, v in enumerate(rmses)})
+    results.update({'global_equation_string': model.global_equation_string, 'fine_tuned': model.insite})
+    return results, model

@@ -271,3 +271,96 @@ def n_step_rmses(pred_seq_scaled, data_seq, scaling, norm_const=TUMOUR_DEATH_THR
     keep = np.setdiff1d(np.arange(un.shape[0]), nan_idx)
     mse_orig = mse[keep].sum(0).sum(-1) / data_seq['active_entries'][keep].sum(0).sum(-1)
     return np.sqrt(mse_orig) / norm_const * 100.0
+
+
+# ------------------------------------------------------------------------------------------------
+# individualisation (INSITE)
+# ------------------------------------------------------------------------------------------------
+def insite_objective(theta_flat, x, codes, u, n_fit, theta0_flat, lam, norm, dt=STANDARD_DT, steps=STEPS_FOR_DT,
+                     with_grad=True):
+    """f_to_min_func (sindy.py:781-794) for one row + its gradient by forward sensitivities.
+    x: un-scaled prev_outputs (W,), codes (W,) treatment index, n_fit = sequence_length - projection_horizon."""
+    theta = np.asarray(theta_flat, dtype=np.float64).reshape(4, 4)
+    theta0 = np.asarray(theta0_flat, dtype=np.float64).reshape(4, 4)
+    mask = (np.abs(theta0) > 1e-3).astype(np.float64)          # coef_sparse_mask, sindy.py:589
+    c = theta * mask
+    h = dt / steps
+    v = float(x[0])
+    s = np.zeros((4, 4))
+    acc = 0.0
+    gacc = np.zeros((4, 4))
+    for k in range(int(n_fit)):
+        a = int(codes[k])
+        c0, c1, c2, c3 = c[a]
+        for _ in range(steps):
+            vu = v * u
+            f = ((c0 + c1 * v) + c2 * u) + c3 * vu
+            if with_grad:
+                dfdv = c1 + c3 * u
+                df = np.zeros((4, 4))
+                df[a] = np.array([1.0, v, u, vu]) * mask[a]
+                s = s + h * (dfdv * s + df)
+            v = v + h * f
+        r = x[k + 1] - v
+        acc += r * r
+        if with_grad:
+            gacc += -2.0 * r * s
+    mse = acc / n_fit
+    diff = theta - theta0
+    val = mse / norm + lam * np.mean(diff ** 2)
+    if not with_grad:
+        return val
+    grad = gacc / n_fit / norm + lam * 2.0 * diff / 16.0
+    return val, grad.reshape(-1)
+
+
+def insite_bfgs_row(x, codes, u, seq_len, ph, theta0, lam, gtol=1e-12, maxiter=3200):
+    """_fine_tuning_inner (sindy.py:587-631) with scipy's BFGS standing in for jax's (UNPINNED: the two
+    differ at the iterate level).  Returns (theta (4,4), f0, f_end)."""
+    from scipy.optimize import minimize
+    W = len(x)
+    n_fit = min(int(seq_len) - ph, W - 1)
+    t0 = np.asarray(theta0, dtype=np.float64).reshape(-1)
+    if n_fit <= 0:
+        return t0.reshape(4, 4).copy(), 0.0, 0.0
+    start = insite_objective(t0, x, codes, u, n_fit, t0, lam, 1.0, with_grad=False)
+    norm = 2.5 * start
+    fun = lambda th: insite_objective(th, x, codes, u, n_fit, t0, lam, norm)
+    f0 = fun(t0)[0]
+    res = minimize(fun, t0, jac=True, method='BFGS', options={'gtol': gtol, 'maxiter': maxiter})
+    th = res.x if res.fun <= f0 else t0
+    return th.reshape(4, 4), f0, min(res.fun, f0)
+
+
+def ridge_prior_row(x, codes, u, n_fit, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10, dt=STANDARD_DT):
+    """Batched per-row estimator of the north star (K5b): per treatment, mean-normalised normal equations of
+    the row's snippets, ridge shrunk to the population coefficients on the population support, thresholded."""
+    prior = np.asarray(prior, dtype=np.float64).reshape(4, 4)
+    G = np.zeros((4, 4, 4)); b = np.zeros((4, 4)); cnt = np.zeros(4)
+    W = len(x)
+    for k in range(int(n_fit)):
+        a = int(codes[k]); a1 = int(codes[min(k + 1, W - 1)])
+        xd = (x[k + 1] - x[k]) / dt
+        pts = [x[k]] + ([x[k + 1]] if (k == n_fit - 1 or a1 != a) else [])
+        for xv in pts:
+            th = np.array([1.0, xv, u, xv * u])
+            G[a] += np.outer(th, th); b[a] += th * xd; cnt[a] += 1
+    out = prior.copy()
+    for a in range(4):
+        ind = np.abs(prior[a]) > support_tol
+        if cnt[a] == 0 or not ind.any():
+            continue
+        Ga, ba = G[a] / cnt[a], b[a] / cnt[a]
+        c = np.zeros(4)
+        for _ in range(max_iter):
+            c = np.zeros(4)
+            c[ind] = np.linalg.solve(Ga[np.ix_(ind, ind)] + lam * np.eye(ind.sum()), ba[ind] + lam * prior[a][ind])
+            big = ind & (np.abs(c) >= threshold)
+            if np.array_equal(big, ind):
+                break
+            ind = big
+            if not ind.any():
+                c = np.zeros(4)
+                break
+        out[a] = c
+    return out
