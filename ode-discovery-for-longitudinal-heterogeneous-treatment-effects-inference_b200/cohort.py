@@ -26,12 +26,50 @@ def shard_bounds(n_total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_stats(stats):
-    """Sum the packed statistics over ranks (no-op without a process group)."""
+def allreduce_stats(stats, ordered=False):
+    """Sum the packed statistics over ranks in place (no-op without a process group).
+
+    ordered=False: one all-reduce (NCCL ring/tree order: fixed for a given world size, so every rank gets
+    the same bits, but the bits differ between world sizes at the 1e-16 level).
+    ordered=True : all-gather of the per-rank partials + summation in rank order on every rank -- the
+    reduction order no longer depends on the collective algorithm."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return stats
+    if not ordered:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        return stats
+    world = dist.get_world_size()
+    parts = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(parts, stats)
+    acc = parts[0].clone()
+    for p in parts[1:]:
+        acc += p
+    stats.copy_(acc)
     return stats
+
+
+def pack_stats(G, b, counts, moments=None):
+    """(G (4,4,4), b (4,4), counts (4,), moments (8,)) -> the 68-double packed layout of include/b200i.h."""
+    out = np.zeros(dev.STATS_DOUBLES)
+    for a in range(4):
+        k = a * dev.GRAM_PER_TREATMENT
+        for i in range(4):
+            for j in range(i, 4):
+                out[k] = G[a][i][j]
+                k += 1
+        out[a * dev.GRAM_PER_TREATMENT + 10:a * dev.GRAM_PER_TREATMENT + 14] = b[a]
+        out[a * dev.GRAM_PER_TREATMENT + 14] = counts[a]
+    if moments is not None:
+        out[4 * dev.GRAM_PER_TREATMENT:] = moments
+    return out
+
+
+def source_prefix_length(row_offsets, n_total):
+    """Number of leading patients whose rows cover row indices [0, n_total): the global source prefix every
+    rank must simulate before its own shard of a counterfactual cohort (cross-row window)."""
+    off = np.asarray(row_offsets)
+    return int(np.searchsorted(off, n_total, side='left'))
 
 
 class FactualFitPipeline:

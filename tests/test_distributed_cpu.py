@@ -1,0 +1,80 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous patient sharding, the sum
+all-reduce of the packed population statistics (plain and rank-ordered) and the counterfactual source
+prefix.  Per-shard statistics come from the oracle's C normal equations (tests may use the oracle)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as h
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, ordered, out_dir):
+    sys.path.insert(0, h.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200_insite import cohort
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(n_total, seed=13)
+    lo, hi = cohort.shard_bounds(n_total, rank, world)
+    sub_p = {k: (v[lo:hi] if isinstance(v, np.ndarray) else v) for k, v in params.items()}
+    sub_d = {k: v[lo:hi] for k, v in draws.items()}
+    sim = so.sim_factual(sub_p, 60, sub_d)
+    G, b, cnt = so.theta_gram(sim, sub_p['patient_types'])
+    stats = torch.from_numpy(cohort.pack_stats(G, b, cnt))
+    cohort.allreduce_stats(stats, ordered=ordered)
+    np.save(os.path.join(out_dir, f"stats_{int(ordered)}_{rank}.npy"), stats.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+def test_sharded_statistics_allreduce_equals_whole_cohort(tmp_path, ordered):
+    from b200_insite import cohort, device as dev
+    from oracle import sim_oracle as so
+    n_total, world = 1001, 2          # odd: shards of 501 and 500
+    mp.spawn(_worker, args=(world, _free_port(), n_total, ordered, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"stats_{int(ordered)}_{r}.npy") for r in range(world)]
+    assert np.array_equal(got[0], got[1]), "ranks must hold bit-identical statistics"
+    params, draws = h.random_cohort(n_total, seed=13)
+    sim = so.sim_factual(params, 60, draws)
+    G, b, cnt = so.theta_gram(sim, params['patient_types'])
+    u = dev.unpack_stats(got[0])
+    assert np.array_equal(u['count'], cnt)
+    np.testing.assert_allclose(u['G'], G, rtol=1e-13)
+    np.testing.assert_allclose(u['b'], b, rtol=1e-10, atol=1e-8)
+    c_ref, s_ref = so.stlsq_from_gram(G, b)
+    c_got, s_got = so.stlsq_from_gram(u['G'], u['b'])
+    assert np.array_equal(s_ref, s_got)
+    np.testing.assert_allclose(c_got, c_ref, rtol=1e-9)
+
+
+def test_shard_bounds_cover_the_cohort_exactly():
+    from b200_insite.cohort import shard_bounds
+    for n in (0, 1, 7, 8, 1_000_003):
+        for world in (1, 2, 4, 8):
+            b = [shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_source_prefix_length():
+    from b200_insite.cohort import source_prefix_length
+    off = np.array([0, 236, 472, 700, 936])        # rows emitted before each patient
+    assert source_prefix_length(off, 1) == 1       # row 0 lives in patient 0
+    assert source_prefix_length(off, 236) == 1
+    assert source_prefix_length(off, 237) == 2
+    assert source_prefix_length(off, 936) == 4
