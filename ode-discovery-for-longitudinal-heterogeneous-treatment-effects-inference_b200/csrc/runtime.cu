@@ -67,10 +67,10 @@ int encode_tmap_2d_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64
     if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
     else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-    else {
-        set_error("tensor map: box of %u columns is not 32/64/128 bytes", box_cols);
+    else if (row_bytes % 16 != 0 || box_cols > 256) {
+        set_error("tensor map: box of %u columns (rows of %u bytes) is not supported", box_cols, row_bytes);
         return B200I_E_UNSUPPORTED;
-    }
+    }   // any other multiple of 16 bytes: unswizzled rows
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * 8u};
     cuuint32_t box[2] = {box_cols, box_rows};

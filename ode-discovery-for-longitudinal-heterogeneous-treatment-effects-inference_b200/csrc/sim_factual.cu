@@ -8,6 +8,7 @@
 //   * sim_factual_generic: the same per-column arithmetic with direct global accesses; covers odd T,
 //     unaligned buffers and the `assigned_actions` fixed policy, and cross-checks the TMA kernel.
 // With GRAM the population statistics of theta_gram (K4) are accumulated while simulating.
+#include "fastmath.cuh"
 #include "sim_math.cuh"
 #include "stats_reduce.cuh"
 #include "tma.cuh"
@@ -16,7 +17,7 @@
 namespace b200i {
 
 struct SimC {
-    double death, density, sphere, chemo_amt, radio_amt, decay, fd_dt;
+    double death, density, sphere, chemo_amt, radio_amt, decay, fd_dt, inv_sphere;
     int window;
 };
 
@@ -342,204 +343,9 @@ sim_factual_tma(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c,
     if (GRAM) stats_block_finish(block_acc, P >> 5, ws, &s_is_last);
 }
 
-// ------------------------------------------------------------------------------------------------
-// TMA-tiled kernel, generation 2: in-place tiles + packed flags (high occupancy)
-//
-// ncu on generation 1 (profiles/r1_k1_v2_*.txt) showed a latency-bound kernel: 8 warps/SM (104 KB of
-// staging per CTA, 204 registers), issue slots 32 % busy, 25 % of the stall samples in the mbarrier
-// wait.  Generation 2 cuts shared memory to 34 KB per 128 patients so that 4 CTAs (16 warps) fit:
-//   * the four input tiles are overwritten in place by the four real-valued outputs (volume, chemo
-//     dosage, two probabilities): a slot is read and written only by its owning thread;
-//   * the five 0/1-valued outputs (chemo/radio application, radio dosage = 2*radio application,
-//     death and recovery flags) are staged as one packed byte per (patient, column) and expanded by
-//     the whole CTA with coalesced 16-byte global stores;
-//   * dead patients keep computing on garbage with masked outputs instead of predicated-off state
-//     updates (the compiler turned the early return into ~100 selects per column).
-// ------------------------------------------------------------------------------------------------
-// steady-state column (t >= 16: window full; caller masks t >= T-1 through `act`)
-__device__ __forceinline__ void fast_column(int t, bool in_range, const SimC &c, const Patient &p, FactualState &s,
-                                            double noise, double urec, double uchemo, double uradio, double &oV,
-                                            double &oC, double &oPc, double &oPr, unsigned &flags)
-{
-    const bool act = s.alive && in_range;
-    double Vn = gompertz_step(p, s.V, s.C, s.D, noise);
-#pragma unroll
-    for (int j = 0; j < 14; ++j) s.win[j] = s.win[j + 1];
-    s.win[14] = calc_diameter(s.V, c.sphere);
-    const double metric = np_mean_full(s.win);
-    const double pr = sigmoid_prob(p.radio_beta, metric, p.radio_int);
-    const double pc = p.same_sigmoid ? pr : sigmoid_prob(p.chemo_beta, metric, p.chemo_int);
-    const bool ra = uradio < pr;
-    const bool ca = uchemo < pc;
-    const double C = __dadd_rn(__dmul_rn(s.C, c.decay), ca ? c.chemo_amt : 0.0);
-    const bool death = Vn > c.death;
-    Vn = death ? c.death : Vn;
-    const bool recov = !death && recovery_test<true>(urec, Vn, c.density);
-    Vn = recov ? 0.0 : Vn;
-    oV = act ? Vn : 0.0;
-    oC = act ? C : 0.0;
-    oPc = act ? pc : 0.0;
-    oPr = act ? pr : 0.0;
-    flags = act ? ((ca ? 1u : 0u) | (ra ? 2u : 0u) | (death ? 4u : 0u) | (recov ? 8u : 0u)) : 0u;
-    s.V = Vn; s.C = C; s.D = ra ? c.radio_amt : 0.0;
-    s.t_end = act ? t : s.t_end;
-    s.alive = act && !(death || recov);
-}
-
-template <int P, int MINB>
-__global__ void __launch_bounds__(P, MINB)
-sim_factual_tma2(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, const double *__restrict__ params,
-                 double *__restrict__ out_ca, double *__restrict__ out_ra, double *__restrict__ out_D,
-                 double *__restrict__ out_death, double *__restrict__ out_recov, double *__restrict__ seq_len_out)
-{
-    constexpr int TC = 8, ROW_BYTES = 64, TILE_BYTES = P * ROW_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar;
-    uint8_t *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [4][TILE]
-    uint8_t *flag_buf = tiles + 4 * TILE_BYTES;                                      // [2][P][TC] bytes
-
-    const int tid = threadIdx.x;
-    const int nchunks = (T + TC - 1) / TC;
-    const int64_t ntiles = (n + P - 1) / P;
-    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_tiles * nchunks;
-
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-#pragma unroll
-        for (int a = 0; a < 4; ++a) tma_prefetch_desc(&maps.in[a]);
-        tma_prefetch_desc(&maps.out[0]); tma_prefetch_desc(&maps.out[1]);
-        tma_prefetch_desc(&maps.out[5]); tma_prefetch_desc(&maps.out[6]);
-    }
-    __syncthreads();
-
-    auto issue_load = [&](int64_t g) {
-        const int64_t tile = blockIdx.x + (g / nchunks) * gridDim.x;
-        const int ch = (int)(g % nchunks);
-        mbar_arrive_expect_tx(&bar, 4u * TILE_BYTES);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) tma_load_2d(tiles + a * TILE_BYTES, &maps.in[a], ch * TC, (int)(tile * P), &bar);
-    };
-    if (tid == 0 && total > 0) issue_load(0);
-
-    Patient p;
-    FactualState s;
-    PatientGram pg_unused; Moments mom_unused;
-    int64_t patient = 0;
-    bool exists = false;
-
-    for (int64_t g = 0; g < total; ++g) {
-        const int64_t tile = blockIdx.x + (g / nchunks) * gridDim.x;
-        const int ch = (int)(g % nchunks);
-        uint8_t *flags_s = flag_buf + (g & 1) * (P * TC);
-        if (ch == 0) {
-            patient = tile * P + tid;
-            exists = patient < n;
-            p = load_patient(params, n, exists ? patient : 0);
-            state_init(s, exists);
-        }
-        mbar_wait(&bar, (uint32_t)(g & 1));
-
-        const bool steady = (ch * TC >= 16) && (c.window == 15);
-        unsigned packed[2] = {0u, 0u};   // 8 flag nibbles... one byte per column
-#pragma unroll 1
-        for (int q = 0; q < TC / 2; ++q) {
-            const uint32_t off = swz_off<ROW_BYTES>(tid, q);
-            const double2 nz = *reinterpret_cast<const double2 *>(tiles + 0 * TILE_BYTES + off);
-            const double2 ur = *reinterpret_cast<const double2 *>(tiles + 1 * TILE_BYTES + off);
-            const double2 uc = *reinterpret_cast<const double2 *>(tiles + 2 * TILE_BYTES + off);
-            const double2 ud = *reinterpret_cast<const double2 *>(tiles + 3 * TILE_BYTES + off);
-            const int t0 = ch * TC + 2 * q;
-            double v0, c0, pc0, pr0, v1, c1, pc1, pr1;
-            unsigned fl0, fl1;
-            if (steady) {
-                fast_column(t0, t0 < T - 1, c, p, s, nz.x, ur.x, uc.x, ud.x, v0, c0, pc0, pr0, fl0);
-                fast_column(t0 + 1, t0 + 1 < T - 1, c, p, s, nz.y, ur.y, uc.y, ud.y, v1, c1, pc1, pr1, fl1);
-            } else {
-                Column o0, o1;
-                factual_column<false, false>(t0, T, c, p, s, nz.x, ur.x, uc.x, ud.x, nullptr, o0, pg_unused, mom_unused);
-                factual_column<false, false>(t0 + 1, T, c, p, s, nz.y, ur.y, uc.y, ud.y, nullptr, o1, pg_unused, mom_unused);
-                v0 = o0.V; c0 = o0.C; pc0 = o0.pc; pr0 = o0.pr;
-                v1 = o1.V; c1 = o1.C; pc1 = o1.pc; pr1 = o1.pr;
-                fl0 = (o0.ca != 0.0 ? 1u : 0u) | (o0.ra != 0.0 ? 2u : 0u) | (o0.death != 0.0 ? 4u : 0u) | (o0.recov != 0.0 ? 8u : 0u);
-                fl1 = (o1.ca != 0.0 ? 1u : 0u) | (o1.ra != 0.0 ? 2u : 0u) | (o1.death != 0.0 ? 4u : 0u) | (o1.recov != 0.0 ? 8u : 0u);
-            }
-            *reinterpret_cast<double2 *>(tiles + 0 * TILE_BYTES + off) = make_double2(v0, v1);
-            *reinterpret_cast<double2 *>(tiles + 1 * TILE_BYTES + off) = make_double2(c0, c1);
-            *reinterpret_cast<double2 *>(tiles + 2 * TILE_BYTES + off) = make_double2(pc0, pc1);
-            *reinterpret_cast<double2 *>(tiles + 3 * TILE_BYTES + off) = make_double2(pr0, pr1);
-            const unsigned two = fl0 | (fl1 << 8);
-            packed[q >> 1] |= two << ((q & 1) * 16);
-        }
-        *reinterpret_cast<uint2 *>(flags_s + tid * TC) = make_uint2(packed[0], packed[1]);
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_2d(&maps.out[0], ch * TC, (int)(tile * P), tiles + 0 * TILE_BYTES);
-            tma_store_2d(&maps.out[1], ch * TC, (int)(tile * P), tiles + 1 * TILE_BYTES);
-            tma_store_2d(&maps.out[5], ch * TC, (int)(tile * P), tiles + 2 * TILE_BYTES);
-            tma_store_2d(&maps.out[6], ch * TC, (int)(tile * P), tiles + 3 * TILE_BYTES);
-            tma_store_commit();
-        }
-        // expand the packed flags: thread -> (row, column pair), 16-byte stores, 8 rows per warp instruction
-        {
-            const int64_t row0 = tile * P;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int e = it * P + tid;          // 0 .. 4P-1
-                const int row = e >> 2, cp = e & 3;
-                const int col = ch * TC + cp * 2;
-                if (row0 + row < n && col < T) {     // T even: a column pair is in or out as a whole
-                    const unsigned two = *reinterpret_cast<const unsigned short *>(flags_s + row * TC + cp * 2);
-                    const unsigned a = two & 0xffu, b = two >> 8;
-                    const int64_t gofs = (row0 + row) * T + col;
-                    *reinterpret_cast<double2 *>(out_ca + gofs) = make_double2((a & 1u) ? 1.0 : 0.0, (b & 1u) ? 1.0 : 0.0);
-                    *reinterpret_cast<double2 *>(out_ra + gofs) = make_double2((a & 2u) ? 1.0 : 0.0, (b & 2u) ? 1.0 : 0.0);
-                    *reinterpret_cast<double2 *>(out_D + gofs) =
-                        make_double2((a & 2u) ? c.radio_amt : 0.0, (b & 2u) ? c.radio_amt : 0.0);
-                    *reinterpret_cast<double2 *>(out_death + gofs) = make_double2((a & 4u) ? 1.0 : 0.0, (b & 4u) ? 1.0 : 0.0);
-                    *reinterpret_cast<double2 *>(out_recov + gofs) = make_double2((a & 8u) ? 1.0 : 0.0, (b & 8u) ? 1.0 : 0.0);
-                }
-            }
-        }
-        if (tid == 0) {
-            tma_store_wait_read();                    // tiles are free again
-            if (g + 1 < total) issue_load(g + 1);
-        }
-        if (ch == nchunks - 1 && exists) {
-            seq_len_out[patient] = (double)(s.t_end + 1);
-        }
-    }
-    if (tid == 0) tma_store_wait_all();
-}
-
-template <int P, int MINB>
-static int launch_tma2(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
-                       double *const out[9], double *seq_len, cudaStream_t st)
-{
-    constexpr int SMEM = 4 * P * 64 + 2 * P * 8 + 1024;
-    TmapPack pack;
-    for (int a = 0; a < 4; ++a) {
-        int rc = encode_tmap_2d_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, P, 8, false);
-        if (rc) return rc;
-    }
-    for (int a = 0; a < 9; ++a) {
-        int rc = encode_tmap_2d_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, P, 8, false);
-        if (rc) return rc;
-    }
-    auto kern = sim_factual_tma2<P, MINB>;
-    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    int per_sm = 0;
-    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P, SMEM));
-    B200I_REQUIRE(per_sm >= 1, B200I_E_UNSUPPORTED, "sim_factual_tma2<%d>: does not fit on an SM", P);
-    const int64_t ntiles = (n + P - 1) / P;
-    int64_t grid = (int64_t)num_sms() * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    // out order: V C D ca ra pc pr death recov
-    kern<<<(unsigned)grid, P, SMEM, st>>>(pack, n, T, c, params, out[3], out[4], out[2], out[7], out[8], seq_len);
-    return check_cuda(cudaGetLastError(), "sim_factual_tma2 launch");
-}
+}  // namespace b200i
+#include "sim_factual_ws.cuh"
+namespace b200i {
 
 // ------------------------------------------------------------------------------------------------
 // host launchers
@@ -585,11 +391,17 @@ static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const doub
         case 7: return launch_tma<256, 4, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         case 8: return launch_tma<128, 16, 1, 1, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 10: if (!GRAM) return launch_tma2<128, 4>(n, T, c, params, in, out, seq_len, st); break;
-        case 11: if (!GRAM) return launch_tma2<128, 3>(n, T, c, params, in, out, seq_len, st); break;
-        case 12: if (!GRAM) return launch_tma2<64, 8>(n, T, c, params, in, out, seq_len, st); break;
-        case 13: if (!GRAM) return launch_tma2<128, 5>(n, T, c, params, in, out, seq_len, st); break;
-        case 14: if (!GRAM) return launch_tma2<256, 2>(n, T, c, params, in, out, seq_len, st); break;
+        // generation 6 (sim_factual_ws.cuh): <patients per CTA, 16-column boxes per chunk, CTAs per SM, mode>;
+        // 2x = data movement only (profiling aid)
+        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 14: if (!GRAM) return launch_ws<64, 1, 6, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 20: if (!GRAM) return launch_ws<32, 2, 6, 1>(n, T, c, params, in, out, seq_len, st); break;
+        case 21: if (!GRAM) return launch_ws<64, 2, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
+        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
+        case 23: if (!GRAM) return launch_ws<32, 1, 11, 1>(n, T, c, params, in, out, seq_len, st); break;
         default:
             break;
     }
@@ -628,7 +440,7 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
                   "sim_factual: fused gram needs static_feature and fd_dt > 0");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SimC c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay, fd_dt,
-           k->window_size};
+           1.0 / k->sphere_coef, k->window_size};
     const double *in[4] = {noise, recovery_rvs, chemo_rvs, radio_rvs};
     double *out[9] = {cancer_volume, chemo_dosage, radio_dosage, chemo_application, radio_application,
                       chemo_probabilities, radio_probabilities, death_flags, recovery_flags};

@@ -1,0 +1,470 @@
+// sim_factual_ws.cuh -- K1 generation 6 (default): software-pipelined columns on in-place 128-byte-row tiles.
+// Included by sim_factual.cu (needs TmapPack, SimC, FactualState/factual_column, tma.cuh, fastmath.cuh).
+//
+// What the measurements said about the earlier generations (B200, 1M patients x 60 columns):
+//   * gen 1 ncu (profiles/r1_k1_gen1_variant2_ncu.txt): issue-bound on a bloated instruction stream --
+//     489 warp instructions per patient-column, 25 % of them FP64, one dependent chain per column.
+//   * a data-movement-only build of gen 4/5 (64-byte rows, then 128-byte rows requested one 16-column
+//     chunk at a time) ran almost as slowly as the full kernel: short row segments that are touched ~5 us
+//     apart defeat DRAM page locality and L2 line reuse (dram read 1.7x the algorithmic bytes, 50 % of
+//     peak).  The same skeleton moving whole 480-byte rows reached 5.86 TB/s (profiles/r1_k1_skeleton.md).
+//   * FP64 dependent-issue latency is 8 cycles, MUFU.RCP64H 17, I2F+D2I 36 (scripts/dbg/fp64_lat.cu): a warp
+//     that walks one dependent chain per column cannot fill its issue slots, and shared memory (in-place
+//     tiles cost 32 B per patient-column) caps the number of resident warps.
+// Generation 6:
+//   * a chunk is NB adjacent boxes of {16 columns x P patients} per array, all requested back to back, so
+//     DRAM sees 128*NB contiguous bytes per row at once; every box is its own SWIZZLE_128B tile
+//     (conflict-free 16-byte LDS/STS for thread-per-patient access).  One in-place stage per CTA: volume,
+//     chemo dosage and the treatment probability overwrite the random draws and leave through TMA; the five
+//     0/1-valued outputs travel as one packed byte per (patient, column) and are expanded to float64 with
+//     coalesced 16-byte stores (radio dosage = dose x application).  Small single-stage CTAs (P = 32: one
+//     warp, no CTA-wide barrier) overlap each other's copy phases.
+//   * the column recurrence is software-pipelined into three independent chains per loop body:
+//       (1) log(K / V[t-1])                                   -> V[t]
+//       (2) exp / reciprocal of the sigmoid of column t-1     -> treatment, chemo concentration of t-1
+//       (3) cube root of V[t-1], window mean                  -> sigmoid argument of column t
+//     (2) consumes what (3) produced one body earlier; V[t] needs (1) and (2).  The critical path per column
+//     drops from ~45 to ~26 dependent FP64 operations.
+//   * arithmetic from fastmath.cuh with all polynomial constants pinned in registers; no special-case
+//     paths in the hot loop.  A tile that does not satisfy the fast path's preconditions (chemo and radio
+//     sigmoids differ, |sigmoid argument| could exceed 700, window_size != 15, non-normal K / V0) is
+//     processed by the generic column function with the library log/exp/cbrt instead -- results stay
+//     defined for any input.
+//   * the 15-slot diameter window is an 18-register file shifted once per four columns (four columns are
+//     unrolled so every window index is static); while it fills (t <= 15, exactly box 0 of chunk 0, which
+//     has its own code copy) numpy's pairwise sum degenerates to a running sum plus one 8-leaf tree at t = 8.
+//   * inactive columns (after death / recovery, and the never-simulated last column) are zeroed by a
+//     rarely taken clean-up branch per four columns instead of predicating every output.
+#pragma once
+
+namespace b200i {
+
+template <int P, int NB>
+struct WsCfg {
+    static constexpr int BOX_COLS = 16, TCH = BOX_COLS * NB;          // columns per chunk
+    static constexpr int TILE_BYTES = P * 128;                        // one box of one array
+    static constexpr int STAGE_BYTES = NB * 4 * TILE_BYTES;           // [NB][4][TILE]
+    static constexpr int FLAG_PITCH = TCH + 4;                        // byte c+1 = column c; byte 0 = dummy
+    static constexpr int FLAG_BYTES = P * FLAG_PITCH;
+    static constexpr int DUMMY_BYTES = P * 16;                        // per-thread scratch slot
+    static constexpr int SMEM_BYTES = STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + 1024;
+    static_assert(P % 32 == 0 && TILE_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+};
+
+// simulator constants + fastmath constants, loaded once per thread and pinned in registers
+struct WsK {
+    fm::FmK f;
+    double sphere, inv_sphere, decay, dose, death, ndensity, inv15;
+};
+
+struct WsPatient {
+    fm::LogNum K;                       // carrying capacity, pre-split for log_ratio
+    double rho, beta_c, rd, nb, si;     // rd = alpha*d + beta*d^2 at d = radio dose; nb = -beta_sigmoid
+};
+
+struct WsState {
+    double V;          // V[t-1]
+    double Cq;         // C[t-2]
+    double zq;         // sigmoid argument of column t-1
+    double ucp, udp;   // chemo / radio draws of column t-1
+    double S;          // running window sum while the window fills
+    unsigned flp;      // death / recovery bits of column t-1 (its chemo / radio bits are still pending)
+    bool alive;
+    int t_end;
+};
+
+__device__ __forceinline__ void pin(double &x) { asm volatile("" : "+d"(x)); }
+
+// numpy pairwise sum of 8 values
+__device__ __forceinline__ double ws_tree8(double a0, double a1, double a2, double a3, double a4, double a5,
+                                           double a6, double a7)
+{
+    return __dadd_rn(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)), __dadd_rn(__dadd_rn(a4, a5), __dadd_rn(a6, a7)));
+}
+
+__device__ __noinline__ bool ws_recovery_rare(double u, double x)
+{
+    // u < exp(x) outside the hot path's shortcut (x >= 0 is handled by the caller)       :346
+    return u < exp(x);
+}
+
+// treatment of column t-1 from its sigmoid argument (chain 2): probability, assignment, chemo concentration
+__device__ __forceinline__ void ws_treat(const WsK &k, const WsState &s, double &pr, bool &ra, bool &ca, double &C1)
+{
+    pr = fm::rcp_fast(__dadd_rn(1.0, fm::exp_fast(k.f, s.zq)));                          // :322-323
+    ra = s.udp < pr;                                                                      // :328-335
+    ca = s.ucp < pr;
+    C1 = __dadd_rn(__dmul_rn(s.Cq, k.decay), ca ? k.dose : 0.0);                          // :338
+}
+
+// One loop body: volume of column t, treatment of column t-1, sigmoid argument of column t.
+// FILL: the window is still filling (t <= 15); J = position in the unrolled group of four.
+template <bool FILL, int J>
+__device__ __forceinline__ void ws_body(int t, int Tm1, const WsK &k, const WsPatient &p, WsState &s, double (&w)[18],
+                                        double v0, double nz, double ur, double uc, double ud, double &oV,
+                                        double &oC, double &oP, unsigned &oF)
+{
+    if (FILL && J == 0 && t == 0) {
+        // column 0: the initial volume, nothing else                                     :282-289
+        oV = v0; oC = 0.0; oP = 0.0; oF = 0u;
+        s.V = v0;
+        return;
+    }
+    // ---- chain 2: treatment of column t-1 (column 0 has none) ----
+    double pr, C1;
+    bool ra, ca;
+    if (FILL && J == 1 && t == 1) {
+        pr = 0.0; C1 = 0.0; ra = ca = false;
+    } else {
+        ws_treat(k, s, pr, ra, ca, C1);
+    }
+    // ---- chain 3: diameter window -> sigmoid argument of column t.  w holds cube roots; the factor 2 of
+    // calc_diameter commutes exactly with the sum and the division                       :309-313
+    const double cn = fm::cbrt_fast(fm::div_small(s.V, k.sphere, k.inv_sphere));
+    w[14 + J] = cn;
+    double mean;
+    if (FILL) {
+        if (J == 0 && t == 8)
+            s.S = ws_tree8(w[7], w[8], w[9], w[10], w[11], w[12], w[13], w[14]);
+        else
+            s.S = __dadd_rn(s.S, cn);
+        mean = fm::div_small(s.S, (double)t, fm::kInvN[t & 15]);
+    } else {
+        double r = ws_tree8(w[J], w[J + 1], w[J + 2], w[J + 3], w[J + 4], w[J + 5], w[J + 6], w[J + 7]);
+#pragma unroll
+        for (int j = 8; j < 15; ++j) r = __dadd_rn(r, w[J + j]);
+        mean = fm::div_small(r, 15.0, k.inv15);
+    }
+    const double z = __dmul_rn(p.nb, __dsub_rn(__dmul_rn(mean, 2.0), p.si));
+    // ---- chain 1: V * (1 + rho*log(K/V) - beta_c*C - (alpha*d + beta*d^2) + noise)      :300-302
+    double g1 = __dadd_rn(1.0, __dmul_rn(p.rho, fm::log_ratio(k.f, p.K, s.V)));
+    g1 = __dsub_rn(g1, __dmul_rn(p.beta_c, C1));
+    g1 = __dsub_rn(g1, ra ? p.rd : 0.0);
+    g1 = __dadd_rn(g1, nz);
+    double Vn = __dmul_rn(s.V, g1);
+    const bool act = s.alive && (t < Tm1);
+    const bool death = Vn > k.death;                                                       // :340-343
+    Vn = death ? k.death : Vn;
+    // recovery: u < exp(-V * density); exp is below 4.3e-18 unless V < 6.9e-8             :346-349
+    const double x = __dmul_rn(Vn, k.ndensity);
+    bool recov = x >= 0.0;
+    if (act && !recov && (x > -40.0 || ur < 1e-17))
+        recov = (x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x);
+    recov = recov && !death;
+    Vn = recov ? 0.0 : Vn;
+    // outputs: volume and death/recovery bits of column t; treatment of column t-1
+    oV = Vn; oC = C1; oP = pr;
+    oF = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
+    s.flp = (death ? 4u : 0u) | (recov ? 8u : 0u);
+    s.V = Vn; s.Cq = C1; s.zq = z; s.ucp = uc; s.udp = ud;
+    s.t_end = act ? t : s.t_end;
+    s.alive = act && !(death || recov);
+}
+
+// ---- generic (slow) path for tiles outside the fast path's preconditions ----------------------
+struct WsSlow {
+    Patient p;
+    FactualState s;
+};
+
+template <int P>
+__device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int tid, int t_first, int ncols, int T,
+                                           const SimC &c, WsSlow *st)
+{
+    PatientGram pg;
+    Moments mom;
+    for (int cidx = 0; cidx < ncols; ++cidx) {
+        const int box = cidx >> 4, q = (cidx & 15) >> 1, lohi = cidx & 1;
+        uint8_t *base = stage + box * 4 * (P * 128) + swz_off<128>((uint32_t)tid, (uint32_t)q) + lohi * 8;
+        double *pn = reinterpret_cast<double *>(base), *pu = reinterpret_cast<double *>(base + 1 * P * 128),
+               *pc = reinterpret_cast<double *>(base + 2 * P * 128), *pr = reinterpret_cast<double *>(base + 3 * P * 128);
+        Column o;
+        factual_column<false, false>(t_first + cidx, T, c, st->p, st->s, *pn, *pu, *pc, *pr, nullptr, o, pg, mom);
+        *pn = o.V; *pu = o.C; *pc = o.pc; *pr = o.pr;
+        flags_s[cidx + 1] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
+                                      (o.recov != 0.0 ? 8u : 0u));
+    }
+}
+
+// MODE 0: simulator.  MODE 1: data movement only (threads copy draws to outputs) -- profiling aid that
+// measures what the load/store skeleton sustains without the arithmetic.
+template <int P, int NB, int MINB, int MODE>
+__global__ void __launch_bounds__(P, MINB)
+sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, const double *__restrict__ params,
+               double *__restrict__ out_ca, double *__restrict__ out_ra, double *__restrict__ out_D,
+               double *__restrict__ out_death, double *__restrict__ out_recov, double *__restrict__ seq_len_out)
+{
+    using Cfg = WsCfg<P, NB>;
+    constexpr int TCH = Cfg::TCH, HALF = TCH / 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar;
+    uint8_t *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [NB][4][TILE]
+    uint8_t *flag_buf = tiles + Cfg::STAGE_BYTES;                                    // [P][FLAG_PITCH]
+    uint8_t *dummy_buf = flag_buf + Cfg::FLAG_BYTES;                                 // [P][16]
+
+    const int tid = threadIdx.x;
+    const int nchunks = (T + TCH - 1) / TCH;
+    const int64_t ntiles = (n + P - 1) / P;
+    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;
+
+    auto cta_sync = [&]() {
+        if (P == 32) __syncwarp(); else __syncthreads();
+    };
+    auto issue_load = [&](int64_t tile, int ch) {
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                tma_load_2d(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16, (int)(tile * P),
+                            &full_bar);
+    };
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_prefetch_desc(&maps.in[a]);
+        tma_prefetch_desc(&maps.out[0]); tma_prefetch_desc(&maps.out[1]);
+        tma_prefetch_desc(&maps.out[5]); tma_prefetch_desc(&maps.out[6]);
+        if (total > 0) issue_load(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    // constants -> registers
+    WsK k;
+    k.f = fm::consts();
+    k.sphere = c.sphere; k.inv_sphere = c.inv_sphere; k.decay = c.decay; k.dose = c.chemo_amt; k.death = c.death;
+    k.ndensity = -c.density; k.inv15 = fm::kInvN[15];
+    if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) pin(k.f.lg[i]);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) pin(k.f.ec[i]);
+        pin(k.f.ln2hi); pin(k.f.ln2lo); pin(k.f.sqrt2); pin(k.f.log2e);
+        pin(k.sphere); pin(k.inv_sphere); pin(k.decay); pin(k.dose); pin(k.death); pin(k.ndensity); pin(k.inv15);
+    }
+
+    const uint32_t off0 = (uint32_t)tid * 128u + (((uint32_t)tid & 7u) << 4);   // swizzled 16-byte unit 0 of the row
+    uint8_t *flags_s = flag_buf + tid * Cfg::FLAG_PITCH;
+    double *dummy = reinterpret_cast<double *>(dummy_buf + tid * 16);
+    WsPatient p;
+    WsState s;
+    WsSlow slow;
+    double w[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) w[j] = 0.0;
+    p.K = fm::log_num(1.0); p.rho = p.beta_c = p.rd = p.nb = p.si = 0.0;
+    s.V = s.Cq = s.zq = s.ucp = s.udp = s.S = 0.0; s.flp = 0u; s.alive = false; s.t_end = 0;
+    double v0 = 0.0;
+    int64_t patient = 0;
+    bool exists = false, tile_slow = false;
+    const int Tm1 = T - 1;
+    int64_t tile = blockIdx.x;
+    int ch = 0;
+    const unsigned one_hi = 0x3ff00000u;
+    const unsigned amt_hi = (unsigned)__double2hiint(c.radio_amt), amt_lo = (unsigned)__double2loint(c.radio_amt);
+
+    for (int64_t g = 0; g < total; ++g) {
+        if (MODE == 0 && ch == 0) {
+            patient = tile * P + tid;
+            exists = patient < n;
+            const int64_t pi = exists ? patient : 0;
+            v0 = exists ? __ldg(params + pi) : 1.0;
+            const double alpha = __ldg(params + 1 * n + pi), beta = __ldg(params + 3 * n + pi);
+            const double Kcap = __ldg(params + 5 * n + pi);
+            const double ci = __ldg(params + 6 * n + pi), ri = __ldg(params + 7 * n + pi);
+            const double cb = __ldg(params + 8 * n + pi), rb = __ldg(params + 9 * n + pi);
+            p.rho = __ldg(params + 2 * n + pi);
+            p.beta_c = __ldg(params + 4 * n + pi);
+            p.K = fm::log_num(Kcap);
+            p.si = ri;
+            p.nb = -rb;
+            p.rd = __dadd_rn(__dmul_rn(alpha, c.radio_amt), __dmul_rn(beta, __dmul_rn(c.radio_amt, c.radio_amt)));
+            s.V = 1.0; s.Cq = s.zq = s.ucp = s.udp = s.S = 0.0; s.flp = 0u; s.alive = exists; s.t_end = 0;
+            // fast-path preconditions for this patient: one sigmoid, its argument stays inside exp_fast's
+            // domain for every reachable mean diameter, K and V0 positive and normal, window of 15
+            const double vmax = fmax(v0, c.death);
+            const double dmax = 2.02 * cbrt(vmax * c.inv_sphere);
+            const double zmax = fabs(rb) * fmax(fabs(ri), fabs(dmax - ri));
+            const bool ok = (ci == ri) && (cb == rb) && (zmax <= 700.0) && (Kcap > 1e-300) && (Kcap < 1e300) &&
+                            (v0 > 1e-300) && (v0 < 1e300) && (c.window == 15);
+            const bool bad = exists && !ok;
+            tile_slow = (P == 32) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0);
+            if (tile_slow) {
+                slow.p = load_patient(params, n, pi);
+                state_init(slow.s, exists);
+            }
+        }
+        mbar_wait(&full_bar, (uint32_t)(g & 1));
+        const int t_first = ch * TCH;
+
+        if (MODE == 0 && tile_slow) {
+            ws_slow_chunk<P>(tiles, flags_s, tid, t_first, TCH, T, c, &slow);
+        } else {
+            // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
+            double *prevC = dummy, *prevP = dummy + 1;
+            uint8_t *flag_dst = flags_s;   // byte of column t_first - 1 (dummy byte for the first group)
+            auto run_box = [&](auto fill_tag, uint8_t *box, int tb) {
+                constexpr bool FILL = decltype(fill_tag)::value;
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t offA = off0 ^ ((uint32_t)h << 5), offB = offA ^ 16u;
+                    double2 *pa[4], *pb[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        pa[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offA);
+                        pb[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offB);
+                    }
+                    const double2 nzA = *pa[0], urA = *pa[1], ucA = *pa[2], udA = *pa[3];
+                    const double2 nzB = *pb[0], urB = *pb[1], ucB = *pb[2], udB = *pb[3];
+                    const int t0 = tb + h * 4;
+                    double oV[4], oC[4], oP[4];
+                    unsigned oF[4];
+                    if (MODE == 1) {
+                        oV[0] = nzA.x; oV[1] = nzA.y; oV[2] = nzB.x; oV[3] = nzB.y;
+                        oC[0] = urA.x; oC[1] = urA.y; oC[2] = urB.x; oC[3] = urB.y;
+                        oP[0] = udA.x; oP[1] = udA.y; oP[2] = udB.x; oP[3] = udB.y;
+                        oF[0] = oF[1] = oF[2] = oF[3] = 0u;
+                    } else {
+                        ws_body<FILL, 0>(t0, Tm1, k, p, s, w, v0, nzA.x, urA.x, ucA.x, udA.x, oV[0], oC[0], oP[0], oF[0]);
+                        ws_body<FILL, 1>(t0 + 1, Tm1, k, p, s, w, v0, nzA.y, urA.y, ucA.y, udA.y, oV[1], oC[1], oP[1], oF[1]);
+                        ws_body<FILL, 2>(t0 + 2, Tm1, k, p, s, w, v0, nzB.x, urB.x, ucB.x, udB.x, oV[2], oC[2], oP[2], oF[2]);
+                        ws_body<FILL, 3>(t0 + 3, Tm1, k, p, s, w, v0, nzB.y, urB.y, ucB.y, udB.y, oV[3], oC[3], oP[3], oF[3]);
+#pragma unroll
+                        for (int j = 0; j < 14; ++j) w[j] = w[j + 4];
+                        if (t0 + 3 > s.t_end) {
+                            // columns after the patient's last simulated one stay zero (rare: death / recovery /
+                            // t = T-1).  oV[j] belongs to column t0+j, the treatment outputs to column t0+j-1.
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (t0 + j > s.t_end) oV[j] = 0.0;
+                                if (t0 + j - 1 > s.t_end) { oC[j] = oP[j] = 0.0; oF[j] = 0u; }
+                            }
+                        }
+                    }
+                    *pa[0] = make_double2(oV[0], oV[1]);
+                    *pb[0] = make_double2(oV[2], oV[3]);
+                    *prevC = oC[0]; *prevP = oP[0];
+                    *pa[1] = make_double2(oC[1], oC[2]);
+                    *pa[3] = make_double2(oP[1], oP[2]);
+                    pb[1]->x = oC[3];
+                    pb[3]->x = oP[3];
+                    prevC = &pb[1]->y; prevP = &pb[3]->y;
+                    flag_dst[0] = (uint8_t)oF[0]; flag_dst[1] = (uint8_t)oF[1];
+                    flag_dst[2] = (uint8_t)oF[2]; flag_dst[3] = (uint8_t)oF[3];
+                    flag_dst += 4;
+                }
+            };
+#pragma unroll 1
+            for (int b = 0; b < NB; ++b) {
+                uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
+                if (t_first + b * 16 == 0)
+                    run_box(std::true_type{}, box, 0);
+                else
+                    run_box(std::false_type{}, box, t_first + b * 16);
+            }
+            // treatment of the chunk's last column (the next chunk's first body repeats it from the same state)
+            {
+                const int tl = t_first + TCH - 1;
+                double pr = 0.0, C1 = 0.0;
+                unsigned f = 0u;
+                if (MODE == 0 && tl <= s.t_end && tl >= 1) {
+                    bool ra, ca;
+                    ws_treat(k, s, pr, ra, ca, C1);
+                    f = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
+                }
+                *prevC = C1; *prevP = pr; flag_dst[0] = (uint8_t)f;
+            }
+        }
+        fence_proxy_async_smem();
+        cta_sync();
+        if (tid == 0) {
+            const int src_pc = (MODE == 0 && tile_slow) ? 2 : 3;   // fast path: one sigmoid serves both arrays
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
+                const int c0 = t_first + b * 16;
+                if (c0 < T) {
+                    tma_store_2d(&maps.out[0], c0, (int)(tile * P), box + 0 * Cfg::TILE_BYTES);
+                    tma_store_2d(&maps.out[1], c0, (int)(tile * P), box + 1 * Cfg::TILE_BYTES);
+                    tma_store_2d(&maps.out[5], c0, (int)(tile * P), box + src_pc * Cfg::TILE_BYTES);
+                    tma_store_2d(&maps.out[6], c0, (int)(tile * P), box + 3 * Cfg::TILE_BYTES);
+                }
+            }
+            tma_store_commit();
+        }
+        // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes
+        {
+            const int64_t row0 = tile * P;
+#pragma unroll 2
+            for (int it = 0; it < HALF; ++it) {
+                const int e = it * P + tid;
+                const int row = e / HALF, cp = e % HALF;
+                const int col = t_first + cp * 2;
+                if (row0 + row < n && col < T) {   // T is even: a column pair is inside or outside as a whole
+                    const uint8_t *fb = flag_buf + row * Cfg::FLAG_PITCH + cp * 2 + 1;
+                    const unsigned f0 = fb[0], f1 = fb[1];
+                    const int64_t gofs = (row0 + row) * T + col;
+                    auto put = [&](double *dst, unsigned bit, unsigned hi, unsigned lo) {
+                        const bool b0 = (f0 & bit) != 0u, b1 = (f1 & bit) != 0u;
+                        double2 v;
+                        v.x = __hiloint2double((int)(b0 ? hi : 0u), (int)(b0 ? lo : 0u));
+                        v.y = __hiloint2double((int)(b1 ? hi : 0u), (int)(b1 ? lo : 0u));
+                        *reinterpret_cast<double2 *>(dst + gofs) = v;
+                    };
+                    put(out_ca, 1u, one_hi, 0u);
+                    put(out_ra, 2u, one_hi, 0u);
+                    put(out_D, 2u, amt_hi, amt_lo);
+                    put(out_death, 4u, one_hi, 0u);
+                    put(out_recov, 8u, one_hi, 0u);
+                }
+            }
+        }
+        cta_sync();   // every thread is done with the flag bytes before the next chunk rewrites them
+        const bool last = (ch == nchunks - 1);
+        if (tid == 0) {
+            tma_store_wait_read();   // the tiles are free again
+            if (g + 1 < total) issue_load(last ? tile + gridDim.x : tile, last ? 0 : ch + 1);
+        }
+        if (last) {
+            if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
+            ch = 0;
+            tile += gridDim.x;
+        } else {
+            ++ch;
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
+}
+
+template <int P, int NB, int MINB, int MODE>
+static int launch_ws(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
+                     double *const out[9], double *seq_len, cudaStream_t st)
+{
+    using Cfg = WsCfg<P, NB>;
+    TmapPack pack;
+    for (int a = 0; a < 4; ++a) {
+        int rc = encode_tmap_2d_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, P, 16, false);
+        if (rc) return rc;
+    }
+    for (int a = 0; a < 9; ++a) {
+        int rc = encode_tmap_2d_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, P, 16, false);
+        if (rc) return rc;
+    }
+    auto kern = sim_factual_ws<P, NB, MINB, MODE>;
+    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int per_sm = 0;
+    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P, Cfg::SMEM_BYTES));
+    B200I_REQUIRE(per_sm >= 1, B200I_E_UNSUPPORTED, "sim_factual_ws<%d,%d>: does not fit on an SM", P, NB);
+    const int64_t ntiles = (n + P - 1) / P;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    // out order: V C D ca ra pc pr death recov
+    kern<<<(unsigned)grid, P, Cfg::SMEM_BYTES, st>>>(pack, n, T, c, params, out[3], out[4], out[2], out[7], out[8],
+                                                     seq_len);
+    return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
+}
+
+}  // namespace b200i

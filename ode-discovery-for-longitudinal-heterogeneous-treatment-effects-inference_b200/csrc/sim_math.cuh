@@ -97,6 +97,16 @@ __device__ __forceinline__ void window_push(double (&a)[MAXN], int &cnt, int cap
     cnt += full ? 0 : 1;
 }
 
+// numpy's pairwise sum of a completely filled 15-slot window (static order): 8 accumulators, tree, tail
+__device__ __forceinline__ double np_sum_full(const double (&a)[15])
+{
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])),
+                           __dadd_rn(__dadd_rn(a[4], a[5]), __dadd_rn(a[6], a[7])));
+#pragma unroll
+    for (int j = 8; j < 15; ++j) res = __dadd_rn(res, a[j]);
+    return res;
+}
+
 // np.mean of a completely filled window (n == MAXN), static summation order
 template <int MAXN>
 __device__ __forceinline__ double np_mean_full(const double (&a)[MAXN])

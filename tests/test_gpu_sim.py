@@ -54,6 +54,22 @@ def test_factual_variants_match_oracle(dev, variant):
     _check_factual(got, ref, f"variant {variant}")
 
 
+@pytest.mark.parametrize("variant", [0, 10, 11, 12, 13, 14])
+def test_factual_fast_path_preconditions_fall_back_per_tile(dev, variant):
+    """Tiles whose patients break the lean kernel's preconditions (chemo and radio sigmoids differ, sigmoid
+    argument beyond exp_fast's domain) are processed by the generic column function inside the same launch."""
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(1000, seed=21)
+    dmax = 12.999999999999998
+    params['radio_sigmoid_betas'][100:140] = 6.0 / dmax          # differs from the chemo sigmoid
+    params['chemo_sigmoid_intercepts'][300:303] = 5.0
+    params['chemo_sigmoid_betas'][500:520] = 5000.0 / dmax        # |z| up to ~2500: exp overflows to inf / 0
+    params['radio_sigmoid_betas'][500:520] = 5000.0 / dmax
+    ref = so.sim_factual(params, 60, draws)
+    got, _ = _run_factual(dev, params, draws, variant=variant)
+    _check_factual(got, ref, f"fallback variant {variant}")
+
+
 def test_factual_matches_reference_fixture(dev):
     """Reference outputs themselves (tests/golden/ref_sim_small.npz), reference RNG order."""
     g = h.load_npz('ref_sim_small.npz')
