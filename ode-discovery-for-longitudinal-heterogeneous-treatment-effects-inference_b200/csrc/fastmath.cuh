@@ -245,7 +245,11 @@ B200I_HD double cbrt_fast(double x)
 {
     const float xf = (float)x;
 #if defined(__CUDA_ARCH__)
-    const double y0 = (double)exp2f(__log2f(xf) * 0.33333334f);   // MUFU.LG2 / MUFU.EX2, ~2^-21
+    float lg, y0f;   // MUFU.LG2 / MUFU.EX2 without the denormal fix-up sequences, ~2^-21
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    lg *= 0.33333334f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(lg));
+    const double y0 = (double)y0f;
 #else
     const double y0 = (double)cbrtf(xf);
 #endif

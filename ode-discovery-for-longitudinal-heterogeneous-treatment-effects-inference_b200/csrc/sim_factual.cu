@@ -449,7 +449,7 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
     bool tma_ok = (T % 2 == 0) && assigned_actions == nullptr;
     for (int a = 0; a < 4; ++a) tma_ok = tma_ok && aligned16(in[a]);
     for (int a = 0; a < 9; ++a) tma_ok = tma_ok && aligned16(out[a]);
-    if (variant == 0) variant = tma_ok ? 2 : 1;
+    if (variant == 0) variant = !tma_ok ? 1 : (gram ? 2 : 10);
     if (variant >= 2) {
         B200I_REQUIRE(assigned_actions == nullptr, B200I_E_UNSUPPORTED,
                       "sim_factual: assigned_actions is only handled by the generic kernel (variant 1)");

@@ -44,10 +44,12 @@ struct WsCfg {
     static constexpr int BOX_COLS = 16, TCH = BOX_COLS * NB;          // columns per chunk
     static constexpr int TILE_BYTES = P * 128;                        // one box of one array
     static constexpr int STAGE_BYTES = NB * 4 * TILE_BYTES;           // [NB][4][TILE]
-    static constexpr int FLAG_PITCH = TCH + 4;                        // byte c+1 = column c; byte 0 = dummy
+    static constexpr int FLAG_PITCH = TCH + 4;                        // byte c+2 = column c; byte 1 = dummy
     static constexpr int FLAG_BYTES = P * FLAG_PITCH;
     static constexpr int DUMMY_BYTES = P * 16;                        // per-thread scratch slot
-    static constexpr int SMEM_BYTES = STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + 1024;
+    static constexpr int LUT_BYTES = 5 * 4 * 16;                      // flag expansion table [array][2 bits] -> double2
+    static constexpr int SMEM_BYTES = STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + LUT_BYTES + 1024;
+    static_assert(P % (TCH / 2) == 0 || (TCH / 2) % P == 0, "flag expansion mapping");
     static_assert(P % 32 == 0 && TILE_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
@@ -181,17 +183,23 @@ __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int
         Column o;
         factual_column<false, false>(t_first + cidx, T, c, st->p, st->s, *pn, *pu, *pc, *pr, nullptr, o, pg, mom);
         *pn = o.V; *pu = o.C; *pc = o.pc; *pr = o.pr;
-        flags_s[cidx + 1] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
+        flags_s[cidx + 2] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
                                       (o.recov != 0.0 ? 8u : 0u));
     }
 }
+
+struct WsRaw {
+    const double *in[4];   // the draw arrays again as raw pointers (whole-row L2 prefetch)
+};
+// opts bit 0: prefetch the next tile's whole rows into L2; bit 1: evict-first hint on every output store;
+// bit 2: evict-last hint on the draw loads.
 
 // MODE 0: simulator.  MODE 1: data movement only (threads copy draws to outputs) -- profiling aid that
 // measures what the load/store skeleton sustains without the arithmetic.
 template <int P, int NB, int MINB, int MODE>
 __global__ void __launch_bounds__(P, MINB)
-sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, const double *__restrict__ params,
-               double *__restrict__ out_ca, double *__restrict__ out_ra, double *__restrict__ out_D,
+sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ WsRaw raw, int opts, int64_t n, int T, SimC c,
+               const double *__restrict__ params, double *__restrict__ out_ca, double *__restrict__ out_ra, double *__restrict__ out_D,
                double *__restrict__ out_death, double *__restrict__ out_recov, double *__restrict__ seq_len_out)
 {
     using Cfg = WsCfg<P, NB>;
@@ -201,6 +209,7 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
     uint8_t *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [NB][4][TILE]
     uint8_t *flag_buf = tiles + Cfg::STAGE_BYTES;                                    // [P][FLAG_PITCH]
     uint8_t *dummy_buf = flag_buf + Cfg::FLAG_BYTES;                                 // [P][16]
+    double2 *lut = reinterpret_cast<double2 *>(dummy_buf + Cfg::DUMMY_BYTES);        // [5][4]
 
     const int tid = threadIdx.x;
     const int nchunks = (T + TCH - 1) / TCH;
@@ -211,14 +220,35 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
     auto cta_sync = [&]() {
         if (P == 32) __syncwarp(); else __syncthreads();
     };
+    const bool opt_prefetch = (opts & 1) != 0, opt_evict_first = (opts & 2) != 0, opt_evict_last = (opts & 4) != 0;
+    auto prefetch_tile = [&](int64_t tile) {
+        const int64_t r0 = tile * P;
+        if (r0 >= n) return;
+        const int64_t rows = (n - r0 < P) ? (n - r0) : P;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) l2_prefetch_bulk(raw.in[a] + r0 * T, (uint32_t)(rows * T * 8));
+    };
     auto issue_load = [&](int64_t tile, int ch) {
         mbar_arrive_expect_tx(&full_bar, (uint32_t)Cfg::STAGE_BYTES);
+        if (opt_evict_last) {
+            const uint64_t pol = l2_policy_evict_last();
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+            for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-                tma_load_2d(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16, (int)(tile * P),
-                            &full_bar);
+                for (int a = 0; a < 4; ++a)
+                    tma_load_2d_hint(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16,
+                                     (int)(tile * P), &full_bar, pol);
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    tma_load_2d(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16, (int)(tile * P),
+                                &full_bar);
+        }
+        // while the tile's last chunk is in flight, pull the next tile's whole rows into L2: DRAM then sees
+        // contiguous P x 480-byte reads and the next tile's chunk loads are L2 hits
+        if (opt_prefetch && nchunks > 1 && ch == nchunks - 1) prefetch_tile(tile + gridDim.x);
     };
 
     if (tid == 0) {
@@ -228,7 +258,17 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
         for (int a = 0; a < 4; ++a) tma_prefetch_desc(&maps.in[a]);
         tma_prefetch_desc(&maps.out[0]); tma_prefetch_desc(&maps.out[1]);
         tma_prefetch_desc(&maps.out[5]); tma_prefetch_desc(&maps.out[6]);
-        if (total > 0) issue_load(blockIdx.x, 0);
+        if (total > 0) {
+            if (opt_prefetch && nchunks > 1) prefetch_tile(blockIdx.x);
+            issue_load(blockIdx.x, 0);
+        }
+    }
+    if (tid < 20) {
+        // flag expansion table: array a in {chemo app, radio app, radio dosage, death, recovery}, index = the
+        // array's bit of the even column | its bit of the odd column << 1
+        const int a = tid >> 2, idx = tid & 3;
+        const double one = (a == 2) ? c.radio_amt : 1.0;
+        lut[tid] = make_double2((idx & 1) ? one : 0.0, (idx & 2) ? one : 0.0);
     }
     __syncthreads();
 
@@ -263,8 +303,6 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
     const int Tm1 = T - 1;
     int64_t tile = blockIdx.x;
     int ch = 0;
-    const unsigned one_hi = 0x3ff00000u;
-    const unsigned amt_hi = (unsigned)__double2hiint(c.radio_amt), amt_lo = (unsigned)__double2loint(c.radio_amt);
 
     for (int64_t g = 0; g < total; ++g) {
         if (MODE == 0 && ch == 0) {
@@ -296,6 +334,13 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
                 slow.p = load_patient(params, n, pi);
                 state_init(slow.s, exists);
             }
+            // the next tile's parameters: pull them into L2 now, the loads above then cost an L2 hit
+            const int64_t pnext = patient + (int64_t)gridDim.x * P;
+            if ((tid & 3) == 0 && pnext < n) {
+#pragma unroll
+                for (int a = 0; a < 10; ++a)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(params + a * n + pnext));
+            }
         }
         mbar_wait(&full_bar, (uint32_t)(g & 1));
         const int t_first = ch * TCH;
@@ -305,7 +350,7 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
         } else {
             // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
             double *prevC = dummy, *prevP = dummy + 1;
-            uint8_t *flag_dst = flags_s;   // byte of column t_first - 1 (dummy byte for the first group)
+            uint8_t *flag_dst = flags_s + 1;   // byte of column t_first - 1 (dummy byte for the first group)
             auto run_box = [&](auto fill_tag, uint8_t *box, int tb) {
                 constexpr bool FILL = decltype(fill_tag)::value;
 #pragma unroll 1
@@ -386,7 +431,13 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
             for (int b = 0; b < NB; ++b) {
                 uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
                 const int c0 = t_first + b * 16;
-                if (c0 < T) {
+                if (c0 < T && opt_evict_first) {
+                    const uint64_t pol = l2_policy_evict_first();
+                    tma_store_2d_hint(&maps.out[0], c0, (int)(tile * P), box + 0 * Cfg::TILE_BYTES, pol);
+                    tma_store_2d_hint(&maps.out[1], c0, (int)(tile * P), box + 1 * Cfg::TILE_BYTES, pol);
+                    tma_store_2d_hint(&maps.out[5], c0, (int)(tile * P), box + src_pc * Cfg::TILE_BYTES, pol);
+                    tma_store_2d_hint(&maps.out[6], c0, (int)(tile * P), box + 3 * Cfg::TILE_BYTES, pol);
+                } else if (c0 < T) {
                     tma_store_2d(&maps.out[0], c0, (int)(tile * P), box + 0 * Cfg::TILE_BYTES);
                     tma_store_2d(&maps.out[1], c0, (int)(tile * P), box + 1 * Cfg::TILE_BYTES);
                     tma_store_2d(&maps.out[5], c0, (int)(tile * P), box + src_pc * Cfg::TILE_BYTES);
@@ -395,39 +446,53 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
             }
             tma_store_commit();
         }
-        // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes
-        {
-            const int64_t row0 = tile * P;
-#pragma unroll 2
-            for (int it = 0; it < HALF; ++it) {
-                const int e = it * P + tid;
-                const int row = e / HALF, cp = e % HALF;
-                const int col = t_first + cp * 2;
-                if (row0 + row < n && col < T) {   // T is even: a column pair is inside or outside as a whole
-                    const uint8_t *fb = flag_buf + row * Cfg::FLAG_PITCH + cp * 2 + 1;
-                    const unsigned f0 = fb[0], f1 = fb[1];
-                    const int64_t gofs = (row0 + row) * T + col;
-                    auto put = [&](double *dst, unsigned bit, unsigned hi, unsigned lo) {
-                        const bool b0 = (f0 & bit) != 0u, b1 = (f1 & bit) != 0u;
-                        double2 v;
-                        v.x = __hiloint2double((int)(b0 ? hi : 0u), (int)(b0 ? lo : 0u));
-                        v.y = __hiloint2double((int)(b1 ? hi : 0u), (int)(b1 ? lo : 0u));
-                        *reinterpret_cast<double2 *>(dst + gofs) = v;
-                    };
-                    put(out_ca, 1u, one_hi, 0u);
-                    put(out_ra, 2u, one_hi, 0u);
-                    put(out_D, 2u, amt_hi, amt_lo);
-                    put(out_death, 4u, one_hi, 0u);
-                    put(out_recov, 8u, one_hi, 0u);
-                }
-            }
-        }
-        cta_sync();   // every thread is done with the flag bytes before the next chunk rewrites them
+        // the next chunk's loads go out before the flag expansion, which then overlaps their latency
         const bool last = (ch == nchunks - 1);
         if (tid == 0) {
             tma_store_wait_read();   // the tiles are free again
             if (g + 1 < total) issue_load(last ? tile + gridDim.x : tile, last ? 0 : ch + 1);
         }
+        // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes.
+        // Each array's double2 comes from a 4-entry table indexed by its bit of the two columns.
+        {
+            constexpr int RSTEP = (P >= HALF) ? P / HALF : 1;          // rows advanced per iteration
+            constexpr int ITERS = HALF;                                  // P * HALF items over P threads
+            const int64_t row0 = tile * P;
+            const int cp = (P >= HALF) ? (tid % HALF) : tid;
+            const int r_first = (P >= HALF) ? (tid / HALF) : 0;
+#pragma unroll 2
+            for (int it = 0; it < ITERS; ++it) {
+                int row, cpi;
+                if (P >= HALF) { row = r_first + it * RSTEP; cpi = cp; }
+                else { const int e = it * P + tid; row = e / HALF; cpi = e % HALF; }
+                const int col = t_first + cpi * 2;
+                if (row0 + row < n && col < T) {   // T is even: a column pair is inside or outside as a whole
+                    const unsigned two = *reinterpret_cast<const unsigned short *>(flag_buf + row * Cfg::FLAG_PITCH + cpi * 2 + 2);
+                    const int64_t gofs = (row0 + row) * T + col;
+                    // bits: 1 chemo, 2 radio, 4 death, 8 recovery; low byte = even column, high byte = odd column
+                    const unsigned i_ca = (two & 1u) | ((two >> 7) & 2u);
+                    const unsigned i_ra = ((two >> 1) & 1u) | ((two >> 8) & 2u);
+                    const unsigned i_de = ((two >> 2) & 1u) | ((two >> 9) & 2u);
+                    const unsigned i_re = ((two >> 3) & 1u) | ((two >> 10) & 2u);
+                    const double2 v_ca = lut[0 + i_ca], v_ra = lut[4 + i_ra], v_D = lut[8 + i_ra], v_de = lut[12 + i_de],
+                                  v_re = lut[16 + i_re];
+                    if (opt_evict_first) {
+                        __stcs(reinterpret_cast<double2 *>(out_ca + gofs), v_ca);
+                        __stcs(reinterpret_cast<double2 *>(out_ra + gofs), v_ra);
+                        __stcs(reinterpret_cast<double2 *>(out_D + gofs), v_D);
+                        __stcs(reinterpret_cast<double2 *>(out_death + gofs), v_de);
+                        __stcs(reinterpret_cast<double2 *>(out_recov + gofs), v_re);
+                    } else {
+                        *reinterpret_cast<double2 *>(out_ca + gofs) = v_ca;
+                        *reinterpret_cast<double2 *>(out_ra + gofs) = v_ra;
+                        *reinterpret_cast<double2 *>(out_D + gofs) = v_D;
+                        *reinterpret_cast<double2 *>(out_death + gofs) = v_de;
+                        *reinterpret_cast<double2 *>(out_recov + gofs) = v_re;
+                    }
+                }
+            }
+        }
+        cta_sync();   // every thread is done with the flag bytes before the next chunk rewrites them
         if (last) {
             if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
             ch = 0;
@@ -437,6 +502,13 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c, 
         }
     }
     if (tid == 0) tma_store_wait_all();
+}
+
+// tuning switches of the data-movement skeleton (see WsRaw); B200I_WS_OPTS overrides the default
+static int ws_env_opts()
+{
+    const char *e = getenv("B200I_WS_OPTS");
+    return e ? atoi(e) : 6;   // measured best: evict-first on output stores, evict-last on draw loads
 }
 
 template <int P, int NB, int MINB, int MODE>
@@ -462,8 +534,11 @@ static int launch_ws(int64_t n, int T, const SimC &c, const double *params, cons
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
     // out order: V C D ca ra pc pr death recov
-    kern<<<(unsigned)grid, P, Cfg::SMEM_BYTES, st>>>(pack, n, T, c, params, out[3], out[4], out[2], out[7], out[8],
-                                                     seq_len);
+    WsRaw raw;
+    for (int a = 0; a < 4; ++a) raw.in[a] = in[a];
+    static const int opts = ws_env_opts();
+    kern<<<(unsigned)grid, P, Cfg::SMEM_BYTES, st>>>(pack, raw, opts, n, T, c, params, out[3], out[4], out[2], out[7],
+                                                     out[8], seq_len);
     return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
 }
 

@@ -14,9 +14,11 @@
 // treatment-code byte per step.  Then one thread walks one patient.  HBM traffic = 3 arrays once.
 // The moments needed by get_scaling_params (cancer_simulation.py:776-796) come from a second,
 // element-parallel kernel over the same arrays (masked_moments).
+#include "fastmath.cuh"
 #include "sim_math.cuh"
 #include "stats_reduce.cuh"
 #include "tma.cuh"
+#include <stdlib.h>
 
 namespace b200i {
 
@@ -121,6 +123,174 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
     stats_block_finish(block_acc, GP >> 5, ws, &s_is_last);
 }
 
+// ------------------------------------------------------------------------------------------------
+// theta_gram, second generation (default when T is even and the arrays are 16-byte aligned): ONE pass over
+// the five arrays produces both the normal equations and the scaling moments.
+//
+// The first generation (theta_gram_kernel + masked_moments_kernel) took 0.73 + 0.35 ms at 1M patients
+// (profiles/r1_launches_first.csv): two launches that both read the volume array, a thread walking a
+// 480-byte-pitch row in shared memory (8-way bank conflicts) and a serial load -> pack -> walk per CTA.
+//   * warp = 32 consecutive patients; every warp of the CTA runs its own tile pipeline (own mbarrier)
+//   * volume rows arrive by per-row bulk copies (cp.async.bulk, one row per lane) into a 16-byte padded
+//     pitch, so the thread-per-patient walk reads two columns per conflict-free LDS.128
+//   * while they are in flight the warp streams the four other arrays with coalesced 16-byte loads:
+//     applications -> one treatment-code byte per step (transposed [T][33] layout: conflict-free both
+//     ways), dosages -> masked moments on the fly
+//   * the per-patient sums are expanded with the static feature and kept in registers across tiles; the
+//     shuffle / shared-memory / ordered-grid reduction runs once per thread at the end
+// ------------------------------------------------------------------------------------------------
+constexpr int G2_WARPS = 4;
+
+template <int MAXT>
+__global__ void __launch_bounds__(G2_WARPS * 32, 2)
+theta_gram2_kernel(int64_t n, int T, double fd_dt, double inv_dt, const double *__restrict__ vol,
+                   const double *__restrict__ chemo, const double *__restrict__ radio,
+                   const double *__restrict__ seq_len, const double *__restrict__ static_feature,
+                   const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint64_t bars[G2_WARPS];
+    __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pitch = T * 8 + 16;                                   // volume row pitch (bytes)
+    const int warp_bytes = 32 * pitch + ((T * 33 + 15) & ~15);
+    uint8_t *s_vol = smem_raw + (size_t)warp * warp_bytes;          // [32][pitch]
+    uint8_t *s_code = s_vol + 32 * pitch;                           // [T][33]
+
+    for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += blockDim.x) (&block_acc[0][0])[j] = 0.0;
+    if (lane == 0) mbar_init(&bars[warp], 32);
+    mbar_fence_init();
+    __syncthreads();
+
+    double acc[4][B200I_GRAM_PER_TREATMENT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) acc[a][j] = 0.0;
+    double mv = 0, mvv = 0, mc = 0, mcc = 0, md = 0, mdd = 0, mcnt = 0, mrows = 0;
+
+    const int64_t ntiles = (n + 31) / 32;
+    const int half = T / 2;
+    uint32_t phase = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * G2_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * G2_WARPS) {
+        const int64_t first = tile * 32;
+        const int rows = (int)((n - first < 32) ? (n - first) : 32);
+        // volume rows: lane j copies row j
+        if (lane < rows) {
+            mbar_arrive_expect_tx(&bars[warp], (uint32_t)(T * 8));
+            bulk_load_1d(s_vol + lane * pitch, vol + (first + lane) * T, (uint32_t)(T * 8), &bars[warp]);
+        } else {
+            mbar_arrive(&bars[warp]);
+        }
+        // the four other arrays, two columns per lane and row
+        const double2 *gc2 = reinterpret_cast<const double2 *>(chemo + first * T);
+        const double2 *gr2 = reinterpret_cast<const double2 *>(radio + first * T);
+        const double2 *gC2 = chemo_dos ? reinterpret_cast<const double2 *>(chemo_dos + first * T) : nullptr;
+        const double2 *gD2 = radio_dos ? reinterpret_cast<const double2 *>(radio_dos + first * T) : nullptr;
+        int L_lane = (lane < rows) ? (int)__ldg(seq_len + first + lane) : 0;
+        L_lane = L_lane > T ? T : L_lane;
+        for (int cb = 0; cb < half; cb += 32) {
+            const bool active = cb + lane < half;          // every lane iterates (warp shuffles below)
+            const int c = active ? cb + lane : 0;
+            // batches of 8 rows: all 32 loads of a batch are issued before the first dependent store
+            for (int j0 = 0; j0 < rows; j0 += 8) {
+                double2 va[8], vb[8], vC[8], vD[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = (j0 + i < rows) ? j0 + i : rows - 1;
+                    const int64_t e = (int64_t)j * half + c;
+                    va[i] = __ldg(gc2 + e); vb[i] = __ldg(gr2 + e);
+                    vC[i] = gC2 ? __ldg(gC2 + e) : make_double2(0.0, 0.0);
+                    vD[i] = gD2 ? __ldg(gD2 + e) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = j0 + i;
+                    const int L = __shfl_sync(0xffffffffu, L_lane, j & 31);
+                    if (active && j < rows) {
+                        s_code[(2 * c) * 33 + j] = (uint8_t)((va[i].x != 0.0 ? 1 : 0) + (vb[i].x != 0.0 ? 2 : 0));
+                        s_code[(2 * c + 1) * 33 + j] = (uint8_t)((va[i].y != 0.0 ? 1 : 0) + (vb[i].y != 0.0 ? 2 : 0));
+                        const double w0 = (2 * c < L) ? 1.0 : 0.0, w1 = (2 * c + 1 < L) ? 1.0 : 0.0;
+                        mc += w0 * vC[i].x + w1 * vC[i].y;
+                        mcc += w0 * vC[i].x * vC[i].x + w1 * vC[i].y * vC[i].y;
+                        md += w0 * vD[i].x + w1 * vD[i].y;
+                        mdd += w0 * vD[i].x * vD[i].x + w1 * vD[i].y * vD[i].y;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        mbar_wait(&bars[warp], phase);
+        phase ^= 1u;
+        // thread-per-patient walk over the snippets (pkpd/utils.py:433-462 + FiniteDifference order 1)
+        if (lane < rows) {
+            int Ls = (int)seq_len[first + lane];
+            Ls = Ls > T ? T : Ls;
+            const int L = Ls > T - 1 ? T - 1 : Ls;
+            const double u = static_feature[first + lane];
+            const uint8_t *row = s_vol + lane * pitch;
+            PatientGram pg;
+            pg.clear();
+            // one regression sample (x0 -> x1 under treatment a) plus, when the snippet ends at x1, its
+            // backward-difference end point: both rows share xdot and the treatment, so they are merged and
+            // filed with one-hot weights -- branch-free, 20 independent FMA chains
+            auto sample = [&](double x0, double x1, int a, bool end) {
+                const double xdot = fm::div_small(__dsub_rn(x1, x0), fd_dt, inv_dt);
+                const double e = end ? 1.0 : 0.0;
+                const double cnt = 1.0 + e, sx = fma(e, x1, x0), sxx = fma(e * x1, x1, x0 * x0);
+                const double sd = cnt * xdot, sxd = sx * xdot;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double wt = (a == t) ? 1.0 : 0.0;
+                    pg.s[t][0] = fma(wt, cnt, pg.s[t][0]); pg.s[t][1] = fma(wt, sx, pg.s[t][1]);
+                    pg.s[t][2] = fma(wt, sxx, pg.s[t][2]); pg.s[t][3] = fma(wt, sd, pg.s[t][3]);
+                    pg.s[t][4] = fma(wt, sxd, pg.s[t][4]);
+                }
+            };
+            double2 cur = *reinterpret_cast<const double2 *>(row);
+            int a0 = s_code[lane];
+            for (int k = 0; k < L; k += 2) {
+                const double2 nxt = *reinterpret_cast<const double2 *>(row + (k + 2) * 8);   // pitch padding keeps it in bounds
+                const int a1 = s_code[(k + 1) * 33 + lane];
+                const int a2 = (k + 2 < T) ? s_code[(k + 2) * 33 + lane] : 0;
+                sample(cur.x, cur.y, a0, k == L - 1 || a1 != a0);
+                mv += cur.x; mvv += cur.x * cur.x;
+                if (k + 1 < L) {
+                    sample(cur.y, nxt.x, a1, k + 1 == L - 1 || a2 != a1);
+                    mv += cur.y; mvv += cur.y * cur.y;
+                }
+                a0 = a2;
+                cur = nxt;
+            }
+            if (Ls > L) {   // sequence_length == T: the last entry is active but starts no sample
+                const double x = *reinterpret_cast<const double *>(row + (size_t)L * 8);
+                mv += x; mvv += x * x;
+            }
+            mcnt += (double)Ls; mrows += 1.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double g[B200I_GRAM_PER_TREATMENT];
+                expand_gram(pg.s[a], u, g);
+#pragma unroll
+                for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) acc[a][j] += g[j];
+            }
+        }
+        __syncwarp();   // the warp's tile is reused by its next iteration
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j)
+            warp_acc_add(block_acc[warp], a * B200I_GRAM_PER_TREATMENT + j, acc[a][j], lane);
+    const int m0 = 4 * B200I_GRAM_PER_TREATMENT;
+    warp_acc_add(block_acc[warp], m0 + 0, mv, lane);  warp_acc_add(block_acc[warp], m0 + 1, mvv, lane);
+    warp_acc_add(block_acc[warp], m0 + 2, mc, lane);  warp_acc_add(block_acc[warp], m0 + 3, mcc, lane);
+    warp_acc_add(block_acc[warp], m0 + 4, md, lane);  warp_acc_add(block_acc[warp], m0 + 5, mdd, lane);
+    warp_acc_add(block_acc[warp], m0 + 6, mcnt, lane); warp_acc_add(block_acc[warp], m0 + 7, mrows, lane);
+    stats_block_finish(block_acc, G2_WARPS, ws, &s_is_last);
+}
+
 // sum x, sum x^2 over active entries [i, :seq_len[i]] of up to three (N,T) arrays; one warp per row.
 // Writes moments into a second StatsWorkspace-style partial area (slots 60..67 of the same layout).
 __global__ void __launch_bounds__(256)
@@ -195,6 +365,30 @@ extern "C" int b200i_theta_gram(int64_t n, int32_t T, double fd_dt, const double
     // stats + tickets start from zero for every call (partials are fully overwritten)
     B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
     if (n == 0) return 0;
+    {
+        const bool v2 = (T % 2 == 0) && T <= 256 && aligned16(cancer_volume) && aligned16(chemo_application) &&
+                        aligned16(radio_application) && (!chemo_dosage || aligned16(chemo_dosage)) &&
+                        (!radio_dosage || aligned16(radio_dosage)) && getenv("B200I_THETA_GRAM_V1") == nullptr;
+        if (v2) {
+            const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
+            const size_t smem2 = warp_bytes * G2_WARPS;
+            auto k2 = theta_gram2_kernel<256>;
+            B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            int per_sm2 = 0;
+            B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, G2_WARPS * 32, smem2));
+            if (per_sm2 >= 1) {
+                const int64_t ntiles2 = (n + 31) / 32;
+                int64_t grid2 = (int64_t)num_sms() * per_sm2;
+                const int64_t need = (ntiles2 + G2_WARPS - 1) / G2_WARPS;
+                if (grid2 > need) grid2 = need;
+                if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
+                k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
+                                                                  radio_application, sequence_lengths, static_feature,
+                                                                  chemo_dosage, radio_dosage, ws);
+                return check_cuda(cudaGetLastError(), "theta_gram2 launch");
+            }
+        }
+    }
     const size_t smem = (size_t)GP * T * 9;
     const bool bulk = (T % 2 == 0) && aligned16(cancer_volume) && aligned16(chemo_application) &&
                       aligned16(radio_application);

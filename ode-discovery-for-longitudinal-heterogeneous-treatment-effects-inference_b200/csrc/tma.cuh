@@ -66,6 +66,39 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy value)
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, int c0, int c1, const void *smem_src, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                                 uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// contiguous global range -> L2 (no shared-memory destination); addr and bytes multiples of 16
+__device__ __forceinline__ void l2_prefetch_bulk(const void *gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
