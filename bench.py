@@ -26,6 +26,19 @@ warnings.filterwarnings('ignore')
 METRIC = "patient-steps/sec (cancer_sim factual + INSITE population fit)"
 UNIT = "patient-steps/s"
 K1_BYTES_PER_PATIENT = lambda T: 4 * T * 8 + 9 * T * 8 + 10 * 8 + 8      # 6328 B at T=60
+K4_BYTES_PER_PATIENT = lambda T: 3 * T * 8 + 8 + 8                         # 1456 B at T=60
+K1_KERNEL = "sim_factual_ws<32,2,6,0>"      # csrc/sim_factual_ws.cuh, variant 10 (default)
+K4_KERNEL = "theta_gram2_kernel"            # csrc/theta_gram.cu
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+    same kernel at the bench workload (profiles/r1_traffic.json); None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_peak_hbm():
@@ -209,22 +222,31 @@ def run_b200(args):
     barrier()
     k1_ms = []
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            pipe.step_device()
-        e1.record()
-        barrier()
-        total_ms = e0.elapsed_time(e1)
-        # dominant kernel alone (same buffers, inputs > L2): CUDA events around the single launch
-        for a, b in ev:
-            a.record()
-            dev.sim_factual(pipe.params, *pipe.draws, T, pipe.consts, out=pipe.out, variant=args.variant,
-                            fused_static=pipe.static if args.fused else None)
-            b.record()
-        torch.cuda.synchronize()
-        k1_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = ClockSampler(local_rank)   # sampled from here to the end of the end-to-end loop (all GPU-busy)
+    clocks.t.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        pipe.step_device()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    # dominant kernel alone (same buffers, inputs > L2): CUDA events around the single launch
+    for a, b in ev:
+        a.record()
+        dev.sim_factual(pipe.params, *pipe.draws, T, pipe.consts, out=pipe.out, variant=args.variant,
+                        fused_static=pipe.static if args.fused else None)
+        b.record()
+    torch.cuda.synchronize()
+    k1_ms = [a.elapsed_time(b) for a, b in ev]
+    # second kernel of the step (population statistics), same way
+    for a, b in ev:
+        a.record()
+        dev.theta_gram(pipe.out['cancer_volume'], pipe.out['chemo_application'], pipe.out['radio_application'],
+                       pipe.out['sequence_lengths'], pipe.static, pipe.out['chemo_dosage'], pipe.out['radio_dosage'])
+        b.record()
+    torch.cuda.synchronize()
+    k4_ms = [a.elapsed_time(b) for a, b in ev]
     steps_exec = pipe.executed_steps()
     t = torch.tensor([total_ms, steps_exec], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -250,6 +272,7 @@ def run_b200(args):
         pipe.step_host(h_block, h_static, h_draws, h_result)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    clocks.stop.set(); clocks.t.join(timeout=6)
     te = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -260,6 +283,8 @@ def run_b200(args):
         peak, peak_src = measured_peak_hbm()
         k1 = float(np.mean(k1_ms))
         achieved = K1_BYTES_PER_PATIENT(T) * n / (k1 / 1e3) / 1e9
+        k4 = float(np.mean(k4_ms))
+        achieved4 = K4_BYTES_PER_PATIENT(T) * n / (k4 / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -276,10 +301,19 @@ def run_b200(args):
                         "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": float(te[0]),
                         "what": "FactualFitPipeline.step_host: pinned host params+draws -> H2D -> K1,K4,K5 -> D2H "
                                 "coefficients/support/statistics"},
-                "gpu_launches": pipe.launches_per_step * args.steps + args.steps,
-                "roofline": {"bound": "hbm", "kernel": "sim_factual_tma", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel_ms": k1, "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n},
+                "gpu_launches": pipe.launches_per_step * args.steps,
+                "roofline": {"bound": "hbm", "kernel": K1_KERNEL, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(K1_KERNEL),
+                             "peak_source": peak_src, "kernel_ms": k1,
+                             "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n,
+                             "share_of_step": k1 / ms_per_step},
+                "roofline_theta_gram": {"bound": "hbm", "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
+                                        "unit": "GB/s", "frac": achieved4 / peak, "traffic": ncu_traffic(K4_KERNEL),
+                                        "kernel_ms": k4, "algorithmic_bytes_per_launch": K4_BYTES_PER_PATIENT(T) * n,
+                                        "bytes_read_per_launch": (5 * T * 8 + 16) * n,
+                                        "note": "the launch also produces the scaling moments, which need the two "
+                                                "dosage arrays: it reads 5 arrays, the algorithmic figure counts 3",
+                                        "share_of_step": k4 / ms_per_step},
                 "population_coefs": coefs.tolist()}
         if world == 1 and not args.no_cpu_baseline:
             v, sec, detail = cpu_reference_arm(args.ref_patients, T, 1)

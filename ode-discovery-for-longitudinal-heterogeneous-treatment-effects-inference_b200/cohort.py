@@ -89,7 +89,7 @@ class FactualFitPipeline:
         self.stats = torch.zeros(dev.STATS_DOUBLES, **f64)
         self.coefs = None
         self.support = None
-        self.launches_per_step = 3 if fused else 4   # sim (+gram +moments) + stlsq
+        self.launches_per_step = 2 if fused else 3   # simulate_factual (+ theta_gram) + stlsq_population
 
     # -- inputs ------------------------------------------------------------------------------------
     def load_host(self, params_block, static, draws, non_blocking=True):

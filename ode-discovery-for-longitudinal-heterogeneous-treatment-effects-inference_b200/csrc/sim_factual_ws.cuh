@@ -192,7 +192,7 @@ struct WsRaw {
     const double *in[4];   // the draw arrays again as raw pointers (whole-row L2 prefetch)
 };
 // opts bit 0: prefetch the next tile's whole rows into L2; bit 1: evict-first hint on every output store;
-// bit 2: evict-last hint on the draw loads.
+// bit 2: evict-last hint on the draw loads; bit 3: L2 prefetch of the tile's later chunks with its first.
 
 // MODE 0: simulator.  MODE 1: data movement only (threads copy draws to outputs) -- profiling aid that
 // measures what the load/store skeleton sustains without the arithmetic.
@@ -220,7 +220,8 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
     auto cta_sync = [&]() {
         if (P == 32) __syncwarp(); else __syncthreads();
     };
-    const bool opt_prefetch = (opts & 1) != 0, opt_evict_first = (opts & 2) != 0, opt_evict_last = (opts & 4) != 0;
+    const bool opt_prefetch = (opts & 1) != 0, opt_evict_first = (opts & 2) != 0, opt_evict_last = (opts & 4) != 0,
+               opt_rest_l2 = (opts & 8) != 0;
     auto prefetch_tile = [&](int64_t tile) {
         const int64_t r0 = tile * P;
         if (r0 >= n) return;
@@ -249,6 +250,13 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
         // while the tile's last chunk is in flight, pull the next tile's whole rows into L2: DRAM then sees
         // contiguous P x 480-byte reads and the next tile's chunk loads are L2 hits
         if (opt_prefetch && nchunks > 1 && ch == nchunks - 1) prefetch_tile(tile + gridDim.x);
+        // bit 3: together with the tile's first chunk, request its remaining boxes into L2 -- DRAM serves every
+        // row in one go and the 128-byte lines that straddle a chunk boundary are fetched once
+        if (opt_rest_l2 && ch == 0) {
+            for (int c0 = TCH; c0 < T; c0 += 16)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) tma_prefetch_2d(&maps.in[a], c0, (int)(tile * P));
+        }
     };
 
     if (tid == 0) {

@@ -94,6 +94,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// one box of a tiled tensor map -> L2 (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 // contiguous global range -> L2 (no shared-memory destination); addr and bytes multiples of 16
 __device__ __forceinline__ void l2_prefetch_bulk(const void *gptr, uint32_t bytes)
 {
