@@ -49,7 +49,7 @@ struct WsCfg {
     static constexpr int DUMMY_BYTES = P * 16;                        // per-thread scratch slot
     static constexpr int LUT_BYTES = 5 * 4 * 16;                      // flag expansion table [array][2 bits] -> double2
     static constexpr int SMEM_BYTES = STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + LUT_BYTES + 1024;
-    static_assert(P % (TCH / 2) == 0 || (TCH / 2) % P == 0, "flag expansion mapping");
+    static_assert(P % (TCH / 2) == 0, "flag expansion mapping");
     static_assert(P % 32 == 0 && TILE_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
@@ -149,9 +149,9 @@ __device__ __forceinline__ void ws_body(int t, int Tm1, const WsK &k, const WsPa
     Vn = death ? k.death : Vn;
     // recovery: u < exp(-V * density); exp is below 4.3e-18 unless V < 6.9e-8             :346-349
     const double x = __dmul_rn(Vn, k.ndensity);
-    bool recov = x >= 0.0;
-    if (act && !recov && (x > -40.0 || ur < 1e-17))
-        recov = (x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x);
+    bool recov = false;
+    if (act && !(x <= -40.0 && ur >= 1e-17))   // also taken for NaN, like the reference's comparison
+        recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
     recov = recov && !death;
     Vn = recov ? 0.0 : Vn;
     // outputs: volume and death/recovery bits of column t; treatment of column t-1
@@ -463,20 +463,21 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
         // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes.
         // Each array's double2 comes from a 4-entry table indexed by its bit of the two columns.
         {
-            constexpr int RSTEP = (P >= HALF) ? P / HALF : 1;          // rows advanced per iteration
-            constexpr int ITERS = HALF;                                  // P * HALF items over P threads
+            static_assert(P >= HALF, "flag expansion mapping: every thread keeps one column pair");
+            constexpr int RSTEP = P / HALF;                      // rows advanced per iteration
             const int64_t row0 = tile * P;
-            const int cp = (P >= HALF) ? (tid % HALF) : tid;
-            const int r_first = (P >= HALF) ? (tid / HALF) : 0;
-#pragma unroll 2
-            for (int it = 0; it < ITERS; ++it) {
-                int row, cpi;
-                if (P >= HALF) { row = r_first + it * RSTEP; cpi = cp; }
-                else { const int e = it * P + tid; row = e / HALF; cpi = e % HALF; }
-                const int col = t_first + cpi * 2;
-                if (row0 + row < n && col < T) {   // T is even: a column pair is inside or outside as a whole
-                    const unsigned two = *reinterpret_cast<const unsigned short *>(flag_buf + row * Cfg::FLAG_PITCH + cpi * 2 + 2);
-                    const int64_t gofs = (row0 + row) * T + col;
+            const int rows_valid = (n - row0 < P) ? (int)(n - row0) : P;
+            const int cp = tid % HALF, r_first = tid / HALF;
+            const int col = t_first + cp * 2;
+            if (col < T) {   // T is even: a column pair is inside or outside as a whole
+                const int64_t tile_ofs = row0 * T + col;
+                double *b_ca = out_ca + tile_ofs, *b_ra = out_ra + tile_ofs, *b_D = out_D + tile_ofs,
+                       *b_de = out_death + tile_ofs, *b_re = out_recov + tile_ofs;
+                const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 2;
+                int ofs = r_first * T;
+#pragma unroll 4
+                for (int row = r_first; row < rows_valid; row += RSTEP, ofs += RSTEP * T, fp += RSTEP * Cfg::FLAG_PITCH) {
+                    const unsigned two = *reinterpret_cast<const unsigned short *>(fp);
                     // bits: 1 chemo, 2 radio, 4 death, 8 recovery; low byte = even column, high byte = odd column
                     const unsigned i_ca = (two & 1u) | ((two >> 7) & 2u);
                     const unsigned i_ra = ((two >> 1) & 1u) | ((two >> 8) & 2u);
@@ -485,17 +486,17 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
                     const double2 v_ca = lut[0 + i_ca], v_ra = lut[4 + i_ra], v_D = lut[8 + i_ra], v_de = lut[12 + i_de],
                                   v_re = lut[16 + i_re];
                     if (opt_evict_first) {
-                        __stcs(reinterpret_cast<double2 *>(out_ca + gofs), v_ca);
-                        __stcs(reinterpret_cast<double2 *>(out_ra + gofs), v_ra);
-                        __stcs(reinterpret_cast<double2 *>(out_D + gofs), v_D);
-                        __stcs(reinterpret_cast<double2 *>(out_death + gofs), v_de);
-                        __stcs(reinterpret_cast<double2 *>(out_recov + gofs), v_re);
+                        __stcs(reinterpret_cast<double2 *>(b_ca + ofs), v_ca);
+                        __stcs(reinterpret_cast<double2 *>(b_ra + ofs), v_ra);
+                        __stcs(reinterpret_cast<double2 *>(b_D + ofs), v_D);
+                        __stcs(reinterpret_cast<double2 *>(b_de + ofs), v_de);
+                        __stcs(reinterpret_cast<double2 *>(b_re + ofs), v_re);
                     } else {
-                        *reinterpret_cast<double2 *>(out_ca + gofs) = v_ca;
-                        *reinterpret_cast<double2 *>(out_ra + gofs) = v_ra;
-                        *reinterpret_cast<double2 *>(out_D + gofs) = v_D;
-                        *reinterpret_cast<double2 *>(out_death + gofs) = v_de;
-                        *reinterpret_cast<double2 *>(out_recov + gofs) = v_re;
+                        *reinterpret_cast<double2 *>(b_ca + ofs) = v_ca;
+                        *reinterpret_cast<double2 *>(b_ra + ofs) = v_ra;
+                        *reinterpret_cast<double2 *>(b_D + ofs) = v_D;
+                        *reinterpret_cast<double2 *>(b_de + ofs) = v_de;
+                        *reinterpret_cast<double2 *>(b_re + ofs) = v_re;
                     }
                 }
             }
