@@ -87,6 +87,52 @@ int encode_tmap_2d_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64
     return 0;
 }
 
+int encode_tmap_2d_pitched_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                               uint32_t box_rows, uint32_t box_cols)
+{
+    encode_tiled_fn enc = get_encode();
+    B200I_REQUIRE(enc != nullptr, B200I_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    B200I_REQUIRE(box_cols * 8u == 128u && pitch_bytes % 16 == 0 && rows > 0 && cols > 0 && aligned16(base),
+                  B200I_E_UNSUPPORTED, "tensor map (pitched): box of %u columns, pitch %llu, base %p", box_cols,
+                  (unsigned long long)pitch_bytes, base);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (pitched) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu base=%p)",
+                  (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, base);
+        return B200I_E_DRIVER;
+    }
+    return 0;
+}
+
+int encode_tmap_3d_rowgroups_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t group_rows,
+                                 uint32_t box_groups, uint32_t box_cols)
+{
+    encode_tiled_fn enc = get_encode();
+    B200I_REQUIRE(enc != nullptr, B200I_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    B200I_REQUIRE(box_cols * 8u == 128u && rows % group_rows == 0 && rows > 0, B200I_E_UNSUPPORTED,
+                  "tensor map (row groups): box of %u columns, %llu rows in groups of %u", box_cols,
+                  (unsigned long long)rows, group_rows);
+    cuuint64_t gdim[3] = {cols, group_rows, rows / group_rows};
+    cuuint64_t gstride[2] = {cols * 8u, cols * 8u * group_rows};
+    cuuint32_t box[3] = {box_cols, 1, box_groups};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%llu cols=%llu base=%p)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, base);
+        return B200I_E_DRIVER;
+    }
+    return 0;
+}
+
 }  // namespace b200i
 
 extern "C" const char *b200i_last_error(void) { return b200i::g_err; }

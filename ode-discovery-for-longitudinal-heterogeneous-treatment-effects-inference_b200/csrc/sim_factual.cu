@@ -159,8 +159,9 @@ struct FactualPtrs {
 };
 
 template <bool GRAM>
-__global__ void __launch_bounds__(128) sim_factual_generic(int64_t n, int T, SimC c, const double *__restrict__ params,
-                                                           FactualPtrs io, const double *__restrict__ static_feature,
+__global__ void __launch_bounds__(128) sim_factual_generic(int64_t n, int64_t pstride, int T, SimC c,
+                                                           const double *__restrict__ params, FactualPtrs io,
+                                                           const double *__restrict__ static_feature,
                                                            StatsWorkspace *ws)
 {
     __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(128) sim_factual_generic(int64_t n, int T, Sim
     const int64_t n_round = ((n + blockDim.x - 1) / blockDim.x) * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += span) {
         const bool exists = i < n;
-        Patient p = load_patient(params, n, exists ? i : 0);
+        Patient p = load_patient(params, pstride, exists ? i : 0);
         FactualState s;
         state_init(s, exists);
         PatientGram pg; Moments mom;
@@ -378,6 +379,27 @@ static int launch_tma(int64_t n, int T, const SimC &c, const double *params, con
     return check_cuda(cudaGetLastError(), "sim_factual_tma launch");
 }
 
+// line-aligned row-class kernel for the full 128-row tiles, generic kernel for the last n % 128 rows;
+// T % 4 != 0 has no aligned mapping and uses the plain tiles
+template <int P, int NB, int MINB, int MODE>
+static int launch_ws_rows(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
+                          double *const out[9], double *seq_len, cudaStream_t st)
+{
+    if (T % 4 != 0) return launch_ws<P, NB, MINB, MODE, false>(n, n, T, c, params, in, out, seq_len, st);
+    const int64_t n_main = (n / 128) * 128, n_tail = n - n_main;
+    int rc = launch_ws<P, NB, MINB, MODE, true>(n_main, n, T, c, params, in, out, seq_len, st);
+    if (rc || n_tail == 0) return rc;
+    FactualPtrs io;
+    io.noise = in[0] + n_main * T; io.rec = in[1] + n_main * T; io.chemo_rvs = in[2] + n_main * T;
+    io.radio_rvs = in[3] + n_main * T;
+    io.assigned = nullptr;
+    for (int a = 0; a < 9; ++a) io.out[a] = out[a] + n_main * T;
+    io.seq_len = seq_len + n_main;
+    sim_factual_generic<false><<<(unsigned)((n_tail + 127) / 128), 128, 0, st>>>(n_tail, n, T, c, params + n_main, io,
+                                                                              nullptr, nullptr);
+    return check_cuda(cudaGetLastError(), "sim_factual_generic (tail) launch");
+}
+
 template <bool GRAM>
 static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
                         double *const out[9], double *seq_len, const double *sf, StatsWorkspace *ws, cudaStream_t st)
@@ -391,17 +413,19 @@ static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const doub
         case 7: return launch_tma<256, 4, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         case 8: return launch_tma<128, 16, 1, 1, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        // generation 6 (sim_factual_ws.cuh): <patients per CTA, 16-column boxes per chunk, CTAs per SM, mode>;
-        // 2x = data movement only (profiling aid)
-        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 14: if (!GRAM) return launch_ws<64, 1, 6, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 20: if (!GRAM) return launch_ws<32, 2, 6, 1>(n, T, c, params, in, out, seq_len, st); break;
-        case 21: if (!GRAM) return launch_ws<64, 2, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
-        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
-        case 23: if (!GRAM) return launch_ws<32, 1, 11, 1>(n, T, c, params, in, out, seq_len, st); break;
+        // generation 6 (sim_factual_ws.cuh): <patients per tile, 16-column boxes per chunk, CTAs per SM, mode>;
+        // launch_ws_rows = the experimental line-aligned row-class mapping; 2x = data movement only (profiling aid)
+        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 14: if (!GRAM) return launch_ws_rows<32, 2, 1, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 15: if (!GRAM) return launch_ws_rows<32, 1, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
+        case 20: if (!GRAM) return launch_ws<32, 2, 6, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 21: if (!GRAM) return launch_ws<32, 1, 11, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 24: if (!GRAM) return launch_ws_rows<32, 2, 1, 1>(n, T, c, params, in, out, seq_len, st); break;
+        case 25: if (!GRAM) return launch_ws_rows<32, 1, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
         default:
             break;
     }
@@ -466,8 +490,8 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
     if (gram)
-        sim_factual_generic<true><<<(unsigned)grid, 128, 0, st>>>(n, T, c, params, io, static_feature, ws);
+        sim_factual_generic<true><<<(unsigned)grid, 128, 0, st>>>(n, n, T, c, params, io, static_feature, ws);
     else
-        sim_factual_generic<false><<<(unsigned)grid, 128, 0, st>>>(n, T, c, params, io, static_feature, ws);
+        sim_factual_generic<false><<<(unsigned)grid, 128, 0, st>>>(n, n, T, c, params, io, static_feature, ws);
     return check_cuda(cudaGetLastError(), "sim_factual_generic launch");
 }

@@ -48,7 +48,9 @@ struct WsCfg {
     static constexpr int FLAG_BYTES = P * FLAG_PITCH;
     static constexpr int DUMMY_BYTES = P * 16;                        // per-thread scratch slot
     static constexpr int LUT_BYTES = 5 * 4 * 16;                      // flag expansion table [array][2 bits] -> double2
-    static constexpr int SMEM_BYTES = STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + LUT_BYTES + 1024;
+    static constexpr int WARP_REGION = (STAGE_BYTES + FLAG_BYTES + DUMMY_BYTES + 1023) & ~1023;   // one tile's buffers
+    static constexpr int SMEM_BYTES = WARP_REGION + LUT_BYTES + 1024;
+    static constexpr int SMEM_BYTES_4 = 4 * WARP_REGION + LUT_BYTES + 1024;   // row-class mapping: four warps
     static_assert(P % (TCH / 2) == 0, "flag expansion mapping");
     static_assert(P % 32 == 0 && TILE_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
@@ -176,6 +178,7 @@ __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int
     PatientGram pg;
     Moments mom;
     for (int cidx = 0; cidx < ncols; ++cidx) {
+        if (t_first + cidx < 0) continue;   // skewed first box: columns left of column 0
         const int box = cidx >> 4, q = (cidx & 15) >> 1, lohi = cidx & 1;
         uint8_t *base = stage + box * 4 * (P * 128) + swz_off<128>((uint32_t)tid, (uint32_t)q) + lohi * 8;
         double *pn = reinterpret_cast<double *>(base), *pu = reinterpret_cast<double *>(base + 1 * P * 128),
@@ -188,89 +191,133 @@ __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int
     }
 }
 
-struct WsRaw {
-    const double *in[4];   // the draw arrays again as raw pointers (whole-row L2 prefetch)
-};
-// opts bit 0: prefetch the next tile's whole rows into L2; bit 1: evict-first hint on every output store;
-// bit 2: evict-last hint on the draw loads; bit 3: L2 prefetch of the tile's later chunks with its first.
-
+// opts bit 1: evict-first hint on every output store; bit 2: evict-last hint on the draw loads.
+//
 // MODE 0: simulator.  MODE 1: data movement only (threads copy draws to outputs) -- profiling aid that
 // measures what the load/store skeleton sustains without the arithmetic.
-template <int P, int NB, int MINB, int MODE>
-__global__ void __launch_bounds__(P, MINB)
-sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ WsRaw raw, int opts, int64_t n, int T, SimC c,
-               const double *__restrict__ params, double *__restrict__ out_ca, double *__restrict__ out_ra, double *__restrict__ out_D,
-               double *__restrict__ out_death, double *__restrict__ out_recov, double *__restrict__ seq_len_out)
+//
+// SKEW (the default): line-aligned row segments for T*8 not a multiple of 128.
+//   The skeleton measurements (profiles/r1_k1_skeleton.md) show that what costs DRAM efficiency is not the
+//   length of a row segment but its alignment: with 512-byte rows (T = 64) even 128-byte boxes sustain 5.7 TB/s,
+//   with 480-byte rows (T = 60) the same boxes start on 32-byte boundaries, every request straddles two
+//   128-byte lines that are fetched / written twice, and the skeleton drops to 3.5-4.5 TB/s.  For T = 60 four
+//   consecutive rows are exactly 15 lines, and row j of such a group becomes line-aligned when its boxes start
+//   at column 16 m - s_j with s_j = (j T) mod 16 (8 j T + 8 (16 m - s_j) = 0 mod 128).  So a work item is
+//   (128 consecutive rows, class j): the 32 rows = j mod 4.  TMA rejects negative start coordinates, so each
+//   class has its own 2-D maps (row pitch 4 T * 8 bytes) whose base is moved instead: the input view of class j
+//   starts s_j columns before its first row (those columns alias the tail of the previous row: read, never
+//   used), the output view starts at the first line boundary inside the row, and the row's first 16 - s_j
+//   columns -- the partial line it shares with the previous row -- are written with ordinary 16-byte stores.
+//   DRAM also wants the accesses of one moment to be dense in address space (giving each class to its own
+//   CTA measured 1.6-1.9 ms: aligned, but every request then opens its own DRAM page).  So a CTA is four warps
+//   = the four classes of one 128-row tile; each warp has its own tiles, barrier and column range (no
+//   divergence inside a warp), and the four leaders issue their loads right after a CTA-wide barrier, so that
+//   the memory system sees one line of each of 128 consecutive rows at once.  Rows beyond the last full
+//   128-row tile go through the generic kernel.
+// tensor maps of the row-class mapping: [class][array]; out arrays = volume, chemo dosage, chemo / radio probability
+struct TmapPackSkew {
+    CUtensorMap in[4][4];
+    CUtensorMap out[4][4];
+};
+template <bool SKEW> struct WsMaps { typedef TmapPack type; };
+template <> struct WsMaps<true> { typedef TmapPackSkew type; };
+
+__device__ __forceinline__ const CUtensorMap *ws_in_map(const TmapPack &m, int, int a) { return &m.in[a]; }
+__device__ __forceinline__ const CUtensorMap *ws_in_map(const TmapPackSkew &m, int j, int a) { return &m.in[j][a]; }
+// o: 0 volume, 1 chemo dosage, 2 chemo probability, 3 radio probability
+__device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPack &m, int, int o)
+{
+    return &m.out[o == 0 ? 0 : (o == 1 ? 1 : (o == 2 ? 5 : 6))];
+}
+__device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPackSkew &m, int j, int o) { return &m.out[j][o]; }
+
+template <int P, int NB, int MINB, int MODE, bool SKEW>
+__global__ void __launch_bounds__(SKEW ? 128 : P, MINB)
+sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opts, int64_t n, int64_t pstride, int T, SimC c,
+               const double *__restrict__ params, double *__restrict__ out_ca, double *__restrict__ out_ra,
+               double *__restrict__ out_D, double *__restrict__ out_death, double *__restrict__ out_recov,
+               double *__restrict__ seq_len_out, double *__restrict__ out_V, double *__restrict__ out_C,
+               double *__restrict__ out_pc, double *__restrict__ out_pr)
 {
     using Cfg = WsCfg<P, NB>;
     constexpr int TCH = Cfg::TCH, HALF = TCH / 2;
+    static_assert(!SKEW || P == 32, "the row-class mapping is one warp per class");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar;
-    uint8_t *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [NB][4][TILE]
+    __shared__ uint64_t full_bars[4];
+    const int tid = threadIdx.x;
+    const int warp = SKEW ? (tid >> 5) : 0;            // row class in the row-class mapping
+    const int rid = SKEW ? (tid & 31) : tid;           // row of the (warp's) tile
+    const bool leader = rid == 0;
+    uint64_t &full_bar = full_bars[warp];
+    uint8_t *smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *tiles = smem_al + warp * Cfg::WARP_REGION;                              // [NB][4][TILE]
     uint8_t *flag_buf = tiles + Cfg::STAGE_BYTES;                                    // [P][FLAG_PITCH]
     uint8_t *dummy_buf = flag_buf + Cfg::FLAG_BYTES;                                 // [P][16]
-    double2 *lut = reinterpret_cast<double2 *>(dummy_buf + Cfg::DUMMY_BYTES);        // [5][4]
+    double2 *lut = reinterpret_cast<double2 *>(smem_al + (SKEW ? 4 : 1) * Cfg::WARP_REGION);   // [5][4]
 
-    const int tid = threadIdx.x;
-    const int nchunks = (T + TCH - 1) / TCH;
-    const int64_t ntiles = (n + P - 1) / P;
-    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_tiles * nchunks;
+    // work items: plain = tile of P rows; row classes = tile of 128 rows (warp j takes the rows = j mod 4)
+    constexpr int ncls = 4;
+    const int64_t n_items = SKEW ? n / 128 : (n + P - 1) / P;
+    const bool opt_evict_first = (opts & 2) != 0, opt_evict_last = (opts & 4) != 0;
 
-    auto cta_sync = [&]() {
+    struct Item {
+        int64_t tile;   // first row = tile * (SKEW ? 128 : P)
+        int j, shift, nboxes, nch;
+    };
+    auto item_of = [&](int64_t w) {
+        Item it;
+        if (SKEW) {
+            it.tile = w; it.j = warp;
+            it.shift = (it.j * T) & 15;                    // 8 (16 m - shift) + 8 j T = 0 mod 128 (T % 4 == 0)
+        } else {
+            it.tile = w; it.j = 0; it.shift = 0;
+        }
+        it.nboxes = (T + it.shift + 15) / 16;
+        it.nch = (it.nboxes + NB - 1) / NB;
+        return it;
+    };
+    auto cta_sync = [&]() {   // everybody who shares this tile
         if (P == 32) __syncwarp(); else __syncthreads();
     };
-    const bool opt_prefetch = (opts & 1) != 0, opt_evict_first = (opts & 2) != 0, opt_evict_last = (opts & 4) != 0,
-               opt_rest_l2 = (opts & 8) != 0;
-    auto prefetch_tile = [&](int64_t tile) {
-        const int64_t r0 = tile * P;
-        if (r0 >= n) return;
-        const int64_t rows = (n - r0 < P) ? (n - r0) : P;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) l2_prefetch_bulk(raw.in[a] + r0 * T, (uint32_t)(rows * T * 8));
+    // chunks per item: the row-class warps run in lockstep, so all of them loop over the longest class
+    const int nch_all = SKEW ? ((T + 12 + 15) / 16 + NB - 1) / NB : ((T + 15) / 16 + NB - 1) / NB;
+    // box m of the item: tile columns [16 m, 16 m + 16) = global columns [16 m - shift, ...)
+    auto load_box = [&](void *dst, int a, const Item &it, int m, uint64_t pol) {
+        const CUtensorMap *map = ws_in_map(maps, it.j, a);
+        const int r0 = SKEW ? (int)(it.tile * 32) : (int)(it.tile * P);
+        if (opt_evict_last) tma_load_2d_hint(dst, map, 16 * m, r0, &full_bar, pol);
+        else tma_load_2d(dst, map, 16 * m, r0, &full_bar);
     };
-    auto issue_load = [&](int64_t tile, int ch) {
-        mbar_arrive_expect_tx(&full_bar, (uint32_t)Cfg::STAGE_BYTES);
-        if (opt_evict_last) {
-            const uint64_t pol = l2_policy_evict_last();
+    // the output views of a shifted class start at its second box (the first, partial one is stored by hand)
+    auto store_box = [&](const void *src, int o, const Item &it, int m, uint64_t pol) {
+        const CUtensorMap *map = ws_out_map(maps, it.j, o);
+        const int r0 = SKEW ? (int)(it.tile * 32) : (int)(it.tile * P);
+        const int c0 = 16 * (m - ((SKEW && it.shift > 0) ? 1 : 0));
+        if (opt_evict_first) tma_store_2d_hint(map, c0, r0, src, pol);
+        else tma_store_2d(map, c0, r0, src);
+    };
+    auto issue_load = [&](const Item &it, int ch) {
+        int nb = it.nboxes - ch * NB;
+        nb = nb > NB ? NB : nb;
+        mbar_arrive_expect_tx(&full_bar, (uint32_t)(nb * 4 * Cfg::TILE_BYTES));
+        const uint64_t pol = opt_evict_last ? l2_policy_evict_last() : 0ull;
+        for (int b = 0; b < nb; ++b)
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    tma_load_2d_hint(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16,
-                                     (int)(tile * P), &full_bar, pol);
-        } else {
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    tma_load_2d(tiles + (b * 4 + a) * Cfg::TILE_BYTES, &maps.in[a], ch * TCH + b * 16, (int)(tile * P),
-                                &full_bar);
-        }
-        // while the tile's last chunk is in flight, pull the next tile's whole rows into L2: DRAM then sees
-        // contiguous P x 480-byte reads and the next tile's chunk loads are L2 hits
-        if (opt_prefetch && nchunks > 1 && ch == nchunks - 1) prefetch_tile(tile + gridDim.x);
-        // bit 3: together with the tile's first chunk, request its remaining boxes into L2 -- DRAM serves every
-        // row in one go and the 128-byte lines that straddle a chunk boundary are fetched once
-        if (opt_rest_l2 && ch == 0) {
-            for (int c0 = TCH; c0 < T; c0 += 16)
-#pragma unroll
-                for (int a = 0; a < 4; ++a) tma_prefetch_2d(&maps.in[a], c0, (int)(tile * P));
-        }
+            for (int a = 0; a < 4; ++a)
+                load_box(tiles + (b * 4 + a) * Cfg::TILE_BYTES, a, it, ch * NB + b, pol);
     };
 
-    if (tid == 0) {
+    if (leader) {
         mbar_init(&full_bar, 1);
         mbar_fence_init();
 #pragma unroll
-        for (int a = 0; a < 4; ++a) tma_prefetch_desc(&maps.in[a]);
-        tma_prefetch_desc(&maps.out[0]); tma_prefetch_desc(&maps.out[1]);
-        tma_prefetch_desc(&maps.out[5]); tma_prefetch_desc(&maps.out[6]);
-        if (total > 0) {
-            if (opt_prefetch && nchunks > 1) prefetch_tile(blockIdx.x);
-            issue_load(blockIdx.x, 0);
+        for (int a = 0; a < 4; ++a) {
+            tma_prefetch_desc(ws_in_map(maps, warp, a));
+            tma_prefetch_desc(ws_out_map(maps, warp, a));
         }
     }
+    __syncthreads();
+    if (leader && (int64_t)blockIdx.x < n_items) issue_load(item_of(blockIdx.x), 0);
     if (tid < 20) {
         // flag expansion table: array a in {chemo app, radio app, radio dosage, death, recovery}, index = the
         // array's bit of the even column | its bit of the odd column << 1
@@ -294,9 +341,9 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
         pin(k.sphere); pin(k.inv_sphere); pin(k.decay); pin(k.dose); pin(k.death); pin(k.ndensity); pin(k.inv15);
     }
 
-    const uint32_t off0 = (uint32_t)tid * 128u + (((uint32_t)tid & 7u) << 4);   // swizzled 16-byte unit 0 of the row
-    uint8_t *flags_s = flag_buf + tid * Cfg::FLAG_PITCH;
-    double *dummy = reinterpret_cast<double *>(dummy_buf + tid * 16);
+    const uint32_t off0 = (uint32_t)rid * 128u + (((uint32_t)rid & 7u) << 4);   // swizzled 16-byte unit 0 of the row
+    uint8_t *flags_s = flag_buf + rid * Cfg::FLAG_PITCH;
+    double *dummy = reinterpret_cast<double *>(dummy_buf + rid * 16);
     WsPatient p;
     WsState s;
     WsSlow slow;
@@ -306,24 +353,24 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
     p.K = fm::log_num(1.0); p.rho = p.beta_c = p.rd = p.nb = p.si = 0.0;
     s.V = s.Cq = s.zq = s.ucp = s.udp = s.S = 0.0; s.flp = 0u; s.alive = false; s.t_end = 0;
     double v0 = 0.0;
-    int64_t patient = 0;
-    bool exists = false, tile_slow = false;
     const int Tm1 = T - 1;
-    int64_t tile = blockIdx.x;
-    int ch = 0;
+    uint32_t phase = 0;
 
-    for (int64_t g = 0; g < total; ++g) {
-        if (MODE == 0 && ch == 0) {
-            patient = tile * P + tid;
-            exists = patient < n;
+    for (int64_t wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+        const Item it = item_of(wi);
+        // ---- the item's patients: lane <-> row ----
+        const int64_t patient = SKEW ? it.tile * 128 + ncls * rid + it.j : it.tile * P + tid;
+        const bool exists = patient < n;
+        bool tile_slow = false;
+        if (MODE == 0) {
             const int64_t pi = exists ? patient : 0;
             v0 = exists ? __ldg(params + pi) : 1.0;
-            const double alpha = __ldg(params + 1 * n + pi), beta = __ldg(params + 3 * n + pi);
-            const double Kcap = __ldg(params + 5 * n + pi);
-            const double ci = __ldg(params + 6 * n + pi), ri = __ldg(params + 7 * n + pi);
-            const double cb = __ldg(params + 8 * n + pi), rb = __ldg(params + 9 * n + pi);
-            p.rho = __ldg(params + 2 * n + pi);
-            p.beta_c = __ldg(params + 4 * n + pi);
+            const double alpha = __ldg(params + 1 * pstride + pi), beta = __ldg(params + 3 * pstride + pi);
+            const double Kcap = __ldg(params + 5 * pstride + pi);
+            const double ci = __ldg(params + 6 * pstride + pi), ri = __ldg(params + 7 * pstride + pi);
+            const double cb = __ldg(params + 8 * pstride + pi), rb = __ldg(params + 9 * pstride + pi);
+            p.rho = __ldg(params + 2 * pstride + pi);
+            p.beta_c = __ldg(params + 4 * pstride + pi);
             p.K = fm::log_num(Kcap);
             p.si = ri;
             p.nb = -rb;
@@ -339,193 +386,214 @@ sim_factual_ws(const __grid_constant__ TmapPack maps, const __grid_constant__ Ws
             const bool bad = exists && !ok;
             tile_slow = (P == 32) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0);
             if (tile_slow) {
-                slow.p = load_patient(params, n, pi);
+                slow.p = load_patient(params, pstride, pi);
                 state_init(slow.s, exists);
             }
-            // the next tile's parameters: pull them into L2 now, the loads above then cost an L2 hit
-            const int64_t pnext = patient + (int64_t)gridDim.x * P;
-            if ((tid & 3) == 0 && pnext < n) {
-#pragma unroll
-                for (int a = 0; a < 10; ++a)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(params + a * n + pnext));
-            }
         }
-        mbar_wait(&full_bar, (uint32_t)(g & 1));
-        const int t_first = ch * TCH;
 
-        if (MODE == 0 && tile_slow) {
-            ws_slow_chunk<P>(tiles, flags_s, tid, t_first, TCH, T, c, &slow);
-        } else {
-            // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
-            double *prevC = dummy, *prevP = dummy + 1;
-            uint8_t *flag_dst = flags_s + 1;   // byte of column t_first - 1 (dummy byte for the first group)
-            auto run_box = [&](auto fill_tag, uint8_t *box, int tb) {
-                constexpr bool FILL = decltype(fill_tag)::value;
+        for (int ch = 0; ch < nch_all; ++ch) {
+          if (ch < it.nch) {
+            mbar_wait(&full_bar, phase);
+            phase ^= 1u;
+            const int t_first = ch * TCH - it.shift;             // global column of the chunk's first tile column
+            int nb = it.nboxes - ch * NB;
+            nb = nb > NB ? NB : nb;
+
+            if (MODE == 0 && tile_slow) {
+                ws_slow_chunk<P>(tiles, flags_s, rid, t_first, nb * 16, T, c, &slow);
+            } else {
+                // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
+                double *prevC = dummy, *prevP = dummy + 1;
+                int t_done = -1;                               // last column this chunk has simulated
+                auto run_quads = [&](auto fill_tag, uint8_t *box, int tb, int lb, int h0, int h1) {
+                    constexpr bool FILL = decltype(fill_tag)::value;
 #pragma unroll 1
-                for (int h = 0; h < 4; ++h) {
-                    const uint32_t offA = off0 ^ ((uint32_t)h << 5), offB = offA ^ 16u;
-                    double2 *pa[4], *pb[4];
+                    for (int h = h0; h < h1; ++h) {
+                        const uint32_t offA = off0 ^ ((uint32_t)h << 5), offB = offA ^ 16u;
+                        double2 *pa[4], *pb[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        pa[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offA);
-                        pb[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offB);
-                    }
-                    const double2 nzA = *pa[0], urA = *pa[1], ucA = *pa[2], udA = *pa[3];
-                    const double2 nzB = *pb[0], urB = *pb[1], ucB = *pb[2], udB = *pb[3];
-                    const int t0 = tb + h * 4;
-                    double oV[4], oC[4], oP[4];
-                    unsigned oF[4];
-                    if (MODE == 1) {
-                        oV[0] = nzA.x; oV[1] = nzA.y; oV[2] = nzB.x; oV[3] = nzB.y;
-                        oC[0] = urA.x; oC[1] = urA.y; oC[2] = urB.x; oC[3] = urB.y;
-                        oP[0] = udA.x; oP[1] = udA.y; oP[2] = udB.x; oP[3] = udB.y;
-                        oF[0] = oF[1] = oF[2] = oF[3] = 0u;
-                    } else {
-                        ws_body<FILL, 0>(t0, Tm1, k, p, s, w, v0, nzA.x, urA.x, ucA.x, udA.x, oV[0], oC[0], oP[0], oF[0]);
-                        ws_body<FILL, 1>(t0 + 1, Tm1, k, p, s, w, v0, nzA.y, urA.y, ucA.y, udA.y, oV[1], oC[1], oP[1], oF[1]);
-                        ws_body<FILL, 2>(t0 + 2, Tm1, k, p, s, w, v0, nzB.x, urB.x, ucB.x, udB.x, oV[2], oC[2], oP[2], oF[2]);
-                        ws_body<FILL, 3>(t0 + 3, Tm1, k, p, s, w, v0, nzB.y, urB.y, ucB.y, udB.y, oV[3], oC[3], oP[3], oF[3]);
+                        for (int a = 0; a < 4; ++a) {
+                            pa[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offA);
+                            pb[a] = reinterpret_cast<double2 *>(box + a * Cfg::TILE_BYTES + offB);
+                        }
+                        const double2 nzA = *pa[0], urA = *pa[1], ucA = *pa[2], udA = *pa[3];
+                        const double2 nzB = *pb[0], urB = *pb[1], ucB = *pb[2], udB = *pb[3];
+                        const int t0 = tb + h * 4;
+                        double oV[4], oC[4], oP[4];
+                        unsigned oF[4];
+                        if (MODE == 1) {
+                            oV[0] = nzA.x; oV[1] = nzA.y; oV[2] = nzB.x; oV[3] = nzB.y;
+                            oC[0] = urA.x; oC[1] = urA.y; oC[2] = urB.x; oC[3] = urB.y;
+                            oP[0] = udA.x; oP[1] = udA.y; oP[2] = udB.x; oP[3] = udB.y;
+                            oF[0] = oF[1] = oF[2] = oF[3] = 0u;
+                        } else {
+                            ws_body<FILL, 0>(t0, Tm1, k, p, s, w, v0, nzA.x, urA.x, ucA.x, udA.x, oV[0], oC[0], oP[0], oF[0]);
+                            ws_body<FILL, 1>(t0 + 1, Tm1, k, p, s, w, v0, nzA.y, urA.y, ucA.y, udA.y, oV[1], oC[1], oP[1], oF[1]);
+                            ws_body<FILL, 2>(t0 + 2, Tm1, k, p, s, w, v0, nzB.x, urB.x, ucB.x, udB.x, oV[2], oC[2], oP[2], oF[2]);
+                            ws_body<FILL, 3>(t0 + 3, Tm1, k, p, s, w, v0, nzB.y, urB.y, ucB.y, udB.y, oV[3], oC[3], oP[3], oF[3]);
 #pragma unroll
-                        for (int j = 0; j < 14; ++j) w[j] = w[j + 4];
-                        if (t0 + 3 > s.t_end) {
-                            // columns after the patient's last simulated one stay zero (rare: death / recovery /
-                            // t = T-1).  oV[j] belongs to column t0+j, the treatment outputs to column t0+j-1.
+                            for (int j = 0; j < 14; ++j) w[j] = w[j + 4];
+                            if (t0 + 3 > s.t_end) {
+                                // columns after the patient's last simulated one stay zero (rare: death / recovery
+                                // / t = T-1).  oV[j] belongs to column t0+j, the treatment outputs to column t0+j-1.
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (t0 + j > s.t_end) oV[j] = 0.0;
-                                if (t0 + j - 1 > s.t_end) { oC[j] = oP[j] = 0.0; oF[j] = 0u; }
+                                for (int j = 0; j < 4; ++j) {
+                                    if (t0 + j > s.t_end) oV[j] = 0.0;
+                                    if (t0 + j - 1 > s.t_end) { oC[j] = oP[j] = 0.0; oF[j] = 0u; }
+                                }
                             }
                         }
+                        *pa[0] = make_double2(oV[0], oV[1]);
+                        *pb[0] = make_double2(oV[2], oV[3]);
+                        *prevC = oC[0]; *prevP = oP[0];
+                        *pa[1] = make_double2(oC[1], oC[2]);
+                        *pa[3] = make_double2(oP[1], oP[2]);
+                        pb[1]->x = oC[3];
+                        pb[3]->x = oP[3];
+                        prevC = &pb[1]->y; prevP = &pb[3]->y;
+                        uint8_t *fd = flags_s + 1 + lb + h * 4;    // byte of column t0 - 1 (byte 1 = dummy)
+                        fd[0] = (uint8_t)oF[0]; fd[1] = (uint8_t)oF[1]; fd[2] = (uint8_t)oF[2]; fd[3] = (uint8_t)oF[3];
+                        t_done = t0 + 3;
                     }
-                    *pa[0] = make_double2(oV[0], oV[1]);
-                    *pb[0] = make_double2(oV[2], oV[3]);
-                    *prevC = oC[0]; *prevP = oP[0];
-                    *pa[1] = make_double2(oC[1], oC[2]);
-                    *pa[3] = make_double2(oP[1], oP[2]);
-                    pb[1]->x = oC[3];
-                    pb[3]->x = oP[3];
-                    prevC = &pb[1]->y; prevP = &pb[3]->y;
-                    flag_dst[0] = (uint8_t)oF[0]; flag_dst[1] = (uint8_t)oF[1];
-                    flag_dst[2] = (uint8_t)oF[2]; flag_dst[3] = (uint8_t)oF[3];
-                    flag_dst += 4;
+                };
+                for (int b = 0; b < nb; ++b) {
+                    uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
+                    const int tb = t_first + b * 16;
+                    // quads left of column 0 (skewed first box) and right of the horizon are skipped; the window
+                    // fills during columns 0..15, which have their own code copy
+                    int h_lo = tb < 0 ? (-tb) >> 2 : 0;
+                    int h_hi = (T - tb + 3) >> 2;
+                    h_hi = h_hi > 4 ? 4 : h_hi;
+                    int h_fill = (16 - tb) >> 2;                 // quads with t0 < 16
+                    h_fill = h_fill < h_lo ? h_lo : (h_fill > h_hi ? h_hi : h_fill);
+                    if (h_fill > h_lo) run_quads(std::true_type{}, box, tb, b * 16, h_lo, h_fill);
+                    if (h_hi > h_fill) run_quads(std::false_type{}, box, tb, b * 16, h_fill, h_hi);
                 }
-            };
-#pragma unroll 1
-            for (int b = 0; b < NB; ++b) {
-                uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
-                if (t_first + b * 16 == 0)
-                    run_box(std::true_type{}, box, 0);
-                else
-                    run_box(std::false_type{}, box, t_first + b * 16);
-            }
-            // treatment of the chunk's last column (the next chunk's first body repeats it from the same state)
-            {
-                const int tl = t_first + TCH - 1;
-                double pr = 0.0, C1 = 0.0;
-                unsigned f = 0u;
-                if (MODE == 0 && tl <= s.t_end && tl >= 1) {
-                    bool ra, ca;
-                    ws_treat(k, s, pr, ra, ca, C1);
-                    f = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
+                // treatment of the chunk's last simulated column (the next chunk's first body repeats it from the
+                // same state)
+                if (t_done >= 0) {
+                    double pr = 0.0, C1 = 0.0;
+                    unsigned f = 0u;
+                    if (MODE == 0 && t_done <= s.t_end && t_done >= 1) {
+                        bool ra, ca;
+                        ws_treat(k, s, pr, ra, ca, C1);
+                        f = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
+                    }
+                    *prevC = C1; *prevP = pr;
+                    flags_s[2 + (t_done - t_first)] = (uint8_t)f;
                 }
-                *prevC = C1; *prevP = pr; flag_dst[0] = (uint8_t)f;
             }
-        }
-        fence_proxy_async_smem();
-        cta_sync();
-        if (tid == 0) {
+            fence_proxy_async_smem();
+            cta_sync();
             const int src_pc = (MODE == 0 && tile_slow) ? 2 : 3;   // fast path: one sigmoid serves both arrays
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
-                const int c0 = t_first + b * 16;
-                if (c0 < T && opt_evict_first) {
-                    const uint64_t pol = l2_policy_evict_first();
-                    tma_store_2d_hint(&maps.out[0], c0, (int)(tile * P), box + 0 * Cfg::TILE_BYTES, pol);
-                    tma_store_2d_hint(&maps.out[1], c0, (int)(tile * P), box + 1 * Cfg::TILE_BYTES, pol);
-                    tma_store_2d_hint(&maps.out[5], c0, (int)(tile * P), box + src_pc * Cfg::TILE_BYTES, pol);
-                    tma_store_2d_hint(&maps.out[6], c0, (int)(tile * P), box + 3 * Cfg::TILE_BYTES, pol);
-                } else if (c0 < T) {
-                    tma_store_2d(&maps.out[0], c0, (int)(tile * P), box + 0 * Cfg::TILE_BYTES);
-                    tma_store_2d(&maps.out[1], c0, (int)(tile * P), box + 1 * Cfg::TILE_BYTES);
-                    tma_store_2d(&maps.out[5], c0, (int)(tile * P), box + src_pc * Cfg::TILE_BYTES);
-                    tma_store_2d(&maps.out[6], c0, (int)(tile * P), box + 3 * Cfg::TILE_BYTES);
+            if (SKEW && ch == 0 && it.shift > 0) {
+                // head of the rows: the 16 - shift columns before the first line boundary, tile columns
+                // [shift, 16) of box 0, by hand (16-byte stores; lanes <-> column pairs, rows in turn)
+                const int npairs = (16 - it.shift) >> 1;
+                const int64_t row0 = it.tile * 128 + it.j;
+                for (int idx = rid; idx < 32 * npairs; idx += 32) {
+                    const int row = idx / npairs, cpair = idx - row * npairs;
+                    const uint32_t so = swz_off<128>((uint32_t)row, (uint32_t)((it.shift >> 1) + cpair));
+                    const int64_t go = (row0 + ncls * row) * T + 2 * cpair;
+                    const double2 vV = *reinterpret_cast<const double2 *>(tiles + 0 * Cfg::TILE_BYTES + so);
+                    const double2 vC = *reinterpret_cast<const double2 *>(tiles + 1 * Cfg::TILE_BYTES + so);
+                    const double2 vc = *reinterpret_cast<const double2 *>(tiles + src_pc * Cfg::TILE_BYTES + so);
+                    const double2 vr = *reinterpret_cast<const double2 *>(tiles + 3 * Cfg::TILE_BYTES + so);
+                    __stcs(reinterpret_cast<double2 *>(out_V + go), vV);
+                    __stcs(reinterpret_cast<double2 *>(out_C + go), vC);
+                    __stcs(reinterpret_cast<double2 *>(out_pc + go), vc);
+                    __stcs(reinterpret_cast<double2 *>(out_pr + go), vr);
                 }
+                __syncwarp();
             }
-            tma_store_commit();
-        }
-        // the next chunk's loads go out before the flag expansion, which then overlaps their latency
-        const bool last = (ch == nchunks - 1);
-        if (tid == 0) {
-            tma_store_wait_read();   // the tiles are free again
-            if (g + 1 < total) issue_load(last ? tile + gridDim.x : tile, last ? 0 : ch + 1);
-        }
-        // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes.
-        // Each array's double2 comes from a 4-entry table indexed by its bit of the two columns.
-        {
-            static_assert(P >= HALF, "flag expansion mapping: every thread keeps one column pair");
-            constexpr int RSTEP = P / HALF;                      // rows advanced per iteration
-            const int64_t row0 = tile * P;
-            const int rows_valid = (n - row0 < P) ? (int)(n - row0) : P;
-            const int cp = tid % HALF, r_first = tid / HALF;
-            const int col = t_first + cp * 2;
-            if (col < T) {   // T is even: a column pair is inside or outside as a whole
-                const int64_t tile_ofs = row0 * T + col;
-                double *b_ca = out_ca + tile_ofs, *b_ra = out_ra + tile_ofs, *b_D = out_D + tile_ofs,
-                       *b_de = out_death + tile_ofs, *b_re = out_recov + tile_ofs;
-                const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 2;
-                int ofs = r_first * T;
+            if (leader) {
+                const uint64_t pol = opt_evict_first ? l2_policy_evict_first() : 0ull;
+                for (int b = 0; b < nb; ++b) {
+                    uint8_t *box = tiles + b * 4 * Cfg::TILE_BYTES;
+                    const int m = ch * NB + b;
+                    if (SKEW && it.shift > 0 && m == 0) continue;   // stored by hand above
+                    if (16 * m - it.shift < T) {
+                        store_box(box + 0 * Cfg::TILE_BYTES, 0, it, m, pol);
+                        store_box(box + 1 * Cfg::TILE_BYTES, 1, it, m, pol);
+                        store_box(box + src_pc * Cfg::TILE_BYTES, 2, it, m, pol);
+                        store_box(box + 3 * Cfg::TILE_BYTES, 3, it, m, pol);
+                    }
+                }
+                tma_store_commit();
+                tma_store_wait_read();   // the tiles are free again
+            }
+          }
+            // the next chunk's loads go out before the flag expansion, which then overlaps their latency; the
+            // row-class warps issue them together (see above)
+            if (SKEW) __syncthreads();
+            if (leader) {
+                if (ch + 1 < it.nch) issue_load(it, ch + 1);
+                else if (ch + 1 == nch_all && wi + gridDim.x < n_items) issue_load(item_of(wi + gridDim.x), 0);
+            }
+          if (ch < it.nch) {
+            const int t_first = ch * TCH - it.shift;
+            int nb = it.nboxes - ch * NB;
+            nb = nb > NB ? NB : nb;
+            // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes.
+            // Each array's double2 comes from a 4-entry table indexed by its bit of the two columns.
+            {
+                static_assert(P >= HALF, "flag expansion mapping: every thread keeps one column pair");
+                constexpr int RSTEP = P / HALF;                      // rows advanced per iteration
+                const int64_t row0 = SKEW ? it.tile * 128 + it.j : it.tile * P;
+                const int rmul = SKEW ? ncls : 1;                        // global rows per local row
+                const int rows_valid = SKEW ? 32 : ((n - row0 < P) ? (int)(n - row0) : P);
+                const int cp = rid % HALF, r_first = rid / HALF;
+                const int col = t_first + cp * 2;
+                if (col >= 0 && col < T && cp * 2 < nb * 16) {   // T, shift even: a column pair is in or out as a whole
+                    const int64_t tile_ofs = row0 * T + col;
+                    double *b_ca = out_ca + tile_ofs, *b_ra = out_ra + tile_ofs, *b_D = out_D + tile_ofs,
+                           *b_de = out_death + tile_ofs, *b_re = out_recov + tile_ofs;
+                    const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 2;
+                    int ofs = r_first * rmul * T;
 #pragma unroll 4
-                for (int row = r_first; row < rows_valid; row += RSTEP, ofs += RSTEP * T, fp += RSTEP * Cfg::FLAG_PITCH) {
-                    const unsigned two = *reinterpret_cast<const unsigned short *>(fp);
-                    // bits: 1 chemo, 2 radio, 4 death, 8 recovery; low byte = even column, high byte = odd column
-                    const unsigned i_ca = (two & 1u) | ((two >> 7) & 2u);
-                    const unsigned i_ra = ((two >> 1) & 1u) | ((two >> 8) & 2u);
-                    const unsigned i_de = ((two >> 2) & 1u) | ((two >> 9) & 2u);
-                    const unsigned i_re = ((two >> 3) & 1u) | ((two >> 10) & 2u);
-                    const double2 v_ca = lut[0 + i_ca], v_ra = lut[4 + i_ra], v_D = lut[8 + i_ra], v_de = lut[12 + i_de],
-                                  v_re = lut[16 + i_re];
-                    if (opt_evict_first) {
-                        __stcs(reinterpret_cast<double2 *>(b_ca + ofs), v_ca);
-                        __stcs(reinterpret_cast<double2 *>(b_ra + ofs), v_ra);
-                        __stcs(reinterpret_cast<double2 *>(b_D + ofs), v_D);
-                        __stcs(reinterpret_cast<double2 *>(b_de + ofs), v_de);
-                        __stcs(reinterpret_cast<double2 *>(b_re + ofs), v_re);
-                    } else {
-                        *reinterpret_cast<double2 *>(b_ca + ofs) = v_ca;
-                        *reinterpret_cast<double2 *>(b_ra + ofs) = v_ra;
-                        *reinterpret_cast<double2 *>(b_D + ofs) = v_D;
-                        *reinterpret_cast<double2 *>(b_de + ofs) = v_de;
-                        *reinterpret_cast<double2 *>(b_re + ofs) = v_re;
+                    for (int row = r_first; row < rows_valid;
+                         row += RSTEP, ofs += RSTEP * rmul * T, fp += RSTEP * Cfg::FLAG_PITCH) {
+                        const unsigned two = *reinterpret_cast<const unsigned short *>(fp);
+                        // bits: 1 chemo, 2 radio, 4 death, 8 recovery; low byte = even column, high byte = odd column
+                        const unsigned i_ca = (two & 1u) | ((two >> 7) & 2u);
+                        const unsigned i_ra = ((two >> 1) & 1u) | ((two >> 8) & 2u);
+                        const unsigned i_de = ((two >> 2) & 1u) | ((two >> 9) & 2u);
+                        const unsigned i_re = ((two >> 3) & 1u) | ((two >> 10) & 2u);
+                        const double2 v_ca = lut[0 + i_ca], v_ra = lut[4 + i_ra], v_D = lut[8 + i_ra],
+                                      v_de = lut[12 + i_de], v_re = lut[16 + i_re];
+                        if (opt_evict_first) {
+                            __stcs(reinterpret_cast<double2 *>(b_ca + ofs), v_ca);
+                            __stcs(reinterpret_cast<double2 *>(b_ra + ofs), v_ra);
+                            __stcs(reinterpret_cast<double2 *>(b_D + ofs), v_D);
+                            __stcs(reinterpret_cast<double2 *>(b_de + ofs), v_de);
+                            __stcs(reinterpret_cast<double2 *>(b_re + ofs), v_re);
+                        } else {
+                            *reinterpret_cast<double2 *>(b_ca + ofs) = v_ca;
+                            *reinterpret_cast<double2 *>(b_ra + ofs) = v_ra;
+                            *reinterpret_cast<double2 *>(b_D + ofs) = v_D;
+                            *reinterpret_cast<double2 *>(b_de + ofs) = v_de;
+                            *reinterpret_cast<double2 *>(b_re + ofs) = v_re;
+                        }
                     }
                 }
             }
+            cta_sync();   // every thread is done with the flag bytes before the next chunk rewrites them
+          }
         }
-        cta_sync();   // every thread is done with the flag bytes before the next chunk rewrites them
-        if (last) {
-            if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
-            ch = 0;
-            tile += gridDim.x;
-        } else {
-            ++ch;
-        }
+        if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
     }
-    if (tid == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
 }
 
-// tuning switches of the data-movement skeleton (see WsRaw); B200I_WS_OPTS overrides the default
+// tuning switches of the data-movement skeleton; B200I_WS_OPTS overrides the default
 static int ws_env_opts()
 {
     const char *e = getenv("B200I_WS_OPTS");
     return e ? atoi(e) : 6;   // measured best: evict-first on output stores, evict-last on draw loads
 }
 
-template <int P, int NB, int MINB, int MODE>
-static int launch_ws(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
-                     double *const out[9], double *seq_len, cudaStream_t st)
+static int ws_encode(TmapPack &pack, int64_t n, int T, int P, const double *const in[4], double *const out[9])
 {
-    using Cfg = WsCfg<P, NB>;
-    TmapPack pack;
     for (int a = 0; a < 4; ++a) {
         int rc = encode_tmap_2d_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, P, 16, false);
         if (rc) return rc;
@@ -534,20 +602,51 @@ static int launch_ws(int64_t n, int T, const SimC &c, const double *params, cons
         int rc = encode_tmap_2d_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, P, 16, false);
         if (rc) return rc;
     }
-    auto kern = sim_factual_ws<P, NB, MINB, MODE>;
-    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    return 0;
+}
+// per-class views of the (n, T) arrays, n a multiple of 4: class j = rows j, j+4, ... with a pitch of 4 rows
+static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int ncls, const double *const in[4], double *const out[9])
+{
+    const int oidx[4] = {0, 1, 5, 6};   // volume, chemo dosage, chemo / radio probabilities
+    for (int j = 0; j < ncls; ++j) {
+        const int shift = (j * T) & (4 * ncls - 1), head = (16 - shift) & 15;
+        for (int a = 0; a < 4; ++a) {
+            int rc = encode_tmap_2d_pitched_f64(&pack.in[j][a], in[a] + (j * T - shift), (uint64_t)(n / ncls),
+                                                (uint64_t)(T + shift), (uint64_t)T * 8 * ncls, 32, 16);
+            if (rc) return rc;
+            rc = encode_tmap_2d_pitched_f64(&pack.out[j][a], out[oidx[a]] + (j * T + head), (uint64_t)(n / ncls),
+                                            (uint64_t)(T - head), (uint64_t)T * 8 * ncls, 32, 16);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+template <int P, int NB, int MINB, int MODE, bool SKEW>
+static int launch_ws(int64_t n, int64_t pstride, int T, const SimC &c, const double *params, const double *const in[4],
+                     double *const out[9], double *seq_len, cudaStream_t st)
+{
+    using Cfg = WsCfg<P, NB>;
+    if (n <= 0) return 0;
+    typename WsMaps<SKEW>::type pack;
+    {
+        int rc = ws_encode(pack, n, T, SKEW ? 4 : P, in, out);
+        if (rc) return rc;
+    }
+    auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW>;
+    constexpr int SMEM = SKEW ? Cfg::SMEM_BYTES_4 : Cfg::SMEM_BYTES;
+    constexpr int NT = SKEW ? 128 : P;
+    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int per_sm = 0;
-    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P, Cfg::SMEM_BYTES));
+    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SMEM));
     B200I_REQUIRE(per_sm >= 1, B200I_E_UNSUPPORTED, "sim_factual_ws<%d,%d>: does not fit on an SM", P, NB);
-    const int64_t ntiles = (n + P - 1) / P;
+    const int64_t n_items = SKEW ? n / 128 : (n + P - 1) / P;
     int64_t grid = (int64_t)num_sms() * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    // out order: V C D ca ra pc pr death recov
-    WsRaw raw;
-    for (int a = 0; a < 4; ++a) raw.in[a] = in[a];
+    if (grid > n_items) grid = n_items;
     static const int opts = ws_env_opts();
-    kern<<<(unsigned)grid, P, Cfg::SMEM_BYTES, st>>>(pack, raw, opts, n, T, c, params, out[3], out[4], out[2], out[7],
-                                                     out[8], seq_len);
+    // out order: V C D ca ra pc pr death recov
+    kern<<<(unsigned)grid, NT, SMEM, st>>>(pack, opts, n, pstride, T, c, params, out[3], out[4], out[2], out[7],
+                                                     out[8], seq_len, out[0], out[1], out[5], out[6]);
     return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
 }
 

@@ -94,6 +94,38 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// 3-D variants (column, row in group, group) for the line-aligned row-class mapping of sim_factual_ws
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                                 uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)),
+          "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *map, int c0, int c1, int c2, const void *smem_src,
+                                                  uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+                 : "memory");
+}
 // one box of a tiled tensor map -> L2 (no shared-memory destination)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
 {
@@ -130,5 +162,12 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t p, uint32_t q)
 // Encodes a 2-D tiled map over a (rows, cols) float64 row-major array: box = {box_cols, box_rows}.
 int encode_tmap_2d_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols,
                        uint32_t box_rows, uint32_t box_cols, bool promote_256);
+// 2-D map with an explicit row pitch (bytes): box = {box_cols, box_rows}, 128-byte rows, SWIZZLE_128B
+int encode_tmap_2d_pitched_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                               uint32_t box_rows, uint32_t box_cols);
+// The same array seen as {cols, group_rows, rows / group_rows}: box = {box_cols, 1, box_groups}, i.e. every
+// group_rows-th row.  rows must be a multiple of group_rows.
+int encode_tmap_3d_rowgroups_f64(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t group_rows,
+                                 uint32_t box_groups, uint32_t box_cols);
 
 }  // namespace b200i

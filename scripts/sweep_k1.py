@@ -21,7 +21,7 @@ FUSED = [bool(int(v)) for v in os.environ.get('FUSED', '0').split(',')]
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    T = 60
+    T = int(os.environ.get('T', '60'))
     dev.require_cuda()
     g = torch.Generator(device='cuda'); g.manual_seed(0)
     # synthetic cohort with the parameter distribution's typical magnitudes (timing only)
