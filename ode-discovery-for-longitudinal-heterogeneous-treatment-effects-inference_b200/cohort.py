@@ -74,7 +74,9 @@ def source_prefix_length(row_offsets, n_total):
 
 class FactualFitPipeline:
     def __init__(self, n_local, T=60, window_size=15, threshold=1e-3, alpha=0.5, max_iter=100, variant=0,
-                 fused=False):
+                 fused=False, pitch=None):
+        """pitch: row pitch (elements) of the device-resident (N,T) arrays; None = dense rows (the reference's
+        numpy layout), dev.aligned_pitch(T) = rows padded to 128-byte lines (the faster layout)."""
         dev.require_cuda()
         self.n, self.T = int(n_local), int(T)
         self.consts = dev.sim_consts(window_size, 0)
@@ -83,8 +85,9 @@ class FactualFitPipeline:
         f64 = dict(dtype=torch.float64, device='cuda')
         self.params = torch.empty((10, self.n), **f64)
         self.static = torch.empty((self.n,), **f64)
-        self.draws = [torch.empty((self.n, self.T), **f64) for _ in range(4)]   # noise, recovery, chemo, radio
-        self.out = {k: torch.empty((self.n, self.T), **f64) for k in dev.FACTUAL_OUT_KEYS}
+        self.pitch = self.T if pitch is None else int(pitch)
+        self.draws = [dev.alloc_rows(self.n, self.T, self.pitch) for _ in range(4)]   # noise, recovery, chemo, radio
+        self.out = {k: dev.alloc_rows(self.n, self.T, self.pitch) for k in dev.FACTUAL_OUT_KEYS}
         self.out['sequence_lengths'] = torch.empty((self.n,), **f64)
         self.stats = torch.zeros(dev.STATS_DOUBLES, **f64)
         self.coefs = None

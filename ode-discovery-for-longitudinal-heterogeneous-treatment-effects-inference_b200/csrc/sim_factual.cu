@@ -385,9 +385,9 @@ template <int P, int NB, int MINB, int MODE>
 static int launch_ws_rows(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
                           double *const out[9], double *seq_len, cudaStream_t st)
 {
-    if (T % 4 != 0) return launch_ws<P, NB, MINB, MODE, false>(n, n, T, c, params, in, out, seq_len, st);
+    if (T % 4 != 0) return launch_ws<P, NB, MINB, MODE, false>(n, n, T, T, c, params, in, out, seq_len, st);
     const int64_t n_main = (n / 128) * 128, n_tail = n - n_main;
-    int rc = launch_ws<P, NB, MINB, MODE, true>(n_main, n, T, c, params, in, out, seq_len, st);
+    int rc = launch_ws<P, NB, MINB, MODE, true>(n_main, n, T, T, c, params, in, out, seq_len, st);
     if (rc || n_tail == 0) return rc;
     FactualPtrs io;
     io.noise = in[0] + n_main * T; io.rec = in[1] + n_main * T; io.chemo_rvs = in[2] + n_main * T;
@@ -401,9 +401,12 @@ static int launch_ws_rows(int64_t n, int T, const SimC &c, const double *params,
 }
 
 template <bool GRAM>
-static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
-                        double *const out[9], double *seq_len, const double *sf, StatsWorkspace *ws, cudaStream_t st)
+static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC &c, const double *params,
+                        const double *const in[4], double *const out[9], double *seq_len, const double *sf,
+                        StatsWorkspace *ws, cudaStream_t st)
 {
+    B200I_REQUIRE(pitch == T || (variant >= 10 && variant <= 13) || (variant >= 20 && variant <= 22), B200I_E_UNSUPPORTED,
+                  "sim_factual: variant %d needs dense rows (row_pitch %lld, T %d)", variant, (long long)pitch, T);
     switch (variant) {
         case 2: return launch_tma<128, 8, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         case 3: return launch_tma<128, 4, 2, 3, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
@@ -415,15 +418,15 @@ static int dispatch_tma(int variant, int64_t n, int T, const SimC &c, const doub
         case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         // generation 6 (sim_factual_ws.cuh): <patients per tile, 16-column boxes per chunk, CTAs per SM, mode>;
         // launch_ws_rows = the experimental line-aligned row-class mapping; 2x = data movement only (profiling aid)
-        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
-        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
-        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
-        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 14: if (!GRAM) return launch_ws_rows<32, 2, 1, 0>(n, T, c, params, in, out, seq_len, st); break;
         case 15: if (!GRAM) return launch_ws_rows<32, 1, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 20: if (!GRAM) return launch_ws<32, 2, 6, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
-        case 21: if (!GRAM) return launch_ws<32, 1, 11, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
-        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1, false>(n, n, T, c, params, in, out, seq_len, st); break;
+        case 20: if (!GRAM) return launch_ws<32, 2, 6, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 21: if (!GRAM) return launch_ws<32, 1, 11, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 24: if (!GRAM) return launch_ws_rows<32, 2, 1, 1>(n, T, c, params, in, out, seq_len, st); break;
         case 25: if (!GRAM) return launch_ws_rows<32, 1, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
         default:
@@ -448,6 +451,25 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
                                  const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
                                  void *stream)
 {
+    return b200i_sim_factual_pitched(n, T, T, k, params, noise, recovery_rvs, chemo_rvs, radio_rvs, assigned_actions,
+                                     cancer_volume, chemo_dosage, radio_dosage, chemo_application, radio_application,
+                                     chemo_probabilities, radio_probabilities, death_flags, recovery_flags,
+                                     sequence_lengths, static_feature, fd_dt, gram_workspace, variant, stream);
+}
+
+extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                         const double *params, const double *noise, const double *recovery_rvs,
+                                         const double *chemo_rvs, const double *radio_rvs,
+                                         const double *assigned_actions, double *cancer_volume, double *chemo_dosage,
+                                         double *radio_dosage, double *chemo_application, double *radio_application,
+                                         double *chemo_probabilities, double *radio_probabilities, double *death_flags,
+                                         double *recovery_flags, double *sequence_lengths,
+                                         const double *static_feature, double fd_dt, void *gram_workspace,
+                                         int32_t variant, void *stream)
+{
+    const int64_t pitch = row_pitch;
+    B200I_REQUIRE(pitch == T || (pitch > T && pitch % 2 == 0), B200I_E_ARG, "sim_factual: row_pitch %lld (T = %d) must be even and >= T",
+                  (long long)pitch, T);
     B200I_REQUIRE(n >= 0, B200I_E_ARG, "sim_factual: negative n");
     if (n == 0) return 0;
     B200I_REQUIRE(k && params && noise && recovery_rvs && chemo_rvs && radio_rvs && cancer_volume &&
@@ -474,12 +496,13 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
     for (int a = 0; a < 4; ++a) tma_ok = tma_ok && aligned16(in[a]);
     for (int a = 0; a < 9; ++a) tma_ok = tma_ok && aligned16(out[a]);
     if (variant == 0) variant = !tma_ok ? 1 : (gram ? 2 : 10);
+    B200I_REQUIRE(pitch == T || variant >= 2, B200I_E_UNSUPPORTED, "sim_factual: pitched rows need even T and 16-byte aligned arrays");
     if (variant >= 2) {
         B200I_REQUIRE(assigned_actions == nullptr, B200I_E_UNSUPPORTED,
                       "sim_factual: assigned_actions is only handled by the generic kernel (variant 1)");
         B200I_REQUIRE(tma_ok, B200I_E_ALIGN, "sim_factual: TMA variant needs even T and 16-byte aligned arrays");
-        return gram ? dispatch_tma<true>(variant, n, T, c, params, in, out, sequence_lengths, static_feature, ws, st)
-                    : dispatch_tma<false>(variant, n, T, c, params, in, out, sequence_lengths, static_feature, ws, st);
+        return gram ? dispatch_tma<true>(variant, n, T, pitch, c, params, in, out, sequence_lengths, static_feature, ws, st)
+                    : dispatch_tma<false>(variant, n, T, pitch, c, params, in, out, sequence_lengths, static_feature, ws, st);
     }
     FactualPtrs io;
     io.noise = noise; io.rec = recovery_rvs; io.chemo_rvs = chemo_rvs; io.radio_rvs = radio_rvs;

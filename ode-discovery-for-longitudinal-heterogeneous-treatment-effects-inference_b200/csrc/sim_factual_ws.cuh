@@ -233,7 +233,8 @@ __device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPackSkew &m, 
 
 template <int P, int NB, int MINB, int MODE, bool SKEW>
 __global__ void __launch_bounds__(SKEW ? 128 : P, MINB)
-sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opts, int64_t n, int64_t pstride, int T, SimC c,
+sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opts, int64_t n, int64_t pstride, int T,
+               int64_t pitch, SimC c,
                const double *__restrict__ params, double *__restrict__ out_ca, double *__restrict__ out_ra,
                double *__restrict__ out_D, double *__restrict__ out_death, double *__restrict__ out_recov,
                double *__restrict__ seq_len_out, double *__restrict__ out_V, double *__restrict__ out_C,
@@ -545,14 +546,14 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                 const int cp = rid % HALF, r_first = rid / HALF;
                 const int col = t_first + cp * 2;
                 if (col >= 0 && col < T && cp * 2 < nb * 16) {   // T, shift even: a column pair is in or out as a whole
-                    const int64_t tile_ofs = row0 * T + col;
+                    const int64_t tile_ofs = row0 * pitch + col;
                     double *b_ca = out_ca + tile_ofs, *b_ra = out_ra + tile_ofs, *b_D = out_D + tile_ofs,
                            *b_de = out_death + tile_ofs, *b_re = out_recov + tile_ofs;
                     const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 2;
-                    int ofs = r_first * rmul * T;
+                    int ofs = r_first * rmul * (int)pitch;
 #pragma unroll 4
                     for (int row = r_first; row < rows_valid;
-                         row += RSTEP, ofs += RSTEP * rmul * T, fp += RSTEP * Cfg::FLAG_PITCH) {
+                         row += RSTEP, ofs += RSTEP * rmul * (int)pitch, fp += RSTEP * Cfg::FLAG_PITCH) {
                         const unsigned two = *reinterpret_cast<const unsigned short *>(fp);
                         // bits: 1 chemo, 2 radio, 4 death, 8 recovery; low byte = even column, high byte = odd column
                         const unsigned i_ca = (two & 1u) | ((two >> 7) & 2u);
@@ -592,21 +593,24 @@ static int ws_env_opts()
     return e ? atoi(e) : 6;   // measured best: evict-first on output stores, evict-last on draw loads
 }
 
-static int ws_encode(TmapPack &pack, int64_t n, int T, int P, const double *const in[4], double *const out[9])
+static int ws_encode(TmapPack &pack, int64_t n, int T, int64_t pitch, int P, const double *const in[4],
+                     double *const out[9])
 {
     for (int a = 0; a < 4; ++a) {
-        int rc = encode_tmap_2d_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, P, 16, false);
+        int rc = encode_tmap_2d_pitched_f64(&pack.in[a], in[a], (uint64_t)n, (uint64_t)T, (uint64_t)pitch * 8, P, 16);
         if (rc) return rc;
     }
     for (int a = 0; a < 9; ++a) {
-        int rc = encode_tmap_2d_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, P, 16, false);
+        int rc = encode_tmap_2d_pitched_f64(&pack.out[a], out[a], (uint64_t)n, (uint64_t)T, (uint64_t)pitch * 8, P, 16);
         if (rc) return rc;
     }
     return 0;
 }
 // per-class views of the (n, T) arrays, n a multiple of 4: class j = rows j, j+4, ... with a pitch of 4 rows
-static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int ncls, const double *const in[4], double *const out[9])
+static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int64_t pitch, int ncls, const double *const in[4],
+                     double *const out[9])
 {
+    B200I_REQUIRE(pitch == T, B200I_E_UNSUPPORTED, "row-class mapping: dense rows only (pitch %lld, T %d)", (long long)pitch, T);
     const int oidx[4] = {0, 1, 5, 6};   // volume, chemo dosage, chemo / radio probabilities
     for (int j = 0; j < ncls; ++j) {
         const int shift = (j * T) & (4 * ncls - 1), head = (16 - shift) & 15;
@@ -623,14 +627,14 @@ static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int ncls, const doubl
 }
 
 template <int P, int NB, int MINB, int MODE, bool SKEW>
-static int launch_ws(int64_t n, int64_t pstride, int T, const SimC &c, const double *params, const double *const in[4],
-                     double *const out[9], double *seq_len, cudaStream_t st)
+static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const SimC &c, const double *params,
+                     const double *const in[4], double *const out[9], double *seq_len, cudaStream_t st)
 {
     using Cfg = WsCfg<P, NB>;
     if (n <= 0) return 0;
     typename WsMaps<SKEW>::type pack;
     {
-        int rc = ws_encode(pack, n, T, SKEW ? 4 : P, in, out);
+        int rc = ws_encode(pack, n, T, pitch, SKEW ? 4 : P, in, out);
         if (rc) return rc;
     }
     auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW>;
@@ -645,7 +649,7 @@ static int launch_ws(int64_t n, int64_t pstride, int T, const SimC &c, const dou
     if (grid > n_items) grid = n_items;
     static const int opts = ws_env_opts();
     // out order: V C D ca ra pc pr death recov
-    kern<<<(unsigned)grid, NT, SMEM, st>>>(pack, opts, n, pstride, T, c, params, out[3], out[4], out[2], out[7],
+    kern<<<(unsigned)grid, NT, SMEM, st>>>(pack, opts, n, pstride, T, pitch, c, params, out[3], out[4], out[2], out[7],
                                                      out[8], seq_len, out[0], out[1], out[5], out[6]);
     return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
 }

@@ -143,7 +143,7 @@ constexpr int G2_WARPS = 4;
 
 template <int MAXT>
 __global__ void __launch_bounds__(G2_WARPS * 32, 2)
-theta_gram2_kernel(int64_t n, int T, double fd_dt, double inv_dt, const double *__restrict__ vol,
+theta_gram2_kernel(int64_t n, int T, int64_t rp, double fd_dt, double inv_dt, const double *__restrict__ vol,
                    const double *__restrict__ chemo, const double *__restrict__ radio,
                    const double *__restrict__ seq_len, const double *__restrict__ static_feature,
                    const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws)
@@ -179,15 +179,16 @@ theta_gram2_kernel(int64_t n, int T, double fd_dt, double inv_dt, const double *
         // volume rows: lane j copies row j
         if (lane < rows) {
             mbar_arrive_expect_tx(&bars[warp], (uint32_t)(T * 8));
-            bulk_load_1d(s_vol + lane * pitch, vol + (first + lane) * T, (uint32_t)(T * 8), &bars[warp]);
+            bulk_load_1d(s_vol + lane * pitch, vol + (first + lane) * rp, (uint32_t)(T * 8), &bars[warp]);
         } else {
             mbar_arrive(&bars[warp]);
         }
         // the four other arrays, two columns per lane and row
-        const double2 *gc2 = reinterpret_cast<const double2 *>(chemo + first * T);
-        const double2 *gr2 = reinterpret_cast<const double2 *>(radio + first * T);
-        const double2 *gC2 = chemo_dos ? reinterpret_cast<const double2 *>(chemo_dos + first * T) : nullptr;
-        const double2 *gD2 = radio_dos ? reinterpret_cast<const double2 *>(radio_dos + first * T) : nullptr;
+        const double2 *gc2 = reinterpret_cast<const double2 *>(chemo + first * rp);
+        const double2 *gr2 = reinterpret_cast<const double2 *>(radio + first * rp);
+        const double2 *gC2 = chemo_dos ? reinterpret_cast<const double2 *>(chemo_dos + first * rp) : nullptr;
+        const double2 *gD2 = radio_dos ? reinterpret_cast<const double2 *>(radio_dos + first * rp) : nullptr;
+        const int64_t rp2 = rp / 2;
         int L_lane = (lane < rows) ? (int)__ldg(seq_len + first + lane) : 0;
         L_lane = L_lane > T ? T : L_lane;
         for (int cb = 0; cb < half; cb += 32) {
@@ -199,7 +200,7 @@ theta_gram2_kernel(int64_t n, int T, double fd_dt, double inv_dt, const double *
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int j = (j0 + i < rows) ? j0 + i : rows - 1;
-                    const int64_t e = (int64_t)j * half + c;
+                    const int64_t e = (int64_t)j * rp2 + c;
                     va[i] = __ldg(gc2 + e); vb[i] = __ldg(gr2 + e);
                     vC[i] = gC2 ? __ldg(gC2 + e) : make_double2(0.0, 0.0);
                     vD[i] = gD2 ? __ldg(gD2 + e) : make_double2(0.0, 0.0);
@@ -355,6 +356,18 @@ extern "C" int b200i_theta_gram(int64_t n, int32_t T, double fd_dt, const double
                                 const double *chemo_dosage, const double *radio_dosage, void *gram_workspace,
                                 void *stream)
 {
+    return b200i_theta_gram_pitched(n, T, T, fd_dt, cancer_volume, chemo_application, radio_application, sequence_lengths,
+                                    static_feature, chemo_dosage, radio_dosage, gram_workspace, stream);
+}
+
+extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
+                                        const double *cancer_volume, const double *chemo_application,
+                                        const double *radio_application, const double *sequence_lengths,
+                                        const double *static_feature, const double *chemo_dosage,
+                                        const double *radio_dosage, void *gram_workspace, void *stream)
+{
+    B200I_REQUIRE(row_pitch >= T && (row_pitch == T || row_pitch % 2 == 0), B200I_E_ARG,
+                  "theta_gram: row_pitch %lld (T = %d) must be even and >= T", (long long)row_pitch, T);
     B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths &&
                       static_feature && gram_workspace,
                   B200I_E_ARG, "theta_gram: NULL argument or negative n");
@@ -368,7 +381,7 @@ extern "C" int b200i_theta_gram(int64_t n, int32_t T, double fd_dt, const double
     {
         const bool v2 = (T % 2 == 0) && T <= 256 && aligned16(cancer_volume) && aligned16(chemo_application) &&
                         aligned16(radio_application) && (!chemo_dosage || aligned16(chemo_dosage)) &&
-                        (!radio_dosage || aligned16(radio_dosage)) && getenv("B200I_THETA_GRAM_V1") == nullptr;
+                        (!radio_dosage || aligned16(radio_dosage)) && (row_pitch != T || getenv("B200I_THETA_GRAM_V1") == nullptr);
         if (v2) {
             const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
             const size_t smem2 = warp_bytes * G2_WARPS;
@@ -382,13 +395,14 @@ extern "C" int b200i_theta_gram(int64_t n, int32_t T, double fd_dt, const double
                 const int64_t need = (ntiles2 + G2_WARPS - 1) / G2_WARPS;
                 if (grid2 > need) grid2 = need;
                 if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
-                k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
+                k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
                                                                   radio_application, sequence_lengths, static_feature,
                                                                   chemo_dosage, radio_dosage, ws);
                 return check_cuda(cudaGetLastError(), "theta_gram2 launch");
             }
         }
     }
+    B200I_REQUIRE(row_pitch == T, B200I_E_UNSUPPORTED, "theta_gram: pitched rows need even T <= 256 and 16-byte aligned arrays");
     const size_t smem = (size_t)GP * T * 9;
     const bool bulk = (T % 2 == 0) && aligned16(cancer_volume) && aligned16(chemo_application) &&
                       aligned16(radio_application);

@@ -41,6 +41,37 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _ptr_rows(t):
+    """Pointer of an (N,T) device tensor whose rows may be pitched (stride(0) >= T, stride(1) == 1)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1), "rows must be unit-stride CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def row_pitch(*tensors):
+    """Common row pitch (elements) of a set of (N,T) tensors; raises if they differ."""
+    pitches = {int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1]) for t in tensors if t is not None}
+    if len(pitches) != 1:
+        raise ValueError(f"all (N,T) arrays of one call must share their row pitch, got {sorted(pitches)}")
+    return pitches.pop()
+
+
+def alloc_rows(n, T, pitch=None, dtype=torch.float64):
+    """(n, T) device tensor; with pitch > T the rows are padded (cudaMallocPitch style).  A pitch that makes a row a
+    multiple of 128 bytes (64 for T = 60) keeps the tiled kernels' 16-column boxes on 128-byte lines."""
+    pitch = T if pitch is None else int(pitch)
+    if pitch == T:
+        return torch.empty((n, T), dtype=dtype, device='cuda')
+    return torch.empty((n, pitch), dtype=dtype, device='cuda')[:, :T]
+
+
+def aligned_pitch(T, elem_bytes=8, line=128):
+    """Smallest pitch >= T (elements) whose rows are a multiple of `line` bytes."""
+    per = line // elem_bytes
+    return ((T + per - 1) // per) * per
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -87,14 +118,18 @@ def sim_factual(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=Non
     lib = _native.load()
     n = params_dev.shape[1]
     consts = consts or sim_consts()
+    pitch = row_pitch(noise, recovery, chemo_rvs, radio_rvs) if n > 1 else T
     if out is None:
-        out = {k: torch.empty((n, T), dtype=torch.float64, device='cuda') for k in FACTUAL_OUT_KEYS}
+        out = {k: alloc_rows(n, T, pitch) for k in FACTUAL_OUT_KEYS}
         out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
+    elif n > 1:
+        pitch = row_pitch(noise, recovery, chemo_rvs, radio_rvs, *[out[k] for k in FACTUAL_OUT_KEYS])
     ws = gram_workspace() if fused_static is not None else None
-    rc = lib.b200i_sim_factual(n, T, ctypes.byref(consts), _ptr(params_dev), _ptr(noise), _ptr(recovery),
-                               _ptr(chemo_rvs), _ptr(radio_rvs), _ptr(assigned_actions),
-                               *[_ptr(out[k]) for k in FACTUAL_OUT_KEYS], _ptr(out['sequence_lengths']),
-                               _ptr(fused_static), float(fd_dt), _ptr(ws), int(variant), _stream())
+    rc = lib.b200i_sim_factual_pitched(n, T, pitch, ctypes.byref(consts), _ptr(params_dev), _ptr_rows(noise),
+                                       _ptr_rows(recovery), _ptr_rows(chemo_rvs), _ptr_rows(radio_rvs),
+                                       _ptr(assigned_actions), *[_ptr_rows(out[k]) for k in FACTUAL_OUT_KEYS],
+                                       _ptr(out['sequence_lengths']), _ptr(fused_static), float(fd_dt), _ptr(ws),
+                                       int(variant), _stream())
     _native.check(rc, "b200i_sim_factual")
     return out, (ws[:STATS_DOUBLES] if ws is not None else None)
 
@@ -105,9 +140,10 @@ def theta_gram(cancer_volume, chemo_application, radio_application, sequence_len
     lib = _native.load()
     n, T = cancer_volume.shape
     ws = gram_workspace(tag)
-    rc = lib.b200i_theta_gram(n, T, float(fd_dt), _ptr(cancer_volume), _ptr(chemo_application),
-                              _ptr(radio_application), _ptr(sequence_lengths), _ptr(static_feature),
-                              _ptr(chemo_dosage), _ptr(radio_dosage), _ptr(ws), _stream())
+    pitch = row_pitch(cancer_volume, chemo_application, radio_application, chemo_dosage, radio_dosage) if n > 1 else T
+    rc = lib.b200i_theta_gram_pitched(n, T, pitch, float(fd_dt), _ptr_rows(cancer_volume), _ptr_rows(chemo_application),
+                                      _ptr_rows(radio_application), _ptr(sequence_lengths), _ptr(static_feature),
+                                      _ptr_rows(chemo_dosage), _ptr_rows(radio_dosage), _ptr(ws), _stream())
     _native.check(rc, "b200i_theta_gram")
     return ws[:STATS_DOUBLES]
 

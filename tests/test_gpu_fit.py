@@ -67,6 +67,27 @@ def test_theta_gram_matches_oracle_design_matrices(dev, seed1):
     assert u['patients'] == 1000 and u['active'] == o['train']['sequence_lengths'].sum()
 
 
+def test_theta_gram_pitched_rows_bit_identical_to_dense(dev, seed1):
+    """b200i_theta_gram_pitched: rows padded to 128-byte lines give the same statistics bit for bit."""
+    import torch
+    _, o, _, _ = seed1
+    sim = o['train']
+    dense = _device_stats(dev, sim, sim['patient_types']).clone()
+    n, T = sim['cancer_volume'].shape
+
+    def pitched(a):
+        t = dev.alloc_rows(n, T, dev.aligned_pitch(T))
+        t._base.fill_(float('nan'))
+        t.copy_(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+        return t
+    stats = dev.theta_gram(pitched(sim['cancer_volume']), pitched(sim['chemo_application']),
+                           pitched(sim['radio_application']), dev.to_device(sim['sequence_lengths']),
+                           dev.to_device(np.asarray(sim['patient_types'], dtype=np.float64)),
+                           pitched(sim['chemo_dosage']), pitched(sim['radio_dosage']))
+    torch.cuda.synchronize()
+    assert torch.equal(stats, dense)
+
+
 def test_population_stlsq_reproduces_reference_log(dev, seed1):
     import torch
     _, o, _, _ = seed1

@@ -70,6 +70,30 @@ def test_factual_fast_path_preconditions_fall_back_per_tile(dev, variant):
     _check_factual(got, ref, f"fallback variant {variant}")
 
 
+@pytest.mark.parametrize("variant,pitch", [(0, 64), (10, 64), (11, 64), (12, 64), (13, 64), (0, 62), (10, 72)])
+def test_factual_pitched_rows_bit_identical_to_dense(dev, variant, pitch):
+    """cudaMallocPitch-style rows (b200i_sim_factual_pitched): same kernels, same bits, padding untouched."""
+    import torch
+    from oracle import sim_oracle as so
+    params, draws = h.random_cohort(1500, seed=9)
+    ref = so.sim_factual(params, 60, draws)
+    pd_ = dev.to_device(dev.pack_params(params))
+    ins = []
+    for k in ('noise', 'recovery', 'chemo', 'radio'):
+        t = dev.alloc_rows(1500, 60, pitch)
+        t.copy_(torch.from_numpy(draws[k]).cuda())
+        ins.append(t)
+    out = {k: dev.alloc_rows(1500, 60, pitch) for k in dev.FACTUAL_OUT_KEYS}
+    for k in out:
+        out[k]._base.fill_(-7.0)        # padding columns must survive
+    out['sequence_lengths'] = torch.empty((1500,), dtype=torch.float64, device='cuda')
+    got, _ = dev.sim_factual(pd_, *ins, 60, out=out, variant=variant)
+    torch.cuda.synchronize()
+    for k in dev.FACTUAL_OUT_KEYS:
+        assert bool((got[k]._base[:, 60:] == -7.0).all()), f"{k}: padding overwritten"
+    _check_factual({k: v.cpu().numpy() for k, v in got.items()}, ref, f"pitch {pitch} variant {variant}")
+
+
 def test_factual_matches_reference_fixture(dev):
     """Reference outputs themselves (tests/golden/ref_sim_small.npz), reference RNG order."""
     g = h.load_npz('ref_sim_small.npz')
