@@ -27,7 +27,8 @@ METRIC = "patient-steps/sec (cancer_sim factual + INSITE population fit)"
 UNIT = "patient-steps/s"
 K1_BYTES_PER_PATIENT = lambda T: 4 * T * 8 + 9 * T * 8 + 10 * 8 + 8      # 6328 B at T=60
 K4_BYTES_PER_PATIENT = lambda T: 3 * T * 8 + 8 + 8                         # 1456 B at T=60
-K1_KERNEL = "sim_factual_ws<32,2,6,0>"      # csrc/sim_factual_ws.cuh, variant 10 (default)
+K1_KERNELS = {"pitched": "sim_factual_ws<32,1,11,0>",   # csrc/sim_factual_ws.cuh, variant 12 (128-byte-aligned rows)
+              "dense": "sim_factual_ws<32,2,6,0>"}      # variant 10 (dense 480-byte rows)
 K4_KERNEL = "theta_gram2_kernel"            # csrc/theta_gram.cu
 
 
@@ -325,8 +326,8 @@ def run_b200(args):
                         "what": "FactualFitPipeline.step_host: pinned host params+draws -> H2D -> K1,K4,K5 -> D2H "
                                 "coefficients/support/statistics"},
                 "gpu_launches": pipe.launches_per_step * args.steps,
-                "roofline": {"bound": "hbm", "kernel": K1_KERNEL, "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(K1_KERNEL),
+                "roofline": {"bound": "hbm", "kernel": K1_KERNELS[args.layout], "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(K1_KERNELS[args.layout]),
                              "peak_source": peak_src, "kernel_ms": k1,
                              "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n,
                              "share_of_step": k1 / ms_per_step,
@@ -334,7 +335,8 @@ def run_b200(args):
                                  "kernel_ms": k1_dense_ms,
                                  "achieved": K1_BYTES_PER_PATIENT(T) * n / (k1_dense_ms / 1e3) / 1e9,
                                  "frac": K1_BYTES_PER_PATIENT(T) * n / (k1_dense_ms / 1e3) / 1e9 / peak,
-                                 "note": "same kernel on the reference's dense 480-byte rows (bit-identical outputs)"}},
+                                 "kernel": K1_KERNELS["dense"], "traffic": ncu_traffic(K1_KERNELS["dense"]),
+                                 "note": "same arithmetic on the reference's dense 480-byte rows (bit-identical outputs)"}},
                 "roofline_theta_gram": {"bound": "hbm", "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
                                         "unit": "GB/s", "frac": achieved4 / peak, "traffic": ncu_traffic(K4_KERNEL),
                                         "kernel_ms": k4, "algorithmic_bytes_per_launch": K4_BYTES_PER_PATIENT(T) * n,

@@ -495,7 +495,8 @@ extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch
     bool tma_ok = (T % 2 == 0) && assigned_actions == nullptr;
     for (int a = 0; a < 4; ++a) tma_ok = tma_ok && aligned16(in[a]);
     for (int a = 0; a < 9; ++a) tma_ok = tma_ok && aligned16(out[a]);
-    if (variant == 0) variant = !tma_ok ? 1 : (gram ? 2 : 10);
+    // auto: rows on 128-byte lines -> one box per chunk and 11 warps per SM; otherwise two boxes per chunk
+    if (variant == 0) variant = !tma_ok ? 1 : (gram ? 2 : ((pitch * 8) % 128 == 0 ? 12 : 10));
     B200I_REQUIRE(pitch == T || variant >= 2, B200I_E_UNSUPPORTED, "sim_factual: pitched rows need even T and 16-byte aligned arrays");
     if (variant >= 2) {
         B200I_REQUIRE(assigned_actions == nullptr, B200I_E_UNSUPPORTED,

@@ -17,7 +17,11 @@ T = 60
 dev.require_cuda()
 params, block, static, draws = synth_inputs(n, T, 0)
 block, static = block.cuda(), static.cuda()
-out = {k: torch.empty((n, T), dtype=torch.float64, device='cuda') for k in dev.FACTUAL_OUT_KEYS}
+pitch = int(os.environ.get('PITCH', str(T)))
+def _rows(src):
+    t = dev.alloc_rows(n, T, pitch); t.copy_(src); return t
+draws = [_rows(d) for d in draws]
+out = {k: dev.alloc_rows(n, T, pitch) for k in dev.FACTUAL_OUT_KEYS}
 out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
 ts = []
 for i in range(reps):

@@ -34,10 +34,13 @@ def main():
     params[5] = 14137.166941154068
     params[6] = 6.499999999999999; params[7] = 6.499999999999999
     params[8] = 2.0 / 12.999999999999998; params[9] = 2.0 / 12.999999999999998
-    noise = 0.01 * torch.randn((n, T), generator=g, device='cuda', dtype=torch.float64)
-    rec, chemo, radio = (torch.rand((n, T), generator=g, device='cuda', dtype=torch.float64) for _ in range(3))
+    pitch = int(os.environ.get('PITCH', str(T)))
+    def rows(src):
+        t = dev.alloc_rows(n, T, pitch); t.copy_(src); return t
+    noise = rows(0.01 * torch.randn((n, T), generator=g, device='cuda', dtype=torch.float64))
+    rec, chemo, radio = (rows(torch.rand((n, T), generator=g, device='cuda', dtype=torch.float64)) for _ in range(3))
     static = torch.randint(1, 4, (n,), generator=g, device='cuda').double()
-    out = {k: torch.empty((n, T), dtype=torch.float64, device='cuda') for k in dev.FACTUAL_OUT_KEYS}
+    out = {k: dev.alloc_rows(n, T, pitch) for k in dev.FACTUAL_OUT_KEYS}
     out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
     bytes_alg = n * (4 * T * 8 + 9 * T * 8 + 10 * 8 + 8)
     res = []

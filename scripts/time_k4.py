@@ -11,6 +11,10 @@ T = 60
 dev.require_cuda()
 params, block, static, draws = synth_inputs(n, T, 0)
 block, static = block.cuda(), static.cuda()
+pitch = int(os.environ.get('PITCH', str(T)))
+def _rows(src):
+    t = dev.alloc_rows(n, T, pitch); t.copy_(src); return t
+draws = [_rows(d) for d in draws]
 out, _ = dev.sim_factual(block, *draws, T)
 del draws
 ts = []
