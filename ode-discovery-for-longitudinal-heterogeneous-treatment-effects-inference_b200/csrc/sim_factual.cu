@@ -405,7 +405,7 @@ static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC
                         const double *const in[4], double *const out[9], double *seq_len, const double *sf,
                         StatsWorkspace *ws, cudaStream_t st)
 {
-    B200I_REQUIRE(pitch == T || (variant >= 10 && variant <= 13) || (variant >= 20 && variant <= 22), B200I_E_UNSUPPORTED,
+    B200I_REQUIRE(pitch == T || (variant >= 10 && variant <= 13) || variant == 16 || variant == 17 || (variant >= 20 && variant <= 22), B200I_E_UNSUPPORTED,
                   "sim_factual: variant %d needs dense rows (row_pitch %lld, T %d)", variant, (long long)pitch, T);
     switch (variant) {
         case 2: return launch_tma<128, 8, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
@@ -418,9 +418,11 @@ static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC
         case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         // generation 6 (sim_factual_ws.cuh): <patients per tile, 16-column boxes per chunk, CTAs per SM, mode>;
         // launch_ws_rows = the experimental line-aligned row-class mapping; 2x = data movement only (profiling aid)
-        case 10: if (!GRAM) return launch_ws<32, 2, 6, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 10: return launch_ws<32, 2, 6, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
         case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
-        case 12: if (!GRAM) return launch_ws<32, 1, 11, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
+        case 12: return launch_ws<32, 1, 11, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 16: return launch_ws<32, 1, 8, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 17: return launch_ws<32, 1, 9, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
         case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 14: if (!GRAM) return launch_ws_rows<32, 2, 1, 0>(n, T, c, params, in, out, seq_len, st); break;
         case 15: if (!GRAM) return launch_ws_rows<32, 1, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
@@ -496,7 +498,7 @@ extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch
     for (int a = 0; a < 4; ++a) tma_ok = tma_ok && aligned16(in[a]);
     for (int a = 0; a < 9; ++a) tma_ok = tma_ok && aligned16(out[a]);
     // auto: rows on 128-byte lines -> one box per chunk and 11 warps per SM; otherwise two boxes per chunk
-    if (variant == 0) variant = !tma_ok ? 1 : (gram ? 2 : ((pitch * 8) % 128 == 0 ? 12 : 10));
+    if (variant == 0) variant = !tma_ok ? 1 : ((pitch * 8) % 128 == 0 ? 12 : 10);
     B200I_REQUIRE(pitch == T || variant >= 2, B200I_E_UNSUPPORTED, "sim_factual: pitched rows need even T and 16-byte aligned arrays");
     if (variant >= 2) {
         B200I_REQUIRE(assigned_actions == nullptr, B200I_E_UNSUPPORTED,

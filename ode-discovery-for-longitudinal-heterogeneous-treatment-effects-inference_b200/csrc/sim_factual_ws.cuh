@@ -169,14 +169,35 @@ __device__ __forceinline__ void ws_body(int t, int Tm1, const WsK &k, const WsPa
 struct WsSlow {
     Patient p;
     FactualState s;
+    PatientGram pg;
+    Moments mom;
 };
 
-template <int P>
+// one regression sample (x0 -> x1 under treatment a) of the SINDy fit plus, when the constant-treatment snippet
+// ends at x1, its backward-difference end point (pkpd/utils.py:433-462 + FiniteDifference order 1): both rows
+// share xdot and the treatment, so they are merged and filed with one-hot weights (branch-free, 20 FMA chains)
+__device__ __forceinline__ void ws_gram_sample(PatientGram &pg, bool valid, bool end, double x0, double x1, unsigned a,
+                                               double fd_dt, double inv_dt)
+{
+    const double xdot = fm::div_small(__dsub_rn(x1, x0), fd_dt, inv_dt);
+    const double e = end ? 1.0 : 0.0;
+    const double cnt = 1.0 + e, sx = fma(e, x1, x0), sxx = fma(e * x1, x1, x0 * x0);
+    const double sd = cnt * xdot, sxd = sx * xdot;
+#pragma unroll
+    for (unsigned t = 0; t < 4; ++t) {
+        const double wt = (valid && a == t) ? 1.0 : 0.0;
+        pg.s[t][0] = fma(wt, cnt, pg.s[t][0]); pg.s[t][1] = fma(wt, sx, pg.s[t][1]);
+        pg.s[t][2] = fma(wt, sxx, pg.s[t][2]); pg.s[t][3] = fma(wt, sd, pg.s[t][3]);
+        pg.s[t][4] = fma(wt, sxd, pg.s[t][4]);
+    }
+}
+
+template <int P, bool GRAM>
 __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int tid, int t_first, int ncols, int T,
                                            const SimC &c, WsSlow *st)
 {
-    PatientGram pg;
-    Moments mom;
+    PatientGram &pg = st->pg;
+    Moments &mom = st->mom;
     for (int cidx = 0; cidx < ncols; ++cidx) {
         if (t_first + cidx < 0) continue;   // skewed first box: columns left of column 0
         const int box = cidx >> 4, q = (cidx & 15) >> 1, lohi = cidx & 1;
@@ -184,7 +205,7 @@ __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int
         double *pn = reinterpret_cast<double *>(base), *pu = reinterpret_cast<double *>(base + 1 * P * 128),
                *pc = reinterpret_cast<double *>(base + 2 * P * 128), *pr = reinterpret_cast<double *>(base + 3 * P * 128);
         Column o;
-        factual_column<false, false>(t_first + cidx, T, c, st->p, st->s, *pn, *pu, *pc, *pr, nullptr, o, pg, mom);
+        factual_column<GRAM, false>(t_first + cidx, T, c, st->p, st->s, *pn, *pu, *pc, *pr, nullptr, o, pg, mom);
         *pn = o.V; *pu = o.C; *pc = o.pc; *pr = o.pr;
         flags_s[cidx + 2] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
                                       (o.recov != 0.0 ? 8u : 0u));
@@ -231,15 +252,19 @@ __device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPack &m, int,
 }
 __device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPackSkew &m, int j, int o) { return &m.out[j][o]; }
 
-template <int P, int NB, int MINB, int MODE, bool SKEW>
+template <int P, int NB, int MINB, int MODE, bool SKEW, bool GRAM>
 __global__ void __launch_bounds__(SKEW ? 128 : P, MINB)
 sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opts, int64_t n, int64_t pstride, int T,
                int64_t pitch, SimC c,
                const double *__restrict__ params, double *__restrict__ out_ca, double *__restrict__ out_ra,
                double *__restrict__ out_D, double *__restrict__ out_death, double *__restrict__ out_recov,
                double *__restrict__ seq_len_out, double *__restrict__ out_V, double *__restrict__ out_C,
-               double *__restrict__ out_pc, double *__restrict__ out_pr)
+               double *__restrict__ out_pc, double *__restrict__ out_pr, const double *__restrict__ static_feature,
+               StatsWorkspace *ws)
 {
+    static_assert(!GRAM || (!SKEW && MODE == 0), "fused statistics: plain tiles, simulator mode");
+    __shared__ double block_acc[GRAM ? (P / 32) : 1][STATS_PAD];
+    __shared__ unsigned int s_is_last;
     using Cfg = WsCfg<P, NB>;
     constexpr int TCH = Cfg::TCH, HALF = TCH / 2;
     static_assert(!SKEW || P == 32, "the row-class mapping is one warp per class");
@@ -319,6 +344,9 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
     }
     __syncthreads();
     if (leader && (int64_t)blockIdx.x < n_items) issue_load(item_of(blockIdx.x), 0);
+    if (GRAM) {
+        for (int j = tid; j < (P / 32) * STATS_PAD; j += P) (&block_acc[0][0])[j] = 0.0;
+    }
     if (tid < 20) {
         // flag expansion table: array a in {chemo app, radio app, radio dosage, death, recovery}, index = the
         // array's bit of the even column | its bit of the odd column << 1
@@ -356,6 +384,13 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
     double v0 = 0.0;
     const int Tm1 = T - 1;
     uint32_t phase = 0;
+    // fused population statistics (GRAM): per-patient sums, folded into the CTA accumulators once per tile
+    PatientGram pg;
+    Moments mom;
+    double gVm1 = 0.0, gVm2 = 0.0;      // V[t0-1], V[t0-2] of the next group of four
+    unsigned gcm2 = 0u, g_nra = 0u;     // treatment of column t0-2; radio applications so far
+    int g_tlast = -4;                   // first column of the last simulated group
+    const double inv_dt = 1.0 / c.fd_dt;
 
     for (int64_t wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
         const Item it = item_of(wi);
@@ -389,6 +424,11 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
             if (tile_slow) {
                 slow.p = load_patient(params, pstride, pi);
                 state_init(slow.s, exists);
+                if (GRAM) { slow.pg.clear(); slow.mom.clear(); }
+            }
+            if (GRAM) {
+                pg.clear(); mom.clear();
+                gVm1 = gVm2 = 0.0; gcm2 = 0u; g_nra = 0u; g_tlast = -4;
             }
         }
 
@@ -401,7 +441,7 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
             nb = nb > NB ? NB : nb;
 
             if (MODE == 0 && tile_slow) {
-                ws_slow_chunk<P>(tiles, flags_s, rid, t_first, nb * 16, T, c, &slow);
+                ws_slow_chunk<P, GRAM>(tiles, flags_s, rid, t_first, nb * 16, T, c, &slow);
             } else {
                 // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
                 double *prevC = dummy, *prevP = dummy + 1;
@@ -441,6 +481,28 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                                 for (int j = 0; j < 4; ++j) {
                                     if (t0 + j > s.t_end) oV[j] = 0.0;
                                     if (t0 + j - 1 > s.t_end) { oC[j] = oP[j] = 0.0; oF[j] = 0u; }
+                                }
+                            }
+                            if (GRAM) {
+                                // regression samples k = t0-2 .. t0+1 are complete now: x[k+1] and the treatment of
+                                // column k+1 are known, columns after the last simulated one are already zero (so
+                                // is x[seq_len], the sample the reference's snippet code appends)
+                                const unsigned c0 = oF[0] & 3u, c1 = oF[1] & 3u, c2 = oF[2] & 3u, c3 = oF[3] & 3u;
+                                const int te = s.t_end;
+                                ws_gram_sample(pg, t0 >= 2 && t0 - 2 <= te, t0 - 2 == te || c0 != gcm2, gVm2, gVm1, gcm2,
+                                               c.fd_dt, inv_dt);
+                                ws_gram_sample(pg, t0 >= 1 && t0 - 1 <= te, t0 - 1 == te || c1 != c0, gVm1, oV[0], c0,
+                                               c.fd_dt, inv_dt);
+                                ws_gram_sample(pg, t0 <= te, t0 == te || c2 != c1, oV[0], oV[1], c1, c.fd_dt, inv_dt);
+                                ws_gram_sample(pg, t0 + 1 <= te, t0 + 1 == te || c3 != c2, oV[1], oV[2], c2, c.fd_dt,
+                                               inv_dt);
+                                gVm2 = oV[2]; gVm1 = oV[3]; gcm2 = c3; g_tlast = t0;
+                                // moments of get_scaling_params: inactive entries are zero, so plain sums do
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    mom.sv += oV[j]; mom.svv += oV[j] * oV[j];
+                                    mom.sc += oC[j]; mom.scc += oC[j] * oC[j];
+                                    g_nra += (oF[j] >> 1) & 1u;
                                 }
                             }
                         }
@@ -582,8 +644,23 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
           }
         }
         if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
+        if (GRAM) {
+            const double u = exists ? __ldg(static_feature + patient) : 0.0;
+            const int lane = tid & 31, wrp = tid >> 5;
+            if (tile_slow) {
+                factual_finish<true>(c, slow.s, slow.pg);
+                fold_patient_stats(block_acc[wrp], lane, slow.pg, slow.mom, u, exists, slow.s.t_end + 1);
+            } else {
+                // the last sample (k = seq_len - 1) when it lies in the second half of the last group
+                ws_gram_sample(pg, g_tlast + 2 <= s.t_end, true, gVm2, gVm1, gcm2, c.fd_dt, inv_dt);
+                mom.sd = c.radio_amt * (double)g_nra;
+                mom.sdd = c.radio_amt * c.radio_amt * (double)g_nra;
+                fold_patient_stats(block_acc[wrp], lane, pg, mom, u, exists, s.t_end + 1);
+            }
+        }
     }
     if (leader) tma_store_wait_all();
+    if (GRAM) stats_block_finish(block_acc, P / 32, ws, &s_is_last);
 }
 
 // tuning switches of the data-movement skeleton; B200I_WS_OPTS overrides the default
@@ -626,9 +703,10 @@ static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int64_t pitch, int nc
     return 0;
 }
 
-template <int P, int NB, int MINB, int MODE, bool SKEW>
+template <int P, int NB, int MINB, int MODE, bool SKEW, bool GRAM = false>
 static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const SimC &c, const double *params,
-                     const double *const in[4], double *const out[9], double *seq_len, cudaStream_t st)
+                     const double *const in[4], double *const out[9], double *seq_len, cudaStream_t st,
+                     const double *static_feature = nullptr, StatsWorkspace *ws = nullptr)
 {
     using Cfg = WsCfg<P, NB>;
     if (n <= 0) return 0;
@@ -637,7 +715,7 @@ static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const Sim
         int rc = ws_encode(pack, n, T, pitch, SKEW ? 4 : P, in, out);
         if (rc) return rc;
     }
-    auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW>;
+    auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW, GRAM>;
     constexpr int SMEM = SKEW ? Cfg::SMEM_BYTES_4 : Cfg::SMEM_BYTES;
     constexpr int NT = SKEW ? 128 : P;
     B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -647,10 +725,11 @@ static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const Sim
     const int64_t n_items = SKEW ? n / 128 : (n + P - 1) / P;
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > n_items) grid = n_items;
+    if (GRAM && grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
     static const int opts = ws_env_opts();
     // out order: V C D ca ra pc pr death recov
     kern<<<(unsigned)grid, NT, SMEM, st>>>(pack, opts, n, pstride, T, pitch, c, params, out[3], out[4], out[2], out[7],
-                                                     out[8], seq_len, out[0], out[1], out[5], out[6]);
+                                                     out[8], seq_len, out[0], out[1], out[5], out[6], static_feature, ws);
     return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
 }
 

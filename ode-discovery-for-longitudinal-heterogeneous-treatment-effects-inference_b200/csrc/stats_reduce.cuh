@@ -38,10 +38,10 @@ __device__ __forceinline__ void stats_block_finish(double (*block_acc)[STATS_PAD
 {
     __syncthreads();
     const int tid = threadIdx.x;
-    if (tid < STATS) {
+    for (int i = tid; i < STATS; i += blockDim.x) {   // blocks smaller than STATS threads loop
         double v = 0.0;
-        for (int w = 0; w < nwarps; ++w) v += block_acc[w][tid];
-        ws->partials[blockIdx.x][tid] = v;
+        for (int w = 0; w < nwarps; ++w) v += block_acc[w][i];
+        ws->partials[blockIdx.x][i] = v;
     }
     __threadfence();
     __syncthreads();
@@ -52,10 +52,10 @@ __device__ __forceinline__ void stats_block_finish(double (*block_acc)[STATS_PAD
     __syncthreads();
     if (*s_is_last) {
         __threadfence();
-        if (tid < STATS) {
+        for (int i = tid; i < STATS; i += blockDim.x) {
             double v = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(&ws->partials[b][tid]);
-            ws->stats[tid] = v;
+            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(&ws->partials[b][i]);
+            ws->stats[i] = v;
         }
         if (tid == 0) ws->ticket[0] = 0u;  // ready for the next launch
     }

@@ -107,7 +107,7 @@ def test_fused_simulator_statistics_equal_standalone(dev):
     pd_ = dev.to_device(dev.pack_params(params))
     static = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64))
     args = [dev.to_device(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 0, 10, 12):
         out, fused = dev.sim_factual(pd_, *args, 60, variant=variant, fused_static=static)
         fused = fused.clone()
         alone = dev.theta_gram(out['cancer_volume'], out['chemo_application'], out['radio_application'],
@@ -118,6 +118,16 @@ def test_fused_simulator_statistics_equal_standalone(dev):
     u = dev.unpack_stats(fused.cpu().numpy())
     assert np.array_equal(u['count'], cnt)
     np.testing.assert_allclose(u['G'], G, rtol=1e-10)
+    # lean kernel with tiles that fall back to the generic column function (mixed sigmoids): same statistics
+    dmax = 12.999999999999998
+    params['radio_sigmoid_betas'][700:760] = 6.0 / dmax
+    pd2 = dev.to_device(dev.pack_params(params))
+    out, fused = dev.sim_factual(pd2, *args, 60, variant=12, fused_static=static)
+    fused = fused.clone()
+    alone = dev.theta_gram(out['cancer_volume'], out['chemo_application'], out['radio_application'],
+                           out['sequence_lengths'], static, out['chemo_dosage'], out['radio_dosage'], tag="t2")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(fused.cpu().numpy(), alone.cpu().numpy(), rtol=1e-12, atol=1e-9)
 
 
 @pytest.mark.parametrize("threshold,alpha", [(1e-3, 0.5), (0.08, 0.5), (0.6, 0.05), (5.0, 0.5)])
