@@ -13,6 +13,7 @@
 // from j's compact arrays: a prefix of j's factual trajectory, then a short tail (the counterfactual
 // value(s) of that row), then zeros.  32 consecutive patients almost always share j, so the reads of
 // F_j broadcast within the warp.
+#include "fastmath.cuh"
 #include "sim_math.cuh"
 
 namespace b200i {
@@ -190,9 +191,24 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
 // K3
 // ------------------------------------------------------------------------------------------------
 // one projected step, cancer_simulation.py:739-743 (note the two 1e-07 terms and no clipping)
-__device__ __forceinline__ double proj_step(const Patient &p, double V, double C, double D, double noise)
+// The 35 projected steps per factual step dominate K3, so the division and the logarithm are the lean ones of
+// fastmath.cuh (correctly rounded division, log <= 0.9 ulp) whenever the operands are positive, finite and normal;
+// anything else (negative projected volumes give the NaN that invalidates an option, :745-746) takes the library
+// path, so the validity masks follow the reference exactly.
+__device__ __noinline__ double proj_log_slow(double K, double V)
 {
-    const double lg = log(__dadd_rn(__ddiv_rn(p.K, __dadd_rn(V, 1e-07)), 1e-07));
+    return log(__dadd_rn(__ddiv_rn(K, __dadd_rn(V, 1e-07)), 1e-07));
+}
+__device__ __forceinline__ double proj_step(const fm::FmK &fk, const Patient &p, double V, double C, double D, double noise)
+{
+    const double den = __dadd_rn(V, 1e-07);
+    double lg;
+    if (den > 1e-200 && den < 1e200) {
+        const double x = __dadd_rn(fm::div_fast(p.K, den), 1e-07);
+        lg = fm::log_ratio(fk, fm::log_num(x), 1.0);
+    } else {
+        lg = proj_log_slow(p.K, V);
+    }
     return growth(p, V, lg, C, D, noise);
 }
 
@@ -206,11 +222,23 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
                         int *__restrict__ n_rows, int *__restrict__ err)
 {
     static_assert(H >= 1 && H <= MAXH, "projection horizon");
-    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
+    // The 2H x H projected volumes of a step (400 B per patient at H = 5) are staged in shared memory and written
+    // by the whole warp, one patient's block per instruction (25 lanes x 16 B contiguous): per-thread 8-byte stores
+    // 23.6 KB apart kept this kernel at 0.8 TB/s of scattered sector writes.
+    extern __shared__ __align__(16) double cf_stage[];           // [blockDim][PITCH]
+    constexpr int BLK = 2 * H * H, PITCH = BLK + 1;
+    const int lane = threadIdx.x & 31;
+    double *my_stage = cf_stage + (size_t)threadIdx.x * PITCH;
+    const double *warp_stage = cf_stage + (size_t)(threadIdx.x - lane) * PITCH;
+    const int64_t i_raw = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool exists = i_raw < hi;
+    const int64_t i = exists ? i_raw : lo;                       // lanes past the end idle through the warp copies
+    const int64_t i_warp0 = i_raw - lane;
     const int64_t gi = base + i;
     const int NW = T + H;  // noise row width
     const Patient p = load_patient(params, n, i);
+    const fm::FmK fk = fm::consts();
+    bool missing = false;
     WindowRow w;
     w.F = nullptr; w.n_f = 0; w.tail_len = 0; w.self = (gi == 0);
 #pragma unroll
@@ -218,7 +246,8 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
     if (!w.self) {
         const int64_t j = find_owner(src.off, src.n, gi);
         if (j < 0) {
-            if (src_required) { atomicExch(err, 1); return; }
+            if (src_required && exists) { atomicExch(err, 1); }
+            missing = src_required != 0;
         } else {
             int r = (int)(gi - src.off[j]);
             int ts = 0, o = 0;
@@ -246,14 +275,17 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
     for (int q = 0; q < 16; ++q) s.win[q] = 0.0;
     double *Fr = F_out + i * T;
     uint8_t *cr = codes_out + i * T;
-    Fr[0] = p.v0;
+    if (exists) Fr[0] = p.v0;
     double self_F1 = 0.0, self_tail[H];
 #pragma unroll
     for (int q = 0; q < H; ++q) self_tail[q] = 0.0;
     int steps = 0, rows = 0;
-    bool alive = true;
+    bool alive = exists && !missing;
     for (int t = 0; t < T - 1; ++t) {
-        if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; valid_out[i * (T - 1) + t] = 0; continue; }
+        const bool live = alive;
+        if (!live) {
+            if (exists) { Fr[t + 1] = 0.0; cr[t] = 0; valid_out[i * (T - 1) + t] = 0; }
+        } else {
         double w_t;
         if (w.self) {
             // row 0 = first row this patient emits at t = 0: [F0, F1, projections of that option, 0, ...]
@@ -273,74 +305,59 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         Fr[t + 1] = Fn;
         cr[t] = (uint8_t)fo;
 
-        // ---- 2H sliding-treatment projections (:707-756); noise index of projected step k is t+2+k
+        // ---- 2H sliding-treatment projections (:707-756); noise index of projected step k is t+2+k.
+        // Level-major order: at projected step k the untreated baseline, the k+1 chemo options and the k+1 radio
+        // options that have started are 2k+3 independent recursions, written back to back so that the scheduler
+        // can interleave them (option-major order ran each 5-step chain on its own: 0.1 IPC per warp).
         const double *nz = noise + i * NW + t + 2;
-        double Vb[H + 1], Cb[H];
+        double Vb[H + 1], Cb[H];     // untreated path and its chemo concentration
+        double Vc[H], Cc[H];         // option sft (chemo at step sft): current volume / concentration
+        double Vr[H];                // option H + sft (radio at step sft): current volume
+        double *cfr = my_stage;
         Vb[0] = Fn;
+        unsigned nan_c = 0u, nan_r = 0u;   // options that produced a NaN so far (:745-746)
+        unsigned nan_b = 0u;               // bit k: baseline volume Vb[k+1] is NaN
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            Cb[k] = __dadd_rn(__dmul_rn(k == 0 ? C_t : Cb[k - 1], c.decay), 0.0);
-            Vb[k + 1] = proj_step(p, Vb[k], Cb[k], 0.0, nz[k]);
+            const double Cprev_b = (k == 0) ? C_t : Cb[k - 1];
+            Cb[k] = __dadd_rn(__dmul_rn(Cprev_b, c.decay), 0.0);
+            Vb[k + 1] = proj_step(fk, p, Vb[k], Cb[k], 0.0, nz[k]);
+            if (isnan(Vb[k + 1])) nan_b |= 1u << k;
+#pragma unroll
+            for (int sft = 0; sft <= k; ++sft) {
+                // chemo option: its own concentration from the step it starts
+                const double Vin_c = (sft == k) ? Vb[k] : Vc[sft];
+                const double Cin = (sft == k) ? Cprev_b : Cc[sft];
+                Cc[sft] = __dadd_rn(__dmul_rn(Cin, c.decay), sft == k ? c.chemo_amt : 0.0);
+                Vc[sft] = proj_step(fk, p, Vin_c, Cc[sft], 0.0, nz[k]);
+                if (isnan(Vc[sft])) nan_c |= 1u << sft;
+                cfr[sft * H + k] = Vc[sft];
+                // radio option: baseline concentration, dose at the step it starts
+                const double Vin_r = (sft == k) ? Vb[k] : Vr[sft];
+                Vr[sft] = proj_step(fk, p, Vin_r, Cb[k], sft == k ? c.radio_amt : 0.0, nz[k]);
+                if (isnan(Vr[sft])) nan_r |= 1u << sft;
+                cfr[(H + sft) * H + k] = Vr[sft];
+            }
+            // options that start later still follow the baseline at this step
+#pragma unroll
+            for (int sft = k + 1; sft < H; ++sft) {
+                cfr[sft * H + k] = Vb[k + 1];
+                cfr[(H + sft) * H + k] = Vb[k + 1];
+            }
         }
-        double *cfr = cf_out + (i * (T - 1) + t) * (2 * H) * H;
+        // an option is dropped if any of its H volumes is NaN: its own steps or the baseline steps before its start
         unsigned vmask = 0;
-        bool first_done = false;
 #pragma unroll
         for (int sft = 0; sft < H; ++sft) {
-            // option sft: chemo at projected step sft
-            {
-                double V = Vb[sft];
-                double C = 0.0;
-                bool nan_any = false;
-                double outv[H];
-#pragma unroll
-                for (int k = 0; k < H; ++k) {
-                    if (k < sft) {
-                        outv[k] = Vb[k + 1];
-                    } else {
-                        const double prev = (k == sft) ? (sft == 0 ? C_t : Cb[sft - 1]) : C;
-                        C = __dadd_rn(__dmul_rn(prev, c.decay), k == sft ? c.chemo_amt : 0.0);
-                        V = proj_step(p, V, C, 0.0, nz[k]);
-                        outv[k] = V;
-                    }
-                    nan_any |= isnan(outv[k]);
-                    cfr[sft * H + k] = outv[k];
-                }
-                if (!nan_any) {
-                    vmask |= 1u << sft;
-                    if (t == 0 && !first_done) {
-                        first_done = true;
-#pragma unroll
-                        for (int k = 0; k < H; ++k) self_tail[k] = outv[k];
-                    }
-                }
-            }
+            const unsigned before = nan_b & ((1u << sft) - 1u);
+            if (before == 0u && !((nan_c >> sft) & 1u)) vmask |= 1u << sft;
+            if (before == 0u && !((nan_r >> sft) & 1u)) vmask |= 1u << (H + sft);
         }
+        if (t == 0 && vmask != 0u) {
+            // row 0 of patient 0 = its first emitted option (window quirk): keep that option's projections
+            const int o = __ffs(vmask) - 1;
 #pragma unroll
-        for (int sft = 0; sft < H; ++sft) {
-            // option H + sft: radiotherapy at projected step sft
-            double V = Vb[sft];
-            bool nan_any = false;
-            double outv[H];
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                if (k < sft) {
-                    outv[k] = Vb[k + 1];
-                } else {
-                    V = proj_step(p, V, Cb[k], k == sft ? c.radio_amt : 0.0, nz[k]);
-                    outv[k] = V;
-                }
-                nan_any |= isnan(outv[k]);
-                cfr[(H + sft) * H + k] = outv[k];
-            }
-            if (!nan_any) {
-                vmask |= 1u << (H + sft);
-                if (t == 0 && !first_done) {
-                    first_done = true;
-#pragma unroll
-                    for (int k = 0; k < H; ++k) self_tail[k] = outv[k];
-                }
-            }
+            for (int k = 0; k < H; ++k) self_tail[k] = cfr[o * H + k];
         }
         valid_out[i * (T - 1) + t] = (uint16_t)vmask;
         rows += __popc(vmask);
@@ -352,10 +369,28 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         s.F = Fn;
         s.Cprev = C_t;
         if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
+        }
+        // the warp writes the staged blocks of its live patients: one block per instruction
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        __syncwarp();
+        for (unsigned m = live_mask; m != 0u; m &= m - 1u) {
+            const int r = __ffs(m) - 1;
+            if (lane < BLK / 2) {
+                // PITCH is odd: 8-byte loads from the stage, 16-byte store (the global block is 16-byte aligned)
+                const double *src_row = warp_stage + (size_t)r * PITCH + 2 * lane;
+                double2 v;
+                v.x = src_row[0]; v.y = src_row[1];
+                double *dst = cf_out + ((i_warp0 + r) * (T - 1) + t) * BLK;
+                __stcs(reinterpret_cast<double2 *>(dst) + lane, v);
+            }
+        }
+        __syncwarp();
     }
-    cr[T - 1] = 0;
-    n_steps[i] = steps;
-    n_rows[i] = rows;
+    if (exists) {
+        cr[T - 1] = 0;
+        n_steps[i] = steps;
+        n_rows[i] = rows;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -607,7 +642,14 @@ extern "C" int b200i_sim_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const
         if (source) src = CfSrc{source->n, source->factual, source->codes, source->cf, source->valid, source->row_offsets};
         else src = CfSrc{lo, factual, codes, cf, valid, row_offsets};
         const unsigned grid = (unsigned)((hi - lo + 127) / 128);
-        cf_treatment_seq_kernel<5><<<grid, 128, 0, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs,
+        constexpr int STAGE_BYTES = 128 * (2 * 5 * 5 + 1) * 8;   // [128 threads][2H*H + 1] doubles
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200I_CUDA(cudaFuncSetAttribute(cf_treatment_seq_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            STAGE_BYTES));
+            attr_set = true;
+        }
+        cf_treatment_seq_kernel<5><<<grid, 128, STAGE_BYTES, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs,
                                                          radio_rvs, global_base, src, required ? 1 : 0, factual, codes,
                                                          cf, valid, n_steps, n_rows, d_err);
         return check_cuda(cudaGetLastError(), "cf_treatment_seq launch");
