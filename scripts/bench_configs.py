@@ -86,11 +86,14 @@ def main():
                       "rows_per_s": n / ms * 1e3, "euler_steps_per_s": n * 59 * 5 / ms * 1e3}), flush=True)
     nb = min(n, int(os.environ.get("BFGS_ROWS", "200000")))
     ms, (c7, status, fval) = timed(lambda: dev.insite_bfgs(x[:nb].contiguous(), codes[:nb].contiguous(),
-                                                           seq[:nb].contiguous(), 1, static[:nb].contiguous(), prior, 10.0),
+                                                           fit_len[:nb].contiguous(), 1, static[:nb].contiguous(), prior, 10.0),
                                    reps=2)
     print(json.dumps({"kernel": "insite_bfgs (K7, 16 coefficients per row, FP64)", "rows": nb, "ms": ms,
                       "fits_per_s": nb / ms * 1e3,
-                      "status_hist": np.bincount(status.cpu().numpy().astype(np.int64) & 7, minlength=4).tolist()}), flush=True)
+                      "status_hist (0 converged, 1 max_iter, 3/5 line search exhausted, 4 perfect start, 6 kept theta0)":
+                          np.bincount(status.cpu().numpy().astype(np.int64) & 255, minlength=7).tolist(),
+                      "mean_iterations": float((status.cpu().numpy().astype(np.int64) >> 8).mean()),
+                      "mean_objective_ratio": float((fval[:, 1] / fval[:, 0].clamp_min(1e-300)).mean().item())}), flush=True)
 
 
 if __name__ == "__main__":
