@@ -159,6 +159,11 @@ B200I_API int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t subs
                       const double *x0, const double *static_feature, const uint8_t *codes,
                       const double *coefs, int32_t coefs_per_row, double drop_below,
                       double *pred, void *stream);
+/* FP32 variant (BASELINE config C4, "FP32 vs FP64"): same interface, state / coefficients / Euler steps in float32. */
+B200I_API int b200i_ode_rollout_f32(int64_t rows, int32_t W, double dt, int32_t substeps,
+                      const double *x0, const double *static_feature, const uint8_t *codes,
+                      const double *coefs, int32_t coefs_per_row, double drop_below,
+                      double *pred, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * treatment codes: code = chemo + 2*radio of the (R,Wfull) application arrays, columns [0,W)

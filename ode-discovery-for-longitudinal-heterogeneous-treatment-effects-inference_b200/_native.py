@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200i_theta_gram": (ctypes.c_int, [c_i64, c_i32, c_f64] + [c_vp] * 9),
     "b200i_stlsq_population": (ctypes.c_int, [c_vp, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp]),
     "b200i_ode_rollout": (ctypes.c_int, [c_i64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_vp, c_vp]),
+    "b200i_ode_rollout_f32": (ctypes.c_int, [c_i64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_vp, c_vp]),
     "b200i_treatment_codes": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200i_masked_se_workspace_bytes": (c_i64, []),
     "b200i_masked_se": (ctypes.c_int, [c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

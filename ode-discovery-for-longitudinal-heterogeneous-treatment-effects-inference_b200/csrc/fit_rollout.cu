@@ -29,11 +29,23 @@ __global__ void stlsq_population_kernel(const double *__restrict__ stats, double
 // as one contiguous, fully coalesced chunk per CTA.
 constexpr int RP = 128;
 
+// single-rounding arithmetic in the rollout's compute type (no FMA contraction: mirrors the reference's
+// separate multiply / add, pkpd/utils.py:68-71)
+__device__ __forceinline__ double r_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double r_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float r_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float r_mul(float a, float b) { return __fmul_rn(a, b); }
+
+// R = double: the reference's arithmetic (jax_enable_x64).  R = float: the FP32 variant of BASELINE config C4
+// (same inputs and outputs in float64, state / coefficients / Euler steps in float32; agrees to ~1e-5 relative
+// over 295 sub-steps, tolerance 1e-4).
+template <typename R>
 __global__ void __launch_bounds__(RP)
-ode_rollout_kernel(int64_t rows, int W, double h, int substeps, const double *__restrict__ x0,
+ode_rollout_kernel(int64_t rows, int W, double h_d, int substeps, const double *__restrict__ x0,
                    const double *__restrict__ static_feature, const uint8_t *__restrict__ codes,
                    const double *__restrict__ coefs, int per_row, double drop_below, double *__restrict__ pred)
 {
+    const R h = (R)h_d;
     extern __shared__ double s_out[];  // [RP][W | 1]
     __shared__ double s_coef[16];
     const int pitch = W | 1;
@@ -48,36 +60,36 @@ ode_rollout_kernel(int64_t rows, int W, double h, int substeps, const double *__
         const int64_t first = tile * RP;
         const int64_t r = first + tid;
         if (r < rows) {
-            double c[4][4];
+            R c[4][4];
             if (per_row) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const double v = coefs[r * 16 + j];
-                    c[j >> 2][j & 3] = (fabs(v) > drop_below) ? v : 0.0;
+                    c[j >> 2][j & 3] = (R)((fabs(v) > drop_below) ? v : 0.0);
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) c[j >> 2][j & 3] = s_coef[j];
+                for (int j = 0; j < 16; ++j) c[j >> 2][j & 3] = (R)s_coef[j];
             }
-            double v = x0[r];
-            const double u = static_feature[r];
+            R v = (R)x0[r];
+            const R u = (R)static_feature[r];
             const uint8_t *cr = codes + r * W;
             for (int k = 0; k < W; ++k) {
                 const int a = cr[k] & 3;
                 // select the treatment's ODE (argmax of the one-hot, sindy.py:310 / :499)
-                const double c0 = a == 0 ? c[0][0] : a == 1 ? c[1][0] : a == 2 ? c[2][0] : c[3][0];
-                const double c1 = a == 0 ? c[0][1] : a == 1 ? c[1][1] : a == 2 ? c[2][1] : c[3][1];
-                const double c2 = a == 0 ? c[0][2] : a == 1 ? c[1][2] : a == 2 ? c[2][2] : c[3][2];
-                const double c3 = a == 0 ? c[0][3] : a == 1 ? c[1][3] : a == 2 ? c[2][3] : c[3][3];
-                const double c2u = __dmul_rn(c2, u);
+                const R c0 = a == 0 ? c[0][0] : a == 1 ? c[1][0] : a == 2 ? c[2][0] : c[3][0];
+                const R c1 = a == 0 ? c[0][1] : a == 1 ? c[1][1] : a == 2 ? c[2][1] : c[3][1];
+                const R c2 = a == 0 ? c[0][2] : a == 1 ? c[1][2] : a == 2 ? c[2][2] : c[3][2];
+                const R c3 = a == 0 ? c[0][3] : a == 1 ? c[1][3] : a == 2 ? c[2][3] : c[3][3];
+                const R c2u = r_mul(c2, u);
                 for (int sidx = 0; sidx < substeps; ++sidx) {
                     // y + (c0*1 + c1*y + c2*u + c3*(y*u)) * h   (pkpd/utils.py:68-71, sindy.py:491-496)
-                    double f = __dadd_rn(c0, __dmul_rn(c1, v));
-                    f = __dadd_rn(f, c2u);
-                    f = __dadd_rn(f, __dmul_rn(c3, __dmul_rn(v, u)));
-                    v = __dadd_rn(v, __dmul_rn(f, h));
+                    R f = r_add(c0, r_mul(c1, v));
+                    f = r_add(f, c2u);
+                    f = r_add(f, r_mul(c3, r_mul(v, u)));
+                    v = r_add(v, r_mul(f, h));
                 }
-                s_out[tid * pitch + k] = v;
+                s_out[tid * pitch + k] = (double)v;
             }
         }
         __syncthreads();
@@ -193,9 +205,29 @@ extern "C" int b200i_stlsq_population(const double *stats, double threshold, dou
     return check_cuda(cudaGetLastError(), "stlsq_population launch");
 }
 
+static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
+                            const double *static_feature, const uint8_t *codes, const double *coefs,
+                            int32_t coefs_per_row, double drop_below, double *pred, void *stream);
+
 extern "C" int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
                                  const double *static_feature, const uint8_t *codes, const double *coefs,
                                  int32_t coefs_per_row, double drop_below, double *pred, void *stream)
+{
+    return ode_rollout_impl(false, rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below,
+                            pred, stream);
+}
+
+extern "C" int b200i_ode_rollout_f32(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
+                                     const double *static_feature, const uint8_t *codes, const double *coefs,
+                                     int32_t coefs_per_row, double drop_below, double *pred, void *stream)
+{
+    return ode_rollout_impl(true, rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below,
+                            pred, stream);
+}
+
+static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
+                            const double *static_feature, const uint8_t *codes, const double *coefs,
+                            int32_t coefs_per_row, double drop_below, double *pred, void *stream)
 {
     B200I_REQUIRE(rows >= 0 && x0 && static_feature && codes && coefs && pred, B200I_E_ARG,
                   "ode_rollout: NULL argument or negative rows");
@@ -203,11 +235,12 @@ extern "C" int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t sub
     if (rows == 0) return 0;
     const size_t smem = (size_t)RP * (W | 1) * sizeof(double);
     B200I_REQUIRE(smem <= 200 * 1024, B200I_E_UNSUPPORTED, "ode_rollout: W=%d too wide", W);
-    B200I_CUDA(cudaFuncSetAttribute(ode_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = f32 ? ode_rollout_kernel<float> : ode_rollout_kernel<double>;
+    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = (rows + RP - 1) / RP;
     const int64_t cap = (int64_t)num_sms() * 3;
     if (grid > cap) grid = cap;
-    ode_rollout_kernel<<<(unsigned)grid, RP, smem, static_cast<cudaStream_t>(stream)>>>(
+    kern<<<(unsigned)grid, RP, smem, static_cast<cudaStream_t>(stream)>>>(
         rows, W, dt / substeps, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, pred);
     return check_cuda(cudaGetLastError(), "ode_rollout launch");
 }

@@ -169,15 +169,18 @@ def treatment_codes(chemo_application, radio_application, W):
     return codes
 
 
-def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS_FOR_DT, drop_below=1e-3, out=None):
-    """K6.  codes (R,W) uint8; coefs (4,4) or (R,4,4).  Returns (R,W) un-scaled predictions."""
+def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS_FOR_DT, drop_below=1e-3, out=None,
+                fp32=False):
+    """K6.  codes (R,W) uint8; coefs (4,4) or (R,4,4).  Returns (R,W) un-scaled predictions.
+    fp32: integrate in float32 (inputs / outputs stay float64)."""
     lib = _native.load()
     rows, W = codes.shape
     per_row = 1 if coefs.dim() == 3 else 0
     if out is None:
         out = torch.empty((rows, W), dtype=torch.float64, device='cuda')
-    rc = lib.b200i_ode_rollout(rows, W, float(dt), int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes),
-                               _ptr(coefs), per_row, float(drop_below), _ptr(out), _stream())
+    fn = lib.b200i_ode_rollout_f32 if fp32 else lib.b200i_ode_rollout
+    rc = fn(rows, W, float(dt), int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes),
+            _ptr(coefs), per_row, float(drop_below), _ptr(out), _stream())
     _native.check(rc, "b200i_ode_rollout")
     return out
 

@@ -84,6 +84,10 @@ def main():
     ms, pred = timed(lambda: dev.ode_rollout(x[:, 0].contiguous(), static, codes[:, :T - 1].contiguous(), pc))
     print(json.dumps({"kernel": "ode_rollout (K6, per-row coefficients, 59 x 5 Euler sub-steps)", "rows": n, "ms": ms,
                       "rows_per_s": n / ms * 1e3, "euler_steps_per_s": n * 59 * 5 / ms * 1e3}), flush=True)
+    ms32, pred32 = timed(lambda: dev.ode_rollout(x[:, 0].contiguous(), static, codes[:, :T - 1].contiguous(), pc, fp32=True))
+    dev_rel = float(((pred32 - pred).abs() / pred.abs().clamp_min(1e-3 * float(pred.abs().max()))).max().item())
+    print(json.dumps({"kernel": "ode_rollout_f32 (K6 in float32)", "rows": n, "ms": ms32, "rows_per_s": n / ms32 * 1e3,
+                      "max_rel_dev_vs_fp64": dev_rel}), flush=True)
     nb = min(n, int(os.environ.get("BFGS_ROWS", "200000")))
     ms, (c7, status, fval) = timed(lambda: dev.insite_bfgs(x[:nb].contiguous(), codes[:nb].contiguous(),
                                                            fit_len[:nb].contiguous(), 1, static[:nb].contiguous(), prior, 10.0),

@@ -151,6 +151,27 @@ def test_population_stlsq_support_matches_oracle(dev, seed1, threshold, alpha):
         np.testing.assert_allclose(coefs[a], c_ref, rtol=1e-7, atol=1e-12)
 
 
+def test_rollout_fp32_within_1e4_of_fp64(dev, seed1):
+    """FP32 variant of the discovered-ODE rollout (BASELINE config C4): 1e-4 relative to the FP64 path."""
+    import torch
+    _, o, _, _ = seed1
+    log = h.load_json('ref_log_seed1.json')['sindy']
+    coefs = dev.to_device(np.array(log['coefs']))
+    one = o['one']
+    R, T = one['cancer_volume'].shape
+    codes = dev.treatment_codes(dev.to_device(one['chemo_application']), dev.to_device(one['radio_application']), T - 1)
+    x0 = dev.to_device(np.ascontiguousarray(one['cancer_volume'][:, 0]))
+    static = dev.to_device(np.asarray(one['patient_types'], dtype=np.float64))
+    p64 = dev.ode_rollout(x0, static, codes, coefs)
+    p32 = dev.ode_rollout(x0, static, codes, coefs, fp32=True)
+    torch.cuda.synchronize()
+    a, b = p64.cpu().numpy(), p32.cpu().numpy()
+    assert np.isfinite(b).all()
+    scale = np.maximum(np.abs(a), 1e-3 * np.abs(a).max())       # relative to the trajectory's scale
+    assert np.max(np.abs(a - b) / scale) < 1e-4                 # north star: 1e-4 in FP32
+    assert not np.array_equal(a, b)                             # it really is a different arithmetic
+
+
 def test_rollout_and_metrics_reproduce_reference_log(dev, seed1):
     """K6 + masked-SE on the one-step and treatment-sequence test sets: the 8 logged SINDy RMSEs."""
     import torch
