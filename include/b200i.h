@@ -126,6 +126,22 @@ B200I_API int b200i_theta_gram(int64_t n, int32_t T, double fd_dt,
                      const double *static_feature,
                      const double *chemo_dosage, const double *radio_dosage,
                      void *gram_workspace, void *stream);
+/* mode 1 = the joint model's reduction (sindy.py:160-171 with joint_model=True; pkpd/utils.py:493-497, 656-672): one
+ * trajectory per patient, x_k = cancer_volume[k+1] for k < sequence_length, inputs of sample k = the applications of
+ * column k, order-1 finite differences over the whole trajectory; same 15 statistics per treatment code, from which
+ * b200i_stlsq_joint assembles the 11x11 normal equations.  mode 0 = b200i_theta_gram_pitched. */
+B200I_API int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
+                     const double *cancer_volume, const double *chemo_application,
+                     const double *radio_application, const double *sequence_lengths,
+                     const double *static_feature,
+                     const double *chemo_dosage, const double *radio_dosage,
+                     void *gram_workspace, void *stream);
+/* Joint-model STLSQ + unbias (pysindy semantics as b200i_stlsq_population) on the 11-term library
+ * [1,x0,u0,u1,u2,x0u0,x0u1,x0u2,u0u1,u0u2,u1u2] (u0 chemo, u1 radio, u2 static feature).
+ * out: coefs11 (11,), support11 (11,) int32, coefs44 (4,4): the expression with |c| > drop_below restricted to each
+ *      treatment code chemo + 2*radio, i.e. what b200i_ode_rollout integrates (pass drop_below < 0 there). */
+B200I_API int b200i_stlsq_joint(const double *stats, double threshold, double alpha, int32_t max_iter, double drop_below,
+                     double *coefs11, int32_t *support11, double *coefs44, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
                      const double *cancer_volume, const double *chemo_application,

@@ -20,7 +20,8 @@ def _tree(d):
     return Config(**{k: _tree(v) if isinstance(v, dict) else v for k, v in d.items()})
 
 
-def default_config(insite=True, gamma=2.0, seed=1, n_train=1000, n_val=100, n_test=100, **model_overrides):
+def default_config(insite=True, gamma=2.0, seed=1, n_train=1000, n_val=100, n_test=100, treatment_mode='multiclass',
+                   **model_overrides):
     """Defaults of the reference: sindy_alpha 0.5 (config.yaml:18), sindy_threshold 1e-3 (:21), lam 10 (:25),
     window 15, lag 0, T 60, H 5, sliding_treatment (cancer_sim.yaml:13-17), insite.yaml:3-23."""
     model = dict(name='INSITE' if insite else 'SINDy', lag_features=1, insite_val_error_threshold=1e-4, lam=10.0,
@@ -37,5 +38,5 @@ def default_config(insite=True, gamma=2.0, seed=1, n_train=1000, n_val=100, n_te
         'dataset': dict(name='tumor_generator', coeff=gamma, chemo_coeff=gamma, radio_coeff=gamma, seed=seed,
                         num_patients=dict(train=n_train, val=n_val, test=n_test), window_size=15, lag=0,
                         max_seq_length=60, projection_horizon=5, cf_seq_mode='sliding_treatment',
-                        val_batch_size=512, treatment_mode='multiclass'),
+                        val_batch_size=512, treatment_mode=treatment_mode),
         'exp': dict(seed=seed, unscale_rmse=True, percentage_rmse=True, logging=False)})

@@ -24,6 +24,129 @@ __global__ void stlsq_population_kernel(const double *__restrict__ stats, double
     }
 }
 
+// ---- K5j: joint model (one ODE over [x0, chemo, radio, static]; sindy.py:185-204 with joint_model=True) ------------
+// The 11-term library [1,x0,u0,u1,u2,x0u0,x0u1,x0u2,u0u1,u0u2,u1u2] (PolynomialLibrary(degree=2,
+// interaction_only=True) on four inputs) evaluated at a treatment (u0,u1) = (chemo,radio) in {0,1}^2 is a linear
+// image of psi = [1,x0,u2,x0u2], so its normal equations are assembled from the same per-treatment statistics that
+// theta_gram (mode 1) reduces: G11 = sum_a M_a G_a M_a^T, b11 = sum_a M_a b_a.  Then STLSQ + unbias as in stlsq.cuh,
+// for JP features (single thread, local arrays).
+constexpr int JP = 11;
+
+__device__ bool solve_spd_jp(const double (&G)[JP][JP], const double (&b)[JP], unsigned mask, double ridge, double (&c)[JP])
+{
+    double A[JP][JP], r[JP], sc[JP], y[JP];
+    bool ok = true;
+    for (int i = 0; i < JP; ++i) {
+        const bool si = (mask >> i) & 1u;
+        const double d = si ? G[i][i] + ridge : 1.0;
+        ok = ok && (d > 0.0);
+        sc[i] = si ? 1.0 / sqrt(d > 0.0 ? d : 1.0) : 1.0;
+        r[i] = si ? b[i] * sc[i] : 0.0;
+    }
+    for (int i = 0; i < JP; ++i)
+        for (int j = 0; j < JP; ++j) {
+            const bool sel = ((mask >> i) & 1u) && ((mask >> j) & 1u);
+            A[i][j] = sel ? (G[i][j] + ((i == j) ? ridge : 0.0)) * sc[i] * sc[j] : ((i == j) ? 1.0 : 0.0);
+        }
+    for (int j = 0; j < JP; ++j) {
+        double d = A[j][j];
+        for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+        ok = ok && (d > 0.0);
+        d = sqrt(d > 0.0 ? d : 1.0);
+        A[j][j] = d;
+        for (int i = j + 1; i < JP; ++i) {
+            double v = A[i][j];
+            for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k];
+            A[i][j] = v / d;
+        }
+    }
+    for (int i = 0; i < JP; ++i) {
+        double v = r[i];
+        for (int k = 0; k < i; ++k) v -= A[i][k] * y[k];
+        y[i] = v / A[i][i];
+    }
+    for (int i = JP - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < JP; ++k) v -= A[k][i] * y[k];
+        y[i] = v / A[i][i];
+    }
+    for (int i = 0; i < JP; ++i) c[i] = ((mask >> i) & 1u) ? y[i] * sc[i] : 0.0;
+    return ok;
+}
+
+__global__ void stlsq_joint_kernel(const double *__restrict__ stats, double threshold, double alpha, int max_iter,
+                                   double drop_below, double *__restrict__ coefs11, int *__restrict__ support11,
+                                   double *__restrict__ coefs44)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // feature f = mult_f(u0,u1) * psi[idx_f]
+    const int idx[JP] = {0, 1, 0, 0, 2, 1, 1, 3, 0, 2, 2};
+    double G[JP][JP], b[JP], coef[JP];
+    for (int i = 0; i < JP; ++i) {
+        b[i] = 0.0; coef[i] = 0.0;
+        for (int j = 0; j < JP; ++j) G[i][j] = 0.0;
+    }
+    double total = 0.0;
+    for (int a = 0; a < 4; ++a) {
+        double Ga[4][4], ba[4];
+        unpack_gram(stats + a * B200I_GRAM_PER_TREATMENT, Ga, ba);
+        total += stats[a * B200I_GRAM_PER_TREATMENT + 14];
+        const double u0 = (double)(a & 1), u1 = (double)(a >> 1);
+        const double m[JP] = {1.0, 1.0, u0, u1, 1.0, u0, u1, 1.0, u0 * u1, u0, u1};
+        for (int i = 0; i < JP; ++i) {
+            b[i] += m[i] * ba[idx[i]];
+            for (int j = 0; j < JP; ++j) G[i][j] += m[i] * m[j] * Ga[idx[i]][idx[j]];
+        }
+    }
+    unsigned ind = (1u << JP) - 1u;
+    if (total > 0.0) {
+        const int n_selected0 = JP;
+        unsigned prev_pattern = ind;   // history_[0] is the dense OLS initial guess
+        for (int it = 0; it < max_iter; ++it) {
+            if (ind == 0u) {
+                for (int j = 0; j < JP; ++j) coef[j] = 0.0;
+                break;
+            }
+            double c[JP];
+            if (!solve_spd_jp(G, b, ind, alpha, c)) break;
+            unsigned big = 0u;
+            for (int j = 0; j < JP; ++j) {
+                if (((ind >> j) & 1u) && fabs(c[j]) >= threshold) big |= 1u << j;
+                else c[j] = 0.0;
+                coef[j] = c[j];
+            }
+            ind = big;
+            unsigned pattern = 0u;
+            for (int j = 0; j < JP; ++j) pattern |= (coef[j] != 0.0 ? 1u : 0u) << j;
+            const bool no_change = (pattern == prev_pattern);
+            prev_pattern = pattern;
+            if (__popc(ind) == n_selected0 || no_change) break;
+        }
+        if (ind != 0u) {   // unbias: ordinary least squares on the support
+            double c[JP];
+            if (solve_spd_jp(G, b, ind, 0.0, c))
+                for (int j = 0; j < JP; ++j) coef[j] = c[j];
+        }
+    } else {
+        ind = 0u;
+    }
+    for (int j = 0; j < JP; ++j) {
+        coefs11[j] = coef[j];
+        support11[j] = (int)((ind >> j) & 1u);
+    }
+    // the expression the reference integrates keeps the terms with |c| > drop_below (pkpd/utils.py:387-391);
+    // restricted to a treatment it is the 4-term ODE over [1, x0, u2, x0 u2] that ode_rollout takes
+    double e[JP];
+    for (int j = 0; j < JP; ++j) e[j] = (fabs(coef[j]) > drop_below) ? coef[j] : 0.0;
+    for (int a = 0; a < 4; ++a) {
+        const double u0 = (double)(a & 1), u1 = (double)(a >> 1);
+        coefs44[a * 4 + 0] = e[0] + e[2] * u0 + e[3] * u1 + e[8] * u0 * u1;
+        coefs44[a * 4 + 1] = e[1] + e[5] * u0 + e[6] * u1;
+        coefs44[a * 4 + 2] = e[4] + e[9] * u0 + e[10] * u1;
+        coefs44[a * 4 + 3] = e[7];
+    }
+}
+
 // ---- K6 ------------------------------------------------------------------------------------------
 // thread per row; predictions staged in shared memory (odd pitch: conflict-free) and written back
 // as one contiguous, fully coalesced chunk per CTA.
@@ -203,6 +326,16 @@ extern "C" int b200i_stlsq_population(const double *stats, double threshold, dou
     stlsq_population_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, threshold, alpha, max_iter, coefs,
                                                                              support);
     return check_cuda(cudaGetLastError(), "stlsq_population launch");
+}
+
+extern "C" int b200i_stlsq_joint(const double *stats, double threshold, double alpha, int32_t max_iter, double drop_below,
+                                 double *coefs11, int32_t *support11, double *coefs44, void *stream)
+{
+    B200I_REQUIRE(stats && coefs11 && support11 && coefs44, B200I_E_ARG, "stlsq_joint: NULL argument");
+    B200I_REQUIRE(threshold >= 0 && alpha >= 0 && max_iter >= 1, B200I_E_ARG, "stlsq_joint: bad scalar argument");
+    stlsq_joint_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, threshold, alpha, max_iter, drop_below,
+                                                                        coefs11, support11, coefs44);
+    return check_cuda(cudaGetLastError(), "stlsq_joint launch");
 }
 
 static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,

@@ -143,7 +143,7 @@ constexpr int G2_WARPS = 4;
 
 template <int MAXT>
 __global__ void __launch_bounds__(G2_WARPS * 32, 2)
-theta_gram2_kernel(int64_t n, int T, int64_t rp, double fd_dt, double inv_dt, const double *__restrict__ vol,
+theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double inv_dt, const double *__restrict__ vol,
                    const double *__restrict__ chemo, const double *__restrict__ radio,
                    const double *__restrict__ seq_len, const double *__restrict__ static_feature,
                    const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws)
@@ -249,9 +249,31 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, double fd_dt, double inv_dt, co
                     pg.s[t][4] = fma(wt, sxd, pg.s[t][4]);
                 }
             };
+            if (mode == 1) {
+                // joint model (process_sindy_training_data(joint=True), pkpd/utils.py:493-497 with the arguments of
+                // :656-672): ONE trajectory per patient, x_k = V[k+1] (the outputs), inputs of sample k = the
+                // applications of column k; FiniteDifference order 1 over the whole trajectory (last point backward)
+                const double *xr = reinterpret_cast<const double *>(row);
+                double xd_prev = 0.0;
+                for (int k = 0; k < L; ++k) {
+                    const double x = xr[k + 1];
+                    const double xdot = (k < L - 1) ? fm::div_small(__dsub_rn(xr[k + 2], x), fd_dt, inv_dt) : xd_prev;
+                    const int a = s_code[k * 33 + lane];
+                    const double sxx = x * x, sxd = x * xdot;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const double wt = (a == t) ? 1.0 : 0.0;
+                        pg.s[t][0] += wt; pg.s[t][1] = fma(wt, x, pg.s[t][1]);
+                        pg.s[t][2] = fma(wt, sxx, pg.s[t][2]); pg.s[t][3] = fma(wt, xdot, pg.s[t][3]);
+                        pg.s[t][4] = fma(wt, sxd, pg.s[t][4]);
+                    }
+                    xd_prev = xdot;
+                }
+                for (int k = 0; k < Ls; ++k) { mv += xr[k]; mvv += xr[k] * xr[k]; }
+            }
             double2 cur = *reinterpret_cast<const double2 *>(row);
             int a0 = s_code[lane];
-            for (int k = 0; k < L; k += 2) {
+            for (int k = 0; mode == 0 && k < L; k += 2) {
                 const double2 nxt = *reinterpret_cast<const double2 *>(row + (k + 2) * 8);   // pitch padding keeps it in bounds
                 const int a1 = s_code[(k + 1) * 33 + lane];
                 const int a2 = (k + 2 < T) ? s_code[(k + 2) * 33 + lane] : 0;
@@ -264,7 +286,7 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, double fd_dt, double inv_dt, co
                 a0 = a2;
                 cur = nxt;
             }
-            if (Ls > L) {   // sequence_length == T: the last entry is active but starts no sample
+            if (mode == 0 && Ls > L) {   // sequence_length == T: the last entry is active but starts no sample
                 const double x = *reinterpret_cast<const double *>(row + (size_t)L * 8);
                 mv += x; mvv += x * x;
             }
@@ -366,6 +388,17 @@ extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch,
                                         const double *static_feature, const double *chemo_dosage,
                                         const double *radio_dosage, void *gram_workspace, void *stream)
 {
+    return b200i_theta_gram_mode(n, T, row_pitch, 0, fd_dt, cancer_volume, chemo_application, radio_application,
+                                 sequence_lengths, static_feature, chemo_dosage, radio_dosage, gram_workspace, stream);
+}
+
+extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
+                                     const double *cancer_volume, const double *chemo_application,
+                                     const double *radio_application, const double *sequence_lengths,
+                                     const double *static_feature, const double *chemo_dosage,
+                                     const double *radio_dosage, void *gram_workspace, void *stream)
+{
+    B200I_REQUIRE(mode == 0 || mode == 1, B200I_E_ARG, "theta_gram: mode %d (0 = per-treatment snippets, 1 = joint)", mode);
     B200I_REQUIRE(row_pitch >= T && (row_pitch == T || row_pitch % 2 == 0), B200I_E_ARG,
                   "theta_gram: row_pitch %lld (T = %d) must be even and >= T", (long long)row_pitch, T);
     B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths &&
@@ -381,7 +414,8 @@ extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch,
     {
         const bool v2 = (T % 2 == 0) && T <= 256 && aligned16(cancer_volume) && aligned16(chemo_application) &&
                         aligned16(radio_application) && (!chemo_dosage || aligned16(chemo_dosage)) &&
-                        (!radio_dosage || aligned16(radio_dosage)) && (row_pitch != T || getenv("B200I_THETA_GRAM_V1") == nullptr);
+                        (!radio_dosage || aligned16(radio_dosage)) &&
+                        (row_pitch != T || mode != 0 || getenv("B200I_THETA_GRAM_V1") == nullptr);
         if (v2) {
             const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
             const size_t smem2 = warp_bytes * G2_WARPS;
@@ -395,14 +429,15 @@ extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch,
                 const int64_t need = (ntiles2 + G2_WARPS - 1) / G2_WARPS;
                 if (grid2 > need) grid2 = need;
                 if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
-                k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
+                k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, mode, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
                                                                   radio_application, sequence_lengths, static_feature,
                                                                   chemo_dosage, radio_dosage, ws);
                 return check_cuda(cudaGetLastError(), "theta_gram2 launch");
             }
         }
     }
-    B200I_REQUIRE(row_pitch == T, B200I_E_UNSUPPORTED, "theta_gram: pitched rows need even T <= 256 and 16-byte aligned arrays");
+    B200I_REQUIRE(row_pitch == T && mode == 0, B200I_E_UNSUPPORTED,
+                  "theta_gram: pitched rows and the joint mode need even T <= 256 and 16-byte aligned arrays");
     const size_t smem = (size_t)GP * T * 9;
     const bool bulk = (T % 2 == 0) && aligned16(cancer_volume) && aligned16(chemo_application) &&
                       aligned16(radio_application);

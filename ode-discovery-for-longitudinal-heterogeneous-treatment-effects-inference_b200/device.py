@@ -135,13 +135,14 @@ def sim_factual(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=Non
 
 
 def theta_gram(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature,
-               chemo_dosage=None, radio_dosage=None, fd_dt=STANDARD_DT, tag="default"):
-    """K4.  Returns the (68,) packed statistics (view into the workspace)."""
+               chemo_dosage=None, radio_dosage=None, fd_dt=STANDARD_DT, tag="default", joint=False):
+    """K4.  Returns the (68,) packed statistics (view into the workspace).  joint: the joint model's reduction
+    (one trajectory per patient over the outputs, see include/b200i.h)."""
     lib = _native.load()
     n, T = cancer_volume.shape
     ws = gram_workspace(tag)
     pitch = row_pitch(cancer_volume, chemo_application, radio_application, chemo_dosage, radio_dosage) if n > 1 else T
-    rc = lib.b200i_theta_gram_pitched(n, T, pitch, float(fd_dt), _ptr_rows(cancer_volume), _ptr_rows(chemo_application),
+    rc = lib.b200i_theta_gram_mode(n, T, pitch, 1 if joint else 0, float(fd_dt), _ptr_rows(cancer_volume), _ptr_rows(chemo_application),
                                       _ptr_rows(radio_application), _ptr(sequence_lengths), _ptr(static_feature),
                                       _ptr_rows(chemo_dosage), _ptr_rows(radio_dosage), _ptr(ws), _stream())
     _native.check(rc, "b200i_theta_gram")
@@ -157,6 +158,19 @@ def stlsq_population(stats, threshold=1e-3, alpha=0.5, max_iter=100):
                                     _ptr(support), _stream())
     _native.check(rc, "b200i_stlsq_population")
     return coefs, support
+
+
+def stlsq_joint(stats, threshold=1e-3, alpha=0.5, max_iter=100, drop_below=1e-3):
+    """K5j.  stats (68,) from theta_gram(joint=True) -> (coefs (11,), support (11,) int32, per-treatment (4,4)
+    coefficients of the thresholded expression for ode_rollout(drop_below=-1))."""
+    lib = _native.load()
+    coefs = torch.empty((11,), dtype=torch.float64, device='cuda')
+    support = torch.empty((11,), dtype=torch.int32, device='cuda')
+    c44 = torch.empty((4, 4), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_stlsq_joint(_ptr(stats), float(threshold), float(alpha), int(max_iter), float(drop_below),
+                               _ptr(coefs), _ptr(support), _ptr(c44), _stream())
+    _native.check(rc, "b200i_stlsq_joint")
+    return coefs, support, c44
 
 
 def treatment_codes(chemo_application, radio_application, W):

@@ -12,7 +12,7 @@ What runs where
     tau-step slicing         get_autoregressive_predictions (sindy.py:717-760)
     metrics                  numpy on the host, formulas of time_varying_model.py:236-313
 
-Not implemented (outside the cancer_sim hot path): Weak-SINDy, EQ_4/EQ_5 datasets, the joint
+Not implemented (outside the cancer_sim hot path): Weak-SINDy, EQ_4/EQ_5 datasets, INSITE on the joint
 11-term model, smoothing / quantisation options, ray-tune finetune.  They raise NotImplementedError.
 """
 import logging
@@ -26,6 +26,9 @@ logger = logging.getLogger(__name__)
 
 FEATURE_LIBRARY_NAMES = ['1', 'x0', 'u0', 'x0 u0']      # PolynomialLibrary(degree=2, interaction_only=True)
 FEATURE_NAMES = ['x0', 'u0']
+# joint model (model.joint_model=True, treatment_mode='multilabel'): one ODE over [x0, chemo, radio, static]
+JOINT_FEATURE_LIBRARY_NAMES = ['1', 'x0', 'u0', 'u1', 'u2', 'x0 u0', 'x0 u1', 'x0 u2', 'u0 u1', 'u0 u2', 'u1 u2']
+JOINT_FEATURE_NAMES = ['x0', 'u0', 'u1', 'u2']
 
 
 def equation_string_core(feature_library_names, feature_names, coefs, quantize=False, quantize_round_to=3):
@@ -90,11 +93,17 @@ class SINDY:
         self.last_fit_info = {}
         if self.dataset_name != 'CANCER_SIM':
             raise NotImplementedError(f"dataset {m.dataset_name!r}: only cancer_sim is on the accelerated path")
-        for flag in ('wsindy', 'joint_model', 'smooth_input_data', 'use_smoothed_finite_difference', 'sindy_quantize',
+        for flag in ('wsindy', 'smooth_input_data', 'use_smoothed_finite_difference', 'sindy_quantize',
                      'ablation_more_complex_basis_functions'):
             if getattr(self, flag):
                 raise NotImplementedError(f"model.{flag}=True is outside the accelerated INSITE path (SURVEY.md §8a/f)")
-        if self.treatment_mode != 'multiclass':
+        if self.joint_model:
+            # the "one ODE" ablation (results/ablation/one_ode): 11-term library, multilabel treatments
+            if self.treatment_mode != 'multilabel':
+                raise NotImplementedError("model.joint_model=True is configured with treatment_mode='multilabel'")
+            if self.insite:
+                raise NotImplementedError("INSITE individualisation of the joint model is not on the accelerated path")
+        elif self.treatment_mode != 'multiclass':
             raise NotImplementedError("treatment_mode must be 'multiclass' for the per-treatment SINDy models")
 
     @staticmethod
@@ -115,7 +124,12 @@ class SINDY:
         prev = np.squeeze(dataset.data['prev_outputs'] * sp['output_stds'] + sp['output_means'], axis=-1)
         lo, hi = self.dim_outcome, self.dim_outcome + self.dim_static_features
         static = dataset.data['static_features'] * sp['inputs_stds'][lo:hi] + sp['input_means'][lo:hi]
-        codes = np.argmax(dataset.data['current_treatments'], axis=-1).astype(np.uint8)
+        ct = dataset.data['current_treatments']
+        if self.treatment_mode == 'multilabel':      # (chemo, radio) applications -> code chemo + 2*radio
+            cti = ct.astype(np.int64)                # sindy.py:396
+            codes = (cti[..., 0] + 2 * cti[..., 1]).astype(np.uint8)
+        else:
+            codes = np.argmax(ct, axis=-1).astype(np.uint8)
         seq = dataset.data['sequence_lengths'].astype(np.int64)
         return prev, static[:, 0], codes, seq
 
@@ -133,7 +147,24 @@ class SINDY:
         chemo[:, :T - 1] = (codes & 1)
         radio[:, :T - 1] = (codes >> 1) & 1
         stats = dev.theta_gram(dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio),
-                               dev.to_device(seq.astype(np.float64)), dev.to_device(static), fd_dt=self.dt)
+                               dev.to_device(seq.astype(np.float64)), dev.to_device(static), fd_dt=self.dt,
+                               joint=bool(self.joint_model))
+        if self.joint_model:
+            coefs11, support11, c44 = dev.stlsq_joint(stats, threshold=self.sindy_threshold, alpha=self.sindy_alpha,
+                                                      max_iter=100, drop_below=1e-3)
+            torch.cuda.current_stream().synchronize()
+            self.joint_coefs = coefs11.cpu().numpy()[None, :]                  # (1, 11), sindy.py:336
+            self.support_ = support11.cpu().numpy().astype(bool)[None, :]
+            self.rollout_coefs_ = c44.cpu().numpy()                            # thresholded expression per treatment
+            self.population_stats_ = stats.cpu().numpy().copy()
+            self.feature_library_names = list(JOINT_FEATURE_LIBRARY_NAMES)
+            self.feature_names = list(JOINT_FEATURE_NAMES)
+            str_0 = equation_string_core(self.feature_library_names, self.feature_names, self.joint_coefs[0],
+                                         quantize=self.sindy_quantize,
+                                         quantize_round_to=self.sindy_quantize_global_model_round_to)
+            self.global_equation_string = f'Joint Model: x_dot = {str_0}'      # sindy.py:314
+            logger.info('[Model Raw]: ' + self.global_equation_string)
+            return self
         coefs, support = dev.stlsq_population(stats, threshold=self.sindy_threshold, alpha=self.sindy_alpha, max_iter=100)
         torch.cuda.current_stream().synchronize()
         self.joint_coefs = coefs.cpu().numpy()
@@ -169,7 +200,10 @@ class SINDY:
         """Open-loop rollout of the population ODE (terms with |c| <= 1e-3 dropped, pkpd/utils.py:388)."""
         sp = dataset.scaling_params
         prev, static, codes, _ = self._unscaled_inputs(dataset)
-        un = self._rollout(prev, static, codes, dev.to_device(self.joint_coefs), 1e-3)
+        if self.joint_model:
+            un = self._rollout(prev, static, codes, dev.to_device(self.rollout_coefs_), -1.0)
+        else:
+            un = self._rollout(prev, static, codes, dev.to_device(self.joint_coefs), 1e-3)
         return ((un - sp['output_means']) / sp['output_stds'])[..., None]
 
     def individualised_coefficients(self, dataset, projection_horizon=1):

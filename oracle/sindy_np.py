@@ -191,6 +191,89 @@ def fit_population(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
     return coefs, sup, stats
 
 
+# ---- joint model (one ODE over [x0, chemo, radio, static]; ablation "one_ode") ---------------------
+JOINT_NAMES = ('1', 'x0', 'u0', 'u1', 'u2', 'x0*u0', 'x0*u1', 'x0*u2', 'u0*u1', 'u0*u2', 'u1*u2')
+
+
+def de_format_joint(data, scaling):
+    """pkpd/utils.py:543-554, :656-672 with process_sindy_training_data(joint=True) :493-497 for CANCER_SIM
+    (sequence_lengths_offset = 0, sindy.py:160-171): one trajectory per patient,
+    X = unscaled_outputs[:L] (the *outputs*, i.e. V[1:1+L]) and U = [current_treatments[:L] (multilabel:
+    chemo, radio application), static repeated]."""
+    static = data['static_features'] * scaling['inputs_stds'][1:2] + scaling['input_means'][1:2]
+    cur = np.squeeze(data['current_treatments'])
+    assert cur.shape[-1] == 2, "the joint model is configured with treatment_mode='multilabel'"
+    out = np.squeeze(data['unscaled_outputs'])
+    sl = data['sequence_lengths'].astype(np.int64)
+    trajs = []
+    for p in range(out.shape[0]):
+        L = int(sl[p])
+        trajs.append((out[p, :L], np.concatenate([cur[p, :L], np.full((L, 1), static[p, 0])], axis=1)))
+    return trajs
+
+
+def library_p11(x, U):
+    """PolynomialLibrary(degree=2, interaction_only=True) on [x0, u0, u1, u2] (JOINT_NAMES order)."""
+    u0, u1, u2 = U[:, 0], U[:, 1], U[:, 2]
+    return np.stack([np.ones_like(x), x, u0, u1, u2, x * u0, x * u1, x * u2, u0 * u1, u0 * u2, u1 * u2], axis=1)
+
+
+def design_matrices_joint(trajs, dt=STANDARD_DT):
+    th = np.concatenate([library_p11(x, U) for x, U in trajs], axis=0)
+    xd = np.concatenate([finite_difference_order1(x, dt) for x, _ in trajs], axis=0)
+    return th, xd
+
+
+def fit_population_joint(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
+    """sindy.py:185-204 with joint_model=True -> joint_coefs (1,11), support (11,), number of rows."""
+    th, xd = design_matrices_joint(de_format_joint(data, scaling), dt)
+    coef, sup = stlsq_fit(th, xd, threshold, alpha)
+    return coef[None, :], sup, th.shape[0]
+
+
+def equation_string_joint(coefs):
+    """pkpd/utils.py:386-391 + sindy.py:314."""
+    s = ''
+    for i, c in enumerate(coefs[0]):
+        if np.abs(c) > 1e-3:
+            s += f'+{c}*' + JOINT_NAMES[i]
+    return f'Joint Model: x_dot = {s}'
+
+
+def joint_to_per_treatment(coefs11):
+    """The 11-term ODE restricted to a treatment (chemo, radio) in {0,1}^2 is a 4-term ODE in [1, x0, u2, x0*u2]:
+    returns (4,4) indexed by the multiclass code chemo + 2*radio (what the rollout kernels take)."""
+    c = np.asarray(coefs11, dtype=np.float64).reshape(-1)
+    out = np.zeros((4, 4))
+    for code in range(4):
+        u0, u1 = float(code & 1), float(code >> 1)
+        out[code] = [c[0] + c[2] * u0 + c[3] * u1 + c[8] * u0 * u1, c[1] + c[5] * u0 + c[6] * u1,
+                     c[4] + c[9] * u0 + c[10] * u1, c[7]]
+    return out
+
+
+def predictions_population_joint(data, scaling, coefs11, dt=STANDARD_DT, steps=STEPS_FOR_DT):
+    """_get_non_fine_tuned_predictions (sindy.py:371-431) with the joint closure (:316-318): Euler rollout of
+    the 11-term expression, treatments = the two multilabel columns."""
+    prev = np.squeeze(data['prev_outputs'] * scaling['output_stds'] + scaling['output_means'], -1)
+    static = data['static_features'] * scaling['inputs_stds'][1:2] + scaling['input_means'][1:2]
+    cur = np.squeeze(data['current_treatments']).astype(np.int64).astype(np.float64)   # :396 astype(int64)
+    c = effective_coefs(np.asarray(coefs11, dtype=np.float64).reshape(-1))
+    R, W, _ = cur.shape
+    v = prev[:, 0].astype(np.float64).copy()
+    u2 = static[:, 0]
+    out = np.empty((R, W))
+    h = dt / steps
+    for k in range(W):
+        u0, u1 = cur[:, k, 0], cur[:, k, 1]
+        for _ in range(steps):
+            f = (c[0] + c[1] * v + c[2] * u0 + c[3] * u1 + c[4] * u2 + c[5] * v * u0 + c[6] * v * u1 + c[7] * v * u2
+                 + c[8] * u0 * u1 + c[9] * u0 * u2 + c[10] * u1 * u2)
+            v = v + f * h
+        out[:, k] = v
+    return ((out - scaling['output_means']) / scaling['output_stds'])[..., None]
+
+
 def equation_string(coefs, names=('1', 'x0', 'u0', 'x0*u0')):
     """pkpd/utils.py:386-391 + sindy.py:295."""
     parts = []

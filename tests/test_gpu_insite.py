@@ -149,3 +149,51 @@ def test_insite_class_ridge_prior_improves_on_population(dev, collection):
                             collection)
     assert ind['encoder_test_rmse_all'] < pop['encoder_test_rmse_all']
     assert ind['decoder_test_rmse_2-step'] < pop['decoder_test_rmse_2-step'] * 1.05
+
+
+# ---- joint ("one ODE") model: SURVEY.md section 8(f) F2 -----------------------------------------------------
+@pytest.fixture(scope="module")
+def collection_joint():
+    from b200_insite.dataset import SyntheticCancerDatasetCollection
+    col = SyntheticCancerDatasetCollection(2.0, 2.0, {'train': 1000, 'val': 100, 'test': 100}, seed=10,
+                                           treatment_mode='multilabel')
+    col.process_data_multi()
+    return col
+
+
+def test_joint_statistics_match_explicit_design_matrices(dev, collection_joint):
+    """theta_gram(mode 1) + the assembly inside b200i_stlsq_joint vs the oracle's explicit 56 300 x 11 design matrix."""
+    import torch
+    from oracle import sindy_np as sp
+    from b200_insite.config import default_config
+    from b200_insite.sindy import SINDY
+    model = SINDY(default_config(insite=False, seed=10, treatment_mode='multilabel', joint_model=True), collection_joint)
+    model.fit(collection_joint.train_f)
+    tr = collection_joint.train_f
+    th, xd = sp.design_matrices_joint(sp.de_format_joint(tr.data, tr.scaling_params))
+    u = dev.unpack_stats(model.population_stats_)
+    # per-treatment blocks: psi = [1, x0, u2, x0 u2] rows of the samples with that (chemo, radio)
+    for a in range(4):
+        rows = (th[:, 2] == (a & 1)) & (th[:, 3] == (a >> 1))
+        psi = th[rows][:, [0, 1, 4, 7]]
+        assert u['count'][a] == rows.sum()
+        np.testing.assert_allclose(u['G'][a], psi.T @ psi, rtol=1e-10)
+        np.testing.assert_allclose(u['b'][a], psi.T @ xd[rows], rtol=1e-8, atol=1e-6)
+    assert int(u['count'].sum()) == th.shape[0] == 56300
+
+
+def test_joint_model_class_reproduces_reference_ablation_log(dev, collection_joint):
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    log = h.load_json('ref_log_joint_seed10.json')['sindy']
+    res, model = run_experiment(default_config(insite=False, seed=10, treatment_mode='multilabel', joint_model=True),
+                                collection_joint)
+    assert model.joint_coefs.shape == (1, 11)
+    np.testing.assert_allclose(model.joint_coefs[0], log['coefs'], rtol=1e-8)
+    assert model.support_.all()
+    for k in ('encoder_test_rmse_all', 'encoder_test_rmse_orig', 'encoder_test_rmse_last'):
+        np.testing.assert_allclose(res[k], log[k], rtol=1e-8)
+    got = [res[f'decoder_test_rmse_{k}-step'] for k in range(2, 7)]
+    np.testing.assert_allclose(got, log['decoder_test_rmse_2_to_6_step'], rtol=1e-8)
+    assert res['global_equation_string'][:30] == log['global_equation_string'][:30]
+    assert res['global_equation_string'].count('*') == log['global_equation_string'].count('*')

@@ -131,6 +131,35 @@ def test_population_fit_and_metrics_reproduce_reference_log(seed1):
     assert sp.equation_string(coefs).startswith('Treatment 0: x_dot = +-0.0560145608')
 
 
+def test_joint_model_reproduces_reference_ablation_log():
+    """Known-answer test for the joint ("one ODE", 11-term) model: results/ablation/one_ode/...txt:10 of the reference
+    (multilabel treatments; the run's cached dataset is the seed-10 collection)."""
+    log = h.load_json('ref_log_joint_seed10.json')
+    o = h.oracle_collection(h.collection_inputs(log['seed'], 2.0, 1000, 100, 100))
+    means, stds = so.scaling_params(o['train'])
+    dtr, sc = sp.process_data(o['train'], means, stds, treatment_mode='multilabel')
+    coefs, sup, rows = sp.fit_population_joint(dtr, sc)
+    np.testing.assert_allclose(coefs[0], log['sindy']['coefs'], rtol=1e-11)
+    assert sup.all() and rows == log['sindy']['rows']
+    assert sp.equation_string_joint(coefs)[:33] == log['sindy']['global_equation_string'][:33]   # same format, ~1e-14 digits
+    d1, _ = sp.process_data(o['one'], means, stds, treatment_mode='multilabel')
+    orig, all_, last = sp.masked_rmse(sp.predictions_population_joint(d1, sc, coefs), d1, sc)
+    np.testing.assert_allclose([all_, orig, last], [log['sindy']['encoder_test_rmse_all'], log['sindy']['encoder_test_rmse_orig'],
+                                                    log['sindy']['encoder_test_rmse_last']], rtol=1e-11)
+    d2, _ = sp.process_data(o['seq'], means, stds, treatment_mode='multilabel')
+    d2s = sp.process_sequential_test(d2, sc, 5)
+    ps = sp.slice_autoregressive(sp.predictions_population_joint(d2, sc, coefs), d2['sequence_lengths'], 5)
+    np.testing.assert_allclose(sp.n_step_rmses(ps, d2s, sc), log['sindy']['decoder_test_rmse_2_to_6_step'], rtol=1e-11)
+    # the 11-term expression restricted to a treatment is the 4-term ODE the rollout kernels integrate
+    c44 = sp.joint_to_per_treatment(sp.effective_coefs(coefs))
+    codes = (np.squeeze(d1['current_treatments'])[..., 0] + 2 * np.squeeze(d1['current_treatments'])[..., 1]).astype(np.int64)
+    prev = np.squeeze(d1['prev_outputs'] * sc['output_stds'] + sc['output_means'], -1)
+    static = d1['static_features'] * sc['inputs_stds'][1:2] + sc['input_means'][1:2]
+    un = sp.rollout_unscaled(prev[:, 0], codes, static[:, 0], c44)
+    ref = sp.predictions_population_joint(d1, sc, coefs)[..., 0] * sc['output_stds'] + sc['output_means']
+    np.testing.assert_allclose(un, ref, rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (GPU box)")
 def test_oracle_against_live_reference():
     """In the build container the unmodified reference is importable: compare directly."""
