@@ -69,12 +69,16 @@ B200I_API int b200i_device_sms(int *sms_out);
  *      order (:275-279; noise already multiplied by 0.01); assigned_actions (N,T,2) or NULL (:317).
  * out: nine (N,T) arrays + sequence_lengths (N,), keys of the dict at :356-367.  Every element of
  *      every output is written (zeros included) -- buffers need not be pre-zeroed.
- * variant: 0 = auto (TMA-tiled kernel when T is even and all (N,T) pointers are 16 B aligned, else the
- *      generic kernel); 1 = generic thread-per-patient kernel; >=2 = explicit TMA tile shapes
- *      (see csrc/sim_factual.cu), used by the tuning sweep in bench.py.
- * gram_partials: NULL, or a workspace of b200i_gram_workspace_bytes() bytes: the kernel then also
- *      accumulates the population statistics of K4 on the fly (fused theta_gram) and leaves the
- *      reduced result in the first B200I_STATS_DOUBLES doubles of the workspace.
+ * variant: 0 = auto: the lean tiled kernel (csrc/sim_factual_ws.cuh) when T is even and all (N,T) pointers are
+ *      16 B aligned -- one 16-column box per chunk when rows start on 128-byte lines (pitched entry point), two
+ *      otherwise -- else the generic kernel; 1 = generic thread-per-patient kernel (odd T, assigned_actions);
+ *      2-9 = first-generation TMA tile shapes; 10-13, 16, 17 = explicit shapes of the lean kernel; 14, 15 = its
+ *      experimental line-aligned row-class mapping; 20-25 = data-movement-only builds (profiling aid: outputs are
+ *      copies of the draws).  See csrc/sim_factual.cu::dispatch_tma.
+ * gram_workspace: NULL, or a workspace of b200i_gram_workspace_bytes() bytes: the kernel then also
+ *      accumulates the population statistics of K4 on the fly (fused theta_gram; variants 1-9, 10, 12, 16, 17) and
+ *      leaves the reduced result in the first B200I_STATS_DOUBLES doubles of the workspace.  Measured slower than
+ *      the two separate launches on B200 (2.0 vs 1.2 + 0.5 ms at 1M patients), so the pipeline does not use it.
  * ---------------------------------------------------------------------------------------------- */
 B200I_API int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *consts,
                       const double *params,

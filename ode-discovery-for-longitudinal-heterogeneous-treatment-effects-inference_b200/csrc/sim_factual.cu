@@ -1,12 +1,13 @@
 // sim_factual.cu -- K1: simulate_factual (cancer_simulation.py:218-375, loop :282-354) on sm_100a.
 //
-// One thread per patient walks the T columns sequentially.  Two kernels:
-//   * sim_factual_tma<P,TC,SIN,GRAM>: persistent CTAs of P threads; the four (N,T) random-draw arrays
-//     and the nine (N,T) outputs move as TMA boxes {TC columns, P patients} through swizzled shared
-//     memory tiles (conflict-free 16-byte LDS/STS per thread), loads tracked by mbarriers with SIN
-//     stages, stores by bulk async-groups.  HBM traffic = algorithmic bytes (each element touched once).
-//   * sim_factual_generic: the same per-column arithmetic with direct global accesses; covers odd T,
-//     unaligned buffers and the `assigned_actions` fixed policy, and cross-checks the TMA kernel.
+// One thread per patient walks the T columns sequentially.  Kernels, newest first:
+//   * sim_factual_ws (sim_factual_ws.cuh, the default): in-place tiles of {16 columns x 32 patients} per array moved
+//     by TMA, software-pipelined lean column arithmetic (fastmath.cuh), per-tile fallback to the generic column
+//     function; optional row pitch; optional fused population statistics.
+//   * sim_factual_tma<P,TC,SIN,GRAM> (first generation, variants 2-9): persistent CTAs of P threads, separate input
+//     and output tiles, library log/exp/cbrt.  Kept as an independent cross-check of the lean kernel.
+//   * sim_factual_generic: the same per-column arithmetic with direct global accesses; covers odd T, unaligned
+//     buffers, the `assigned_actions` fixed policy and the last n % 128 rows of the row-class mapping.
 // With GRAM the population statistics of theta_gram (K4) are accumulated while simulating.
 #include "fastmath.cuh"
 #include "sim_math.cuh"
