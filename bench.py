@@ -29,7 +29,9 @@ K1_BYTES_PER_PATIENT = lambda T: 4 * T * 8 + 9 * T * 8 + 10 * 8 + 8      # SURVE
 K4_BYTES_PER_PATIENT = lambda T: 3 * T * 8 + 8 + 8                         # 1456 B at T=60
 K1_KERNELS = {"pitched": "sim_factual_ws<32,1,11,0>",   # csrc/sim_factual_ws.cuh, variant 12 (128-byte-aligned rows)
               "dense": "sim_factual_ws<32,2,6,0>"}      # variant 10 (dense 480-byte rows)
-K4_KERNEL = "theta_gram2_kernel"            # csrc/theta_gram.cu
+K1_SIDE_BYTES_PER_PATIENT = lambda T: ((T + 15) // 16) * 16 + 6 * 8    # lean fit: code bytes + six moment sums written
+K4_KERNEL = "theta_gram2_kernel<codes>"     # csrc/theta_gram.cu, fed by the simulator's side outputs (lean fit)
+K4_LEAN_BYTES_PER_PATIENT = lambda T: T * 8 + ((T + 15) // 16) * 16 + 8 + 8 + 6 * 8   # volume row, code bytes, seq_len, type, moments
 
 
 def ncu_traffic(kernel):
@@ -207,7 +209,7 @@ def run_b200(args):
     n, T = args.patients, args.seq_length        # per GPU (weak scaling)
     params, block, static, draws = synth_inputs(n, T, seed=rank)
     pitch = dev.aligned_pitch(T) if args.layout == "pitched" else T
-    pipe = FactualFitPipeline(n, T, variant=args.variant, fused=args.fused, pitch=pitch)
+    pipe = FactualFitPipeline(n, T, variant=args.variant, fused=args.fused, pitch=pitch, lean_fit=bool(args.lean_fit))
     pipe.params.copy_(block.cuda()); pipe.static.copy_(static.cuda())
     for d, s in zip(pipe.draws, draws):
         d.copy_(s)
@@ -234,18 +236,28 @@ def run_b200(args):
     barrier()
     total_ms = e0.elapsed_time(e1)
     # dominant kernel alone (same buffers, inputs > L2): CUDA events around the single launch
+    def launch_k1():
+        if pipe.lean_fit:    # the launch the pipeline uses: simulator + its side outputs for the lean fit
+            dev.sim_factual_side(pipe.params, *pipe.draws, T, pipe.consts, out=pipe.out, codes=pipe.codes,
+                                 patient_moments=pipe.patient_moments, variant=args.variant)
+        else:
+            dev.sim_factual(pipe.params, *pipe.draws, T, pipe.consts, out=pipe.out, variant=args.variant,
+                            fused_static=pipe.static if args.fused else None)
     for a, b in ev:
         a.record()
-        dev.sim_factual(pipe.params, *pipe.draws, T, pipe.consts, out=pipe.out, variant=args.variant,
-                        fused_static=pipe.static if args.fused else None)
+        launch_k1()
         b.record()
     torch.cuda.synchronize()
     k1_ms = [a.elapsed_time(b) for a, b in ev]
     # second kernel of the step (population statistics), same way
     for a, b in ev:
         a.record()
-        dev.theta_gram(pipe.out['cancer_volume'], pipe.out['chemo_application'], pipe.out['radio_application'],
-                       pipe.out['sequence_lengths'], pipe.static, pipe.out['chemo_dosage'], pipe.out['radio_dosage'])
+        if pipe.lean_fit:
+            dev.theta_gram_codes(pipe.out['cancer_volume'], pipe.codes, pipe.out['sequence_lengths'], pipe.static,
+                                 pipe.patient_moments)
+        else:
+            dev.theta_gram(pipe.out['cancer_volume'], pipe.out['chemo_application'], pipe.out['radio_application'],
+                           pipe.out['sequence_lengths'], pipe.static, pipe.out['chemo_dosage'], pipe.out['radio_dosage'])
         b.record()
     torch.cuda.synchronize()
     k4_ms = [a.elapsed_time(b) for a, b in ev]
@@ -303,9 +315,11 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         k1 = float(np.mean(k1_ms))
+        # algorithmic bytes stay the reference I/O contract's; the lean fit's side outputs (112 B/patient) are extra
         achieved = K1_BYTES_PER_PATIENT(T) * n / (k1 / 1e3) / 1e9
         k4 = float(np.mean(k4_ms))
-        achieved4 = K4_BYTES_PER_PATIENT(T) * n / (k4 / 1e3) / 1e9
+        k4_bytes = (K4_LEAN_BYTES_PER_PATIENT(T) if pipe.lean_fit else K4_BYTES_PER_PATIENT(T)) * n
+        achieved4 = k4_bytes / (k4 / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -314,7 +328,7 @@ def run_b200(args):
                            "patient_steps": "executed = sum(sequence_length-1)",
                            "nominal_patient_steps_per_s": n * world * (T - 1) / (ms_per_step / 1e3),
                            "cache": "inputs (1.9 GB draws) and outputs (4.3 GB) per step exceed the 126 MB L2",
-                           "sim_variant": args.variant, "fused_gram": bool(args.fused),
+                           "sim_variant": args.variant, "fused_gram": bool(args.fused), "lean_fit": bool(pipe.lean_fit),
                            "layout": (f"(N,{T}) float64 arrays with a row pitch of {pitch} elements ({pitch * 8}-byte rows: "
                                       f"every row starts on a 128-byte line); dense rows are measured beside it in "
                                       f"roofline.dense_rows") if pitch != T else f"dense (N,{T}) float64 rows",
@@ -331,6 +345,7 @@ def run_b200(args):
                              "peak_source": peak_src, "kernel_ms": k1,
                              "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n,
                              "share_of_step": k1 / ms_per_step,
+                             "side_outputs_bytes_per_launch": K1_SIDE_BYTES_PER_PATIENT(T) * n if pipe.lean_fit else 0,
                              "dense_rows": None if k1_dense_ms is None else {
                                  "kernel_ms": k1_dense_ms,
                                  "achieved": K1_BYTES_PER_PATIENT(T) * n / (k1_dense_ms / 1e3) / 1e9,
@@ -339,10 +354,13 @@ def run_b200(args):
                                  "note": "same arithmetic on the reference's dense 480-byte rows (bit-identical outputs)"}},
                 "roofline_theta_gram": {"bound": "hbm", "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
                                         "unit": "GB/s", "frac": achieved4 / peak, "traffic": ncu_traffic(K4_KERNEL),
-                                        "kernel_ms": k4, "algorithmic_bytes_per_launch": K4_BYTES_PER_PATIENT(T) * n,
-                                        "bytes_read_per_launch": (5 * T * 8 + 16) * n,
-                                        "note": "the launch also produces the scaling moments, which need the two "
-                                                "dosage arrays: it reads 5 arrays, the algorithmic figure counts 3",
+                                        "kernel_ms": k4, "algorithmic_bytes_per_launch": k4_bytes,
+                                        "note": ("lean fit: the simulator kernel also writes one treatment-code byte per "
+                                                 "step and six per-patient moment sums (68 MB + 48 MB per 1M patients, "
+                                                 "inside its own time above); this launch reads the volumes and those "
+                                                 "instead of five (N,T) arrays (SURVEY 8d counts 1456 B/patient for the "
+                                                 "three-array form)") if pipe.lean_fit else
+                                                "standalone theta_gram2: reads 5 arrays (Gram + moments)",
                                         "share_of_step": k4 / ms_per_step},
                 "population_coefs": coefs.tolist()}
         if world == 1 and not args.no_cpu_baseline:
@@ -366,6 +384,8 @@ def main():
     ap.add_argument("--seq-length", type=int, default=60)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--fused", type=int, default=0)
+    ap.add_argument("--lean-fit", type=int, default=1, help="simulator side outputs + theta_gram_codes (default) or "
+                    "the standalone five-array theta_gram")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],
                     help="device-resident (N,T) arrays: rows padded to 128-byte lines, or the reference's dense rows")
     ap.add_argument("--ref-patients", type=int, default=400_000, help="bounded CPU sample")

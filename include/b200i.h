@@ -146,6 +146,26 @@ B200I_API int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, int
  *      treatment code chemo + 2*radio, i.e. what b200i_ode_rollout integrates (pass drop_below < 0 there). */
 B200I_API int b200i_stlsq_joint(const double *stats, double threshold, double alpha, int32_t max_iter, double drop_below,
                      double *coefs11, int32_t *support11, double *coefs44, void *stream);
+/* Lean fit of the device-resident pipeline.  b200i_sim_factual_side = b200i_sim_factual_pitched (tiled kernel, no
+ * assigned_actions, no fused statistics) plus two side outputs of the simulator kernel: codes_out (N, code_pitch)
+ * uint8 = chemo + 2*radio application per step, and patient_moments_out (6, N) = per-patient sums over the active
+ * entries of volume, volume^2, chemo dosage, its square, radio dosage, its square.  b200i_theta_gram_codes finishes
+ * the population statistics from cancer_volume + those two (0.6 instead of 2.4 GB per million patients); same
+ * statistics layout and reduction as b200i_theta_gram_mode.  code_pitch: multiple of 16, >= T rounded up to 16. */
+B200I_API int b200i_sim_factual_side(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
+                      const double *params,
+                      const double *noise, const double *recovery_rvs,
+                      const double *chemo_rvs, const double *radio_rvs,
+                      double *cancer_volume, double *chemo_dosage, double *radio_dosage,
+                      double *chemo_application, double *radio_application,
+                      double *chemo_probabilities, double *radio_probabilities,
+                      double *death_flags, double *recovery_flags, double *sequence_lengths,
+                      uint8_t *codes_out, int64_t code_pitch, double *patient_moments_out,
+                      int32_t variant, void *stream);
+B200I_API int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
+                     const double *cancer_volume, const uint8_t *codes, int64_t code_pitch,
+                     const double *sequence_lengths, const double *static_feature,
+                     const double *patient_moments, void *gram_workspace, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
                      const double *cancer_volume, const double *chemo_application,

@@ -401,11 +401,26 @@ static int launch_ws_rows(int64_t n, int T, const SimC &c, const double *params,
     return check_cuda(cudaGetLastError(), "sim_factual_generic (tail) launch");
 }
 
+struct SideOut {
+    uint8_t *codes;
+    int64_t code_pitch;
+    double *pmom;
+};
+
 template <bool GRAM>
 static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC &c, const double *params,
                         const double *const in[4], double *const out[9], double *seq_len, const double *sf,
-                        StatsWorkspace *ws, cudaStream_t st)
+                        StatsWorkspace *ws, cudaStream_t st, SideOut side = SideOut{nullptr, 0, nullptr})
 {
+    if (side.codes != nullptr) {   // side outputs for the lean fit: the two default shapes only
+        B200I_REQUIRE(!GRAM && (variant == 10 || variant == 12), B200I_E_UNSUPPORTED,
+                      "sim_factual: side outputs need variant 0, 10 or 12 without the fused statistics");
+        if (variant == 10)
+            return launch_ws<32, 2, 6, 0, false, 2>(n, n, T, pitch, c, params, in, out, seq_len, st, nullptr, nullptr,
+                                                    side.codes, side.code_pitch, side.pmom);
+        return launch_ws<32, 1, 11, 0, false, 2>(n, n, T, pitch, c, params, in, out, seq_len, st, nullptr, nullptr,
+                                                 side.codes, side.code_pitch, side.pmom);
+    }
     B200I_REQUIRE(pitch == T || (variant >= 10 && variant <= 13) || variant == 16 || variant == 17 || (variant >= 20 && variant <= 22), B200I_E_UNSUPPORTED,
                   "sim_factual: variant %d needs dense rows (row_pitch %lld, T %d)", variant, (long long)pitch, T);
     switch (variant) {
@@ -419,11 +434,11 @@ static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC
         case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         // generation 6 (sim_factual_ws.cuh): <patients per tile, 16-column boxes per chunk, CTAs per SM, mode>;
         // launch_ws_rows = the experimental line-aligned row-class mapping; 2x = data movement only (profiling aid)
-        case 10: return launch_ws<32, 2, 6, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 10: return launch_ws<32, 2, 6, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
         case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
-        case 12: return launch_ws<32, 1, 11, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 16: return launch_ws<32, 1, 8, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 17: return launch_ws<32, 1, 9, 0, false, GRAM>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 12: return launch_ws<32, 1, 11, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 16: return launch_ws<32, 1, 8, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
+        case 17: return launch_ws<32, 1, 9, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
         case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 14: if (!GRAM) return launch_ws_rows<32, 2, 1, 0>(n, T, c, params, in, out, seq_len, st); break;
         case 15: if (!GRAM) return launch_ws_rows<32, 1, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
@@ -460,6 +475,33 @@ extern "C" int b200i_sim_factual(int64_t n, int32_t T, const b200i_sim_consts *k
                                      sequence_lengths, static_feature, fd_dt, gram_workspace, variant, stream);
 }
 
+static int sim_factual_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k, const double *params,
+                            const double *noise, const double *recovery_rvs, const double *chemo_rvs,
+                            const double *radio_rvs, const double *assigned_actions, double *cancer_volume,
+                            double *chemo_dosage, double *radio_dosage, double *chemo_application,
+                            double *radio_application, double *chemo_probabilities, double *radio_probabilities,
+                            double *death_flags, double *recovery_flags, double *sequence_lengths,
+                            const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
+                            void *stream, SideOut side);
+
+extern "C" int b200i_sim_factual_side(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                      const double *params, const double *noise, const double *recovery_rvs,
+                                      const double *chemo_rvs, const double *radio_rvs, double *cancer_volume,
+                                      double *chemo_dosage, double *radio_dosage, double *chemo_application,
+                                      double *radio_application, double *chemo_probabilities,
+                                      double *radio_probabilities, double *death_flags, double *recovery_flags,
+                                      double *sequence_lengths, uint8_t *codes_out, int64_t code_pitch,
+                                      double *patient_moments_out, int32_t variant, void *stream)
+{
+    B200I_REQUIRE(codes_out && patient_moments_out && code_pitch >= T && code_pitch % 2 == 0, B200I_E_ARG,
+                  "sim_factual_side: codes_out / patient_moments_out missing or code_pitch %lld < T or odd",
+                  (long long)code_pitch);
+    return sim_factual_impl(n, T, row_pitch, k, params, noise, recovery_rvs, chemo_rvs, radio_rvs, nullptr, cancer_volume,
+                            chemo_dosage, radio_dosage, chemo_application, radio_application, chemo_probabilities,
+                            radio_probabilities, death_flags, recovery_flags, sequence_lengths, nullptr, 1.0, nullptr,
+                            variant, stream, SideOut{codes_out, code_pitch, patient_moments_out});
+}
+
 extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
                                          const double *params, const double *noise, const double *recovery_rvs,
                                          const double *chemo_rvs, const double *radio_rvs,
@@ -469,6 +511,21 @@ extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch
                                          double *recovery_flags, double *sequence_lengths,
                                          const double *static_feature, double fd_dt, void *gram_workspace,
                                          int32_t variant, void *stream)
+{
+    return sim_factual_impl(n, T, row_pitch, k, params, noise, recovery_rvs, chemo_rvs, radio_rvs, assigned_actions,
+                            cancer_volume, chemo_dosage, radio_dosage, chemo_application, radio_application,
+                            chemo_probabilities, radio_probabilities, death_flags, recovery_flags, sequence_lengths,
+                            static_feature, fd_dt, gram_workspace, variant, stream, SideOut{nullptr, 0, nullptr});
+}
+
+static int sim_factual_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k, const double *params,
+                            const double *noise, const double *recovery_rvs, const double *chemo_rvs,
+                            const double *radio_rvs, const double *assigned_actions, double *cancer_volume,
+                            double *chemo_dosage, double *radio_dosage, double *chemo_application,
+                            double *radio_application, double *chemo_probabilities, double *radio_probabilities,
+                            double *death_flags, double *recovery_flags, double *sequence_lengths,
+                            const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
+                            void *stream, SideOut side)
 {
     const int64_t pitch = row_pitch;
     B200I_REQUIRE(pitch == T || (pitch > T && pitch % 2 == 0), B200I_E_ARG, "sim_factual: row_pitch %lld (T = %d) must be even and >= T",
@@ -506,8 +563,11 @@ extern "C" int b200i_sim_factual_pitched(int64_t n, int32_t T, int64_t row_pitch
                       "sim_factual: assigned_actions is only handled by the generic kernel (variant 1)");
         B200I_REQUIRE(tma_ok, B200I_E_ALIGN, "sim_factual: TMA variant needs even T and 16-byte aligned arrays");
         return gram ? dispatch_tma<true>(variant, n, T, pitch, c, params, in, out, sequence_lengths, static_feature, ws, st)
-                    : dispatch_tma<false>(variant, n, T, pitch, c, params, in, out, sequence_lengths, static_feature, ws, st);
+                    : dispatch_tma<false>(variant, n, T, pitch, c, params, in, out, sequence_lengths, static_feature, ws, st,
+                                          side);
     }
+    B200I_REQUIRE(side.codes == nullptr, B200I_E_UNSUPPORTED,
+                  "sim_factual: side outputs need the tiled kernel (even T, 16-byte aligned arrays)");
     FactualPtrs io;
     io.noise = noise; io.rec = recovery_rvs; io.chemo_rvs = chemo_rvs; io.radio_rvs = radio_rvs;
     io.assigned = assigned_actions;

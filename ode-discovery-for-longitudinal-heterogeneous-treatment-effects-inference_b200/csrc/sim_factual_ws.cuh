@@ -44,7 +44,7 @@ struct WsCfg {
     static constexpr int BOX_COLS = 16, TCH = BOX_COLS * NB;          // columns per chunk
     static constexpr int TILE_BYTES = P * 128;                        // one box of one array
     static constexpr int STAGE_BYTES = NB * 4 * TILE_BYTES;           // [NB][4][TILE]
-    static constexpr int FLAG_PITCH = TCH + 4;                        // byte c+2 = column c; byte 1 = dummy
+    static constexpr int FLAG_PITCH = TCH + 4;                        // byte c+4 = column c (4-byte aligned); byte 3 = dummy
     static constexpr int FLAG_BYTES = P * FLAG_PITCH;
     static constexpr int DUMMY_BYTES = P * 16;                        // per-thread scratch slot
     static constexpr int LUT_BYTES = 5 * 4 * 16;                      // flag expansion table [array][2 bits] -> double2
@@ -207,7 +207,7 @@ __device__ __noinline__ void ws_slow_chunk(uint8_t *stage, uint8_t *flags_s, int
         Column o;
         factual_column<GRAM, false>(t_first + cidx, T, c, st->p, st->s, *pn, *pu, *pc, *pr, nullptr, o, pg, mom);
         *pn = o.V; *pu = o.C; *pc = o.pc; *pr = o.pr;
-        flags_s[cidx + 2] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
+        flags_s[cidx + 4] = (uint8_t)((o.ca != 0.0 ? 1u : 0u) | (o.ra != 0.0 ? 2u : 0u) | (o.death != 0.0 ? 4u : 0u) |
                                       (o.recov != 0.0 ? 8u : 0u));
     }
 }
@@ -252,7 +252,10 @@ __device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPack &m, int,
 }
 __device__ __forceinline__ const CUtensorMap *ws_out_map(const TmapPackSkew &m, int j, int o) { return &m.out[j][o]; }
 
-template <int P, int NB, int MINB, int MODE, bool SKEW, bool GRAM>
+// STATS: 0 none; 1 fused population statistics (GRAM); 2 side outputs for the lean fit (SIDE): one treatment-code
+// byte per (patient, column) and six per-patient moment sums, from which theta_gram_codes finishes the statistics
+// reading 0.6 instead of 2.4 GB per million patients.
+template <int P, int NB, int MINB, int MODE, bool SKEW, int STATS>
 __global__ void __launch_bounds__(SKEW ? 128 : P, MINB)
 sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opts, int64_t n, int64_t pstride, int T,
                int64_t pitch, SimC c,
@@ -260,9 +263,10 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                double *__restrict__ out_D, double *__restrict__ out_death, double *__restrict__ out_recov,
                double *__restrict__ seq_len_out, double *__restrict__ out_V, double *__restrict__ out_C,
                double *__restrict__ out_pc, double *__restrict__ out_pr, const double *__restrict__ static_feature,
-               StatsWorkspace *ws)
+               StatsWorkspace *ws, uint8_t *__restrict__ codes_out, int64_t code_pitch, double *__restrict__ pmom_out)
 {
-    static_assert(!GRAM || (!SKEW && MODE == 0), "fused statistics: plain tiles, simulator mode");
+    constexpr bool GRAM = STATS == 1, SIDE = STATS == 2;
+    static_assert(STATS == 0 || (!SKEW && MODE == 0), "statistics: plain tiles, simulator mode");
     __shared__ double block_acc[GRAM ? (P / 32) : 1][STATS_PAD];
     __shared__ unsigned int s_is_last;
     using Cfg = WsCfg<P, NB>;
@@ -424,9 +428,9 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
             if (tile_slow) {
                 slow.p = load_patient(params, pstride, pi);
                 state_init(slow.s, exists);
-                if (GRAM) { slow.pg.clear(); slow.mom.clear(); }
+                if (GRAM || SIDE) { slow.pg.clear(); slow.mom.clear(); }
             }
-            if (GRAM) {
+            if (GRAM || SIDE) {
                 pg.clear(); mom.clear();
                 gVm1 = gVm2 = 0.0; gcm2 = 0u; g_nra = 0u; g_tlast = -4;
             }
@@ -441,7 +445,7 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
             nb = nb > NB ? NB : nb;
 
             if (MODE == 0 && tile_slow) {
-                ws_slow_chunk<P, GRAM>(tiles, flags_s, rid, t_first, nb * 16, T, c, &slow);
+                ws_slow_chunk<P, GRAM || SIDE>(tiles, flags_s, rid, t_first, nb * 16, T, c, &slow);
             } else {
                 // first body of the chunk recomputes the previous column's treatment; its outputs go to scratch
                 double *prevC = dummy, *prevP = dummy + 1;
@@ -497,6 +501,8 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                                 ws_gram_sample(pg, t0 + 1 <= te, t0 + 1 == te || c3 != c2, oV[1], oV[2], c2, c.fd_dt,
                                                inv_dt);
                                 gVm2 = oV[2]; gVm1 = oV[3]; gcm2 = c3; g_tlast = t0;
+                            }
+                            if (GRAM || SIDE) {
                                 // moments of get_scaling_params: inactive entries are zero, so plain sums do
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -514,7 +520,7 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                         pb[1]->x = oC[3];
                         pb[3]->x = oP[3];
                         prevC = &pb[1]->y; prevP = &pb[3]->y;
-                        uint8_t *fd = flags_s + 1 + lb + h * 4;    // byte of column t0 - 1 (byte 1 = dummy)
+                        uint8_t *fd = flags_s + 3 + lb + h * 4;    // byte of column t0 - 1 (byte 3 = dummy)
                         fd[0] = (uint8_t)oF[0]; fd[1] = (uint8_t)oF[1]; fd[2] = (uint8_t)oF[2]; fd[3] = (uint8_t)oF[3];
                         t_done = t0 + 3;
                     }
@@ -543,7 +549,7 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                         f = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
                     }
                     *prevC = C1; *prevP = pr;
-                    flags_s[2 + (t_done - t_first)] = (uint8_t)f;
+                    flags_s[4 + (t_done - t_first)] = (uint8_t)f;
                 }
             }
             fence_proxy_async_smem();
@@ -597,6 +603,18 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
             const int t_first = ch * TCH - it.shift;
             int nb = it.nboxes - ch * NB;
             nb = nb > NB ? NB : nb;
+            if (SIDE && exists) {
+                // treatment codes chemo + 2*radio of the chunk's columns: the thread's own flag bytes, 16 per store
+                // (code_pitch is a multiple of 16 that covers T rounded up, so whole boxes fit)
+                const uint32_t *fw = reinterpret_cast<const uint32_t *>(flags_s + 4);
+                uint8_t *crow = codes_out + patient * code_pitch + t_first;
+                for (int b = 0; b < nb; ++b) {
+                    uint4 v;
+                    v.x = fw[4 * b + 0] & 0x03030303u; v.y = fw[4 * b + 1] & 0x03030303u;
+                    v.z = fw[4 * b + 2] & 0x03030303u; v.w = fw[4 * b + 3] & 0x03030303u;
+                    *reinterpret_cast<uint4 *>(crow + 16 * b) = v;
+                }
+            }
             // expand the packed flag bytes: item = (row, column pair); consecutive lanes write consecutive 16 bytes.
             // Each array's double2 comes from a 4-entry table indexed by its bit of the two columns.
             {
@@ -611,7 +629,7 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
                     const int64_t tile_ofs = row0 * pitch + col;
                     double *b_ca = out_ca + tile_ofs, *b_ra = out_ra + tile_ofs, *b_D = out_D + tile_ofs,
                            *b_de = out_death + tile_ofs, *b_re = out_recov + tile_ofs;
-                    const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 2;
+                    const uint8_t *fp = flag_buf + r_first * Cfg::FLAG_PITCH + cp * 2 + 4;
                     int ofs = r_first * rmul * (int)pitch;
 #pragma unroll 4
                     for (int row = r_first; row < rows_valid;
@@ -644,6 +662,14 @@ sim_factual_ws(const __grid_constant__ typename WsMaps<SKEW>::type maps, int opt
           }
         }
         if (MODE == 0 && exists) seq_len_out[patient] = (double)((tile_slow ? slow.s.t_end : s.t_end) + 1);
+        if (SIDE && exists) {
+            const Moments &mm = tile_slow ? slow.mom : mom;
+            const double sd = tile_slow ? slow.mom.sd : c.radio_amt * (double)g_nra;
+            const double sdd = tile_slow ? slow.mom.sdd : c.radio_amt * c.radio_amt * (double)g_nra;
+            pmom_out[0 * pstride + patient] = mm.sv;  pmom_out[1 * pstride + patient] = mm.svv;
+            pmom_out[2 * pstride + patient] = mm.sc;  pmom_out[3 * pstride + patient] = mm.scc;
+            pmom_out[4 * pstride + patient] = sd;     pmom_out[5 * pstride + patient] = sdd;
+        }
         if (GRAM) {
             const double u = exists ? __ldg(static_feature + patient) : 0.0;
             const int lane = tid & 31, wrp = tid >> 5;
@@ -703,10 +729,11 @@ static int ws_encode(TmapPackSkew &pack, int64_t n, int T, int64_t pitch, int nc
     return 0;
 }
 
-template <int P, int NB, int MINB, int MODE, bool SKEW, bool GRAM = false>
+template <int P, int NB, int MINB, int MODE, bool SKEW, int STATS = 0>
 static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const SimC &c, const double *params,
                      const double *const in[4], double *const out[9], double *seq_len, cudaStream_t st,
-                     const double *static_feature = nullptr, StatsWorkspace *ws = nullptr)
+                     const double *static_feature = nullptr, StatsWorkspace *ws = nullptr, uint8_t *codes_out = nullptr,
+                     int64_t code_pitch = 0, double *pmom_out = nullptr)
 {
     using Cfg = WsCfg<P, NB>;
     if (n <= 0) return 0;
@@ -715,7 +742,8 @@ static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const Sim
         int rc = ws_encode(pack, n, T, pitch, SKEW ? 4 : P, in, out);
         if (rc) return rc;
     }
-    auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW, GRAM>;
+    constexpr bool GRAM = STATS == 1;
+    auto kern = sim_factual_ws<P, NB, MINB, MODE, SKEW, STATS>;
     constexpr int SMEM = SKEW ? Cfg::SMEM_BYTES_4 : Cfg::SMEM_BYTES;
     constexpr int NT = SKEW ? 128 : P;
     B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -729,7 +757,8 @@ static int launch_ws(int64_t n, int64_t pstride, int T, int64_t pitch, const Sim
     static const int opts = ws_env_opts();
     // out order: V C D ca ra pc pr death recov
     kern<<<(unsigned)grid, NT, SMEM, st>>>(pack, opts, n, pstride, T, pitch, c, params, out[3], out[4], out[2], out[7],
-                                                     out[8], seq_len, out[0], out[1], out[5], out[6], static_feature, ws);
+                                                     out[8], seq_len, out[0], out[1], out[5], out[6], static_feature, ws, codes_out,
+                                                     code_pitch, pmom_out);
     return check_cuda(cudaGetLastError(), "sim_factual_ws launch");
 }
 

@@ -141,12 +141,16 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
 // ------------------------------------------------------------------------------------------------
 constexpr int G2_WARPS = 4;
 
-template <int MAXT>
+// CODES: the lean fit of the device pipeline -- treatment codes (one byte per step) and six per-patient moment sums
+// written by the simulator kernel (b200i_sim_factual_side) replace the two application and two dosage arrays:
+// 0.6 instead of 2.4 GB per million patients.
+template <int MAXT, bool CODES>
 __global__ void __launch_bounds__(G2_WARPS * 32, 2)
 theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double inv_dt, const double *__restrict__ vol,
                    const double *__restrict__ chemo, const double *__restrict__ radio,
                    const double *__restrict__ seq_len, const double *__restrict__ static_feature,
-                   const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws)
+                   const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws,
+                   const uint8_t *__restrict__ codes, int64_t code_pitch, const double *__restrict__ pmom)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t bars[G2_WARPS];
@@ -183,6 +187,26 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
         } else {
             mbar_arrive(&bars[warp]);
         }
+        if (CODES) {
+            // code bytes: 16 per 16-byte load, item = (row, 16-byte unit); transposed into the [T][33] table
+            const int units = (T + 15) >> 4;
+            for (int e = lane; e < rows * units; e += 32) {
+                const int j = e / units, uq = e - j * units;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(codes + (first + j) * code_pitch) + uq);
+                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int col = uq * 16 + q;
+                    if (col < T) s_code[col * 33 + j] = (uint8_t)((wv[q >> 2] >> (8 * (q & 3))) & 3u);
+                }
+            }
+            if (lane < rows) {   // the simulator's per-patient sums over the active entries
+                const int64_t pidx = first + lane;
+                mv += __ldg(pmom + 0 * n + pidx);  mvv += __ldg(pmom + 1 * n + pidx);
+                mc += __ldg(pmom + 2 * n + pidx);  mcc += __ldg(pmom + 3 * n + pidx);
+                md += __ldg(pmom + 4 * n + pidx);  mdd += __ldg(pmom + 5 * n + pidx);
+            }
+        }
         // the four other arrays, two columns per lane and row
         const double2 *gc2 = reinterpret_cast<const double2 *>(chemo + first * rp);
         const double2 *gr2 = reinterpret_cast<const double2 *>(radio + first * rp);
@@ -191,7 +215,7 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
         const int64_t rp2 = rp / 2;
         int L_lane = (lane < rows) ? (int)__ldg(seq_len + first + lane) : 0;
         L_lane = L_lane > T ? T : L_lane;
-        for (int cb = 0; cb < half; cb += 32) {
+        for (int cb = 0; !CODES && cb < half; cb += 32) {
             const bool active = cb + lane < half;          // every lane iterates (warp shuffles below)
             const int c = active ? cb + lane : 0;
             // batches of 8 rows: all 32 loads of a batch are issued before the first dependent store
@@ -269,7 +293,7 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
                     }
                     xd_prev = xdot;
                 }
-                for (int k = 0; k < Ls; ++k) { mv += xr[k]; mvv += xr[k] * xr[k]; }
+                if (!CODES) for (int k = 0; k < Ls; ++k) { mv += xr[k]; mvv += xr[k] * xr[k]; }
             }
             double2 cur = *reinterpret_cast<const double2 *>(row);
             int a0 = s_code[lane];
@@ -278,15 +302,15 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
                 const int a1 = s_code[(k + 1) * 33 + lane];
                 const int a2 = (k + 2 < T) ? s_code[(k + 2) * 33 + lane] : 0;
                 sample(cur.x, cur.y, a0, k == L - 1 || a1 != a0);
-                mv += cur.x; mvv += cur.x * cur.x;
+                if (!CODES) { mv += cur.x; mvv += cur.x * cur.x; }
                 if (k + 1 < L) {
                     sample(cur.y, nxt.x, a1, k + 1 == L - 1 || a2 != a1);
-                    mv += cur.y; mvv += cur.y * cur.y;
+                    if (!CODES) { mv += cur.y; mvv += cur.y * cur.y; }
                 }
                 a0 = a2;
                 cur = nxt;
             }
-            if (mode == 0 && Ls > L) {   // sequence_length == T: the last entry is active but starts no sample
+            if (!CODES && mode == 0 && Ls > L) {   // sequence_length == T: the last entry is active but starts no sample
                 const double x = *reinterpret_cast<const double *>(row + (size_t)L * 8);
                 mv += x; mvv += x * x;
             }
@@ -392,6 +416,42 @@ extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch,
                                  sequence_lengths, static_feature, chemo_dosage, radio_dosage, gram_workspace, stream);
 }
 
+extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
+                                      const double *cancer_volume, const uint8_t *codes, int64_t code_pitch,
+                                      const double *sequence_lengths, const double *static_feature,
+                                      const double *patient_moments, void *gram_workspace, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && cancer_volume && codes && sequence_lengths && static_feature && patient_moments &&
+                      gram_workspace,
+                  B200I_E_ARG, "theta_gram_codes: NULL argument or negative n");
+    B200I_REQUIRE(T >= 2 && T <= 256 && T % 2 == 0 && fd_dt > 0 && (mode == 0 || mode == 1), B200I_E_UNSUPPORTED,
+                  "theta_gram_codes: T=%d (even, <= 256), fd_dt > 0, mode 0/1", T);
+    B200I_REQUIRE(row_pitch >= T && (row_pitch == T || row_pitch % 2 == 0) && code_pitch >= ((T + 15) / 16) * 16 &&
+                      code_pitch % 16 == 0 && aligned16(cancer_volume) && aligned16(codes),
+                  B200I_E_ARG, "theta_gram_codes: row_pitch %lld / code_pitch %lld (multiple of 16, >= T rounded up)",
+                  (long long)row_pitch, (long long)code_pitch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
+    B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
+    if (n == 0) return 0;
+    const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
+    const size_t smem2 = warp_bytes * G2_WARPS;
+    auto k2 = theta_gram2_kernel<256, true>;
+    B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int per_sm2 = 0;
+    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, G2_WARPS * 32, smem2));
+    B200I_REQUIRE(per_sm2 >= 1, B200I_E_UNSUPPORTED, "theta_gram_codes: T=%d does not fit in shared memory", T);
+    const int64_t ntiles2 = (n + 31) / 32;
+    int64_t grid2 = (int64_t)num_sms() * per_sm2;
+    const int64_t need = (ntiles2 + G2_WARPS - 1) / G2_WARPS;
+    if (grid2 > need) grid2 = need;
+    if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
+    k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, mode, fd_dt, 1.0 / fd_dt, cancer_volume, nullptr,
+                                                      nullptr, sequence_lengths, static_feature, nullptr, nullptr, ws,
+                                                      codes, code_pitch, patient_moments);
+    return check_cuda(cudaGetLastError(), "theta_gram_codes launch");
+}
+
 extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
                                      const double *cancer_volume, const double *chemo_application,
                                      const double *radio_application, const double *sequence_lengths,
@@ -419,7 +479,7 @@ extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, in
         if (v2) {
             const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
             const size_t smem2 = warp_bytes * G2_WARPS;
-            auto k2 = theta_gram2_kernel<256>;
+            auto k2 = theta_gram2_kernel<256, false>;
             B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             int per_sm2 = 0;
             B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, G2_WARPS * 32, smem2));
@@ -431,7 +491,7 @@ extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, in
                 if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
                 k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, mode, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
                                                                   radio_application, sequence_lengths, static_feature,
-                                                                  chemo_dosage, radio_dosage, ws);
+                                                                  chemo_dosage, radio_dosage, ws, nullptr, 0, nullptr);
                 return check_cuda(cudaGetLastError(), "theta_gram2 launch");
             }
         }

@@ -134,6 +134,44 @@ def sim_factual(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=Non
     return out, (ws[:STATS_DOUBLES] if ws is not None else None)
 
 
+def sim_factual_side(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, consts=None, out=None, codes=None,
+                     patient_moments=None, variant=0):
+    """K1 with the side outputs of the lean fit: returns (out dict, codes (N, code_pitch) uint8, moments (6, N))."""
+    lib = _native.load()
+    n = params_dev.shape[1]
+    consts = consts or sim_consts()
+    pitch = row_pitch(noise, recovery, chemo_rvs, radio_rvs) if n > 1 else T
+    if out is None:
+        out = {k: alloc_rows(n, T, pitch) for k in FACTUAL_OUT_KEYS}
+        out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
+    elif n > 1:
+        pitch = row_pitch(noise, recovery, chemo_rvs, radio_rvs, *[out[k] for k in FACTUAL_OUT_KEYS])
+    if codes is None:
+        codes = torch.zeros((n, ((T + 15) // 16) * 16), dtype=torch.uint8, device='cuda')
+    if patient_moments is None:
+        patient_moments = torch.empty((6, n), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_sim_factual_side(n, T, pitch, ctypes.byref(consts), _ptr(params_dev), _ptr_rows(noise),
+                                    _ptr_rows(recovery), _ptr_rows(chemo_rvs), _ptr_rows(radio_rvs),
+                                    *[_ptr_rows(out[k]) for k in FACTUAL_OUT_KEYS], _ptr(out['sequence_lengths']),
+                                    _ptr(codes), int(codes.shape[1]), _ptr(patient_moments), int(variant), _stream())
+    _native.check(rc, "b200i_sim_factual_side")
+    return out, codes, patient_moments
+
+
+def theta_gram_codes(cancer_volume, codes, sequence_lengths, static_feature, patient_moments, fd_dt=STANDARD_DT,
+                     tag="default", joint=False):
+    """K4 from the simulator's side outputs (see sim_factual_side).  Returns the (68,) packed statistics."""
+    lib = _native.load()
+    n, T = cancer_volume.shape
+    ws = gram_workspace(tag)
+    pitch = row_pitch(cancer_volume) if n > 1 else T
+    rc = lib.b200i_theta_gram_codes(n, T, pitch, 1 if joint else 0, float(fd_dt), _ptr_rows(cancer_volume), _ptr(codes),
+                                    int(codes.shape[1]), _ptr(sequence_lengths), _ptr(static_feature),
+                                    _ptr(patient_moments), _ptr(ws), _stream())
+    _native.check(rc, "b200i_theta_gram_codes")
+    return ws[:STATS_DOUBLES]
+
+
 def theta_gram(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature,
                chemo_dosage=None, radio_dosage=None, fd_dt=STANDARD_DT, tag="default", joint=False):
     """K4.  Returns the (68,) packed statistics (view into the workspace).  joint: the joint model's reduction

@@ -23,11 +23,15 @@ def _rows(src):
 draws = [_rows(d) for d in draws]
 out = {k: dev.alloc_rows(n, T, pitch) for k in dev.FACTUAL_OUT_KEYS}
 out['sequence_lengths'] = torch.empty((n,), dtype=torch.float64, device='cuda')
+_codes = torch.zeros((n, 64), dtype=torch.uint8, device='cuda'); _pm = torch.empty((6, n), dtype=torch.float64, device='cuda')
 ts = []
 for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    dev.sim_factual(block, *draws, T, out=out, variant=variant, fused_static=static if fused else None)
+    if os.environ.get('SIDE'):
+        dev.sim_factual_side(block, *draws, T, out=out, codes=_codes, patient_moments=_pm, variant=variant)
+    else:
+        dev.sim_factual(block, *draws, T, out=out, variant=variant, fused_static=static if fused else None)
     e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print("ms per launch:", ["%.3f" % t for t in ts], "mean seq len", out['sequence_lengths'].mean().item())

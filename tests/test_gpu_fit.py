@@ -67,6 +67,36 @@ def test_theta_gram_matches_oracle_design_matrices(dev, seed1):
     assert u['patients'] == 1000 and u['active'] == o['train']['sequence_lengths'].sum()
 
 
+@pytest.mark.parametrize("pitch", [60, 64])
+def test_lean_fit_side_outputs_reproduce_the_statistics(dev, pitch):
+    """b200i_sim_factual_side + b200i_theta_gram_codes (treatment-code bytes and per-patient moment sums written by
+    the simulator kernel) vs b200i_sim_factual + b200i_theta_gram: same outputs, same Gram, moments to rounding."""
+    import torch
+    params, draws = h.random_cohort(5000, seed=78)
+    dmax = 12.999999999999998
+    params['radio_sigmoid_betas'][900:940] = 6.0 / dmax          # some tiles take the generic fallback
+    pd_ = dev.to_device(dev.pack_params(params))
+    static = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64))
+    ins = []
+    for k in ('noise', 'recovery', 'chemo', 'radio'):
+        t = dev.alloc_rows(5000, 60, pitch)
+        t.copy_(torch.from_numpy(draws[k]).cuda())
+        ins.append(t)
+    out_a, _ = dev.sim_factual(pd_, *ins, 60)
+    ref = dev.theta_gram(out_a['cancer_volume'], out_a['chemo_application'], out_a['radio_application'],
+                         out_a['sequence_lengths'], static, out_a['chemo_dosage'], out_a['radio_dosage'], tag="ta").clone()
+    out_b, codes, pm = dev.sim_factual_side(pd_, *ins, 60)
+    lean = dev.theta_gram_codes(out_b['cancer_volume'], codes, out_b['sequence_lengths'], static, pm, tag="tb").clone()
+    torch.cuda.synchronize()
+    for k in out_a:
+        assert torch.equal(out_a[k], out_b[k]), k
+    want = (out_a['chemo_application'] + 2 * out_a['radio_application']).to(torch.uint8)
+    assert torch.equal(codes[:, :60], want)
+    a, b = ref.cpu().numpy(), lean.cpu().numpy()
+    assert np.array_equal(a[:60], b[:60])                        # Gram / right-hand sides / counts: same walk
+    np.testing.assert_allclose(b[60:], a[60:], rtol=1e-12)       # moments: different summation order
+
+
 def test_theta_gram_pitched_rows_bit_identical_to_dense(dev, seed1):
     """b200i_theta_gram_pitched: rows padded to 128-byte lines give the same statistics bit for bit."""
     import torch
