@@ -347,6 +347,7 @@ sim_factual_tma(const __grid_constant__ TmapPack maps, int64_t n, int T, SimC c,
 
 }  // namespace b200i
 #include "sim_factual_ws.cuh"
+#include "sim_factual_rng.cuh"
 namespace b200i {
 
 // ------------------------------------------------------------------------------------------------
@@ -581,4 +582,73 @@ static int sim_factual_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i
     else
         sim_factual_generic<false><<<(unsigned)grid, 128, 0, st>>>(n, n, T, c, params, io, static_feature, ws);
     return check_cuda(cudaGetLastError(), "sim_factual_generic launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1L: device-generated draws (sim_factual_rng.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200i_philox_draws(int64_t n, int32_t T, int64_t row_pitch, uint64_t seed, int64_t patient_base,
+                                  double *noise, double *recovery_rvs, double *chemo_rvs, double *radio_rvs,
+                                  void *stream)
+{
+    B200I_REQUIRE(n >= 0 && patient_base >= 0, B200I_E_ARG, "philox_draws: negative n or patient_base");
+    if (n == 0) return 0;
+    B200I_REQUIRE(noise && recovery_rvs && chemo_rvs && radio_rvs, B200I_E_ARG, "philox_draws: NULL argument");
+    B200I_REQUIRE(T >= 2 && T % 2 == 0 && row_pitch >= T && row_pitch % 2 == 0, B200I_E_UNSUPPORTED,
+                  "philox_draws: T=%d and row_pitch=%lld must be even, row_pitch >= T", T, (long long)row_pitch);
+    B200I_REQUIRE(aligned16(noise) && aligned16(recovery_rvs) && aligned16(chemo_rvs) && aligned16(radio_rvs),
+                  B200I_E_ALIGN, "philox_draws: arrays must be 16-byte aligned");
+    const int64_t total = n * (T / 2);
+    int64_t grid = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    philox_draws_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, T, row_pitch, (uint32_t)seed, (uint32_t)(seed >> 32), patient_base, noise, recovery_rvs, chemo_rvs, radio_rvs);
+    return check_cuda(cudaGetLastError(), "philox_draws launch");
+}
+
+extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                     const double *params, uint64_t seed, int64_t patient_base, double *cancer_volume,
+                                     uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
+                                     double *patient_moments_out, const double *static_feature, double fd_dt,
+                                     void *gram_workspace, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && patient_base >= 0, B200I_E_ARG, "sim_factual_rng: negative n or patient_base");
+    if (n == 0) {
+        if (gram_workspace)
+            B200I_CUDA(cudaMemsetAsync(gram_workspace, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32,
+                                       static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    B200I_REQUIRE(k && params && cancer_volume && sequence_lengths, B200I_E_ARG, "sim_factual_rng: NULL argument");
+    B200I_REQUIRE(T >= 4 && T <= 1024 && T % 2 == 0, B200I_E_UNSUPPORTED, "sim_factual_rng: seq_length %d (even, 4..1024)", T);
+    B200I_REQUIRE(row_pitch >= T && row_pitch % 2 == 0 && aligned16(cancer_volume), B200I_E_ALIGN,
+                  "sim_factual_rng: row_pitch %lld must be even and >= T, cancer_volume 16-byte aligned", (long long)row_pitch);
+    B200I_REQUIRE(codes_out == nullptr || (code_pitch >= ((T + 15) / 16) * 16 && code_pitch % 16 == 0 && aligned16(codes_out)),
+                  B200I_E_ARG, "sim_factual_rng: code_pitch %lld (multiple of 16, >= T rounded up to 16)", (long long)code_pitch);
+    B200I_REQUIRE(k->lag == 0 && k->window_size >= 1 && k->window_size <= 15, B200I_E_UNSUPPORTED,
+                  "sim_factual_rng: lag=%d window_size=%d (lag 0, window 1..15)", k->lag, k->window_size);
+    B200I_REQUIRE(n < (int64_t)1 << 31, B200I_E_UNSUPPORTED, "sim_factual_rng: n=%lld >= 2^31", (long long)n);
+    const bool gram = gram_workspace != nullptr;
+    B200I_REQUIRE(!gram || (static_feature && fd_dt > 0), B200I_E_ARG,
+                  "sim_factual_rng: fused statistics need static_feature and fd_dt > 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SimC c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay,
+           fd_dt > 0 ? fd_dt : 1.0, 1.0 / k->sphere_coef, k->window_size};
+    CUtensorMap vmap;
+    {
+        int rc = encode_tmap_2d_pitched_f64(&vmap, cancer_volume, (uint64_t)n, (uint64_t)T, (uint64_t)row_pitch * 8, 32, 16);
+        if (rc) return rc;
+    }
+    StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
+    if (gram) {
+        B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
+        return launch_rng<1, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
+                                       nullptr, static_feature, ws, st);
+    }
+    if (patient_moments_out)
+        return launch_rng<2, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
+                                       patient_moments_out, nullptr, nullptr, st);
+    return launch_rng<0, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
+                                   nullptr, nullptr, nullptr, st);
 }

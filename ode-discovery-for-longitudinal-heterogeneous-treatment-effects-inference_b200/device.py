@@ -158,6 +158,46 @@ def sim_factual_side(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, const
     return out, codes, patient_moments
 
 
+def philox_draws(n, T, seed, patient_base=0, pitch=None):
+    """The device generator's draws as the four (N,T) arrays of the reference contract (noise already x 0.01):
+    returns [noise, recovery, chemo, radio].  b200i_sim_factual on these reproduces sim_factual_rng bit for bit."""
+    lib = _native.load()
+    pitch = T if pitch is None else int(pitch)
+    arrs = [alloc_rows(n, T, pitch) for _ in range(4)]
+    rc = lib.b200i_philox_draws(n, T, pitch, int(seed), int(patient_base), *[_ptr_rows(a) for a in arrs], _stream())
+    _native.check(rc, "b200i_philox_draws")
+    return arrs
+
+
+def sim_factual_rng(params_dev, T, seed, patient_base=0, consts=None, volume=None, codes=None, sequence_lengths=None,
+                    patient_moments=None, fused_static=None, fd_dt=STANDARD_DT, pitch=None, moments=True, tag="default"):
+    """K1L: simulate_factual with device-generated draws (Philox4x32-10 counted by global patient index).
+
+    Returns (volume (N,T) [row pitch `pitch`], codes (N, code_pitch) uint8 = chemo + 2*radio application,
+    sequence_lengths (N,), moments (6,N) or None, stats (68,) or None).  fused_static: (N,) static feature ->
+    the population statistics of theta_gram are accumulated inside the kernel (moments are then not written)."""
+    lib = _native.load()
+    n = params_dev.shape[1]
+    consts = consts or sim_consts()
+    if volume is None:
+        volume = alloc_rows(n, T, aligned_pitch(T) if pitch is None else pitch)
+    vp = row_pitch(volume) if n > 1 else T
+    if codes is None:
+        codes = torch.empty((n, ((T + 15) // 16) * 16), dtype=torch.uint8, device='cuda')
+    if sequence_lengths is None:
+        sequence_lengths = torch.empty((n,), dtype=torch.float64, device='cuda')
+    ws = gram_workspace(tag) if fused_static is not None else None
+    if ws is None and moments and patient_moments is None:
+        patient_moments = torch.empty((6, n), dtype=torch.float64, device='cuda')
+    if ws is not None:
+        patient_moments = None
+    rc = lib.b200i_sim_factual_rng(n, T, vp, ctypes.byref(consts), _ptr(params_dev), int(seed), int(patient_base),
+                                   _ptr_rows(volume), _ptr(codes), int(codes.shape[1]), _ptr(sequence_lengths),
+                                   _ptr(patient_moments), _ptr(fused_static), float(fd_dt), _ptr(ws), _stream())
+    _native.check(rc, "b200i_sim_factual_rng")
+    return volume, codes, sequence_lengths, patient_moments, (ws[:STATS_DOUBLES] if ws is not None else None)
+
+
 def theta_gram_codes(cancer_volume, codes, sequence_lengths, static_feature, patient_moments, fd_dt=STANDARD_DT,
                      tag="default", joint=False):
     """K4 from the simulator's side outputs (see sim_factual_side).  Returns the (68,) packed statistics."""

@@ -1,0 +1,117 @@
+"""K1L (device-generated draws): the Philox generator vs its numpy restatement, and the fused simulator vs the
+pre-drawn-array contract of K1 on the same draws.  All calls go through the C ABI (b200_insite.device)."""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from b200_insite import device as dev
+    dev.require_cuda()
+    return dev
+
+
+def test_philox_draws_match_numpy_restatement(dev):
+    """Uniforms bit-exact; Box-Muller noise to 1e-12 relative (1e-16 absolute near the zeros of cos/sin) (libdevice vs libm log / sincos, <= 2 ulp each)."""
+    import torch
+    from oracle import philox_np as ph
+    for n, T, seed, base, pitch in ((257, 60, 7, 0, 60), (100, 62, (5 << 32) + 11, (1 << 33) + 5, 64)):
+        got = dev.philox_draws(n, T, seed, patient_base=base, pitch=pitch)
+        torch.cuda.synchronize()
+        want = ph.draw_factual(n, T, seed, patient_base=base)
+        for g, k in zip(got[1:], ('recovery', 'chemo', 'radio')):
+            assert np.array_equal(g.cpu().numpy(), want[k]), k
+        np.testing.assert_allclose(got[0].cpu().numpy(), want["noise"], rtol=1e-12, atol=1e-16)   # cos(pi x) near its zeros
+    u = got[2].cpu().numpy()
+    assert u.min() >= 0.0 and u.max() < 1.0
+
+
+def _cohort(n, seed, slow_rows=None):
+    params, _ = h.random_cohort(n, seed=seed)
+    if slow_rows is not None:   # mixed sigmoids: those 32-patient tiles take the generic column function
+        params['radio_sigmoid_betas'][slow_rows] = 6.0 / 12.999999999999998
+    return params
+
+
+@pytest.mark.parametrize("n,T,pitch,slow", [(5000, 60, 64, None), (4999, 60, 60, slice(900, 940)), (333, 62, 64, None),
+                                            (70, 20, 20, slice(0, 3)), (31, 4, 4, None)])
+def test_sim_factual_rng_equals_k1_on_exported_draws(dev, n, T, pitch, slow):
+    """b200i_sim_factual_rng == b200i_sim_factual fed with b200i_philox_draws, bit for bit: volumes, treatment codes,
+    sequence lengths, per-patient moment sums."""
+    import torch
+    params = _cohort(n, 81, slow)
+    pd_ = dev.to_device(dev.pack_params(params))
+    seed, base = 20231018, 12345
+    draws = dev.philox_draws(n, T, seed, patient_base=base, pitch=pitch)
+    out, _ = dev.sim_factual(pd_, *draws, T)
+    vol, codes, sl, pm, _ = dev.sim_factual_rng(pd_, T, seed, patient_base=base, pitch=pitch)
+    torch.cuda.synchronize()
+    assert torch.equal(vol, out['cancer_volume'])
+    assert torch.equal(sl, out['sequence_lengths'])
+    want = (out['chemo_application'] + 2 * out['radio_application']).to(torch.uint8)
+    assert torch.equal(codes[:, :T], want)
+    assert int(codes[:, T:].sum()) == 0
+    # moments: sums over the active entries (inactive entries are zero)
+    v, c, d = out['cancer_volume'].cpu().numpy(), out['chemo_dosage'].cpu().numpy(), out['radio_dosage'].cpu().numpy()
+    got = pm.cpu().numpy()
+    for j, a in enumerate((v, v * v, c, c * c, d, d * d)):
+        np.testing.assert_allclose(got[j], a.sum(axis=1), rtol=1e-12, atol=1e-300)
+    assert 2 < float(sl.mean()) <= T - 1
+
+
+def test_sim_factual_rng_is_shard_invariant(dev):
+    """Counter = global patient index: two shards with patient_base reproduce the single launch bit for bit."""
+    import torch
+    n, T = 3000, 60
+    params = _cohort(n, 82)
+    block = dev.pack_params(params)
+    whole = dev.sim_factual_rng(dev.to_device(block), T, 99)
+    parts = [dev.sim_factual_rng(dev.to_device(block[:, a:b]), T, 99, patient_base=a) for a, b in ((0, 1111), (1111, n))]
+    torch.cuda.synchronize()
+    for j in range(4):
+        cat = torch.cat([p[j] for p in parts], dim=1 if j == 3 else 0)
+        assert torch.equal(cat, whole[j]), j
+
+
+@pytest.mark.parametrize("slow", [None, slice(700, 760)])
+def test_sim_factual_rng_fused_statistics(dev, slow):
+    """Fused population statistics of the generator kernel == theta_gram on K1's arrays for the same draws, and the
+    lean pair (moments + codes -> theta_gram_codes) gives the same; STLSQ support identical."""
+    import torch
+    n, T = 5000, 60
+    params = _cohort(n, 83, slow)
+    pd_ = dev.to_device(dev.pack_params(params))
+    static = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64))
+    draws = dev.philox_draws(n, T, 5, pitch=64)
+    out, _ = dev.sim_factual(pd_, *draws, T)
+    alone = dev.theta_gram(out['cancer_volume'], out['chemo_application'], out['radio_application'],
+                           out['sequence_lengths'], static, out['chemo_dosage'], out['radio_dosage'], tag="r0").clone()
+    vol, codes, sl, pm, fused = dev.sim_factual_rng(pd_, T, 5, fused_static=static, tag="r1")
+    fused = fused.clone()
+    vol2, codes2, sl2, pm2, _ = dev.sim_factual_rng(pd_, T, 5)
+    lean = dev.theta_gram_codes(vol2, codes2, sl2, static, pm2, tag="r2").clone()
+    torch.cuda.synchronize()
+    assert torch.equal(vol, vol2) and torch.equal(codes, codes2)
+    a, f, l = alone.cpu().numpy(), fused.cpu().numpy(), lean.cpu().numpy()
+    np.testing.assert_allclose(f, a, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(l, a, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(dev.unpack_stats(f)['count'], dev.unpack_stats(a)['count'])
+    ca, sa = dev.stlsq_population(alone)
+    cf, sf = dev.stlsq_population(fused)
+    torch.cuda.synchronize()
+    assert torch.equal(sa, sf)
+    np.testing.assert_allclose(cf.cpu().numpy(), ca.cpu().numpy(), rtol=1e-9, atol=1e-13)
+
+
+def test_sim_factual_rng_argument_errors(dev):
+    import torch
+    params = _cohort(64, 84)
+    pd_ = dev.to_device(dev.pack_params(params))
+    with pytest.raises(RuntimeError, match="seq_length"):
+        dev.sim_factual_rng(pd_, 61, 1, volume=dev.alloc_rows(64, 61, 62))
+    with pytest.raises(RuntimeError, match="code_pitch"):
+        dev.sim_factual_rng(pd_, 60, 1, codes=torch.empty((64, 60), dtype=torch.uint8, device='cuda'))

@@ -179,3 +179,20 @@ def test_oracle_against_live_reference():
               'patient_current_t'):
         assert np.array_equal(o[k], ref[k]), k
     np.testing.assert_allclose(o['cancer_volume'], ref['cancer_volume'], rtol=1e-13, atol=1e-15)
+
+
+def test_philox_block_function_known_answers():
+    """Random123 kat_vectors for philox4x32-10 pin the generator restatement (oracle/philox_np.py)."""
+    from oracle import philox_np as ph
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = ph.philox4x32_10(*[np.uint64(c) for c in ctr], *key)
+        assert tuple(int(g) for g in got) == want
+    d = ph.draw_factual(2000, 60, 3)
+    assert abs(d['noise'].std() / 0.01 - 1) < 0.01 and abs(d['noise'].mean()) < 1e-4
+    for k in ('recovery', 'chemo', 'radio'):
+        assert 0.0 <= d[k].min() and d[k].max() < 1.0 and abs(d[k].mean() - 0.5) < 0.005
+    assert abs(np.corrcoef(d['noise'][:, 0::2].ravel(), d['noise'][:, 1::2].ravel())[0, 1]) < 0.01
