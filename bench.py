@@ -197,7 +197,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from b200_insite import device as dev
-    from b200_insite.cohort import FactualFitPipeline
+    from b200_insite.cohort import FactualFitPipeline, GeneratedFitPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -311,6 +311,48 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = steps_exec_all / (float(te[0]) / 1e3)
     coefs = h_result[:16].numpy().reshape(4, 4).copy()
+    del h_draws
+
+    # ---- throughput mode: draws generated inside the simulator kernel (K1L) ------------------------------
+    # the reference's simulate_factual draws its random numbers itself (cancer_simulation.py:275-279): the call's
+    # inputs are the patient parameters.  Host parameters -> chunked H2D overlapped with K1L -> fit -> D2H result.
+    gen = GeneratedFitPipeline(n, T, seed=1234, patient_base=rank * n, chunks=args.rng_chunks)
+    gen.params.copy_(pipe.params); gen.static.copy_(pipe.static)
+    for _ in range(args.warmup):
+        gen.step_device()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        gen.step_device()
+    g1.record()
+    barrier()
+    gen_ms = g0.elapsed_time(g1) / args.steps
+    for a, b in ev:
+        a.record()
+        gen._simulate()
+        b.record()
+    torch.cuda.synchronize()
+    k1l_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    gen_exec = gen.executed_steps()
+    for _ in range(max(1, min(args.warmup, 3))):
+        gen.step_host(h_block, h_static, h_result)
+    barrier()
+    gen_e2e_steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(gen_e2e_steps):
+        gen.step_host(h_block, h_static, h_result)
+    barrier()
+    gen_e2e_ms = 1e3 * (time.perf_counter() - t0) / gen_e2e_steps
+    gen_coefs = h_result[:16].numpy().reshape(4, 4).copy()
+    tg = torch.tensor([gen_ms, gen_e2e_ms, -gen_exec], dtype=torch.float64, device='cuda')
+    if world > 1:
+        tgs = torch.tensor([gen_exec], dtype=torch.float64, device='cuda'); dist.all_reduce(tgs, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gen_exec_all = float(tgs[0])
+    else:
+        gen_exec_all = gen_exec
+    gen_ms, gen_e2e_ms = float(tg[0]), float(tg[1])
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
@@ -335,10 +377,25 @@ def run_b200(args):
                            "noise": "pre-drawn arrays resident in HBM (reference I/O contract)",
                            "parallelism": f"patients sharded over {world} GPU(s); allreduce of 68 doubles"},
                 "clocks": clocks.summary(),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(),
-                        "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": float(te[0]),
-                        "what": "FactualFitPipeline.step_host: pinned host params+draws -> H2D -> K1,K4,K5 -> D2H "
-                                "coefficients/support/statistics"},
+                "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen.h2d_bytes(),
+                        "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": gen_e2e_ms,
+                        "what": "GeneratedFitPipeline.step_host: pinned host parameters (the inputs of the reference's "
+                                "simulate_factual call, which draws its random numbers itself) -> H2D in "
+                                f"{len(gen.bounds)} chunks overlapped with K1L (simulator with the Philox4x32-10 draws "
+                                "generated in registers, bit-identical to K1 on the exported draws) -> theta_gram_codes "
+                                "-> STLSQ -> D2H coefficients/support/statistics"},
+                "e2e_host_draws": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(),
+                                   "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": float(te[0]),
+                                   "what": "FactualFitPipeline.step_host: pinned host params + the four pre-drawn (N,T) "
+                                           "arrays of the K1 contract -> H2D -> K1,K4,K5 -> D2H (PCIe-bound: 2 GB of "
+                                           "draws per step)"},
+                "device_rng": {"value": gen_exec_all / (gen_ms / 1e3), "unit": UNIT, "ms_per_step": gen_ms,
+                               "kernel": "sim_factual_rng_kernel<2,3>", "kernel_ms": k1l_ms,
+                               "bound": "instruction issue / FP64 pipe (0.63 KB of HBM traffic per patient)",
+                               "hbm_bytes_per_launch": (80 + T * 8 + ((T + 15) // 16) * 16 + 8 + 48) * n,
+                               "what": "GeneratedFitPipeline.step_device: parameters resident, draws generated in the "
+                                       "simulator kernel, lean cohort (volume + code bytes + moments) -> fit",
+                               "population_coefs": gen_coefs.tolist()},
                 "gpu_launches": pipe.launches_per_step * args.steps,
                 "roofline": {"bound": "hbm", "kernel": K1_KERNELS[args.layout], "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(K1_KERNELS[args.layout]),
@@ -386,6 +443,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--lean-fit", type=int, default=1, help="simulator side outputs + theta_gram_codes (default) or "
                     "the standalone five-array theta_gram")
+    ap.add_argument("--rng-chunks", type=int, default=4, help="H2D/compute overlap chunks of the generated-draws e2e path")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],
                     help="device-resident (N,T) arrays: rows padded to 128-byte lines, or the reference's dense rows")
     ap.add_argument("--ref-patients", type=int, default=400_000, help="bounded CPU sample")

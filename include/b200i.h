@@ -172,20 +172,21 @@ B200I_API int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, in
  * (csrc/philox.cuh), so a patient's draws are independent of the launch shape, the shard and the number of GPUs.
  * b200i_philox_draws writes exactly those draws as the four arrays of the K1 contract (noise already x 0.01);
  * b200i_sim_factual on them reproduces b200i_sim_factual_rng bit for bit.
- * b200i_sim_factual_rng: in : params (10,N), seed, patient_base (global index of row 0).
+ * b200i_sim_factual_rng: in : params (10, params_stride >= N): a launch may cover a column range of a larger block
+ *        (chunked host->device pipelines), seed, patient_base (global index of row 0).
  *   out: cancer_volume (N,T) with row_pitch (even, >= T); codes_out (N, code_pitch) uint8 = chemo + 2*radio
  *        application per step, or NULL (code_pitch: multiple of 16, >= T rounded up to 16; bytes >= T of a row are
- *        written as 0 up to T rounded up to 16); sequence_lengths (N,) float64; patient_moments_out (6,N) as
- *        b200i_sim_factual_side, or NULL.
+ *        written as 0 up to T rounded up to 16); sequence_lengths (N,) float64; patient_moments_out
+ *        (6, moments_stride >= N) as b200i_sim_factual_side, or NULL.
  *   gram_workspace != NULL (with static_feature (N,), fd_dt > 0): the population statistics of K4 (Gram + moments,
  *        same layout and meaning as b200i_theta_gram) are accumulated in the same kernel; patient_moments_out is
  *        then ignored.  T even, 4..1024. */
 B200I_API int b200i_philox_draws(int64_t n, int32_t T, int64_t row_pitch, uint64_t seed, int64_t patient_base,
                      double *noise, double *recovery_rvs, double *chemo_rvs, double *radio_rvs, void *stream);
 B200I_API int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
-                     const double *params, uint64_t seed, int64_t patient_base,
+                     const double *params, int64_t params_stride, uint64_t seed, int64_t patient_base,
                      double *cancer_volume, uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
-                     double *patient_moments_out, const double *static_feature, double fd_dt,
+                     double *patient_moments_out, int64_t moments_stride, const double *static_feature, double fd_dt,
                      void *gram_workspace, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,

@@ -10,6 +10,9 @@ bit-identical population coefficients.
     FactualFitPipeline.step_host()    the same through host buffers: pinned params + pre-drawn noise
                                       are copied H2D, results (coefficients, support, scaling moments)
                                       are copied back
+    GeneratedFitPipeline              throughput mode: the draws come from the device generator inside the
+                                      simulator kernel (K1L), so a step's host inputs are the parameters only;
+                                      step_host() overlaps their chunked H2D copy with the simulation
 Reference path being replaced: SyntheticCancerDataset(mode='factual') -> get_scaling_params ->
 SINDY.fit (dataset.py:58-63, cancer_simulation.py:218-375/776-796, sindy.py:145-338).
 """
@@ -146,3 +149,81 @@ class FactualFitPipeline:
     def executed_steps(self):
         """Executed simulator loop iterations of the last step: sum(sequence_length - 1)."""
         return float((self.out['sequence_lengths'] - 1.0).sum().item())
+
+
+class GeneratedFitPipeline:
+    """Factual cohort + population fit with device-generated draws (throughput mode).
+
+    The reference's simulate_factual draws its random numbers itself (cancer_simulation.py:275-279), so the call's
+    inputs are the patient parameters; here the draws come from Philox4x32-10 counted by the global patient index
+    inside the simulator kernel (K1L, b200i_sim_factual_rng) and the cohort is kept in its lean device form:
+    volume (N,T) float64 + one treatment-code byte per step + sequence lengths + six per-patient moment sums,
+    which is exactly what the fit (b200i_theta_gram_codes -> all-reduce -> b200i_stlsq_population) consumes."""
+
+    def __init__(self, n_local, T=60, seed=0, patient_base=0, window_size=15, threshold=1e-3, alpha=0.5, max_iter=100,
+                 chunks=4):
+        dev.require_cuda()
+        self.n, self.T = int(n_local), int(T)
+        self.seed, self.patient_base = int(seed), int(patient_base)
+        self.consts = dev.sim_consts(window_size, 0)
+        self.threshold, self.alpha, self.max_iter = threshold, alpha, max_iter
+        f64 = dict(dtype=torch.float64, device='cuda')
+        self.params = torch.empty((10, self.n), **f64)
+        self.static = torch.empty((self.n,), **f64)
+        self.volume = dev.alloc_rows(self.n, self.T, dev.aligned_pitch(self.T))
+        self.codes = torch.empty((self.n, ((self.T + 15) // 16) * 16), dtype=torch.uint8, device='cuda')
+        self.sequence_lengths = torch.empty((self.n,), **f64)
+        self.patient_moments = torch.empty((6, self.n), **f64)
+        self.stats = torch.zeros(dev.STATS_DOUBLES, **f64)
+        self.coefs = self.support = None
+        chunks = max(1, min(int(chunks), self.n // 32 if self.n >= 32 else 1))
+        step = -(-self.n // chunks)
+        step = -(-step // 32) * 32                                   # whole 32-patient tiles per chunk
+        self.bounds = [(a, min(a + step, self.n)) for a in range(0, self.n, step)]
+        self.copy_stream = torch.cuda.Stream()
+        self.copied = [torch.cuda.Event() for _ in self.bounds]
+        self.launches_per_step = len(self.bounds) + 2               # K1L per chunk + theta_gram_codes + stlsq_population
+
+    def h2d_bytes(self):
+        return (10 + 1) * self.n * 8
+
+    def _simulate(self, rows=None):
+        dev.sim_factual_rng(self.params, self.T, self.seed, patient_base=self.patient_base, consts=self.consts,
+                            volume=self.volume, codes=self.codes, sequence_lengths=self.sequence_lengths,
+                            patient_moments=self.patient_moments, rows=rows)
+
+    def _fit(self):
+        stats = dev.theta_gram_codes(self.volume, self.codes, self.sequence_lengths, self.static, self.patient_moments)
+        self.stats.copy_(stats)
+        allreduce_stats(self.stats)
+        self.coefs, self.support = dev.stlsq_population(self.stats, self.threshold, self.alpha, self.max_iter)
+        return self.coefs
+
+    def step_device(self):
+        """Parameters already resident in HBM: one K1L launch over the shard, then the fit."""
+        self._simulate()
+        return self._fit()
+
+    def step_host(self, params_block, static, result_host):
+        """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.  The parameter
+        rows of chunk c+1 are copied on a second stream while chunk c is being simulated."""
+        main = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(main)          # the previous step's kernels have released the buffers
+        with torch.cuda.stream(self.copy_stream):
+            for (a, b), ev in zip(self.bounds, self.copied):
+                for r in range(10):
+                    self.params[r, a:b].copy_(params_block[r, a:b], non_blocking=True)
+                self.static[a:b].copy_(static[a:b], non_blocking=True)
+                ev.record(self.copy_stream)
+        for (a, b), ev in zip(self.bounds, self.copied):
+            main.wait_event(ev)
+            self._simulate(rows=(a, b))
+        self._fit()
+        result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
+        result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
+        result_host[32:32 + dev.STATS_DOUBLES].copy_(self.stats, non_blocking=True)
+        main.synchronize()
+        return result_host
+
+    def executed_steps(self):
+        return float((self.sequence_lengths - 1.0).sum().item())

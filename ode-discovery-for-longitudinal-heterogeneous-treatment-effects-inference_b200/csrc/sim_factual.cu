@@ -608,10 +608,10 @@ extern "C" int b200i_philox_draws(int64_t n, int32_t T, int64_t row_pitch, uint6
 }
 
 extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
-                                     const double *params, uint64_t seed, int64_t patient_base, double *cancer_volume,
-                                     uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
-                                     double *patient_moments_out, const double *static_feature, double fd_dt,
-                                     void *gram_workspace, void *stream)
+                                     const double *params, int64_t params_stride, uint64_t seed, int64_t patient_base,
+                                     double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
+                                     double *sequence_lengths, double *patient_moments_out, int64_t moments_stride,
+                                     const double *static_feature, double fd_dt, void *gram_workspace, void *stream)
 {
     B200I_REQUIRE(n >= 0 && patient_base >= 0, B200I_E_ARG, "sim_factual_rng: negative n or patient_base");
     if (n == 0) {
@@ -621,6 +621,9 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
         return 0;
     }
     B200I_REQUIRE(k && params && cancer_volume && sequence_lengths, B200I_E_ARG, "sim_factual_rng: NULL argument");
+    B200I_REQUIRE(params_stride >= n && (patient_moments_out == nullptr || moments_stride >= n), B200I_E_ARG,
+                  "sim_factual_rng: params_stride %lld / moments_stride %lld must be >= n", (long long)params_stride,
+                  (long long)moments_stride);
     B200I_REQUIRE(T >= 4 && T <= 1024 && T % 2 == 0, B200I_E_UNSUPPORTED, "sim_factual_rng: seq_length %d (even, 4..1024)", T);
     B200I_REQUIRE(row_pitch >= T && row_pitch % 2 == 0 && aligned16(cancer_volume), B200I_E_ALIGN,
                   "sim_factual_rng: row_pitch %lld must be even and >= T, cancer_volume 16-byte aligned", (long long)row_pitch);
@@ -643,12 +646,12 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
     StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
     if (gram) {
         B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
-        return launch_rng<1, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
-                                       nullptr, static_feature, ws, st);
+        return launch_rng<1, RNG_MINB>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+                                       sequence_lengths, nullptr, static_feature, ws, st);
     }
     if (patient_moments_out)
-        return launch_rng<2, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
-                                       patient_moments_out, nullptr, nullptr, st);
-    return launch_rng<0, RNG_MINB>(vmap, n, T, c, params, seed, patient_base, codes_out, code_pitch, sequence_lengths,
-                                   nullptr, nullptr, nullptr, st);
+        return launch_rng<2, RNG_MINB>(vmap, n, params_stride, moments_stride, T, c, params, seed, patient_base, codes_out,
+                                       code_pitch, sequence_lengths, patient_moments_out, nullptr, nullptr, st);
+    return launch_rng<0, RNG_MINB>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+                                   sequence_lengths, nullptr, nullptr, nullptr, st);
 }

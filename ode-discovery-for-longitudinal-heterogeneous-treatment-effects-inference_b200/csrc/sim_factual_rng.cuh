@@ -62,7 +62,7 @@ __device__ __noinline__ void rng_slow_box(uint8_t *buf, uint8_t *crow, int lane,
 
 template <int STATS, int MINB>
 __global__ void __launch_bounds__(RNG_WARPS * 32, MINB)
-sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int64_t pstride, int T, SimC c,
+sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int64_t pstride, int64_t mstride, int T, SimC c,
                        const double *__restrict__ params, uint32_t seed_lo, uint32_t seed_hi, int64_t patient_base,
                        uint8_t *__restrict__ codes_out, int64_t code_pitch, double *__restrict__ seq_len_out,
                        double *__restrict__ pmom_out, const double *__restrict__ static_feature, StatsWorkspace *ws)
@@ -233,9 +233,9 @@ sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int6
             const Moments &mm = tile_slow ? slow.mom : mom;
             const double sd = tile_slow ? slow.mom.sd : c.radio_amt * (double)g_nra;
             const double sdd = tile_slow ? slow.mom.sdd : c.radio_amt * c.radio_amt * (double)g_nra;
-            pmom_out[0 * pstride + patient] = mm.sv;  pmom_out[1 * pstride + patient] = mm.svv;
-            pmom_out[2 * pstride + patient] = mm.sc;  pmom_out[3 * pstride + patient] = mm.scc;
-            pmom_out[4 * pstride + patient] = sd;     pmom_out[5 * pstride + patient] = sdd;
+            pmom_out[0 * mstride + patient] = mm.sv;  pmom_out[1 * mstride + patient] = mm.svv;
+            pmom_out[2 * mstride + patient] = mm.sc;  pmom_out[3 * mstride + patient] = mm.scc;
+            pmom_out[4 * mstride + patient] = sd;     pmom_out[5 * mstride + patient] = sdd;
         }
         if (GRAM) {
             const double u = exists ? __ldg(static_feature + patient) : 0.0;
@@ -295,7 +295,8 @@ philox_draws_kernel(int64_t n, int T, int64_t pitch, uint32_t seed_lo, uint32_t 
 }
 
 template <int STATS, int MINB>
-static int launch_rng(const CUtensorMap &vmap, int64_t n, int T, const SimC &c, const double *params, uint64_t seed,
+static int launch_rng(const CUtensorMap &vmap, int64_t n, int64_t pstride, int64_t mstride, int T, const SimC &c,
+                      const double *params, uint64_t seed,
                       int64_t patient_base, uint8_t *codes_out, int64_t code_pitch, double *seq_len, double *pmom,
                       const double *static_feature, StatsWorkspace *ws, cudaStream_t st)
 {
@@ -311,7 +312,7 @@ static int launch_rng(const CUtensorMap &vmap, int64_t n, int T, const SimC &c, 
     const int64_t need = (ntiles + RNG_WARPS - 1) / RNG_WARPS;
     if (grid > need) grid = need;
     if (STATS == 1 && grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
-    kern<<<(unsigned)grid, RNG_WARPS * 32, smem, st>>>(vmap, n, n, T, c, params, (uint32_t)seed, (uint32_t)(seed >> 32),
+    kern<<<(unsigned)grid, RNG_WARPS * 32, smem, st>>>(vmap, n, pstride, mstride, T, c, params, (uint32_t)seed, (uint32_t)(seed >> 32),
                                                        patient_base, codes_out, code_pitch, seq_len, pmom,
                                                        static_feature, ws);
     return check_cuda(cudaGetLastError(), "sim_factual_rng launch");

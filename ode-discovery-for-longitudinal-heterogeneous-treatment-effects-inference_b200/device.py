@@ -170,30 +170,41 @@ def philox_draws(n, T, seed, patient_base=0, pitch=None):
 
 
 def sim_factual_rng(params_dev, T, seed, patient_base=0, consts=None, volume=None, codes=None, sequence_lengths=None,
-                    patient_moments=None, fused_static=None, fd_dt=STANDARD_DT, pitch=None, moments=True, tag="default"):
+                    patient_moments=None, fused_static=None, fd_dt=STANDARD_DT, pitch=None, moments=True, tag="default",
+                    rows=None):
     """K1L: simulate_factual with device-generated draws (Philox4x32-10 counted by global patient index).
 
     Returns (volume (N,T) [row pitch `pitch`], codes (N, code_pitch) uint8 = chemo + 2*radio application,
     sequence_lengths (N,), moments (6,N) or None, stats (68,) or None).  fused_static: (N,) static feature ->
-    the population statistics of theta_gram are accumulated inside the kernel (moments are then not written)."""
+    the population statistics of theta_gram are accumulated inside the kernel (moments are then not written).
+    rows=(a, b): simulate only patients [a, b) of the given full-size buffers (chunked pipelines); their generator
+    counters are patient_base + a ..., so the result does not depend on the chunking."""
     lib = _native.load()
-    n = params_dev.shape[1]
+    n_all = params_dev.shape[1]
+    a, b = (0, n_all) if rows is None else (int(rows[0]), int(rows[1]))
+    n = b - a
     consts = consts or sim_consts()
     if volume is None:
-        volume = alloc_rows(n, T, aligned_pitch(T) if pitch is None else pitch)
-    vp = row_pitch(volume) if n > 1 else T
+        volume = alloc_rows(n_all, T, aligned_pitch(T) if pitch is None else pitch)
+    vp = row_pitch(volume) if n_all > 1 else T
     if codes is None:
-        codes = torch.empty((n, ((T + 15) // 16) * 16), dtype=torch.uint8, device='cuda')
+        codes = torch.empty((n_all, ((T + 15) // 16) * 16), dtype=torch.uint8, device='cuda')
     if sequence_lengths is None:
-        sequence_lengths = torch.empty((n,), dtype=torch.float64, device='cuda')
+        sequence_lengths = torch.empty((n_all,), dtype=torch.float64, device='cuda')
     ws = gram_workspace(tag) if fused_static is not None else None
     if ws is None and moments and patient_moments is None:
-        patient_moments = torch.empty((6, n), dtype=torch.float64, device='cuda')
+        patient_moments = torch.empty((6, n_all), dtype=torch.float64, device='cuda')
     if ws is not None:
         patient_moments = None
-    rc = lib.b200i_sim_factual_rng(n, T, vp, ctypes.byref(consts), _ptr(params_dev), int(seed), int(patient_base),
-                                   _ptr_rows(volume), _ptr(codes), int(codes.shape[1]), _ptr(sequence_lengths),
-                                   _ptr(patient_moments), _ptr(fused_static), float(fd_dt), _ptr(ws), _stream())
+    cp = int(codes.shape[1])
+
+    def off(t, elems, size=8):
+        return None if t is None else ctypes.c_void_p(t.data_ptr() + elems * size)
+    assert params_dev.is_contiguous() and codes.is_contiguous() and sequence_lengths.is_contiguous()
+    rc = lib.b200i_sim_factual_rng(n, T, vp, ctypes.byref(consts), off(params_dev, a), n_all, int(seed),
+                                   int(patient_base) + a, off(volume, a * vp), off(codes, a * cp, 1), cp,
+                                   off(sequence_lengths, a), off(patient_moments, a), n_all, off(fused_static, a),
+                                   float(fd_dt), _ptr(ws), _stream())
     _native.check(rc, "b200i_sim_factual_rng")
     return volume, codes, sequence_lengths, patient_moments, (ws[:STATS_DOUBLES] if ws is not None else None)
 
