@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--lean-fit", type=int, default=1, help="simulator side outputs + theta_gram_codes (default) or "
                     "the standalone five-array theta_gram")
-    ap.add_argument("--rng-chunks", type=int, default=4, help="H2D/compute overlap chunks of the generated-draws e2e path")
+    ap.add_argument("--rng-chunks", type=int, default=16, help="H2D/compute overlap chunks of the generated-draws e2e path")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],
                     help="device-resident (N,T) arrays: rows padded to 128-byte lines, or the reference's dense rows")
     ap.add_argument("--ref-patients", type=int, default=400_000, help="bounded CPU sample")

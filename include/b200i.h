@@ -180,14 +180,26 @@ B200I_API int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, in
  *        (6, moments_stride >= N) as b200i_sim_factual_side, or NULL.
  *   gram_workspace != NULL (with static_feature (N,), fd_dt > 0): the population statistics of K4 (Gram + moments,
  *        same layout and meaning as b200i_theta_gram) are accumulated in the same kernel; patient_moments_out is
- *        then ignored.  T even, 4..1024. */
+ *        then ignored.  T even, 4..1024.
+ *   variant: 0 = default (= 2: phased kernel, generator loop and one-column simulator loop that each fit the L0
+ *        instruction cache, 16 warps per SM); 1 = first generation (four unrolled columns, generator inlined);
+ *        both give identical bits. */
 B200I_API int b200i_philox_draws(int64_t n, int32_t T, int64_t row_pitch, uint64_t seed, int64_t patient_base,
                      double *noise, double *recovery_rvs, double *chemo_rvs, double *radio_rvs, void *stream);
 B200I_API int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
                      const double *params, int64_t params_stride, uint64_t seed, int64_t patient_base,
                      double *cancer_volume, uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
                      double *patient_moments_out, int64_t moments_stride, const double *static_feature, double fd_dt,
-                     void *gram_workspace, void *stream);
+                     void *gram_workspace, int32_t variant, void *stream);
+/* Host-resident parameters: params_host (10,N) and static_host (N,) [or NULL] are PINNED HOST arrays; they are copied
+ * into params / static_feature in `chunks` column ranges on copy_stream, and every range is simulated on `stream`
+ * (b200i_sim_factual_rng with the per-patient moments) as soon as it has arrived, so the PCIe transfer overlaps the
+ * simulation.  Same outputs as one b200i_sim_factual_rng launch over all N patients. */
+B200I_API int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
+                     const double *params_host, const double *static_host, double *params, double *static_feature,
+                     uint64_t seed, int64_t patient_base, double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
+                     double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                     void *copy_stream, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
                      const double *cancer_volume, const double *chemo_application,

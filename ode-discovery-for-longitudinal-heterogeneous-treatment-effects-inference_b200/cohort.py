@@ -161,7 +161,7 @@ class GeneratedFitPipeline:
     which is exactly what the fit (b200i_theta_gram_codes -> all-reduce -> b200i_stlsq_population) consumes."""
 
     def __init__(self, n_local, T=60, seed=0, patient_base=0, window_size=15, threshold=1e-3, alpha=0.5, max_iter=100,
-                 chunks=4):
+                 chunks=16):
         dev.require_cuda()
         self.n, self.T = int(n_local), int(T)
         self.seed, self.patient_base = int(seed), int(patient_base)
@@ -179,9 +179,9 @@ class GeneratedFitPipeline:
         chunks = max(1, min(int(chunks), self.n // 32 if self.n >= 32 else 1))
         step = -(-self.n // chunks)
         step = -(-step // 32) * 32                                   # whole 32-patient tiles per chunk
-        self.bounds = [(a, min(a + step, self.n)) for a in range(0, self.n, step)]
+        self.bounds = [(a, min(a + step, self.n)) for a in range(0, self.n, step)]   # what the C side will use
+        self.chunks = len(self.bounds)
         self.copy_stream = torch.cuda.Stream()
-        self.copied = [torch.cuda.Event() for _ in self.bounds]
         self.launches_per_step = len(self.bounds) + 2               # K1L per chunk + theta_gram_codes + stlsq_population
 
     def h2d_bytes(self):
@@ -208,16 +208,9 @@ class GeneratedFitPipeline:
         """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.  The parameter
         rows of chunk c+1 are copied on a second stream while chunk c is being simulated."""
         main = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(main)          # the previous step's kernels have released the buffers
-        with torch.cuda.stream(self.copy_stream):
-            for (a, b), ev in zip(self.bounds, self.copied):
-                for r in range(10):
-                    self.params[r, a:b].copy_(params_block[r, a:b], non_blocking=True)
-                self.static[a:b].copy_(static[a:b], non_blocking=True)
-                ev.record(self.copy_stream)
-        for (a, b), ev in zip(self.bounds, self.copied):
-            main.wait_event(ev)
-            self._simulate(rows=(a, b))
+        dev.upload_simulate_rng(params_block, static, self.params, self.static, self.T, self.seed, self.patient_base,
+                                self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
+                                self.chunks, self.copy_stream)
         self._fit()
         result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
         result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)

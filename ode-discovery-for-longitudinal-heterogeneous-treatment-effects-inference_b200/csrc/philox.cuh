@@ -7,7 +7,9 @@
 // number of GPUs.  One call yields the 2 x 64 bits of one stream for the two columns of a pair:
 //     counter = (patient lo, patient hi, column / 2, stream),  key = (seed lo, seed hi)
 //     stream 0: Box-Muller pair -> noise of the even / odd column;  1: recovery;  2: chemo;  3: radio
-//     uniform: the top 52 bits of a 64-bit word fill the mantissa of a double in [1,2); u = that - 1  (in [0,1))
+//     uniform: the top 52 bits of a 64-bit word fill the mantissa of a double in [1,2); u = that - 1  (in [0,1));
+//              the recovery stream adds 2^-53 (bin centres, in (0,1)): its smallest value exceeds exp(-40), so the
+//              simulator kernel only has to generate it when the recovery test can succeed at all (V < 6.9e-8)
 //     normal:  r = sqrt(-2 log(2 - m1)), (z_even, z_odd) = r * (cospi, sinpi)(2 * (m2 - 1)),  noise = 0.01 * z
 // The test-suite restates this in numpy and pins the block function to the Random123 known-answer vectors.
 #pragma once
@@ -55,6 +57,26 @@ __device__ __forceinline__ void uniform_pair(const PairKey &k, uint32_t tp, uint
     u_even = __dsub_rn(mant12(r.x, r.y), 1.0);
     u_odd = __dsub_rn(mant12(r.z, r.w), 1.0);
 }
+
+// the two recovery uniforms of column pair tp (stream 1): bin centres, in (0,1)
+__device__ __forceinline__ void recovery_pair(const PairKey &k, uint32_t tp, double &u_even, double &u_odd)
+{
+    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, 1u}, k.k0, k.k1);
+    u_even = __dadd_rn(__dsub_rn(mant12(r.x, r.y), 1.0), 0x1p-53);
+    u_odd = __dadd_rn(__dsub_rn(mant12(r.z, r.w), 1.0), 0x1p-53);
+}
+
+// recovery draw of one column, generated on demand
+struct LazyRecovery {
+    const PairKey *key;
+    uint32_t tp, odd;
+    __device__ __forceinline__ double get() const
+    {
+        double a, b;
+        recovery_pair(*key, tp, a, b);
+        return odd ? b : a;
+    }
+};
 
 // the two noise terms 0.01 * N(0,1) of column pair tp (stream 0)
 __device__ __forceinline__ void noise_pair(const PairKey &k, uint32_t tp, double &z_even, double &z_odd)

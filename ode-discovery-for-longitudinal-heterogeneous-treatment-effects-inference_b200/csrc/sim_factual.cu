@@ -10,6 +10,7 @@
 //     buffers, the `assigned_actions` fixed policy and the last n % 128 rows of the row-class mapping.
 // With GRAM the population statistics of theta_gram (K4) are accumulated while simulating.
 #include "fastmath.cuh"
+#include "philox.cuh"
 #include "sim_math.cuh"
 #include "stats_reduce.cuh"
 #include "tma.cuh"
@@ -611,7 +612,8 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
                                      const double *params, int64_t params_stride, uint64_t seed, int64_t patient_base,
                                      double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
                                      double *sequence_lengths, double *patient_moments_out, int64_t moments_stride,
-                                     const double *static_feature, double fd_dt, void *gram_workspace, void *stream)
+                                     const double *static_feature, double fd_dt, void *gram_workspace, int32_t variant,
+                                     void *stream)
 {
     B200I_REQUIRE(n >= 0 && patient_base >= 0, B200I_E_ARG, "sim_factual_rng: negative n or patient_base");
     if (n == 0) {
@@ -646,12 +648,84 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
     StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
     if (gram) {
         B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
-        return launch_rng<1, RNG_MINB>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+        if (variant == 1)
+            return launch_rng<1, 3, 1>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
                                        sequence_lengths, nullptr, static_feature, ws, st);
+        return launch_rng<1, 3, 2>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+                                   sequence_lengths, nullptr, static_feature, ws, st);
     }
-    if (patient_moments_out)
-        return launch_rng<2, RNG_MINB>(vmap, n, params_stride, moments_stride, T, c, params, seed, patient_base, codes_out,
+    // variant 0 / 2: second generation (phased, one column per loop body, 16 warps per SM); 1: first generation
+    // (four unrolled columns with the generator inlined, 12 warps per SM) -- kept as an independent cross-check
+    B200I_REQUIRE(variant >= 0 && variant <= 2, B200I_E_UNSUPPORTED, "sim_factual_rng: variant %d (0 auto, 1, 2)", variant);
+    if (patient_moments_out) {
+        if (variant == 1)
+            return launch_rng<2, 3, 1>(vmap, n, params_stride, moments_stride, T, c, params, seed, patient_base, codes_out,
                                        code_pitch, sequence_lengths, patient_moments_out, nullptr, nullptr, st);
-    return launch_rng<0, RNG_MINB>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+        return launch_rng<2, 4, 2>(vmap, n, params_stride, moments_stride, T, c, params, seed, patient_base, codes_out,
+                                   code_pitch, sequence_lengths, patient_moments_out, nullptr, nullptr, st);
+    }
+    if (variant == 1)
+        return launch_rng<0, 3, 1>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
                                    sequence_lengths, nullptr, nullptr, nullptr, st);
+    return launch_rng<0, 4, 2>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
+                               sequence_lengths, nullptr, nullptr, nullptr, st);
+}
+
+// Host parameters -> device, chunk by chunk on `copy_stream`, each chunk simulated on `stream` as soon as it has
+// arrived (events), so the PCIe transfer of chunk c+1 overlaps the simulation of chunk c.  One call replaces
+// ~12 framework calls per chunk of the Python pipeline (the step is ~2 ms: host-side launch cost matters).
+extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                         const double *params_host, const double *static_host, double *params,
+                                         double *static_feature, uint64_t seed, int64_t patient_base,
+                                         double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
+                                         double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                                         void *copy_stream, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && chunks >= 1 && chunks <= 64, B200I_E_ARG, "upload_simulate_rng: n=%lld chunks=%d (1..64)",
+                  (long long)n, chunks);
+    if (n == 0) return 0;
+    B200I_REQUIRE(params_host && params && copy_stream && copy_stream != stream, B200I_E_ARG,
+                  "upload_simulate_rng: NULL argument, or copy_stream == stream (no overlap possible)");
+    B200I_REQUIRE((static_host == nullptr) == (static_feature == nullptr), B200I_E_ARG,
+                  "upload_simulate_rng: static_host and static_feature must both be given or both be NULL");
+    cudaStream_t cs = static_cast<cudaStream_t>(copy_stream), st = static_cast<cudaStream_t>(stream);
+    int64_t step = (n + chunks - 1) / chunks;
+    step = ((step + 31) / 32) * 32;   // whole 32-patient tiles per chunk
+    // chunk kernels alternate between `stream` and an internal second stream, so that the next chunk fills the SMs
+    // the previous one is draining (each chunk is only one or two waves of 32-patient tiles)
+    static thread_local cudaStream_t aux[16] = {};
+    int devid = 0;
+    B200I_CUDA(cudaGetDevice(&devid));
+    B200I_REQUIRE(devid >= 0 && devid < 16, B200I_E_UNSUPPORTED, "upload_simulate_rng: device index %d", devid);
+    if (aux[devid] == nullptr) B200I_CUDA(cudaStreamCreateWithFlags(&aux[devid], cudaStreamNonBlocking));
+    cudaStream_t sx = aux[devid];
+    // the previous work on `stream` may still read the parameter block / write the outputs
+    cudaEvent_t ev;
+    B200I_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    int rc = check_cuda(cudaEventRecord(ev, st), "cudaEventRecord");
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(cs, ev, 0), "cudaStreamWaitEvent");
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(sx, ev, 0), "cudaStreamWaitEvent");
+    int c = 0;
+    for (int64_t a = 0; a < n && !rc; a += step, ++c) {
+        const int64_t b = (a + step < n) ? a + step : n;
+        cudaStream_t run = (c & 1) ? sx : st;
+        rc = check_cuda(cudaMemcpy2DAsync(params + a, (size_t)n * 8, params_host + a, (size_t)n * 8, (size_t)(b - a) * 8,
+                                          B200I_NUM_PARAMS, cudaMemcpyHostToDevice, cs), "cudaMemcpy2DAsync(params)");
+        if (!rc && static_host)
+            rc = check_cuda(cudaMemcpyAsync(static_feature + a, static_host + a, (size_t)(b - a) * 8,
+                                            cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(static)");
+        if (!rc) rc = check_cuda(cudaEventRecord(ev, cs), "cudaEventRecord");
+        if (!rc) rc = check_cuda(cudaStreamWaitEvent(run, ev, 0), "cudaStreamWaitEvent");
+        if (!rc)
+            rc = b200i_sim_factual_rng(b - a, T, row_pitch, k, params + a, n, seed, patient_base + a,
+                                       cancer_volume + a * row_pitch, codes_out ? codes_out + a * code_pitch : nullptr,
+                                       code_pitch, sequence_lengths + a, patient_moments_out ? patient_moments_out + a : nullptr,
+                                       n, nullptr, 0.0, nullptr, 0, run);
+    }
+    if (!rc && c > 1) {   // `stream` continues after the chunks of the second stream
+        rc = check_cuda(cudaEventRecord(ev, sx), "cudaEventRecord");
+        if (!rc) rc = check_cuda(cudaStreamWaitEvent(st, ev, 0), "cudaStreamWaitEvent");
+    }
+    cudaEventDestroy(ev);   // deferred by the runtime until the recorded work has completed
+    return rc;
 }

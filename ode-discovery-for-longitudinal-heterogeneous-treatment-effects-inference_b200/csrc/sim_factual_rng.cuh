@@ -26,7 +26,6 @@
 namespace b200i {
 
 constexpr int RNG_WARPS = 4;
-constexpr int RNG_MINB = 3;                  // CTAs per SM the register budget is sized for
 constexpr int RNG_VOL_BYTES = 2 * 32 * 128;   // two tiles of 32 patients x 16 columns per warp
 
 __host__ __device__ inline int rng_code_copy_words(int T) { return ((T + 15) / 16) * 4; }     // words written per row
@@ -42,7 +41,7 @@ __device__ __noinline__ void rng_slow_box(uint8_t *buf, uint8_t *crow, int lane,
         const int t = 16 * m + cidx;
         double nz[2], ur[2], uc[2], ud[2], v2[2];
         rng::noise_pair(key, (uint32_t)(t >> 1), nz[0], nz[1]);
-        rng::uniform_pair(key, (uint32_t)(t >> 1), 1u, ur[0], ur[1]);
+        rng::recovery_pair(key, (uint32_t)(t >> 1), ur[0], ur[1]);
         rng::uniform_pair(key, (uint32_t)(t >> 1), 2u, uc[0], uc[1]);
         rng::uniform_pair(key, (uint32_t)(t >> 1), 3u, ud[0], ud[1]);
 #pragma unroll
@@ -161,11 +160,10 @@ sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int6
                     for (int h = 0; h < h_hi; ++h) {
                         const int t0 = 16 * m + 4 * h;
                         const uint32_t tp = (uint32_t)(t0 >> 1);
-                        double nz[4], ur[4], uc[4], ud[4];
+                        double nz[4], uc[4], ud[4];
+                        const rng::LazyRecovery ur[4] = {{&key, tp, 0u}, {&key, tp, 1u}, {&key, tp + 1u, 0u}, {&key, tp + 1u, 1u}};
                         rng::noise_pair(key, tp, nz[0], nz[1]);
                         rng::noise_pair(key, tp + 1u, nz[2], nz[3]);
-                        rng::uniform_pair(key, tp, 1u, ur[0], ur[1]);
-                        rng::uniform_pair(key, tp + 1u, 1u, ur[2], ur[3]);
                         rng::uniform_pair(key, tp, 2u, uc[0], uc[1]);
                         rng::uniform_pair(key, tp + 1u, 2u, uc[2], uc[3]);
                         rng::uniform_pair(key, tp, 3u, ud[0], ud[1]);
@@ -267,6 +265,291 @@ sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int6
     if (GRAM) stats_block_finish(block_acc, RNG_WARPS, ws, &s_is_last);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second generation: phased, one column per loop body.
+// ncu on the first kernel (profiles/r1_k1l_gen1_ncu.txt): the warps wait for INSTRUCTIONS, not data -- stall
+// no_instruction 3.3 per issued instruction, issue slots 39 % busy.  Its loop body (four unrolled columns + eight
+// inlined Philox calls + two Box-Muller transforms) is 1700 instructions = 27 KB of SASS against a 6 KB L0 / 32 KB
+// L1.5 instruction cache shared by 12 warps at different program counters.  Here the work of eight columns is split
+// into two short loops that each fit the L0 cache:
+//   G  (per column pair, ~350 instructions): Philox + Box-Muller -> noise, chemo and radio draws into a small
+//      per-warp scratch (72-byte pitch: conflict-free 8-byte accesses);
+//   S  (per column, ~300 instructions): ws_col = the column arithmetic of ws_body with the diameter window shifted
+//      by one register per column (14 moves) instead of four unrolled copies with static window offsets.
+// Same draws, same arithmetic, same outputs as the first kernel, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int RNG2_SCRATCH_PITCH = 72;                               // bytes per patient row, 8 columns + pad
+constexpr int RNG2_SCRATCH_BYTES = 3 * 32 * RNG2_SCRATCH_PITCH;      // noise, chemo and radio draws of 8 columns
+constexpr int RNG2_VOL_BYTES = 32 * 128;                             // one tile of 32 patients x 16 columns per warp
+
+__host__ __device__ inline int rng2_warp_bytes(int T)
+{
+    return (RNG2_VOL_BYTES + RNG2_SCRATCH_BYTES + 32 * rng_code_words(T) * 4 + 1023) & ~1023;
+}
+
+// one column: volume of column t, treatment of column t-1, sigmoid argument of column t (see ws_body)
+template <class UR>
+__device__ __forceinline__ void ws_col(int t, int Tm1, const WsK &k, const WsPatient &p, WsState &s, double (&w)[15],
+                                       double v0, double nz, const UR &ur_in, double uc, double ud, double &oV,
+                                       double &oC, unsigned &oF)
+{
+    if (t == 0) {
+        oV = v0; oC = 0.0; oF = 0u;
+        s.V = v0;
+        return;
+    }
+    double pr, C1;
+    bool ra, ca;
+    if (t == 1) {
+        pr = 0.0; C1 = 0.0; ra = ca = false;
+    } else {
+        ws_treat(k, s, pr, ra, ca, C1);
+    }
+    const double cn = fm::cbrt_fast(fm::div_small(s.V, k.sphere, k.inv_sphere));
+#pragma unroll
+    for (int j = 0; j < 14; ++j) w[j] = w[j + 1];
+    w[14] = cn;
+    double mean;
+    if (t <= 15) {   // the window fills: numpy's pairwise sum is a running sum plus one 8-leaf tree at t = 8
+        s.S = (t == 8) ? ws_tree8(w[7], w[8], w[9], w[10], w[11], w[12], w[13], w[14]) : __dadd_rn(s.S, cn);
+        mean = fm::div_small(s.S, (double)t, fm::kInvN[t & 15]);
+    } else {
+        double r = ws_tree8(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int j = 8; j < 15; ++j) r = __dadd_rn(r, w[j]);
+        mean = fm::div_small(r, 15.0, k.inv15);
+    }
+    const double z = __dmul_rn(p.nb, __dsub_rn(__dmul_rn(mean, 2.0), p.si));
+    double g1 = __dadd_rn(1.0, __dmul_rn(p.rho, fm::log_ratio(k.f, p.K, s.V)));
+    g1 = __dsub_rn(g1, __dmul_rn(p.beta_c, C1));
+    g1 = __dsub_rn(g1, ra ? p.rd : 0.0);
+    g1 = __dadd_rn(g1, nz);
+    double Vn = __dmul_rn(s.V, g1);
+    const bool act = s.alive && (t < Tm1);
+    const bool death = Vn > k.death;
+    Vn = death ? k.death : Vn;
+    const double x = __dmul_rn(Vn, k.ndensity);
+    bool recov = false;
+    if (WsUrLazy<UR>::value) {
+        if (act && !(x <= -40.0)) {
+            const double ur = ws_ur_value(ur_in);
+            recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
+        }
+    } else {
+        const double ur = ws_ur_value(ur_in);
+        if (act && !(x <= -40.0 && ur >= 1e-17))
+            recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
+    }
+    recov = recov && !death;
+    Vn = recov ? 0.0 : Vn;
+    oV = Vn; oC = C1;
+    oF = s.flp | (ca ? 1u : 0u) | (ra ? 2u : 0u);
+    s.flp = (death ? 4u : 0u) | (recov ? 8u : 0u);
+    s.V = Vn; s.Cq = C1; s.zq = z; s.ucp = uc; s.udp = ud;
+    s.t_end = act ? t : s.t_end;
+    s.alive = act && !(death || recov);
+}
+
+template <int STATS, int MINB>
+__global__ void __launch_bounds__(RNG_WARPS * 32, MINB)
+sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int64_t pstride, int64_t mstride, int T, SimC c,
+                        const double *__restrict__ params, uint32_t seed_lo, uint32_t seed_hi, int64_t patient_base,
+                        uint8_t *__restrict__ codes_out, int64_t code_pitch, double *__restrict__ seq_len_out,
+                        double *__restrict__ pmom_out, const double *__restrict__ static_feature, StatsWorkspace *ws)
+{
+    constexpr bool GRAM = STATS == 1, SIDE = STATS == 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ double block_acc[GRAM ? RNG_WARPS : 1][STATS_PAD];
+    __shared__ unsigned int s_is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *vt = smem_al + (size_t)warp * rng2_warp_bytes(T);                  // [32 x 128 B], swizzled
+    uint8_t *nz_row = vt + RNG2_VOL_BYTES + lane * RNG2_SCRATCH_PITCH;           // this patient's 8 noise terms
+    uint8_t *uc_row = nz_row + 32 * RNG2_SCRATCH_PITCH;                          // ... chemo uniforms
+    uint8_t *ud_row = uc_row + 32 * RNG2_SCRATCH_PITCH;                          // ... radio uniforms
+    uint32_t *ct = reinterpret_cast<uint32_t *>(vt + RNG2_VOL_BYTES + RNG2_SCRATCH_BYTES);   // [32][code_words]
+    const int code_words = rng_code_words(T), copy_words = rng_code_copy_words(T);
+    uint8_t *crow = reinterpret_cast<uint8_t *>(ct + lane * code_words);
+
+    if (GRAM) {
+        for (int j = tid; j < RNG_WARPS * STATS_PAD; j += RNG_WARPS * 32) (&block_acc[0][0])[j] = 0.0;
+        __syncthreads();
+    }
+    if (lane == 0) tma_prefetch_desc(&vmap);
+    for (int j = 0; j < code_words; ++j) reinterpret_cast<uint32_t *>(crow)[j] = 0u;   // bytes >= T-1 stay zero
+
+    WsK k;
+    k.f = fm::consts();
+    k.sphere = c.sphere; k.inv_sphere = c.inv_sphere; k.decay = c.decay; k.dose = c.chemo_amt; k.death = c.death;
+    k.ndensity = -c.density; k.inv15 = fm::kInvN[15];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pin(k.f.lg[i]);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pin(k.f.ec[i]);
+    pin(k.f.ln2hi); pin(k.f.ln2lo); pin(k.f.sqrt2); pin(k.f.log2e);
+    pin(k.sphere); pin(k.inv_sphere); pin(k.decay); pin(k.dose); pin(k.death); pin(k.ndensity); pin(k.inv15);
+
+    const uint32_t row_off = (uint32_t)lane * 128u, row_x = (uint32_t)lane & 7u;
+    const int Tm1 = T - 1;
+    const int nboxes = (T + 15) >> 4;
+    const double inv_dt = 1.0 / c.fd_dt;
+    const int64_t ntiles = (n + 31) / 32;
+
+    for (int64_t tile = (int64_t)blockIdx.x * RNG_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * RNG_WARPS) {
+        const int64_t patient = tile * 32 + lane;
+        const bool exists = patient < n;
+        const int64_t pi = exists ? patient : 0;
+        const int64_t gp = patient_base + patient;
+        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi};
+
+        WsPatient p;
+        WsState s;
+        WsSlow slow;
+        double w[15];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) w[j] = 0.0;
+        const double v0 = exists ? __ldg(params + pi) : 1.0;
+        const double alpha = __ldg(params + 1 * pstride + pi), beta = __ldg(params + 3 * pstride + pi);
+        const double Kcap = __ldg(params + 5 * pstride + pi);
+        const double ci = __ldg(params + 6 * pstride + pi), ri = __ldg(params + 7 * pstride + pi);
+        const double cb = __ldg(params + 8 * pstride + pi), rb = __ldg(params + 9 * pstride + pi);
+        p.rho = __ldg(params + 2 * pstride + pi);
+        p.beta_c = __ldg(params + 4 * pstride + pi);
+        p.K = fm::log_num(Kcap);
+        p.si = ri;
+        p.nb = -rb;
+        p.rd = __dadd_rn(__dmul_rn(alpha, c.radio_amt), __dmul_rn(beta, __dmul_rn(c.radio_amt, c.radio_amt)));
+        s.V = 1.0; s.Cq = s.zq = s.ucp = s.udp = s.S = 0.0; s.flp = 0u; s.alive = exists; s.t_end = 0;
+        const double vmax = fmax(v0, c.death);
+        const double dmax = 2.02 * cbrt(vmax * c.inv_sphere);
+        const double zmax = fabs(rb) * fmax(fabs(ri), fabs(dmax - ri));
+        const bool ok = (ci == ri) && (cb == rb) && (zmax <= 700.0) && (Kcap > 1e-300) && (Kcap < 1e300) &&
+                        (v0 > 1e-300) && (v0 < 1e300) && (c.window == 15);
+        const bool tile_slow = __any_sync(0xffffffffu, exists && !ok) != 0;
+        if (tile_slow) {
+            slow.p = load_patient(params, pstride, pi);
+            state_init(slow.s, exists);
+            slow.pg.clear(); slow.mom.clear();
+        }
+        PatientGram pg;
+        Moments mom;
+        pg.clear(); mom.clear();
+        double gVm1 = 0.0, gVm2 = 0.0;   // V[t-1], V[t-2]
+        unsigned gcm2 = 0u, g_nra = 0u;  // treatment of column t-2; radio applications so far
+
+        for (int m = 0; m < nboxes; ++m) {
+            uint8_t *buf = vt;
+            if (tile_slow) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                rng_slow_box<GRAM || SIDE>(buf, crow, lane, m, T, c, &slow, key);
+            } else {
+                for (int half = 0; half < 2; ++half) {
+                    const int tc0 = 16 * m + 8 * half;
+                    if (tc0 >= T) break;
+                    // ---- G: draws of the eight columns ----
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t tp = (uint32_t)(tc0 >> 1) + (uint32_t)q;
+                        double a, b;
+                        rng::noise_pair(key, tp, a, b);
+                        *reinterpret_cast<double *>(nz_row + 16 * q) = a;
+                        *reinterpret_cast<double *>(nz_row + 16 * q + 8) = b;
+                        rng::uniform_pair(key, tp, 2u, a, b);
+                        *reinterpret_cast<double *>(uc_row + 16 * q) = a;
+                        *reinterpret_cast<double *>(uc_row + 16 * q + 8) = b;
+                        rng::uniform_pair(key, tp, 3u, a, b);
+                        *reinterpret_cast<double *>(ud_row + 16 * q) = a;
+                        *reinterpret_cast<double *>(ud_row + 16 * q + 8) = b;
+                    }
+                    // ---- S: the eight columns; the previous box has left the volume tile by now ----
+                    if (half == 0) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    int cend = T - tc0;
+                    cend = cend > 8 ? 8 : cend;
+#pragma unroll 1
+                    for (int cc = 0; cc < cend; ++cc) {
+                        const int t = tc0 + cc;
+                        double *pv = reinterpret_cast<double *>(buf + row_off + ((((uint32_t)(4 * half + (cc >> 1))) ^ row_x) << 4) + 8 * (cc & 1));
+                        const double nz = *reinterpret_cast<const double *>(nz_row + 8 * cc);
+                        const double uc = *reinterpret_cast<const double *>(uc_row + 8 * cc);
+                        const double ud = *reinterpret_cast<const double *>(ud_row + 8 * cc);
+                        const rng::LazyRecovery ur{&key, (uint32_t)(t >> 1), (uint32_t)(t & 1)};
+                        double oV, oC;
+                        unsigned oF;
+                        ws_col(t, Tm1, k, p, s, w, v0, nz, ur, uc, ud, oV, oC, oF);
+                        // columns after the last simulated one stay zero; oV belongs to column t, the treatment
+                        // outputs to column t-1
+                        oV = (t > s.t_end) ? 0.0 : oV;
+                        const bool dead_prev = t - 1 > s.t_end;
+                        oC = dead_prev ? 0.0 : oC;
+                        oF = dead_prev ? 0u : oF;
+                        const unsigned c1 = oF & 3u;
+                        if (GRAM) {
+                            // regression sample k = t-2 is complete: x[k+1] and the treatment of column k+1 are known
+                            ws_gram_sample(pg, t >= 2 && t - 2 <= s.t_end, t - 2 == s.t_end || c1 != gcm2, gVm2, gVm1, gcm2,
+                                           c.fd_dt, inv_dt);
+                            gVm2 = gVm1; gVm1 = oV; gcm2 = c1;
+                        }
+                        if (GRAM || SIDE) {
+                            mom.sv += oV; mom.svv += oV * oV;
+                            mom.sc += oC; mom.scc += oC * oC;
+                            g_nra += (oF >> 1) & 1u;
+                        }
+                        *pv = oV;
+                        if (t > 0) crow[t - 1] = (uint8_t)c1;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&vmap, 16 * m, (int)(tile * 32), buf);
+                tma_store_commit();
+            }
+        }
+        const int t_end = tile_slow ? slow.s.t_end : s.t_end;
+        if (exists) seq_len_out[patient] = (double)(t_end + 1);
+        if (SIDE && exists) {
+            const Moments &mm = tile_slow ? slow.mom : mom;
+            const double sd = tile_slow ? slow.mom.sd : c.radio_amt * (double)g_nra;
+            const double sdd = tile_slow ? slow.mom.sdd : c.radio_amt * c.radio_amt * (double)g_nra;
+            pmom_out[0 * mstride + patient] = mm.sv;  pmom_out[1 * mstride + patient] = mm.svv;
+            pmom_out[2 * mstride + patient] = mm.sc;  pmom_out[3 * mstride + patient] = mm.scc;
+            pmom_out[4 * mstride + patient] = sd;     pmom_out[5 * mstride + patient] = sdd;
+        }
+        if (GRAM) {
+            const double u = exists ? __ldg(static_feature + patient) : 0.0;
+            if (tile_slow) {
+                factual_finish<true>(c, slow.s, slow.pg);
+                fold_patient_stats(block_acc[warp], lane, slow.pg, slow.mom, u, exists, t_end + 1);
+            } else {
+                // the last sample k = T-2 (x[T-1] = 0 is the never-simulated column)
+                ws_gram_sample(pg, T - 2 <= s.t_end, true, gVm2, gVm1, gcm2, c.fd_dt, inv_dt);
+                mom.sd = c.radio_amt * (double)g_nra;
+                mom.sdd = c.radio_amt * c.radio_amt * (double)g_nra;
+                fold_patient_stats(block_acc[warp], lane, pg, mom, u, exists, t_end + 1);
+            }
+        }
+        __syncwarp();
+        if (codes_out != nullptr) {
+            const int units = copy_words >> 2;
+            const int rows = (n - tile * 32 < 32) ? (int)(n - tile * 32) : 32;
+            for (int e = lane; e < rows * units; e += 32) {
+                const int r = e / units, q = e - r * units;
+                const uint32_t *src = ct + r * code_words + 4 * q;
+                const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+                *reinterpret_cast<uint4 *>(codes_out + (tile * 32 + r) * code_pitch + 16 * q) = v;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (GRAM) stats_block_finish(block_acc, RNG_WARPS, ws, &s_is_last);
+}
+
 // the generator's draws as the four (N,T) arrays of the reference contract (noise already multiplied by 0.01):
 // thread = (patient, column pair), consecutive lanes -> consecutive 16 bytes of a row
 __global__ void __launch_bounds__(256)
@@ -285,7 +568,7 @@ philox_draws_kernel(int64_t n, int T, int64_t pitch, uint32_t seed_lo, uint32_t 
         const int64_t o = i * pitch + 2 * tp;
         rng::noise_pair(key, (uint32_t)tp, a, b);
         *reinterpret_cast<double2 *>(noise + o) = make_double2(a, b);
-        rng::uniform_pair(key, (uint32_t)tp, 1u, a, b);
+        rng::recovery_pair(key, (uint32_t)tp, a, b);
         *reinterpret_cast<double2 *>(rec + o) = make_double2(a, b);
         rng::uniform_pair(key, (uint32_t)tp, 2u, a, b);
         *reinterpret_cast<double2 *>(chemo + o) = make_double2(a, b);
@@ -294,14 +577,17 @@ philox_draws_kernel(int64_t n, int T, int64_t pitch, uint32_t seed_lo, uint32_t 
     }
 }
 
-template <int STATS, int MINB>
+template <int STATS, int MINB, int GEN = 2>
 static int launch_rng(const CUtensorMap &vmap, int64_t n, int64_t pstride, int64_t mstride, int T, const SimC &c,
                       const double *params, uint64_t seed,
                       int64_t patient_base, uint8_t *codes_out, int64_t code_pitch, double *seq_len, double *pmom,
                       const double *static_feature, StatsWorkspace *ws, cudaStream_t st)
 {
-    auto kern = sim_factual_rng_kernel<STATS, MINB>;
-    const int smem = RNG_WARPS * rng_warp_bytes(T) + 1024;
+    void (*kern)(const CUtensorMap, int64_t, int64_t, int64_t, int, SimC, const double *, uint32_t, uint32_t, int64_t, uint8_t *,
+                 int64_t, double *, double *, const double *, StatsWorkspace *);
+    if constexpr (GEN == 2) kern = sim_factual_rng2_kernel<STATS, MINB>;
+    else kern = sim_factual_rng_kernel<STATS, MINB>;
+    const int smem = RNG_WARPS * (GEN == 2 ? rng2_warp_bytes(T) : rng_warp_bytes(T)) + 1024;
     B200I_REQUIRE(smem <= 227 * 1024, B200I_E_UNSUPPORTED, "sim_factual_rng: T=%d does not fit in shared memory", T);
     B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;

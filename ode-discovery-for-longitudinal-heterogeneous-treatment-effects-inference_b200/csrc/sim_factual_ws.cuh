@@ -101,11 +101,19 @@ __device__ __forceinline__ void ws_treat(const WsK &k, const WsState &s, double 
     C1 = __dadd_rn(__dmul_rn(s.Cq, k.decay), ca ? k.dose : 0.0);                          // :338
 }
 
+// Recovery draw of a column.  The tiled kernel passes the value it loaded; the generator kernel passes a lazy draw:
+// its recovery uniforms lie in (0,1) with a smallest value of 2^-53 > exp(-40), so the draw can only matter when
+// -V * density > -40 (V < 6.9e-8, i.e. an eradicated tumour) and is generated in that rare branch only.
+__device__ __forceinline__ double ws_ur_value(double u) { return u; }
+__device__ __forceinline__ double ws_ur_value(const rng::LazyRecovery &u) { return u.get(); }
+template <class U> struct WsUrLazy { static constexpr bool value = false; };
+template <> struct WsUrLazy<rng::LazyRecovery> { static constexpr bool value = true; };
+
 // One loop body: volume of column t, treatment of column t-1, sigmoid argument of column t.
 // FILL: the window is still filling (t <= 15); J = position in the unrolled group of four.
-template <bool FILL, int J>
+template <bool FILL, int J, class UR>
 __device__ __forceinline__ void ws_body(int t, int Tm1, const WsK &k, const WsPatient &p, WsState &s, double (&w)[18],
-                                        double v0, double nz, double ur, double uc, double ud, double &oV,
+                                        double v0, double nz, const UR &ur_in, double uc, double ud, double &oV,
                                         double &oC, double &oP, unsigned &oF)
 {
     if (FILL && J == 0 && t == 0) {
@@ -152,8 +160,16 @@ __device__ __forceinline__ void ws_body(int t, int Tm1, const WsK &k, const WsPa
     // recovery: u < exp(-V * density); exp is below 4.3e-18 unless V < 6.9e-8             :346-349
     const double x = __dmul_rn(Vn, k.ndensity);
     bool recov = false;
-    if (act && !(x <= -40.0 && ur >= 1e-17))   // also taken for NaN, like the reference's comparison
-        recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
+    if (WsUrLazy<UR>::value) {
+        if (act && !(x <= -40.0)) {   // also taken for NaN, like the reference's comparison
+            const double ur = ws_ur_value(ur_in);
+            recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
+        }
+    } else {
+        const double ur = ws_ur_value(ur_in);
+        if (act && !(x <= -40.0 && ur >= 1e-17))   // also taken for NaN, like the reference's comparison
+            recov = (x >= 0.0) ? (x == x) : ((x > -40.0) ? (ur < fm::exp_fast(k.f, x)) : ws_recovery_rare(ur, x));
+    }
     recov = recov && !death;
     Vn = recov ? 0.0 : Vn;
     // outputs: volume and death/recovery bits of column t; treatment of column t-1

@@ -171,7 +171,7 @@ def philox_draws(n, T, seed, patient_base=0, pitch=None):
 
 def sim_factual_rng(params_dev, T, seed, patient_base=0, consts=None, volume=None, codes=None, sequence_lengths=None,
                     patient_moments=None, fused_static=None, fd_dt=STANDARD_DT, pitch=None, moments=True, tag="default",
-                    rows=None):
+                    rows=None, variant=0):
     """K1L: simulate_factual with device-generated draws (Philox4x32-10 counted by global patient index).
 
     Returns (volume (N,T) [row pitch `pitch`], codes (N, code_pitch) uint8 = chemo + 2*radio application,
@@ -204,9 +204,26 @@ def sim_factual_rng(params_dev, T, seed, patient_base=0, consts=None, volume=Non
     rc = lib.b200i_sim_factual_rng(n, T, vp, ctypes.byref(consts), off(params_dev, a), n_all, int(seed),
                                    int(patient_base) + a, off(volume, a * vp), off(codes, a * cp, 1), cp,
                                    off(sequence_lengths, a), off(patient_moments, a), n_all, off(fused_static, a),
-                                   float(fd_dt), _ptr(ws), _stream())
+                                   float(fd_dt), _ptr(ws), int(variant), _stream())
     _native.check(rc, "b200i_sim_factual_rng")
     return volume, codes, sequence_lengths, patient_moments, (ws[:STATS_DOUBLES] if ws is not None else None)
+
+
+def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, seed, patient_base, consts, volume, codes,
+                        sequence_lengths, patient_moments, chunks, copy_stream):
+    """Pinned host parameters -> chunked H2D on copy_stream, each chunk simulated (K1L) on the current stream as soon
+    as it has arrived (b200i_upload_simulate_rng)."""
+    lib = _native.load()
+    n = params_dev.shape[1]
+    assert params_host.is_pinned() and params_host.is_contiguous() and tuple(params_host.shape) == (10, n)
+    assert static_host is None or (static_host.is_pinned() and static_host.is_contiguous())
+    vp = row_pitch(volume) if n > 1 else T
+    rc = lib.b200i_upload_simulate_rng(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
+                                       None if static_host is None else ctypes.c_void_p(static_host.data_ptr()),
+                                       _ptr(params_dev), _ptr(static_dev), int(seed), int(patient_base), _ptr_rows(volume),
+                                       _ptr(codes), int(codes.shape[1]), _ptr(sequence_lengths), _ptr(patient_moments),
+                                       int(chunks), ctypes.c_void_p(copy_stream.cuda_stream), _stream())
+    _native.check(rc, "b200i_upload_simulate_rng")
 
 
 def theta_gram_codes(cancer_volume, codes, sequence_lengths, static_feature, patient_moments, fd_dt=STANDARD_DT,

@@ -3,7 +3,7 @@
 Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123) with
 counter = (patient lo, patient hi, column // 2, stream) and key = (seed lo, seed hi); stream 0 -> Box-Muller noise
 pair (x 0.01), 1 recovery, 2 chemo, 3 radio uniforms; the top 52 bits of a 64-bit word fill the mantissa of a double
-in [1,2).  The block function is pinned to the Random123 known-answer vectors in tests/test_oracle.py.  The reference
+in [1,2) (the recovery stream adds 2^-53: bin centres).  The block function is pinned to the Random123 known-answer vectors in tests/test_oracle.py.  The reference
 itself draws from numpy's global MT19937 stream (cancer_simulation.py:275-279); this generator only exists in
 throughput mode, so parity with the reference goes through b200i_philox_draws -> b200i_sim_factual.
 """
@@ -48,6 +48,8 @@ def draw_factual(n, T, seed, patient_base=0):
             rad = 0.01 * np.sqrt(-2.0 * np.log(2.0 - a))
             ang = np.pi * (2.0 * (b - 1.0))
             ev, od = rad * np.cos(ang), rad * np.sin(ang)
+        elif s == 1:      # recovery: bin centres, in (0,1)
+            ev, od = (a - 1.0) + 2.0 ** -53, (b - 1.0) + 2.0 ** -53
         else:
             ev, od = a - 1.0, b - 1.0
         arr = np.empty((n, T))

@@ -23,7 +23,8 @@ for name, kw in (("plain", dict(moments=False)), ("moments", dict(patient_moment
     for i in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = dev.sim_factual_rng(block, T, 1234, volume=vol, codes=codes, sequence_lengths=sl, **kw)
+        out = dev.sim_factual_rng(block, T, 1234, volume=vol, codes=codes, sequence_lengths=sl,
+                                  variant=int(os.environ.get('VARIANT', '0')), **kw)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(name, "ms per launch:", ["%.3f" % t for t in ts], "mean seq len", sl.mean().item(), flush=True)

@@ -49,7 +49,10 @@ def test_sim_factual_rng_equals_k1_on_exported_draws(dev, n, T, pitch, slow):
     draws = dev.philox_draws(n, T, seed, patient_base=base, pitch=pitch)
     out, _ = dev.sim_factual(pd_, *draws, T)
     vol, codes, sl, pm, _ = dev.sim_factual_rng(pd_, T, seed, patient_base=base, pitch=pitch)
+    g1 = dev.sim_factual_rng(pd_, T, seed, patient_base=base, pitch=pitch, variant=1)   # first-generation kernel
     torch.cuda.synchronize()
+    for a, b in zip((vol, codes, sl, pm), g1):
+        assert torch.equal(a, b)
     assert torch.equal(vol, out['cancer_volume'])
     assert torch.equal(sl, out['sequence_lengths'])
     want = (out['chemo_application'] + 2 * out['radio_application']).to(torch.uint8)
@@ -92,12 +95,14 @@ def test_sim_factual_rng_fused_statistics(dev, slow):
                            out['sequence_lengths'], static, out['chemo_dosage'], out['radio_dosage'], tag="r0").clone()
     vol, codes, sl, pm, fused = dev.sim_factual_rng(pd_, T, 5, fused_static=static, tag="r1")
     fused = fused.clone()
+    fused1 = dev.sim_factual_rng(pd_, T, 5, fused_static=static, tag="r3", variant=1)[4].clone()
     vol2, codes2, sl2, pm2, _ = dev.sim_factual_rng(pd_, T, 5)
     lean = dev.theta_gram_codes(vol2, codes2, sl2, static, pm2, tag="r2").clone()
     torch.cuda.synchronize()
     assert torch.equal(vol, vol2) and torch.equal(codes, codes2)
     a, f, l = alone.cpu().numpy(), fused.cpu().numpy(), lean.cpu().numpy()
     np.testing.assert_allclose(f, a, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(fused1.cpu().numpy(), a, rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(l, a, rtol=1e-12, atol=1e-9)
     assert np.array_equal(dev.unpack_stats(f)['count'], dev.unpack_stats(a)['count'])
     ca, sa = dev.stlsq_population(alone)
@@ -115,3 +120,28 @@ def test_sim_factual_rng_argument_errors(dev):
         dev.sim_factual_rng(pd_, 61, 1, volume=dev.alloc_rows(64, 61, 62))
     with pytest.raises(RuntimeError, match="code_pitch"):
         dev.sim_factual_rng(pd_, 60, 1, codes=torch.empty((64, 60), dtype=torch.uint8, device='cuda'))
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
+    """GeneratedFitPipeline.step_host (pinned host parameters, chunked H2D overlapped with K1L through
+    b200i_upload_simulate_rng) == step_device on resident parameters: cohort and statistics bit for bit."""
+    import torch
+    from b200_insite.cohort import GeneratedFitPipeline
+    n, T = 4133, 60
+    params = _cohort(n, 85)
+    block = torch.from_numpy(dev.pack_params(params)).pin_memory()
+    static = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.float64)).pin_memory()
+    a = GeneratedFitPipeline(n, T, seed=3, patient_base=1000, chunks=chunks)
+    b = GeneratedFitPipeline(n, T, seed=3, patient_base=1000)
+    b.params.copy_(block); b.static.copy_(static)
+    res = torch.zeros(32 + dev.STATS_DOUBLES, dtype=torch.float64).pin_memory()
+    a.step_host(block, static, res)
+    coefs = b.step_device()
+    torch.cuda.synchronize()
+    assert a.chunks == len(a.bounds) <= chunks
+    assert torch.equal(a.volume, b.volume) and torch.equal(a.codes, b.codes)
+    assert torch.equal(a.sequence_lengths, b.sequence_lengths) and torch.equal(a.patient_moments, b.patient_moments)
+    assert torch.equal(a.stats, b.stats)
+    assert np.array_equal(res[:16].numpy().reshape(4, 4), coefs.cpu().numpy())
+    assert np.array_equal(res[32:].numpy(), b.stats.cpu().numpy())
