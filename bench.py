@@ -29,6 +29,8 @@ K1_BYTES_PER_PATIENT = lambda T: 4 * T * 8 + 9 * T * 8 + 10 * 8 + 8      # SURVE
 K4_BYTES_PER_PATIENT = lambda T: 3 * T * 8 + 8 + 8                         # 1456 B at T=60
 K1_KERNELS = {"pitched": "sim_factual_ws<32,1,11,0>",   # csrc/sim_factual_ws.cuh, variant 12 (128-byte-aligned rows)
               "dense": "sim_factual_ws<32,2,6,0>"}      # variant 10 (dense 480-byte rows)
+K1_SIDE_KERNELS = {"pitched": "sim_factual_ws<32,1,11,0,side>", "dense": "sim_factual_ws<32,2,6,0,side>"}   # + lean-fit side outputs
+K1L_KERNEL = "sim_factual_rng2_kernel<2,4>"             # csrc/sim_factual_rng.cuh: draws generated in registers
 K1_SIDE_BYTES_PER_PATIENT = lambda T: ((T + 15) // 16) * 16 + 6 * 8    # lean fit: code bytes + six moment sums written
 K4_KERNEL = "theta_gram2_kernel<codes>"     # csrc/theta_gram.cu, fed by the simulator's side outputs (lean fit)
 K4_LEAN_BYTES_PER_PATIENT = lambda T: T * 8 + ((T + 15) // 16) * 16 + 8 + 8 + 6 * 8   # volume row, code bytes, seq_len, type, moments
@@ -40,6 +42,14 @@ def ncu_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def ncu_entry(kernel):
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))[kernel]
     except Exception:
         return None
 
@@ -305,7 +315,6 @@ def run_b200(args):
         pipe.step_host(h_block, h_static, h_draws, h_result)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    clocks.stop.set(); clocks.t.join(timeout=6)
     te = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -344,6 +353,7 @@ def run_b200(args):
         gen.step_host(h_block, h_static, h_result)
     barrier()
     gen_e2e_ms = 1e3 * (time.perf_counter() - t0) / gen_e2e_steps
+    clocks.stop.set(); clocks.t.join(timeout=6)
     gen_coefs = h_result[:16].numpy().reshape(4, 4).copy()
     tg = torch.tensor([gen_ms, gen_e2e_ms, -gen_exec], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -357,10 +367,14 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         k1 = float(np.mean(k1_ms))
+        k1_name = (K1_SIDE_KERNELS if pipe.lean_fit else K1_KERNELS)[args.layout]
         # algorithmic bytes stay the reference I/O contract's; the lean fit's side outputs (112 B/patient) are extra
         achieved = K1_BYTES_PER_PATIENT(T) * n / (k1 / 1e3) / 1e9
         k4 = float(np.mean(k4_ms))
-        k4_bytes = (K4_LEAN_BYTES_PER_PATIENT(T) if pipe.lean_fit else K4_BYTES_PER_PATIENT(T)) * n
+        # algorithmic bytes = SURVEY.md 8(d)'s per-patient figure for the Gram reduction (volume + the two application
+        # arrays + sequence length + patient type = 1456 B at T=60); the lean launch actually reads less than that
+        k4_bytes = K4_BYTES_PER_PATIENT(T) * n
+        k4_read = (K4_LEAN_BYTES_PER_PATIENT(T) if pipe.lean_fit else (5 * T * 8 + 16)) * n
         achieved4 = k4_bytes / (k4 / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -390,15 +404,17 @@ def run_b200(args):
                                            "arrays of the K1 contract -> H2D -> K1,K4,K5 -> D2H (PCIe-bound: 2 GB of "
                                            "draws per step)"},
                 "device_rng": {"value": gen_exec_all / (gen_ms / 1e3), "unit": UNIT, "ms_per_step": gen_ms,
-                               "kernel": "sim_factual_rng_kernel<2,3>", "kernel_ms": k1l_ms,
-                               "bound": "instruction issue / FP64 pipe (0.63 KB of HBM traffic per patient)",
+                               "kernel": K1L_KERNEL, "kernel_ms": k1l_ms,
+                               "bound": "FP64 dependent-issue latency / instruction issue (0.68 KB of HBM traffic per "
+                                        "patient); ncu: profiles/r1_k1l_gen2_ncu.txt",
+                               "ncu": ncu_entry(K1L_KERNEL),
                                "hbm_bytes_per_launch": (80 + T * 8 + ((T + 15) // 16) * 16 + 8 + 48) * n,
                                "what": "GeneratedFitPipeline.step_device: parameters resident, draws generated in the "
                                        "simulator kernel, lean cohort (volume + code bytes + moments) -> fit",
                                "population_coefs": gen_coefs.tolist()},
                 "gpu_launches": pipe.launches_per_step * args.steps,
-                "roofline": {"bound": "hbm", "kernel": K1_KERNELS[args.layout], "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(K1_KERNELS[args.layout]),
+                "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(k1_name),
                              "peak_source": peak_src, "kernel_ms": k1,
                              "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n,
                              "share_of_step": k1 / ms_per_step,
@@ -412,6 +428,7 @@ def run_b200(args):
                 "roofline_theta_gram": {"bound": "hbm", "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
                                         "unit": "GB/s", "frac": achieved4 / peak, "traffic": ncu_traffic(K4_KERNEL),
                                         "kernel_ms": k4, "algorithmic_bytes_per_launch": k4_bytes,
+                                        "bytes_read_per_launch": k4_read, "read_gbs": k4_read / (k4 / 1e3) / 1e9,
                                         "note": ("lean fit: the simulator kernel also writes one treatment-code byte per "
                                                  "step and six per-patient moment sums (68 MB + 48 MB per 1M patients, "
                                                  "inside its own time above); this launch reads the volumes and those "

@@ -140,12 +140,15 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
 //     shuffle / shared-memory / ordered-grid reduction runs once per thread at the end
 // ------------------------------------------------------------------------------------------------
 constexpr int G2_WARPS = 4;
+// packed slot -> (power of the static feature u, per-patient sum {n, sum x, sum x^2, sum xdot, sum x xdot}); cf. expand_gram
+__device__ const unsigned char kSlotPower[B200I_GRAM_PER_TREATMENT] = {0, 0, 1, 1, 0, 1, 1, 2, 2, 2, 0, 0, 1, 1, 0};
+__device__ const unsigned char kSlotMoment[B200I_GRAM_PER_TREATMENT] = {0, 1, 0, 1, 2, 1, 2, 0, 1, 2, 3, 4, 3, 4, 0};
 
 // CODES: the lean fit of the device pipeline -- treatment codes (one byte per step) and six per-patient moment sums
 // written by the simulator kernel (b200i_sim_factual_side) replace the two application and two dosage arrays:
 // 0.6 instead of 2.4 GB per million patients.
 template <int MAXT, bool CODES>
-__global__ void __launch_bounds__(G2_WARPS * 32, 2)
+__global__ void __launch_bounds__(G2_WARPS * 32, CODES ? 3 : 2)   // the five-array form keeps 32 loads in flight per thread
 theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double inv_dt, const double *__restrict__ vol,
                    const double *__restrict__ chemo, const double *__restrict__ radio,
                    const double *__restrict__ seq_len, const double *__restrict__ static_feature,
@@ -154,7 +157,7 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t bars[G2_WARPS];
-    __shared__ double block_acc[STATS_MAX_WARPS][STATS_PAD];
+    __shared__ double block_acc[G2_WARPS][STATS_PAD];
     __shared__ unsigned int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pitch = T * 8 + 16;                                   // volume row pitch (bytes)
@@ -162,17 +165,18 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
     uint8_t *s_vol = smem_raw + (size_t)warp * warp_bytes;          // [32][pitch]
     uint8_t *s_code = s_vol + 32 * pitch;                           // [T][33]
 
-    for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += blockDim.x) (&block_acc[0][0])[j] = 0.0;
+    for (int j = tid; j < G2_WARPS * STATS_PAD; j += blockDim.x) (&block_acc[0][0])[j] = 0.0;
     if (lane == 0) mbar_init(&bars[warp], 32);
     mbar_fence_init();
     __syncthreads();
 
-    double acc[4][B200I_GRAM_PER_TREATMENT];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) acc[a][j] = 0.0;
+    // Population sums.  A patient contributes its 20 sums s[a][m] times 1, u, u^2 (u = static feature).  Instead of
+    // 60 expanded accumulators per thread (120 registers, which capped the kernel at 8 warps per SM), the 32
+    // patients of a tile are reduced through shared memory: lane j < 20 owns sum j = (treatment, moment) and adds
+    // the tile's 32 values in patient order with the three weights -- 3 accumulators per lane, fixed order.
+    double A0 = 0.0, A1 = 0.0, A2 = 0.0;
     double mv = 0, mvv = 0, mc = 0, mcc = 0, md = 0, mdd = 0, mcnt = 0, mrows = 0;
+    double *s_red = reinterpret_cast<double *>(s_vol);   // [20][33] sums + [32] u: aliases the volume tile after the walk
 
     const int64_t ntiles = (n + 31) / 32;
     const int half = T / 2;
@@ -315,21 +319,44 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
                 mv += x; mvv += x * x;
             }
             mcnt += (double)Ls; mrows += 1.0;
+            __syncwarp();   // every lane has finished reading its volume row
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                double g[B200I_GRAM_PER_TREATMENT];
-                expand_gram(pg.s[a], u, g);
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) acc[a][j] += g[j];
+                for (int m = 0; m < 5; ++m) s_red[(a * 5 + m) * 33 + lane] = pg.s[a][m];
+            s_red[20 * 33 + lane] = u;
+        } else {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 20; ++j) s_red[j * 33 + lane] = 0.0;
+            s_red[20 * 33 + lane] = 0.0;
+        }
+        __syncwarp();
+        if (lane < 20) {
+            const double *mine = s_red + lane * 33, *us = s_red + 20 * 33;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                const double v = mine[q], uq = us[q];
+                A0 += v;
+                A1 = fma(uq, v, A1);
+                A2 = fma(uq * uq, v, A2);
             }
         }
         __syncwarp();   // the warp's tile is reused by its next iteration
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j)
-            warp_acc_add(block_acc[warp], a * B200I_GRAM_PER_TREATMENT + j, acc[a][j], lane);
+    // lane j holds the sums of (treatment j / 5, moment j % 5) with weights 1, u, u^2 -> packed layout of b200i.h:
+    // G00 G01 G02 G03 G11 G12 G13 G22 G23 G33 | b0 b1 b2 b3 | count  per treatment (Theta = [1, x, u, x u])
+    {
+        double *fin = s_red;   // [3][20]
+        __syncwarp();
+        if (lane < 20) { fin[lane] = A0; fin[20 + lane] = A1; fin[40 + lane] = A2; }
+        __syncwarp();
+        for (int idx = lane; idx < 4 * B200I_GRAM_PER_TREATMENT; idx += 32) {
+            const int a = idx / B200I_GRAM_PER_TREATMENT, sl = idx - a * B200I_GRAM_PER_TREATMENT;
+            block_acc[warp][idx] += fin[kSlotPower[sl] * 20 + a * 5 + kSlotMoment[sl]];
+        }
+        __syncwarp();
+    }
     const int m0 = 4 * B200I_GRAM_PER_TREATMENT;
     warp_acc_add(block_acc[warp], m0 + 0, mv, lane);  warp_acc_add(block_acc[warp], m0 + 1, mvv, lane);
     warp_acc_add(block_acc[warp], m0 + 2, mc, lane);  warp_acc_add(block_acc[warp], m0 + 3, mcc, lane);
