@@ -66,16 +66,17 @@ __device__ __forceinline__ void recovery_pair(const PairKey &k, uint32_t tp, dou
     u_odd = __dadd_rn(__dsub_rn(mant12(r.z, r.w), 1.0), 0x1p-53);
 }
 
-// recovery draw of one column, generated on demand
+// recovery draw of one column, generated on demand (rare: kept out of line so that the callers' loops stay small)
+__device__ __noinline__ double recovery_draw(uint32_t p_lo, uint32_t p_hi, uint32_t k0, uint32_t k1, uint32_t tp, uint32_t odd)
+{
+    double a, b;
+    recovery_pair(PairKey{p_lo, p_hi, k0, k1}, tp, a, b);
+    return odd ? b : a;
+}
 struct LazyRecovery {
     const PairKey *key;
     uint32_t tp, odd;
-    __device__ __forceinline__ double get() const
-    {
-        double a, b;
-        recovery_pair(*key, tp, a, b);
-        return odd ? b : a;
-    }
+    __device__ __forceinline__ double get() const { return recovery_draw(key->p_lo, key->p_hi, key->k0, key->k1, tp, odd); }
 };
 
 // the two noise terms 0.01 * N(0,1) of column pair tp (stream 0)

@@ -274,8 +274,8 @@ sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int6
 // into two short loops that each fit the L0 cache:
 //   G  (per column pair, ~350 instructions): Philox + Box-Muller -> noise, chemo and radio draws into a small
 //      per-warp scratch (72-byte pitch: conflict-free 8-byte accesses);
-//   S  (per column, ~300 instructions): ws_col = the column arithmetic of ws_body with the diameter window shifted
-//      by one register per column (14 moves) instead of four unrolled copies with static window offsets.
+//   S  (per column pair): ws_col = the column arithmetic of ws_body, two unrolled columns with static window
+//      offsets, the 17-slot diameter window shifted by two once per pair.
 // Same draws, same arithmetic, same outputs as the first kernel, bit for bit.
 // ------------------------------------------------------------------------------------------------
 constexpr int RNG2_SCRATCH_PITCH = 72;                               // bytes per patient row, 8 columns + pad
@@ -287,36 +287,38 @@ __host__ __device__ inline int rng2_warp_bytes(int T)
     return (RNG2_VOL_BYTES + RNG2_SCRATCH_BYTES + 32 * rng_code_words(T) * 4 + 1023) & ~1023;
 }
 
-// one column: volume of column t, treatment of column t-1, sigmoid argument of column t (see ws_body)
-template <class UR>
-__device__ __forceinline__ void ws_col(int t, int Tm1, const WsK &k, const WsPatient &p, WsState &s, double (&w)[15],
+// one column: volume of column t, treatment of column t-1, sigmoid argument of column t (see ws_body).
+// J = position in the unrolled column pair.  The diameter window lives in w[17]: before the pair w[0..14] are the 15
+// most recent cube roots (oldest first); column J appends its own at w[15 + J] and reads w[1 + J .. 15 + J]; the
+// caller shifts the file by two once per pair (7.5 register-pair moves per column).
+template <int J, class UR>
+__device__ __forceinline__ void ws_col(int t, int Tm1, const WsK &k, const WsPatient &p, WsState &s, double (&w)[17],
                                        double v0, double nz, const UR &ur_in, double uc, double ud, double &oV,
                                        double &oC, unsigned &oF)
 {
-    if (t == 0) {
+    if (J == 0 && t == 0) {
         oV = v0; oC = 0.0; oF = 0u;
         s.V = v0;
         return;
     }
     double pr, C1;
     bool ra, ca;
-    if (t == 1) {
+    if (J == 1 && t == 1) {
         pr = 0.0; C1 = 0.0; ra = ca = false;
     } else {
         ws_treat(k, s, pr, ra, ca, C1);
     }
     const double cn = fm::cbrt_fast(fm::div_small(s.V, k.sphere, k.inv_sphere));
-#pragma unroll
-    for (int j = 0; j < 14; ++j) w[j] = w[j + 1];
-    w[14] = cn;
+    w[15 + J] = cn;
     double mean;
     if (t <= 15) {   // the window fills: numpy's pairwise sum is a running sum plus one 8-leaf tree at t = 8
-        s.S = (t == 8) ? ws_tree8(w[7], w[8], w[9], w[10], w[11], w[12], w[13], w[14]) : __dadd_rn(s.S, cn);
+        s.S = (J == 0 && t == 8) ? ws_tree8(w[8 + J], w[9 + J], w[10 + J], w[11 + J], w[12 + J], w[13 + J], w[14 + J], w[15 + J])
+                                 : __dadd_rn(s.S, cn);
         mean = fm::div_small(s.S, (double)t, fm::kInvN[t & 15]);
     } else {
-        double r = ws_tree8(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        double r = ws_tree8(w[1 + J], w[2 + J], w[3 + J], w[4 + J], w[5 + J], w[6 + J], w[7 + J], w[8 + J]);
 #pragma unroll
-        for (int j = 8; j < 15; ++j) r = __dadd_rn(r, w[j]);
+        for (int j = 8; j < 15; ++j) r = __dadd_rn(r, w[1 + J + j]);
         mean = fm::div_small(r, 15.0, k.inv15);
     }
     const double z = __dmul_rn(p.nb, __dsub_rn(__dmul_rn(mean, 2.0), p.si));
@@ -405,9 +407,9 @@ sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int
         WsPatient p;
         WsState s;
         WsSlow slow;
-        double w[15];
+        double w[17];
 #pragma unroll
-        for (int j = 0; j < 15; ++j) w[j] = 0.0;
+        for (int j = 0; j < 17; ++j) w[j] = 0.0;
         const double v0 = exists ? __ldg(params + pi) : 1.0;
         const double alpha = __ldg(params + 1 * pstride + pi), beta = __ldg(params + 3 * pstride + pi);
         const double Kcap = __ldg(params + 5 * pstride + pi);
@@ -470,36 +472,43 @@ sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int
                     int cend = T - tc0;
                     cend = cend > 8 ? 8 : cend;
 #pragma unroll 1
-                    for (int cc = 0; cc < cend; ++cc) {
-                        const int t = tc0 + cc;
-                        double *pv = reinterpret_cast<double *>(buf + row_off + ((((uint32_t)(4 * half + (cc >> 1))) ^ row_x) << 4) + 8 * (cc & 1));
-                        const double nz = *reinterpret_cast<const double *>(nz_row + 8 * cc);
-                        const double uc = *reinterpret_cast<const double *>(uc_row + 8 * cc);
-                        const double ud = *reinterpret_cast<const double *>(ud_row + 8 * cc);
-                        const rng::LazyRecovery ur{&key, (uint32_t)(t >> 1), (uint32_t)(t & 1)};
-                        double oV, oC;
-                        unsigned oF;
-                        ws_col(t, Tm1, k, p, s, w, v0, nz, ur, uc, ud, oV, oC, oF);
-                        // columns after the last simulated one stay zero; oV belongs to column t, the treatment
-                        // outputs to column t-1
-                        oV = (t > s.t_end) ? 0.0 : oV;
-                        const bool dead_prev = t - 1 > s.t_end;
-                        oC = dead_prev ? 0.0 : oC;
-                        oF = dead_prev ? 0u : oF;
-                        const unsigned c1 = oF & 3u;
-                        if (GRAM) {
-                            // regression sample k = t-2 is complete: x[k+1] and the treatment of column k+1 are known
-                            ws_gram_sample(pg, t >= 2 && t - 2 <= s.t_end, t - 2 == s.t_end || c1 != gcm2, gVm2, gVm1, gcm2,
-                                           c.fd_dt, inv_dt);
-                            gVm2 = gVm1; gVm1 = oV; gcm2 = c1;
-                        }
-                        if (GRAM || SIDE) {
-                            mom.sv += oV; mom.svv += oV * oV;
-                            mom.sc += oC; mom.scc += oC * oC;
-                            g_nra += (oF >> 1) & 1u;
-                        }
-                        *pv = oV;
-                        if (t > 0) crow[t - 1] = (uint8_t)c1;
+                    for (int cc = 0; cc < cend; cc += 2) {   // T is even: whole pairs
+                        double *pv = reinterpret_cast<double *>(buf + row_off + ((((uint32_t)(4 * half + (cc >> 1))) ^ row_x) << 4));
+                        auto column = [&](auto jtag) {
+                            constexpr int J = decltype(jtag)::value;
+                            const int t = tc0 + cc + J;
+                            const double nz = *reinterpret_cast<const double *>(nz_row + 8 * (cc + J));
+                            const double uc = *reinterpret_cast<const double *>(uc_row + 8 * (cc + J));
+                            const double ud = *reinterpret_cast<const double *>(ud_row + 8 * (cc + J));
+                            const rng::LazyRecovery ur{&key, (uint32_t)(t >> 1), (uint32_t)J};
+                            double oV, oC;
+                            unsigned oF;
+                            ws_col<J>(t, Tm1, k, p, s, w, v0, nz, ur, uc, ud, oV, oC, oF);
+                            // columns after the last simulated one stay zero; oV belongs to column t, the treatment
+                            // outputs to column t-1
+                            oV = (t > s.t_end) ? 0.0 : oV;
+                            const bool dead_prev = t - 1 > s.t_end;
+                            oC = dead_prev ? 0.0 : oC;
+                            oF = dead_prev ? 0u : oF;
+                            const unsigned c1 = oF & 3u;
+                            if (GRAM) {
+                                // regression sample k = t-2 is complete: x[k+1] and the treatment of column k+1 are known
+                                ws_gram_sample(pg, t >= 2 && t - 2 <= s.t_end, t - 2 == s.t_end || c1 != gcm2, gVm2, gVm1,
+                                               gcm2, c.fd_dt, inv_dt);
+                                gVm2 = gVm1; gVm1 = oV; gcm2 = c1;
+                            }
+                            if (GRAM || SIDE) {
+                                mom.sv += oV; mom.svv += oV * oV;
+                                mom.sc += oC; mom.scc += oC * oC;
+                                g_nra += (oF >> 1) & 1u;
+                            }
+                            pv[J] = oV;
+                            if (t > 0) crow[t - 1] = (uint8_t)c1;
+                        };
+                        column(std::integral_constant<int, 0>{});
+                        column(std::integral_constant<int, 1>{});
+#pragma unroll
+                        for (int j = 0; j < 15; ++j) w[j] = w[j + 2];
                     }
                 }
             }
