@@ -151,7 +151,9 @@ B200I_API int b200i_stlsq_joint(const double *stats, double threshold, double al
  * uint8 = chemo + 2*radio application per step, and patient_moments_out (6, N) = per-patient sums over the active
  * entries of volume, volume^2, chemo dosage, its square, radio dosage, its square.  b200i_theta_gram_codes finishes
  * the population statistics from cancer_volume + those two (0.6 instead of 2.4 GB per million patients); same
- * statistics layout and reduction as b200i_theta_gram_mode.  code_pitch: multiple of 16, >= T rounded up to 16. */
+ * statistics layout and reduction as b200i_theta_gram_mode.  code_pitch: multiple of 16, >= T rounded up to 16;
+ * moments_stride: elements between the six rows of patient_moments (0 = n; larger when the launch covers a row range
+ * of a bigger cohort). */
 B200I_API int b200i_sim_factual_side(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
                       const double *params,
                       const double *noise, const double *recovery_rvs,
@@ -165,7 +167,7 @@ B200I_API int b200i_sim_factual_side(int64_t n, int32_t T, int64_t row_pitch, co
 B200I_API int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
                      const double *cancer_volume, const uint8_t *codes, int64_t code_pitch,
                      const double *sequence_lengths, const double *static_feature,
-                     const double *patient_moments, void *gram_workspace, void *stream);
+                     const double *patient_moments, int64_t moments_stride, void *gram_workspace, void *stream);
 /* K1L  simulate_factual with device-generated draws (throughput mode, SURVEY.md 8d "lean variant").
  * The reference draws its four (N,T) arrays from numpy's sequential global stream (cancer_simulation.py:275-279);
  * here they come from Philox4x32-10 counted by (patient_base + i, column / 2, stream) and keyed by `seed`
@@ -194,11 +196,15 @@ B200I_API int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, con
 /* Host-resident parameters: params_host (10,N) and static_host (N,) [or NULL] are PINNED HOST arrays; they are copied
  * into params / static_feature in `chunks` column ranges on copy_stream, and every range is simulated on `stream`
  * (b200i_sim_factual_rng with the per-patient moments) as soon as it has arrived, so the PCIe transfer overlaps the
- * simulation.  Same outputs as one b200i_sim_factual_rng launch over all N patients. */
+ * simulation.  Same outputs as one b200i_sim_factual_rng launch over all N patients.
+ * chunk_gram_workspaces != NULL (chunks x b200i_gram_workspace_bytes() bytes, with fd_dt > 0 and stats_out[68]): each
+ * range's share of the population statistics (b200i_theta_gram_codes) is launched right behind its simulation and the
+ * shares are summed in range order into stats_out, so only the last range's work is left when the copy ends. */
 B200I_API int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
                      const double *params_host, const double *static_host, double *params, double *static_feature,
                      uint64_t seed, int64_t patient_base, double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
                      double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                     double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                      void *copy_stream, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,

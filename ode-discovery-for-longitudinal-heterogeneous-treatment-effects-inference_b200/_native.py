@@ -39,12 +39,13 @@ SIGNATURES = {
     "b200i_sim_factual_side": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp] + [c_vp] * 4 +
                                [c_vp] * 10 + [c_vp, c_i64, c_vp, c_i32, c_vp]),
     "b200i_theta_gram_codes": (ctypes.c_int, [c_i64, c_i32, c_i64, c_i32, c_f64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp,
-                                              c_vp, c_vp]),
+                                              c_i64, c_vp, c_vp]),
     "b200i_philox_draws": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.c_uint64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200i_sim_factual_rng": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, c_i64, ctypes.c_uint64,
                                              c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_f64, c_vp, c_i32, c_vp]),
     "b200i_upload_simulate_rng": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, c_vp, c_vp, c_vp,
-                                                 ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
+                                                 ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_f64, c_vp, c_vp,
+                                                 c_vp, c_vp]),
     "b200i_gram_workspace_bytes": (c_i64, []),
     "b200i_theta_gram": (ctypes.c_int, [c_i64, c_i32, c_f64] + [c_vp] * 9),
     "b200i_stlsq_population": (ctypes.c_int, [c_vp, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp]),

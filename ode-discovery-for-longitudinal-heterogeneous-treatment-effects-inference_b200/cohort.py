@@ -182,6 +182,7 @@ class GeneratedFitPipeline:
         self.bounds = [(a, min(a + step, self.n)) for a in range(0, self.n, step)]   # what the C side will use
         self.chunks = len(self.bounds)
         self.copy_stream = torch.cuda.Stream()
+        self.chunk_ws = dev.chunk_workspaces(self.chunks)
         self.launches_per_step = len(self.bounds) + 2               # K1L per chunk + theta_gram_codes + stlsq_population
 
     def h2d_bytes(self):
@@ -206,12 +207,14 @@ class GeneratedFitPipeline:
 
     def step_host(self, params_block, static, result_host):
         """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.  The parameter
-        rows of chunk c+1 are copied on a second stream while chunk c is being simulated."""
+        rows of chunk c+1 are copied on a second stream while chunk c is being simulated and reduced to its share of
+        the population statistics; the shares are summed in chunk order (bits depend on the chunk count only)."""
         main = torch.cuda.current_stream()
         dev.upload_simulate_rng(params_block, static, self.params, self.static, self.T, self.seed, self.patient_base,
                                 self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
-                                self.chunks, self.copy_stream)
-        self._fit()
+                                self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats)
+        allreduce_stats(self.stats)
+        self.coefs, self.support = dev.stlsq_population(self.stats, self.threshold, self.alpha, self.max_iter)
         result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
         result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
         result_host[32:32 + dev.STATS_DOUBLES].copy_(self.stats, non_blocking=True)

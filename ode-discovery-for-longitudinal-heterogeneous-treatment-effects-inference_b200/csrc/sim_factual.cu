@@ -674,13 +674,28 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
 // Host parameters -> device, chunk by chunk on `copy_stream`, each chunk simulated on `stream` as soon as it has
 // arrived (events), so the PCIe transfer of chunk c+1 overlaps the simulation of chunk c.  One call replaces
 // ~12 framework calls per chunk of the Python pipeline (the step is ~2 ms: host-side launch cost matters).
+// sum of the per-chunk statistics in chunk order (fixed order => reproducible bits for a given chunk count)
+__global__ void sum_chunk_stats_kernel(const uint8_t *ws_base, size_t ws_stride, int chunks, double *out)
+{
+    const int i = threadIdx.x;
+    if (i >= B200I_STATS_DOUBLES) return;
+    double v = 0.0;
+    for (int c = 0; c < chunks; ++c) v += reinterpret_cast<const StatsWorkspace *>(ws_base + (size_t)c * ws_stride)->stats[i];
+    out[i] = v;
+}
+
 extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
                                          const double *params_host, const double *static_host, double *params,
                                          double *static_feature, uint64_t seed, int64_t patient_base,
                                          double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
                                          double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                                         double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                                          void *copy_stream, void *stream)
 {
+    const bool fit = chunk_gram_workspaces != nullptr;
+    B200I_REQUIRE(!fit || (stats_out && static_feature && codes_out && patient_moments_out && fd_dt > 0), B200I_E_ARG,
+                  "upload_simulate_rng: the per-chunk fit needs stats_out, static_feature, codes_out, patient_moments_out, fd_dt");
+    const size_t ws_stride = (size_t)b200i_gram_workspace_bytes();
     B200I_REQUIRE(n >= 0 && chunks >= 1 && chunks <= 64, B200I_E_ARG, "upload_simulate_rng: n=%lld chunks=%d (1..64)",
                   (long long)n, chunks);
     if (n == 0) return 0;
@@ -721,10 +736,18 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
                                        cancer_volume + a * row_pitch, codes_out ? codes_out + a * code_pitch : nullptr,
                                        code_pitch, sequence_lengths + a, patient_moments_out ? patient_moments_out + a : nullptr,
                                        n, nullptr, 0.0, nullptr, 0, run);
+        if (!rc && fit)   // the chunk's share of the population statistics, right behind its simulation
+            rc = b200i_theta_gram_codes(b - a, T, row_pitch, 0, fd_dt, cancer_volume + a * row_pitch, codes_out + a * code_pitch,
+                                        code_pitch, sequence_lengths + a, static_feature + a, patient_moments_out + a, n,
+                                        static_cast<uint8_t *>(chunk_gram_workspaces) + (size_t)c * ws_stride, run);
     }
     if (!rc && c > 1) {   // `stream` continues after the chunks of the second stream
         rc = check_cuda(cudaEventRecord(ev, sx), "cudaEventRecord");
         if (!rc) rc = check_cuda(cudaStreamWaitEvent(st, ev, 0), "cudaStreamWaitEvent");
+    }
+    if (!rc && fit) {
+        sum_chunk_stats_kernel<<<1, 96, 0, st>>>(static_cast<const uint8_t *>(chunk_gram_workspaces), ws_stride, c, stats_out);
+        rc = check_cuda(cudaGetLastError(), "sum_chunk_stats launch");
     }
     cudaEventDestroy(ev);   // deferred by the runtime until the recorded work has completed
     return rc;

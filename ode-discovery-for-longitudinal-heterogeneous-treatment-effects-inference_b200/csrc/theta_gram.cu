@@ -153,7 +153,7 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
                    const double *__restrict__ chemo, const double *__restrict__ radio,
                    const double *__restrict__ seq_len, const double *__restrict__ static_feature,
                    const double *__restrict__ chemo_dos, const double *__restrict__ radio_dos, StatsWorkspace *ws,
-                   const uint8_t *__restrict__ codes, int64_t code_pitch, const double *__restrict__ pmom)
+                   const uint8_t *__restrict__ codes, int64_t code_pitch, const double *__restrict__ pmom, int64_t mstride)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t bars[G2_WARPS];
@@ -206,9 +206,9 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
             }
             if (lane < rows) {   // the simulator's per-patient sums over the active entries
                 const int64_t pidx = first + lane;
-                mv += __ldg(pmom + 0 * n + pidx);  mvv += __ldg(pmom + 1 * n + pidx);
-                mc += __ldg(pmom + 2 * n + pidx);  mcc += __ldg(pmom + 3 * n + pidx);
-                md += __ldg(pmom + 4 * n + pidx);  mdd += __ldg(pmom + 5 * n + pidx);
+                mv += __ldg(pmom + 0 * mstride + pidx);  mvv += __ldg(pmom + 1 * mstride + pidx);
+                mc += __ldg(pmom + 2 * mstride + pidx);  mcc += __ldg(pmom + 3 * mstride + pidx);
+                md += __ldg(pmom + 4 * mstride + pidx);  mdd += __ldg(pmom + 5 * mstride + pidx);
             }
         }
         // the four other arrays, two columns per lane and row
@@ -446,8 +446,11 @@ extern "C" int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch,
 extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, int32_t mode, double fd_dt,
                                       const double *cancer_volume, const uint8_t *codes, int64_t code_pitch,
                                       const double *sequence_lengths, const double *static_feature,
-                                      const double *patient_moments, void *gram_workspace, void *stream)
+                                      const double *patient_moments, int64_t moments_stride, void *gram_workspace,
+                                      void *stream)
 {
+    if (moments_stride == 0) moments_stride = n;
+    B200I_REQUIRE(moments_stride >= n, B200I_E_ARG, "theta_gram_codes: moments_stride %lld < n", (long long)moments_stride);
     B200I_REQUIRE(n >= 0 && cancer_volume && codes && sequence_lengths && static_feature && patient_moments &&
                       gram_workspace,
                   B200I_E_ARG, "theta_gram_codes: NULL argument or negative n");
@@ -464,9 +467,17 @@ extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, i
     const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
     const size_t smem2 = warp_bytes * G2_WARPS;
     auto k2 = theta_gram2_kernel<256, true>;
-    B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    int per_sm2 = 0;
-    B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, G2_WARPS * 32, smem2));
+    static thread_local size_t cfg_smem[16];
+    static thread_local int cfg_per_sm[16];
+    int devid = 0;
+    B200I_CUDA(cudaGetDevice(&devid));
+    B200I_REQUIRE(devid >= 0 && devid < 16, B200I_E_UNSUPPORTED, "theta_gram_codes: device index %d", devid);
+    if (cfg_smem[devid] != smem2) {   // once per (device, T): this launch is issued per chunk by the upload pipeline
+        B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm[devid], k2, G2_WARPS * 32, smem2));
+        cfg_smem[devid] = smem2;
+    }
+    const int per_sm2 = cfg_per_sm[devid];
     B200I_REQUIRE(per_sm2 >= 1, B200I_E_UNSUPPORTED, "theta_gram_codes: T=%d does not fit in shared memory", T);
     const int64_t ntiles2 = (n + 31) / 32;
     int64_t grid2 = (int64_t)num_sms() * per_sm2;
@@ -475,7 +486,7 @@ extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, i
     if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
     k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, mode, fd_dt, 1.0 / fd_dt, cancer_volume, nullptr,
                                                       nullptr, sequence_lengths, static_feature, nullptr, nullptr, ws,
-                                                      codes, code_pitch, patient_moments);
+                                                      codes, code_pitch, patient_moments, moments_stride);
     return check_cuda(cudaGetLastError(), "theta_gram_codes launch");
 }
 
@@ -518,7 +529,7 @@ extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, in
                 if (grid2 > STATS_MAX_BLOCKS) grid2 = STATS_MAX_BLOCKS;
                 k2<<<(unsigned)grid2, G2_WARPS * 32, smem2, st>>>(n, T, row_pitch, mode, fd_dt, 1.0 / fd_dt, cancer_volume, chemo_application,
                                                                   radio_application, sequence_lengths, static_feature,
-                                                                  chemo_dosage, radio_dosage, ws, nullptr, 0, nullptr);
+                                                                  chemo_dosage, radio_dosage, ws, nullptr, 0, nullptr, 0);
                 return check_cuda(cudaGetLastError(), "theta_gram2 launch");
             }
         }

@@ -209,10 +209,18 @@ def sim_factual_rng(params_dev, T, seed, patient_base=0, consts=None, volume=Non
     return volume, codes, sequence_lengths, patient_moments, (ws[:STATS_DOUBLES] if ws is not None else None)
 
 
+def chunk_workspaces(chunks):
+    """Per-chunk statistics workspaces for upload_simulate_rng (zero-initialised once; the kernels reset them)."""
+    lib = _native.load()
+    return torch.zeros(int(chunks) * ((lib.b200i_gram_workspace_bytes() + 7) // 8), dtype=torch.float64, device='cuda')
+
+
 def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, seed, patient_base, consts, volume, codes,
-                        sequence_lengths, patient_moments, chunks, copy_stream):
+                        sequence_lengths, patient_moments, chunks, copy_stream, chunk_ws=None, stats_out=None,
+                        fd_dt=STANDARD_DT):
     """Pinned host parameters -> chunked H2D on copy_stream, each chunk simulated (K1L) on the current stream as soon
-    as it has arrived (b200i_upload_simulate_rng)."""
+    as it has arrived (b200i_upload_simulate_rng).  chunk_ws (chunk_workspaces(chunks)) + stats_out (68,): each
+    chunk's share of the population statistics is computed right behind its simulation and summed in chunk order."""
     lib = _native.load()
     n = params_dev.shape[1]
     assert params_host.is_pinned() and params_host.is_contiguous() and tuple(params_host.shape) == (10, n)
@@ -222,7 +230,8 @@ def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, see
                                        None if static_host is None else ctypes.c_void_p(static_host.data_ptr()),
                                        _ptr(params_dev), _ptr(static_dev), int(seed), int(patient_base), _ptr_rows(volume),
                                        _ptr(codes), int(codes.shape[1]), _ptr(sequence_lengths), _ptr(patient_moments),
-                                       int(chunks), ctypes.c_void_p(copy_stream.cuda_stream), _stream())
+                                       int(chunks), float(fd_dt), _ptr(chunk_ws), _ptr(stats_out),
+                                       ctypes.c_void_p(copy_stream.cuda_stream), _stream())
     _native.check(rc, "b200i_upload_simulate_rng")
 
 
@@ -235,7 +244,7 @@ def theta_gram_codes(cancer_volume, codes, sequence_lengths, static_feature, pat
     pitch = row_pitch(cancer_volume) if n > 1 else T
     rc = lib.b200i_theta_gram_codes(n, T, pitch, 1 if joint else 0, float(fd_dt), _ptr_rows(cancer_volume), _ptr(codes),
                                     int(codes.shape[1]), _ptr(sequence_lengths), _ptr(static_feature),
-                                    _ptr(patient_moments), _ptr(ws), _stream())
+                                    _ptr(patient_moments), int(patient_moments.shape[1]), _ptr(ws), _stream())
     _native.check(rc, "b200i_theta_gram_codes")
     return ws[:STATS_DOUBLES]
 

@@ -142,6 +142,11 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     assert a.chunks == len(a.bounds) <= chunks
     assert torch.equal(a.volume, b.volume) and torch.equal(a.codes, b.codes)
     assert torch.equal(a.sequence_lengths, b.sequence_lengths) and torch.equal(a.patient_moments, b.patient_moments)
-    assert torch.equal(a.stats, b.stats)
-    assert np.array_equal(res[:16].numpy().reshape(4, 4), coefs.cpu().numpy())
-    assert np.array_equal(res[32:].numpy(), b.stats.cpu().numpy())
+    # statistics: per-chunk shares summed in chunk order vs one launch (same values, different summation order)
+    np.testing.assert_allclose(a.stats.cpu().numpy(), b.stats.cpu().numpy(), rtol=1e-12, atol=1e-9)
+    assert np.array_equal(a.stats.cpu().numpy()[[14, 29, 44, 59, 66, 67]], b.stats.cpu().numpy()[[14, 29, 44, 59, 66, 67]])  # counts
+    assert np.array_equal(res[16:32].numpy().reshape(4, 4) != 0, b.support.cpu().numpy() != 0)
+    np.testing.assert_allclose(res[:16].numpy().reshape(4, 4), coefs.cpu().numpy(), rtol=1e-9, atol=1e-13)
+    assert np.array_equal(res[32:].numpy(), a.stats.cpu().numpy())
+    if chunks == 1:
+        assert torch.equal(a.stats, b.stats)
