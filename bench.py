@@ -364,6 +364,33 @@ def run_b200(args):
         gen_exec_all = gen_exec
     gen_ms, gen_e2e_ms = float(tg[0]), float(tg[1])
 
+    # ---- second half of BASELINE's metric: individualised per-patient fits and discovered-ODE rollouts (config C4) ----
+    indiv = None
+    if rank == 0:
+        def med(fn, reps=5):
+            out_ = fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); out_ = fn(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts)), out_
+        xv = gen.volume.contiguous()
+        cd = gen.codes[:, :T].contiguous()
+        fit_len = gen.sequence_lengths.to(torch.int32)
+        prior = gen.coefs.contiguous()
+        ms_fit, pc = med(lambda: dev.stlsq_batched(xv, cd, fit_len, gen.static, prior, 10.0))
+        x0 = xv[:, 0].contiguous(); cd1 = cd[:, :T - 1].contiguous()
+        ms_roll, pred = med(lambda: dev.ode_rollout(x0, gen.static, cd1, pc))
+        ms_roll32, pred32 = med(lambda: dev.ode_rollout(x0, gen.static, cd1, pc, fp32=True))
+        dev32 = float(((pred32 - pred).abs() / pred.abs().clamp_min(1e-3 * float(pred.abs().max()))).max().item())
+        indiv = {"what": "per-patient ridge-to-prior STLSQ fits (K5b, 16 coefficients per patient, FP64) on the generated "
+                         "cohort and 59-step discovered-ODE rollouts with the per-patient coefficients (K6)",
+                 "fits_per_s": n / (ms_fit / 1e3), "fit_ms": ms_fit,
+                 "rollout_patient_steps_per_s": n * (T - 1) / (ms_roll / 1e3), "rollout_ms": ms_roll,
+                 "rollout_f32_ms": ms_roll32, "rollout_f32_max_rel_dev_vs_f64": dev32}
+        del xv, cd, pc, pred, pred32
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         k1 = float(np.mean(k1_ms))
@@ -436,6 +463,7 @@ def run_b200(args):
                                                  "three-array form)") if pipe.lean_fit else
                                                 "standalone theta_gram2: reads 5 arrays (Gram + moments)",
                                         "share_of_step": k4 / ms_per_step},
+                "individualisation": indiv,
                 "population_coefs": coefs.tolist()}
         if world == 1 and not args.no_cpu_baseline:
             v, sec, detail = cpu_reference_arm(args.ref_patients, T, 1)
