@@ -11,12 +11,17 @@
 Same constructor arguments, attributes and ``.data`` dictionaries (keys, shapes, dtypes: SURVEY.md
 App. D), so ``SINDY`` and the reference's ``train_sindy.main`` can consume them unchanged.  The
 reference's O(R*T) python loops (one-hot encoding :131-141, active mask :162-164, per-row slicing
-:427-439) are replaced by vectorised numpy; the values are identical.
+:427-439) are replaced by vectorised numpy; the values are identical.  After the simulators these transforms are
+what a default-size experiment spends its time in (0.5 of 0.66 s), so they avoid strided writes and temporaries:
+one-hot rows are gathered from an identity table, shifted copies are written into preallocated arrays, and the
+reference's two deepcopies of the whole dictionary (:470, :541) become dictionary copies that share the arrays
+(nothing on this path writes into them).
 """
 import logging
-from copy import deepcopy
 
 import numpy as np
+
+_EYE4 = np.vstack([np.eye(4), np.zeros((1, 4))])   # row 4 = all zero: a treatment pair that is not 0/1-valued
 
 from .cancer_simulation import (TUMOUR_DEATH_THRESHOLD, generate_params, get_scaling_params, simulate_factual,
                                 simulate_counterfactual_1_step, simulate_counterfactuals_treatment_seq)
@@ -81,28 +86,37 @@ class SyntheticCancerDataset:
         cancer_volume = (self.data['cancer_volume'] - mean['cancer_volume']) / std['cancer_volume']
         patient_types = (self.data['patient_types'] - mean['patient_types']) / std['patient_types']
         width = cancer_volume.shape[1]
-        patient_types = np.repeat(np.asarray(patient_types)[:, None], width, axis=1)
+        patient_types = np.asarray(patient_types)
 
         chemo = self.data['chemo_application']
         radio = self.data['radio_application']
         seq_len = self.data['sequence_lengths']
-        treatments = np.stack([chemo[:, :-1], radio[:, :-1]], axis=-1)
+        R = chemo.shape[0]
         if self.treatment_mode == 'multiclass':
-            c, r = treatments[..., 0], treatments[..., 1]
-            one_hot = np.zeros(treatments.shape[:2] + (4,))
-            one_hot[..., 0] = (c == 0) & (r == 0)
-            one_hot[..., 1] = (c == 1) & (r == 0)
-            one_hot[..., 2] = (c == 0) & (r == 1)
-            one_hot[..., 3] = (c == 1) & (r == 1)
-            self.data['prev_treatments'] = one_hot[:, :-1, :]
+            # one_hot[..., a] = (c, r) == ((0,0), (1,0), (0,1), (1,1))[a]  (:131-141): a row of the identity table
+            c, r = chemo[:, :-1], radio[:, :-1]
+            idx = (c == 1).astype(np.int8) + 2 * (r == 1).astype(np.int8)
+            bad = ~(((c == 0) | (c == 1)) & ((r == 0) | (r == 1)))
+            if bad.any():
+                idx[bad] = 4
+            one_hot = _EYE4[idx]
+            prev_tr = np.zeros((R, width - 1, 4))
+            prev_tr[:, 1:, :] = one_hot[:, :-1, :]
             self.data['current_treatments'] = one_hot
         elif self.treatment_mode == 'multilabel':
-            self.data['prev_treatments'] = treatments[:, :-1, :]
+            treatments = np.empty((R, width - 1, 2))
+            treatments[..., 0] = chemo[:, :-1]
+            treatments[..., 1] = radio[:, :-1]
+            prev_tr = np.zeros((R, width - 1, 2))
+            prev_tr[:, 1:, :] = treatments[:, :-1, :]
             self.data['current_treatments'] = treatments
         else:
             raise ValueError(self.treatment_mode)
+        self.data['prev_treatments'] = prev_tr   # zero row for t = 0, then current_treatments[:, :-1] (:141, :183-185)
 
-        current_covariates = np.stack([cancer_volume[:, :-1], patient_types[:, :-1]], axis=-1)
+        current_covariates = np.empty((R, width - 1, 2))
+        current_covariates[..., 0] = cancer_volume[:, :-1]
+        current_covariates[..., 1] = patient_types[:, None]
         outputs = cancer_volume[:, 1:, np.newaxis]
         output_means = mean[['cancer_volume']].values.flatten()[0]
         output_stds = std[['cancer_volume']].values.flatten()[0]
@@ -116,8 +130,6 @@ class SyntheticCancerDataset:
                                'output_means': output_means, 'output_stds': output_stds}
         self.data['prev_outputs'] = current_covariates[:, :, :1]
         self.data['static_features'] = current_covariates[:, 0, 1:]
-        zero_init = np.zeros((current_covariates.shape[0], 1, self.data['prev_treatments'].shape[-1]))
-        self.data['prev_treatments'] = np.concatenate([zero_init, self.data['prev_treatments']], axis=1)
         self.processed = True
         return self.data
 
@@ -155,7 +167,7 @@ class SyntheticCancerDataset:
         seq['patient_types'] = self.data['patient_types']
         seq['patient_ids_all_trajectories'] = self.data['patient_ids_all_trajectories']
         seq['patient_current_t'] = self.data['patient_current_t']
-        self.data_original = deepcopy(self.data)
+        self.data_original = dict(self.data)     # the reference deep-copies (:470); arrays are shared here
         self.data = seq
         self.processed_sequential = True
         return self.data
@@ -165,7 +177,7 @@ class SyntheticCancerDataset:
         assert self.processed_sequential
         if not self.processed_autoregressive:
             self.data_processed_seq = self.data
-            self.data = deepcopy(self.data_original)
+            self.data = dict(self.data_original)   # (:541)
             self.data['future_past_split'] = self.data['sequence_lengths'] - projection_horizon
             self.processed_autoregressive = True
         return self.data

@@ -91,3 +91,48 @@ def test_product_never_imports_the_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(root, fn)).read()
                 assert 'oracle' not in src.replace('# oracle', ''), f"{fn} mentions the oracle"
+
+
+@pytest.mark.parametrize("mode", ["multiclass", "multilabel"])
+def test_dataset_transforms_equal_the_restatement(mode):
+    """process_data / process_sequential_test / process_sequential_multi of the product's dataset
+    classes (vectorised numpy) vs the loop-for-loop restatement of dataset.py:92-192, 395-473, 533-552, on the
+    oracle's simulator output (no GPU needed: the dataset objects are filled in by hand)."""
+    import warnings
+    from oracle import sindy_np as sp
+    from b200_insite.dataset import SyntheticCancerDataset, SyntheticCancerDatasetCollection
+    from b200_insite.cancer_simulation import TUMOUR_DEATH_THRESHOLD
+    warnings.filterwarnings('ignore')
+    inputs = h.collection_inputs(5, 2.0, 96, 16, 16)
+    o = h.oracle_collection(inputs)
+
+    def mk(data, name):
+        d = object.__new__(SyntheticCancerDataset)
+        d.data = dict(data); d.subset_name = name
+        d.processed = d.processed_sequential = d.processed_autoregressive = False
+        d.treatment_mode = mode; d.exploded = False; d.norm_const = TUMOUR_DEATH_THRESHOLD
+        return d
+    col = object.__new__(SyntheticCancerDatasetCollection)
+    col.train_f, col.val_f = mk(o['train'], 'train'), mk(o['val'], 'val')
+    col.test_cf_one_step, col.test_cf_treatment_seq = mk(o['one'], 'test'), mk(o['seq'], 'test')
+    col.projection_horizon = 5
+    col.train_scaling_params = col.train_f.get_scaling_params()
+    means, stds = col.train_f.get_scaling_params()
+    col.process_data_multi()
+    keys = ('prev_treatments', 'current_treatments', 'current_covariates', 'outputs', 'active_entries',
+            'unscaled_outputs', 'prev_outputs', 'static_features')
+    for ds, name in ((col.train_f, 'train'), (col.val_f, 'val'), (col.test_cf_one_step, 'one')):
+        want, sc = sp.process_data(o[name], means, stds, treatment_mode=mode)
+        for k in keys:
+            assert ds.data[k].shape == want[k].shape and np.array_equal(ds.data[k], want[k]), (name, k)
+        for k in sc:
+            assert np.array_equal(np.asarray(ds.scaling_params[k]), np.asarray(sc[k])), k
+    want, sc = sp.process_data(o['seq'], means, stds, treatment_mode=mode)
+    seq = col.test_cf_treatment_seq
+    for k in keys:                                   # after process_sequential_multi .data is the full-length form again
+        assert np.array_equal(seq.data[k], want[k]), ('seq', k)
+    assert np.array_equal(seq.data['future_past_split'], o['seq']['sequence_lengths'] - 5)
+    want5 = sp.process_sequential_test(want, sc, 5)
+    for k in want5:
+        assert np.array_equal(seq.data_processed_seq[k], want5[k]), ('seq5', k)
+    assert 'future_past_split' not in seq.data_original
