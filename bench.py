@@ -54,6 +54,27 @@ def ncu_entry(kernel):
         return None
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPU cores that are local to its GPU (NVML affinity mask) before any pinned host buffer
+    is allocated: cudaHostAlloc places pages on the calling thread's NUMA node, and with one rank per GPU the eight
+    host->device streams of a node otherwise share one socket's memory and inter-socket links.  Returns the core
+    list, or None when NVML / affinity control is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -213,6 +234,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev.require_cuda()
@@ -416,7 +438,9 @@ def run_b200(args):
                                       f"every row starts on a 128-byte line); dense rows are measured beside it in "
                                       f"roofline.dense_rows") if pitch != T else f"dense (N,{T}) float64 rows",
                            "noise": "pre-drawn arrays resident in HBM (reference I/O contract)",
-                           "parallelism": f"patients sharded over {world} GPU(s); allreduce of 68 doubles"},
+                           "parallelism": f"patients sharded over {world} GPU(s); allreduce of 68 doubles",
+                           "host_affinity": (f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus
+                                             else "default")},
                 "clocks": clocks.summary(),
                 "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen.h2d_bytes(),
                         "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": gen_e2e_ms,
