@@ -212,8 +212,10 @@ __device__ __forceinline__ double proj_step(const fm::FmK &fk, const Patient &p,
     return growth(p, V, lg, C, D, noise);
 }
 
-template <int H>
-__global__ void __launch_bounds__(128)
+constexpr int K3_MINB_DEFAULT = 3;   // measured at 1M patients: 2 -> 23.8 ms, 3 -> 20.1 ms, 4 (spills) -> 23.4 ms
+
+template <int H, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const double *__restrict__ params,
                         const double *__restrict__ noise, const double *__restrict__ rec,
                         const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
@@ -643,15 +645,18 @@ extern "C" int b200i_sim_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const
         else src = CfSrc{lo, factual, codes, cf, valid, row_offsets};
         const unsigned grid = (unsigned)((hi - lo + 127) / 128);
         constexpr int STAGE_BYTES = 128 * (2 * 5 * 5 + 1) * 8;   // [128 threads][2H*H + 1] doubles
-        static bool attr_set = false;
-        if (!attr_set) {
-            B200I_CUDA(cudaFuncSetAttribute(cf_treatment_seq_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            STAGE_BYTES));
-            attr_set = true;
-        }
-        cf_treatment_seq_kernel<5><<<grid, 128, STAGE_BYTES, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs,
-                                                         radio_rvs, global_base, src, required ? 1 : 0, factual, codes,
-                                                         cf, valid, n_steps, n_rows, d_err);
+        // resident CTAs per SM the register budget is sized for (2: 199 registers, 3: 168, 4: 128); B200I_K3_MINB overrides
+        static const int minb = getenv("B200I_K3_MINB") ? atoi(getenv("B200I_K3_MINB")) : K3_MINB_DEFAULT;
+        auto go = [&](auto kern) -> int {
+            B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+            kern<<<grid, 128, STAGE_BYTES, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs, radio_rvs,
+                                                 global_base, src, required ? 1 : 0, factual, codes, cf, valid, n_steps,
+                                                 n_rows, d_err);
+            return 0;
+        };
+        int rc_ = minb == 2 ? go(cf_treatment_seq_kernel<5, 2>) : (minb == 4 ? go(cf_treatment_seq_kernel<5, 4>)
+                                                                              : go(cf_treatment_seq_kernel<5, 3>));
+        if (rc_) return rc_;
         return check_cuda(cudaGetLastError(), "cf_treatment_seq launch");
     };
     return run_levels(n, global_base, source, n_rows, row_offsets, total_rows_host, levels_host, st, launch);
