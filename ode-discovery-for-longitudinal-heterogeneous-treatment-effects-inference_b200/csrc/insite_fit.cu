@@ -103,6 +103,7 @@ stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict
 // K7: cooperative BFGS, 16 lanes per row
 // ------------------------------------------------------------------------------------------------
 constexpr int BFGS_THREADS = 128;
+constexpr int K7_MINB_DEFAULT = 4;
 constexpr int BFGS_GROUPS = BFGS_THREADS / 16;
 constexpr int BFGS_MAXW = 80;
 
@@ -184,7 +185,8 @@ __device__ __forceinline__ double quadmin(double a, double fa, double fpa, doubl
     return a - fpa / (2.0 * B);
 }
 
-__global__ void __launch_bounds__(BFGS_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(BFGS_THREADS, MINB)
 insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x,
                    const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
                    const double *__restrict__ static_u, const double *__restrict__ theta0_g, double lam, double gtol,
@@ -391,8 +393,21 @@ extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t sub
     int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
-    insite_bfgs_kernel<<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    // resident CTAs per SM the register budget is sized for; B200I_K7_MINB overrides (tuning aid)
+    static const int minb = getenv("B200I_K7_MINB") ? atoi(getenv("B200I_K7_MINB")) : K7_MINB_DEFAULT;
+    cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+    if (minb == 3)
+        insite_bfgs_kernel<3><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
         rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
         max_iter, coefs_out, status_out, fval_out);
+    else if (minb == 5)
+        insite_bfgs_kernel<5><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
+        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+        max_iter, coefs_out, status_out, fval_out);
+    else
+        insite_bfgs_kernel<4><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
+        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+        max_iter, coefs_out, status_out, fval_out);
+
     return check_cuda(cudaGetLastError(), "insite_bfgs launch");
 }
