@@ -19,11 +19,13 @@ import b200_insite.cancer_simulation as cs
 
 
 def timed(fn, reps=3, warm=1):
+    r = None
     for _ in range(warm):
         r = fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
+        r = None   # release the previous result first: a 24 GB cohort otherwise forces fresh cudaMallocs inside the timing
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); r = fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
