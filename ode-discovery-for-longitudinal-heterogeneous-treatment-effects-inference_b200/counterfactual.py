@@ -77,6 +77,18 @@ def sim_cf_treatment_seq(params_dev, noise, recovery, chemo_rvs, radio_rvs, T, H
                          levels.value)
 
 
+def generated_draws(n, T, H, seed, patient_base=0):
+    """Throughput mode: the per-patient draws of the counterfactual generators (0.01 * randn(T + H), rand(T) x 3;
+    cancer_simulation.py:440-453, :640-653) from the device generator instead of numpy's sequential stream --
+    Philox4x32-10 counted by (global patient index, column pair, stream), csrc/philox.cuh, so the draws of a patient
+    do not depend on the shard or on H.  Returns (noise (n, T+H), recovery, chemo, radio (n, T)) on the device."""
+    W = T + H
+    Wg = W + (W & 1)                                   # the generator works in column pairs
+    noise, rec, chemo, radio = dev.philox_draws(n, Wg, seed, patient_base=patient_base)
+    cut = lambda a, w: a if a.shape[1] == w else a[:, :w].contiguous()
+    return cut(noise, W), cut(rec, T), cut(chemo, T), cut(radio, T)
+
+
 def expand(cohort, patient_types_dev, row_begin=0, row_end=None):
     """Dense reference rows [row_begin,row_end) as a dict of device tensors (reference key names)."""
     lib = _native.load()

@@ -54,6 +54,17 @@ def main():
                       "bytes_written": n_cf * ((T - 1) * 2 * H * H * 8 + T * 9 + (T - 1) * 2 + 16),
                       "write_GBs": n_cf * ((T - 1) * 2 * H * H * 8 + T * 9) / ms / 1e6}), flush=True)
     del coh
+    # the same from host parameters only: H2D of the parameter block, draws from the device generator, K3
+    h_block = torch.from_numpy(dev.pack_params(params)).pin_memory()
+    def c3_from_host():
+        b = h_block.cuda(non_blocking=True)
+        dr = cfm.generated_draws(n_cf, T, H, seed=5)
+        return cfm.sim_cf_treatment_seq(b, *dr, T, H)
+    ms, coh = timed(c3_from_host)
+    print(json.dumps({"kernel": "C3 end to end: pinned host parameters -> H2D -> device-generated draws -> K3", "patients": n_cf,
+                      "ms": ms, "rows": int(coh.total_rows), "rows_per_s": int(coh.total_rows) / ms * 1e3,
+                      "h2d_bytes": int(h_block.numel() * 8)}), flush=True)
+    del coh
     noise1 = noise[:, :T].contiguous()
     del noise
     ms, coh = timed(lambda: cfm.sim_cf_one_step(block, noise1, rec, chemo, radio, T))

@@ -150,3 +150,30 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     assert np.array_equal(res[32:].numpy(), a.stats.cpu().numpy())
     if chunks == 1:
         assert torch.equal(a.stats, b.stats)
+
+
+def test_generated_counterfactual_draws_and_cohort(dev):
+    """counterfactual.generated_draws: the device generator's draws in the layout of the counterfactual simulators
+    (noise (N, T+H) with odd width) equal the numpy restatement, and K3 on them equals the C oracle."""
+    import torch
+    from oracle import philox_np as ph, sim_oracle as so
+    from b200_insite import counterfactual as cfm
+    n, T, H = 40, 60, 5
+    noise, rec, chemo, radio = cfm.generated_draws(n, T, H, seed=21, patient_base=7)
+    torch.cuda.synchronize()
+    want = ph.draw_factual(n, T + H + 1, 21, patient_base=7)
+    assert noise.shape == (n, T + H) and rec.shape == (n, T)
+    np.testing.assert_allclose(noise.cpu().numpy(), want['noise'][:, :T + H], rtol=1e-12, atol=1e-16)
+    for g, k in ((rec, 'recovery'), (chemo, 'chemo'), (radio, 'radio')):
+        assert np.array_equal(g.cpu().numpy(), want[k][:, :T])
+    params = _cohort(n, 86)
+    draws = {'noise': noise.cpu().numpy(), 'recovery': rec.cpu().numpy(), 'chemo': chemo.cpu().numpy(),
+             'radio': radio.cpu().numpy()}
+    ref = so.sim_cf_treatment_seq(params, T, H, draws)
+    coh = cfm.sim_cf_treatment_seq(dev.to_device(dev.pack_params(params)), noise, rec, chemo, radio, T, H)
+    dense = cfm.expand(coh, dev.to_device(np.asarray(params['patient_types'], dtype=np.float64)))
+    torch.cuda.synchronize()
+    assert coh.total_rows == ref['cancer_volume'].shape[0]
+    for k in ('chemo_application', 'radio_application', 'sequence_lengths', 'patient_current_t'):
+        assert np.array_equal(dense[k].cpu().numpy(), ref[k]), k
+    np.testing.assert_allclose(dense['cancer_volume'].cpu().numpy(), ref['cancer_volume'], rtol=1e-9, atol=1e-12)
