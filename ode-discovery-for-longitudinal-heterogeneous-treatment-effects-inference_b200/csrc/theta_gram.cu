@@ -451,9 +451,14 @@ extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, i
 {
     if (moments_stride == 0) moments_stride = n;
     B200I_REQUIRE(moments_stride >= n, B200I_E_ARG, "theta_gram_codes: moments_stride %lld < n", (long long)moments_stride);
-    B200I_REQUIRE(n >= 0 && cancer_volume && codes && sequence_lengths && static_feature && patient_moments &&
-                      gram_workspace,
-                  B200I_E_ARG, "theta_gram_codes: NULL argument or negative n");
+    B200I_REQUIRE(n >= 0 && gram_workspace, B200I_E_ARG, "theta_gram_codes: negative n or NULL workspace");
+    if (n == 0) {   // an empty cohort (its arrays may be NULL): zero statistics
+        B200I_CUDA(cudaMemsetAsync(gram_workspace, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32,
+                                   static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    B200I_REQUIRE(cancer_volume && codes && sequence_lengths && static_feature && patient_moments, B200I_E_ARG,
+                  "theta_gram_codes: NULL argument");
     B200I_REQUIRE(T >= 2 && T <= 256 && T % 2 == 0 && fd_dt > 0 && (mode == 0 || mode == 1), B200I_E_UNSUPPORTED,
                   "theta_gram_codes: T=%d (even, <= 256), fd_dt > 0, mode 0/1", T);
     B200I_REQUIRE(row_pitch >= T && (row_pitch == T || row_pitch % 2 == 0) && code_pitch >= ((T + 15) / 16) * 16 &&

@@ -177,3 +177,30 @@ def test_generated_counterfactual_draws_and_cohort(dev):
     for k in ('chemo_application', 'radio_application', 'sequence_lengths', 'patient_current_t'):
         assert np.array_equal(dense[k].cpu().numpy(), ref[k]), k
     np.testing.assert_allclose(dense['cancer_volume'].cpu().numpy(), ref['cancer_volume'], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [0, 1, 33])
+def test_sim_factual_rng_tiny_and_empty_cohorts(dev, n):
+    """Empty, single-patient and ragged (one full tile + one patient) cohorts: same results as K1 on the exported
+    draws; the empty cohort leaves zero statistics."""
+    import torch
+    T = 60
+    params = _cohort(max(n, 1), 87)
+    block = dev.pack_params(params)[:, :n]
+    pd_ = dev.to_device(block) if n else torch.empty((10, 0), dtype=torch.float64, device='cuda')
+    static = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64)[:n]) if n else \
+        torch.empty((0,), dtype=torch.float64, device='cuda')
+    vol, codes, sl, pm, _ = dev.sim_factual_rng(pd_, T, 5, pitch=T)
+    stats = dev.theta_gram_codes(vol, codes, sl, static, pm, tag="tiny").clone()
+    torch.cuda.synchronize()
+    assert vol.shape == (n, T) and codes.shape[0] == n and sl.shape == (n,)
+    if n == 0:
+        assert float(stats.abs().sum()) == 0.0
+        return
+    draws = dev.philox_draws(n, T, 5, pitch=T)
+    out, _ = dev.sim_factual(pd_, *draws, T)
+    alone = dev.theta_gram(out['cancer_volume'], out['chemo_application'], out['radio_application'],
+                           out['sequence_lengths'], static, out['chemo_dosage'], out['radio_dosage'], tag="tiny2")
+    torch.cuda.synchronize()
+    assert torch.equal(vol, out['cancer_volume']) and torch.equal(sl, out['sequence_lengths'])
+    np.testing.assert_allclose(stats.cpu().numpy(), alone.cpu().numpy(), rtol=1e-12, atol=1e-9)
