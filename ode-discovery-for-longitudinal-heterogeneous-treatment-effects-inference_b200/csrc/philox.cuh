@@ -39,6 +39,36 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t
     return c;
 }
 
+// The ten round keys of a seed.  Kernels receive them as a __grid_constant__ parameter: every use is then a
+// constant-bank operand of the XOR instead of two uniform-datapath additions per round and call.
+struct RoundKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ inline RoundKeys round_keys(uint32_t k0, uint32_t k1)
+{
+    RoundKeys rk;
+    for (int r = 0; r < 10; ++r) {
+        rk.k0[r] = k0; rk.k1[r] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return rk;
+}
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, const RoundKeys &rk)
+{
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+        U4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk.k0[r];
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk.k1[r];
+        n.w = (uint32_t)p0;
+        c = n;
+    }
+    return c;
+}
+
 #ifdef __CUDACC__
 // double in [1,2) whose mantissa is the top 52 bits of (hi:lo)
 __device__ __forceinline__ double mant12(uint32_t lo, uint32_t hi)
@@ -48,12 +78,13 @@ __device__ __forceinline__ double mant12(uint32_t lo, uint32_t hi)
 
 struct PairKey {
     uint32_t p_lo, p_hi, k0, k1;
+    const RoundKeys *rk;   // round keys of (k0, k1), normally the kernel's __grid_constant__ parameter
 };
 
 // the two uniforms in [0,1) of stream s (1..3) for column pair tp
 __device__ __forceinline__ void uniform_pair(const PairKey &k, uint32_t tp, uint32_t s, double &u_even, double &u_odd)
 {
-    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, s}, k.k0, k.k1);
+    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, s}, *k.rk);
     u_even = __dsub_rn(mant12(r.x, r.y), 1.0);
     u_odd = __dsub_rn(mant12(r.z, r.w), 1.0);
 }
@@ -61,7 +92,7 @@ __device__ __forceinline__ void uniform_pair(const PairKey &k, uint32_t tp, uint
 // the two recovery uniforms of column pair tp (stream 1): bin centres, in (0,1)
 __device__ __forceinline__ void recovery_pair(const PairKey &k, uint32_t tp, double &u_even, double &u_odd)
 {
-    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, 1u}, k.k0, k.k1);
+    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, 1u}, *k.rk);
     u_even = __dadd_rn(__dsub_rn(mant12(r.x, r.y), 1.0), 0x1p-53);
     u_odd = __dadd_rn(__dsub_rn(mant12(r.z, r.w), 1.0), 0x1p-53);
 }
@@ -70,7 +101,8 @@ __device__ __forceinline__ void recovery_pair(const PairKey &k, uint32_t tp, dou
 __device__ __noinline__ double recovery_draw(uint32_t p_lo, uint32_t p_hi, uint32_t k0, uint32_t k1, uint32_t tp, uint32_t odd)
 {
     double a, b;
-    recovery_pair(PairKey{p_lo, p_hi, k0, k1}, tp, a, b);
+    const RoundKeys rk = round_keys(k0, k1);
+    recovery_pair(PairKey{p_lo, p_hi, k0, k1, &rk}, tp, a, b);
     return odd ? b : a;
 }
 struct LazyRecovery {
@@ -82,7 +114,7 @@ struct LazyRecovery {
 // the two noise terms 0.01 * N(0,1) of column pair tp (stream 0)
 __device__ __forceinline__ void noise_pair(const PairKey &k, uint32_t tp, double &z_even, double &z_odd)
 {
-    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, 0u}, k.k0, k.k1);
+    const U4 r = philox4x32_10(U4{k.p_lo, k.p_hi, tp, 0u}, *k.rk);
     const double u1 = __dsub_rn(2.0, mant12(r.x, r.y));                  // (0,1]
     const double a2 = __dmul_rn(2.0, __dsub_rn(mant12(r.z, r.w), 1.0));  // [0,2): angle / pi
     const double rad = __dmul_rn(0.01, sqrt(__dmul_rn(-2.0, log(u1))));

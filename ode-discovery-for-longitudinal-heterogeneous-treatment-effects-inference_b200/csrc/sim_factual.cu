@@ -604,7 +604,8 @@ extern "C" int b200i_philox_draws(int64_t n, int32_t T, int64_t row_pitch, uint6
     const int64_t cap = (int64_t)num_sms() * 16;
     if (grid > cap) grid = cap;
     philox_draws_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        n, T, row_pitch, (uint32_t)seed, (uint32_t)(seed >> 32), patient_base, noise, recovery_rvs, chemo_rvs, radio_rvs);
+        n, T, row_pitch, rng::round_keys((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)seed, (uint32_t)(seed >> 32),
+        patient_base, noise, recovery_rvs, chemo_rvs, radio_rvs);
     return check_cuda(cudaGetLastError(), "philox_draws launch");
 }
 

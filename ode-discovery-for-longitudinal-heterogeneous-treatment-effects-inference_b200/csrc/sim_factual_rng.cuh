@@ -62,7 +62,8 @@ __device__ __noinline__ void rng_slow_box(uint8_t *buf, uint8_t *crow, int lane,
 template <int STATS, int MINB>
 __global__ void __launch_bounds__(RNG_WARPS * 32, MINB)
 sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int64_t pstride, int64_t mstride, int T, SimC c,
-                       const double *__restrict__ params, uint32_t seed_lo, uint32_t seed_hi, int64_t patient_base,
+                       const double *__restrict__ params, const __grid_constant__ rng::RoundKeys rkeys, uint32_t seed_lo,
+                        uint32_t seed_hi, int64_t patient_base,
                        uint8_t *__restrict__ codes_out, int64_t code_pitch, double *__restrict__ seq_len_out,
                        double *__restrict__ pmom_out, const double *__restrict__ static_feature, StatsWorkspace *ws)
 {
@@ -108,7 +109,7 @@ sim_factual_rng_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int6
         const bool exists = patient < n;
         const int64_t pi = exists ? patient : 0;
         const int64_t gp = patient_base + patient;
-        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi};
+        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi, &rkeys};
 
         WsPatient p;
         WsState s;
@@ -355,7 +356,8 @@ __device__ __forceinline__ void ws_col(int t, int Tm1, const WsK &k, const WsPat
 template <int STATS, int MINB>
 __global__ void __launch_bounds__(RNG_WARPS * 32, MINB)
 sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int64_t pstride, int64_t mstride, int T, SimC c,
-                        const double *__restrict__ params, uint32_t seed_lo, uint32_t seed_hi, int64_t patient_base,
+                        const double *__restrict__ params, const __grid_constant__ rng::RoundKeys rkeys, uint32_t seed_lo,
+                        uint32_t seed_hi, int64_t patient_base,
                         uint8_t *__restrict__ codes_out, int64_t code_pitch, double *__restrict__ seq_len_out,
                         double *__restrict__ pmom_out, const double *__restrict__ static_feature, StatsWorkspace *ws)
 {
@@ -402,7 +404,7 @@ sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int
         const bool exists = patient < n;
         const int64_t pi = exists ? patient : 0;
         const int64_t gp = patient_base + patient;
-        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi};
+        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi, &rkeys};
 
         WsPatient p;
         WsState s;
@@ -562,7 +564,8 @@ sim_factual_rng2_kernel(const __grid_constant__ CUtensorMap vmap, int64_t n, int
 // the generator's draws as the four (N,T) arrays of the reference contract (noise already multiplied by 0.01):
 // thread = (patient, column pair), consecutive lanes -> consecutive 16 bytes of a row
 __global__ void __launch_bounds__(256)
-philox_draws_kernel(int64_t n, int T, int64_t pitch, uint32_t seed_lo, uint32_t seed_hi, int64_t patient_base,
+philox_draws_kernel(int64_t n, int T, int64_t pitch, const __grid_constant__ rng::RoundKeys rkeys, uint32_t seed_lo,
+                    uint32_t seed_hi, int64_t patient_base,
                     double *__restrict__ noise, double *__restrict__ rec, double *__restrict__ chemo,
                     double *__restrict__ radio)
 {
@@ -572,7 +575,7 @@ philox_draws_kernel(int64_t n, int T, int64_t pitch, uint32_t seed_lo, uint32_t 
         const int64_t i = e / half;
         const int tp = (int)(e - i * half);
         const int64_t gp = patient_base + i;
-        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi};
+        const rng::PairKey key{(uint32_t)gp, (uint32_t)((uint64_t)gp >> 32), seed_lo, seed_hi, &rkeys};
         double a, b;
         const int64_t o = i * pitch + 2 * tp;
         rng::noise_pair(key, (uint32_t)tp, a, b);
@@ -592,7 +595,8 @@ static int launch_rng(const CUtensorMap &vmap, int64_t n, int64_t pstride, int64
                       int64_t patient_base, uint8_t *codes_out, int64_t code_pitch, double *seq_len, double *pmom,
                       const double *static_feature, StatsWorkspace *ws, cudaStream_t st)
 {
-    void (*kern)(const CUtensorMap, int64_t, int64_t, int64_t, int, SimC, const double *, uint32_t, uint32_t, int64_t, uint8_t *,
+    void (*kern)(const CUtensorMap, int64_t, int64_t, int64_t, int, SimC, const double *, const rng::RoundKeys, uint32_t, uint32_t,
+                 int64_t, uint8_t *,
                  int64_t, double *, double *, const double *, StatsWorkspace *);
     if constexpr (GEN == 2) kern = sim_factual_rng2_kernel<STATS, MINB>;
     else kern = sim_factual_rng_kernel<STATS, MINB>;
@@ -615,7 +619,8 @@ static int launch_rng(const CUtensorMap &vmap, int64_t n, int64_t pstride, int64
     const int64_t need = (ntiles + RNG_WARPS - 1) / RNG_WARPS;
     if (grid > need) grid = need;
     if (STATS == 1 && grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
-    kern<<<(unsigned)grid, RNG_WARPS * 32, smem, st>>>(vmap, n, pstride, mstride, T, c, params, (uint32_t)seed, (uint32_t)(seed >> 32),
+    kern<<<(unsigned)grid, RNG_WARPS * 32, smem, st>>>(vmap, n, pstride, mstride, T, c, params,
+                                                       rng::round_keys((uint32_t)seed, (uint32_t)(seed >> 32)), (uint32_t)seed, (uint32_t)(seed >> 32),
                                                        patient_base, codes_out, code_pitch, seq_len, pmom,
                                                        static_feature, ws);
     return check_cuda(cudaGetLastError(), "sim_factual_rng launch");
