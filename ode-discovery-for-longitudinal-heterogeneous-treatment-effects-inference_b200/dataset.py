@@ -100,6 +100,9 @@ class SyntheticCancerDataset:
             if bad.any():
                 idx[bad] = 4
             one_hot = _EYE4[idx]
+            # np.argmax(one_hot, -1) without the reduction (an all-zero row has argmax 0): read by SINDY
+            self.treatment_codes_ = np.where(idx == 4, 0, idx).astype(np.uint8)
+            self._codes_owner = one_hot
             prev_tr = np.zeros((R, width - 1, 4))
             prev_tr[:, 1:, :] = one_hot[:, :-1, :]
             self.data['current_treatments'] = one_hot
