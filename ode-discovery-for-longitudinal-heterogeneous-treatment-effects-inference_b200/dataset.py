@@ -23,6 +23,89 @@ import numpy as np
 
 _EYE4 = np.vstack([np.eye(4), np.zeros((1, 4))])   # row 4 = all zero: a treatment pair that is not 0/1-valued
 
+
+class LazyDict(dict):
+    """The ``.data`` dictionary of a processed dataset.  The three (R, W, k) arrays that nothing on the SINDy / INSITE
+    path reads -- one-hot ``current_treatments``, ``prev_treatments``, ``current_covariates``: 3 of the 4 GB a
+    10k/1k/1k collection writes -- are built on first access.  Indexing, ``in``, ``get`` see them as ordinary keys;
+    anything that enumerates the dictionary (``keys``, ``items``, iteration, ``len``, pickling, ``dict(d)``) builds
+    them first, so consumers of the reference's dictionaries cannot tell the difference."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._lazy = {}
+        self._on_set = {}
+
+    def set_lazy(self, key, fn):
+        dict.pop(self, key, None)
+        self._lazy[key] = fn
+
+    def on_set(self, key, fn):
+        """fn() is called when `key` is assigned from outside (cached views of it become invalid)."""
+        self._on_set[key] = fn
+
+    def materialise(self):
+        for k in list(self._lazy):
+            self[k]
+        return self
+
+    def __missing__(self, key):
+        if key not in self._lazy:
+            raise KeyError(key)
+        v = self._lazy.pop(key)()
+        dict.__setitem__(self, key, v)
+        return v
+
+    def __setitem__(self, key, value):
+        self._lazy.pop(key, None)
+        if key in self._on_set:
+            self._on_set[key]()
+        dict.__setitem__(self, key, value)
+
+    def __delitem__(self, key):
+        if self._lazy.pop(key, None) is None:
+            dict.__delitem__(self, key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def pop(self, key, *default):
+        if key in self._lazy:
+            self[key]
+        return dict.pop(self, key, *default)
+
+    def __iter__(self):
+        return dict.__iter__(self.materialise())
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._lazy)
+
+    def keys(self):
+        return dict.keys(self.materialise())
+
+    def items(self):
+        return dict.items(self.materialise())
+
+    def values(self):
+        return dict.values(self.materialise())
+
+    def copy(self):
+        """Shallow copy that stays lazy (arrays and pending builders are shared)."""
+        new = LazyDict()
+        dict.update(new, dict.items(self))
+        new._lazy = dict(self._lazy)
+        return new
+
+    def __reduce__(self):
+        return (dict, (dict(dict.items(self.materialise())),))
+
+    def __deepcopy__(self, memo):
+        from copy import deepcopy
+        return deepcopy(dict(dict.items(self.materialise())), memo)
+
 from .cancer_simulation import (TUMOUR_DEATH_THRESHOLD, generate_params, get_scaling_params, simulate_factual,
                                 simulate_counterfactual_1_step, simulate_counterfactuals_treatment_seq)
 
@@ -64,7 +147,7 @@ class SyntheticCancerDataset:
         return {k: v[index] for k, v in self.data.items() if hasattr(v, '__len__') and len(v) == len(self)}
 
     def __len__(self):
-        return self.data['current_covariates'].shape[0]
+        return self.data['outputs'].shape[0]      # = current_covariates.shape[0] (:86), without building that array
 
     def get_scaling_params(self):
         return get_scaling_params(self.data)
@@ -92,6 +175,7 @@ class SyntheticCancerDataset:
         radio = self.data['radio_application']
         seq_len = self.data['sequence_lengths']
         R = chemo.shape[0]
+        data = LazyDict(self.data)
         if self.treatment_mode == 'multiclass':
             # one_hot[..., a] = (c, r) == ((0,0), (1,0), (0,1), (1,1))[a]  (:131-141): a row of the identity table
             c, r = chemo[:, :-1], radio[:, :-1]
@@ -99,40 +183,53 @@ class SyntheticCancerDataset:
             bad = ~(((c == 0) | (c == 1)) & ((r == 0) | (r == 1)))
             if bad.any():
                 idx[bad] = 4
-            one_hot = _EYE4[idx]
+            self._treatment_rows = lambda rows, cols: _EYE4[idx[rows, cols]]     # current_treatments[rows, cols, :]
+            data.set_lazy('current_treatments', lambda: _EYE4[idx])
             # np.argmax(one_hot, -1) without the reduction (an all-zero row has argmax 0): read by SINDY
             self.treatment_codes_ = np.where(idx == 4, 0, idx).astype(np.uint8)
-            self._codes_owner = one_hot
-            prev_tr = np.zeros((R, width - 1, 4))
-            prev_tr[:, 1:, :] = one_hot[:, :-1, :]
-            self.data['current_treatments'] = one_hot
+            data.on_set('current_treatments', lambda: setattr(self, 'treatment_codes_', None))
+            k_tr = 4
         elif self.treatment_mode == 'multilabel':
-            treatments = np.empty((R, width - 1, 2))
-            treatments[..., 0] = chemo[:, :-1]
-            treatments[..., 1] = radio[:, :-1]
-            prev_tr = np.zeros((R, width - 1, 2))
-            prev_tr[:, 1:, :] = treatments[:, :-1, :]
-            self.data['current_treatments'] = treatments
+            def treatments():
+                t = np.empty((R, width - 1, 2))
+                t[..., 0] = chemo[:, :-1]
+                t[..., 1] = radio[:, :-1]
+                return t
+            self._treatment_rows = lambda rows, cols: np.stack([chemo[rows, cols], radio[rows, cols]], axis=-1)
+            data.set_lazy('current_treatments', treatments)
+            k_tr = 2
         else:
             raise ValueError(self.treatment_mode)
-        self.data['prev_treatments'] = prev_tr   # zero row for t = 0, then current_treatments[:, :-1] (:141, :183-185)
 
-        current_covariates = np.empty((R, width - 1, 2))
-        current_covariates[..., 0] = cancer_volume[:, :-1]
-        current_covariates[..., 1] = patient_types[:, None]
+        def prev_treatments():   # zero row for t = 0, then current_treatments[:, :-1] (:141, :183-185)
+            p = np.zeros((R, width - 1, k_tr))
+            p[:, 1:, :] = data['current_treatments'][:, :-1, :]
+            return p
+        data.set_lazy('prev_treatments', prev_treatments)
+
+        def current_covariates():
+            cov = np.empty((R, width - 1, 2))
+            cov[..., 0] = cancer_volume[:, :-1]
+            cov[..., 1] = patient_types[:, None]
+            return cov
+        data.set_lazy('current_covariates', current_covariates)
+        self._covariate_rows = lambda rows, cols: np.stack(
+            [cancer_volume[rows, cols], np.broadcast_to(patient_types[rows], np.shape(cols))], axis=-1)
+
         outputs = cancer_volume[:, 1:, np.newaxis]
         output_means = mean[['cancer_volume']].values.flatten()[0]
         output_stds = std[['cancer_volume']].values.flatten()[0]
         active = (np.arange(outputs.shape[1])[None, :] < seq_len.astype(np.int64)[:, None]).astype(np.float64)
 
-        self.data['current_covariates'] = current_covariates
-        self.data['outputs'] = outputs
-        self.data['active_entries'] = active[:, :, None]
-        self.data['unscaled_outputs'] = outputs * std['cancer_volume'] + mean['cancer_volume']
+        data['outputs'] = outputs
+        data['active_entries'] = active[:, :, None]
+        data['unscaled_outputs'] = outputs * std['cancer_volume'] + mean['cancer_volume']
         self.scaling_params = {'input_means': input_means, 'inputs_stds': input_stds,
                                'output_means': output_means, 'output_stds': output_stds}
-        self.data['prev_outputs'] = current_covariates[:, :, :1]
-        self.data['static_features'] = current_covariates[:, 0, 1:]
+        # = current_covariates[:, :, :1] and current_covariates[:, 0, 1:] of the reference (:186-187), same values
+        data['prev_outputs'] = cancer_volume[:, :-1, np.newaxis]
+        data['static_features'] = patient_types[:, np.newaxis].copy()
+        self.data = data
         self.processed = True
         return self.data
 
@@ -147,19 +244,18 @@ class SyntheticCancerDataset:
         H = projection_horizon
         seq_len = self.data['sequence_lengths'].astype(np.int64)
         outputs = self.data['outputs']
-        cur = self.data['current_treatments']
-        prev = self.data['prev_treatments'][:, 1:, :]
-        cov = self.data['current_covariates']
         R, W, _ = outputs.shape
         fact = seq_len - H
         rows = np.arange(R)[:, None]
         k = np.arange(H)[None, :]
-        prev_idx = np.mod(fact[:, None] - 1 + k, prev.shape[1])   # python slices with a negative start never occur (sl > H)
+        # prev = prev_treatments[:, 1:] = current_treatments[:, :-1]  (W - 1 entries)
+        prev_idx = np.mod(fact[:, None] - 1 + k, W - 1)   # python slices with a negative start never occur (sl > H)
+        cov_last = self._covariate_rows(np.arange(R), fact - 1)                    # current_covariates[i, fact-1]
         seq = {
             'active_encoder_r': (np.arange(W - H)[None, :] < fact[:, None]).astype(np.float64),
-            'prev_treatments': prev[rows, prev_idx, :],
-            'current_treatments': cur[rows, fact[:, None] + k, :],
-            'current_covariates': np.repeat(cov[np.arange(R), fact - 1][:, None, :], H, axis=1),
+            'prev_treatments': self._treatment_rows(rows, prev_idx),
+            'current_treatments': self._treatment_rows(rows, fact[:, None] + k),
+            'current_covariates': np.repeat(cov_last[:, None, :], H, axis=1),
             'outputs': outputs[rows, fact[:, None] + k, :],
             'sequence_lengths': np.full(R, float(H)),
             'active_entries': np.ones((R, H, 1)),
@@ -170,7 +266,7 @@ class SyntheticCancerDataset:
         seq['patient_types'] = self.data['patient_types']
         seq['patient_ids_all_trajectories'] = self.data['patient_ids_all_trajectories']
         seq['patient_current_t'] = self.data['patient_current_t']
-        self.data_original = dict(self.data)     # the reference deep-copies (:470); arrays are shared here
+        self.data_original = self.data.copy()    # the reference deep-copies (:470); arrays are shared here
         self.data = seq
         self.processed_sequential = True
         return self.data
@@ -180,7 +276,7 @@ class SyntheticCancerDataset:
         assert self.processed_sequential
         if not self.processed_autoregressive:
             self.data_processed_seq = self.data
-            self.data = dict(self.data_original)   # (:541)
+            self.data = self.data_original.copy()  # (:541)
             self.data['future_past_split'] = self.data['sequence_lengths'] - projection_horizon
             self.processed_autoregressive = True
         return self.data

@@ -124,18 +124,18 @@ class SINDY:
         prev = np.squeeze(dataset.data['prev_outputs'] * sp['output_stds'] + sp['output_means'], axis=-1)
         lo, hi = self.dim_outcome, self.dim_outcome + self.dim_static_features
         static = dataset.data['static_features'] * sp['inputs_stds'][lo:hi] + sp['input_means'][lo:hi]
-        ct = dataset.data['current_treatments']
         if self.treatment_mode == 'multilabel':      # (chemo, radio) applications -> code chemo + 2*radio
-            cti = ct.astype(np.int64)                # sindy.py:396
+            cti = dataset.data['current_treatments'].astype(np.int64)                # sindy.py:396
             codes = (cti[..., 0] + 2 * cti[..., 1]).astype(np.uint8)
         else:
             # argmax of the one-hot rows (sindy.py:397).  The product's own dataset classes keep the index array the
-            # one-hot encoding was built from (0.4 s of numpy argmax per 767k x 59 rows otherwise)
+            # one-hot encoding is built from (and drop it when 'current_treatments' is reassigned), so neither the
+            # 1.2 GB one-hot array of a 10k/1k/1k collection nor its argmax (0.4 s) is needed here
             cached = getattr(dataset, 'treatment_codes_', None)
-            if cached is not None and getattr(dataset, '_codes_owner', None) is ct:
+            if cached is not None and cached.shape == prev.shape:
                 codes = cached
             else:
-                codes = np.argmax(ct, axis=-1).astype(np.uint8)
+                codes = np.argmax(dataset.data['current_treatments'], axis=-1).astype(np.uint8)
         seq = dataset.data['sequence_lengths'].astype(np.int64)
         return prev, static[:, 0], codes, seq
 
