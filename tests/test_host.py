@@ -136,3 +136,33 @@ def test_dataset_transforms_equal_the_restatement(mode):
     for k in want5:
         assert np.array_equal(seq.data_processed_seq[k], want5[k]), ('seq5', k)
     assert 'future_past_split' not in seq.data_original
+
+
+def test_lazy_dataset_dictionary_behaves_like_a_dict():
+    """dataset.LazyDict: pending arrays are ordinary keys for indexing / `in` / get, enumeration and pickling build
+    them, copies stay lazy and share arrays, assigning a watched key fires its hook."""
+    import copy
+    import pickle
+    from b200_insite.dataset import LazyDict
+    calls = []
+    d = LazyDict(a=np.arange(3))
+    d.set_lazy('b', lambda: calls.append('b') or np.ones(2))
+    fired = []
+    d.on_set('b', lambda: fired.append(1))
+    assert 'b' in d and len(d) == 2 and not calls
+    c = d.copy()
+    assert isinstance(c, LazyDict) and c['a'] is d['a'] and not calls
+    assert d.get('zz', 7) == 7 and d.get('b').sum() == 2 and calls == ['b']
+    assert d['b'] is d['b'] and calls == ['b']                       # built once
+    assert sorted(c.keys()) == ['a', 'b'] and calls == ['b', 'b']    # the copy builds its own on enumeration
+    p = pickle.loads(pickle.dumps(c))
+    assert type(p) is dict and sorted(p) == ['a', 'b']
+    e = LazyDict(x=1)
+    e.set_lazy('y', lambda: [1, 2])
+    assert type(copy.deepcopy(e)) is dict and dict(e) == {'x': 1, 'y': [1, 2]}
+    d['b'] = np.zeros(1)
+    assert fired == [1] and d['b'].shape == (1,)
+    with pytest.raises(KeyError):
+        d['missing']
+    del c['b']
+    assert 'b' not in c
