@@ -4,22 +4,23 @@
 // The reference draws four (N,T) float64 arrays before its loop (cancer_simulation.py:275-279) and K1 reads them
 // from HBM: 1.9 of the 6.3 GB a 1M-patient launch moves, and 2 GB per step over PCIe when the cohort starts on the
 // host.  SURVEY.md 8(d) names the lean variant: device generator, outputs = volume (float64) + one treatment-code
-// byte per step + sequence length.  This kernel is that variant:
+// byte per step + sequence length.  The kernels of this file are that variant:
 //   * thread = patient, warp = 32 consecutive patients, no CTA-wide synchronisation in the main loop;
 //   * draws: Philox4x32-10 counted by (global patient, column pair, stream) -- philox.cuh -- so a patient's draws do
 //     not depend on the launch shape, the shard or the number of GPUs; b200i_philox_draws exports the same numbers
-//     as the four (N,T) arrays, and b200i_sim_factual on those arrays reproduces this kernel bit for bit (tested);
-//   * column arithmetic: ws_body of the tiled kernel (three independent chains per column, fastmath.cuh), tiles
+//     as the four (N,T) arrays, and b200i_sim_factual on those arrays reproduces these kernels bit for bit (tested);
+//   * column arithmetic: ws_body / ws_col = the lean three-chain column of the tiled kernel (fastmath.cuh); tiles
 //     outside its preconditions take the generic column function with the same draws;
-//   * volume: 16-column x 32-patient SWIZZLE_128B tiles in shared memory, two per warp, stored by TMA
-//     (cp.async.bulk.tensor, the next box is computed while the previous one drains);
+//   * volume: 16-column x 32-patient SWIZZLE_128B tiles in shared memory, stored by TMA (cp.async.bulk.tensor);
 //   * treatment codes chemo + 2*radio: one byte per step, staged per tile in shared memory (odd word pitch) and
 //     written with coalesced 16-byte stores; layout = what b200i_theta_gram_codes reads;
 //   * STATS 2: the six per-patient moment sums of get_scaling_params (as b200i_sim_factual_side);
-//     STATS 1: the population statistics of K4 accumulated on the fly (Gram + moments), reduced in a fixed order:
-//     parameters in, fit statistics out, 0.55 KB written per patient.
-// HBM traffic: 80 B read + T*8 + ceil16(T) + 8 (+48) B written per patient -- the kernel is bound by instruction
-// issue (FP64 chains + ~170 integer instructions per column for the generator), not by memory.
+//     STATS 1: the population statistics of K4 accumulated on the fly (Gram + moments), reduced in a fixed order.
+// Two generations (identical bits; `variant` of b200i_sim_factual_rng): sim_factual_rng_kernel inlines the generator
+// into a four-column loop body (12 warps / SM; bound by instruction fetch), sim_factual_rng2_kernel (the default,
+// further down) splits generator and simulator into two short loops (16 warps / SM; bound by instruction issue).
+// HBM traffic: 80 B read + T*8 + ceil16(T) + 8 (+48) B written per patient = 7 % of the HBM peak at 1.17 ms per
+// million patients -- these kernels are bound by the SM front end and the FP64 pipe, not by memory.
 #pragma once
 #include "philox.cuh"
 
