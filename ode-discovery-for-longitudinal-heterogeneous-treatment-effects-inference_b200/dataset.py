@@ -152,6 +152,22 @@ class SyntheticCancerDataset:
     def get_scaling_params(self):
         return get_scaling_params(self.data)
 
+    # The reference caches whole collections with shelve (run_utils.py:4-19), i.e. pickles them: the row builders are
+    # closures and stay behind; a restored dataset reads the (then materialised) arrays instead.
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_treatment_rows', None)
+        state.pop('_covariate_rows', None)
+        return state
+
+    def _rows_of_treatments(self, rows, cols):
+        f = getattr(self, '_treatment_rows', None)
+        return f(rows, cols) if f is not None else self.data['current_treatments'][rows, cols, :]
+
+    def _rows_of_covariates(self, rows, cols):
+        f = getattr(self, '_covariate_rows', None)
+        return f(rows, cols) if f is not None else self.data['current_covariates'][rows, cols, :]
+
     # -- dataset.py:92-192 ---------------------------------------------------------------------------
     def process_data(self, scaling_params, include_continuous_treatment=False):
         if self.processed:
@@ -250,11 +266,11 @@ class SyntheticCancerDataset:
         k = np.arange(H)[None, :]
         # prev = prev_treatments[:, 1:] = current_treatments[:, :-1]  (W - 1 entries)
         prev_idx = np.mod(fact[:, None] - 1 + k, W - 1)   # python slices with a negative start never occur (sl > H)
-        cov_last = self._covariate_rows(np.arange(R), fact - 1)                    # current_covariates[i, fact-1]
+        cov_last = self._rows_of_covariates(np.arange(R), fact - 1)                    # current_covariates[i, fact-1]
         seq = {
             'active_encoder_r': (np.arange(W - H)[None, :] < fact[:, None]).astype(np.float64),
-            'prev_treatments': self._treatment_rows(rows, prev_idx),
-            'current_treatments': self._treatment_rows(rows, fact[:, None] + k),
+            'prev_treatments': self._rows_of_treatments(rows, prev_idx),
+            'current_treatments': self._rows_of_treatments(rows, fact[:, None] + k),
             'current_covariates': np.repeat(cov_last[:, None, :], H, axis=1),
             'outputs': outputs[rows, fact[:, None] + k, :],
             'sequence_lengths': np.full(R, float(H)),

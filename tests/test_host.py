@@ -136,6 +136,19 @@ def test_dataset_transforms_equal_the_restatement(mode):
     for k in want5:
         assert np.array_equal(seq.data_processed_seq[k], want5[k]), ('seq5', k)
     assert 'future_past_split' not in seq.data_original
+    # the reference caches collections with shelve (run_utils.py:4-19): a pickled + restored collection is equal, and a
+    # restored dataset that is processed only afterwards still works (row builders are closures and stay behind)
+    import pickle
+    back = pickle.loads(pickle.dumps(col))
+    for k in keys:
+        assert np.array_equal(back.test_cf_treatment_seq.data[k], want[k]), ('pickled', k)
+    assert np.array_equal(back.test_cf_treatment_seq.data_processed_seq['outputs'], want5['outputs'])
+    fresh = mk(o['seq'], 'test')
+    fresh.process_data(col.train_f.get_scaling_params())
+    fresh = pickle.loads(pickle.dumps(fresh))
+    fresh.process_sequential_test(5)
+    for k in want5:
+        assert np.array_equal(fresh.data[k], want5[k]), ('restored', k)
 
 
 def test_lazy_dataset_dictionary_behaves_like_a_dict():
