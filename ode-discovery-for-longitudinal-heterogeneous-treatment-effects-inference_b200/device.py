@@ -244,7 +244,8 @@ def theta_gram_codes(cancer_volume, codes, sequence_lengths, static_feature, pat
     pitch = row_pitch(cancer_volume) if n > 1 else T
     rc = lib.b200i_theta_gram_codes(n, T, pitch, 1 if joint else 0, float(fd_dt), _ptr_rows(cancer_volume), _ptr(codes),
                                     int(codes.shape[1]), _ptr(sequence_lengths), _ptr(static_feature),
-                                    _ptr(patient_moments), int(patient_moments.shape[1]), _ptr(ws), _stream())
+                                    ctypes.c_void_p(patient_moments.data_ptr()), int(patient_moments.stride(0)), _ptr(ws),
+                                    _stream())
     _native.check(rc, "b200i_theta_gram_codes")
     return ws[:STATS_DOUBLES]
 
