@@ -68,6 +68,15 @@ def pack_stats(G, b, counts, moments=None):
     return out
 
 
+def chunk_bounds(n, chunks):
+    """Column ranges of the chunked upload (the formula of b200i_upload_simulate_rng): at most `chunks` ranges of
+    whole 32-patient tiles that cover [0, n)."""
+    n, chunks = int(n), max(1, min(int(chunks), n // 32 if n >= 32 else 1))
+    step = -(-n // chunks)
+    step = -(-step // 32) * 32
+    return [(a, min(a + step, n)) for a in range(0, n, step)]
+
+
 def source_prefix_length(row_offsets, n_total):
     """Number of leading patients whose rows cover row indices [0, n_total): the global source prefix every
     rank must simulate before its own shard of a counterfactual cohort (cross-row window)."""
@@ -176,10 +185,7 @@ class GeneratedFitPipeline:
         self.patient_moments = torch.empty((6, self.n), **f64)
         self.stats = torch.zeros(dev.STATS_DOUBLES, **f64)
         self.coefs = self.support = None
-        chunks = max(1, min(int(chunks), self.n // 32 if self.n >= 32 else 1))
-        step = -(-self.n // chunks)
-        step = -(-step // 32) * 32                                   # whole 32-patient tiles per chunk
-        self.bounds = [(a, min(a + step, self.n)) for a in range(0, self.n, step)]   # what the C side will use
+        self.bounds = chunk_bounds(self.n, chunks)                   # what the C side will use
         self.chunks = len(self.bounds)
         self.copy_stream = torch.cuda.Stream()
         self.chunk_ws = dev.chunk_workspaces(self.chunks)

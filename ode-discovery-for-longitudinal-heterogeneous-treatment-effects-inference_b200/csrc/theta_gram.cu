@@ -192,23 +192,38 @@ theta_gram2_kernel(int64_t n, int T, int64_t rp, int mode, double fd_dt, double 
             mbar_arrive(&bars[warp]);
         }
         if (CODES) {
-            // code bytes: 16 per 16-byte load, item = (row, 16-byte unit); transposed into the [T][33] table
-            const int units = (T + 15) >> 4;
-            for (int e = lane; e < rows * units; e += 32) {
-                const int j = e / units, uq = e - j * units;
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(codes + (first + j) * code_pitch) + uq);
-                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+            // everything this tile needs from global memory is requested before the first dependent instruction:
+            // the per-patient scalars, then the code bytes in batches of four 16-byte loads per lane (item = (row,
+            // 16-byte unit)), which are transposed into the [T][33] table while the volume rows are still in flight
+            const int64_t pidx = first + (lane < rows ? lane : 0);
+            const double p0 = __ldg(pmom + 0 * mstride + pidx), p1 = __ldg(pmom + 1 * mstride + pidx);
+            const double p2 = __ldg(pmom + 2 * mstride + pidx), p3 = __ldg(pmom + 3 * mstride + pidx);
+            const double p4 = __ldg(pmom + 4 * mstride + pidx), p5 = __ldg(pmom + 5 * mstride + pidx);
+            const int units = (T + 15) >> 4, items = rows * units;
+            for (int e0 = 0; e0 < items; e0 += 128) {
+                uint4 v[4];
+                int jj[4], uu[4];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int col = uq * 16 + q;
-                    if (col < T) s_code[col * 33 + j] = (uint8_t)((wv[q >> 2] >> (8 * (q & 3))) & 3u);
+                for (int b = 0; b < 4; ++b) {
+                    const int e = e0 + 32 * b + lane;
+                    const int ec = e < items ? e : 0;
+                    jj[b] = ec / units; uu[b] = ec - jj[b] * units;
+                    v[b] = __ldg(reinterpret_cast<const uint4 *>(codes + (first + jj[b]) * code_pitch) + uu[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (e0 + 32 * b + lane < items) {
+                        const unsigned wv[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int col = uu[b] * 16 + q;
+                            if (col < T) s_code[col * 33 + jj[b]] = (uint8_t)((wv[q >> 2] >> (8 * (q & 3))) & 3u);
+                        }
+                    }
                 }
             }
             if (lane < rows) {   // the simulator's per-patient sums over the active entries
-                const int64_t pidx = first + lane;
-                mv += __ldg(pmom + 0 * mstride + pidx);  mvv += __ldg(pmom + 1 * mstride + pidx);
-                mc += __ldg(pmom + 2 * mstride + pidx);  mcc += __ldg(pmom + 3 * mstride + pidx);
-                md += __ldg(pmom + 4 * mstride + pidx);  mdd += __ldg(pmom + 5 * mstride + pidx);
+                mv += p0; mvv += p1; mc += p2; mcc += p3; md += p4; mdd += p5;
             }
         }
         // the four other arrays, two columns per lane and row

@@ -78,3 +78,24 @@ def test_source_prefix_length():
     assert source_prefix_length(off, 236) == 1
     assert source_prefix_length(off, 237) == 2
     assert source_prefix_length(off, 936) == 4
+
+
+def test_generated_cohort_sharding_is_a_partition_of_the_global_counter_space():
+    """GeneratedFitPipeline: rank r simulates global patients [lo_r, hi_r) (patient_base = lo_r), and within a rank the
+    upload chunks are whole 32-patient tiles that cover the shard once: every global patient index -- the counter of
+    the draw generator -- is simulated exactly once for any world size and chunk count."""
+    from b200_insite.cohort import shard_bounds, chunk_bounds
+    for n_total in (1, 31, 32, 1000, 4133, 1_000_003):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            for rank in range(world):
+                lo, hi = shard_bounds(n_total, rank, world)
+                assert lo == seen
+                for chunks in (1, 4, 16, 64):
+                    b = chunk_bounds(hi - lo, chunks) if hi > lo else []
+                    assert len(b) <= chunks
+                    assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+                    assert (not b) or (b[0][0] == 0 and b[-1][1] == hi - lo)
+                    assert all(a % 32 == 0 for a, _ in b)
+                seen = hi
+            assert seen == n_total
