@@ -5,10 +5,21 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port of the reference)
 
 Workload (BASELINE.json configs[1]): cancer_sim factual simulation + INSITE population fit at
-1M patients x 60 steps per GPU, FP64.  One "step" = one pass of the hot path over the cohort:
-K1 simulate_factual (reference I/O contract: 4 pre-drawn (N,60) draw arrays in, 9 (N,60) arrays +
-sequence lengths out) -> K4 theta_gram + moments -> [allreduce of 68 doubles] -> K5 STLSQ.
+1M patients x 60 steps per GPU, FP64.  One "step" = one pass of the hot path over the cohort.
 metric = executed patient-steps per second (sum over patients of sequence_length-1).
+
+Keys of the JSON line beyond the contract:
+  value / ms_per_step   device-resident step on the reference I/O contract: K1 simulate_factual (4 pre-drawn (N,60)
+                        draw arrays in, 9 (N,60) arrays + sequence lengths out, + code bytes / per-patient moments for
+                        the fit) -> K4 theta_gram_codes -> [all-reduce of 68 doubles] -> K5 STLSQ
+  roofline              K1, HBM-bound: algorithmic bytes (6328 B/patient) / CUDA-event time of the launch alone
+  roofline_theta_gram   K4, by SURVEY 8d's 1456 B/patient; read_gbs = bytes the lean launch actually reads
+  e2e                   host parameters in -> coefficients out (GeneratedFitPipeline.step_host): the draws come from
+                        the device generator inside the simulator kernel (K1L), chunked H2D overlapped with compute
+  e2e_host_draws        the same through the pre-drawn-array contract (2 GB of draws per step over PCIe)
+  device_rng            the generated-draws path with parameters resident (K1L -> K4 -> K5)
+  individualisation     per-patient STLSQ fits/s (K5b) and discovered-ODE rollout steps/s (K6): BASELINE's second metric
+  cpu_baseline          the oracle's C restatement on one host thread, bounded sample (N=1 only)
 """
 import argparse
 import json
