@@ -204,3 +204,29 @@ def test_sim_factual_rng_tiny_and_empty_cohorts(dev, n):
     torch.cuda.synchronize()
     assert torch.equal(vol, out['cancer_volume']) and torch.equal(sl, out['sequence_lengths'])
     np.testing.assert_allclose(stats.cpu().numpy(), alone.cpu().numpy(), rtol=1e-12, atol=1e-9)
+
+
+def test_sim_factual_rng_full_size_equals_k1_on_exported_draws(dev):
+    """BASELINE size (1M patients x 60 steps): the generated-draws kernel and K1 on the exported draws agree bit for
+    bit (row indices beyond 2^16 tiles, 64-bit offsets), and the chunked host pipeline reproduces the same cohort."""
+    import torch
+    from b200_insite.cohort import GeneratedFitPipeline
+    n, T, seed, base = 1_000_000, 60, 77, 3_000_000_000
+    params = _cohort(n, 88)
+    block = torch.from_numpy(dev.pack_params(params))
+    pd_ = block.cuda()
+    draws = dev.philox_draws(n, T, seed, patient_base=base, pitch=64)
+    out, _ = dev.sim_factual(pd_, *draws, T)
+    del draws
+    vol, codes, sl, pm, _ = dev.sim_factual_rng(pd_, T, seed, patient_base=base)
+    torch.cuda.synchronize()
+    assert torch.equal(vol, out['cancer_volume']) and torch.equal(sl, out['sequence_lengths'])
+    assert torch.equal(codes[:, :T], (out['chemo_application'] + 2 * out['radio_application']).to(torch.uint8))
+    del out
+    pipe = GeneratedFitPipeline(n, T, seed=seed, patient_base=base, chunks=16)
+    static = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.float64)).pin_memory()
+    res = torch.zeros(32 + dev.STATS_DOUBLES, dtype=torch.float64).pin_memory()
+    pipe.step_host(block.pin_memory(), static, res)
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.volume, vol) and torch.equal(pipe.codes, codes) and torch.equal(pipe.patient_moments, pm)
+    assert 55.0 < float(sl.mean()) < 58.0 and np.isfinite(res.numpy()).all()
