@@ -367,6 +367,14 @@ B200I_API int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t subs
                       const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
                       const double *static_feature, const double *theta0, double lam, double gtol,
                       int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+/* The same for the joint ("one ODE") model, sindy.py:503-517 with joint_model=True: theta0 / coefs_out hold the 11
+ * coefficients of [1, x0, u0, u1, u2, x0 u0, x0 u1, x0 u2, u0 u1, u0 u2, u1 u2] (x0 volume, u0 chemo, u1 radio
+ * application, u2 static feature); codes = chemo + 2*radio application per step; coefs_out is (rows, 11); the
+ * penalty is lam * mean over the 11 coefficients. */
+B200I_API int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
+                      const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
+                      const double *static_feature, const double *theta0, double lam, double gtol,
+                      int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
 
 #ifdef __cplusplus
 }

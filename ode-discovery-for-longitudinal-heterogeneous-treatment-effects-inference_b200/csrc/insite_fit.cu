@@ -164,6 +164,58 @@ __device__ __forceinline__ void eval_objective(const RowData &d, double theta, d
     g = gacc * inv / d.norm + d.lam * 2.0 * diff * (1.0 / 16.0);
 }
 
+// The same for the joint ("one ODE") model (sindy.py:503-517): one 11-term equation over (x0 = volume, u0 = chemo
+// application, u1 = radio application, u2 = static feature), library order of PolynomialLibrary(degree=2,
+// interaction_only=True): 1 x0 u0 u1 u2 x0u0 x0u1 x0u2 u0u1 u0u2 u1u2.  Lane j < 11 owns coefficient j; its basis value
+// is (x0 or 1) * w_j(treatment code), w_j tabulated per row for the four codes; the constant part and the slope of
+// the step's right-hand side are two masked sums over the lanes.  Lanes 11..15 carry zeros.
+__device__ __forceinline__ void eval_objective_joint(const RowData &d, double theta, double theta0, double mask_j,
+                                                     int j, unsigned gmask, double &f, double &g)
+{
+    const bool is_x = (j == 1) || (j >= 5 && j <= 7);
+    double wtab[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double ch = (double)(a & 1), ra = (double)(a >> 1), st = d.u;
+        double w;
+        switch (j) {
+            case 0: case 1: w = 1.0; break;
+            case 2: case 5: w = ch; break;
+            case 3: case 6: w = ra; break;
+            case 4: case 7: w = st; break;
+            case 8: w = ch * ra; break;
+            case 9: w = ch * st; break;
+            case 10: w = ra * st; break;
+            default: w = 0.0;
+        }
+        wtab[a] = w;
+    }
+    const double tm = theta * mask_j;
+    double v = d.x[0], s = 0.0, acc = 0.0, gacc = 0.0;
+    for (int k = 0; k < d.n_fit; ++k) {
+        const int a = d.codes[k] & 3;
+        const double wa = a == 0 ? wtab[0] : (a == 1 ? wtab[1] : (a == 2 ? wtab[2] : wtab[3]));
+        const double tw = tm * wa;
+        const double c_const = sum16(is_x ? 0.0 : tw, gmask);
+        const double c_x = sum16(is_x ? tw : 0.0, gmask);
+        const double wj = wa * mask_j;
+        for (int q = 0; q < d.substeps; ++q) {
+            const double fval = c_const + c_x * v;
+            const double dfj = is_x ? wj * v : wj;
+            s = s + d.h * (c_x * s + dfj);
+            v = v + d.h * fval;
+        }
+        const double r = d.x[k + 1] - v;
+        acc += r * r;
+        gacc += -2.0 * r * s;
+    }
+    const double inv = 1.0 / (double)d.n_fit;
+    const double diff = theta - theta0;
+    const double pen = sum16(diff * diff, gmask) * (1.0 / 11.0);
+    f = acc * inv / d.norm + d.lam * pen;
+    g = gacc * inv / d.norm + d.lam * 2.0 * diff * (1.0 / 11.0);
+}
+
 // minimiser of the cubic through (a,fa,fpa), (b,fb), (c,fc); NaN if it does not exist (scipy _cubicmin)
 __device__ __forceinline__ double cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc)
 {
@@ -185,7 +237,7 @@ __device__ __forceinline__ double quadmin(double a, double fa, double fpa, doubl
     return a - fpa / (2.0 * B);
 }
 
-template <int MINB>
+template <int MINB, bool JOINT = false>
 __global__ void __launch_bounds__(BFGS_THREADS, MINB)
 insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x,
                    const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
@@ -199,8 +251,13 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
     const int gbase = lane & 16;
     const unsigned gmask = 0xFFFFu << gbase;
     const int my_a = j >> 2, my_m = j & 3;
-    const double theta0 = theta0_g[j];
+    constexpr int NP = JOINT ? 11 : 16;                       // coefficients per row
+    const double theta0 = j < NP ? theta0_g[j] : 0.0;
     const double mask_j = fabs(theta0) > 1e-3 ? 1.0 : 0.0;   // coef_sparse_mask, sindy.py:589
+    auto objective = [&](const RowData &d, double th, double &f, double &g) {
+        if (JOINT) eval_objective_joint(d, th, theta0, mask_j, j, gmask, f, g);
+        else eval_objective(d, th, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+    };
     const int64_t ngroups = (int64_t)gridDim.x * BFGS_GROUPS;
     const int64_t iters = (rows + ngroups - 1) / ngroups;
 
@@ -220,7 +277,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
         __syncwarp(gmask);
         if (!valid) continue;
         if (n_fit <= 0) {   // sequence_length <= projection_horizon: population coefficients (sindy.py:571-585)
-            coefs_out[r * 16 + j] = theta0;
+            if (j < NP) coefs_out[r * NP + j] = theta0;
             if (j == 0) { status_out[r] = -2; fval_out[2 * r] = 0.0; fval_out[2 * r + 1] = 0.0; }
             continue;
         }
@@ -229,7 +286,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
         d.h = dt / substeps; d.substeps = substeps; d.norm = 1.0; d.lam = lam;
 
         double theta = theta0, f, g;
-        eval_objective(d, theta, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+        objective(d, theta, f, g);
         const double start_res = f;                 // norm_const = 1 (sindy.py:591-603)
         d.norm = 2.5 * start_res;                   // sindy.py:616
         int status = 0, it = 0;
@@ -237,7 +294,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
         if (!(d.norm > 0.0) || !isfinite(d.norm)) {
             status = 4;                             // perfect fit already (or non-finite): keep theta0
         } else {
-            eval_objective(d, theta, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+            objective(d, theta, f, g);
             f0 = f;
             double Hrow[16];
 #pragma unroll
@@ -268,7 +325,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                 bool need_zoom = false;
                 for (int i = 1; i <= 10; ++i) {
                     double fi, gi;
-                    eval_objective(d, theta + alpha * p, theta0, mask_j, my_a, my_m, gmask, gbase, fi, gi);
+                    objective(d, theta + alpha * p, fi, gi);
                     const double dphi_i = sum16(gi * p, gmask);
                     if (!isfinite(fi) || fi > phi0 + c1 * alpha * dphi0 || (fi >= phi_prev && i > 1)) {
                         lo = a_prev; phi_lo = phi_prev; dphi_lo = dphi_prev; hi = alpha; phi_hi = fi;
@@ -302,7 +359,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                             if (isnan(aj) || aj > a_max - fabs(qchk) || aj < a_min + fabs(qchk)) aj = lo + 0.5 * dalpha;
                         }
                         double fj, gj;
-                        eval_objective(d, theta + aj * p, theta0, mask_j, my_a, my_m, gmask, gbase, fj, gj);
+                        objective(d, theta + aj * p, fj, gj);
                         const double dphi_j = sum16(gj * p, gmask);
                         if (!isfinite(fj) || fj > phi0 + c1 * aj * dphi0 || fj >= phi_lo) {
                             a_rec = hi; phi_rec = phi_hi; have_rec = true;
@@ -353,7 +410,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
             if (it >= max_iter && status == 0) status = 1;
             if (!(f <= f0) || !isfinite(f)) { theta = theta0; f = f0; status = 6; }   // never accept a worse point
         }
-        coefs_out[r * 16 + j] = theta;
+        if (j < NP) coefs_out[r * NP + j] = theta;
         if (j == 0) { status_out[r] = status | (it << 8); fval_out[2 * r] = f0; fval_out[2 * r + 1] = f; }
     }
 }
@@ -393,21 +450,31 @@ extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t sub
     int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
-    // resident CTAs per SM the register budget is sized for; B200I_K7_MINB overrides (tuning aid)
-    static const int minb = getenv("B200I_K7_MINB") ? atoi(getenv("B200I_K7_MINB")) : K7_MINB_DEFAULT;
-    cudaStream_t st_ = static_cast<cudaStream_t>(stream);
-    if (minb == 3)
-        insite_bfgs_kernel<3><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
+    // register budget for 4 CTAs per SM (measured: 3 -> 85 ms, 4 -> 69 ms, 5 -> 76 ms per 200k rows)
+    insite_bfgs_kernel<K7_MINB_DEFAULT, false><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
         max_iter, coefs_out, status_out, fval_out);
-    else if (minb == 5)
-        insite_bfgs_kernel<5><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
-        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-        max_iter, coefs_out, status_out, fval_out);
-    else
-        insite_bfgs_kernel<4><<<(unsigned)grid, BFGS_THREADS, 0, st_>>>(
-        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-        max_iter, coefs_out, status_out, fval_out);
-
     return check_cuda(cudaGetLastError(), "insite_bfgs launch");
+}
+
+extern "C" int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
+                                       const uint8_t *codes, const int32_t *sequence_lengths,
+                                       int32_t projection_horizon, const double *static_feature, const double *theta0,
+                                       double lam, double gtol, int32_t max_iter, double *coefs_out,
+                                       int32_t *status_out, double *fval_out, void *stream)
+{
+    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs_joint: negative rows");
+    if (rows == 0) return 0;
+    B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
+                  B200I_E_ARG, "insite_bfgs_joint: NULL argument");
+    B200I_REQUIRE(W >= 2 && W <= BFGS_MAXW, B200I_E_UNSUPPORTED, "insite_bfgs_joint: W=%d outside [2,%d]", W, BFGS_MAXW);
+    B200I_REQUIRE(dt > 0 && substeps >= 1 && lam >= 0 && max_iter >= 1, B200I_E_ARG,
+                  "insite_bfgs_joint: bad scalar argument");
+    int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    insite_bfgs_kernel<K7_MINB_DEFAULT, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+        max_iter, coefs_out, status_out, fval_out);
+    return check_cuda(cudaGetLastError(), "insite_bfgs_joint launch");
 }

@@ -329,10 +329,19 @@ def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3,
 
 
 def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol=1e-12,
-                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT):
-    """K7.  Returns (coefs (R,4,4), status (R,) int32, fval (R,2))."""
+                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT, joint=False):
+    """K7.  Returns (coefs (R,4,4) [joint: (R,11)], status (R,) int32, fval (R,2))."""
     lib = _native.load()
     rows, W = x.shape
+    if joint:
+        coefs = torch.empty((rows, 11), dtype=torch.float64, device='cuda')
+        status = torch.empty((rows,), dtype=torch.int32, device='cuda')
+        fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
+        rc = lib.b200i_insite_bfgs_joint(rows, W, float(dt), int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
+                                         int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam),
+                                         float(gtol), int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+        _native.check(rc, "b200i_insite_bfgs_joint")
+        return coefs, status, fval
     coefs = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
     status = torch.empty((rows,), dtype=torch.int32, device='cuda')
     fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')

@@ -397,6 +397,57 @@ def insite_objective(theta_flat, x, codes, u, n_fit, theta0_flat, lam, norm, dt=
     return val, grad.reshape(-1)
 
 
+def insite_objective_joint(theta11, x, codes, u, n_fit, theta0_11, lam, norm, dt=STANDARD_DT, steps=STEPS_FOR_DT,
+                            with_grad=True):
+    """f_to_min_func (sindy.py:781-794) for the joint model (pred_dy_dt of :503-517: one 11-term expression in
+    x0 = volume, u0 = chemo, u1 = radio application, u2 = static feature) + gradient by forward sensitivities.
+    codes = chemo + 2*radio per step."""
+    theta = np.asarray(theta11, dtype=np.float64).reshape(11)
+    theta0 = np.asarray(theta0_11, dtype=np.float64).reshape(11)
+    mask = (np.abs(theta0) > 1e-3).astype(np.float64)
+    c = theta * mask
+    h = dt / steps
+    v = float(x[0])
+    s = np.zeros(11)
+    acc = 0.0
+    gacc = np.zeros(11)
+    for k in range(int(n_fit)):
+        u0, u1 = float(int(codes[k]) & 1), float(int(codes[k]) >> 1)
+        for _ in range(steps):
+            basis = np.array([1.0, v, u0, u1, u, v * u0, v * u1, v * u, u0 * u1, u0 * u, u1 * u])
+            f = float(np.dot(c, basis))
+            if with_grad:
+                dfdv = c[1] + c[5] * u0 + c[6] * u1 + c[7] * u
+                s = s + h * (dfdv * s + basis * mask)
+            v = v + h * f
+        r = x[k + 1] - v
+        acc += r * r
+        if with_grad:
+            gacc += -2.0 * r * s
+    diff = theta - theta0
+    val = acc / n_fit / norm + lam * np.mean(diff ** 2)
+    if not with_grad:
+        return val
+    return val, gacc / n_fit / norm + lam * 2.0 * diff / 11.0
+
+
+def insite_bfgs_row_joint(x, codes, u, seq_len, ph, theta0_11, lam, gtol=1e-12, maxiter=3200):
+    """_fine_tuning_inner for the joint model with scipy's BFGS (UNPINNED at the iterate level, like insite_bfgs_row)."""
+    from scipy.optimize import minimize
+    n_fit = int(min(seq_len - ph, len(x) - 1))
+    theta0 = np.asarray(theta0_11, dtype=np.float64).reshape(11)
+    if n_fit <= 0:
+        return theta0.copy(), 0.0, 0.0
+    start = insite_objective_joint(theta0, x, codes, u, n_fit, theta0, lam, 1.0, with_grad=False)
+    norm = 2.5 * start
+    if not (norm > 0) or not np.isfinite(norm):
+        return theta0.copy(), 0.0, 0.0
+    fun = lambda t: insite_objective_joint(t, x, codes, u, n_fit, theta0, lam, norm)
+    res = minimize(fun, theta0.copy(), jac=True, method='BFGS', options={'gtol': gtol, 'maxiter': maxiter})
+    f0 = fun(theta0)[0]
+    return (res.x if res.fun <= f0 else theta0.copy()), f0, min(res.fun, f0)
+
+
 def insite_bfgs_row(x, codes, u, seq_len, ph, theta0, lam, gtol=1e-12, maxiter=3200):
     """_fine_tuning_inner (sindy.py:587-631) with scipy's BFGS standing in for jax's (UNPINNED: the two
     differ at the iterate level).  Returns (theta (4,4), f0, f_end)."""

@@ -197,3 +197,73 @@ def test_joint_model_class_reproduces_reference_ablation_log(dev, collection_joi
     np.testing.assert_allclose(got, log['decoder_test_rmse_2_to_6_step'], rtol=1e-8)
     assert res['global_equation_string'][:30] == log['global_equation_string'][:30]
     assert res['global_equation_string'].count('*') == log['global_equation_string'].count('*')
+
+
+def _rows_joint(collection, which, n_rows, seed=0):
+    ds = collection.test_cf_one_step if which == 'one' else collection.test_cf_treatment_seq
+    sp = ds.scaling_params
+    prev = np.squeeze(ds.data['prev_outputs'] * sp['output_stds'] + sp['output_means'], -1)
+    static = (ds.data['static_features'] * sp['inputs_stds'][1:2] + sp['input_means'][1:2])[:, 0]
+    ct = ds.data['current_treatments'].astype(np.int64)
+    codes = (ct[..., 0] + 2 * ct[..., 1]).astype(np.uint8)
+    seq = ds.data['sequence_lengths'].astype(np.int64)
+    idx = np.random.RandomState(seed).choice(prev.shape[0], n_rows, replace=False)
+    return prev[idx], static[idx], codes[idx], seq[idx]
+
+
+def test_joint_bfgs_objective_and_optimum_vs_scipy(dev, collection_joint):
+    """b200i_insite_bfgs_joint: the reported objective values are the restated f_to_min_func of the 11-term joint
+    model at the same points (1e-9), the optimum is at least as good as scipy-BFGS on the same objective, masked
+    coefficients never move."""
+    import torch
+    from oracle import sindy_np as sp
+    theta0 = np.array(h.load_json('ref_log_joint_seed10.json')['sindy']['coefs'])
+    for which, ph in (('one', 1), ('seq', 5)):
+        x, u, codes, seq = _rows_joint(collection_joint, which, 32, seed=6)
+        coefs, status, fval = dev.insite_bfgs(dev.to_device(x), dev.to_device(codes, dtype=torch.uint8),
+                                              dev.to_device(seq, dtype=torch.int32), ph, dev.to_device(u),
+                                              dev.to_device(theta0), lam=10.0, joint=True)
+        torch.cuda.synchronize()
+        coefs, status, fval = coefs.cpu().numpy(), status.cpu().numpy(), fval.cpu().numpy()
+        assert coefs.shape == (32, 11)
+        W = x.shape[1]
+        for r in range(x.shape[0]):
+            n_fit = min(int(seq[r]) - ph, W - 1)
+            if n_fit <= 0:
+                assert status[r] == -2 and np.array_equal(coefs[r], theta0)
+                continue
+            start = sp.insite_objective_joint(theta0, x[r], codes[r], u[r], n_fit, theta0, 10.0, 1.0, with_grad=False)
+            norm = 2.5 * start
+            f0 = sp.insite_objective_joint(theta0, x[r], codes[r], u[r], n_fit, theta0, 10.0, norm, with_grad=False)
+            fe = sp.insite_objective_joint(coefs[r], x[r], codes[r], u[r], n_fit, theta0, 10.0, norm, with_grad=False)
+            np.testing.assert_allclose(fval[r, 0], f0, rtol=1e-9)
+            np.testing.assert_allclose(fval[r, 1], fe, rtol=1e-9)
+            _, _, f_scipy = sp.insite_bfgs_row_joint(x[r], codes[r], u[r], seq[r], ph, theta0, 10.0)
+            assert fe <= f_scipy * (1 + 1e-6) + 1e-12, (which, r, fe, f_scipy, status[r])
+            assert fe <= f0
+            small = np.abs(theta0) <= 1e-3
+            assert np.array_equal(coefs[r][small], theta0[small])
+
+
+def test_joint_insite_class_close_to_reference_ablation_log(dev, collection_joint):
+    """INSITE on the joint model through the class API vs results/ablation/one_ode/...txt:6 (optimiser restated, rows
+    with a failed zoom fall back to the population coefficients as sindy.py:628-631 => one-step RMSEs to 8e-3
+    relative (measured: 5.5e-4 .. 4.9e-3), tau-step RMSEs within -7 % / +0.2 %; the population line of the same run matches to 1e-8).  Keeping the progress of those rows instead
+    gives lower errors than the reference reports."""
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    log = h.load_json('ref_log_joint_seed10.json')['insite']
+    res, model = run_experiment(default_config(insite=True, seed=10, treatment_mode='multilabel', joint_model=True),
+                                collection_joint)
+    print(model.last_fit_info, {k: res[k] for k in res if 'rmse' in k})
+    for k in ('encoder_test_rmse_all', 'encoder_test_rmse_orig', 'encoder_test_rmse_last'):
+        np.testing.assert_allclose(res[k], log[k], rtol=8e-3)
+    got = [res[f'decoder_test_rmse_{k}-step'] for k in range(2, 7)]
+    # tau-step errors (fits on sequence_length - 5 points): jax's zoom fails on more rows than this line search does,
+    # and every such row falls back to the population ODE; ours are up to 5 % lower, never higher (unpinned optimiser)
+    ref5 = np.array(log['decoder_test_rmse_2_to_6_step'])
+    assert np.all(np.array(got) <= ref5 * 1.002) and np.all(np.array(got) >= ref5 * 0.93), got
+    assert res['fine_tuned'] is True and model.joint_coefs.shape == (1, 11) and model.zoom_failure_fallback
+    keep, _ = run_experiment(default_config(insite=True, seed=10, treatment_mode='multilabel', joint_model=True,
+                                            insite_zoom_failure_fallback=False), collection_joint)
+    assert keep['encoder_test_rmse_all'] < res['encoder_test_rmse_all']
