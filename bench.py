@@ -377,13 +377,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     k1l_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     gen_exec = gen.executed_steps()
+    # the reference's generate_params builds K and its four sigmoid rows from scalars (cancer_simulation.py:83-88, :202): found
+    # once per cohort (not per step), those rows are filled on the device instead of crossing PCIe
+    uniform = dev.uniform_param_rows(params) if args.uniform_rows else {}
     for _ in range(max(1, min(args.warmup, 3))):
-        gen.step_host(h_block, h_static, h_result)
+        gen.step_host(h_block, h_static, h_result, uniform=uniform)
     barrier()
     gen_e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(gen_e2e_steps):
-        gen.step_host(h_block, h_static, h_result)
+        gen.step_host(h_block, h_static, h_result, uniform=uniform)
     barrier()
     gen_e2e_ms = 1e3 * (time.perf_counter() - t0) / gen_e2e_steps
     clocks.stop.set(); clocks.t.join(timeout=6)
@@ -453,10 +456,12 @@ def run_b200(args):
                            "host_affinity": (f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus
                                              else "default")},
                 "clocks": clocks.summary(),
-                "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen.h2d_bytes(),
+                "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen.h2d_bytes(uniform),
+                        "uniform_parameter_rows": sorted(uniform),
                         "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": gen_e2e_ms,
                         "what": "GeneratedFitPipeline.step_host: pinned host parameters (the inputs of the reference's "
-                                "simulate_factual call, which draws its random numbers itself) -> H2D in "
+                                "simulate_factual call, which draws its random numbers itself; rows that are one scalar "
+                                "for the cohort -- generate_params' K and four sigmoid rows -- are filled on the device) -> H2D in "
                                 f"{len(gen.bounds)} chunks overlapped with K1L (simulator with the Philox4x32-10 draws "
                                 "generated in registers, bit-identical to K1 on the exported draws) -> theta_gram_codes "
                                 "-> STLSQ -> D2H coefficients/support/statistics"},
@@ -524,6 +529,8 @@ def main():
     ap.add_argument("--lean-fit", type=int, default=1, help="simulator side outputs + theta_gram_codes (default) or "
                     "the standalone five-array theta_gram")
     ap.add_argument("--rng-chunks", type=int, default=16, help="H2D/compute overlap chunks of the generated-draws e2e path")
+    ap.add_argument("--uniform-rows", type=int, default=1, help="e2e: fill cohort-wide scalar parameter rows on the device "
+                    "instead of copying them (0 = copy all ten rows)")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],
                     help="device-resident (N,T) arrays: rows padded to 128-byte lines, or the reference's dense rows")
     ap.add_argument("--ref-patients", type=int, default=400_000, help="bounded CPU sample")

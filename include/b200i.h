@@ -197,11 +197,15 @@ B200I_API int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, con
  * into params / static_feature in `chunks` column ranges on copy_stream, and every range is simulated on `stream`
  * (b200i_sim_factual_rng with the per-patient moments) as soon as it has arrived, so the PCIe transfer overlaps the
  * simulation.  Same outputs as one b200i_sim_factual_rng launch over all N patients.
+ * uniform_mask: bit r set = parameter row r is one scalar for the whole cohort (the reference's generate_params builds
+ * K and its four sigmoid rows that way, cancer_simulation.py:83-88, :202): the row is not read from params_host but filled on the
+ * device with uniform_values_host[r] (host array of 10 doubles; NULL when the mask is 0).
  * chunk_gram_workspaces != NULL (chunks x b200i_gram_workspace_bytes() bytes, with fd_dt > 0 and stats_out[68]): each
  * range's share of the population statistics (b200i_theta_gram_codes) is launched right behind its simulation and the
  * shares are summed in range order into stats_out, so only the last range's work is left when the copy ends. */
 B200I_API int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
-                     const double *params_host, const double *static_host, double *params, double *static_feature,
+                     const double *params_host, uint32_t uniform_mask, const double *uniform_values_host,
+                     const double *static_host, double *params, double *static_feature,
                      uint64_t seed, int64_t patient_base, double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
                      double *sequence_lengths, double *patient_moments_out, int32_t chunks,
                      double fd_dt, void *chunk_gram_workspaces, double *stats_out,

@@ -43,7 +43,8 @@ SIGNATURES = {
     "b200i_philox_draws": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.c_uint64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200i_sim_factual_rng": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, c_i64, ctypes.c_uint64,
                                              c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_f64, c_vp, c_i32, c_vp]),
-    "b200i_upload_simulate_rng": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, c_vp, c_vp, c_vp,
+    "b200i_upload_simulate_rng": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, ctypes.c_uint32,
+                                                 ctypes.POINTER(c_f64), c_vp, c_vp, c_vp,
                                                  ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_f64, c_vp, c_vp,
                                                  c_vp, c_vp]),
     "b200i_gram_workspace_bytes": (c_i64, []),

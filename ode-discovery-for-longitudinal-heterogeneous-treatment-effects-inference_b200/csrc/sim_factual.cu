@@ -685,8 +685,24 @@ __global__ void sum_chunk_stats_kernel(const uint8_t *ws_base, size_t ws_stride,
     out[i] = v;
 }
 
+// parameter rows that are one scalar for the whole cohort are filled on the device instead of being copied
+struct UniformRows {
+    double v[B200I_NUM_PARAMS];
+};
+__global__ void __launch_bounds__(256)
+fill_uniform_rows_kernel(double *__restrict__ params, int64_t n, uint32_t mask, UniformRows u)
+{
+    for (int r = 0; r < B200I_NUM_PARAMS; ++r) {
+        if (!((mask >> r) & 1u)) continue;
+        const double v = u.v[r];
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+            params[r * n + i] = v;
+    }
+}
+
 extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
-                                         const double *params_host, const double *static_host, double *params,
+                                         const double *params_host, uint32_t uniform_mask,
+                                         const double *uniform_values_host, const double *static_host, double *params,
                                          double *static_feature, uint64_t seed, int64_t patient_base,
                                          double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
                                          double *sequence_lengths, double *patient_moments_out, int32_t chunks,
@@ -704,6 +720,8 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
                   "upload_simulate_rng: NULL argument, or copy_stream == stream (no overlap possible)");
     B200I_REQUIRE((static_host == nullptr) == (static_feature == nullptr), B200I_E_ARG,
                   "upload_simulate_rng: static_host and static_feature must both be given or both be NULL");
+    B200I_REQUIRE(uniform_mask < (1u << B200I_NUM_PARAMS) && (uniform_mask == 0 || uniform_values_host), B200I_E_ARG,
+                  "upload_simulate_rng: uniform_mask 0x%x needs uniform_values_host[10]", uniform_mask);
     cudaStream_t cs = static_cast<cudaStream_t>(copy_stream), st = static_cast<cudaStream_t>(stream);
     int64_t step = (n + chunks - 1) / chunks;
     step = ((step + 31) / 32) * 32;   // whole 32-patient tiles per chunk
@@ -715,6 +733,12 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
     B200I_REQUIRE(devid >= 0 && devid < 16, B200I_E_UNSUPPORTED, "upload_simulate_rng: device index %d", devid);
     if (aux[devid] == nullptr) B200I_CUDA(cudaStreamCreateWithFlags(&aux[devid], cudaStreamNonBlocking));
     cudaStream_t sx = aux[devid];
+    if (uniform_mask) {   // stream-ordered after the previous readers of the block, before every chunk (event below)
+        UniformRows u;
+        for (int r = 0; r < B200I_NUM_PARAMS; ++r) u.v[r] = uniform_values_host[r];
+        fill_uniform_rows_kernel<<<num_sms() * 4, 256, 0, st>>>(params, n, uniform_mask, u);
+        B200I_CUDA(cudaGetLastError());
+    }
     // the previous work on `stream` may still read the parameter block / write the outputs
     cudaEvent_t ev;
     B200I_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -725,8 +749,15 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
     for (int64_t a = 0; a < n && !rc; a += step, ++c) {
         const int64_t b = (a + step < n) ? a + step : n;
         cudaStream_t run = (c & 1) ? sx : st;
-        rc = check_cuda(cudaMemcpy2DAsync(params + a, (size_t)n * 8, params_host + a, (size_t)n * 8, (size_t)(b - a) * 8,
-                                          B200I_NUM_PARAMS, cudaMemcpyHostToDevice, cs), "cudaMemcpy2DAsync(params)");
+        for (int r0 = 0; r0 < B200I_NUM_PARAMS && !rc;) {   // maximal runs of rows that are real arrays
+            if ((uniform_mask >> r0) & 1u) { ++r0; continue; }
+            int r1 = r0;
+            while (r1 < B200I_NUM_PARAMS && !((uniform_mask >> r1) & 1u)) ++r1;
+            rc = check_cuda(cudaMemcpy2DAsync(params + (size_t)r0 * n + a, (size_t)n * 8, params_host + (size_t)r0 * n + a,
+                                              (size_t)n * 8, (size_t)(b - a) * 8, r1 - r0, cudaMemcpyHostToDevice, cs),
+                            "cudaMemcpy2DAsync(params)");
+            r0 = r1;
+        }
         if (!rc && static_host)
             rc = check_cuda(cudaMemcpyAsync(static_feature + a, static_host + a, (size_t)(b - a) * 8,
                                             cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(static)");

@@ -82,6 +82,18 @@ def require_cuda():
     _native.load()
 
 
+def uniform_param_rows(params):
+    """{row index: value} of the parameter rows that hold one scalar for the whole cohort.  The reference's
+    generate_params builds K and the four sigmoid rows from scalars (cancer_simulation.py:83-88, :202); a chunked upload need not
+    send them.  One pass over the host arrays (a property of the cohort, found once, not per step)."""
+    out = {}
+    for r, k in enumerate(PARAM_KEYS):
+        a = np.asarray(params[k], dtype=np.float64)
+        if a.size and a.min() == a.max():
+            out[r] = float(a[0])
+    return out
+
+
 def pack_params(params):
     """dict of (N,) arrays (generate_params layout) -> (10,N) float64 numpy block."""
     return np.ascontiguousarray(np.stack([np.asarray(params[k], dtype=np.float64) for k in PARAM_KEYS], axis=0))
@@ -217,7 +229,7 @@ def chunk_workspaces(chunks):
 
 def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, seed, patient_base, consts, volume, codes,
                         sequence_lengths, patient_moments, chunks, copy_stream, chunk_ws=None, stats_out=None,
-                        fd_dt=STANDARD_DT):
+                        fd_dt=STANDARD_DT, uniform=None):
     """Pinned host parameters -> chunked H2D on copy_stream, each chunk simulated (K1L) on the current stream as soon
     as it has arrived (b200i_upload_simulate_rng).  chunk_ws (chunk_workspaces(chunks)) + stats_out (68,): each
     chunk's share of the population statistics is computed right behind its simulation and summed in chunk order."""
@@ -226,7 +238,12 @@ def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, see
     assert params_host.is_pinned() and params_host.is_contiguous() and tuple(params_host.shape) == (10, n)
     assert static_host is None or (static_host.is_pinned() and static_host.is_contiguous())
     vp = row_pitch(volume) if n > 1 else T
+    mask, vals = 0, (ctypes.c_double * 10)()
+    for r, v in (uniform or {}).items():     # parameter rows that are one scalar for the whole cohort: not copied
+        mask |= 1 << int(r)
+        vals[int(r)] = float(v)
     rc = lib.b200i_upload_simulate_rng(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
+                                       mask, vals if mask else None,
                                        None if static_host is None else ctypes.c_void_p(static_host.data_ptr()),
                                        _ptr(params_dev), _ptr(static_dev), int(seed), int(patient_base), _ptr_rows(volume),
                                        _ptr(codes), int(codes.shape[1]), _ptr(sequence_lengths), _ptr(patient_moments),

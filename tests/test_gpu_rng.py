@@ -150,6 +150,18 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     assert np.array_equal(res[32:].numpy(), a.stats.cpu().numpy())
     if chunks == 1:
         assert torch.equal(a.stats, b.stats)
+    # parameter rows that are one scalar for the cohort (K and the four sigmoid rows of generate_params) are filled on the
+    # device instead of being copied: same cohort, and a host block whose uniform rows hold garbage is never read there
+    uni = dev.uniform_param_rows(params)
+    assert sorted(uni) == [5, 6, 7, 8, 9]
+    junk = block.clone()
+    junk[5:10] = float('nan')
+    c = GeneratedFitPipeline(n, T, seed=3, patient_base=1000, chunks=chunks)
+    c.params.fill_(-1.0)
+    c.step_host(junk.pin_memory(), static, res, uniform=uni)
+    torch.cuda.synchronize()
+    assert torch.equal(c.params, b.params) and torch.equal(c.volume, b.volume) and torch.equal(c.codes, b.codes)
+    assert torch.equal(c.stats, a.stats) and c.h2d_bytes(uni) == 6 * n * 8
 
 
 def test_generated_counterfactual_draws_and_cohort(dev):
