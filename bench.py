@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0)
     ap.add_argument("--lean-fit", type=int, default=1, help="simulator side outputs + theta_gram_codes (default) or "
                     "the standalone five-array theta_gram")
-    ap.add_argument("--rng-chunks", type=int, default=16, help="H2D/compute overlap chunks of the generated-draws e2e path")
+    ap.add_argument("--rng-chunks", type=int, default=8, help="H2D/compute overlap chunks of the generated-draws e2e path")
     ap.add_argument("--uniform-rows", type=int, default=1, help="e2e: fill cohort-wide scalar parameter rows on the device "
                     "instead of copying them (0 = copy all ten rows)")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],

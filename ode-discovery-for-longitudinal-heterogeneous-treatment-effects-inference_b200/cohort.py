@@ -170,7 +170,7 @@ class GeneratedFitPipeline:
     which is exactly what the fit (b200i_theta_gram_codes -> all-reduce -> b200i_stlsq_population) consumes."""
 
     def __init__(self, n_local, T=60, seed=0, patient_base=0, window_size=15, threshold=1e-3, alpha=0.5, max_iter=100,
-                 chunks=16):
+                 chunks=8):
         dev.require_cuda()
         self.n, self.T = int(n_local), int(T)
         self.seed, self.patient_base = int(seed), int(patient_base)
