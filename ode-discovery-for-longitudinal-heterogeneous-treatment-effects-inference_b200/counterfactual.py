@@ -151,3 +151,58 @@ def treatment_seq_dense(simulation_params, seq_length, projection_horizon, draws
     return {k: dense[k].cpu().numpy() for k in
             ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'patient_types',
              'patient_ids_all_trajectories', 'patient_current_t')}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU: contiguous patient shards of one counterfactual cohort (the A3/A4 cross-row exception)
+# ------------------------------------------------------------------------------------------------------------------
+def rows_per_patient_floor(kind, H=5):
+    """Rows a patient emits at the very least per executed step (one-step: 4 options; sequences: 2H minus NaN drops,
+    in practice 2H) -- only used to size the first guess of the source prefix."""
+    return 4 if kind == 'one_step' else 2 * H
+
+
+def exchange_row_bases(total_rows_local):
+    """Exclusive scan of the per-rank row totals over the process group: (row index of this rank's first row, total
+    rows of the cohort).  This is the only exchange the sharded generators need (world_size int64 values); without a
+    process group it is (0, total_rows_local)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return 0, int(total_rows_local)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev_ = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    mine = torch.tensor([int(total_rows_local)], dtype=torch.int64, device=dev_)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    totals = [int(p.item()) for p in parts]
+    return sum(totals[:rank]), sum(totals)
+
+
+def sim_cf_shard(kind, T, H, n_total, global_base, shard_inputs, prefix_inputs, consts=None, row_base=None):
+    """One rank's shard [global_base, global_base + n_shard) of an n_total-patient counterfactual cohort.
+
+    Patient i's treatment probabilities read OUTPUT ROW i of the whole cohort (cancer_simulation.py:471 / :671), a row
+    emitted by one of the first ~n_total/227 (one-step) or ~n_total/562 (sequences) patients.  Every rank therefore
+    simulates that global source prefix itself (prefix_inputs: device params (10,P) + the four draw arrays of patients
+    0..P-1; with device-generated draws that is a regeneration, not a transfer), level by level, and then its own
+    shard in ONE launch against the prefix (b200i_cf_source): no collective on the data path.  The reference row
+    indices of the shard's rows need the row totals of the ranks before it: exchange_row_bases (one all-gather of an
+    int64 per rank), or row_base when the caller already knows it.
+
+    shard_inputs / prefix_inputs: (params_dev, noise, recovery, chemo_rvs, radio_rvs).
+    Returns (shard cohort with GLOBAL row_offsets, prefix cohort, total rows of the whole cohort or None)."""
+    run = sim_cf_one_step if kind == 'one_step' else sim_cf_treatment_seq
+    extra = () if kind == 'one_step' else (H,)
+    src = run(*prefix_inputs, T, *extra, consts=consts)
+    covered = int(src.row_offsets[-1].item())
+    if covered < n_total and src.n < n_total:
+        raise ValueError(f"source prefix of {src.n} patients emits {covered} rows but the cohort reads rows up to "
+                         f"{n_total}: simulate a longer prefix")
+    shard = run(*shard_inputs, T, *extra, consts=consts, global_base=int(global_base), source=src)
+    if row_base is None:
+        row_base, total = exchange_row_bases(shard.total_rows)
+    else:
+        total = None
+    shard.row_offsets += int(row_base)
+    shard.row_base = int(row_base)
+    return shard, src, total

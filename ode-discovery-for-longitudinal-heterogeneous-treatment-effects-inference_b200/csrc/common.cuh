@@ -10,6 +10,10 @@ namespace b200i {
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 int num_sms();
+// Process-wide, thread-safe launch configuration of a kernel with dynamic shared memory: raises the kernel's
+// MaxDynamicSharedMemorySize to `bytes` if it is lower (never lowers it, so concurrent callers with different sizes
+// cannot invalidate each other's launches) and returns the resident CTAs per SM for (threads, bytes) in *per_sm.
+int ensure_dyn_smem(const void *func, int bytes, int threads, int *per_sm);
 
 #define B200I_CUDA(call)                                   \
     do {                                                   \

@@ -2,6 +2,9 @@
 #include <cuda.h>
 #include <stdarg.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -38,22 +41,47 @@ int num_sms()
     return cached;
 }
 
+int ensure_dyn_smem(const void *func, int bytes, int threads, int *per_sm)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> raised;                   // (kernel, device) -> attribute value
+    static std::map<std::tuple<const void *, int, int, int>, int> occupancy;     // (kernel, device, threads, bytes)
+    int dev = 0;
+    B200I_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int &cur = raised[{func, dev}];
+    if (bytes > cur) {
+        B200I_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        cur = bytes;
+    }
+    if (per_sm) {
+        auto key = std::make_tuple(func, dev, threads, bytes);
+        auto it = occupancy.find(key);
+        if (it == occupancy.end()) {
+            int v = 0;
+            B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, func, threads, (size_t)bytes));
+            it = occupancy.emplace(key, v).first;
+        }
+        *per_sm = it->second;
+    }
+    return 0;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static encode_tiled_fn get_encode()
 {
-    static encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised exactly once, thread-safe (C++11 magic statics)
+    static const encode_tiled_fn fn = []() -> encode_tiled_fn {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<encode_tiled_fn>(p);
-    }
+            return reinterpret_cast<encode_tiled_fn>(p);
+        return nullptr;
+    }();
     return fn;
 }
 

@@ -529,14 +529,16 @@ template <typename Launch>
 static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, int *n_rows, int64_t *off,
                       int64_t *total_rows_host, int *levels_host, cudaStream_t st, Launch launch)
 {
+    // validate before allocating; every later exit goes through the cudaFreeAsync below
+    B200I_REQUIRE(source != nullptr || base == 0, B200I_E_ARG, "sim_cf: a shard (global_base > 0) needs a source cohort");
     int *d_err = nullptr;
     B200I_CUDA(cudaMallocAsync(&d_err, sizeof(int), st));
-    B200I_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-    B200I_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t), st));
     int levels = 0;
     int64_t total = 0;
-    int rc = 0;
-    if (source != nullptr) {
+    int rc = check_cuda(cudaMemsetAsync(d_err, 0, sizeof(int), st), "memset err");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(off, 0, sizeof(int64_t), st), "memset off");
+    if (rc) {
+    } else if (source != nullptr) {
         rc = launch(0, n, true, d_err);
         if (!rc) {
             scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, 0, n);
@@ -544,7 +546,6 @@ static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, in
         }
         levels = 1;
     } else {
-        B200I_REQUIRE(base == 0, B200I_E_ARG, "sim_cf: a shard (global_base > 0) needs a source cohort");
         int64_t lo = 0, hi = (n > 0) ? 1 : 0;
         while (lo < n && !rc) {
             rc = launch(lo, hi, false, d_err);

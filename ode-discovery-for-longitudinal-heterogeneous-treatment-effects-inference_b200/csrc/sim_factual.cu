@@ -495,9 +495,11 @@ extern "C" int b200i_sim_factual_side(int64_t n, int32_t T, int64_t row_pitch, c
                                       double *sequence_lengths, uint8_t *codes_out, int64_t code_pitch,
                                       double *patient_moments_out, int32_t variant, void *stream)
 {
-    B200I_REQUIRE(codes_out && patient_moments_out && code_pitch >= T && code_pitch % 2 == 0, B200I_E_ARG,
-                  "sim_factual_side: codes_out / patient_moments_out missing or code_pitch %lld < T or odd",
-                  (long long)code_pitch);
+    B200I_REQUIRE(codes_out && patient_moments_out, B200I_E_ARG, "sim_factual_side: codes_out / patient_moments_out missing");
+    // the kernel stores the code bytes of every 16-column box (the ragged last one included) as one 16-byte word
+    B200I_REQUIRE(code_pitch % 16 == 0 && code_pitch >= ((T + 15) / 16) * 16, B200I_E_ARG,
+                  "sim_factual_side: code_pitch %lld (multiple of 16, >= T rounded up to 16)", (long long)code_pitch);
+    B200I_REQUIRE(aligned16(codes_out), B200I_E_ALIGN, "sim_factual_side: codes_out must be 16-byte aligned");
     return sim_factual_impl(n, T, row_pitch, k, params, noise, recovery_rvs, chemo_rvs, radio_rvs, nullptr, cancer_volume,
                             chemo_dosage, radio_dosage, chemo_application, radio_application, chemo_probabilities,
                             radio_probabilities, death_flags, recovery_flags, sequence_lengths, nullptr, 1.0, nullptr,
@@ -646,6 +648,9 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
         int rc = encode_tmap_2d_pitched_f64(&vmap, cancer_volume, (uint64_t)n, (uint64_t)T, (uint64_t)row_pitch * 8, 32, 16);
         if (rc) return rc;
     }
+    // variant 0 / 2: second generation (phased, one column per loop body, 16 warps per SM); 1: first generation
+    // (four unrolled columns with the generator inlined, 12 warps per SM) -- kept as an independent cross-check
+    B200I_REQUIRE(variant >= 0 && variant <= 2, B200I_E_UNSUPPORTED, "sim_factual_rng: variant %d (0 auto, 1, 2)", variant);
     StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
     if (gram) {
         B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
@@ -655,9 +660,6 @@ extern "C" int b200i_sim_factual_rng(int64_t n, int32_t T, int64_t row_pitch, co
         return launch_rng<1, 3, 2>(vmap, n, params_stride, 0, T, c, params, seed, patient_base, codes_out, code_pitch,
                                    sequence_lengths, nullptr, static_feature, ws, st);
     }
-    // variant 0 / 2: second generation (phased, one column per loop body, 16 warps per SM); 1: first generation
-    // (four unrolled columns with the generator inlined, 12 warps per SM) -- kept as an independent cross-check
-    B200I_REQUIRE(variant >= 0 && variant <= 2, B200I_E_UNSUPPORTED, "sim_factual_rng: variant %d (0 auto, 1, 2)", variant);
     if (patient_moments_out) {
         if (variant == 1)
             return launch_rng<2, 3, 1>(vmap, n, params_stride, moments_stride, T, c, params, seed, patient_base, codes_out,

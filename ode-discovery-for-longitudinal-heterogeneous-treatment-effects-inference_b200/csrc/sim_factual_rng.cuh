@@ -604,16 +604,11 @@ static int launch_rng(const CUtensorMap &vmap, int64_t n, int64_t pstride, int64
     const int smem = RNG_WARPS * (GEN == 2 ? rng2_warp_bytes(T) : rng_warp_bytes(T)) + 1024;
     B200I_REQUIRE(smem <= 227 * 1024, B200I_E_UNSUPPORTED, "sim_factual_rng: T=%d does not fit in shared memory", T);
     // attribute + occupancy once per (device, shared-memory size): a chunked pipeline launches this 16x per 2 ms step
-    static thread_local int cfg_smem[16], cfg_per_sm[16];
-    int devid = 0;
-    B200I_CUDA(cudaGetDevice(&devid));
-    B200I_REQUIRE(devid >= 0 && devid < 16, B200I_E_UNSUPPORTED, "sim_factual_rng: device index %d", devid);
-    if (cfg_smem[devid] != smem) {
-        B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm[devid], kern, RNG_WARPS * 32, smem));
-        cfg_smem[devid] = smem;
+    int per_sm = 0;
+    {
+        int rc = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem, RNG_WARPS * 32, &per_sm);
+        if (rc) return rc;
     }
-    const int per_sm = cfg_per_sm[devid];
     B200I_REQUIRE(per_sm >= 1, B200I_E_UNSUPPORTED, "sim_factual_rng: kernel does not fit on an SM (T=%d)", T);
     const int64_t ntiles = (n + 31) / 32;
     int64_t grid = (int64_t)num_sms() * per_sm;

@@ -487,17 +487,11 @@ extern "C" int b200i_theta_gram_codes(int64_t n, int32_t T, int64_t row_pitch, i
     const size_t warp_bytes = (size_t)32 * (T * 8 + 16) + (((size_t)T * 33 + 15) & ~(size_t)15);
     const size_t smem2 = warp_bytes * G2_WARPS;
     auto k2 = theta_gram2_kernel<256, true>;
-    static thread_local size_t cfg_smem[16];
-    static thread_local int cfg_per_sm[16];
-    int devid = 0;
-    B200I_CUDA(cudaGetDevice(&devid));
-    B200I_REQUIRE(devid >= 0 && devid < 16, B200I_E_UNSUPPORTED, "theta_gram_codes: device index %d", devid);
-    if (cfg_smem[devid] != smem2) {   // once per (device, T): this launch is issued per chunk by the upload pipeline
-        B200I_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        B200I_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm[devid], k2, G2_WARPS * 32, smem2));
-        cfg_smem[devid] = smem2;
+    int per_sm2 = 0;   // attribute + occupancy cached process-wide: this launch is issued per chunk by the upload pipeline
+    {
+        int rc = ensure_dyn_smem(reinterpret_cast<const void *>(k2), (int)smem2, G2_WARPS * 32, &per_sm2);
+        if (rc) return rc;
     }
-    const int per_sm2 = cfg_per_sm[devid];
     B200I_REQUIRE(per_sm2 >= 1, B200I_E_UNSUPPORTED, "theta_gram_codes: T=%d does not fit in shared memory", T);
     const int64_t ntiles2 = (n + 31) / 32;
     int64_t grid2 = (int64_t)num_sms() * per_sm2;

@@ -97,6 +97,7 @@ class LazyDict(dict):
         new = LazyDict()
         dict.update(new, dict.items(self))
         new._lazy = dict(self._lazy)
+        new._on_set = dict(self._on_set)   # reassigning a watched key of the copy invalidates the cached views too
         return new
 
     def __reduce__(self):

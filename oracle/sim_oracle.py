@@ -37,6 +37,8 @@ def lib():
         _lib.oracle_sim_factual.restype = ctypes.c_int
         _lib.oracle_sim_cf_one_step.restype = ctypes.c_int64
         _lib.oracle_sim_cf_treatment_seq.restype = ctypes.c_int64
+        _lib.oracle_sim_cf_one_step_windowed.restype = ctypes.c_int64
+        _lib.oracle_sim_cf_treatment_seq_windowed.restype = ctypes.c_int64
         _lib.oracle_np_mean.restype = ctypes.c_double
         _lib.oracle_np_sum.restype = ctypes.c_double
     return _lib
@@ -90,7 +92,9 @@ def sim_factual(params, T, draws, assigned_actions=None, n_threads=1):
     return out
 
 
-def sim_cf_one_step(params, T, draws):
+def sim_cf_one_step(params, T, draws, window_rows=None):
+    """window_rows (n, T): the output row each patient reads for its treatment window (cancer_simulation.py:471) when
+    the n patients are a subset of a larger cohort (row = global patient index); None = the reference verbatim."""
     L = lib()
     n = params['initial_volumes'].shape[0]
     pk = [_f64(params[k]) for k in _PARAM_KEYS]
@@ -99,16 +103,22 @@ def sim_cf_one_step(params, T, draws):
     cap = 4 * n * T
     cv, ca, ra = np.empty((cap, T)), np.empty((cap, T)), np.empty((cap, T))
     sl, pta = np.empty(cap), np.empty(cap)
-    rows = L.oracle_sim_cf_one_step(ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(int(params['window_size'])),
-                                    ctypes.c_int(int(params['lag'])), ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
-                                    *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr],
-                                    _p(cv), _p(ca), _p(ra), _p(sl), _p(pta))
+    tail = [ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(int(params['window_size'])),
+            ctypes.c_int(int(params['lag'])), ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
+            *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr], _p(cv), _p(ca), _p(ra), _p(sl), _p(pta)]
+    if window_rows is None:
+        rows = L.oracle_sim_cf_one_step(*tail)
+    else:
+        wr = _f64(window_rows)
+        assert wr.shape == (n, T)
+        rows = L.oracle_sim_cf_one_step_windowed(_p(wr), *tail)
     assert rows >= 0, rows
     return {'cancer_volume': cv[:rows], 'chemo_application': ca[:rows], 'radio_application': ra[:rows],
             'sequence_lengths': sl[:rows], 'patient_types': pta[:rows]}
 
 
-def sim_cf_treatment_seq(params, T, H, draws):
+def sim_cf_treatment_seq(params, T, H, draws, window_rows=None):
+    """window_rows (n, T+H): see sim_cf_one_step (cancer_simulation.py:671)."""
     L = lib()
     n = params['initial_volumes'].shape[0]
     pk = [_f64(params[k]) for k in _PARAM_KEYS]
@@ -118,11 +128,17 @@ def sim_cf_treatment_seq(params, T, H, draws):
     W = T + H
     cv, ca, ra = np.empty((cap, W)), np.empty((cap, W)), np.empty((cap, W))
     sl, pta, pid, pct = np.empty(cap), np.empty(cap), np.empty(cap), np.empty(cap)
-    rows = L.oracle_sim_cf_treatment_seq(ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(H),
-                                         ctypes.c_int(int(params['window_size'])), ctypes.c_int(int(params['lag'])),
-                                         ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
-                                         *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr],
-                                         _p(cv), _p(ca), _p(ra), _p(sl), _p(pta), _p(pid), _p(pct))
+    tail = [ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(H),
+            ctypes.c_int(int(params['window_size'])), ctypes.c_int(int(params['lag'])),
+            ctypes.c_double(TUMOUR_DEATH_THRESHOLD),
+            *[_p(a) for a in pk], _p(pt), *[_p(a) for a in dr],
+            _p(cv), _p(ca), _p(ra), _p(sl), _p(pta), _p(pid), _p(pct)]
+    if window_rows is None:
+        rows = L.oracle_sim_cf_treatment_seq(*tail)
+    else:
+        wr = _f64(window_rows)
+        assert wr.shape == (n, W)
+        rows = L.oracle_sim_cf_treatment_seq_windowed(_p(wr), *tail)
     assert rows >= 0, rows
     return {'cancer_volume': cv[:rows], 'chemo_application': ca[:rows], 'radio_application': ra[:rows],
             'sequence_lengths': sl[:rows], 'patient_types': pta[:rows],

@@ -99,3 +99,50 @@ def test_generated_cohort_sharding_is_a_partition_of_the_global_counter_space():
                     assert all(a % 32 == 0 for a, _ in b)
                 seen = hi
             assert seen == n_total
+
+
+def _cf_worker(rank, world, port, n_total, kind, out_dir):
+    """Sharded counterfactual cohort with the oracle standing in for the GPU kernels: every rank simulates the global
+    source prefix (reference verbatim), then its own shard against the prefix's rows (windowed oracle), then the
+    ranks exchange their row totals (counterfactual.exchange_row_bases -- the host logic under test)."""
+    sys.path.insert(0, h.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200_insite import cohort, counterfactual as cf
+    from oracle import sim_oracle as so
+    T, H = 60, 5
+    seq = kind == 'seq'
+    params, draws = h.random_cohort(n_total, seed=17, extra=H if seq else 0)
+    sub = lambda p, s: {k: (v[s] if isinstance(v, np.ndarray) else v) for k, v in p.items()}
+    run = (lambda p, d, **kw: so.sim_cf_treatment_seq(p, T, H, d, **kw)) if seq else \
+          (lambda p, d, **kw: so.sim_cf_one_step(p, T, d, **kw))
+    P = min(n_total, n_total // cf.rows_per_patient_floor('treatment_seq' if seq else 'one_step', H) + 2)
+    pre = run(sub(params, slice(0, P)), {k: v[:P] for k, v in draws.items()})
+    assert pre['cancer_volume'].shape[0] >= n_total
+    lo, hi = cohort.shard_bounds(n_total, rank, world)
+    if lo == 0:   # patient 0 reads the row it is writing itself: the first shard starts with the verbatim semantics
+        mine = run(sub(params, slice(0, hi)), {k: v[:hi] for k, v in draws.items()})
+    else:
+        mine = run(sub(params, slice(lo, hi)), {k: v[lo:hi] for k, v in draws.items()},
+                   window_rows=pre['cancer_volume'][lo:hi])
+    base, total = cf.exchange_row_bases(mine['cancer_volume'].shape[0])
+    np.savez(os.path.join(out_dir, f"cf_{kind}_{rank}.npz"), base=base, total=total, **mine)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,n_total", [('one', 1301), ('seq', 1203)])
+def test_sharded_counterfactual_cohort_equals_whole_cohort(tmp_path, kind, n_total):
+    """SURVEY 8(e) exception: shards + global source prefix + one all-gather of row totals = the single-process cohort."""
+    from oracle import sim_oracle as so
+    world = 2
+    mp.spawn(_cf_worker, args=(world, _free_port(), n_total, kind, str(tmp_path)), nprocs=world, join=True)
+    params, draws = h.random_cohort(n_total, seed=17, extra=5 if kind == 'seq' else 0)
+    ref = so.sim_cf_treatment_seq(params, 60, 5, draws) if kind == 'seq' else so.sim_cf_one_step(params, 60, draws)
+    parts = [np.load(tmp_path / f"cf_{kind}_{r}.npz") for r in range(world)]
+    R = ref['cancer_volume'].shape[0]
+    assert int(parts[0]['base']) == 0 and int(parts[1]['base']) == parts[0]['cancer_volume'].shape[0]
+    assert int(parts[0]['total']) == int(parts[1]['total']) == R
+    for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths'):
+        got = np.concatenate([p[k] for p in parts])
+        assert np.array_equal(got, ref[k], equal_nan=True), k

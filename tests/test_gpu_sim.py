@@ -261,3 +261,127 @@ def test_cf_dropin_entry_points_seed1_digests(dev):
         assert abs(d['cancer_volume'].sum() - dig[name]['cancer_volume_sum']) <= 1e-9 * abs(dig[name]['cancer_volume_sum'])
     with pytest.raises(NotImplementedError):
         cs.simulate_counterfactuals_treatment_seq(cs.generate_params(4, 2.0, 2.0, 15, 0), 60, 5, 'random_trajectories')
+
+
+# ---- BASELINE-size counterfactual cohorts: wavefront depth 4, row indices past 2^31 / width -------------------------
+def _sub_params(params, idx):
+    return {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in params.items()}
+
+
+def _cohort_levels(off, n):
+    """Dependency level of every patient from the row offsets: level(i) = 1 + level(owner of row i), patient 0 = 1."""
+    owner = np.searchsorted(off, np.arange(n), side='right') - 1
+    lvl = np.ones(n, dtype=np.int32)
+    for i in range(1, n):                      # owner[i] < i
+        lvl[i] = lvl[owner[i]] + 1
+    return lvl
+
+
+@pytest.mark.parametrize("kind,n,seed", [('one', 200_000, 31), ('seq', 340_000, 32)])
+def test_cf_generators_at_wavefront_depth_4(dev, kind, n, seed):
+    """BASELINE config C3 runs 4 dependency levels (1M patients); here the smallest cohorts that reach level 4:
+    row counts, applications, sequence lengths (patient ids, current t) bit-exact and volumes 1e-9 against the
+    oracle on (a) every row of the global source prefix (levels 1-3, the reference verbatim) and (b) a strided set
+    of patients behind it up to the last one (levels 3-4; windowed oracle, pinned to the verbatim one on the CPU).
+    Total rows x width exceeds 2^31, so the expanded row ranges sit behind int32 offsets."""
+    import torch
+    from b200_insite import counterfactual as cf
+    from oracle import sim_oracle as so
+    T, H = 60, 5
+    seq = kind == 'seq'
+    W = T + (H if seq else 0)
+    params, draws = h.random_cohort(n, seed=seed, extra=H if seq else 0)
+    pd_ = dev.to_device(dev.pack_params(params))
+    dd = [dev.to_device(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    ptypes = dev.to_device(np.asarray(params['patient_types'], dtype=np.float64))
+    cohort = cf.sim_cf_treatment_seq(pd_, *dd, T, H) if seq else cf.sim_cf_one_step(pd_, *dd, T)
+    torch.cuda.synchronize()
+    off = cohort.row_offsets.cpu().numpy()
+    assert cohort.levels == 4
+    lvl = _cohort_levels(off, n)
+    assert lvl.max() == 4
+    assert int(off[-1]) == cohort.total_rows and cohort.total_rows * W > 2 ** 31
+    exact = CFS_EXACT if seq else CF1_EXACT
+    run = (lambda p, d, **kw: so.sim_cf_treatment_seq(p, T, H, d, **kw)) if seq else \
+          (lambda p, d, **kw: so.sim_cf_one_step(p, T, d, **kw))
+    # (a) the global source prefix, reference semantics verbatim
+    P = n // (480 if seq else 200)
+    ref = run(_sub_params(params, slice(0, P)), {k: v[:P] for k, v in draws.items()})
+    R = ref['cancer_volume'].shape[0]
+    assert R >= n and int(off[P]) == R
+    got = {k: v.cpu().numpy() for k, v in cf.expand(cohort, ptypes, 0, R).items()}
+    _check_cf(got, ref, exact, f"{kind} prefix n={n}")
+    del got
+    # (b) strided patients behind the prefix, the last ones at level 4
+    idx = np.unique(np.concatenate([np.linspace(P, n - 1, 300).astype(np.int64), np.arange(n - 40, n)]))
+    assert lvl[idx].max() == 4 and (lvl[idx] == 4).sum() >= 40
+    sub = run(_sub_params(params, idx), {k: v[idx] for k, v in draws.items()}, window_rows=ref['cancer_volume'][idx])
+    parts = [cf.expand(cohort, ptypes, int(off[i]), int(off[i + 1])) for i in idx]
+    got = {k: torch.cat([p[k] for p in parts]).cpu().numpy() for k in parts[0]}
+    if seq:   # the windowed oracle numbers the subset's patients 0..len(idx)-1
+        sub['patient_ids_all_trajectories'] = idx[sub['patient_ids_all_trajectories'].astype(np.int64)].astype(np.float64)
+    assert int(off[idx[-1] + 1]) * W > 2 ** 31
+    _check_cf(got, sub, exact, f"{kind} strided n={n}")
+
+
+@pytest.mark.parametrize("kind,n", [('one_step', 5000), ('treatment_seq', 3001)])
+def test_cf_shards_with_source_prefix_equal_the_single_launch(dev, kind, n):
+    """SURVEY 8(e) exception (cancer_simulation.py:471, :671): a cohort split into three contiguous shards, each
+    simulated in one launch against the redundantly simulated global source prefix (b200i_cf_source, global_base),
+    is bit-identical to the single launch with its level loop -- compact arrays and global row offsets."""
+    import torch
+    from b200_insite import cohort as co, counterfactual as cf
+    T, H = 60, 5
+    seq = kind == 'treatment_seq'
+    params, draws = h.random_cohort(n, seed=44, extra=H if seq else 0)
+    pd_ = dev.to_device(dev.pack_params(params))
+    dd = [dev.to_device(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    whole = cf.sim_cf_treatment_seq(pd_, *dd, T, H) if seq else cf.sim_cf_one_step(pd_, *dd, T)
+    torch.cuda.synchronize()
+    assert whole.levels >= 3
+    P = co.source_prefix_length(whole.row_offsets.cpu().numpy(), n)
+    assert 0 < P < n // 3          # the prefix is a small part of the first shard
+    world, base, got = 3, 0, []
+    for rank in range(world):
+        lo, hi = co.shard_bounds(n, rank, world)
+        cut = lambda a, s: a[:, s].contiguous() if a.dim() == 2 and a.shape[0] == 10 else a[s].contiguous()
+        shard_in = (cut(pd_, slice(lo, hi)),) + tuple(cut(a, slice(lo, hi)) for a in dd)
+        prefix_in = (cut(pd_, slice(0, P)),) + tuple(cut(a, slice(0, P)) for a in dd)
+        shard, src, _ = cf.sim_cf_shard(kind, T, H, n, lo, shard_in, prefix_in, row_base=base)
+        torch.cuda.synchronize()
+        assert shard.levels == 1 and src.n == P
+        base += shard.total_rows
+        got.append(shard)
+    assert base == whole.total_rows
+    for name in ('factual', 'codes', 'cf', 'valid', 'n_steps', 'n_rows'):
+        if getattr(whole, name) is None:
+            continue
+        cat = torch.cat([getattr(s, name) for s in got])
+        ref = getattr(whole, name)
+        same = torch.equal(cat.view(torch.uint8) if cat.dtype.is_floating_point else cat,
+                           ref.view(torch.uint8) if ref.dtype.is_floating_point else ref)
+        assert same, f"{kind}: {name} differs between the shards and the single launch"
+    offs = torch.cat([s.row_offsets[:-1] for s in got] + [got[-1].row_offsets[-1:]])
+    assert torch.equal(offs, whole.row_offsets)
+    # a prefix that does not cover the rows the shard reads is an error, not a silent zero window
+    lo, hi = co.shard_bounds(n, 2, world)
+    cut = lambda a, s: a[:, s].contiguous() if a.dim() == 2 and a.shape[0] == 10 else a[s].contiguous()
+    with pytest.raises((RuntimeError, ValueError)):
+        cf.sim_cf_shard(kind, T, H, n, lo, (cut(pd_, slice(lo, hi)),) + tuple(cut(a, slice(lo, hi)) for a in dd),
+                        (cut(pd_, slice(0, 2)),) + tuple(cut(a, slice(0, 2)) for a in dd), row_base=0)
+
+
+def test_sim_factual_side_rejects_a_code_pitch_the_kernel_cannot_store(dev):
+    """The side-output kernel writes the code bytes of every 16-column box as one 16-byte word: a pitch of T = 60 (or
+    any non-multiple of 16) must be refused, not written past the row."""
+    import torch
+    params, draws = h.random_cohort(64, seed=3)
+    pd_ = dev.to_device(dev.pack_params(params))
+    dd = [dev.to_device(draws[k]) for k in ('noise', 'recovery', 'chemo', 'radio')]
+    for bad in (60, 62, 48):
+        codes = torch.zeros((64, bad), dtype=torch.uint8, device='cuda')
+        with pytest.raises(RuntimeError, match="code_pitch"):
+            dev.sim_factual_side(pd_, *dd, 60, codes=codes)
+    out, codes, pm = dev.sim_factual_side(pd_, *dd, 60)
+    torch.cuda.synchronize()
+    assert codes.shape[1] == 64

@@ -196,3 +196,23 @@ def test_philox_block_function_known_answers():
     for k in ('recovery', 'chemo', 'radio'):
         assert 0.0 <= d[k].min() and d[k].max() < 1.0 and abs(d[k].mean() - 0.5) < 0.005
     assert abs(np.corrcoef(d['noise'][:, 0::2].ravel(), d['noise'][:, 1::2].ravel())[0, 1]) < 0.01
+
+
+@pytest.mark.parametrize("kind", ['one', 'seq'])
+def test_windowed_oracle_equals_the_verbatim_restatement(kind):
+    """oracle_sim_cf_*_windowed (a patient's treatment window read from a given output row instead of the running
+    output array) is what the depth-4 GPU tests use to check single patients deep inside 10^5..10^6-patient cohorts;
+    fed the rows of the verbatim restatement it must reproduce that restatement bit for bit."""
+    from oracle import sim_oracle as so
+    n = 500
+    params, draws = h.random_cohort(n, seed=9, extra=5 if kind == 'seq' else 0)
+    run = (lambda p, d, **kw: so.sim_cf_treatment_seq(p, 60, 5, d, **kw)) if kind == 'seq' else \
+          (lambda p, d, **kw: so.sim_cf_one_step(p, 60, d, **kw))
+    full = run(params, draws)
+    idx = np.arange(1, n)
+    sub = {k: (v[idx] if isinstance(v, np.ndarray) else v) for k, v in params.items()}
+    part = run(sub, {k: v[idx] for k, v in draws.items()}, window_rows=full['cancer_volume'][idx])
+    r0 = full['cancer_volume'].shape[0] - part['cancer_volume'].shape[0]
+    assert r0 > 0
+    for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths'):
+        assert np.array_equal(full[k][r0:], part[k], equal_nan=True), k
