@@ -14,6 +14,11 @@ int num_sms();
 // MaxDynamicSharedMemorySize to `bytes` if it is lower (never lowers it, so concurrent callers with different sizes
 // cannot invalidate each other's launches) and returns the resident CTAs per SM for (threads, bytes) in *per_sm.
 int ensure_dyn_smem(const void *func, int bytes, int threads, int *per_sm);
+// Stream-ordered scratch memory from a library-owned pool (one per device) whose release threshold keeps freed blocks
+// cached: the default pool hands its memory back to the driver at every synchronisation, which turns a 480 MB
+// scratch buffer into milliseconds of cudaMalloc per call.
+int pool_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+void pool_free(void *ptr, cudaStream_t stream);
 
 #define B200I_CUDA(call)                                   \
     do {                                                   \

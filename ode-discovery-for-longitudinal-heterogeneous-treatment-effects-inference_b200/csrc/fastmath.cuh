@@ -216,6 +216,60 @@ B200I_HD double log_ratio(const FmK &K, const LogNum &na, double b)
 }
 B200I_HD double log_ratio(double a, double b) { return log_ratio(consts(), log_num(a), b); }
 
+// ---- table-driven log for the projected steps of the treatment-sequence generator (csrc/sim_cf_seq.cuh) ----------
+// log(x) = e ln2 + log(c_j) + log1p(r): x = m 2^e, m in [1,2), j = top LOGT_BITS mantissa bits, c_j the interval's
+// midpoint, r = m / c_j - 1.  The table holds (invc_j, logc_j) with invc_j = 1/c_j rounded to 13 significant bits and
+// logc_j = -log(invc_j), so r = fma(m, invc_j, -1) carries no cancellation error (glibc's construction), |r| < 2^-8
+// + 2^-13 and a degree-6 polynomial leaves 3e-18.  Absolute error < 2 ulp of the result for |log| >= 1: the projected
+// step multiplies the logarithm by rho ~ 1e-4..3e-2 before it meets a number of order 1, so this is far below the
+// last bit of the volume; the factual steps (whose comparisons must match bit for bit) do not use it.
+constexpr int LOGT_BITS = 7;
+constexpr int LOGT_SIZE = 1 << LOGT_BITS;
+struct LogTabEntry {
+    double invc, logc;
+};
+// entry j of the table (filled once per kernel into shared memory / once per process on the host)
+B200I_HD LogTabEntry log_table_entry(int j)
+{
+    const double c = 1.0 + ((double)j + 0.5) / (double)LOGT_SIZE;
+    const double inv = 1.0 / c;
+    LogTabEntry e;
+    e.invc = hi_lo_to_double(double_hi(inv) & 0xffffff00, 0u);   // 12 explicit mantissa bits
+    e.logc = -log(e.invc);
+    return e;
+}
+B200I_CONST double kLp[5] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0};   // log1p(r) = r + r^2 (c2 + c3 r + ... + c6 r^4)
+struct LogTabK {
+    double ln2, c2, c3, c4, c5, c6;
+};
+B200I_HD LogTabK log_tab_consts()
+{
+    LogTabK k;
+    k.ln2 = 0.693147180559945309417232; k.c2 = kLp[0]; k.c3 = kLp[1]; k.c4 = kLp[2]; k.c5 = kLp[3]; k.c6 = kLp[4];
+    return k;
+}
+B200I_HD int log_tab_index(double x) { return (double_hi(x) >> (20 - LOGT_BITS)) & (LOGT_SIZE - 1); }
+// `base` - log(x) for a positive, finite, normal x (base = log of the numerator of a ratio); t = entry log_tab_index(x)
+B200I_HD double base_minus_log_entry(const LogTabK &K, const LogTabEntry t, double base, double x)
+{
+    const int hx = double_hi(x);
+    const int e = (hx >> 20) - 1023;
+    const double m = hi_lo_to_double((hx & 0x000fffff) | 0x3ff00000, double_lo(x));
+    const double r = fma(m, t.invc, -1.0);
+    const double r2 = mul(r, r);
+    double a = fma(r, K.c3, K.c2);
+    double b = fma(r, K.c5, K.c4);
+    b = fma(r2, K.c6, b);
+    a = fma(r2, b, a);
+    const double p = fma(r2, a, r);                   // log1p(r)
+    const double u = sub(fma(-(double)e, K.ln2, base), t.logc);
+    return sub(u, p);
+}
+B200I_HD double base_minus_log_tab(const LogTabK &K, const LogTabEntry *__restrict__ tab, double base, double x)
+{
+    return base_minus_log_entry(K, tab[log_tab_index(x)], base, x);
+}
+
 // exp(x) for |x| <= 700 (callers route anything else to the library function)
 B200I_HD double exp_fast(const FmK &K, double x)
 {

@@ -67,6 +67,38 @@ int ensure_dyn_smem(const void *func, int bytes, int threads, int *per_sm)
     return 0;
 }
 
+static cudaMemPool_t g_pools[64];
+static std::mutex g_pool_mu;
+
+int pool_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+    int dev = 0;
+    B200I_CUDA(cudaGetDevice(&dev));
+    B200I_REQUIRE(dev >= 0 && dev < 64, B200I_E_UNSUPPORTED, "pool_alloc: device index %d", dev);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (g_pools[dev] == nullptr) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            B200I_CUDA(cudaMemPoolCreate(&g_pools[dev], &props));
+            uint64_t keep = UINT64_MAX;
+            B200I_CUDA(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = g_pools[dev];
+    }
+    B200I_CUDA(cudaMallocFromPoolAsync(ptr, bytes, pool, stream));
+    return 0;
+}
+
+void pool_free(void *ptr, cudaStream_t stream)
+{
+    if (ptr) cudaFreeAsync(ptr, stream);
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -150,7 +150,12 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
     int steps = 0;
     bool alive = true;
     for (int t = 0; t < T - 1; ++t) {
-        if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; continue; }
+        if (!alive) {   // steps after the last executed one: zeros (the compact arrays are fully defined)
+            Fr[t + 1] = 0.0; cr[t] = 0;
+            double2 *z = reinterpret_cast<double2 *>(cf_out + (i * (T - 1) + t) * 4);
+            z[0] = make_double2(0.0, 0.0); z[1] = make_double2(0.0, 0.0);
+            continue;
+        }
         double w_t;
         if (w.self) {
             // row 0 is this patient's own t=0 snapshot [F0, F1, 0, ...]; before it exists the row is 0
@@ -287,6 +292,8 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         const bool live = alive;
         if (!live) {
             if (exists) { Fr[t + 1] = 0.0; cr[t] = 0; valid_out[i * (T - 1) + t] = 0; }
+#pragma unroll
+            for (int e = 0; e < BLK; ++e) my_stage[e] = 0.0;   // steps after the last executed one: a block of zeros
         } else {
         double w_t;
         if (w.self) {
@@ -373,7 +380,7 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
         }
         // the warp writes the staged blocks of its live patients: one block per instruction
-        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        const unsigned live_mask = __ballot_sync(0xffffffffu, exists);
         __syncwarp();
         for (unsigned m = live_mask; m != 0u; m &= m - 1u) {
             const int r = __ffs(m) - 1;
@@ -394,6 +401,11 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         n_rows[i] = rows;
     }
 }
+
+}  // namespace b200i
+#include "tma.cuh"
+#include "sim_cf_seq.cuh"
+namespace b200i {
 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan of n_rows[lo..hi) continuing from off[lo]; single CTA
@@ -435,6 +447,101 @@ __global__ void __launch_bounds__(1024) scan_rows_kernel(const int *__restrict__
         if (tid == 1023) s_carry = total_incl;
         __syncthreads();
     }
+}
+
+// the same for long ranges, in three launches: per-CTA sums, scan of the sums (one CTA), per-CTA rescan with its offset
+constexpr int SCAN_CHUNK = 4096;   // entries per CTA (1024 threads x 4)
+__device__ __forceinline__ int64_t block_incl_scan(int64_t v, int64_t *s_warp, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int64_t wv = s_warp[lane];
+        int64_t winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += up;
+        }
+        s_warp[lane] = winc - wv;
+    }
+    __syncthreads();
+    const int64_t r = incl + s_warp[warp];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(1024) scan_chunk_sums_kernel(const int *__restrict__ n_rows, int64_t lo, int64_t hi,
+                                                               int64_t *__restrict__ sums)
+{
+    __shared__ int64_t s_warp[32];
+    const int64_t first = lo + (int64_t)blockIdx.x * SCAN_CHUNK + 4 * threadIdx.x;
+    int64_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (first + q < hi) v += n_rows[first + q];
+    const int64_t incl = block_incl_scan(v, s_warp, threadIdx.x);
+    if (threadIdx.x == 1023) sums[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int64_t *__restrict__ sums, int nb, const int64_t *__restrict__ off_lo)
+{
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    if (threadIdx.x == 0) s_carry = *off_lo;
+    __syncthreads();
+    for (int start = 0; start < nb; start += 1024) {
+        const int b = start + threadIdx.x;
+        const int64_t v = b < nb ? sums[b] : 0;
+        const int64_t incl = block_incl_scan(v, s_warp, threadIdx.x);
+        const int64_t carry = s_carry;
+        if (b < nb) sums[b] = carry + incl - v;          // exclusive, continuing from off[lo]
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) scan_chunk_apply_kernel(const int *__restrict__ n_rows, int64_t *__restrict__ off,
+                                                                int64_t lo, int64_t hi, const int64_t *__restrict__ sums)
+{
+    __shared__ int64_t s_warp[32];
+    const int64_t first = lo + (int64_t)blockIdx.x * SCAN_CHUNK + 4 * threadIdx.x;
+    int64_t r[4], v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[q] = (first + q < hi) ? (int64_t)n_rows[first + q] : 0;
+        v += r[q];
+    }
+    const int64_t incl = block_incl_scan(v, s_warp, threadIdx.x);
+    int64_t run = sums[blockIdx.x] + incl - v;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        run += r[q];
+        if (first + q < hi) off[first + q + 1] = run;
+    }
+}
+// off[i + 1] for i in [lo, hi), continuing from off[lo]
+static int scan_rows(const int *n_rows, int64_t *off, int64_t lo, int64_t hi, cudaStream_t st)
+{
+    if (hi - lo <= 4 * SCAN_CHUNK) {
+        scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, lo, hi);
+        return check_cuda(cudaGetLastError(), "scan_rows launch");
+    }
+    const int nb = (int)((hi - lo + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    int64_t *sums = nullptr;
+    int rc = pool_alloc(reinterpret_cast<void **>(&sums), (size_t)nb * sizeof(int64_t), st);
+    if (rc) return rc;
+    scan_chunk_sums_kernel<<<nb, 1024, 0, st>>>(n_rows, lo, hi, sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, off + lo);
+    scan_chunk_apply_kernel<<<nb, 1024, 0, st>>>(n_rows, off, lo, hi, sums);
+    rc = check_cuda(cudaGetLastError(), "scan_rows launch");
+    pool_free(sums, st);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -531,8 +638,11 @@ static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, in
 {
     // validate before allocating; every later exit goes through the cudaFreeAsync below
     B200I_REQUIRE(source != nullptr || base == 0, B200I_E_ARG, "sim_cf: a shard (global_base > 0) needs a source cohort");
-    int *d_err = nullptr;
-    B200I_CUDA(cudaMallocAsync(&d_err, sizeof(int), st));
+    int *d_err = nullptr;   // scratch: error flag + 8 doubles for the generator's own use (16-byte aligned)
+    {
+        int rc0 = pool_alloc(reinterpret_cast<void **>(&d_err), 128, st);
+        if (rc0) return rc0;
+    }
     int levels = 0;
     int64_t total = 0;
     int rc = check_cuda(cudaMemsetAsync(d_err, 0, sizeof(int), st), "memset err");
@@ -541,8 +651,7 @@ static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, in
     } else if (source != nullptr) {
         rc = launch(0, n, true, d_err);
         if (!rc) {
-            scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, 0, n);
-            rc = check_cuda(cudaGetLastError(), "scan_rows launch");
+            rc = scan_rows(n_rows, off, 0, n, st);
         }
         levels = 1;
     } else {
@@ -550,8 +659,7 @@ static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, in
         while (lo < n && !rc) {
             rc = launch(lo, hi, false, d_err);
             if (rc) break;
-            scan_rows_kernel<<<1, 1024, 0, st>>>(n_rows, off, lo, hi);
-            rc = check_cuda(cudaGetLastError(), "scan_rows launch");
+            rc = scan_rows(n_rows, off, lo, hi, st);
             if (rc) break;
             int64_t off_hi = 0;
             rc = check_cuda(cudaMemcpyAsync(&off_hi, off + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, st), "copy off");
@@ -570,10 +678,11 @@ static int run_levels(int64_t n, int64_t base, const b200i_cf_source *source, in
     if (!rc && (total_rows_host || true))
         rc = check_cuda(cudaMemcpyAsync(&total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st), "copy total");
     if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "final sync");
-    cudaFreeAsync(d_err, st);
+    pool_free(d_err, st);
     if (rc) return rc;
     B200I_REQUIRE(h_err != 1, B200I_E_ARG, "sim_cf: source cohort does not cover the rows this shard reads");
     B200I_REQUIRE(h_err != 2, B200I_E_UNSUPPORTED, "sim_cf: patient 0 emitted no row at t=0 (not modelled)");
+    B200I_REQUIRE(h_err != 3, B200I_E_UNSUPPORTED, "sim_cf: internal: patient 0 reached the two-phase kernels");
     if (total_rows_host) *total_rows_host = total;
     if (levels_host) *levels_host = levels;
     return 0;
@@ -639,28 +748,61 @@ extern "C" int b200i_sim_cf_treatment_seq(int64_t n, int32_t T, int32_t H, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SimC2 c{k->death_threshold, k->cell_density, k->sphere_coef, k->chemo_amt, k->radio_amt, k->drug_decay,
             k->window_size};
+    B200I_REQUIRE(aligned16(cf), B200I_E_ALIGN, "sim_cf_treatment_seq: cf must be 16-byte aligned");
+    // B200I_K3_VARIANT=1: the first-generation kernel for every patient (cross-check); default: two-phase kernels,
+    // the first-generation kernel only for patient 0 (its window reads the row it is writing itself)
+    static const int variant = getenv("B200I_K3_VARIANT") ? atoi(getenv("B200I_K3_VARIANT")) : 0;
+    // resident CTAs per SM the first-generation kernel's register budget is sized for; B200I_K3_MINB overrides
+    static const int minb = getenv("B200I_K3_MINB") ? atoi(getenv("B200I_K3_MINB")) : K3_MINB_DEFAULT;
+    double *conc = nullptr;   // chemo concentration C[t] of the factual trajectories: phase A -> phase B
+    if (variant != 1 && n > 0) {
+        int rc0 = pool_alloc(reinterpret_cast<void **>(&conc), (size_t)n * T * sizeof(double), st);
+        if (rc0) return rc0;
+    }
+    auto legacy = [&](int64_t lo, int64_t hi, const CfSrc &src, bool required, int *d_err) -> int {
+        const unsigned grid = (unsigned)((hi - lo + 127) / 128);
+        constexpr int STAGE_BYTES = 128 * (2 * 5 * 5 + 1) * 8;   // [128 threads][2H*H + 1] doubles
+        auto go = [&](auto kern) -> int {
+            int rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), STAGE_BYTES, 128, nullptr);
+            if (rc_) return rc_;
+            kern<<<grid, 128, STAGE_BYTES, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs, radio_rvs,
+                                                 global_base, src, required ? 1 : 0, factual, codes, cf, valid, n_steps,
+                                                 n_rows, d_err);
+            return check_cuda(cudaGetLastError(), "cf_treatment_seq launch");
+        };
+        return minb == 2 ? go(cf_treatment_seq_kernel<5, 2>) : (minb == 4 ? go(cf_treatment_seq_kernel<5, 4>)
+                                                                           : go(cf_treatment_seq_kernel<5, 3>));
+    };
     auto launch = [&](int64_t lo, int64_t hi, bool required, int *d_err) -> int {
         if (hi <= lo) return 0;
         CfSrc src;
         if (source) src = CfSrc{source->n, source->factual, source->codes, source->cf, source->valid, source->row_offsets};
         else src = CfSrc{lo, factual, codes, cf, valid, row_offsets};
-        const unsigned grid = (unsigned)((hi - lo + 127) / 128);
-        constexpr int STAGE_BYTES = 128 * (2 * 5 * 5 + 1) * 8;   // [128 threads][2H*H + 1] doubles
-        // resident CTAs per SM the register budget is sized for (2: 199 registers, 3: 168, 4: 128); B200I_K3_MINB overrides
-        static const int minb = getenv("B200I_K3_MINB") ? atoi(getenv("B200I_K3_MINB")) : K3_MINB_DEFAULT;
-        auto go = [&](auto kern) -> int {
-            B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
-            kern<<<grid, 128, STAGE_BYTES, st>>>(lo, hi, n, T, c, params, noise, recovery_rvs, chemo_rvs, radio_rvs,
-                                                 global_base, src, required ? 1 : 0, factual, codes, cf, valid, n_steps,
-                                                 n_rows, d_err);
-            return 0;
-        };
-        int rc_ = minb == 2 ? go(cf_treatment_seq_kernel<5, 2>) : (minb == 4 ? go(cf_treatment_seq_kernel<5, 4>)
-                                                                              : go(cf_treatment_seq_kernel<5, 3>));
+        if (variant == 1) return legacy(lo, hi, src, required, d_err);
+        const ProjK pk{fm::log_tab_consts(), 1e-07, 1e300, c.decay, c.chemo_amt};
+        double *self_row = reinterpret_cast<double *>(d_err) + 1;   // run_levels' scratch: [error flag | H doubles]
+        int rc_ = 0;
+        if (global_base + lo == 0) {
+            cf_seq_self_kernel<<<1, 32, 0, st>>>(n, T, H, c, pk, params, noise, chemo_rvs, radio_rvs, self_row, d_err);
+            rc_ = check_cuda(cudaGetLastError(), "cf_seq_self launch");
+            if (rc_) return rc_;
+        }
+        cf_seq_factual_kernel<<<(unsigned)((hi - lo + 127) / 128), 128, 0, st>>>(
+            lo, hi, n, T, H, c, params, noise, recovery_rvs, chemo_rvs, radio_rvs, global_base, src, required ? 1 : 0,
+            self_row, factual, codes, conc, n_steps, d_err);
+        rc_ = check_cuda(cudaGetLastError(), "cf_seq_factual launch");
         if (rc_) return rc_;
-        return check_cuda(cudaGetLastError(), "cf_treatment_seq launch");
+        static const int pb_minb = getenv("B200I_K3_PB_MINB") ? atoi(getenv("B200I_K3_PB_MINB")) : 2;
+        auto kern = pb_minb == 1 ? cf_seq_project_kernel<1> : cf_seq_project_kernel<2>;
+        rc_ = ensure_dyn_smem(reinterpret_cast<const void *>(kern), PB_SMEM_BYTES, PB_THREADS, nullptr);
+        if (rc_) return rc_;
+        kern<<<(unsigned)((hi - lo + 31) / 32), PB_THREADS, PB_SMEM_BYTES, st>>>(lo, hi, n, T, pk, c.radio_amt, params, noise,
+                                                                                factual, conc, n_steps, cf, valid, n_rows);
+        return check_cuda(cudaGetLastError(), "cf_seq_project launch");
     };
-    return run_levels(n, global_base, source, n_rows, row_offsets, total_rows_host, levels_host, st, launch);
+    const int rc_levels = run_levels(n, global_base, source, n_rows, row_offsets, total_rows_host, levels_host, st, launch);
+    pool_free(conc, st);
+    return rc_levels;
 }
 
 extern "C" int b200i_expand_cf_one_step(int64_t n, int32_t T, const double *factual, const uint8_t *codes,

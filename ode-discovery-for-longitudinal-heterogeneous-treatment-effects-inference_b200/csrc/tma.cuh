@@ -138,6 +138,22 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *gptr, uint32_t byte
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// contiguous shared-memory range -> global (non-tensor bulk copy, SASS UBLKCP); both addresses and the size are
+// multiples of 16 bytes; completion through the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void *gdst, const void *smem_src, uint32_t bytes, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+// all but the `N` most recently committed bulk stores have finished reading their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

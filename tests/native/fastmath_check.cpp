@@ -25,6 +25,11 @@ int main(int argc, char **argv)
     double e_div = 0, e_rcp = 0, e_log = 0, e_logsmall = 0, e_exp = 0, e_expwide = 0, e_cbrt = 0, e_d15 = 0;
     long bad_d15 = 0, bad_div = 0;
     const double K = 14137.166941154068;
+    LogTabEntry tab[LOGT_SIZE];
+    for (int j = 0; j < LOGT_SIZE; ++j) tab[j] = log_table_entry(j);
+    const LogTabK ltk = log_tab_consts();
+    const double logK = std::log(K);
+    double e_logtab_abs = 0, e_logtab_ulp = 0;
     for (long i = 0; i < n; ++i) {
         const double a = std::exp((U(g) - 0.5) * 60.0), b = std::exp((U(g) - 0.5) * 60.0);
         const double q = div_fast(a, b);
@@ -34,6 +39,13 @@ int main(int argc, char **argv)
         // tumour volumes: 1e-12 .. 1150.35 against K
         const double V = std::exp(std::log(1e-12) + U(g) * (std::log(1150.3465) - std::log(1e-12)));
         e_log = std::fmax(e_log, ulp_err(log_ratio(K, V), logl((long double)K / V)));
+        {   // table-driven log(K / den) over the projected volumes' range (den = V + 1e-7, V up to 1e4)
+            const double den = std::exp(std::log(1e-7) + U(g) * (std::log(1e4) - std::log(1e-7)));
+            const long double want = logl((long double)K / den);
+            const double got = base_minus_log_tab(ltk, tab, logK, den);
+            e_logtab_abs = std::fmax(e_logtab_abs, (double)fabsl((long double)got - want));
+            if (fabsl(want) >= 1.0L) e_logtab_ulp = std::fmax(e_logtab_ulp, ulp_err(got, want));
+        }
         // generic ratios with |log| >= 1
         if (std::fabs(std::log(a / b)) >= 1.0)
             e_logsmall = std::fmax(e_logsmall, ulp_err(log_ratio(a, b), logl((long double)a / b)));
@@ -54,6 +66,8 @@ int main(int argc, char **argv)
     printf("rcp_fast %.4f %ld\n", e_rcp, n);
     printf("log_ratio_path %.4f %ld\n", e_log, n);
     printf("log_ratio_generic %.4f %ld\n", e_logsmall, n);
+    printf("log_tab_ulp %.4f %ld\n", e_logtab_ulp, n);
+    printf("log_tab_abs %.4g %ld\n", e_logtab_abs, n);
     printf("exp_fast %.4f %ld\n", e_exp, n);
     printf("exp_fast_wide %.4f %ld\n", e_expwide, n);
     printf("cbrt_fast %.4f %ld\n", e_cbrt, n);
