@@ -380,6 +380,48 @@ B200I_API int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_
                       const double *static_feature, const double *theta0, double lam, double gtol,
                       int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation on COMPACT counterfactual cohorts (BASELINE config C3: tau = 1..5 rollouts for 1M patients).
+ *
+ * The reference evaluates one dense row per (patient, t, option): SINDY.get_predictions /
+ * get_autoregressive_predictions (sindy.py:371-431, 433-715, 717-760) followed by
+ * get_normalised_masked_rmse(one_step_counterfactual=True) / get_normalised_n_step_rmses
+ * (time_varying_model.py:236-313).  All rows of one (patient, t) share the factual prefix and -- in INSITE mode -- the
+ * fit problem (fit window = F[0..t] for the one-step rows, sindy.py:786 with projection_horizon 1, F[0..t+1] for the
+ * sequence rows with projection_horizon H), so these entry points read the per-patient arrays of K2 / K3 directly.
+ *
+ * coefs: (4,4) for the whole cohort (coefs_per_step == 0; rows = treatment code chemo + 2*radio, as
+ *        b200i_stlsq_population writes them) or (n, T-1, 4, 4) per (patient, t) (coefs_per_step == 1; what the two
+ *        *_prefix entry points below write).  Terms with |c| <= drop_below are dropped (pass < 0 to keep all).
+ * codes are the generators' factual option indices 2*chemo + radio; n_steps = executed steps per patient.
+ * b200i_cf_eval_one_step:     sums (3*(T-1) + 2) doubles, the layout of b200i_masked_se over the (R, T-1) rows.
+ * b200i_cf_eval_treatment_seq: sums (2*H) doubles: squared error per projection step, then the number of scored rows
+ *                              (valid options) per step.  T <= 128, H <= 8.
+ * Deterministic (ordered, atomics-free reduction) for a fixed n on a given device.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_cf_eval_one_step(int64_t n, int32_t T, double dt, int32_t substeps, const double *factual,
+                           const uint8_t *codes, const double *cf, const int32_t *n_steps,
+                           const double *static_feature, const double *coefs, int32_t coefs_per_step,
+                           double drop_below, double *sums, void *stream);
+B200I_API int b200i_cf_eval_treatment_seq(int64_t n, int32_t T, int32_t H, double dt, int32_t substeps,
+                           const double *factual, const uint8_t *codes, const double *cf, const uint16_t *valid,
+                           const int32_t *n_steps, const double *static_feature, const double *coefs,
+                           int32_t coefs_per_step, double drop_below, double *sums, void *stream);
+/* Individualisation per (patient, t) of a compact cohort: row (i,t) fits on the first t + fit_offset transitions of
+ * the patient's factual trajectory (fit_offset 0: one-step rows, 1: sequence rows); t >= n_steps[i] or an empty
+ * window keeps theta0 / the prior.  Same estimators, arguments and outputs as b200i_insite_bfgs /
+ * b200i_stlsq_batched, with coefs_out (n, T-1, 4, 4), status_out (n, T-1), fval_out (n, T-1, 2): one fit instead of
+ * the 4 (one-step) or <= 2H (sequence) identical ones the dense rows repeat. */
+B200I_API int b200i_insite_bfgs_prefix(int64_t n, int32_t T, int32_t fit_offset, double dt, int32_t substeps,
+                           const double *factual, const uint8_t *codes, const int32_t *n_steps,
+                           const double *static_feature, const double *theta0, double lam, double gtol,
+                           int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+B200I_API int b200i_stlsq_prefix(int64_t n, int32_t T, int32_t fit_offset, double fd_dt, const double *factual,
+                           const uint8_t *codes, const int32_t *n_steps, const double *static_feature,
+                           const double *prior, double support_tol, double lam, double threshold, int32_t max_iter,
+                           double *coefs_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

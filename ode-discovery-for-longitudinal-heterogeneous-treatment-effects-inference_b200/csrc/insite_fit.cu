@@ -25,37 +25,10 @@ namespace b200i {
 // ------------------------------------------------------------------------------------------------
 // K5b
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
-                     const int *__restrict__ fit_len, const double *__restrict__ static_u,
-                     const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
-                     double *__restrict__ coefs_out)
+// ridge-to-prior STLSQ of one row from its per-treatment sums (see b200i_stlsq_batched in include/b200i.h)
+__device__ __forceinline__ void ridge_prior_solve(const PatientGram &pg, double u, const double *s_prior, double support_tol,
+                                                  double lam, double threshold, int max_iter, double *__restrict__ out16)
 {
-    __shared__ double s_prior[16];
-    if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
-    __syncthreads();
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    int n = fit_len[r];
-    if (n > W - 1) n = W - 1;
-    const double u = static_u[r];
-    const double *xr = x + r * W;
-    const uint8_t *cr = codes + r * W;
-    PatientGram pg;
-    pg.clear();
-    if (n > 0) {
-        double x0 = xr[0];
-        int a0 = cr[0] & 3;
-        for (int k = 0; k < n; ++k) {
-            const double x1 = xr[k + 1];
-            const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
-            const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
-            pg.add(a0, x0, xdot);
-            if (k == n - 1 || a1 != a0) pg.add(a0, x1, xdot);
-            x0 = x1;
-            a0 = a1;
-        }
-    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         double g15[B200I_GRAM_PER_TREATMENT], G[4][4], b[4], c[4], pr[4];
@@ -95,7 +68,86 @@ stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict
             for (int j = 0; j < 4; ++j) c[j] = pr[j];   // treatment never observed in the window: keep the prior
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) coefs_out[r * 16 + a * 4 + j] = c[j];
+        for (int j = 0; j < 4; ++j) out16[a * 4 + j] = c[j];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
+                     const int *__restrict__ fit_len, const double *__restrict__ static_u,
+                     const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
+                     double *__restrict__ coefs_out)
+{
+    __shared__ double s_prior[16];
+    if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int n = fit_len[r];
+    if (n > W - 1) n = W - 1;
+    const double u = static_u[r];
+    const double *xr = x + r * W;
+    const uint8_t *cr = codes + r * W;
+    PatientGram pg;
+    pg.clear();
+    if (n > 0) {
+        double x0 = xr[0];
+        int a0 = cr[0] & 3;
+        for (int k = 0; k < n; ++k) {
+            const double x1 = xr[k + 1];
+            const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
+            const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+            pg.add(a0, x0, xdot);
+            if (k == n - 1 || a1 != a0) pg.add(a0, x1, xdot);
+            x0 = x1;
+            a0 = a1;
+        }
+    }
+    ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, coefs_out + r * 16);
+}
+
+// K5b on a compact counterfactual cohort: all rows of one (patient, t) share their fit window F[0..n_fit], so a thread
+// walks one patient once and emits the T-1 fits as running sums: n_fit = t + fit_offset for
+// t < executed steps, else the prior.  Same sums in the same order as stlsq_batched_kernel on the dense rows.
+__global__ void __launch_bounds__(128)
+stlsq_prefix_kernel(int64_t n, int T, int fit_offset, double fd_dt, const double *__restrict__ F,
+                    const uint8_t *__restrict__ codes, const int *__restrict__ n_steps, const double *__restrict__ static_u,
+                    const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
+                    double *__restrict__ coefs_out)
+{
+    __shared__ double s_prior[16];
+    if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int W = T - 1;
+    int ns = n_steps[i];
+    if (ns > W) ns = W;
+    const double u = static_u[i];
+    const double *xr = F + i * T;
+    const uint8_t *cr = codes + i * T;
+    double *out = coefs_out + i * (int64_t)W * 16;
+    PatientGram pg;
+    pg.clear();
+    // rows whose window is empty keep the prior
+    for (int t = 0; t < W; ++t)
+        if (t >= ns || t + fit_offset <= 0) ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, out + t * 16);
+    const int kmax = ns - 1 + fit_offset;     // transitions 0 .. kmax-1 are used by some row
+    double x0 = xr[0];
+    int a0 = ((cr[0] & 1) << 1) | ((cr[0] >> 1) & 1);
+    for (int k = 0; k < kmax && k < W; ++k) {
+        const double x1 = xr[k + 1];
+        const int c1 = cr[k + 1 < T ? k + 1 : k];
+        const int a1 = ((c1 & 1) << 1) | ((c1 >> 1) & 1);
+        const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+        pg.add(a0, x0, xdot);
+        PatientGram tmp = pg;
+        tmp.add(a0, x1, xdot);                // the window of n_fit = k+1 ends here: backward difference at its last point
+        const int t = k + 1 - fit_offset;
+        if (t >= 0 && t < ns) ridge_prior_solve(tmp, u, s_prior, support_tol, lam, threshold, max_iter, out + t * 16);
+        if (a1 != a0) pg = tmp;               // a treatment change makes the end point part of every longer window
+        x0 = x1;
+        a0 = a1;
     }
 }
 
@@ -237,7 +289,11 @@ __device__ __forceinline__ double quadmin(double a, double fa, double fpa, doubl
     return a - fpa / (2.0 * B);
 }
 
-template <int MINB, bool JOINT = false>
+// PREFIX: the rows are the (patient, t) pairs of a compact counterfactual cohort (b200i_insite_bfgs_prefix): row
+// r = patient * (W-1) + t reads the patient's factual trajectory x[patient, 0..W) and its factual option codes
+// (2*chemo + radio, translated to chemo + 2*radio), seq_len holds the patient's executed steps and `ph` the offset of
+// the fit window: n_fit = t + ph for t < executed steps, else the row does not exist (theta0, status -2).
+template <int MINB, bool JOINT = false, bool PREFIX = false>
 __global__ void __launch_bounds__(BFGS_THREADS, MINB)
 insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x,
                    const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
@@ -265,14 +321,24 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
         const int64_t r = itr * ngroups + (int64_t)blockIdx.x * BFGS_GROUPS + grp;
         const bool valid = r < rows;
         int n_fit = 0;
+        int64_t src = r;
         if (valid) {
-            n_fit = seq_len[r] - ph;
+            if (PREFIX) {
+                src = r / (W - 1);
+                const int t = (int)(r - src * (W - 1));
+                n_fit = (t < seq_len[src]) ? t + ph : 0;
+            } else {
+                n_fit = seq_len[r] - ph;
+            }
             if (n_fit > W - 1) n_fit = W - 1;
         }
         __syncwarp(gmask);
         if (valid && n_fit > 0) {
-            for (int k = j; k <= n_fit; k += 16) s_x[grp][k] = x[r * W + k];
-            for (int k = j; k < n_fit; k += 16) s_c[grp][k] = codes[r * W + k];
+            for (int k = j; k <= n_fit; k += 16) s_x[grp][k] = x[src * W + k];
+            for (int k = j; k < n_fit; k += 16) {
+                const int c = codes[src * W + k];
+                s_c[grp][k] = (uint8_t)(PREFIX ? (((c & 1) << 1) | ((c >> 1) & 1)) : c);
+            }
         }
         __syncwarp(gmask);
         if (!valid) continue;
@@ -282,7 +348,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
             continue;
         }
         RowData d;
-        d.x = s_x[grp]; d.codes = s_c[grp]; d.n_fit = n_fit; d.u = static_u[r];
+        d.x = s_x[grp]; d.codes = s_c[grp]; d.n_fit = n_fit; d.u = static_u[src];
         d.h = dt / substeps; d.substeps = substeps; d.norm = 1.0; d.lam = lam;
 
         double theta = theta0, f, g;
@@ -477,4 +543,45 @@ extern "C" int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32
         rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
         max_iter, coefs_out, status_out, fval_out);
     return check_cuda(cudaGetLastError(), "insite_bfgs_joint launch");
+}
+
+extern "C" int b200i_insite_bfgs_prefix(int64_t n, int32_t T, int32_t fit_offset, double dt, int32_t substeps,
+                                        const double *factual, const uint8_t *codes, const int32_t *n_steps,
+                                        const double *static_feature, const double *theta0, double lam, double gtol,
+                                        int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out,
+                                        void *stream)
+{
+    B200I_REQUIRE(n >= 0, B200I_E_ARG, "insite_bfgs_prefix: negative n");
+    if (n == 0) return 0;
+    B200I_REQUIRE(factual && codes && n_steps && static_feature && theta0 && coefs_out && status_out && fval_out,
+                  B200I_E_ARG, "insite_bfgs_prefix: NULL argument");
+    B200I_REQUIRE(T >= 3 && T <= BFGS_MAXW, B200I_E_UNSUPPORTED, "insite_bfgs_prefix: T=%d outside [3,%d]", T, BFGS_MAXW);
+    B200I_REQUIRE(fit_offset >= 0 && fit_offset <= 1, B200I_E_ARG,
+                  "insite_bfgs_prefix: fit_offset is 0 (one-step rows: t transitions) or 1 (sequence rows: t+1)");
+    B200I_REQUIRE(dt > 0 && substeps >= 1 && lam >= 0 && max_iter >= 1, B200I_E_ARG, "insite_bfgs_prefix: bad scalar argument");
+    const int64_t rows = n * (T - 1);
+    int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    insite_bfgs_kernel<K7_MINB_DEFAULT, false, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        rows, T, dt, substeps, factual, codes, n_steps, fit_offset, static_feature, theta0, lam, gtol, max_iter, coefs_out,
+        status_out, fval_out);
+    return check_cuda(cudaGetLastError(), "insite_bfgs_prefix launch");
+}
+
+extern "C" int b200i_stlsq_prefix(int64_t n, int32_t T, int32_t fit_offset, double fd_dt, const double *factual,
+                                  const uint8_t *codes, const int32_t *n_steps, const double *static_feature,
+                                  const double *prior, double support_tol, double lam, double threshold, int32_t max_iter,
+                                  double *coefs_out, void *stream)
+{
+    B200I_REQUIRE(n >= 0, B200I_E_ARG, "stlsq_prefix: negative n");
+    if (n == 0) return 0;
+    B200I_REQUIRE(factual && codes && n_steps && static_feature && prior && coefs_out, B200I_E_ARG, "stlsq_prefix: NULL argument");
+    B200I_REQUIRE(T >= 3 && fd_dt > 0 && lam > 0 && threshold >= 0 && max_iter >= 1 && fit_offset >= 0 && fit_offset <= 1,
+                  B200I_E_ARG, "stlsq_prefix: need T >= 3, fd_dt > 0, lam > 0, threshold >= 0, fit_offset in {0,1}");
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    stlsq_prefix_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(n, T, fit_offset, fd_dt, factual, codes, n_steps,
+                                                                             static_feature, prior, support_tol, lam,
+                                                                             threshold, max_iter, coefs_out);
+    return check_cuda(cudaGetLastError(), "stlsq_prefix launch");
 }

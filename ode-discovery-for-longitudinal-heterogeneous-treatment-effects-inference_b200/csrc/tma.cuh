@@ -138,6 +138,15 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *gptr, uint32_t byte
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// contiguous global range -> shared memory (non-tensor bulk copy, SASS UBLKCP); both addresses and the size are multiples
+// of 16 bytes; completion = complete_tx on the mbarrier
+__device__ __forceinline__ void bulk_load_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // contiguous shared-memory range -> global (non-tensor bulk copy, SASS UBLKCP); both addresses and the size are
 // multiples of 16 bytes; completion through the bulk async-group of the issuing thread
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *smem_src, uint32_t bytes)

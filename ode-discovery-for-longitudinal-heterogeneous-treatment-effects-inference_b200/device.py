@@ -417,3 +417,67 @@ def moments_to_scaling(stats):
         var = max(u[s2] / n - mean * mean, 0.0)
         out[name] = (mean, math.sqrt(var))
     return out
+
+
+# ---- evaluation on compact counterfactual cohorts (csrc/cf_eval.cu) ---------------------------------------------------
+def cf_eval_one_step(factual, codes, cf, n_steps, static_feature, coefs, drop_below=1e-3, dt=STANDARD_DT,
+                     substeps=STEPS_FOR_DT):
+    """K8.  Compact one-step cohort (factual (n,T), codes (n,T) uint8, cf (n,T-1,4), n_steps (n,) int32) scored against
+    the ODE with coefficients (4,4) [whole cohort] or (n,T-1,4,4) [per (patient, t)].  Returns the (3(T-1)+2,) sums of
+    masked_se over the reference's dense rows: se per column, active rows per column, last-entry se per column, total
+    last-entry se, rows."""
+    lib = _native.load()
+    n, T = factual.shape
+    per_step = 1 if coefs.dim() == 4 else 0
+    assert per_step == 0 or tuple(coefs.shape) == (n, T - 1, 4, 4)
+    sums = torch.empty(3 * (T - 1) + 2, dtype=torch.float64, device='cuda')
+    rc = lib.b200i_cf_eval_one_step(n, T, float(dt), int(substeps), _ptr(factual), _ptr(codes), _ptr(cf), _ptr(n_steps),
+                                    _ptr(static_feature), _ptr(coefs), per_step, float(drop_below), _ptr(sums), _stream())
+    _native.check(rc, "b200i_cf_eval_one_step")
+    return sums
+
+
+def cf_eval_treatment_seq(factual, codes, cf, valid, n_steps, static_feature, coefs, drop_below=1e-3, dt=STANDARD_DT,
+                          substeps=STEPS_FOR_DT):
+    """K9.  Compact treatment-sequence cohort (cf (n,T-1,2H,H), valid (n,T-1) bit masks) -> (2H,) sums: squared error per
+    projection step, scored rows per projection step."""
+    lib = _native.load()
+    n, T = factual.shape
+    H = cf.shape[3]
+    per_step = 1 if coefs.dim() == 4 else 0
+    assert per_step == 0 or tuple(coefs.shape) == (n, T - 1, 4, 4)
+    sums = torch.empty(2 * H, dtype=torch.float64, device='cuda')
+    rc = lib.b200i_cf_eval_treatment_seq(n, T, H, float(dt), int(substeps), _ptr(factual), _ptr(codes), _ptr(cf), _ptr(valid),
+                                         _ptr(n_steps), _ptr(static_feature), _ptr(coefs), per_step, float(drop_below),
+                                         _ptr(sums), _stream())
+    _native.check(rc, "b200i_cf_eval_treatment_seq")
+    return sums
+
+
+def insite_bfgs_prefix(factual, codes, n_steps, static_feature, theta0, lam, fit_offset, gtol=1e-12, max_iter=200,
+                       dt=STANDARD_DT, substeps=STEPS_FOR_DT):
+    """K7 per (patient, t) of a compact cohort: fit window = the first t + fit_offset transitions of the factual
+    trajectory.  Returns (coefs (n,T-1,4,4), status (n,T-1) int32, fval (n,T-1,2))."""
+    lib = _native.load()
+    n, T = factual.shape
+    coefs = torch.empty((n, T - 1, 4, 4), dtype=torch.float64, device='cuda')
+    status = torch.empty((n, T - 1), dtype=torch.int32, device='cuda')
+    fval = torch.empty((n, T - 1, 2), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_insite_bfgs_prefix(n, T, int(fit_offset), float(dt), int(substeps), _ptr(factual), _ptr(codes),
+                                      _ptr(n_steps), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
+                                      int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+    _native.check(rc, "b200i_insite_bfgs_prefix")
+    return coefs, status, fval
+
+
+def stlsq_prefix(factual, codes, n_steps, static_feature, prior, lam, fit_offset, threshold=1e-3, support_tol=1e-3,
+                 max_iter=10, fd_dt=STANDARD_DT):
+    """K5b per (patient, t) of a compact cohort (running sums, one pass per patient) -> coefs (n,T-1,4,4)."""
+    lib = _native.load()
+    n, T = factual.shape
+    coefs = torch.empty((n, T - 1, 4, 4), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_stlsq_prefix(n, T, int(fit_offset), float(fd_dt), _ptr(factual), _ptr(codes), _ptr(n_steps),
+                                _ptr(static_feature), _ptr(prior), float(support_tol), float(lam), float(threshold),
+                                int(max_iter), _ptr(coefs), _stream())
+    _native.check(rc, "b200i_stlsq_prefix")
+    return coefs
