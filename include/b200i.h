@@ -422,6 +422,39 @@ B200I_API int b200i_stlsq_prefix(int64_t n, int32_t T, int32_t fit_offset, doubl
                            const double *prior, double support_tol, double lam, double threshold, int32_t max_iter,
                            double *coefs_out, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Irregular sampling (BASELINE config C4).  The reference's integrator takes any time grid -- odeint(func, y0, t),
+ * pkpd/utils.py:68-90: dts = diff(t), every interval split into STEPS_FOR_DT Euler sub-steps of dts[k] / STEPS_FOR_DT
+ * when hmax < dts[0] -- but its live path always feeds the uniform STANDARD_DT (sindy.py:90, :395, :565;
+ * FiniteDifference(is_uniform=True), :195).  These entry points take the interval lengths explicitly:
+ *   dts[k] = t[k+1] - t[k], the time between column k and column k+1 of a row; (W,) shared by all rows
+ *   (dts_per_row == 0) or (R, W) per row (dts_per_row == 1), W as in the uniform entry point of the same name
+ *   (theta_gram: T-1 intervals between the T volumes).
+ * Rollouts step with h = dts[k] / substeps, fits differentiate with (x[k+1] - x[k]) / dts[k] (pysindy
+ * FiniteDifference(order=1) on a time array).  A dts array filled with the uniform dt reproduces the uniform entry
+ * points bit for bit.  Known answers: the reference's in-file odeint tests (dy/dt = 1 => y = t on a dense and on a
+ * two-point grid, pkpd/utils.py:759-828).
+ * b200i_stlsq_batched_dts also offers FP32 STORAGE of the volumes (x_f32 instead of x; arithmetic stays FP64,
+ * SURVEY.md App. E.5): pass exactly one of x / x_f32; dts may be NULL (uniform fd_dt).
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_ode_rollout_dts(int64_t rows, int32_t W, int32_t substeps, const double *x0,
+                           const double *static_feature, const uint8_t *codes, const double *coefs,
+                           int32_t coefs_per_row, double drop_below, const double *dts, int32_t dts_per_row,
+                           int32_t fp32, double *pred, void *stream);
+B200I_API int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x, const float *x_f32, const uint8_t *codes,
+                           const int32_t *fit_len, const double *static_feature, const double *prior,
+                           double support_tol, double lam, double threshold, int32_t max_iter, double fd_dt,
+                           const double *dts, int32_t dts_per_row, double *coefs_out, void *stream);
+B200I_API int b200i_insite_bfgs_dts(int64_t rows, int32_t W, int32_t substeps, const double *x, const uint8_t *codes,
+                           const int32_t *sequence_lengths, int32_t projection_horizon, const double *static_feature,
+                           const double *theta0, double lam, double gtol, int32_t max_iter, const double *dts,
+                           int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+B200I_API int b200i_theta_gram_dts(int64_t n, int32_t T, const double *cancer_volume, const double *chemo_application,
+                           const double *radio_application, const double *sequence_lengths,
+                           const double *static_feature, const double *dts, int32_t dts_per_row,
+                           void *gram_workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,10 +148,6 @@ __global__ void stlsq_joint_kernel(const double *__restrict__ stats, double thre
 }
 
 // ---- K6 ------------------------------------------------------------------------------------------
-// thread per row; predictions staged in shared memory (odd pitch: conflict-free) and written back
-// as one contiguous, fully coalesced chunk per CTA.
-constexpr int RP = 128;
-
 // single-rounding arithmetic in the rollout's compute type (no FMA contraction: mirrors the reference's
 // separate multiply / add, pkpd/utils.py:68-71)
 __device__ __forceinline__ double r_add(double a, double b) { return __dadd_rn(a, b); }
@@ -159,16 +155,143 @@ __device__ __forceinline__ double r_mul(double a, double b) { return __dmul_rn(a
 __device__ __forceinline__ float r_add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float r_mul(float a, float b) { return __fmul_rn(a, b); }
 
+// one interval: `substeps` explicit Euler steps  y + (c0*1 + c1*y + c2*u + c3*(y*u)) * h   (pkpd/utils.py:68-71,
+// sindy.py:491-496) with the ODE of treatment code a (argmax of the one-hot, sindy.py:310 / :499)
+template <typename R>
+__device__ __forceinline__ R euler_interval(R v, const R (&c)[4][4], int a, R u, R h, int substeps)
+{
+    const R c0 = a == 0 ? c[0][0] : a == 1 ? c[1][0] : a == 2 ? c[2][0] : c[3][0];
+    const R c1 = a == 0 ? c[0][1] : a == 1 ? c[1][1] : a == 2 ? c[2][1] : c[3][1];
+    const R c2 = a == 0 ? c[0][2] : a == 1 ? c[1][2] : a == 2 ? c[2][2] : c[3][2];
+    const R c3 = a == 0 ? c[0][3] : a == 1 ? c[1][3] : a == 2 ? c[2][3] : c[3][3];
+    const R c2u = r_mul(c2, u);
+    for (int sidx = 0; sidx < substeps; ++sidx) {
+        R f = r_add(c0, r_mul(c1, v));
+        f = r_add(f, c2u);
+        f = r_add(f, r_mul(c3, r_mul(v, u)));
+        v = r_add(v, r_mul(f, h));
+    }
+    return v;
+}
+
 // R = double: the reference's arithmetic (jax_enable_x64).  R = float: the FP32 variant of BASELINE config C4
 // (same inputs and outputs in float64, state / coefficients / Euler steps in float32; agrees to ~1e-5 relative
 // over 295 sub-steps, tolerance 1e-4).
+//
+// Tiled kernel (W <= R6_MAXW): a warp owns 32 consecutive rows and works on its own; their code bytes and per-row
+// coefficient matrices are contiguous in global memory and arrive by coalesced 16-byte / 8-byte loads into shared
+// memory; a thread integrates one row and parks 16 predictions at a time in a [32][17] staging tile (conflict free
+// both ways) that the warp writes back as 128-byte row segments; per-row interval lengths (irregular sampling)
+// travel through the same tile in the opposite direction.  ~10 KB of shared memory per warp instead of the 60 KB per
+// 128 rows of the first version (3 CTAs / SM, byte-wise strided code loads: 0.61 ms per 1M x 59 rows).
+constexpr int R6_WARPS = 4;
+constexpr int R6_CH = 16;
+constexpr int R6_MAXW = 128;
+
+template <typename R>
+__global__ void __launch_bounds__(R6_WARPS * 32)
+ode_rollout_tiled_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x0,
+                         const double *__restrict__ static_feature, const uint8_t *__restrict__ codes,
+                         const double *__restrict__ coefs, int per_row, double drop_below,
+                         const double *__restrict__ dts, int dts_per_row, double *__restrict__ pred)
+{
+    extern __shared__ __align__(16) uint8_t smem6[];
+    __shared__ double s_coef[16];
+    __shared__ double s_dt[R6_MAXW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int code_bytes = (32 * W + 15) & ~15;
+    double(*s_io)[R6_CH + 1] = reinterpret_cast<double(*)[R6_CH + 1]>(smem6) + (size_t)warp * 32;
+    double(*s_cf)[17] = reinterpret_cast<double(*)[17]>(smem6 + (size_t)R6_WARPS * 32 * (R6_CH + 1) * 8) + (size_t)warp * 32;
+    uint8_t *s_code = smem6 + (size_t)R6_WARPS * 32 * (R6_CH + 1) * 8 + (per_row ? (size_t)R6_WARPS * 32 * 17 * 8 : 0) +
+                      (size_t)warp * code_bytes;
+    if (!per_row && tid < 16) {
+        const double c = coefs[tid];
+        s_coef[tid] = (fabs(c) > drop_below) ? c : 0.0;
+    }
+    if (dts && !dts_per_row)
+        for (int k = tid; k < W; k += blockDim.x) s_dt[k] = dts[k];
+    __syncthreads();
+    const R h_uniform = (R)(dt / substeps);
+    const bool codes16 = (reinterpret_cast<uintptr_t>(codes) & 15u) == 0;
+    const int64_t ntiles = (rows + 31) / 32;
+    for (int64_t tile = (int64_t)blockIdx.x * R6_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * R6_WARPS) {
+        const int64_t first = tile * 32;
+        const int nrows = (int)((rows - first < 32) ? (rows - first) : 32);
+        const int64_t r = first + lane;
+        const bool live = lane < nrows;
+        __syncwarp();
+        {   // code bytes of the tile: contiguous nrows * W bytes starting at a multiple of 32
+            const int nbytes = nrows * W;
+            const uint8_t *g = codes + first * W;
+            int done = 0;
+            if (codes16) {
+                const int n16 = nbytes >> 4;
+                const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+                uint4 *s4 = reinterpret_cast<uint4 *>(s_code);
+                for (int e = lane; e < n16; e += 32) s4[e] = __ldg(g4 + e);
+                done = n16 << 4;
+            }
+            for (int e = done + lane; e < nbytes; e += 32) s_code[e] = g[e];
+        }
+        if (per_row) {
+            const double *g = coefs + first * 16;
+            for (int e = lane; e < nrows * 16; e += 32) s_cf[e >> 4][e & 15] = g[e];
+        }
+        __syncwarp();
+        R c[4][4];
+        R v = (R)0, u = (R)0;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double cv = per_row ? s_cf[lane][j] : s_coef[j];
+                if (per_row) cv = (fabs(cv) > drop_below) ? cv : 0.0;
+                c[j >> 2][j & 3] = (R)cv;
+            }
+            v = (R)x0[r];
+            u = (R)static_feature[r];
+        }
+        for (int k0 = 0; k0 < W; k0 += R6_CH) {
+            const int nc = (W - k0 < R6_CH) ? (W - k0) : R6_CH;
+            if (dts && dts_per_row) {   // interval lengths of this chunk, (nrows, nc) row segments
+                const double *g = dts + first * W + k0;
+                if (nc == R6_CH)
+                    for (int e = lane; e < nrows * R6_CH; e += 32) s_io[e >> 4][e & 15] = g[(int64_t)(e >> 4) * W + (e & 15)];
+                else
+                    for (int e = lane; e < nrows * nc; e += 32) s_io[e / nc][e % nc] = g[(int64_t)(e / nc) * W + (e % nc)];
+                __syncwarp();
+            }
+            if (live) {
+                const uint8_t *cr = s_code + lane * W + k0;
+                for (int kk = 0; kk < nc; ++kk) {
+                    R h = h_uniform;
+                    if (dts) h = (R)((dts_per_row ? s_io[lane][kk] : s_dt[k0 + kk]) / substeps);
+                    v = euler_interval<R>(v, c, cr[kk] & 3, u, h, substeps);
+                    s_io[lane][kk] = (double)v;
+                }
+            }
+            __syncwarp();
+            double *g = pred + first * W + k0;
+            if (nc == R6_CH)
+                for (int e = lane; e < nrows * R6_CH; e += 32) g[(int64_t)(e >> 4) * W + (e & 15)] = s_io[e >> 4][e & 15];
+            else
+                for (int e = lane; e < nrows * nc; e += 32) g[(int64_t)(e / nc) * W + (e % nc)] = s_io[e / nc][e % nc];
+            __syncwarp();
+        }
+    }
+}
+
+// generic kernel (any W): thread per row; predictions staged in shared memory (odd pitch: conflict-free) and written
+// back as one contiguous, fully coalesced chunk per CTA.
+constexpr int RP = 128;
+
 template <typename R>
 __global__ void __launch_bounds__(RP)
-ode_rollout_kernel(int64_t rows, int W, double h_d, int substeps, const double *__restrict__ x0,
+ode_rollout_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x0,
                    const double *__restrict__ static_feature, const uint8_t *__restrict__ codes,
-                   const double *__restrict__ coefs, int per_row, double drop_below, double *__restrict__ pred)
+                   const double *__restrict__ coefs, int per_row, double drop_below, const double *__restrict__ dts,
+                   int dts_per_row, double *__restrict__ pred)
 {
-    const R h = (R)h_d;
+    const R h_uniform = (R)(dt / substeps);
     extern __shared__ double s_out[];  // [RP][W | 1]
     __shared__ double s_coef[16];
     const int pitch = W | 1;
@@ -197,21 +320,10 @@ ode_rollout_kernel(int64_t rows, int W, double h_d, int substeps, const double *
             R v = (R)x0[r];
             const R u = (R)static_feature[r];
             const uint8_t *cr = codes + r * W;
+            const double *dr = dts ? dts + (dts_per_row ? r * W : 0) : nullptr;
             for (int k = 0; k < W; ++k) {
-                const int a = cr[k] & 3;
-                // select the treatment's ODE (argmax of the one-hot, sindy.py:310 / :499)
-                const R c0 = a == 0 ? c[0][0] : a == 1 ? c[1][0] : a == 2 ? c[2][0] : c[3][0];
-                const R c1 = a == 0 ? c[0][1] : a == 1 ? c[1][1] : a == 2 ? c[2][1] : c[3][1];
-                const R c2 = a == 0 ? c[0][2] : a == 1 ? c[1][2] : a == 2 ? c[2][2] : c[3][2];
-                const R c3 = a == 0 ? c[0][3] : a == 1 ? c[1][3] : a == 2 ? c[2][3] : c[3][3];
-                const R c2u = r_mul(c2, u);
-                for (int sidx = 0; sidx < substeps; ++sidx) {
-                    // y + (c0*1 + c1*y + c2*u + c3*(y*u)) * h   (pkpd/utils.py:68-71, sindy.py:491-496)
-                    R f = r_add(c0, r_mul(c1, v));
-                    f = r_add(f, c2u);
-                    f = r_add(f, r_mul(c3, r_mul(v, u)));
-                    v = r_add(v, r_mul(f, h));
-                }
+                const R h = dr ? (R)(dr[k] / substeps) : h_uniform;
+                v = euler_interval<R>(v, c, cr[k] & 3, u, h, substeps);
                 s_out[tid * pitch + k] = (double)v;
             }
         }
@@ -340,14 +452,66 @@ extern "C" int b200i_stlsq_joint(const double *stats, double threshold, double a
 
 static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
                             const double *static_feature, const uint8_t *codes, const double *coefs,
-                            int32_t coefs_per_row, double drop_below, double *pred, void *stream);
+                            int32_t coefs_per_row, double drop_below, const double *dts, int32_t dts_per_row, double *pred,
+                            void *stream)
+{
+    B200I_REQUIRE(rows >= 0 && x0 && static_feature && codes && coefs && pred, B200I_E_ARG,
+                  "ode_rollout: NULL argument or negative rows");
+    B200I_REQUIRE(W >= 1 && W <= 2048 && substeps >= 1, B200I_E_UNSUPPORTED, "ode_rollout: W=%d substeps=%d", W, substeps);
+    B200I_REQUIRE(dts != nullptr || dt > 0, B200I_E_ARG, "ode_rollout: dt must be positive when no interval lengths are given");
+    if (rows == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W <= R6_MAXW) {
+        const int code_bytes = (32 * W + 15) & ~15;
+        const int smem = R6_WARPS * (32 * (R6_CH + 1) * 8 + (coefs_per_row ? 32 * 17 * 8 : 0) + code_bytes);
+        const void *kern = f32 ? reinterpret_cast<const void *>(ode_rollout_tiled_kernel<float>)
+                               : reinterpret_cast<const void *>(ode_rollout_tiled_kernel<double>);
+        int per_sm = 1;
+        {
+            int rc0 = ensure_dyn_smem(kern, smem, R6_WARPS * 32, &per_sm);
+            if (rc0) return rc0;
+        }
+        if (per_sm < 1) per_sm = 1;
+        const int64_t ntiles = (rows + 31) / 32;
+        int64_t grid = (ntiles + R6_WARPS - 1) / R6_WARPS;
+        const int64_t cap = (int64_t)num_sms() * per_sm;
+        if (grid > cap) grid = cap;
+        if (f32)
+            ode_rollout_tiled_kernel<float><<<(unsigned)grid, R6_WARPS * 32, smem, st>>>(
+                rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, dts, dts_per_row, pred);
+        else
+            ode_rollout_tiled_kernel<double><<<(unsigned)grid, R6_WARPS * 32, smem, st>>>(
+                rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, dts, dts_per_row, pred);
+        return check_cuda(cudaGetLastError(), "ode_rollout launch");
+    }
+    const size_t smem = (size_t)RP * (W | 1) * sizeof(double);
+    B200I_REQUIRE(smem <= 200 * 1024, B200I_E_UNSUPPORTED, "ode_rollout: W=%d too wide", W);
+    const void *kern = f32 ? reinterpret_cast<const void *>(ode_rollout_kernel<float>)
+                           : reinterpret_cast<const void *>(ode_rollout_kernel<double>);
+    int per_sm = 1;
+    {
+        int rc0 = ensure_dyn_smem(kern, (int)smem, RP, &per_sm);
+        if (rc0) return rc0;
+    }
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (rows + RP - 1) / RP;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
+    if (grid > cap) grid = cap;
+    if (f32)
+        ode_rollout_kernel<float><<<(unsigned)grid, RP, smem, st>>>(rows, W, dt, substeps, x0, static_feature, codes, coefs,
+                                                                     coefs_per_row, drop_below, dts, dts_per_row, pred);
+    else
+        ode_rollout_kernel<double><<<(unsigned)grid, RP, smem, st>>>(rows, W, dt, substeps, x0, static_feature, codes, coefs,
+                                                                      coefs_per_row, drop_below, dts, dts_per_row, pred);
+    return check_cuda(cudaGetLastError(), "ode_rollout launch");
+}
 
 extern "C" int b200i_ode_rollout(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
                                  const double *static_feature, const uint8_t *codes, const double *coefs,
                                  int32_t coefs_per_row, double drop_below, double *pred, void *stream)
 {
     return ode_rollout_impl(false, rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below,
-                            pred, stream);
+                            nullptr, 0, pred, stream);
 }
 
 extern "C" int b200i_ode_rollout_f32(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
@@ -355,27 +519,17 @@ extern "C" int b200i_ode_rollout_f32(int64_t rows, int32_t W, double dt, int32_t
                                      int32_t coefs_per_row, double drop_below, double *pred, void *stream)
 {
     return ode_rollout_impl(true, rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below,
-                            pred, stream);
+                            nullptr, 0, pred, stream);
 }
 
-static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
-                            const double *static_feature, const uint8_t *codes, const double *coefs,
-                            int32_t coefs_per_row, double drop_below, double *pred, void *stream)
+extern "C" int b200i_ode_rollout_dts(int64_t rows, int32_t W, int32_t substeps, const double *x0,
+                                     const double *static_feature, const uint8_t *codes, const double *coefs,
+                                     int32_t coefs_per_row, double drop_below, const double *dts, int32_t dts_per_row,
+                                     int32_t fp32, double *pred, void *stream)
 {
-    B200I_REQUIRE(rows >= 0 && x0 && static_feature && codes && coefs && pred, B200I_E_ARG,
-                  "ode_rollout: NULL argument or negative rows");
-    B200I_REQUIRE(W >= 1 && W <= 2048 && substeps >= 1, B200I_E_UNSUPPORTED, "ode_rollout: W=%d substeps=%d", W, substeps);
-    if (rows == 0) return 0;
-    const size_t smem = (size_t)RP * (W | 1) * sizeof(double);
-    B200I_REQUIRE(smem <= 200 * 1024, B200I_E_UNSUPPORTED, "ode_rollout: W=%d too wide", W);
-    auto kern = f32 ? ode_rollout_kernel<float> : ode_rollout_kernel<double>;
-    B200I_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (rows + RP - 1) / RP;
-    const int64_t cap = (int64_t)num_sms() * 3;
-    if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, RP, smem, static_cast<cudaStream_t>(stream)>>>(
-        rows, W, dt / substeps, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, pred);
-    return check_cuda(cudaGetLastError(), "ode_rollout launch");
+    B200I_REQUIRE(dts != nullptr, B200I_E_ARG, "ode_rollout_dts: dts is NULL");
+    return ode_rollout_impl(fp32 != 0, rows, W, 0.0, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below,
+                            dts, dts_per_row, pred, stream);
 }
 
 extern "C" int b200i_treatment_codes(int64_t rows, int32_t W, int32_t row_pitch, const double *chemo_application,

@@ -76,13 +76,14 @@ __global__ void __launch_bounds__(128)
 stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
                      const int *__restrict__ fit_len, const double *__restrict__ static_u,
                      const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
-                     double *__restrict__ coefs_out)
+                     const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out)
 {
     __shared__ double s_prior[16];
     if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
     __syncthreads();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
+    const double *dr = dts ? dts + (dts_per_row ? r * W : 0) : nullptr;
     int n = fit_len[r];
     if (n > W - 1) n = W - 1;
     const double u = static_u[r];
@@ -96,7 +97,7 @@ stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict
         for (int k = 0; k < n; ++k) {
             const double x1 = xr[k + 1];
             const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
-            const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+            const double xdot = __ddiv_rn(__dsub_rn(x1, x0), dr ? dr[k] : fd_dt);
             pg.add(a0, x0, xdot);
             if (k == n - 1 || a1 != a0) pg.add(a0, x1, xdot);
             x0 = x1;
@@ -104,6 +105,120 @@ stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict
         }
     }
     ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, coefs_out + r * 16);
+}
+
+// Tiled K5b (W <= K5_MAXW): a warp owns 32 consecutive rows; their code bytes arrive by coalesced 16-byte loads, the
+// volumes (float64, or float32 storage: BASELINE config C4 "FP32 vs FP64") and -- with irregular sampling -- the
+// per-row interval lengths travel 16 columns at a time through [32][17] staging tiles (row segments of 128 bytes in
+// global memory, conflict free in shared memory); a thread walks one row, the warp stops at its longest fit window,
+// and the 16 coefficients per row leave through the same tile as one contiguous block.  The per-thread row walk of
+// stlsq_batched_kernel touches 8 of every 32 bytes it fetches and depends on L1 to see the rest (0.88 ms per 1M rows).
+constexpr int K5_WARPS = 4;
+constexpr int K5_CH = 16;
+constexpr int K5_MAXW = 128;
+
+template <typename X>
+__global__ void __launch_bounds__(K5_WARPS * 32)
+stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restrict__ x, const uint8_t *__restrict__ codes,
+                           const int *__restrict__ fit_len, const double *__restrict__ static_u,
+                           const double *__restrict__ prior, double support_tol, double lam, double threshold,
+                           int max_iter, const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out)
+{
+    extern __shared__ __align__(16) uint8_t smem5[];
+    __shared__ double s_prior[16];
+    __shared__ double s_dtg[K5_MAXW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int code_bytes = (32 * W + 15) & ~15;
+    double(*s_x)[K5_CH + 1] = reinterpret_cast<double(*)[K5_CH + 1]>(smem5) + (size_t)warp * 32;
+    double(*s_t)[K5_CH + 1] = reinterpret_cast<double(*)[K5_CH + 1]>(smem5 + (size_t)K5_WARPS * 32 * (K5_CH + 1) * 8) + (size_t)warp * 32;
+    uint8_t *s_code = smem5 + (size_t)2 * K5_WARPS * 32 * (K5_CH + 1) * 8 + (size_t)warp * code_bytes;
+    if (tid < 16) s_prior[tid] = prior[tid];
+    if (dts && !dts_per_row)
+        for (int k = tid; k < W; k += blockDim.x) s_dtg[k] = dts[k];
+    __syncthreads();
+    const bool codes16 = (reinterpret_cast<uintptr_t>(codes) & 15u) == 0;
+    const int64_t ntiles = (rows + 31) / 32;
+    for (int64_t tile = (int64_t)blockIdx.x * K5_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * K5_WARPS) {
+        const int64_t first = tile * 32;
+        const int nrows = (int)((rows - first < 32) ? (rows - first) : 32);
+        const int64_t r = first + lane;
+        const bool live = lane < nrows;
+        int n = 0;
+        double u = 0.0;
+        if (live) {
+            n = fit_len[r];
+            if (n > W - 1) n = W - 1;
+            if (n < 0) n = 0;
+            u = static_u[r];
+        }
+        int nmax = n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        __syncwarp();
+        if (nmax > 0) {
+            const int nbytes = nrows * W;
+            const uint8_t *g = codes + first * W;
+            int done = 0;
+            if (codes16) {
+                const int n16 = nbytes >> 4;
+                const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+                uint4 *s4 = reinterpret_cast<uint4 *>(s_code);
+                for (int e = lane; e < n16; e += 32) s4[e] = __ldg(g4 + e);
+                done = n16 << 4;
+            }
+            for (int e = done + lane; e < nbytes; e += 32) s_code[e] = g[e];
+        }
+        __syncwarp();
+        PatientGram pg;
+        pg.clear();
+        double x0 = 0.0, dt_k = fd_dt;
+        const uint8_t *cr = s_code + lane * W;
+        // column j of the row: j = 0 starts the walk, j >= 1 closes transition k = j - 1
+        for (int j0 = 0; j0 <= nmax; j0 += K5_CH) {
+            const int nc = (nmax + 1 - j0 < K5_CH) ? (nmax + 1 - j0) : K5_CH;
+            const X *gx = x + first * W + j0;
+            if (nc == K5_CH)
+                for (int e = lane; e < nrows * K5_CH; e += 32) s_x[e >> 4][e & 15] = (double)gx[(int64_t)(e >> 4) * W + (e & 15)];
+            else
+                for (int e = lane; e < nrows * nc; e += 32) s_x[e / nc][e % nc] = (double)gx[(int64_t)(e / nc) * W + (e % nc)];
+            if (dts && dts_per_row) {
+                const double *gt = dts + first * W + j0;
+                if (nc == K5_CH)
+                    for (int e = lane; e < nrows * K5_CH; e += 32) s_t[e >> 4][e & 15] = gt[(int64_t)(e >> 4) * W + (e & 15)];
+                else
+                    for (int e = lane; e < nrows * nc; e += 32) s_t[e / nc][e % nc] = gt[(int64_t)(e / nc) * W + (e % nc)];
+            }
+            __syncwarp();
+            if (live) {
+                for (int jj = 0; jj < nc; ++jj) {
+                    const int j = j0 + jj;
+                    const double xv = s_x[lane][jj];
+                    if (j >= 1 && j <= n) {
+                        const int k = j - 1;
+                        const int a0 = cr[k] & 3;
+                        const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
+                        const double xdot = __ddiv_rn(__dsub_rn(xv, x0), dt_k);
+                        pg.add(a0, x0, xdot);
+                        if (k == n - 1 || a1 != a0) pg.add(a0, xv, xdot);
+                    }
+                    x0 = xv;
+                    if (dts) dt_k = dts_per_row ? s_t[lane][jj] : s_dtg[j];   // length of the interval that starts at column j
+                }
+            }
+            __syncwarp();
+        }
+        double out16[16];
+        if (live) ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, out16);
+        __syncwarp();
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s_x[lane][q] = out16[q];
+        }
+        __syncwarp();
+        double *go = coefs_out + first * 16;
+        for (int e = lane; e < nrows * 16; e += 32) go[e] = s_x[e >> 4][e & 15];
+        __syncwarp();
+    }
 }
 
 // K5b on a compact counterfactual cohort: all rows of one (patient, t) share their fit window F[0..n_fit], so a thread
@@ -162,6 +277,7 @@ constexpr int BFGS_MAXW = 80;
 struct RowData {
     const double *x;       // shared memory: x[0..n_fit]
     const uint8_t *codes;  // shared memory: codes[0..n_fit-1]
+    const double *dts;     // shared memory: interval lengths dts[0..n_fit-1] (irregular sampling), or nullptr
     int n_fit;
     double u, h, norm, lam;
     int substeps;
@@ -186,6 +302,7 @@ __device__ __forceinline__ double max16(double v, unsigned mask)
 
 // objective and gradient component of this lane: f_to_min_func (sindy.py:781-794) with forward
 // sensitivities through the Euler rollout (predict_with_reduced_coefs :767-778, odeint pkpd/utils.py:68-90)
+template <bool DTS>
 __device__ __forceinline__ void eval_objective(const RowData &d, double theta, double theta0, double mask_j, int my_a,
                                                int my_m, unsigned gmask, int gbase, double &f, double &g)
 {
@@ -197,13 +314,14 @@ __device__ __forceinline__ void eval_objective(const RowData &d, double theta, d
         const double c2 = shfl16(tm, 4 * a + 2, gmask, gbase), c3 = shfl16(tm, 4 * a + 3, gmask, gbase);
         const double c2u = c2 * d.u, dfdv = c1 + c3 * d.u;
         const bool mine = (a == my_a);
+        const double h = DTS ? d.dts[k] / d.substeps : d.h;
         for (int q = 0; q < d.substeps; ++q) {
             const double vu = v * d.u;
             const double fval = ((c0 + c1 * v) + c2u) + c3 * vu;
             const double basis = my_m == 0 ? 1.0 : (my_m == 1 ? v : (my_m == 2 ? d.u : vu));
             const double dfj = mine ? basis * mask_j : 0.0;
-            s = s + d.h * (dfdv * s + dfj);
-            v = v + d.h * fval;
+            s = s + h * (dfdv * s + dfj);
+            v = v + h * fval;
         }
         const double r = d.x[k + 1] - v;
         acc += r * r;
@@ -221,6 +339,7 @@ __device__ __forceinline__ void eval_objective(const RowData &d, double theta, d
 // interaction_only=True): 1 x0 u0 u1 u2 x0u0 x0u1 x0u2 u0u1 u0u2 u1u2.  Lane j < 11 owns coefficient j; its basis value
 // is (x0 or 1) * w_j(treatment code), w_j tabulated per row for the four codes; the constant part and the slope of
 // the step's right-hand side are two masked sums over the lanes.  Lanes 11..15 carry zeros.
+template <bool DTS>
 __device__ __forceinline__ void eval_objective_joint(const RowData &d, double theta, double theta0, double mask_j,
                                                      int j, unsigned gmask, double &f, double &g)
 {
@@ -251,11 +370,12 @@ __device__ __forceinline__ void eval_objective_joint(const RowData &d, double th
         const double c_const = sum16(is_x ? 0.0 : tw, gmask);
         const double c_x = sum16(is_x ? tw : 0.0, gmask);
         const double wj = wa * mask_j;
+        const double h = DTS ? d.dts[k] / d.substeps : d.h;
         for (int q = 0; q < d.substeps; ++q) {
             const double fval = c_const + c_x * v;
             const double dfj = is_x ? wj * v : wj;
-            s = s + d.h * (c_x * s + dfj);
-            v = v + d.h * fval;
+            s = s + h * (c_x * s + dfj);
+            v = v + h * fval;
         }
         const double r = d.x[k + 1] - v;
         acc += r * r;
@@ -293,15 +413,16 @@ __device__ __forceinline__ double quadmin(double a, double fa, double fpa, doubl
 // r = patient * (W-1) + t reads the patient's factual trajectory x[patient, 0..W) and its factual option codes
 // (2*chemo + radio, translated to chemo + 2*radio), seq_len holds the patient's executed steps and `ph` the offset of
 // the fit window: n_fit = t + ph for t < executed steps, else the row does not exist (theta0, status -2).
-template <int MINB, bool JOINT = false, bool PREFIX = false>
+template <int MINB, bool JOINT = false, bool PREFIX = false, bool DTS = false>
 __global__ void __launch_bounds__(BFGS_THREADS, MINB)
 insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x,
                    const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
                    const double *__restrict__ static_u, const double *__restrict__ theta0_g, double lam, double gtol,
                    int max_iter, double *__restrict__ coefs_out, int *__restrict__ status_out,
-                   double *__restrict__ fval_out)
+                   double *__restrict__ fval_out, const double *__restrict__ dts = nullptr, int dts_per_row = 0)
 {
     __shared__ double s_x[BFGS_GROUPS][BFGS_MAXW + 1];
+    __shared__ double s_dt[DTS ? BFGS_GROUPS : 1][BFGS_MAXW];
     __shared__ uint8_t s_c[BFGS_GROUPS][BFGS_MAXW];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 4, j = threadIdx.x & 15;
     const int gbase = lane & 16;
@@ -311,8 +432,8 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
     const double theta0 = j < NP ? theta0_g[j] : 0.0;
     const double mask_j = fabs(theta0) > 1e-3 ? 1.0 : 0.0;   // coef_sparse_mask, sindy.py:589
     auto objective = [&](const RowData &d, double th, double &f, double &g) {
-        if (JOINT) eval_objective_joint(d, th, theta0, mask_j, j, gmask, f, g);
-        else eval_objective(d, th, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
+        if (JOINT) eval_objective_joint<DTS>(d, th, theta0, mask_j, j, gmask, f, g);
+        else eval_objective<DTS>(d, th, theta0, mask_j, my_a, my_m, gmask, gbase, f, g);
     };
     const int64_t ngroups = (int64_t)gridDim.x * BFGS_GROUPS;
     const int64_t iters = (rows + ngroups - 1) / ngroups;
@@ -339,6 +460,8 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                 const int c = codes[src * W + k];
                 s_c[grp][k] = (uint8_t)(PREFIX ? (((c & 1) << 1) | ((c >> 1) & 1)) : c);
             }
+            if (DTS)
+                for (int k = j; k < n_fit; k += 16) s_dt[grp][k] = dts[(dts_per_row ? src * W : 0) + k];
         }
         __syncwarp(gmask);
         if (!valid) continue;
@@ -348,7 +471,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
             continue;
         }
         RowData d;
-        d.x = s_x[grp]; d.codes = s_c[grp]; d.n_fit = n_fit; d.u = static_u[src];
+        d.x = s_x[grp]; d.codes = s_c[grp]; d.dts = DTS ? s_dt[grp] : nullptr; d.n_fit = n_fit; d.u = static_u[src];
         d.h = dt / substeps; d.substeps = substeps; d.norm = 1.0; d.lam = lam;
 
         double theta = theta0, f, g;
@@ -485,20 +608,92 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
 
 using namespace b200i;
 
+template <typename X>
+static int stlsq_batched_impl(int64_t rows, int32_t W, double fd_dt, const X *x, const uint8_t *codes,
+                              const int32_t *fit_len, const double *static_feature, const double *prior,
+                              double support_tol, double lam, double threshold, int32_t max_iter, const double *dts,
+                              int32_t dts_per_row, double *coefs_out, void *stream)
+{
+    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "stlsq_batched: negative rows");
+    if (rows == 0) return 0;
+    B200I_REQUIRE(x && codes && fit_len && static_feature && prior && coefs_out, B200I_E_ARG, "stlsq_batched: NULL argument");
+    B200I_REQUIRE(W >= 2 && (dts != nullptr || fd_dt > 0) && lam > 0 && threshold >= 0 && max_iter >= 1, B200I_E_ARG,
+                  "stlsq_batched: need W >= 2, fd_dt > 0, lam > 0 (the per-row design is rank deficient), threshold >= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W <= K5_MAXW) {
+        const int code_bytes = (32 * W + 15) & ~15;
+        const int smem = K5_WARPS * (2 * 32 * (K5_CH + 1) * 8 + code_bytes);
+        const void *kern = reinterpret_cast<const void *>(stlsq_batched_tiled_kernel<X>);
+        int per_sm = 1;
+        {
+            int rc0 = ensure_dyn_smem(kern, smem, K5_WARPS * 32, &per_sm);
+            if (rc0) return rc0;
+        }
+        if (per_sm < 1) per_sm = 1;
+        const int64_t ntiles = (rows + 31) / 32;
+        int64_t grid = (ntiles + K5_WARPS - 1) / K5_WARPS;
+        const int64_t cap = (int64_t)num_sms() * per_sm;
+        if (grid > cap) grid = cap;
+        stlsq_batched_tiled_kernel<X><<<(unsigned)grid, K5_WARPS * 32, smem, st>>>(
+            rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold, max_iter, dts, dts_per_row,
+            coefs_out);
+        return check_cuda(cudaGetLastError(), "stlsq_batched launch");
+    }
+    B200I_REQUIRE(sizeof(X) == sizeof(double), B200I_E_UNSUPPORTED, "stlsq_batched_f32: W=%d > %d", W, K5_MAXW);
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+    stlsq_batched_kernel<<<grid, 128, 0, st>>>(rows, W, fd_dt, reinterpret_cast<const double *>(x), codes, fit_len,
+                                               static_feature, prior, support_tol, lam, threshold, max_iter, dts, dts_per_row,
+                                               coefs_out);
+    return check_cuda(cudaGetLastError(), "stlsq_batched launch");
+}
+
 extern "C" int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const double *x, const uint8_t *codes,
                                    const int32_t *fit_len, const double *static_feature, const double *prior,
                                    double support_tol, double lam, double threshold, int32_t max_iter,
                                    double *coefs_out, void *stream)
 {
-    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "stlsq_batched: negative rows");
+    return stlsq_batched_impl<double>(rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold,
+                                      max_iter, nullptr, 0, coefs_out, stream);
+}
+
+extern "C" int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x, const float *x_f32, const uint8_t *codes,
+                                       const int32_t *fit_len, const double *static_feature, const double *prior,
+                                       double support_tol, double lam, double threshold, int32_t max_iter,
+                                       double fd_dt, const double *dts, int32_t dts_per_row, double *coefs_out, void *stream)
+{
+    B200I_REQUIRE((x != nullptr) != (x_f32 != nullptr), B200I_E_ARG, "stlsq_batched_dts: pass exactly one of x / x_f32");
+    if (x_f32)
+        return stlsq_batched_impl<float>(rows, W, fd_dt, x_f32, codes, fit_len, static_feature, prior, support_tol, lam,
+                                         threshold, max_iter, dts, dts_per_row, coefs_out, stream);
+    return stlsq_batched_impl<double>(rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold,
+                                      max_iter, dts, dts_per_row, coefs_out, stream);
+}
+
+static int insite_bfgs_impl(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x, const uint8_t *codes,
+                            const int32_t *sequence_lengths, int32_t projection_horizon, const double *static_feature,
+                            const double *theta0, double lam, double gtol, int32_t max_iter, const double *dts,
+                            int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out, void *stream)
+{
+    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs: negative rows");
     if (rows == 0) return 0;
-    B200I_REQUIRE(x && codes && fit_len && static_feature && prior && coefs_out, B200I_E_ARG, "stlsq_batched: NULL argument");
-    B200I_REQUIRE(W >= 2 && fd_dt > 0 && lam > 0 && threshold >= 0 && max_iter >= 1, B200I_E_ARG,
-                  "stlsq_batched: need W >= 2, fd_dt > 0, lam > 0 (the per-row design is rank deficient), threshold >= 0");
-    const unsigned grid = (unsigned)((rows + 127) / 128);
-    stlsq_batched_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold, max_iter, coefs_out);
-    return check_cuda(cudaGetLastError(), "stlsq_batched launch");
+    B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
+                  B200I_E_ARG, "insite_bfgs: NULL argument");
+    B200I_REQUIRE(W >= 2 && W <= BFGS_MAXW, B200I_E_UNSUPPORTED, "insite_bfgs: W=%d outside [2,%d]", W, BFGS_MAXW);
+    B200I_REQUIRE((dts != nullptr || dt > 0) && substeps >= 1 && lam >= 0 && max_iter >= 1, B200I_E_ARG,
+                  "insite_bfgs: bad scalar argument");
+    int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    // register budget for 4 CTAs per SM (measured: 3 -> 85 ms, 4 -> 69 ms, 5 -> 76 ms per 200k rows)
+    if (dts)
+        insite_bfgs_kernel<K7_MINB_DEFAULT, false, false, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+            rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+            max_iter, coefs_out, status_out, fval_out, dts, dts_per_row);
+    else
+        insite_bfgs_kernel<K7_MINB_DEFAULT, false><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+            rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
+            max_iter, coefs_out, status_out, fval_out);
+    return check_cuda(cudaGetLastError(), "insite_bfgs launch");
 }
 
 extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
@@ -507,20 +702,19 @@ extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t sub
                                  int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out,
                                  void *stream)
 {
-    B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs: negative rows");
-    if (rows == 0) return 0;
-    B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
-                  B200I_E_ARG, "insite_bfgs: NULL argument");
-    B200I_REQUIRE(W >= 2 && W <= BFGS_MAXW, B200I_E_UNSUPPORTED, "insite_bfgs: W=%d outside [2,%d]", W, BFGS_MAXW);
-    B200I_REQUIRE(dt > 0 && substeps >= 1 && lam >= 0 && max_iter >= 1, B200I_E_ARG, "insite_bfgs: bad scalar argument");
-    int64_t grid = (rows + BFGS_GROUPS - 1) / BFGS_GROUPS;
-    const int64_t cap = (int64_t)num_sms() * 8;
-    if (grid > cap) grid = cap;
-    // register budget for 4 CTAs per SM (measured: 3 -> 85 ms, 4 -> 69 ms, 5 -> 76 ms per 200k rows)
-    insite_bfgs_kernel<K7_MINB_DEFAULT, false><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-        max_iter, coefs_out, status_out, fval_out);
-    return check_cuda(cudaGetLastError(), "insite_bfgs launch");
+    return insite_bfgs_impl(rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0,
+                            lam, gtol, max_iter, nullptr, 0, coefs_out, status_out, fval_out, stream);
+}
+
+extern "C" int b200i_insite_bfgs_dts(int64_t rows, int32_t W, int32_t substeps, const double *x, const uint8_t *codes,
+                                     const int32_t *sequence_lengths, int32_t projection_horizon,
+                                     const double *static_feature, const double *theta0, double lam, double gtol,
+                                     int32_t max_iter, const double *dts, int32_t dts_per_row, double *coefs_out,
+                                     int32_t *status_out, double *fval_out, void *stream)
+{
+    B200I_REQUIRE(dts != nullptr, B200I_E_ARG, "insite_bfgs_dts: dts is NULL");
+    return insite_bfgs_impl(rows, W, 0.0, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0,
+                            lam, gtol, max_iter, dts, dts_per_row, coefs_out, status_out, fval_out, stream);
 }
 
 extern "C" int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,

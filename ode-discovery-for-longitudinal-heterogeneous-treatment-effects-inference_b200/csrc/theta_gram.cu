@@ -36,7 +36,8 @@ template <bool BULK>
 __global__ void __launch_bounds__(GP)
 theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol, const double *__restrict__ chemo,
                   const double *__restrict__ radio, const double *__restrict__ seq_len,
-                  const double *__restrict__ static_feature, StatsWorkspace *ws)
+                  const double *__restrict__ static_feature, StatsWorkspace *ws, const double *__restrict__ dts = nullptr,
+                  int dts_per_row = 0)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t bar;
@@ -44,7 +45,11 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
     __shared__ unsigned int s_is_last;
     double *s_vol = reinterpret_cast<double *>(smem_raw);                         // [GP][T]
     uint8_t *s_code = smem_raw + (size_t)GP * T * sizeof(double);                  // [GP][T]
+    // irregular sampling: interval lengths dts[k] = t[k+1] - t[k], (T-1,) for the cohort or (n, T-1) per patient
+    double *s_dt = reinterpret_cast<double *>(smem_raw + (((size_t)GP * T * 9 + 15) & ~(size_t)15));   // [GP][T-1] or [T-1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (dts && !dts_per_row)
+        for (int k = tid; k < T - 1; k += GP) s_dt[k] = dts[k];
 
     for (int j = tid; j < STATS_MAX_WARPS * STATS_PAD; j += GP) (&block_acc[0][0])[j] = 0.0;
     if (BULK && tid == 0) {
@@ -67,6 +72,10 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
             }
         } else {
             for (int64_t e = tid; e < elems; e += GP) s_vol[e] = gv[e];
+        }
+        if (dts && dts_per_row) {
+            const double *gd = dts + first * (T - 1);
+            for (int64_t e = tid; e < (int64_t)rows * (T - 1); e += GP) s_dt[e] = gd[e];
         }
         // treatment codes: code = chemo + 2*radio (dataset.py:130-141 one-hot index)
         const double *gc = chemo + first * T, *gr = radio + first * T;
@@ -97,12 +106,13 @@ theta_gram_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol
             u = static_feature[first + tid];
             const double *x = s_vol + (size_t)tid * T;
             const uint8_t *a = s_code + (size_t)tid * T;
+            const double *dtr = dts ? s_dt + (dts_per_row ? (size_t)tid * (T - 1) : 0) : nullptr;
             double x0 = x[0];
             int a0 = a[0];
             for (int k = 0; k < L; ++k) {
                 const double x1 = x[k + 1];
                 const int a1 = a[k + 1];
-                const double xdot = __ddiv_rn(__dsub_rn(x1, x0), fd_dt);
+                const double xdot = __ddiv_rn(__dsub_rn(x1, x0), dtr ? dtr[k] : fd_dt);
                 pg.add(a0, x0, xdot);
                 if (k == L - 1 || a1 != a0) pg.add(a0, x1, xdot);
                 x0 = x1;
@@ -564,7 +574,7 @@ extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, in
     if (grid > ntiles) grid = ntiles;
     if (grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
     kern<<<(unsigned)grid, GP, smem, st>>>(n, T, fd_dt, cancer_volume, chemo_application, radio_application,
-                                           sequence_lengths, static_feature, ws);
+                                           sequence_lengths, static_feature, ws, nullptr, 0);
     B200I_CUDA(cudaGetLastError());
     int64_t g2 = (n + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
@@ -572,4 +582,40 @@ extern "C" int b200i_theta_gram_mode(int64_t n, int32_t T, int64_t row_pitch, in
     masked_moments_kernel<<<(unsigned)g2, 256, 0, st>>>(n, T, cancer_volume, chemo_dosage, radio_dosage,
                                                         sequence_lengths, ws);
     return check_cuda(cudaGetLastError(), "theta_gram launch");
+}
+
+// Population statistics on an irregular time grid (BASELINE config C4): finite differences
+// (x[k+1] - x[k]) / (t[k+1] - t[k]), pysindy FiniteDifference(order=1) with a time array instead of a scalar step
+// (the reference always passes the uniform STANDARD_DT, sindy.py:195,203-213; odeint itself takes any grid,
+// pkpd/utils.py:68-90).  dts = interval lengths, (T-1,) for the cohort or (n, T-1) per patient.  Gram part only
+// (no dosage moments); first-generation kernel.
+extern "C" int b200i_theta_gram_dts(int64_t n, int32_t T, const double *cancer_volume, const double *chemo_application,
+                                    const double *radio_application, const double *sequence_lengths,
+                                    const double *static_feature, const double *dts, int32_t dts_per_row,
+                                    void *gram_workspace, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths && static_feature &&
+                      dts && gram_workspace,
+                  B200I_E_ARG, "theta_gram_dts: NULL argument or negative n");
+    B200I_REQUIRE(T >= 2 && T <= 1024, B200I_E_UNSUPPORTED, "theta_gram_dts: T=%d outside [2,1024]", T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StatsWorkspace *ws = static_cast<StatsWorkspace *>(gram_workspace);
+    B200I_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 128 + sizeof(unsigned int) * 32, st));
+    if (n == 0) return 0;
+    const size_t smem = (((size_t)GP * T * 9 + 15) & ~(size_t)15) + (size_t)(dts_per_row ? GP : 1) * (T - 1) * sizeof(double);
+    B200I_REQUIRE(smem <= 220 * 1024, B200I_E_UNSUPPORTED, "theta_gram_dts: T=%d needs %zu bytes of shared memory", T, smem);
+    auto kern = theta_gram_kernel<false>;
+    int per_sm = 1;
+    {
+        int rc0 = ensure_dyn_smem(reinterpret_cast<const void *>(kern), (int)smem, GP, &per_sm);
+        if (rc0) return rc0;
+    }
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (n + GP - 1) / GP;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > STATS_MAX_BLOCKS) grid = STATS_MAX_BLOCKS;
+    kern<<<(unsigned)grid, GP, smem, st>>>(n, T, 1.0, cancer_volume, chemo_application, radio_application, sequence_lengths,
+                                           static_feature, ws, dts, dts_per_row);
+    return check_cuda(cudaGetLastError(), "theta_gram_dts launch");
 }

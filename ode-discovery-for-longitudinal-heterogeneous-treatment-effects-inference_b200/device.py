@@ -282,6 +282,20 @@ def theta_gram(cancer_volume, chemo_application, radio_application, sequence_len
     return ws[:STATS_DOUBLES]
 
 
+def theta_gram_dts(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature, dts,
+                   tag="default"):
+    """K4 on an irregular time grid: dts (T-1,) or (N,T-1) interval lengths.  Returns the (68,) packed statistics
+    (Gram part; the dosage moments are not part of this call)."""
+    lib = _native.load()
+    n, T = cancer_volume.shape
+    ws = gram_workspace(tag)
+    dp, dper = _dts_args(dts, n, T - 1)
+    rc = lib.b200i_theta_gram_dts(n, T, _ptr(cancer_volume), _ptr(chemo_application), _ptr(radio_application),
+                                  _ptr(sequence_lengths), _ptr(static_feature), dp, dper, _ptr(ws), _stream())
+    _native.check(rc, "b200i_theta_gram_dts")
+    return ws[:STATS_DOUBLES]
+
+
 def stlsq_population(stats, threshold=1e-3, alpha=0.5, max_iter=100):
     """K5.  stats (68,) device -> (coefs (4,4) float64, support (4,4) int32), both on device."""
     lib = _native.load()
@@ -316,15 +330,37 @@ def treatment_codes(chemo_application, radio_application, W):
     return codes
 
 
+def _dts_args(dts, rows, W):
+    """(pointer, per_row flag) of an interval-length array: (W,) shared by all rows or (rows, W) per row."""
+    assert dts.is_cuda and dts.is_contiguous() and dts.dtype == torch.float64
+    if dts.dim() == 1:
+        assert dts.shape[0] == W, f"dts must hold {W} interval lengths, got {tuple(dts.shape)}"
+        return _ptr(dts), 0
+    assert tuple(dts.shape) == (rows, W), f"dts must be ({rows}, {W}), got {tuple(dts.shape)}"
+    return _ptr(dts), 1
+
+
+def intervals_from_times(t):
+    """Time grid(s) t (..., W+1) -> interval lengths (..., W) = diff(t) (what odeint computes first, pkpd/utils.py:86)."""
+    return (t[..., 1:] - t[..., :-1]).contiguous()
+
+
 def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS_FOR_DT, drop_below=1e-3, out=None,
-                fp32=False):
+                fp32=False, dts=None):
     """K6.  codes (R,W) uint8; coefs (4,4) or (R,4,4).  Returns (R,W) un-scaled predictions.
-    fp32: integrate in float32 (inputs / outputs stay float64)."""
+    fp32: integrate in float32 (inputs / outputs stay float64).
+    dts: interval lengths (W,) or (R,W) for an irregular time grid (then `dt` is ignored)."""
     lib = _native.load()
     rows, W = codes.shape
     per_row = 1 if coefs.dim() == 3 else 0
     if out is None:
         out = torch.empty((rows, W), dtype=torch.float64, device='cuda')
+    if dts is not None:
+        dp, dper = _dts_args(dts, rows, W)
+        rc = lib.b200i_ode_rollout_dts(rows, W, int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes), _ptr(coefs),
+                                       per_row, float(drop_below), dp, dper, 1 if fp32 else 0, _ptr(out), _stream())
+        _native.check(rc, "b200i_ode_rollout_dts")
+        return out
     fn = lib.b200i_ode_rollout_f32 if fp32 else lib.b200i_ode_rollout
     rc = fn(rows, W, float(dt), int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes),
             _ptr(coefs), per_row, float(drop_below), _ptr(out), _stream())
@@ -333,11 +369,21 @@ def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS
 
 
 def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10,
-                  fd_dt=STANDARD_DT):
-    """K5b.  x (R,W) float64, codes (R,W) uint8, fit_len (R,) int32 -> per-row coefficients (R,4,4)."""
+                  fd_dt=STANDARD_DT, dts=None):
+    """K5b.  x (R,W) float64 (or float32: FP32 storage, FP64 arithmetic), codes (R,W) uint8, fit_len (R,) int32 ->
+    per-row coefficients (R,4,4).  dts: interval lengths (W,) or (R,W) for an irregular time grid."""
     lib = _native.load()
     rows, W = x.shape
     out = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
+    if dts is not None or x.dtype == torch.float32:
+        dp, dper = (None, 0) if dts is None else _dts_args(dts, rows, W)
+        f32 = x.dtype == torch.float32
+        assert x.is_contiguous()
+        rc = lib.b200i_stlsq_batched_dts(rows, W, None if f32 else _ptr(x), _ptr(x) if f32 else None, _ptr(codes),
+                                         _ptr(fit_len), _ptr(static_feature), _ptr(prior), float(support_tol), float(lam),
+                                         float(threshold), int(max_iter), float(fd_dt), dp, dper, _ptr(out), _stream())
+        _native.check(rc, "b200i_stlsq_batched_dts")
+        return out
     rc = lib.b200i_stlsq_batched(rows, W, float(fd_dt), _ptr(x), _ptr(codes), _ptr(fit_len), _ptr(static_feature),
                                  _ptr(prior), float(support_tol), float(lam), float(threshold), int(max_iter),
                                  _ptr(out), _stream())
@@ -346,10 +392,22 @@ def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3,
 
 
 def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol=1e-12,
-                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT, joint=False):
-    """K7.  Returns (coefs (R,4,4) [joint: (R,11)], status (R,) int32, fval (R,2))."""
+                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT, joint=False, dts=None):
+    """K7.  Returns (coefs (R,4,4) [joint: (R,11)], status (R,) int32, fval (R,2)).
+    dts: interval lengths (W,) or (R,W) for an irregular time grid (per-treatment models)."""
     lib = _native.load()
     rows, W = x.shape
+    if dts is not None:
+        assert not joint, "irregular grids are implemented for the per-treatment models"
+        dp, dper = _dts_args(dts, rows, W)
+        coefs = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
+        status = torch.empty((rows,), dtype=torch.int32, device='cuda')
+        fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
+        rc = lib.b200i_insite_bfgs_dts(rows, W, int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
+                                       int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
+                                       int(max_iter), dp, dper, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+        _native.check(rc, "b200i_insite_bfgs_dts")
+        return coefs, status, fval
     if joint:
         coefs = torch.empty((rows, 11), dtype=torch.float64, device='cuda')
         status = torch.empty((rows,), dtype=torch.int32, device='cuda')

@@ -289,16 +289,39 @@ def equation_string(coefs, names=('1', 'x0', 'u0', 'x0*u0')):
 # ------------------------------------------------------------------------------------------------
 # rollout + metrics
 # ------------------------------------------------------------------------------------------------
-def rollout_unscaled(x0, codes, u, coefs, dt=STANDARD_DT, steps=STEPS_FOR_DT):
+def odeint_euler(func, y0, t, *args, hmax=np.inf, steps=STEPS_FOR_DT):
+    """odeint of the reference (pkpd/utils.py:68-90) for an arbitrary time grid t: dts = diff(t); when hmax < dts[0]
+    every interval is split into `steps` Euler sub-steps of dts[k] / steps (odeint_high_resolution_euler), else one
+    Euler step per interval; y <- y + func(y, h, *args) * h (scan_func).  Returns y at every grid point."""
+    t = np.asarray(t, dtype=np.float64)
+    dts = np.diff(t)
+    y = np.asarray(y0, dtype=np.float64)
+    out = [y]
+    fine = hmax < dts[0]
+    for d in dts:
+        if fine:
+            h = d / steps
+            for _ in range(steps):
+                y = y + func(y, h, *args) * h
+        else:
+            y = y + func(y, d, *args) * d
+        out.append(y)
+    return np.stack(out, axis=0)
+
+
+def rollout_unscaled(x0, codes, u, coefs, dt=STANDARD_DT, steps=STEPS_FOR_DT, dts=None):
     """sindy.py:413-431 / :767-778 with pkpd/utils.py:68-90: open loop, 5 Euler sub-steps per
     interval.  x0 (R,), codes (R,W) int treatment index (argmax of the one-hot), u (R,),
-    coefs (4,4) or per-row (R,4,4).  Returns (R,W)."""
+    coefs (4,4) or per-row (R,4,4).  Returns (R,W).
+    dts: interval lengths (W,) or (R,W) of an irregular grid: interval k is integrated as odeint over [0, dts[k]]."""
     R, W = codes.shape
     v = x0.astype(np.float64).copy()
     out = np.empty((R, W))
     h = dt / steps
     rows = np.arange(R)
     for k in range(W):
+        if dts is not None:
+            h = (dts[k] if np.ndim(dts) == 1 else dts[:, k]) / steps
         c = coefs[codes[:, k]] if coefs.ndim == 2 else coefs[rows, codes[:, k]]
         for _ in range(steps):
             v = v + (c[:, 0] * 1 + c[:, 1] * v + c[:, 2] * u + c[:, 3] * (v * u)) * h
@@ -360,7 +383,7 @@ def n_step_rmses(pred_seq_scaled, data_seq, scaling, norm_const=TUMOUR_DEATH_THR
 # individualisation (INSITE)
 # ------------------------------------------------------------------------------------------------
 def insite_objective(theta_flat, x, codes, u, n_fit, theta0_flat, lam, norm, dt=STANDARD_DT, steps=STEPS_FOR_DT,
-                     with_grad=True):
+                     with_grad=True, dts=None):
     """f_to_min_func (sindy.py:781-794) for one row + its gradient by forward sensitivities.
     x: un-scaled prev_outputs (W,), codes (W,) treatment index, n_fit = sequence_length - projection_horizon."""
     theta = np.asarray(theta_flat, dtype=np.float64).reshape(4, 4)
@@ -375,6 +398,8 @@ def insite_objective(theta_flat, x, codes, u, n_fit, theta0_flat, lam, norm, dt=
     for k in range(int(n_fit)):
         a = int(codes[k])
         c0, c1, c2, c3 = c[a]
+        if dts is not None:
+            h = dts[k] / steps
         for _ in range(steps):
             vu = v * u
             f = ((c0 + c1 * v) + c2 * u) + c3 * vu
@@ -466,7 +491,8 @@ def insite_bfgs_row(x, codes, u, seq_len, ph, theta0, lam, gtol=1e-12, maxiter=3
     return th.reshape(4, 4), f0, min(res.fun, f0)
 
 
-def ridge_prior_row(x, codes, u, n_fit, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10, dt=STANDARD_DT):
+def ridge_prior_row(x, codes, u, n_fit, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10, dt=STANDARD_DT,
+                    dts=None):
     """Batched per-row estimator of the north star (K5b): per treatment, mean-normalised normal equations of
     the row's snippets, ridge shrunk to the population coefficients on the population support, thresholded."""
     prior = np.asarray(prior, dtype=np.float64).reshape(4, 4)
@@ -474,7 +500,7 @@ def ridge_prior_row(x, codes, u, n_fit, prior, lam, threshold=1e-3, support_tol=
     W = len(x)
     for k in range(int(n_fit)):
         a = int(codes[k]); a1 = int(codes[min(k + 1, W - 1)])
-        xd = (x[k + 1] - x[k]) / dt
+        xd = (x[k + 1] - x[k]) / (dt if dts is None else dts[k])
         pts = [x[k]] + ([x[k + 1]] if (k == n_fit - 1 or a1 != a) else [])
         for xv in pts:
             th = np.array([1.0, xv, u, xv * u])
@@ -498,3 +524,23 @@ def ridge_prior_row(x, codes, u, n_fit, prior, lam, threshold=1e-3, support_tol=
                 break
         out[a] = c
     return out
+
+
+def normal_equations_irregular(vol, chemo, radio, seq_len, static, dts):
+    """SURVEY.md App. B on an irregular grid: per treatment G = Theta^T Theta, b = Theta^T xdot, sample counts, with
+    xdot_k = (x[k+1] - x[k]) / dts[k] (pysindy FiniteDifference(order=1) on a time array: forward differences, the last
+    point of a snippet backward).  vol (N,T), dts (T-1,) or (N,T-1).  Explicit loops: small cohorts only."""
+    N, T = vol.shape
+    G = np.zeros((4, 4, 4)); b = np.zeros((4, 4)); cnt = np.zeros(4)
+    for i in range(N):
+        L = min(int(seq_len[i]), T - 1)
+        u = static[i]
+        a = (chemo[i] != 0).astype(int) + 2 * (radio[i] != 0).astype(int)
+        d = dts if np.ndim(dts) == 1 else dts[i]
+        for k in range(L):
+            xd = (vol[i, k + 1] - vol[i, k]) / d[k]
+            pts = [vol[i, k]] + ([vol[i, k + 1]] if (k == L - 1 or a[k + 1] != a[k]) else [])
+            for xv in pts:
+                th = np.array([1.0, xv, u, xv * u])
+                G[a[k]] += np.outer(th, th); b[a[k]] += th * xd; cnt[a[k]] += 1
+    return G, b, cnt

@@ -216,3 +216,30 @@ def test_windowed_oracle_equals_the_verbatim_restatement(kind):
     assert r0 > 0
     for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths'):
         assert np.array_equal(full[k][r0:], part[k], equal_nan=True), k
+
+
+def test_odeint_restatement_known_answers_of_the_reference():
+    """The reference's own in-file tests of odeint (pkpd/utils.py:759-780 dense grid, :807-828 two-point grid):
+    dy/dt = 1 from y0 = 0 gives y = t, MSE < 1e-16, with hmax = HMAX = STANDARD_DT / STEPS_FOR_DT."""
+    HMAX = sp.STANDARD_DT / sp.STEPS_FOR_DT
+    t = np.arange(0, 10.0, 10.0 / 60)
+    ones = lambda y, h: np.ones_like(y)
+    y = sp.odeint_euler(ones, np.array(0.0), t, hmax=HMAX)
+    assert y.shape == t.shape and np.mean((y - t) ** 2) < 1e-16
+    t2 = np.array([t[0], t[-1]])
+    y2 = sp.odeint_euler(ones, np.array(0.0), t2, hmax=HMAX)
+    assert np.mean((y2 - t2) ** 2) < 1e-16
+    # the rollout restatement on the same grids: coefficient row [1, 0, 0, 0] is dy/dt = 1
+    c = np.zeros((4, 4)); c[:, 0] = 1.0
+    codes = np.zeros((1, len(t) - 1), dtype=np.int64)
+    r = sp.rollout_unscaled(np.zeros(1), codes, np.ones(1), c, dts=np.diff(t))
+    assert np.mean((r[0] - t[1:]) ** 2) < 1e-16
+    # uniform interval lengths reproduce the uniform-dt code path bit for bit
+    rng = np.random.RandomState(0)
+    cc = rng.randn(4, 4) * 0.1
+    cd = rng.randint(0, 4, size=(5, 20))
+    x0 = rng.rand(5) * 100
+    u = rng.randint(1, 4, size=5).astype(float)
+    a = sp.rollout_unscaled(x0, cd, u, cc)
+    b = sp.rollout_unscaled(x0, cd, u, cc, dts=np.full(20, sp.STANDARD_DT))
+    assert np.array_equal(a, b)
