@@ -18,8 +18,14 @@ Keys of the JSON line beyond the contract:
                         the device generator inside the simulator kernel (K1L), chunked H2D overlapped with compute
   e2e_host_draws        the same through the pre-drawn-array contract (2 GB of draws per step over PCIe)
   device_rng            the generated-draws path with parameters resident (K1L -> K4 -> K5)
-  individualisation     per-patient STLSQ fits/s (K5b) and discovered-ODE rollout steps/s (K6): BASELINE's second metric
+  individualisation     config C4: per-patient STLSQ fits/s (K5b) and discovered-ODE rollout steps/s (K6), uniform and
+                        irregular sampling, FP64 vs FP32; INSITE BFGS fits/s (K7) with its status histogram
+  c3                    config C3: treatment-sequence (K3) and one-step (K2) counterfactual cohorts of the test patients in
+                        compact form, their evaluation tau = 1..5 (K9) / one-step (K8) with the population ODE and with one
+                        INSITE fit per (patient, t): kernel times, rooflines, the eight RMSEs
+  c5                    config C5: the 16M-patient sweep (16M / n_gpus patients per GPU, generated draws, Gram all-reduce)
   cpu_baseline          the oracle's C restatement on one host thread, bounded sample (N=1 only)
+`config` is the workload both arms share (the reference arm prints the same dict); `details` holds this arm's choices.
 """
 import argparse
 import json
@@ -206,12 +212,279 @@ def cpu_reference_arm(n_sample, T, threads, inputs=None, port_check_patients=100
     return steps / (t2 - t0), t2 - t0, detail
 
 
+LOGGED_COEFS = [[-0.05601456082026624, -0.11598756834077, -0.07958279124512227, 0.07326347275734027],
+                [-0.5517350343589641, -0.8761667536689084, -0.053397817822270766, -0.035996455669168224],
+                [-3.649800303098579, -0.8626472911638889, 1.1157911611997717, -0.6373790072514276],
+                [-1.6336216074116419, -3.49858670473956, -3.584018882175004, 0.06151172618047967]]
+
+
+def workload_config(n, world, T):
+    """The workload both arms run (BASELINE.json configs[1]); the reference arm prints the same dict."""
+    return {"workload": "cancer_sim factual + INSITE population fit, 1M patients x 60 steps per GPU (FP64)",
+            "patients_per_gpu": n, "patients_total": n * world, "seq_length": T, "gamma": 2.0,
+            "patient_steps": "executed = sum(sequence_length-1)"}
+
+
+def _median_ms(fn, reps=5, warm=1):
+    import numpy as np
+    import torch
+    out = None
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        out = None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), out
+
+
+def block_c4(gen, T, peak):
+    """Config C4 on the generated factual cohort of this rank: individualised per-patient fits and discovered-ODE
+    rollouts, uniform and irregular sampling, FP64 vs FP32."""
+    import numpy as np
+    import torch
+    from b200_insite import device as dev
+    n = gen.n
+    xv = gen.volume.contiguous()
+    cd = gen.codes[:, :T].contiguous()
+    fit_len = gen.sequence_lengths.to(torch.int32)
+    prior = gen.coefs.contiguous()
+    x32 = xv.to(torch.float32).contiguous()
+    out = {"what": "per-patient ridge-to-prior STLSQ fits (K5b, 16 coefficients per patient) on the generated cohort and "
+                   "59-step discovered-ODE rollouts with the per-patient coefficients (K6, 5 Euler sub-steps per interval)",
+           "patients": n}
+    x0 = xv[:, 0].contiguous(); cd1 = cd[:, :T - 1].contiguous()
+    g = torch.Generator(device='cuda'); g.manual_seed(11)
+    grids = {"uniform": None,
+             "irregular": dev.STANDARD_DT * (0.3 + 2.2 * torch.rand((n, T), generator=g, device='cuda', dtype=torch.float64))}
+    for name, dts in grids.items():
+        d1 = None if dts is None else dts[:, :T - 1].contiguous()
+        ms_fit, pc = _median_ms(lambda: dev.stlsq_batched(xv, cd, fit_len, gen.static, prior, 1e4, dts=dts))
+        ms_fit32, pc32 = _median_ms(lambda: dev.stlsq_batched(x32, cd, fit_len, gen.static, prior, 1e4, dts=dts))
+        pred = torch.empty((n, T - 1), dtype=torch.float64, device='cuda')
+        pred32 = torch.empty_like(pred)
+        ms_roll, _ = _median_ms(lambda: dev.ode_rollout(x0, gen.static, cd1, pc, drop_below=-1.0, dts=d1, out=pred))
+        ms_roll32, _ = _median_ms(lambda: dev.ode_rollout(x0, gen.static, cd1, pc, drop_below=-1.0, dts=d1, out=pred32, fp32=True))
+        scale = pc.abs().amax(dim=(1, 2), keepdim=True)
+        fit_bytes = n * (T * 8 + T + 4 + 8 + 128 + (0 if dts is None else T * 8))
+        roll_bytes = n * (128 + 16 + (T - 1) + (T - 1) * 8 + (0 if dts is None else (T - 1) * 8))
+        out[name] = {
+            "fits_per_s": n / (ms_fit / 1e3), "fit_ms": ms_fit,
+            "fits_per_s_f32_storage": n / (ms_fit32 / 1e3), "fit_f32_storage_ms": ms_fit32,
+            "fit_f32_max_rel_dev_vs_f64": float(((pc32 - pc).abs() / scale).max().item()),
+            "fit_roofline": {"bound": "fp64 issue / latency (4 Cholesky solves per row)", "bytes_per_launch": fit_bytes,
+                             "achieved": fit_bytes / (ms_fit / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": fit_bytes / (ms_fit / 1e3) / 1e9 / peak, "ncu": "profiles/r2_k5b_stlsq_batched_ncu.txt"},
+            "rollout_patient_steps_per_s": n * (T - 1) / (ms_roll / 1e3), "rollout_ms": ms_roll,
+            "rollout_f32_ms": ms_roll32,
+            "rollout_f32_max_rel_dev_vs_f64": float(((pred32 - pred).abs() / pred.abs().clamp_min(1e-3 * float(pred.abs().max()))).max().item()),
+            "rollout_roofline": {"bound": "fp64 pipe (2360 FP64 operations per row in the reference's evaluation order)",
+                                 "bytes_per_launch": roll_bytes, "achieved": roll_bytes / (ms_roll / 1e3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": roll_bytes / (ms_roll / 1e3) / 1e9 / peak,
+                                 "ncu": "profiles/r2_k6_ode_rollout_ncu.txt"}}
+        del pc, pc32, pred, pred32
+    nb = min(n, 100_000)
+    sub = lambda a: a[:nb].contiguous()
+    ms7, (c7, status, fval) = _median_ms(lambda: dev.insite_bfgs(sub(xv), sub(cd), sub(fit_len), 1, sub(gen.static), prior, 10.0),
+                                         reps=2)
+    stn = status.cpu().numpy().astype(np.int64)
+    out["insite_bfgs"] = {"kernel": "insite_bfgs_kernel (K7, 16 lanes per row, BFGS over 16 coefficients, FP64)", "rows": nb,
+                          "ms": ms7, "fits_per_s": nb / (ms7 / 1e3),
+                          "status_hist": {"converged": int(((stn & 255) == 0).sum()), "max_iter": int(((stn & 255) == 1).sum()),
+                                          "zoom_failed": int(((stn & 255) == 3).sum()),
+                                          "line_search_maxiter": int(((stn & 255) == 5).sum()),
+                                          "kept_theta0": int(((stn & 255) == 6).sum()) + int(((stn & 255) == 4).sum()),
+                                          "skipped": int((stn < 0).sum())},
+                          "mean_iterations": float((stn[stn >= 0] >> 8).mean()),
+                          "bound": "FP64 ALU / dependent-issue latency (16 forward sensitivities per Euler sub-step)",
+                          "ncu": "profiles/r2_k7_insite_bfgs_ncu.txt"}
+    return out
+
+
+def block_c3(params, block_dev, static_dev, n, T, H, rank, world, peak, insite_patients):
+    """Config C3: counterfactual cohorts of this rank's patients in compact form + their evaluation.
+    world > 1: the cohort is n * world patients; every rank simulates the global source prefix itself and then its own
+    shard in one launch (counterfactual.sim_cf_shard), evaluates it, and the error sums are all-reduced."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from b200_insite import device as dev
+    from b200_insite import counterfactual as cfm
+    from b200_insite import compact_eval as ce
+    coefs = dev.to_device(np.array(LOGGED_COEFS))
+    n_total = n * world
+    out = {"what": "test-patient counterfactual cohorts in compact per-patient form (the reference's dense layout would be "
+                   f"{n_total * 562 * 65 * 8 * 3 / 1e12:.2f} TB): K3 treatment sequences tau=1..{H} / K2 one-step, draws from "
+                   "the device generator keyed by the global patient index; evaluation with the population ODE of the "
+                   "reference's log line (K9 / K8) and with one INSITE fit per (patient, t)",
+           "patients_total": n_total, "patients_per_gpu": n}
+    prefix_blocks = None
+    if world > 1:
+        # parameters of the global source prefix = the first patients of rank 0
+        P = min(n, max(64, n_total // 150))
+        pre = block_dev[:, :P].contiguous()
+        dist.broadcast(pre, src=0)
+        prefix_blocks = (pre, P)
+
+    def make_generator(kind):
+        """Draws (device generator, keyed by the global patient index) are made once; the returned callable is the timed
+        part: K3 / K2 over this rank's patients (world > 1: source prefix + shard)."""
+        extra = H if kind == 'seq' else 0
+        dr = cfm.generated_draws(n, T, extra, seed=77, patient_base=rank * n)
+        if world == 1:
+            if kind == 'seq':
+                return lambda: cfm.sim_cf_treatment_seq(block_dev, *dr, T, H)
+            return lambda: cfm.sim_cf_one_step(block_dev, *dr, T)
+        pre, P = prefix_blocks
+        pdr = cfm.generated_draws(P, T, extra, seed=77, patient_base=0)
+        return lambda: cfm.sim_cf_shard('treatment_seq' if kind == 'seq' else 'one_step', T, H, n_total, rank * n,
+                                        (block_dev,) + tuple(dr), (pre,) + tuple(pdr))[0]
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    for kind in ('seq', 'one'):
+        ms_gen, coh = _median_ms(make_generator(kind), reps=3)
+        ms_gen = allmax(ms_gen)
+        rows = allsum(int(coh.total_rows) if world == 1 else int(coh.n_rows.sum().item()))
+        steps = allsum(float(coh.n_steps.double().sum().item()))
+        W = T - 1
+        if kind == 'seq':
+            wbytes = n * (W * 2 * H * H * 8 + T * 9 + W * 2 + 16)
+            rbytes = n * ((T + H + 3 * T) * 8 + 80)
+            ebytes = n * (W * 2 * H * H * 8 + T + W * 2 + 8 + 12)
+            name, ename = "cf_seq_factual_kernel + cf_seq_project_kernel (K3)", "cf_eval_seq_kernel (K9)"
+            prof, eprof = "profiles/r2_k3_treatment_seq_ncu.txt", "profiles/r2_k9_cf_eval_seq_ncu.txt"
+        else:
+            wbytes = n * (W * 4 * 8 + T * 9 + 16)
+            rbytes = n * (4 * T * 8 + 80)
+            ebytes = n * (W * 4 * 8 + T * 9 + 12)
+            name, ename = "cf_one_step_kernel (K2)", "cf_eval_one_step_kernel (K8)"
+            prof, eprof = "profiles/r2_k2_one_step_ncu.txt", "profiles/r2_k8_cf_eval_one_step_ncu.txt"
+        ms_ev, sums = _median_ms(lambda: ce.evaluate(coh, static_dev, coefs, 1e-3))
+        ms_ev = allmax(ms_ev)
+        from b200_insite.cohort import allreduce_stats
+        allreduce_stats(sums)
+        sm = sums.cpu().numpy()
+        blk = {"generator": {"kernel": name, "ms": ms_gen, "reference_rows": rows, "rows_per_s": rows / (ms_gen / 1e3),
+                             "rollout_steps_per_s": (steps + (H if kind == 'seq' else 1) * rows) / (ms_gen / 1e3),
+                             "levels": int(coh.levels),
+                             "roofline": {"bound": "hbm (writes) / fp64 log", "bytes_written_per_launch": wbytes,
+                                          "bytes_read_per_launch": rbytes,
+                                          "achieved": (wbytes + rbytes) * world / (ms_gen / 1e3) / 1e9, "peak": peak * world,
+                                          "unit": "GB/s", "frac": (wbytes + rbytes) / (ms_gen / 1e3) / 1e9 / peak, "ncu": prof}},
+               "evaluation_population": {"kernel": ename, "ms": ms_ev, "rows_per_s": rows / (ms_ev / 1e3),
+                                         "roofline": {"bound": "hbm", "bytes_read_per_launch": ebytes,
+                                                      "achieved": ebytes * world / (ms_ev / 1e3) / 1e9, "peak": peak * world,
+                                                      "unit": "GB/s", "frac": ebytes / (ms_ev / 1e3) / 1e9 / peak, "ncu": eprof}}}
+        if kind == 'seq':
+            blk["rmse_tau_1_to_H_percent"] = [float(v) for v in ce.n_step_rmses(sm, H, dev.TUMOUR_DEATH_THRESHOLD)]
+        else:
+            o, a, l = ce.one_step_rmses(sm, W, dev.TUMOUR_DEATH_THRESHOLD)
+            blk["rmse_orig_all_last_percent"] = [float(o), float(a), float(l)]
+        # INSITE: one BFGS fit per (patient, t) (lam = 10), then the same evaluation with the per-step coefficients
+        ni = min(n, insite_patients)
+        if ni > 0:
+            sub = cfm.CompactCohort(coh.kind, ni, T, coh.H, coh.factual[:ni].contiguous(), coh.codes[:ni].contiguous(),
+                                    coh.cf[:ni].contiguous(), None if coh.valid is None else coh.valid[:ni].contiguous(),
+                                    coh.n_steps[:ni].contiguous(), coh.n_rows[:ni].contiguous(), None, 0, 0)
+            st_sub = static_dev[:ni].contiguous()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pc, diag = ce.individualise(sub, st_sub, coefs, estimator='bfgs_rollout', lam=10.0)
+            a1.record()
+            ms_e2, s2 = _median_ms(lambda: ce.evaluate(sub, st_sub, pc, -1.0), reps=3)
+            ms_fit = allmax(a0.elapsed_time(a1))
+            allreduce_stats(s2)
+            s2 = s2.cpu().numpy()
+            stn = diag['status'].cpu().numpy().astype(np.int64)
+            fits = allsum(int((stn >= 0).sum()))
+            ins = {"patients_per_gpu": ni, "fits": fits, "fit_ms": ms_fit, "fits_per_s": fits / (ms_fit / 1e3),
+                   "reference_rows_covered": allsum(int(sub.n_rows.sum().item())), "evaluation_ms": allmax(ms_e2),
+                   "line_search_exhausted_frac": float(((stn[stn >= 0] & 255) == 3).mean()) if (stn >= 0).any() else 0.0}
+            if kind == 'seq':
+                ins["rmse_tau_1_to_H_percent"] = [float(v) for v in ce.n_step_rmses(s2, H, dev.TUMOUR_DEATH_THRESHOLD)]
+            else:
+                o, a, l = ce.one_step_rmses(s2, W, dev.TUMOUR_DEATH_THRESHOLD)
+                ins["rmse_orig_all_last_percent"] = [float(o), float(a), float(l)]
+            blk["insite"] = ins
+            del pc, diag, sub
+        out["treatment_seq" if kind == 'seq' else "one_step"] = blk
+        del coh
+        torch.cuda.empty_cache()
+    return out
+
+
+def block_c5(T, rank, world, total=16_000_000):
+    """Config C5: the 16M-patient sweep, 16M / world patients per GPU: generated draws (K1L), lean fit, all-reduce of
+    the 68 statistics, STLSQ.  Strong scaling over the GPU counts of the scaling run."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import b200_insite.cancer_simulation as cs
+    from b200_insite import device as dev
+    from b200_insite.cohort import GeneratedFitPipeline
+    n = total // world
+    gen = GeneratedFitPipeline(n, T, seed=4321, patient_base=rank * n, chunks=8)
+    np.random.seed(100 + rank)
+    m = min(n, 1_000_000)                       # parameters: 1M generated on the host, tiled to the shard size
+    p = cs.generate_params(m, 2.0, 2.0, 15, 0)
+    blk = torch.from_numpy(dev.pack_params(p)).cuda()
+    st = torch.from_numpy(np.asarray(p['patient_types'], dtype=np.float64)).cuda()
+    reps = -(-n // m)
+    gen.params.copy_(blk.repeat(1, reps)[:, :n]); gen.static.copy_(st.repeat(reps)[:n])
+    del blk, st
+    for _ in range(2):
+        gen.step_device()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 5
+    a.record()
+    for _ in range(k):
+        gen.step_device()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / k
+    t = torch.tensor([ms, gen.executed_steps()], dtype=torch.float64, device='cuda')
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, steps = float(tm[0]), float(ts[1])
+    else:
+        steps = float(t[1])
+    out = {"what": "16M-patient sweep (BASELINE configs[4]): patients sharded over the GPUs, draws generated in the simulator "
+                   "kernel (K1L), lean fit, one all-reduce of 68 doubles, STLSQ; parameters resident",
+           "patients_total": n * world, "patients_per_gpu": n, "ms_per_step": ms, "value": steps / (ms / 1e3),
+           "unit": UNIT, "scaling": "strong (fixed 16M patients)", "population_coefs": gen.coefs.cpu().numpy().tolist()}
+    del gen
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = args.ref_patients
+    n_sample = args.ref_patients or args.patients
     vals, detail = [], None
     inputs = cpu_inputs(n_sample, args.seq_length)
     for i in range(args.warmup + args.steps):
@@ -226,8 +499,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cancer_sim factual + INSITE population fit (CPU sample)", "patients": n_sample,
-                       "seq_length": args.seq_length, "gamma": 2.0},
+            "config": workload_config(args.patients, args.gpus, args.seq_length),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "detail": detail},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -377,16 +649,20 @@ def run_b200(args):
     torch.cuda.synchronize()
     k1l_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     gen_exec = gen.executed_steps()
-    # the reference's generate_params builds K and its four sigmoid rows from scalars (cancer_simulation.py:83-88, :202): found
-    # once per cohort (not per step), those rows are filled on the device instead of crossing PCIe
-    uniform = dev.uniform_param_rows(params) if args.uniform_rows else {}
+    # End to end on the reduced input set: what get_standard_params draws per patient (initial volume, alpha, rho, beta_c,
+    # patient type byte) crosses PCIe; beta = alpha / 10, K and the four sigmoid rows are rebuilt on the device from
+    # generate_params' own arguments (cancer_simulation.py:83-88, :185, :202) -- nothing is found by scanning the arrays.
+    uniform = dev.cohort_scalar_rows(2.0, 2.0) if args.uniform_rows else {}
+    h_types = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.uint8)).pin_memory() if args.uniform_rows else None
+    if args.uniform_rows:     # outside the timed region: the inputs really are what the reduced contract assumes
+        assert np.array_equal(params['beta'], params['alpha'] / 10) and dev.uniform_param_rows(params) == uniform
     for _ in range(max(1, min(args.warmup, 3))):
-        gen.step_host(h_block, h_static, h_result, uniform=uniform)
+        gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types)
     barrier()
     gen_e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(gen_e2e_steps):
-        gen.step_host(h_block, h_static, h_result, uniform=uniform)
+        gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types)
     barrier()
     gen_e2e_ms = 1e3 * (time.perf_counter() - t0) / gen_e2e_steps
     clocks.stop.set(); clocks.t.join(timeout=6)
@@ -400,76 +676,80 @@ def run_b200(args):
         gen_exec_all = gen_exec
     gen_ms, gen_e2e_ms = float(tg[0]), float(tg[1])
 
-    # ---- second half of BASELINE's metric: individualised per-patient fits and discovered-ODE rollouts (config C4) ----
-    indiv = None
-    if rank == 0:
-        def med(fn, reps=5):
-            out_ = fn(); torch.cuda.synchronize()
-            ts = []
-            for _ in range(reps):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); out_ = fn(); b.record(); torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            return float(np.median(ts)), out_
-        xv = gen.volume.contiguous()
-        cd = gen.codes[:, :T].contiguous()
-        fit_len = gen.sequence_lengths.to(torch.int32)
-        prior = gen.coefs.contiguous()
-        ms_fit, pc = med(lambda: dev.stlsq_batched(xv, cd, fit_len, gen.static, prior, 10.0))
-        x0 = xv[:, 0].contiguous(); cd1 = cd[:, :T - 1].contiguous()
-        ms_roll, pred = med(lambda: dev.ode_rollout(x0, gen.static, cd1, pc))
-        ms_roll32, pred32 = med(lambda: dev.ode_rollout(x0, gen.static, cd1, pc, fp32=True))
-        dev32 = float(((pred32 - pred).abs() / pred.abs().clamp_min(1e-3 * float(pred.abs().max()))).max().item())
-        indiv = {"what": "per-patient ridge-to-prior STLSQ fits (K5b, 16 coefficients per patient, FP64) on the generated "
-                         "cohort and 59-step discovered-ODE rollouts with the per-patient coefficients (K6)",
-                 "fits_per_s": n / (ms_fit / 1e3), "fit_ms": ms_fit,
-                 "rollout_patient_steps_per_s": n * (T - 1) / (ms_roll / 1e3), "rollout_ms": ms_roll,
-                 "rollout_f32_ms": ms_roll32, "rollout_f32_max_rel_dev_vs_f64": dev32}
-        del xv, cd, pc, pred, pred32
+    # ---- the other BASELINE configurations (each block is guarded: a failure there must not cost the headline line) ----
+    peak_hbm, _ = measured_peak_hbm()
+    indiv = c3 = c5 = None
+    if rank == 0 and not args.skip_c4:
+        try:
+            indiv = block_c4(gen, T, peak_hbm)
+        except Exception as e:      # noqa: BLE001
+            indiv = {"error": repr(e)}
+    gen_h2d = gen.h2d_bytes(uniform, reduced=h_types is not None)
+    gen_chunks = len(gen.bounds)
+    launches = pipe.launches_per_step * args.steps
+    lean_fit = bool(pipe.lean_fit)
+    pipe_h2d = pipe.h2d_bytes()
+    del gen, pipe
+    torch.cuda.empty_cache()
+    if not args.skip_c3:
+        try:
+            c3 = block_c3(params, block.cuda(), static.cuda(), n, T, 5, rank, world, peak_hbm, args.insite_patients)
+        except Exception as e:      # noqa: BLE001
+            c3 = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    if not args.skip_c5:
+        try:
+            c5 = block_c5(T, rank, world)
+        except Exception as e:      # noqa: BLE001
+            c5 = {"error": repr(e)}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         k1 = float(np.mean(k1_ms))
-        k1_name = (K1_SIDE_KERNELS if pipe.lean_fit else K1_KERNELS)[args.layout]
+        k1_name = (K1_SIDE_KERNELS if lean_fit else K1_KERNELS)[args.layout]
         # algorithmic bytes stay the reference I/O contract's; the lean fit's side outputs (112 B/patient) are extra
         achieved = K1_BYTES_PER_PATIENT(T) * n / (k1 / 1e3) / 1e9
         k4 = float(np.mean(k4_ms))
-        # algorithmic bytes = SURVEY.md 8(d)'s per-patient figure for the Gram reduction (volume + the two application
-        # arrays + sequence length + patient type = 1456 B at T=60); the lean launch actually reads less than that
-        k4_bytes = K4_BYTES_PER_PATIENT(T) * n
-        k4_read = (K4_LEAN_BYTES_PER_PATIENT(T) if pipe.lean_fit else (5 * T * 8 + 16)) * n
-        achieved4 = k4_bytes / (k4 / 1e3) / 1e9
+        # K4 is scored on the bytes the launch reads (volume row, code bytes, sequence length, type, six moment sums);
+        # SURVEY.md 8(d)'s three-array accounting (1456 B/patient) is kept beside it for comparison only
+        k4_read = (K4_LEAN_BYTES_PER_PATIENT(T) if lean_fit else (5 * T * 8 + 16)) * n
+        k4_survey = K4_BYTES_PER_PATIENT(T) * n
+        achieved4 = k4_read / (k4 / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cancer_sim factual + INSITE population fit, 1M patients x 60 steps per GPU (FP64)",
-                           "patients_per_gpu": n, "patients_total": n * world, "seq_length": T, "gamma": 2.0,
-                           "patient_steps": "executed = sum(sequence_length-1)",
-                           "nominal_patient_steps_per_s": n * world * (T - 1) / (ms_per_step / 1e3),
-                           "cache": "inputs (1.9 GB draws) and outputs (4.3 GB) per step exceed the 126 MB L2",
-                           "sim_variant": args.variant, "fused_gram": bool(args.fused), "lean_fit": bool(pipe.lean_fit),
-                           "layout": (f"(N,{T}) float64 arrays with a row pitch of {pitch} elements ({pitch * 8}-byte rows: "
-                                      f"every row starts on a 128-byte line); dense rows are measured beside it in "
-                                      f"roofline.dense_rows") if pitch != T else f"dense (N,{T}) float64 rows",
-                           "noise": "pre-drawn arrays resident in HBM (reference I/O contract)",
-                           "parallelism": f"patients sharded over {world} GPU(s); allreduce of 68 doubles",
-                           "host_affinity": (f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus
-                                             else "default")},
+                "config": workload_config(n, world, T),
+                "details": {"nominal_patient_steps_per_s": n * world * (T - 1) / (ms_per_step / 1e3),
+                            "cache": "inputs (1.9 GB draws) and outputs (4.3 GB) per step exceed the 126 MB L2",
+                            "sim_variant": args.variant, "fused_gram": bool(args.fused), "lean_fit": lean_fit,
+                            "layout": (f"(N,{T}) float64 arrays with a row pitch of {pitch} elements ({pitch * 8}-byte rows: "
+                                       f"every row starts on a 128-byte line); dense rows are measured beside it in "
+                                       f"roofline.dense_rows") if pitch != T else f"dense (N,{T}) float64 rows",
+                            "noise": "pre-drawn arrays resident in HBM (reference I/O contract)",
+                            "parallelism": f"patients sharded over {world} GPU(s); allreduce of 68 doubles",
+                            "host_cores": os.cpu_count(),
+                            "host_affinity": (f"rank 0 bound to the {len(numa_cpus)} cores local to its GPU" if numa_cpus
+                                              else "default")},
                 "clocks": clocks.summary(),
-                "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen.h2d_bytes(uniform),
-                        "uniform_parameter_rows": sorted(uniform),
+                "e2e": {"value": gen_exec_all / (gen_e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gen_h2d,
+                        "h2d_bytes_per_patient": gen_h2d / n,
+                        "rows_rebuilt_on_device": sorted(uniform) + ([3] if h_types is not None else []),
                         "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": gen_e2e_ms,
-                        "what": "GeneratedFitPipeline.step_host: pinned host parameters (the inputs of the reference's "
-                                "simulate_factual call, which draws its random numbers itself; rows that are one scalar "
-                                "for the cohort -- generate_params' K and four sigmoid rows -- are filled on the device) -> H2D in "
-                                f"{len(gen.bounds)} chunks overlapped with K1L (simulator with the Philox4x32-10 draws "
-                                "generated in registers, bit-identical to K1 on the exported draws) -> theta_gram_codes "
-                                "-> STLSQ -> D2H coefficients/support/statistics"},
-                "e2e_host_draws": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(),
-                                   "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": float(te[0]),
-                                   "what": "FactualFitPipeline.step_host: pinned host params + the four pre-drawn (N,T) "
-                                           "arrays of the K1 contract -> H2D -> K1,K4,K5 -> D2H (PCIe-bound: 2 GB of "
-                                           "draws per step)"},
+                        "what": "GeneratedFitPipeline.step_host on the reduced input set: pinned host arrays of what "
+                                "get_standard_params draws per patient (initial volume, alpha, rho, beta_c as float64, the "
+                                "patient type as one byte) -> H2D in "
+                                f"{gen_chunks} chunks overlapped with K1L (simulator with the Philox4x32-10 draws generated in "
+                                "registers, bit-identical to K1 on the exported draws); beta = alpha / 10, K and the four "
+                                "sigmoid rows are rebuilt on the device from generate_params' arguments -> theta_gram_codes "
+                                "-> [all-reduce] -> STLSQ -> D2H coefficients/support/statistics.  The cohort is the "
+                                "reference's statistically, not bitwise (device generator instead of numpy's sequential "
+                                "stream); the bitwise reference contract is e2e_reference_contract"},
+                "e2e_reference_contract": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe_h2d,
+                                           "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": float(te[0]),
+                                           "what": "FactualFitPipeline.step_host: pinned host params + the four pre-drawn "
+                                                   "(N,T) arrays of the K1 contract (the reference's numpy draws) -> H2D -> "
+                                                   "K1,K4,K5 -> D2H (PCIe-bound: 2 GB of draws per step)"},
                 "device_rng": {"value": gen_exec_all / (gen_ms / 1e3), "unit": UNIT, "ms_per_step": gen_ms,
                                "kernel": K1L_KERNEL, "kernel_ms": k1l_ms,
                                "bound": "FP64 dependent-issue latency / instruction issue (0.68 KB of HBM traffic per "
@@ -479,36 +759,43 @@ def run_b200(args):
                                "what": "GeneratedFitPipeline.step_device: parameters resident, draws generated in the "
                                        "simulator kernel, lean cohort (volume + code bytes + moments) -> fit",
                                "population_coefs": gen_coefs.tolist()},
-                "gpu_launches": pipe.launches_per_step * args.steps,
+                "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(k1_name),
                              "peak_source": peak_src, "kernel_ms": k1,
                              "algorithmic_bytes_per_launch": K1_BYTES_PER_PATIENT(T) * n,
                              "share_of_step": k1 / ms_per_step,
-                             "side_outputs_bytes_per_launch": K1_SIDE_BYTES_PER_PATIENT(T) * n if pipe.lean_fit else 0,
+                             "side_outputs_bytes_per_launch": K1_SIDE_BYTES_PER_PATIENT(T) * n if lean_fit else 0,
                              "dense_rows": None if k1_dense_ms is None else {
                                  "kernel_ms": k1_dense_ms,
                                  "achieved": K1_BYTES_PER_PATIENT(T) * n / (k1_dense_ms / 1e3) / 1e9,
                                  "frac": K1_BYTES_PER_PATIENT(T) * n / (k1_dense_ms / 1e3) / 1e9 / peak,
                                  "kernel": K1_KERNELS["dense"], "traffic": ncu_traffic(K1_KERNELS["dense"]),
                                  "note": "same arithmetic on the reference's dense 480-byte rows (bit-identical outputs)"}},
-                "roofline_theta_gram": {"bound": "hbm", "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
+                "roofline_theta_gram": {"bound": "fp64 pipe / latency (ncu: FP64 pipe 48 %, issue slots 58 %, "
+                                                 "profiles/r1_k4_theta_gram_codes_ncu.txt); HBM figures = bytes the launch reads",
+                                        "kernel": K4_KERNEL, "achieved": achieved4, "peak": peak,
                                         "unit": "GB/s", "frac": achieved4 / peak, "traffic": ncu_traffic(K4_KERNEL),
-                                        "kernel_ms": k4, "algorithmic_bytes_per_launch": k4_bytes,
-                                        "bytes_read_per_launch": k4_read, "read_gbs": k4_read / (k4 / 1e3) / 1e9,
-                                        "note": ("lean fit: the simulator kernel also writes one treatment-code byte per "
-                                                 "step and six per-patient moment sums (68 MB + 48 MB per 1M patients, "
-                                                 "inside its own time above); this launch reads the volumes and those "
-                                                 "instead of five (N,T) arrays (SURVEY 8d counts 1456 B/patient for the "
-                                                 "three-array form)") if pipe.lean_fit else
-                                                "standalone theta_gram2: reads 5 arrays (Gram + moments)",
+                                        "kernel_ms": k4, "bytes_read_per_launch": k4_read,
+                                        "survey_8d_accounting": {"bytes_per_launch": k4_survey,
+                                                                 "gbs": k4_survey / (k4 / 1e3) / 1e9,
+                                                                 "frac": k4_survey / (k4 / 1e3) / 1e9 / peak,
+                                                                 "note": "three-array form (1456 B/patient) the lean launch does "
+                                                                         "not move; not a statement about this kernel"},
+                                        "fused_step": {"note": "K1 + K4 scored together with K1's bytes (SURVEY 8d rule for a "
+                                                               "fused fit)",
+                                                       "gbs": K1_BYTES_PER_PATIENT(T) * n / ((k1 + k4) / 1e3) / 1e9,
+                                                       "frac": K1_BYTES_PER_PATIENT(T) * n / ((k1 + k4) / 1e3) / 1e9 / peak},
                                         "share_of_step": k4 / ms_per_step},
                 "individualisation": indiv,
+                "c3": c3,
+                "c5": c5,
                 "population_coefs": coefs.tolist()}
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, detail = cpu_reference_arm(args.ref_patients, T, 1)
+            n_cpu = args.ref_patients or 400_000
+            v, sec, detail = cpu_reference_arm(n_cpu, T, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{args.ref_patients} patients x {T} steps: C restatement of "
+                                    "sample": f"{n_cpu} patients x {T} steps: C restatement of "
                                               f"simulate_factual + scaling moments + C normal equations + STLSQ, "
                                               f"1 thread ({sec:.1f} s)", "detail": detail}
         print(json.dumps(line), flush=True)
@@ -533,8 +820,15 @@ def main():
                     "instead of copying them (0 = copy all ten rows)")
     ap.add_argument("--layout", default="pitched", choices=["pitched", "dense"],
                     help="device-resident (N,T) arrays: rows padded to 128-byte lines, or the reference's dense rows")
-    ap.add_argument("--ref-patients", type=int, default=400_000, help="bounded CPU sample")
+    ap.add_argument("--ref-patients", type=int, default=0,
+                    help="bounded CPU sample; 0 = the workload's patients per GPU for --impl reference, 400k for the "
+                         "single-thread cpu_baseline leg of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-c3", action="store_true", help="skip the counterfactual-cohort block (config C3)")
+    ap.add_argument("--skip-c4", action="store_true", help="skip the individualisation block (config C4)")
+    ap.add_argument("--skip-c5", action="store_true", help="skip the 16M-patient sweep (config C5)")
+    ap.add_argument("--insite-patients", type=int, default=100_000,
+                    help="patients per GPU whose (patient, t) INSITE fits are run in the C3 block (118 fits per patient)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -210,6 +210,19 @@ B200I_API int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch,
                      double *sequence_lengths, double *patient_moments_out, int32_t chunks,
                      double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                      void *copy_stream, void *stream);
+/* The same from the REDUCED parameter set: what get_standard_params actually draws per patient (cancer_simulation.py:
+ * 96-215: initial volume, alpha, rho, beta_c and the patient type) crosses PCIe, everything generate_params derives from
+ * it is rebuilt on the device exactly as the reference builds it -- beta = alpha / 10 (:185, derive_beta != 0; the same
+ * IEEE division), the static feature = the patient type (one byte per patient: patient_types_host pinned uint8 (N,),
+ * patient_types_dev a device staging buffer of N bytes), and the cohort-wide scalar rows through uniform_mask.  With
+ * K and the four sigmoid rows uniform that is 33 instead of 88 bytes per patient. */
+B200I_API int b200i_upload_simulate_rng_reduced(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
+                     const double *params_host, uint32_t uniform_mask, const double *uniform_values_host,
+                     int32_t derive_beta, const uint8_t *patient_types_host, uint8_t *patient_types_dev,
+                     double *params, double *static_feature, uint64_t seed, int64_t patient_base,
+                     double *cancer_volume, uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
+                     double *patient_moments_out, int32_t chunks, double fd_dt, void *chunk_gram_workspaces,
+                     double *stats_out, void *copy_stream, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
                      const double *cancer_volume, const double *chemo_application,

@@ -191,7 +191,9 @@ class GeneratedFitPipeline:
         self.chunk_ws = dev.chunk_workspaces(self.chunks)
         self.launches_per_step = len(self.bounds) + 2               # K1L per chunk + theta_gram_codes + stlsq_population
 
-    def h2d_bytes(self, uniform=None):
+    def h2d_bytes(self, uniform=None, reduced=False):
+        if reduced:      # four drawn parameter rows + one patient-type byte
+            return (10 - len(uniform or {}) - 1) * self.n * 8 + self.n
         return (10 - len(uniform or {}) + 1) * self.n * 8
 
     def _simulate(self, rows=None):
@@ -211,17 +213,28 @@ class GeneratedFitPipeline:
         self._simulate()
         return self._fit()
 
-    def step_host(self, params_block, static, result_host, uniform=None):
+    def step_host(self, params_block, static, result_host, uniform=None, types_u8=None):
         """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.
+        types_u8: pinned uint8 (N,) patient types = the REDUCED input set (what get_standard_params draws: initial volume,
+        alpha, rho, beta_c, patient type); `static` is then ignored, beta = alpha / 10 and the static feature are rebuilt
+        on the device as generate_params builds them: 33 bytes per patient with the five scalar rows in `uniform`.
         uniform: {row: value} of parameter rows that are one scalar for the cohort (device.uniform_param_rows): they
         are filled on the device instead of being copied (88 -> 48 bytes per patient for the reference's cohorts).  The parameter
         rows of chunk c+1 are copied on a second stream while chunk c is being simulated and reduced to its share of
         the population statistics; the shares are summed in chunk order (bits depend on the chunk count only)."""
         main = torch.cuda.current_stream()
-        dev.upload_simulate_rng(params_block, static, self.params, self.static, self.T, self.seed, self.patient_base,
-                                self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
-                                self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats,
-                                uniform=uniform)
+        if types_u8 is not None:
+            if getattr(self, 'types_u8_dev', None) is None:
+                self.types_u8_dev = torch.empty((self.n,), dtype=torch.uint8, device='cuda')
+            dev.upload_simulate_rng(params_block, None, self.params, self.static, self.T, self.seed, self.patient_base,
+                                    self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
+                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats,
+                                    uniform=uniform, derive_beta=True, types_u8_host=types_u8, types_u8_dev=self.types_u8_dev)
+        else:
+            dev.upload_simulate_rng(params_block, static, self.params, self.static, self.T, self.seed, self.patient_base,
+                                    self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
+                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats,
+                                    uniform=uniform)
         allreduce_stats(self.stats)
         self.coefs, self.support = dev.stlsq_population(self.stats, self.threshold, self.alpha, self.max_iter)
         result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)

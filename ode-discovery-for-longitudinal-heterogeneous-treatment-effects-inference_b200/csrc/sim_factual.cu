@@ -702,6 +702,28 @@ fill_uniform_rows_kernel(double *__restrict__ params, int64_t n, uint32_t mask, 
     }
 }
 
+// rows of a chunk that are derived on the device instead of crossing PCIe: beta = alpha / 10 (get_standard_params,
+// cancer_simulation.py:185: the same IEEE division) and the static feature from the patient type byte
+__global__ void __launch_bounds__(256)
+derive_chunk_rows_kernel(double *__restrict__ params, int64_t n, int64_t a, int64_t count, int derive_beta,
+                         const uint8_t *__restrict__ types_u8, double *__restrict__ static_feature)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        if (derive_beta) params[3 * n + a + i] = __ddiv_rn(params[1 * n + a + i], 10.0);
+        if (types_u8) static_feature[a + i] = (double)types_u8[a + i];
+    }
+}
+
+static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                    const double *params_host, uint32_t uniform_mask,
+                                    const double *uniform_values_host, const double *static_host, double *params,
+                                    double *static_feature, uint64_t seed, int64_t patient_base,
+                                    double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
+                                    double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                                    double fd_dt, void *chunk_gram_workspaces, double *stats_out,
+                                    void *copy_stream, void *stream, int derive_beta, const uint8_t *types_u8_host,
+                                    uint8_t *types_u8_dev);
+
 extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
                                          const double *params_host, uint32_t uniform_mask,
                                          const double *uniform_values_host, const double *static_host, double *params,
@@ -710,6 +732,42 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
                                          double *sequence_lengths, double *patient_moments_out, int32_t chunks,
                                          double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                                          void *copy_stream, void *stream)
+{
+    return upload_simulate_rng_impl(n, T, row_pitch, k, params_host, uniform_mask, uniform_values_host, static_host, params,
+                                    static_feature, seed, patient_base, cancer_volume, codes_out, code_pitch,
+                                    sequence_lengths, patient_moments_out, chunks, fd_dt, chunk_gram_workspaces, stats_out,
+                                    copy_stream, stream, 0, nullptr, nullptr);
+}
+
+extern "C" int b200i_upload_simulate_rng_reduced(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                                 const double *params_host, uint32_t uniform_mask,
+                                                 const double *uniform_values_host, int32_t derive_beta,
+                                                 const uint8_t *patient_types_host, uint8_t *patient_types_dev,
+                                                 double *params, double *static_feature, uint64_t seed,
+                                                 int64_t patient_base, double *cancer_volume, uint8_t *codes_out,
+                                                 int64_t code_pitch, double *sequence_lengths, double *patient_moments_out,
+                                                 int32_t chunks, double fd_dt, void *chunk_gram_workspaces,
+                                                 double *stats_out, void *copy_stream, void *stream)
+{
+    B200I_REQUIRE(patient_types_host && patient_types_dev && static_feature, B200I_E_ARG,
+                  "upload_simulate_rng_reduced: patient_types_host / patient_types_dev / static_feature is NULL");
+    B200I_REQUIRE(!derive_beta || !((uniform_mask >> 3) & 1u), B200I_E_ARG,
+                  "upload_simulate_rng_reduced: beta cannot be both derived and uniform");
+    return upload_simulate_rng_impl(n, T, row_pitch, k, params_host, uniform_mask, uniform_values_host, nullptr, params,
+                                    static_feature, seed, patient_base, cancer_volume, codes_out, code_pitch,
+                                    sequence_lengths, patient_moments_out, chunks, fd_dt, chunk_gram_workspaces, stats_out,
+                                    copy_stream, stream, derive_beta ? 1 : 0, patient_types_host, patient_types_dev);
+}
+
+static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                    const double *params_host, uint32_t uniform_mask,
+                                    const double *uniform_values_host, const double *static_host, double *params,
+                                    double *static_feature, uint64_t seed, int64_t patient_base,
+                                    double *cancer_volume, uint8_t *codes_out, int64_t code_pitch,
+                                    double *sequence_lengths, double *patient_moments_out, int32_t chunks,
+                                    double fd_dt, void *chunk_gram_workspaces, double *stats_out,
+                                    void *copy_stream, void *stream, int derive_beta, const uint8_t *types_u8_host,
+                                    uint8_t *types_u8_dev)
 {
     const bool fit = chunk_gram_workspaces != nullptr;
     B200I_REQUIRE(!fit || (stats_out && static_feature && codes_out && patient_moments_out && fd_dt > 0), B200I_E_ARG,
@@ -720,7 +778,7 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
     if (n == 0) return 0;
     B200I_REQUIRE(params_host && params && copy_stream && copy_stream != stream, B200I_E_ARG,
                   "upload_simulate_rng: NULL argument, or copy_stream == stream (no overlap possible)");
-    B200I_REQUIRE((static_host == nullptr) == (static_feature == nullptr), B200I_E_ARG,
+    B200I_REQUIRE(types_u8_host != nullptr || (static_host == nullptr) == (static_feature == nullptr), B200I_E_ARG,
                   "upload_simulate_rng: static_host and static_feature must both be given or both be NULL");
     B200I_REQUIRE(uniform_mask < (1u << B200I_NUM_PARAMS) && (uniform_mask == 0 || uniform_values_host), B200I_E_ARG,
                   "upload_simulate_rng: uniform_mask 0x%x needs uniform_values_host[10]", uniform_mask);
@@ -751,10 +809,11 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
     for (int64_t a = 0; a < n && !rc; a += step, ++c) {
         const int64_t b = (a + step < n) ? a + step : n;
         cudaStream_t run = (c & 1) ? sx : st;
+        const uint32_t skip = uniform_mask | (derive_beta ? (1u << 3) : 0u);   // rows that do not cross PCIe
         for (int r0 = 0; r0 < B200I_NUM_PARAMS && !rc;) {   // maximal runs of rows that are real arrays
-            if ((uniform_mask >> r0) & 1u) { ++r0; continue; }
+            if ((skip >> r0) & 1u) { ++r0; continue; }
             int r1 = r0;
-            while (r1 < B200I_NUM_PARAMS && !((uniform_mask >> r1) & 1u)) ++r1;
+            while (r1 < B200I_NUM_PARAMS && !((skip >> r1) & 1u)) ++r1;
             rc = check_cuda(cudaMemcpy2DAsync(params + (size_t)r0 * n + a, (size_t)n * 8, params_host + (size_t)r0 * n + a,
                                               (size_t)n * 8, (size_t)(b - a) * 8, r1 - r0, cudaMemcpyHostToDevice, cs),
                             "cudaMemcpy2DAsync(params)");
@@ -763,8 +822,17 @@ extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch
         if (!rc && static_host)
             rc = check_cuda(cudaMemcpyAsync(static_feature + a, static_host + a, (size_t)(b - a) * 8,
                                             cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(static)");
+        if (!rc && types_u8_host)
+            rc = check_cuda(cudaMemcpyAsync(types_u8_dev + a, types_u8_host + a, (size_t)(b - a), cudaMemcpyHostToDevice, cs),
+                            "cudaMemcpyAsync(patient types)");
         if (!rc) rc = check_cuda(cudaEventRecord(ev, cs), "cudaEventRecord");
         if (!rc) rc = check_cuda(cudaStreamWaitEvent(run, ev, 0), "cudaStreamWaitEvent");
+        if (!rc && (derive_beta || types_u8_host)) {
+            int64_t g = (b - a + 255) / 256;
+            if (g > num_sms() * 4) g = num_sms() * 4;
+            derive_chunk_rows_kernel<<<(unsigned)g, 256, 0, run>>>(params, n, a, b - a, derive_beta, types_u8_dev, static_feature);
+            rc = check_cuda(cudaGetLastError(), "derive_chunk_rows launch");
+        }
         if (!rc)
             rc = b200i_sim_factual_rng(b - a, T, row_pitch, k, params + a, n, seed, patient_base + a,
                                        cancer_volume + a * row_pitch, codes_out ? codes_out + a * code_pitch : nullptr,

@@ -227,9 +227,19 @@ def chunk_workspaces(chunks):
     return torch.zeros(int(chunks) * ((lib.b200i_gram_workspace_bytes() + 7) // 8), dtype=torch.float64, device='cuda')
 
 
+def cohort_scalar_rows(chemo_coeff, radio_coeff):
+    """{row index: value} of the parameter rows generate_params fills with one scalar for the whole cohort
+    (cancer_simulation.py:83-88, :202): K = calc_volume(30) and the sigmoid intercepts D_MAX / 2 and slopes gamma / D_MAX.
+    They are functions of generate_params' ARGUMENTS, so a caller that knows (chemo_coeff, radio_coeff) need not ship
+    or scan the five (N,) arrays."""
+    d_max = ((TUMOUR_DEATH_THRESHOLD / (4 / 3 * np.pi)) ** (1 / 3)) * 2
+    return {5: float(4 / 3 * np.pi * (30 / 2) ** 3), 6: float(d_max / 2.0), 7: float(d_max / 2.0),
+            8: float(chemo_coeff / d_max), 9: float(radio_coeff / d_max)}
+
+
 def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, seed, patient_base, consts, volume, codes,
                         sequence_lengths, patient_moments, chunks, copy_stream, chunk_ws=None, stats_out=None,
-                        fd_dt=STANDARD_DT, uniform=None):
+                        fd_dt=STANDARD_DT, uniform=None, derive_beta=False, types_u8_host=None, types_u8_dev=None):
     """Pinned host parameters -> chunked H2D on copy_stream, each chunk simulated (K1L) on the current stream as soon
     as it has arrived (b200i_upload_simulate_rng).  chunk_ws (chunk_workspaces(chunks)) + stats_out (68,): each
     chunk's share of the population statistics is computed right behind its simulation and summed in chunk order."""
@@ -242,6 +252,20 @@ def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, see
     for r, v in (uniform or {}).items():     # parameter rows that are one scalar for the whole cohort: not copied
         mask |= 1 << int(r)
         vals[int(r)] = float(v)
+    if types_u8_host is not None:
+        # reduced parameter set: beta derived from alpha, patient types as bytes (b200i_upload_simulate_rng_reduced)
+        assert types_u8_host.is_pinned() and types_u8_host.dtype == torch.uint8 and types_u8_host.numel() == n
+        assert types_u8_dev is not None and types_u8_dev.is_cuda and types_u8_dev.numel() == n
+        rc = lib.b200i_upload_simulate_rng_reduced(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
+                                                   mask, vals if mask else None, 1 if derive_beta else 0,
+                                                   ctypes.c_void_p(types_u8_host.data_ptr()), _ptr(types_u8_dev),
+                                                   _ptr(params_dev), _ptr(static_dev), int(seed), int(patient_base),
+                                                   _ptr_rows(volume), _ptr(codes), int(codes.shape[1]),
+                                                   _ptr(sequence_lengths), _ptr(patient_moments), int(chunks), float(fd_dt),
+                                                   _ptr(chunk_ws), _ptr(stats_out),
+                                                   ctypes.c_void_p(copy_stream.cuda_stream), _stream())
+        _native.check(rc, "b200i_upload_simulate_rng_reduced")
+        return
     rc = lib.b200i_upload_simulate_rng(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
                                        mask, vals if mask else None,
                                        None if static_host is None else ctypes.c_void_p(static_host.data_ptr()),

@@ -162,6 +162,19 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     torch.cuda.synchronize()
     assert torch.equal(c.params, b.params) and torch.equal(c.volume, b.volume) and torch.equal(c.codes, b.codes)
     assert torch.equal(c.stats, a.stats) and c.h2d_bytes(uni) == 6 * n * 8
+    # reduced input set (what get_standard_params draws): beta = alpha / 10 and the static feature are rebuilt on the
+    # device, the scalar rows come from generate_params' arguments -- 33 bytes per patient, the same bits
+    assert dev.cohort_scalar_rows(2.0, 2.0) == uni
+    assert np.array_equal(params['beta'], params['alpha'] / 10)
+    junk[3] = float('nan')
+    types = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.uint8)).pin_memory()
+    d = GeneratedFitPipeline(n, T, seed=3, patient_base=1000, chunks=chunks)
+    d.params.fill_(-1.0); d.static.fill_(-1.0)
+    d.step_host(junk.pin_memory(), None, res, uniform=dev.cohort_scalar_rows(2.0, 2.0), types_u8=types)
+    torch.cuda.synchronize()
+    assert torch.equal(d.params, b.params) and torch.equal(d.static, b.static)
+    assert torch.equal(d.volume, b.volume) and torch.equal(d.codes, b.codes) and torch.equal(d.stats, a.stats)
+    assert d.h2d_bytes(uni, reduced=True) == 33 * n
 
 
 def test_generated_counterfactual_draws_and_cohort(dev):
