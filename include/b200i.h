@@ -39,6 +39,9 @@ extern "C" {
 #define B200I_E_WORKSPACE (-4)  /* workspace too small */
 #define B200I_E_DRIVER (-5)     /* cuTensorMapEncodeTiled unavailable / failed */
 
+#define B200I_LS_ROBUST 0       /* line_search argument of the b200i_insite_bfgs* entry points */
+#define B200I_LS_JAX 1
+
 #define B200I_NUM_PARAMS 10     /* rows of the parameter block, order below */
 /* parameter block `params` is (10, N) row-major, rows in this order (keys of the dict returned by
  * generate_params, cancer_simulation.py:195-203, 84-88):
@@ -370,11 +373,24 @@ B200I_API int b200i_expand_cf_treatment_seq(int64_t n, int32_t T, int32_t H, con
  *   Lineage: determine_individualized_equation_coefs, pkpd_simulation.py:791-836 (dormant in the reference).
  *
  * K7 b200i_insite_bfgs: the reference's live estimator, _fine_tuning_inner (sindy.py:587-631) with
- *   f_to_min_func (:781-794): BFGS (strong-Wolfe line search) over all 16 coefficients from theta0.
+ *   f_to_min_func (:781-794): jax.scipy.optimize.minimize(method='BFGS') over all 16 coefficients from theta0.
  *   Rows with sequence_length <= projection_horizon keep theta0 (:571-585).
- *   status_out (R,) int32: low byte 0 converged / 1 max_iter / 3,5 line search exhausted / 4 perfect start /
- *   6 no improvement (theta0 kept) / -2 skipped; bits 8.. = BFGS iterations.  fval_out (R,2) = objective at
- *   theta0 and at the returned coefficients.
+ *   line_search:
+ *     B200I_LS_JAX    the semantics of jax's minimize_bfgs / line_search / _zoom (un-vendored dependency of the reference,
+ *                     restated): start step min(1, 1.01 * 2 (f_k - f_{k-1}) / dphi_0), bracketing by doubling (10 trials),
+ *                     zoom with cubic / quadratic / bisection trial points, and jax's FAILURE rules -- zoom fails when the
+ *                     signed bracket width a_hi - a_lo is <= 1e-10 (so at once for a reversed bracket) or after 30
+ *                     trials; a failed line search ends BFGS with status 3 and leaves x + a p behind, a = the last trial
+ *                     point if it satisfied both Wolfe conditions, else 1.  Call it with gtol = 1e-5 and max_iter =
+ *                     200 * (number of coefficients): jax ignores the reference's tol=1e-12 argument (minimize() does
+ *                     not forward `tol` to minimize_bfgs).  With these settings the two INSITE lines of the reference's
+ *                     committed logs are reproduced to 5e-15 / 2e-6 relative (tests/test_gpu_insite.py).
+ *     B200I_LS_ROBUST Nocedal-Wright strong-Wolfe search that accepts the best sufficient-decrease point when the
+ *                     curvature test cannot be met (FP64 noise floor) and never returns a point worse than theta0.
+ *   status_out (R,) int32: low byte 0 converged / 1 max_iter / 3 zoom failed (the rows the reference replaces by
+ *   theta0, sindy.py:628-631) / 5 bracketing exhausted / 4 perfect start / 6 no improvement (robust mode: theta0
+ *   kept) / -2 skipped; bits 8.. = BFGS iterations.  fval_out (R,2) = objective at theta0 and at the returned
+ *   coefficients.
  * ---------------------------------------------------------------------------------------------- */
 B200I_API int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const double *x, const uint8_t *codes,
                         const int32_t *fit_len, const double *static_feature, const double *prior,
@@ -383,7 +399,8 @@ B200I_API int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const d
 B200I_API int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
                       const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
                       const double *static_feature, const double *theta0, double lam, double gtol,
-                      int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+                      int32_t max_iter, int32_t line_search, double *coefs_out, int32_t *status_out, double *fval_out,
+                      void *stream);
 /* The same for the joint ("one ODE") model, sindy.py:503-517 with joint_model=True: theta0 / coefs_out hold the 11
  * coefficients of [1, x0, u0, u1, u2, x0 u0, x0 u1, x0 u2, u0 u1, u0 u2, u1 u2] (x0 volume, u0 chemo, u1 radio
  * application, u2 static feature); codes = chemo + 2*radio application per step; coefs_out is (rows, 11); the
@@ -391,7 +408,8 @@ B200I_API int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t subs
 B200I_API int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
                       const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
                       const double *static_feature, const double *theta0, double lam, double gtol,
-                      int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+                      int32_t max_iter, int32_t line_search, double *coefs_out, int32_t *status_out, double *fval_out,
+                      void *stream);
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -429,7 +447,8 @@ B200I_API int b200i_cf_eval_treatment_seq(int64_t n, int32_t T, int32_t H, doubl
 B200I_API int b200i_insite_bfgs_prefix(int64_t n, int32_t T, int32_t fit_offset, double dt, int32_t substeps,
                            const double *factual, const uint8_t *codes, const int32_t *n_steps,
                            const double *static_feature, const double *theta0, double lam, double gtol,
-                           int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+                           int32_t max_iter, int32_t line_search, double *coefs_out, int32_t *status_out, double *fval_out,
+                           void *stream);
 B200I_API int b200i_stlsq_prefix(int64_t n, int32_t T, int32_t fit_offset, double fd_dt, const double *factual,
                            const uint8_t *codes, const int32_t *n_steps, const double *static_feature,
                            const double *prior, double support_tol, double lam, double threshold, int32_t max_iter,
@@ -461,8 +480,9 @@ B200I_API int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x, 
                            const double *dts, int32_t dts_per_row, double *coefs_out, void *stream);
 B200I_API int b200i_insite_bfgs_dts(int64_t rows, int32_t W, int32_t substeps, const double *x, const uint8_t *codes,
                            const int32_t *sequence_lengths, int32_t projection_horizon, const double *static_feature,
-                           const double *theta0, double lam, double gtol, int32_t max_iter, const double *dts,
-                           int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out, void *stream);
+                           const double *theta0, double lam, double gtol, int32_t max_iter, int32_t line_search,
+                           const double *dts, int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out,
+                           void *stream);
 B200I_API int b200i_theta_gram_dts(int64_t n, int32_t T, const double *cancer_volume, const double *chemo_application,
                            const double *radio_application, const double *sequence_lengths,
                            const double *static_feature, const double *dts, int32_t dts_per_row,

@@ -67,19 +67,19 @@ SIGNATURES = {
                                    [ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), c_vp]),
     "b200i_stlsq_batched": (ctypes.c_int, [c_i64, c_i32, c_f64] + [c_vp] * 5 + [c_f64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "b200i_insite_bfgs": (ctypes.c_int, [c_i64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_f64, c_f64,
-                                         c_i32, c_vp, c_vp, c_vp, c_vp]),
+                                         c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200i_insite_bfgs_joint": (ctypes.c_int, [c_i64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_f64, c_f64,
-                                               c_i32, c_vp, c_vp, c_vp, c_vp]),
+                                               c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200i_cf_eval_one_step": (ctypes.c_int, [c_i64, c_i32, c_f64, c_i32] + [c_vp] * 6 + [c_i32, c_f64, c_vp, c_vp]),
     "b200i_cf_eval_treatment_seq": (ctypes.c_int, [c_i64, c_i32, c_i32, c_f64, c_i32] + [c_vp] * 7 + [c_i32, c_f64, c_vp, c_vp]),
-    "b200i_insite_bfgs_prefix": (ctypes.c_int, [c_i64, c_i32, c_i32, c_f64, c_i32] + [c_vp] * 5 + [c_f64, c_f64, c_i32] +
+    "b200i_insite_bfgs_prefix": (ctypes.c_int, [c_i64, c_i32, c_i32, c_f64, c_i32] + [c_vp] * 5 + [c_f64, c_f64, c_i32, c_i32] +
                                  [c_vp] * 4),
     "b200i_stlsq_prefix": (ctypes.c_int, [c_i64, c_i32, c_i32, c_f64] + [c_vp] * 5 + [c_f64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "b200i_ode_rollout_dts": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "b200i_stlsq_batched_dts": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 6 + [c_f64, c_f64, c_f64, c_i32, c_f64, c_vp, c_i32,
                                                                              c_vp, c_vp]),
     "b200i_insite_bfgs_dts": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_f64, c_f64, c_i32,
-                                             c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+                                             c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200i_theta_gram_dts": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 6 + [c_i32, c_vp, c_vp]),
     "b200i_expand_cf_one_step": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 5 + [c_i64, c_i64] + [c_vp] * 5 + [c_vp]),
     "b200i_expand_cf_treatment_seq": (ctypes.c_int, [c_i64, c_i32, c_i32] + [c_vp] * 6 + [c_i64, c_i64] + [c_vp] * 7 +

@@ -150,17 +150,19 @@ def simulate_factual(simulation_params, seq_length, assigned_actions=None):
     return outputs
 
 
-def simulate_counterfactual_1_step(simulation_params, seq_length):
-    """All one-step-ahead counterfactuals of the test patients.  Reference: :378-563."""
+def simulate_counterfactual_1_step(simulation_params, seq_length, lazy=False):
+    """All one-step-ahead counterfactuals of the test patients.  Reference: :378-563.
+    lazy=True (used by this package's own dataset classes): the three dense (R, T) arrays are expanded and copied to
+    the host on first access only; the dictionary carries the device-resident compact cohort."""
     from . import counterfactual as cf
     n = simulation_params['initial_stages'].shape[0]
     draws = _draw_per_patient(n, seq_length, 0)
-    return cf.one_step_dense(simulation_params, int(seq_length), draws)
+    return cf.one_step_dense(simulation_params, int(seq_length), draws, lazy=lazy)
 
 
 def simulate_counterfactuals_treatment_seq(simulation_params, seq_length, projection_horizon,
-                                           cf_seq_mode='sliding_treatment'):
-    """Multi-step counterfactual treatment sequences of the test patients.  Reference: :566-773."""
+                                           cf_seq_mode='sliding_treatment', lazy=False):
+    """Multi-step counterfactual treatment sequences of the test patients.  Reference: :566-773.  lazy: see above."""
     from . import counterfactual as cf
     if cf_seq_mode != 'sliding_treatment':
         # 'random_trajectories' consumes the RNG data-dependently inside the time loop (:704-705);
@@ -168,7 +170,7 @@ def simulate_counterfactuals_treatment_seq(simulation_params, seq_length, projec
         raise NotImplementedError(f"cf_seq_mode={cf_seq_mode!r}: only 'sliding_treatment' is implemented")
     n = simulation_params['initial_stages'].shape[0]
     draws = _draw_per_patient(n, seq_length, int(projection_horizon))
-    return cf.treatment_seq_dense(simulation_params, int(seq_length), int(projection_horizon), draws)
+    return cf.treatment_seq_dense(simulation_params, int(seq_length), int(projection_horizon), draws, lazy=lazy)
 
 
 def get_scaling_params(sim):

@@ -130,22 +130,74 @@ def _upload(simulation_params, draws):
     return params_dev, noise, rec, chemo, radio, ptypes, consts
 
 
-def one_step_dense(simulation_params, seq_length, draws):
-    """numpy-in / numpy-out body of simulate_counterfactual_1_step (dict keys of :554-559)."""
+def _row_meta(cohort, patient_types):
+    """The small per-row arrays of the reference dictionaries from the per-patient arrays (no dense expansion):
+    sequence_lengths, patient_types [, patient_ids_all_trajectories, patient_current_t], all float64 as the reference's
+    np.zeros buffers (:423-430, :621-630)."""
+    T, H = cohort.T, cohort.H
+    ns = cohort.n_steps.cpu().numpy().astype(np.int64)
+    n = ns.shape[0]
+    ptypes = np.asarray(patient_types, dtype=np.float64)
+    if cohort.kind == 'one_step':
+        per_step = np.where(np.arange(T - 1)[None, :] < ns[:, None], 4, 0)
+    else:
+        v = cohort.valid.cpu().numpy().view(np.uint16).astype(np.uint32)
+        pop = np.zeros_like(v)
+        for b in range(2 * H):
+            pop += (v >> b) & 1
+        per_step = np.where(np.arange(T - 1)[None, :] < ns[:, None], pop, 0).astype(np.int64)
+    counts = per_step.reshape(-1)
+    pid = np.repeat(np.repeat(np.arange(n), T - 1), counts)
+    cur_t = np.repeat(np.tile(np.arange(T - 1), n), counts)
+    meta = {'sequence_lengths': (cur_t + 1 + H).astype(np.float64), 'patient_types': ptypes[pid]}
+    if cohort.kind != 'one_step':
+        meta['patient_ids_all_trajectories'] = pid.astype(np.float64)
+        meta['patient_current_t'] = cur_t.astype(np.float64)
+    assert meta['sequence_lengths'].shape[0] == cohort.total_rows
+    return meta
+
+
+def _lazy_dense(cohort, ptypes_dev, patient_types):
+    """Dictionary with the reference's keys (cancer_simulation.py:554-559 / :762-769).  The three (R, width) arrays -- 227
+    resp. 562 rows per test patient -- stay on the device in compact form until somebody reads them: the first access
+    of any of them expands the cohort and copies the dense rows to the host once.  The compact cohort itself travels
+    as attrs['compact'] = (cohort, static feature on the device): SINDY evaluates it without dense rows."""
+    from .lazydict import LazyDict
+    big = ('cancer_volume', 'chemo_application', 'radio_application')
+
+    def build():
+        dense = expand(cohort, ptypes_dev)
+        torch.cuda.current_stream().synchronize()
+        return {k: dense[k].cpu().numpy() for k in big}
+    out = LazyDict()
+    out.set_lazy_group(big, build)
+    for k, v in _row_meta(cohort, patient_types).items():
+        out[k] = v
+    out.attrs['compact'] = (cohort, ptypes_dev)
+    return out
+
+
+def one_step_dense(simulation_params, seq_length, draws, lazy=False):
+    """numpy-in / numpy-out body of simulate_counterfactual_1_step (dict keys of :554-559).
+    lazy: return the dictionary with the dense arrays pending (see _lazy_dense)."""
     dev.require_cuda()
     params_dev, noise, rec, chemo, radio, ptypes, consts = _upload(simulation_params, draws)
     cohort = sim_cf_one_step(params_dev, noise, rec, chemo, radio, seq_length, consts)
+    if lazy:
+        return _lazy_dense(cohort, ptypes, simulation_params['patient_types'])
     dense = expand(cohort, ptypes)
     torch.cuda.current_stream().synchronize()
     return {k: dense[k].cpu().numpy() for k in
             ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'patient_types')}
 
 
-def treatment_seq_dense(simulation_params, seq_length, projection_horizon, draws):
+def treatment_seq_dense(simulation_params, seq_length, projection_horizon, draws, lazy=False):
     """numpy-in / numpy-out body of simulate_counterfactuals_treatment_seq (dict keys of :762-769)."""
     dev.require_cuda()
     params_dev, noise, rec, chemo, radio, ptypes, consts = _upload(simulation_params, draws)
     cohort = sim_cf_treatment_seq(params_dev, noise, rec, chemo, radio, seq_length, projection_horizon, consts)
+    if lazy:
+        return _lazy_dense(cohort, ptypes, simulation_params['patient_types'])
     dense = expand(cohort, ptypes)
     torch.cuda.current_stream().synchronize()
     return {k: dense[k].cpu().numpy() for k in

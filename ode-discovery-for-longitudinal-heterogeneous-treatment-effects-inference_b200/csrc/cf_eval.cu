@@ -86,7 +86,11 @@ __device__ __forceinline__ bool grid_arrive(unsigned int *ticket, unsigned int *
 // K8: one-step cohort.  One warp per patient.
 // sums layout = b200i_masked_se's: se_col[W], cnt_col[W], se_last_col[W], total last se, rows.
 // ------------------------------------------------------------------------------------------------
-template <bool PER_T>
+// The inputs of the NEXT patient of a warp are fetched into registers (TW / 32 volumes and code bytes, TW / 8
+// counterfactual values per lane) before the current one is evaluated, so the global-load latency overlaps the
+// arithmetic; the first version loaded, parked and then computed, and stalled on `long_scoreboard` 8.7 of every 10 issue
+// slots (profiles/r2_k8_cf_eval_one_step_ncu.txt).  TW = 64 or 128: compile-time bound of T (register arrays).
+template <bool PER_T, int TW>
 __global__ void __launch_bounds__(EV_THREADS)
 cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *__restrict__ F,
                         const uint8_t *__restrict__ codes, const double *__restrict__ cf,
@@ -94,11 +98,16 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
                         const double *__restrict__ coefs, double drop_below, double *__restrict__ partials,
                         unsigned int *__restrict__ ticket, double *__restrict__ sums)
 {
-    __shared__ double s_F[EV_WARPS][EV_MAXT];
-    __shared__ __align__(16) double s_cf[EV_WARPS][EV_MAXT * 4];
+    // padded layouts: a lane of the shared-coefficient path owns 4 consecutive columns, i.e. 16 consecutive cf values
+    // and 4 consecutive F values; pitches 17 / 5 keep the lanes of a half-warp in different banks
+    __shared__ double s_F[EV_WARPS][5 * (EV_MAXT / 4) + 8];
+    __shared__ double s_cf[EV_WARPS][17 * (EV_MAXT / 4)];
     __shared__ uint8_t s_code[EV_WARPS][EV_MAXT];
+    __shared__ Affine s_map[EV_WARPS][4];
     __shared__ double s_coef[16];
     __shared__ double s_acc[EV_WARPS][3 * EV_MAXT];
+    auto f_at = [](int k) { return 5 * (k >> 2) + (k & 3); };
+    auto cf_at = [](int k, int o) { return 17 * (k >> 2) + 4 * (k & 3) + o; };
     __shared__ unsigned int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = T - 1;
@@ -112,29 +121,58 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
     for (int j = 0; j < EV_SL; ++j) se[j] = cnt[j] = last[j] = 0.0;
 
     const int64_t nwarps = (int64_t)gridDim.x * EV_WARPS;
-    for (int64_t i = (int64_t)blockIdx.x * EV_WARPS + warp; i < n; i += nwarps) {
-        int ns = n_steps[i];
-        if (ns > W) ns = W;
-        const double u = static_u[i];
-        __syncwarp();
-        for (int k = lane; k < T; k += 32) {
-            s_F[warp][k] = F[i * T + k];
-            s_code[warp][k] = codes[i * T + k];
+    constexpr int SLF = TW / 32, SLC = TW / 8;
+    double rF[SLF], rCF[SLC], r_u = 0.0;
+    uint8_t rC[SLF];
+    int r_ns = 0;
+    auto fetch = [&](int64_t i) {
+#pragma unroll
+        for (int j = 0; j < SLF; ++j) {
+            const int k = lane + 32 * j;
+            if (k < T) { rF[j] = F[i * T + k]; rC[j] = codes[i * T + k]; }
         }
-        for (int e = lane; e < 4 * W; e += 32) s_cf[warp][e] = cf[i * (int64_t)(4 * W) + e];
+#pragma unroll
+        for (int j = 0; j < SLC; ++j) {
+            const int e = lane + 32 * j;
+            if (e < 4 * W) rCF[j] = cf[i * (int64_t)(4 * W) + e];
+        }
+        r_ns = n_steps[i];
+        r_u = static_u[i];
+    };
+    {
+        const int64_t i0 = (int64_t)blockIdx.x * EV_WARPS + warp;
+        if (i0 < n) fetch(i0);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * EV_WARPS + warp; i < n; i += nwarps) {
+        int ns = r_ns;
+        if (ns > W) ns = W;
+        const double u = r_u;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < SLF; ++j) {
+            const int k = lane + 32 * j;
+            if (k < T) { s_F[warp][f_at(k)] = rF[j]; s_code[warp][k] = rC[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < SLC; ++j) {
+            const int e = lane + 32 * j;
+            if (e < 4 * W) s_cf[warp][17 * (e >> 4) + (e & 15)] = rCF[j];
+        }
+        if (i + nwarps < n) fetch(i + nwarps);
+        if (!PER_T && lane < 4)   // the four maps of this patient, by option index 2*chemo + radio
+            s_map[warp][lane] = euler_affine(s_coef[4 * option_to_code(lane)], s_coef[4 * option_to_code(lane) + 1],
+                                             s_coef[4 * option_to_code(lane) + 2], s_coef[4 * option_to_code(lane) + 3], u, h,
+                                             substeps);
         __syncwarp();
         const double F0 = s_F[warp][0];
         if (!PER_T) {
-            Affine m[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                m[a] = euler_affine(s_coef[4 * a], s_coef[4 * a + 1], s_coef[4 * a + 2], s_coef[4 * a + 3], u, h, substeps);
+            const Affine *mo = s_map[warp];
             // affine prefix scan over the factual steps: lane owns steps 4 lane .. 4 lane + 3
             Affine comp{1.0, 0.0};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = 4 * lane + q;
-                if (k < ns) comp = compose(pick(m, option_to_code(s_code[warp][k])), comp);
+                if (k < ns) comp = compose(mo[s_code[warp][k] & 3], comp);
             }
             Affine inc = comp;
 #pragma unroll
@@ -157,8 +195,8 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
                     double e_f = 0.0, e_o = 0.0;
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {
-                        const double p = apply(pick(m, option_to_code(o)), v);
-                        const double target = (o == fo) ? s_F[warp][k + 1] : s_cf[warp][4 * k + o];
+                        const double p = apply(mo[o], v);
+                        const double target = (o == fo) ? s_F[warp][f_at(k + 1)] : s_cf[warp][cf_at(k, o)];
                         const double d = p - target;
                         if (o == fo) e_f = d * d;
                         else e_o += d * d;
@@ -167,7 +205,7 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
                     se[q] += e_f * (double)(4 * (ns - 1 - k) + 1) + e_o;
                     cnt[q] += (double)(4 * (ns - k));
                     last[q] += e_f + e_o;
-                    v = apply(pick(m, option_to_code(fo)), v);
+                    v = apply(mo[fo], v);
                 }
             }
         } else {
@@ -196,7 +234,7 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             const double pr = apply(pick(m, option_to_code(o)), v);
-                            const double target = (o == fo) ? s_F[warp][k + 1] : s_cf[warp][4 * k + o];
+                            const double target = (o == fo) ? s_F[warp][f_at(k + 1)] : s_cf[warp][cf_at(k, o)];
                             const double d = pr - target;
                             e_all += d * d;
                         }
@@ -205,7 +243,7 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
                             if (j == p) { se[j] += e_all; last[j] += e_all; }
                     }
                     v = apply(pick(m, option_to_code(fo)), v);
-                    const double d = v - s_F[warp][k + 1];
+                    const double d = v - s_F[warp][f_at(k + 1)];
                     const double tot = warp_sum((act && k < t) ? 4.0 * d * d : 0.0);
                     if (lane == (k & 31)) {
 #pragma unroll
@@ -259,10 +297,17 @@ cf_eval_one_step_kernel(int64_t n, int T, double h, int substeps, const double *
 // K9: treatment-sequence cohort.  One CTA walks patients; each patient's (T-1, 2H, H) block of projected volumes
 // arrives by one bulk copy into a ring of EV_STAGES shared-memory buffers.
 // sums layout: se[H] (squared error per projection step), then rows[H] (valid rows, the same for every step).
+//
+// One __syncthreads per patient: the small per-patient inputs (code bytes, validity masks, executed steps, static
+// feature, F[0]) of the NEXT patient are loaded into registers while the current one is processed and parked in a
+// double-buffered shared array at the top of the next iteration; that barrier also proves the previous patient's stage
+// free, so one thread refills it.  With shared coefficients every warp runs the factual prefix as an affine scan of
+// its own (2 steps per lane, 5 shuffle rounds) -- the first version walked 59 dependent FMAs behind two more barriers
+// and spent its time in `barrier` / `long_scoreboard` stalls (profiles/r2_k9_cf_eval_seq_ncu.txt: 9.9 ms per 1M patients).
 // ------------------------------------------------------------------------------------------------
-template <bool PER_T>
+template <bool PER_T, int HT>   // HT: compile-time projection horizon (0 = run time)
 __global__ void __launch_bounds__(EV_THREADS)
-cf_eval_seq_kernel(int64_t n, int T, int H, double h, int substeps, const double *__restrict__ F,
+cf_eval_seq_kernel(int64_t n, int T, int H_rt, double h, int substeps, const double *__restrict__ F,
                    const uint8_t *__restrict__ codes, const double *__restrict__ cf, const uint16_t *__restrict__ valid,
                    const int *__restrict__ n_steps, const double *__restrict__ static_u, const double *__restrict__ coefs,
                    double drop_below, double *__restrict__ partials, unsigned int *__restrict__ ticket,
@@ -271,13 +316,14 @@ cf_eval_seq_kernel(int64_t n, int T, int H, double h, int substeps, const double
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t full[EV_STAGES];
     __shared__ Affine s_aff[PER_T ? EV_MAXT : 1][4];
-    __shared__ double s_start[EV_MAXT];
-    __shared__ uint8_t s_code[EV_MAXT];
-    __shared__ uint16_t s_valid[EV_MAXT];
+    __shared__ double s_start[PER_T ? 1 : EV_WARPS][EV_MAXT];
+    __shared__ uint8_t s_code[2][EV_MAXT];
+    __shared__ uint16_t s_valid[2][EV_MAXT];
     __shared__ double s_coef[16];
     __shared__ double s_red[EV_WARPS][2 * EV_MAXH];
     __shared__ unsigned int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = HT > 0 ? HT : H_rt;
     const int W = T - 1, O = 2 * H, npairs = W * O;
     const uint32_t block_bytes = (uint32_t)npairs * H * sizeof(double);
     const uint32_t stage_bytes = (block_bytes + 127u) & ~127u;
@@ -302,63 +348,122 @@ cf_eval_seq_kernel(int64_t n, int T, int H, double h, int substeps, const double
 #pragma unroll
     for (int k = 0; k < EV_MAXH; ++k) se[k] = 0.0;
 
+    // small inputs of the first patient
+    int r_ns = 0;
+    double r_u = 0.0, r_f0 = 0.0;
+    uint8_t r_code = 0;
+    uint16_t r_valid = 0;
+    if ((int64_t)blockIdx.x < n) {
+        const int64_t i = blockIdx.x;
+        r_ns = n_steps[i]; r_u = static_u[i]; r_f0 = F[i * T];
+        if (tid < T) r_code = codes[i * T + tid];
+        if (tid < W) r_valid = valid[i * W + tid];
+    }
     uint32_t it = 0;
     for (int64_t i = blockIdx.x; i < n; i += gridDim.x, ++it) {
         const int s = (int)(it % EV_STAGES);
         const uint32_t parity = (it / EV_STAGES) & 1u;
-        int ns = n_steps[i];
-        if (ns > W) ns = W;
-        const double u = static_u[i];
-        if (tid < T) s_code[tid] = codes[i * T + tid];
-        if (tid < W) s_valid[tid] = valid[i * W + tid];
-        if (!PER_T && tid < 4)
-            s_aff[0][tid] = euler_affine(s_coef[4 * tid], s_coef[4 * tid + 1], s_coef[4 * tid + 2], s_coef[4 * tid + 3], u, h,
-                                         substeps);
-        __syncthreads();
-        // start value of (i,t): xhat[t+1], rolled from F[0] over the factual codes 0..t with the maps of (i,t)
-        if (tid < ns) {
-            const int t = tid;
-            if (PER_T) {
+        const int b = (int)(it & 1u);
+        int ns = r_ns < W ? r_ns : W;
+        const double u = r_u, f0 = r_f0;
+        if (tid < T) s_code[b][tid] = r_code;
+        if (tid < W) s_valid[b][tid] = r_valid;
+        {   // next patient's small inputs -> registers (consumed at the top of the next iteration)
+            const int64_t nx = i + gridDim.x;
+            if (nx < n) {
+                r_ns = n_steps[nx]; r_u = static_u[nx]; r_f0 = F[nx * T];
+                if (tid < T) r_code = codes[nx * T + tid];
+                if (tid < W) r_valid = valid[nx * W + tid];
+            }
+        }
+        __syncthreads();   // small inputs visible; every thread has left the previous patient's stage
+        if (tid == 0 && it >= 1) {
+            const int64_t nxt = i + (int64_t)(EV_STAGES - 1) * gridDim.x;    // patient it + EV_STAGES - 1
+            const int sp = (int)((it - 1) % EV_STAGES);
+            if (nxt < n) {
+                mbar_arrive_expect_tx(&full[sp], block_bytes);
+                bulk_load_g2s(smem_raw + (size_t)sp * stage_bytes, cf + nxt * block_elems, block_bytes, &full[sp]);
+            }
+        }
+        const double *start;
+        Affine m0, m1c, m1r;      // shared coefficients: the maps of codes 0 (none), 1 (chemo), 2 (radio)
+        if (!PER_T) {
+            Affine m[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                m[a] = euler_affine(s_coef[4 * a], s_coef[4 * a + 1], s_coef[4 * a + 2], s_coef[4 * a + 3], u, h, substeps);
+            m0 = m[0]; m1c = m[1]; m1r = m[2];
+            // start value of (i,t) = xhat[t+1] = steps 0..t applied to F[0]: affine scan, lane owns steps 2 lane, 2 lane + 1
+            // (and 64 + 2 lane, 65 + 2 lane for T > 65)
+            Affine carry{1.0, 0.0};
+            for (int base = 0; base < ns; base += 64) {
+                const int k0 = base + 2 * lane;
+                const Affine a0 = (k0 < ns) ? pick(m, option_to_code(s_code[b][k0])) : Affine{1.0, 0.0};
+                const Affine a1 = (k0 + 1 < ns) ? pick(m, option_to_code(s_code[b][k0 + 1])) : Affine{1.0, 0.0};
+                Affine inc = compose(a1, a0);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    Affine prev;
+                    prev.al = __shfl_up_sync(0xffffffffu, inc.al, d);
+                    prev.be = __shfl_up_sync(0xffffffffu, inc.be, d);
+                    if (lane >= d) inc = compose(inc, prev);
+                }
+                Affine exc;
+                exc.al = __shfl_up_sync(0xffffffffu, inc.al, 1);
+                exc.be = __shfl_up_sync(0xffffffffu, inc.be, 1);
+                if (lane == 0) exc = Affine{1.0, 0.0};
+                const Affine upto0 = compose(compose(a0, exc), carry), upto1 = compose(inc, carry);
+                if (k0 < ns) s_start[warp][k0] = apply(upto0, f0);
+                if (k0 + 1 < ns) s_start[warp][k0 + 1] = apply(upto1, f0);
+                Affine last;
+                last.al = __shfl_sync(0xffffffffu, inc.al, 31);
+                last.be = __shfl_sync(0xffffffffu, inc.be, 31);
+                carry = compose(last, carry);
+            }
+            __syncwarp();
+            start = s_start[warp];
+        } else {
+            if (tid < ns) {
+                const int t = tid;
                 const double *c = coefs + (i * W + t) * 16;
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
                     s_aff[t][a] = euler_affine(keep_term(c[4 * a], drop_below), keep_term(c[4 * a + 1], drop_below),
                                                keep_term(c[4 * a + 2], drop_below), keep_term(c[4 * a + 3], drop_below), u,
                                                h, substeps);
+                const Affine *m = s_aff[t];
+                double v = f0;
+#pragma unroll 4
+                for (int k = 0; k <= t; ++k) v = apply(m[option_to_code(s_code[b][k])], v);
+                s_start[0][t] = v;
             }
-            const Affine *m = PER_T ? s_aff[t] : s_aff[0];
-            double v = F[i * T];
-            for (int k = 0; k <= t; ++k) v = apply(m[option_to_code(s_code[k])], v);
-            s_start[t] = v;
+            __syncthreads();
+            start = s_start[0];
+            m0 = m1c = m1r = Affine{1.0, 0.0};
         }
-        __syncthreads();
         mbar_wait(&full[s], parity);
         const double *buf = reinterpret_cast<const double *>(smem_raw + (size_t)s * stage_bytes);
+        int t = tid / O, o = tid - t * O;
+        const int dt_ = EV_THREADS / O, do_ = EV_THREADS - dt_ * O;
         for (int e = tid; e < npairs; e += EV_THREADS) {
-            const int t = e / O, o = e - t * O;
-            if (t < ns && ((s_valid[t] >> o) & 1)) {
-                const Affine *m = PER_T ? s_aff[t] : s_aff[0];
-                const Affine m0 = m[0], m1 = m[o < H ? 1 : 2];   // sliding options: chemo (o < H) or radio once, at step o mod H
+            if (t < ns && ((s_valid[b][t] >> o) & 1)) {
+                Affine b0 = m0, b1 = (o < H) ? m1c : m1r;   // sliding options: chemo (o < H) or radio once, at step o mod H
+                if (PER_T) { b0 = s_aff[t][0]; b1 = s_aff[t][o < H ? 1 : 2]; }
                 const int kk = o < H ? o : o - H;
-                double v = s_start[t];
+                double v = start[t];
+                const double *tg = buf + e * H;
 #pragma unroll
                 for (int k = 0; k < EV_MAXH; ++k) {
                     if (k < H) {
-                        v = apply(k == kk ? m1 : m0, v);
-                        const double d = v - buf[e * H + k];
-                        se[k] += d * d;
+                        v = (k == kk) ? apply(b1, v) : apply(b0, v);
+                        const double d = v - tg[k];
+                        se[k] = fma(d, d, se[k]);
                     }
                 }
                 cnt += 1.0;
             }
-        }
-        __syncthreads();   // every thread is done with stage s, s_start and s_aff
-        if (tid == 0) {
-            const int64_t nxt = i + (int64_t)EV_STAGES * gridDim.x;
-            if (nxt < n) {
-                mbar_arrive_expect_tx(&full[s], block_bytes);
-                bulk_load_g2s(smem_raw + (size_t)s * stage_bytes, cf + nxt * block_elems, block_bytes, &full[s]);
-            }
+            t += dt_; o += do_;
+            if (o >= O) { o -= O; ++t; }
         }
     }
     // block combine, ordered grid combine
@@ -382,7 +487,7 @@ cf_eval_seq_kernel(int64_t n, int T, int H, double h, int substeps, const double
     if (grid_arrive(ticket, &s_flag)) {
         if (tid < NV) {
             double v = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * NV + tid]);
+            for (unsigned int bb = 0; bb < gridDim.x; ++bb) v += __ldcg(&partials[(size_t)bb * NV + tid]);
             const int which = tid / EV_MAXH, k = tid % EV_MAXH;
             if (k < H) sums[which * H + k] = v;
         }
@@ -425,15 +530,15 @@ extern "C" int b200i_cf_eval_one_step(int64_t n, int32_t T, double dt, int32_t s
     if (rc) return rc;
     unsigned int *ticket = static_cast<unsigned int *>(scratch);
     double *partials = reinterpret_cast<double *>(static_cast<uint8_t *>(scratch) + 256);
-    if (coefs_per_step)
-        cf_eval_one_step_kernel<true><<<(unsigned)grid, EV_THREADS, 0, st>>>(n, T, dt / substeps, substeps, factual, codes, cf,
-                                                                              n_steps, static_feature, coefs, drop_below,
-                                                                              partials, ticket, sums);
-    else
-        cf_eval_one_step_kernel<false><<<(unsigned)grid, EV_THREADS, 0, st>>>(n, T, dt / substeps, substeps, factual, codes, cf,
-                                                                               n_steps, static_feature, coefs, drop_below,
-                                                                               partials, ticket, sums);
-    rc = check_cuda(cudaGetLastError(), "cf_eval_one_step launch");
+    const bool small = T <= 64;
+    const void *kern = coefs_per_step ? (small ? reinterpret_cast<const void *>(cf_eval_one_step_kernel<true, 64>)
+                                               : reinterpret_cast<const void *>(cf_eval_one_step_kernel<true, 128>))
+                                      : (small ? reinterpret_cast<const void *>(cf_eval_one_step_kernel<false, 64>)
+                                               : reinterpret_cast<const void *>(cf_eval_one_step_kernel<false, 128>));
+    double hh = dt / substeps;
+    void *args[] = {&n, &T, &hh, &substeps, &factual, &codes, &cf, &n_steps, &static_feature, &coefs, &drop_below, &partials,
+                    &ticket, &sums};
+    rc = check_cuda(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(EV_THREADS), args, 0, st), "cf_eval_one_step launch");
     pool_free(scratch, st);
     return rc;
 }
@@ -459,8 +564,11 @@ extern "C" int b200i_cf_eval_treatment_seq(int64_t n, int32_t T, int32_t H, doub
     const int smem = (int)(EV_STAGES * stage_bytes);
     B200I_REQUIRE(smem <= 200 * 1024, B200I_E_UNSUPPORTED, "cf_eval_treatment_seq: T=%d, H=%d need %d bytes of shared memory", T,
                   H, smem);
-    const void *kern = coefs_per_step ? reinterpret_cast<const void *>(cf_eval_seq_kernel<true>)
-                                      : reinterpret_cast<const void *>(cf_eval_seq_kernel<false>);
+    const bool h5 = H == 5;     // projection_horizon of the reference's configuration (config/dataset/cancer_sim.yaml:16)
+    const void *kern = coefs_per_step ? (h5 ? reinterpret_cast<const void *>(cf_eval_seq_kernel<true, 5>)
+                                            : reinterpret_cast<const void *>(cf_eval_seq_kernel<true, 0>))
+                                      : (h5 ? reinterpret_cast<const void *>(cf_eval_seq_kernel<false, 5>)
+                                            : reinterpret_cast<const void *>(cf_eval_seq_kernel<false, 0>));
     int per_sm = 1;
     {
         int rc0 = ensure_dyn_smem(kern, smem, EV_THREADS, &per_sm);
@@ -476,14 +584,12 @@ extern "C" int b200i_cf_eval_treatment_seq(int64_t n, int32_t T, int32_t H, doub
     if (rc) return rc;
     unsigned int *ticket = static_cast<unsigned int *>(scratch);
     double *partials = reinterpret_cast<double *>(static_cast<uint8_t *>(scratch) + 256);
-    if (coefs_per_step)
-        cf_eval_seq_kernel<true><<<(unsigned)grid, EV_THREADS, smem, st>>>(n, T, H, dt / substeps, substeps, factual, codes, cf,
-                                                                           valid, n_steps, static_feature, coefs, drop_below,
-                                                                           partials, ticket, sums);
-    else
-        cf_eval_seq_kernel<false><<<(unsigned)grid, EV_THREADS, smem, st>>>(n, T, H, dt / substeps, substeps, factual, codes,
-                                                                            cf, valid, n_steps, static_feature, coefs,
-                                                                            drop_below, partials, ticket, sums);
+    double hh = dt / substeps;
+    void *args[] = {&n, &T, &H, &hh, &substeps, &factual, &codes, &cf, &valid, &n_steps, &static_feature, &coefs, &drop_below,
+                    &partials, &ticket, &sums};
+    rc = check_cuda(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(EV_THREADS), args, (size_t)smem, st),
+                    "cf_eval_treatment_seq launch");
+    if (rc) { pool_free(scratch, st); return rc; }
     rc = check_cuda(cudaGetLastError(), "cf_eval_treatment_seq launch");
     pool_free(scratch, st);
     return rc;

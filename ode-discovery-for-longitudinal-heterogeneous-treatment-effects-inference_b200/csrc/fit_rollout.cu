@@ -188,7 +188,30 @@ constexpr int R6_WARPS = 4;
 constexpr int R6_CH = 16;
 constexpr int R6_MAXW = 128;
 
-template <typename R>
+// SUB > 0: compile-time number of sub-steps (fully unrolled); SUB == 0: run-time `substeps`
+template <typename R, int SUB>
+__device__ __forceinline__ R euler_steps(R v, R c0, R c1, R c2u, R c3, R u, R h, int substeps)
+{
+    if (SUB > 0) {
+#pragma unroll
+        for (int sidx = 0; sidx < SUB; ++sidx) {
+            R f = r_add(c0, r_mul(c1, v));
+            f = r_add(f, c2u);
+            f = r_add(f, r_mul(c3, r_mul(v, u)));
+            v = r_add(v, r_mul(f, h));
+        }
+    } else {
+        for (int sidx = 0; sidx < substeps; ++sidx) {
+            R f = r_add(c0, r_mul(c1, v));
+            f = r_add(f, c2u);
+            f = r_add(f, r_mul(c3, r_mul(v, u)));
+            v = r_add(v, r_mul(f, h));
+        }
+    }
+    return v;
+}
+
+template <typename R, int SUB>
 __global__ void __launch_bounds__(R6_WARPS * 32)
 ode_rollout_tiled_kernel(int64_t rows, int W, double dt, int substeps, const double *__restrict__ x0,
                          const double *__restrict__ static_feature, const uint8_t *__restrict__ codes,
@@ -196,17 +219,19 @@ ode_rollout_tiled_kernel(int64_t rows, int W, double dt, int substeps, const dou
                          const double *__restrict__ dts, int dts_per_row, double *__restrict__ pred)
 {
     extern __shared__ __align__(16) uint8_t smem6[];
-    __shared__ double s_coef[16];
+    __shared__ R s_coef[16];
     __shared__ double s_dt[R6_MAXW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int code_bytes = (32 * W + 15) & ~15;
     double(*s_io)[R6_CH + 1] = reinterpret_cast<double(*)[R6_CH + 1]>(smem6) + (size_t)warp * 32;
-    double(*s_cf)[17] = reinterpret_cast<double(*)[17]>(smem6 + (size_t)R6_WARPS * 32 * (R6_CH + 1) * 8) + (size_t)warp * 32;
+    // per-row coefficient table in the compute type, terms with |c| <= drop_below already dropped; pitch 17: the
+    // 4-element row of (lane, code) sits in different banks for different lanes
+    R(*s_cf)[17] = reinterpret_cast<R(*)[17]>(smem6 + (size_t)R6_WARPS * 32 * (R6_CH + 1) * 8) + (size_t)warp * 32;
     uint8_t *s_code = smem6 + (size_t)R6_WARPS * 32 * (R6_CH + 1) * 8 + (per_row ? (size_t)R6_WARPS * 32 * 17 * 8 : 0) +
                       (size_t)warp * code_bytes;
     if (!per_row && tid < 16) {
         const double c = coefs[tid];
-        s_coef[tid] = (fabs(c) > drop_below) ? c : 0.0;
+        s_coef[tid] = (R)((fabs(c) > drop_below) ? c : 0.0);
     }
     if (dts && !dts_per_row)
         for (int k = tid; k < W; k += blockDim.x) s_dt[k] = dts[k];
@@ -235,21 +260,19 @@ ode_rollout_tiled_kernel(int64_t rows, int W, double dt, int substeps, const dou
         }
         if (per_row) {
             const double *g = coefs + first * 16;
-            for (int e = lane; e < nrows * 16; e += 32) s_cf[e >> 4][e & 15] = g[e];
+            for (int e = lane; e < nrows * 16; e += 32) {
+                const double cv = g[e];
+                s_cf[e >> 4][e & 15] = (R)((fabs(cv) > drop_below) ? cv : 0.0);
+            }
         }
-        __syncwarp();
-        R c[4][4];
         R v = (R)0, u = (R)0;
         if (live) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double cv = per_row ? s_cf[lane][j] : s_coef[j];
-                if (per_row) cv = (fabs(cv) > drop_below) ? cv : 0.0;
-                c[j >> 2][j & 3] = (R)cv;
-            }
             v = (R)x0[r];
             u = (R)static_feature[r];
         }
+        __syncwarp();
+        const R *ctab = per_row ? &s_cf[lane][0] : &s_coef[0];
+        const uint8_t *crow = s_code + (live ? lane : 0) * W;     // idle lanes walk row 0 (their results are never stored)
         for (int k0 = 0; k0 < W; k0 += R6_CH) {
             const int nc = (W - k0 < R6_CH) ? (W - k0) : R6_CH;
             if (dts && dts_per_row) {   // interval lengths of this chunk, (nrows, nc) row segments
@@ -260,14 +283,15 @@ ode_rollout_tiled_kernel(int64_t rows, int W, double dt, int substeps, const dou
                     for (int e = lane; e < nrows * nc; e += 32) s_io[e / nc][e % nc] = g[(int64_t)(e / nc) * W + (e % nc)];
                 __syncwarp();
             }
-            if (live) {
-                const uint8_t *cr = s_code + lane * W + k0;
-                for (int kk = 0; kk < nc; ++kk) {
-                    R h = h_uniform;
-                    if (dts) h = (R)((dts_per_row ? s_io[lane][kk] : s_dt[k0 + kk]) / substeps);
-                    v = euler_interval<R>(v, c, cr[kk] & 3, u, h, substeps);
-                    s_io[lane][kk] = (double)v;
-                }
+            const uint8_t *cr = crow + k0;
+#pragma unroll 4
+            for (int kk = 0; kk < nc; ++kk) {
+                const R *c = ctab + 4 * (cr[kk] & 3);   // the treatment's ODE (argmax of the one-hot, sindy.py:310 / :499)
+                const R c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+                R h = h_uniform;
+                if (dts) h = (R)((dts_per_row ? s_io[lane][kk] : s_dt[k0 + kk]) / substeps);
+                v = euler_steps<R, SUB>(v, c0, c1, r_mul(c2, u), c3, u, h, substeps);
+                s_io[lane][kk] = (double)v;
             }
             __syncwarp();
             double *g = pred + first * W + k0;
@@ -464,8 +488,11 @@ static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_
     if (W <= R6_MAXW) {
         const int code_bytes = (32 * W + 15) & ~15;
         const int smem = R6_WARPS * (32 * (R6_CH + 1) * 8 + (coefs_per_row ? 32 * 17 * 8 : 0) + code_bytes);
-        const void *kern = f32 ? reinterpret_cast<const void *>(ode_rollout_tiled_kernel<float>)
-                               : reinterpret_cast<const void *>(ode_rollout_tiled_kernel<double>);
+        const bool sub5 = substeps == 5;      // STEPS_FOR_DT of the reference (pkpd/utils.py:40): unrolled build
+        const void *kern = f32 ? (sub5 ? reinterpret_cast<const void *>(ode_rollout_tiled_kernel<float, 5>)
+                                       : reinterpret_cast<const void *>(ode_rollout_tiled_kernel<float, 0>))
+                               : (sub5 ? reinterpret_cast<const void *>(ode_rollout_tiled_kernel<double, 5>)
+                                       : reinterpret_cast<const void *>(ode_rollout_tiled_kernel<double, 0>));
         int per_sm = 1;
         {
             int rc0 = ensure_dyn_smem(kern, smem, R6_WARPS * 32, &per_sm);
@@ -476,12 +503,9 @@ static int ode_rollout_impl(bool f32, int64_t rows, int32_t W, double dt, int32_
         int64_t grid = (ntiles + R6_WARPS - 1) / R6_WARPS;
         const int64_t cap = (int64_t)num_sms() * per_sm;
         if (grid > cap) grid = cap;
-        if (f32)
-            ode_rollout_tiled_kernel<float><<<(unsigned)grid, R6_WARPS * 32, smem, st>>>(
-                rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, dts, dts_per_row, pred);
-        else
-            ode_rollout_tiled_kernel<double><<<(unsigned)grid, R6_WARPS * 32, smem, st>>>(
-                rows, W, dt, substeps, x0, static_feature, codes, coefs, coefs_per_row, drop_below, dts, dts_per_row, pred);
+        void *args[] = {&rows, &W, &dt, &substeps, &x0, &static_feature, &codes, &coefs, &coefs_per_row, &drop_below, &dts,
+                        &dts_per_row, &pred};
+        B200I_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(R6_WARPS * 32), args, (size_t)smem, st));
         return check_cuda(cudaGetLastError(), "ode_rollout launch");
     }
     const size_t smem = (size_t)RP * (W | 1) * sizeof(double);

@@ -14,9 +14,13 @@
 //       + lam*mean((theta-theta0)^2), xhat = open-loop Euler rollout (5 sub-steps per interval).
 //       16 lanes per row: lane j owns coefficient j, its forward sensitivity d xhat / d theta_j and
 //       row j of the inverse-Hessian approximation; dot products and mat-vecs go through half-warp
-//       shuffles.  Line search: strong Wolfe (c1=1e-4, c2=0.9) with bracketing + zoom as in
-//       jax.scipy.optimize / scipy (Nocedal & Wright alg. 3.5/3.6).  jax's iterate-level behaviour
-//       (in particular how its line search fails at the FP64 noise floor) is NOT pinned: see DESIGN.md.
+//       shuffles.  Line search: strong Wolfe (c1=1e-4, c2=0.9) with bracketing + zoom (Nocedal & Wright alg.
+//       3.5/3.6) in two flavours (include/b200i.h): B200I_LS_JAX restates jax.scipy.optimize's semantics including
+//       the way its zoom FAILS (signed bracket width <= 1e-10, 30 trials) and what a failed search leaves behind --
+//       with gtol = 1e-5 (jax ignores the reference's tol=1e-12) this reproduces both INSITE lines of the reference's
+//       logs (5e-15 and 2e-6 relative); B200I_LS_ROBUST accepts the best sufficient-decrease point at the FP64 noise
+//       floor and never returns a point worse than theta0.
+#include <stdlib.h>
 #include "sim_math.cuh"
 #include "stlsq.cuh"
 
@@ -72,6 +76,57 @@ __device__ __forceinline__ void ridge_prior_solve(const PatientGram &pg, double 
     }
 }
 
+// The same with the treatment loop kept as a loop (one copy of the solver in the instruction stream instead of four):
+// sums = the row's 4 x 5 per-treatment sums and out = its 16 coefficients, both in shared memory.
+__device__ __forceinline__ void ridge_prior_solve_rolled(const double *sums, double u, const double *s_prior,
+                                                         double support_tol, double lam, double threshold, int max_iter,
+                                                         double *out)
+{
+#pragma unroll 1
+    for (int a = 0; a < 4; ++a) {
+        double s5[5], g15[B200I_GRAM_PER_TREATMENT], G[4][4], b[4], c[4], pr[4];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) s5[m] = sums[a * 5 + m];
+        expand_gram(s5, u, g15);
+        unsigned ind = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            pr[j] = s_prior[a * 4 + j];
+            if (fabs(pr[j]) > support_tol) ind |= 1u << j;
+        }
+        const double cnt = g15[14];
+        if (cnt > 0.0 && ind != 0) {
+            const double inv = 1.0 / cnt;   // mean-normalised normal equations
+#pragma unroll
+            for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) g15[j] *= inv;
+            unpack_gram(g15, G, b);
+            for (int it = 0; it < max_iter; ++it) {
+                if (!solve_spd4(G, b, ind, lam, pr, c)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[j] = ((ind >> j) & 1u) ? pr[j] : 0.0;
+                    break;
+                }
+                unsigned big = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((ind >> j) & 1u) && fabs(c[j]) >= threshold) big |= 1u << j;
+                if (big == ind) break;
+                ind = big;
+                if (ind == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[j] = 0.0;
+                    break;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = pr[j];   // treatment never observed in the window: keep the prior
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[a * 4 + j] = c[j];
+    }
+}
+
 __global__ void __launch_bounds__(128)
 stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
                      const int *__restrict__ fit_len, const double *__restrict__ static_u,
@@ -118,7 +173,7 @@ constexpr int K5_CH = 16;
 constexpr int K5_MAXW = 128;
 
 template <typename X>
-__global__ void __launch_bounds__(K5_WARPS * 32)
+__global__ void __launch_bounds__(K5_WARPS * 32, 4)
 stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restrict__ x, const uint8_t *__restrict__ codes,
                            const int *__restrict__ fit_len, const double *__restrict__ static_u,
                            const double *__restrict__ prior, double support_tol, double lam, double threshold,
@@ -130,8 +185,13 @@ stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int code_bytes = (32 * W + 15) & ~15;
     double(*s_x)[K5_CH + 1] = reinterpret_cast<double(*)[K5_CH + 1]>(smem5) + (size_t)warp * 32;
-    double(*s_t)[K5_CH + 1] = reinterpret_cast<double(*)[K5_CH + 1]>(smem5 + (size_t)K5_WARPS * 32 * (K5_CH + 1) * 8) + (size_t)warp * 32;
-    uint8_t *s_code = smem5 + (size_t)2 * K5_WARPS * 32 * (K5_CH + 1) * 8 + (size_t)warp * code_bytes;
+    double(*s_t)[K5_CH + 1] = reinterpret_cast<double(*)[K5_CH + 1]>(
+                                  smem5 + (size_t)K5_WARPS * 32 * (K5_CH + 1) * 8 + (size_t)K5_WARPS * 32 * 21 * 8 +
+                                  (size_t)K5_WARPS * code_bytes) + (size_t)warp * 32;
+    // layout: [x tiles][per-row sums][code bytes][interval-length tiles, only with per-row dts]
+    double(*s_pg)[21] = reinterpret_cast<double(*)[21]>(smem5 + (size_t)K5_WARPS * 32 * (K5_CH + 1) * 8) + (size_t)warp * 32;
+    uint8_t *s_code = smem5 + (size_t)K5_WARPS * 32 * (K5_CH + 1) * 8 + (size_t)K5_WARPS * 32 * 21 * 8 +
+                      (size_t)warp * code_bytes;
     if (tid < 16) s_prior[tid] = prior[tid];
     if (dts && !dts_per_row)
         for (int k = tid; k < W; k += blockDim.x) s_dtg[k] = dts[k];
@@ -198,8 +258,17 @@ stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restric
                         const int a0 = cr[k] & 3;
                         const int a1 = cr[k + 1 < W ? k + 1 : k] & 3;
                         const double xdot = __ddiv_rn(__dsub_rn(xv, x0), dt_k);
-                        pg.add(a0, x0, xdot);
-                        if (k == n - 1 || a1 != a0) pg.add(a0, xv, xdot);
+                        // library row of the sample (x0) and, at the end of a constant-treatment snippet, of its last
+                        // point (x1, backward difference = the same slope), filed under treatment a0 in one go
+                        const double e = (k == n - 1 || a1 != a0) ? 1.0 : 0.0;
+                        const double cx = fma(e, xv, x0), cn = 1.0 + e;
+                        const double cxx = fma(e * xv, xv, x0 * x0), cd = xdot * cn, cxd = xdot * cx;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (a0 == a) {
+                                pg.s[a][0] += cn; pg.s[a][1] += cx; pg.s[a][2] += cxx; pg.s[a][3] += cd; pg.s[a][4] += cxd;
+                            }
+                        }
                     }
                     x0 = xv;
                     if (dts) dt_k = dts_per_row ? s_t[lane][jj] : s_dtg[j];   // length of the interval that starts at column j
@@ -207,13 +276,12 @@ stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restric
             }
             __syncwarp();
         }
-        double out16[16];
-        if (live) ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, out16);
-        __syncwarp();
-        if (live) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) s_x[lane][q] = out16[q];
-        }
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) s_pg[lane][a * 5 + m] = pg.s[a][m];
+        __syncwarp();
+        if (live) ridge_prior_solve_rolled(s_pg[lane], u, s_prior, support_tol, lam, threshold, max_iter, s_x[lane]);
         __syncwarp();
         double *go = coefs_out + first * 16;
         for (int e = lane; e < nrows * 16; e += 32) go[e] = s_x[e >> 4][e & 15];
@@ -419,7 +487,8 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                    const uint8_t *__restrict__ codes, const int *__restrict__ seq_len, int ph,
                    const double *__restrict__ static_u, const double *__restrict__ theta0_g, double lam, double gtol,
                    int max_iter, double *__restrict__ coefs_out, int *__restrict__ status_out,
-                   double *__restrict__ fval_out, const double *__restrict__ dts = nullptr, int dts_per_row = 0)
+                   double *__restrict__ fval_out, const double *__restrict__ dts = nullptr, int dts_per_row = 0,
+                   int ls_mode = 0)
 {
     __shared__ double s_x[BFGS_GROUPS][BFGS_MAXW + 1];
     __shared__ double s_dt[DTS ? BFGS_GROUPS : 1][BFGS_MAXW];
@@ -508,8 +577,9 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                 double a_prev = 0.0, phi_prev = phi0, dphi_prev = dphi0;
                 double cand = 1.01 * 2.0 * (phi0 - old_old) / dphi0;
                 double alpha = (cand > 1.0 || !(cand > 0.0)) ? 1.0 : cand;
+                if (ls_mode == 1) alpha = cand > 1.0 ? 1.0 : cand;      // jax: where(candidate > 1, 1.0, candidate)
                 double a_star = 0.0, f_star = f, g_star = g;
-                bool found = false, ls_failed = false;
+                bool found = false, ls_failed = false, zoom_failed = false;
                 double lo = 0, hi = 0, phi_lo = 0, dphi_lo = 0, phi_hi = 0;
                 bool need_zoom = false;
                 for (int i = 1; i <= 10; ++i) {
@@ -535,17 +605,23 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                     ls_failed = true;
                     for (int z = 0; z < 30; ++z) {
                         const double dalpha = hi - lo;
+                        // ls_mode 1: jax's _zoom declares failure when the SIGNED bracket width a_hi - a_lo is <= 1e-10
+                        // (float64), i.e. also at once for a reversed bracket (a_hi < a_lo); the iteration that notices
+                        // it still evaluates its trial point
+                        if (ls_mode == 1 && dalpha <= 1e-10) zoom_failed = true;
                         const double a_min = dalpha < 0 ? hi : lo, a_max = dalpha < 0 ? lo : hi;
                         double aj = nan("");
                         if (have_rec) {
                             const double cchk = 0.2 * dalpha;
                             aj = cubicmin(lo, phi_lo, dphi_lo, hi, phi_hi, a_rec, phi_rec);
-                            if (isnan(aj) || aj > a_max - fabs(cchk) || aj < a_min + fabs(cchk)) aj = nan("");
+                            if (ls_mode ? (isnan(aj) || !(aj > a_min + cchk) || !(aj < a_max - cchk))
+                                        : (isnan(aj) || aj > a_max - fabs(cchk) || aj < a_min + fabs(cchk))) aj = nan("");
                         }
                         if (isnan(aj)) {
                             const double qchk = 0.1 * dalpha;
                             aj = quadmin(lo, phi_lo, dphi_lo, hi, phi_hi);
-                            if (isnan(aj) || aj > a_max - fabs(qchk) || aj < a_min + fabs(qchk)) aj = lo + 0.5 * dalpha;
+                            if (ls_mode ? (isnan(aj) || !(aj > a_min + qchk) || !(aj < a_max - qchk))
+                                        : (isnan(aj) || aj > a_max - fabs(qchk) || aj < a_min + fabs(qchk))) aj = lo + 0.5 * dalpha;
                         }
                         double fj, gj;
                         objective(d, theta + aj * p, fj, gj);
@@ -559,6 +635,7 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                             }
                             if (dphi_j * (hi - lo) >= 0.0) {
                                 a_rec = hi; phi_rec = phi_hi; hi = lo; phi_hi = phi_lo;
+                                if (ls_mode) { a_rec = lo; phi_rec = phi_lo; }   // jax applies lo_to_j after hi_to_lo
                             } else {
                                 a_rec = lo; phi_rec = phi_lo;
                             }
@@ -567,14 +644,27 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                             // remember the best sufficient-decrease point in case the curvature test never passes
                             a_star = aj; f_star = fj; g_star = gj;
                         }
-                        if (fabs(hi - lo) <= 1e-16 * fmax(1.0, fabs(lo))) break;
+                        if (zoom_failed) break;
+                        if (ls_mode == 0 && fabs(hi - lo) <= 1e-16 * fmax(1.0, fabs(lo))) break;
                     }
+                }
+                if (ls_mode == 1 && need_zoom && (zoom_failed || !found)) {
+                    // jax: a failed zoom ends BFGS (status 3 = 2 + line-search status 1).  The state it leaves behind is
+                    // x + a p with a = the trial point if that happened to satisfy both Wolfe conditions, else the
+                    // initial a_star = 1 of _ZoomState; the reference (sindy.py:628-631) then discards it.
+                    const double a_left = found ? a_star : 1.0;
+                    theta += a_left * p;
+                    objective(d, theta, f, g);
+                    status = 3;
+                    ++it;                 // jax counts the iteration whose line search failed
+                    break;
                 }
                 if (!found) {
                     // line search exhausted (typically at the FP64 noise floor of the objective): accept the
                     // best sufficient-decrease point if it improves f, then stop
                     if (a_star > 0.0 && f_star < f) { theta += a_star * p; f = f_star; g = g_star; }
-                    status = ls_failed ? 3 : 5;
+                    status = (ls_mode == 1) ? 5 : (ls_failed ? 3 : 5);   // mode 1 gets here only from the bracketing phase
+                    if (ls_mode == 1) ++it;
                     break;
                 }
                 // ---- BFGS update of the inverse Hessian ---------------------------------------------
@@ -583,7 +673,8 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                 theta += s_k; old_old = f; f = f_star; g = g_star;
                 const double sy = sum16(s_k * y_k, gmask);
                 double rho = 1.0 / sy;
-                if (!isfinite(rho)) rho = 1000.0;   // jax: rho_k = where(isinf(rho_k), 1000, rho_k)
+                const bool keep_H = ls_mode == 1 && !isfinite(rho);   // jax: H_kp1 = where(isfinite(rho_k), H_kp1, H_k)
+                if (!isfinite(rho)) rho = keep_H ? 0.0 : 1000.0;
                 double Hy = 0.0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) Hy += Hrow[i] * shfl16(y_k, i, gmask, gbase);
@@ -594,10 +685,10 @@ insite_bfgs_kernel(int64_t rows, int W, double dt, int substeps, const double *_
                     const double s_i = shfl16(s_k, i, gmask, gbase), Hy_i = shfl16(Hy, i, gmask, gbase);
                     Hrow[i] = Hrow[i] - rho * (s_k * Hy_i + Hy * s_i) + coef * s_k * s_i;
                 }
-                if (fabs(f_old - f) <= 1e-15 * fmax(fabs(f), 1e-300)) { status = 0; ++it; break; }
+                if (ls_mode == 0 && fabs(f_old - f) <= 1e-15 * fmax(fabs(f), 1e-300)) { status = 0; ++it; break; }
             }
             if (it >= max_iter && status == 0) status = 1;
-            if (!(f <= f0) || !isfinite(f)) { theta = theta0; f = f0; status = 6; }   // never accept a worse point
+            if (ls_mode == 0 && (!(f <= f0) || !isfinite(f))) { theta = theta0; f = f0; status = 6; }   // never accept a worse point
         }
         if (j < NP) coefs_out[r * NP + j] = theta;
         if (j == 0) { status_out[r] = status | (it << 8); fval_out[2 * r] = f0; fval_out[2 * r + 1] = f; }
@@ -622,7 +713,8 @@ static int stlsq_batched_impl(int64_t rows, int32_t W, double fd_dt, const X *x,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (W <= K5_MAXW) {
         const int code_bytes = (32 * W + 15) & ~15;
-        const int smem = K5_WARPS * (2 * 32 * (K5_CH + 1) * 8 + code_bytes);
+        const int smem = K5_WARPS * (32 * (K5_CH + 1) * 8 + 32 * 21 * 8 + code_bytes +
+                                     ((dts && dts_per_row) ? 32 * (K5_CH + 1) * 8 : 0));
         const void *kern = reinterpret_cast<const void *>(stlsq_batched_tiled_kernel<X>);
         int per_sm = 1;
         {
@@ -671,10 +763,12 @@ extern "C" int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x,
 
 static int insite_bfgs_impl(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x, const uint8_t *codes,
                             const int32_t *sequence_lengths, int32_t projection_horizon, const double *static_feature,
-                            const double *theta0, double lam, double gtol, int32_t max_iter, const double *dts,
-                            int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out, void *stream)
+                            const double *theta0, double lam, double gtol, int32_t max_iter, int32_t line_search,
+                            const double *dts, int32_t dts_per_row, double *coefs_out, int32_t *status_out, double *fval_out,
+                            void *stream)
 {
     B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs: negative rows");
+    B200I_REQUIRE(line_search == B200I_LS_JAX || line_search == B200I_LS_ROBUST, B200I_E_ARG, "insite_bfgs: line_search %d", line_search);
     if (rows == 0) return 0;
     B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
                   B200I_E_ARG, "insite_bfgs: NULL argument");
@@ -688,42 +782,43 @@ static int insite_bfgs_impl(int64_t rows, int32_t W, double dt, int32_t substeps
     if (dts)
         insite_bfgs_kernel<K7_MINB_DEFAULT, false, false, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
             rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-            max_iter, coefs_out, status_out, fval_out, dts, dts_per_row);
+            max_iter, coefs_out, status_out, fval_out, dts, dts_per_row, line_search);
     else
         insite_bfgs_kernel<K7_MINB_DEFAULT, false><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
             rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-            max_iter, coefs_out, status_out, fval_out);
+            max_iter, coefs_out, status_out, fval_out, nullptr, 0, line_search);
     return check_cuda(cudaGetLastError(), "insite_bfgs launch");
 }
 
 extern "C" int b200i_insite_bfgs(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
                                  const uint8_t *codes, const int32_t *sequence_lengths, int32_t projection_horizon,
                                  const double *static_feature, const double *theta0, double lam, double gtol,
-                                 int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out,
-                                 void *stream)
+                                 int32_t max_iter, int32_t line_search, double *coefs_out, int32_t *status_out,
+                                 double *fval_out, void *stream)
 {
     return insite_bfgs_impl(rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0,
-                            lam, gtol, max_iter, nullptr, 0, coefs_out, status_out, fval_out, stream);
+                            lam, gtol, max_iter, line_search, nullptr, 0, coefs_out, status_out, fval_out, stream);
 }
 
 extern "C" int b200i_insite_bfgs_dts(int64_t rows, int32_t W, int32_t substeps, const double *x, const uint8_t *codes,
                                      const int32_t *sequence_lengths, int32_t projection_horizon,
                                      const double *static_feature, const double *theta0, double lam, double gtol,
-                                     int32_t max_iter, const double *dts, int32_t dts_per_row, double *coefs_out,
-                                     int32_t *status_out, double *fval_out, void *stream)
+                                     int32_t max_iter, int32_t line_search, const double *dts, int32_t dts_per_row,
+                                     double *coefs_out, int32_t *status_out, double *fval_out, void *stream)
 {
     B200I_REQUIRE(dts != nullptr, B200I_E_ARG, "insite_bfgs_dts: dts is NULL");
     return insite_bfgs_impl(rows, W, 0.0, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0,
-                            lam, gtol, max_iter, dts, dts_per_row, coefs_out, status_out, fval_out, stream);
+                            lam, gtol, max_iter, line_search, dts, dts_per_row, coefs_out, status_out, fval_out, stream);
 }
 
 extern "C" int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x,
                                        const uint8_t *codes, const int32_t *sequence_lengths,
                                        int32_t projection_horizon, const double *static_feature, const double *theta0,
-                                       double lam, double gtol, int32_t max_iter, double *coefs_out,
+                                       double lam, double gtol, int32_t max_iter, int32_t line_search, double *coefs_out,
                                        int32_t *status_out, double *fval_out, void *stream)
 {
     B200I_REQUIRE(rows >= 0, B200I_E_ARG, "insite_bfgs_joint: negative rows");
+    B200I_REQUIRE(line_search == B200I_LS_JAX || line_search == B200I_LS_ROBUST, B200I_E_ARG, "insite_bfgs_joint: line_search %d", line_search);
     if (rows == 0) return 0;
     B200I_REQUIRE(x && codes && sequence_lengths && static_feature && theta0 && coefs_out && status_out && fval_out,
                   B200I_E_ARG, "insite_bfgs_joint: NULL argument");
@@ -735,17 +830,18 @@ extern "C" int b200i_insite_bfgs_joint(int64_t rows, int32_t W, double dt, int32
     if (grid > cap) grid = cap;
     insite_bfgs_kernel<K7_MINB_DEFAULT, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         rows, W, dt, substeps, x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol,
-        max_iter, coefs_out, status_out, fval_out);
+        max_iter, coefs_out, status_out, fval_out, nullptr, 0, line_search);
     return check_cuda(cudaGetLastError(), "insite_bfgs_joint launch");
 }
 
 extern "C" int b200i_insite_bfgs_prefix(int64_t n, int32_t T, int32_t fit_offset, double dt, int32_t substeps,
                                         const double *factual, const uint8_t *codes, const int32_t *n_steps,
                                         const double *static_feature, const double *theta0, double lam, double gtol,
-                                        int32_t max_iter, double *coefs_out, int32_t *status_out, double *fval_out,
-                                        void *stream)
+                                        int32_t max_iter, int32_t line_search, double *coefs_out, int32_t *status_out,
+                                        double *fval_out, void *stream)
 {
     B200I_REQUIRE(n >= 0, B200I_E_ARG, "insite_bfgs_prefix: negative n");
+    B200I_REQUIRE(line_search == B200I_LS_JAX || line_search == B200I_LS_ROBUST, B200I_E_ARG, "insite_bfgs_prefix: line_search %d", line_search);
     if (n == 0) return 0;
     B200I_REQUIRE(factual && codes && n_steps && static_feature && theta0 && coefs_out && status_out && fval_out,
                   B200I_E_ARG, "insite_bfgs_prefix: NULL argument");
@@ -759,7 +855,7 @@ extern "C" int b200i_insite_bfgs_prefix(int64_t n, int32_t T, int32_t fit_offset
     if (grid > cap) grid = cap;
     insite_bfgs_kernel<K7_MINB_DEFAULT, false, true><<<(unsigned)grid, BFGS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         rows, T, dt, substeps, factual, codes, n_steps, fit_offset, static_feature, theta0, lam, gtol, max_iter, coefs_out,
-        status_out, fval_out);
+        status_out, fval_out, nullptr, 0, line_search);
     return check_cuda(cudaGetLastError(), "insite_bfgs_prefix launch");
 }
 

@@ -24,89 +24,7 @@ import numpy as np
 _EYE4 = np.vstack([np.eye(4), np.zeros((1, 4))])   # row 4 = all zero: a treatment pair that is not 0/1-valued
 
 
-class LazyDict(dict):
-    """The ``.data`` dictionary of a processed dataset.  The three (R, W, k) arrays that nothing on the SINDy / INSITE
-    path reads -- one-hot ``current_treatments``, ``prev_treatments``, ``current_covariates``: 3 of the 4 GB a
-    10k/1k/1k collection writes -- are built on first access.  Indexing, ``in``, ``get`` see them as ordinary keys;
-    anything that enumerates the dictionary (``keys``, ``items``, iteration, ``len``, pickling, ``dict(d)``) builds
-    them first, so consumers of the reference's dictionaries cannot tell the difference."""
-
-    def __init__(self, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        self._lazy = {}
-        self._on_set = {}
-
-    def set_lazy(self, key, fn):
-        dict.pop(self, key, None)
-        self._lazy[key] = fn
-
-    def on_set(self, key, fn):
-        """fn() is called when `key` is assigned from outside (cached views of it become invalid)."""
-        self._on_set[key] = fn
-
-    def materialise(self):
-        for k in list(self._lazy):
-            self[k]
-        return self
-
-    def __missing__(self, key):
-        if key not in self._lazy:
-            raise KeyError(key)
-        v = self._lazy.pop(key)()
-        dict.__setitem__(self, key, v)
-        return v
-
-    def __setitem__(self, key, value):
-        self._lazy.pop(key, None)
-        if key in self._on_set:
-            self._on_set[key]()
-        dict.__setitem__(self, key, value)
-
-    def __delitem__(self, key):
-        if self._lazy.pop(key, None) is None:
-            dict.__delitem__(self, key)
-
-    def __contains__(self, key):
-        return dict.__contains__(self, key) or key in self._lazy
-
-    def get(self, key, default=None):
-        return self[key] if key in self else default
-
-    def pop(self, key, *default):
-        if key in self._lazy:
-            self[key]
-        return dict.pop(self, key, *default)
-
-    def __iter__(self):
-        return dict.__iter__(self.materialise())
-
-    def __len__(self):
-        return dict.__len__(self) + len(self._lazy)
-
-    def keys(self):
-        return dict.keys(self.materialise())
-
-    def items(self):
-        return dict.items(self.materialise())
-
-    def values(self):
-        return dict.values(self.materialise())
-
-    def copy(self):
-        """Shallow copy that stays lazy (arrays and pending builders are shared)."""
-        new = LazyDict()
-        dict.update(new, dict.items(self))
-        new._lazy = dict(self._lazy)
-        new._on_set = dict(self._on_set)   # reassigning a watched key of the copy invalidates the cached views too
-        return new
-
-    def __reduce__(self):
-        return (dict, (dict(dict.items(self.materialise())),))
-
-    def __deepcopy__(self, memo):
-        from copy import deepcopy
-        return deepcopy(dict(dict.items(self.materialise())), memo)
-
+from .lazydict import LazyDict
 from .cancer_simulation import (TUMOUR_DEATH_THRESHOLD, generate_params, get_scaling_params, simulate_factual,
                                 simulate_counterfactual_1_step, simulate_counterfactuals_treatment_seq)
 
@@ -131,10 +49,12 @@ class SyntheticCancerDataset:
         if mode == 'factual':
             self.data = simulate_factual(self.params, seq_length)
         elif mode == 'counterfactual_one_step':
-            self.data = simulate_counterfactual_1_step(self.params, seq_length)
+            # lazy: the dense (R, T) rows stay on the device in compact form until something reads them
+            self.data = simulate_counterfactual_1_step(self.params, seq_length, lazy=True)
         elif mode == 'counterfactual_treatment_seq':
             assert projection_horizon is not None
-            self.data = simulate_counterfactuals_treatment_seq(self.params, seq_length, projection_horizon, cf_seq_mode)
+            self.data = simulate_counterfactuals_treatment_seq(self.params, seq_length, projection_horizon, cf_seq_mode,
+                                                               lazy=True)
         else:
             raise ValueError(f"unknown mode {mode!r}")
         self.processed = False
@@ -148,7 +68,15 @@ class SyntheticCancerDataset:
         return {k: v[index] for k, v in self.data.items() if hasattr(v, '__len__') and len(v) == len(self)}
 
     def __len__(self):
-        return self.data['outputs'].shape[0]      # = current_covariates.shape[0] (:86), without building that array
+        return self.data['sequence_lengths'].shape[0]   # = current_covariates.shape[0] (:86), without building that array
+
+    @property
+    def compact_(self):
+        """(CompactCohort, static feature on the device) of a counterfactual test set whose dictionaries have not been
+        tampered with, else None: what SINDY's RMSE methods evaluate instead of the dense rows."""
+        d = self.data_original if (self.processed_sequential and not self.processed_autoregressive) else self.data
+        attrs = getattr(d, 'attrs', None)
+        return attrs.get('compact') if attrs else None
 
     def get_scaling_params(self):
         return get_scaling_params(self.data)
@@ -159,6 +87,7 @@ class SyntheticCancerDataset:
         state = dict(self.__dict__)
         state.pop('_treatment_rows', None)
         state.pop('_covariate_rows', None)
+        state.pop('_treatment_codes', None)
         return state
 
     def _rows_of_treatments(self, rows, cols):
@@ -182,70 +111,94 @@ class SyntheticCancerDataset:
         cols = ['cancer_volume', 'patient_types', 'chemo_application', 'radio_application']
         input_means = mean[cols].values.flatten()
         input_stds = std[cols].values.flatten()
+        base = self.data
+        # counterfactual test sets arrive with their dense rows pending (counterfactual._lazy_dense): then every array
+        # derived from them is pending too, and reassigning any simulator output drops the compact cohort
+        lazy_big = isinstance(base, LazyDict) and base.pending('cancer_volume')
+        data = base.copy() if isinstance(base, LazyDict) else LazyDict(base)
+        mv, sv = mean['cancer_volume'], std['cancer_volume']
+        patient_types = np.asarray((base['patient_types'] - mean['patient_types']) / std['patient_types'])
+        seq_len = base['sequence_lengths']
+        R = seq_len.shape[0]
+        cache = {}
 
-        cancer_volume = (self.data['cancer_volume'] - mean['cancer_volume']) / std['cancer_volume']
-        patient_types = (self.data['patient_types'] - mean['patient_types']) / std['patient_types']
-        width = cancer_volume.shape[1]
-        patient_types = np.asarray(patient_types)
+        def scaled_volume():
+            if 'cv' not in cache:
+                cache['cv'] = (data['cancer_volume'] - mv) / sv
+            return cache['cv']
 
-        chemo = self.data['chemo_application']
-        radio = self.data['radio_application']
-        seq_len = self.data['sequence_lengths']
-        R = chemo.shape[0]
-        data = LazyDict(self.data)
+        def width():
+            return data['cancer_volume'].shape[1]
+
+        def put(key, fn):
+            if lazy_big:
+                data.set_lazy(key, fn)
+            else:
+                data[key] = fn()
+
         if self.treatment_mode == 'multiclass':
             # one_hot[..., a] = (c, r) == ((0,0), (1,0), (0,1), (1,1))[a]  (:131-141): a row of the identity table
-            c, r = chemo[:, :-1], radio[:, :-1]
-            idx = (c == 1).astype(np.int8) + 2 * (r == 1).astype(np.int8)
-            bad = ~(((c == 0) | (c == 1)) & ((r == 0) | (r == 1)))
-            if bad.any():
-                idx[bad] = 4
-            self._treatment_rows = lambda rows, cols: _EYE4[idx[rows, cols]]     # current_treatments[rows, cols, :]
-            data.set_lazy('current_treatments', lambda: _EYE4[idx])
+            def treatment_index():
+                if 'idx' not in cache:
+                    c, r = data['chemo_application'][:, :-1], data['radio_application'][:, :-1]
+                    idx = (c == 1).astype(np.int8) + 2 * (r == 1).astype(np.int8)
+                    bad = ~(((c == 0) | (c == 1)) & ((r == 0) | (r == 1)))
+                    if bad.any():
+                        idx[bad] = 4
+                    cache['idx'] = idx
+                return cache['idx']
+            self._treatment_rows = lambda rows, cols: _EYE4[treatment_index()[rows, cols]]   # current_treatments[rows, cols, :]
+            data.set_lazy('current_treatments', lambda: _EYE4[treatment_index()])
             # np.argmax(one_hot, -1) without the reduction (an all-zero row has argmax 0): read by SINDY
-            self.treatment_codes_ = np.where(idx == 4, 0, idx).astype(np.uint8)
-            data.on_set('current_treatments', lambda: setattr(self, 'treatment_codes_', None))
+            self._treatment_codes = lambda: np.where(treatment_index() == 4, 0, treatment_index()).astype(np.uint8)
+            self.treatment_codes_ = None if lazy_big else self._treatment_codes()
+            data.on_set('current_treatments', lambda: (setattr(self, 'treatment_codes_', None),
+                                                       setattr(self, '_treatment_codes', None)))
             k_tr = 4
         elif self.treatment_mode == 'multilabel':
             def treatments():
-                t = np.empty((R, width - 1, 2))
+                chemo, radio = data['chemo_application'], data['radio_application']
+                t = np.empty((R, width() - 1, 2))
                 t[..., 0] = chemo[:, :-1]
                 t[..., 1] = radio[:, :-1]
                 return t
-            self._treatment_rows = lambda rows, cols: np.stack([chemo[rows, cols], radio[rows, cols]], axis=-1)
+            self._treatment_rows = lambda rows, cols: np.stack([data['chemo_application'][rows, cols],
+                                                                data['radio_application'][rows, cols]], axis=-1)
             data.set_lazy('current_treatments', treatments)
             k_tr = 2
         else:
             raise ValueError(self.treatment_mode)
 
         def prev_treatments():   # zero row for t = 0, then current_treatments[:, :-1] (:141, :183-185)
-            p = np.zeros((R, width - 1, k_tr))
+            p = np.zeros((R, width() - 1, k_tr))
             p[:, 1:, :] = data['current_treatments'][:, :-1, :]
             return p
         data.set_lazy('prev_treatments', prev_treatments)
 
         def current_covariates():
-            cov = np.empty((R, width - 1, 2))
-            cov[..., 0] = cancer_volume[:, :-1]
+            cov = np.empty((R, width() - 1, 2))
+            cov[..., 0] = scaled_volume()[:, :-1]
             cov[..., 1] = patient_types[:, None]
             return cov
         data.set_lazy('current_covariates', current_covariates)
         self._covariate_rows = lambda rows, cols: np.stack(
-            [cancer_volume[rows, cols], np.broadcast_to(patient_types[rows], np.shape(cols))], axis=-1)
+            [scaled_volume()[rows, cols], np.broadcast_to(patient_types[rows], np.shape(cols))], axis=-1)
 
-        outputs = cancer_volume[:, 1:, np.newaxis]
         output_means = mean[['cancer_volume']].values.flatten()[0]
         output_stds = std[['cancer_volume']].values.flatten()[0]
-        active = (np.arange(outputs.shape[1])[None, :] < seq_len.astype(np.int64)[:, None]).astype(np.float64)
-
-        data['outputs'] = outputs
-        data['active_entries'] = active[:, :, None]
-        data['unscaled_outputs'] = outputs * std['cancer_volume'] + mean['cancer_volume']
+        put('outputs', lambda: scaled_volume()[:, 1:, np.newaxis])
+        put('active_entries', lambda: (np.arange(width() - 1)[None, :] < seq_len.astype(np.int64)[:, None])
+            .astype(np.float64)[:, :, None])
+        put('unscaled_outputs', lambda: data['outputs'] * sv + mv)
         self.scaling_params = {'input_means': input_means, 'inputs_stds': input_stds,
                                'output_means': output_means, 'output_stds': output_stds}
         # = current_covariates[:, :, :1] and current_covariates[:, 0, 1:] of the reference (:186-187), same values
-        data['prev_outputs'] = cancer_volume[:, :-1, np.newaxis]
+        put('prev_outputs', lambda: scaled_volume()[:, :-1, np.newaxis])
         data['static_features'] = patient_types[:, np.newaxis].copy()
+        if lazy_big:     # from here on, assigning any of these keys makes the compact cohort stale: it is dropped
+            data.watch_attrs(('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths', 'patient_types',
+                              'prev_outputs', 'outputs', 'unscaled_outputs', 'current_treatments', 'static_features',
+                              'active_entries'))
         self.data = data
         self.processed = True
         return self.data
@@ -259,30 +212,43 @@ class SyntheticCancerDataset:
         if self.processed_sequential:
             return self.data
         H = projection_horizon
-        seq_len = self.data['sequence_lengths'].astype(np.int64)
-        outputs = self.data['outputs']
-        R, W, _ = outputs.shape
+        full = self.data
+        seq_len = full['sequence_lengths'].astype(np.int64)
+        R = seq_len.shape[0]
         fact = seq_len - H
-        rows = np.arange(R)[:, None]
-        k = np.arange(H)[None, :]
-        # prev = prev_treatments[:, 1:] = current_treatments[:, :-1]  (W - 1 entries)
-        prev_idx = np.mod(fact[:, None] - 1 + k, W - 1)   # python slices with a negative start never occur (sl > H)
-        cov_last = self._rows_of_covariates(np.arange(R), fact - 1)                    # current_covariates[i, fact-1]
-        seq = {
-            'active_encoder_r': (np.arange(W - H)[None, :] < fact[:, None]).astype(np.float64),
-            'prev_treatments': self._rows_of_treatments(rows, prev_idx),
-            'current_treatments': self._rows_of_treatments(rows, fact[:, None] + k),
-            'current_covariates': np.repeat(cov_last[:, None, :], H, axis=1),
-            'outputs': outputs[rows, fact[:, None] + k, :],
-            'sequence_lengths': np.full(R, float(H)),
-            'active_entries': np.ones((R, H, 1)),
-        }
-        seq['prev_outputs'] = seq['current_covariates'][:, :, :1]
-        seq['static_features'] = seq['current_covariates'][:, 0, 1:]
-        seq['unscaled_outputs'] = seq['outputs'] * self.scaling_params['output_stds'] + self.scaling_params['output_means']
-        seq['patient_types'] = self.data['patient_types']
-        seq['patient_ids_all_trajectories'] = self.data['patient_ids_all_trajectories']
-        seq['patient_current_t'] = self.data['patient_current_t']
+        scaling = self.scaling_params
+
+        def build():
+            outputs = full['outputs']
+            W = outputs.shape[1]
+            rows = np.arange(R)[:, None]
+            k = np.arange(H)[None, :]
+            # prev = prev_treatments[:, 1:] = current_treatments[:, :-1]  (W - 1 entries)
+            prev_idx = np.mod(fact[:, None] - 1 + k, W - 1)   # python slices with a negative start never occur (sl > H)
+            cov_last = self._rows_of_covariates(np.arange(R), fact - 1)                    # current_covariates[i, fact-1]
+            out = {
+                'active_encoder_r': (np.arange(W - H)[None, :] < fact[:, None]).astype(np.float64),
+                'prev_treatments': self._rows_of_treatments(rows, prev_idx),
+                'current_treatments': self._rows_of_treatments(rows, fact[:, None] + k),
+                'current_covariates': np.repeat(cov_last[:, None, :], H, axis=1),
+                'outputs': outputs[rows, fact[:, None] + k, :],
+            }
+            out['prev_outputs'] = out['current_covariates'][:, :, :1]
+            out['static_features'] = out['current_covariates'][:, 0, 1:]
+            out['unscaled_outputs'] = out['outputs'] * scaling['output_stds'] + scaling['output_means']
+            return out
+        group = ('active_encoder_r', 'prev_treatments', 'current_treatments', 'current_covariates', 'outputs',
+                 'prev_outputs', 'static_features', 'unscaled_outputs')
+        seq = LazyDict()
+        if isinstance(full, LazyDict) and full.pending('cancer_volume'):
+            seq.set_lazy_group(group, build)      # built when somebody reads the sliced rows (the compact path does not)
+        else:
+            seq.update(build())
+        seq['sequence_lengths'] = np.full(R, float(H))
+        seq['active_entries'] = np.ones((R, H, 1))
+        seq['patient_types'] = full['patient_types']
+        seq['patient_ids_all_trajectories'] = full['patient_ids_all_trajectories']
+        seq['patient_current_t'] = full['patient_current_t']
         self.data_original = self.data.copy()    # the reference deep-copies (:470); arrays are shared here
         self.data = seq
         self.processed_sequential = True

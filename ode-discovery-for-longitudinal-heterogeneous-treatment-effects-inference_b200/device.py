@@ -415,12 +415,30 @@ def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3,
     return out
 
 
-def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol=1e-12,
-                max_iter=200, dt=STANDARD_DT, substeps=STEPS_FOR_DT, joint=False, dts=None):
+LINE_SEARCH = {'robust': 0, 'jax': 1}      # B200I_LS_ROBUST / B200I_LS_JAX
+JAX_GTOL = 1e-5                            # minimize_bfgs' default: jax.scipy.optimize.minimize does not forward `tol`
+
+
+def _bfgs_options(line_search, gtol, max_iter, n_coefs):
+    """Defaults of the two line-search flavours: 'jax' = what the reference's minimize(..., method='BFGS', tol=1e-12)
+    really runs (gtol 1e-5, maxiter 200 * n); 'robust' = tight tolerance, best-point acceptance."""
+    mode = LINE_SEARCH[line_search]
+    if gtol is None:
+        gtol = JAX_GTOL if mode == 1 else 1e-12
+    if max_iter is None:
+        max_iter = 200 * n_coefs if mode == 1 else 200
+    return mode, float(gtol), int(max_iter)
+
+
+def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, theta0, lam, gtol=None,
+                max_iter=None, dt=STANDARD_DT, substeps=STEPS_FOR_DT, joint=False, dts=None, line_search='jax'):
     """K7.  Returns (coefs (R,4,4) [joint: (R,11)], status (R,) int32, fval (R,2)).
+    line_search: 'jax' (the reference's optimiser, restated; status 3 rows are the ones sindy.py:628-631 replaces by
+    theta0) or 'robust'; gtol / max_iter default per flavour (see _bfgs_options).
     dts: interval lengths (W,) or (R,W) for an irregular time grid (per-treatment models)."""
     lib = _native.load()
     rows, W = x.shape
+    mode, gtol, max_iter = _bfgs_options(line_search, gtol, max_iter, 11 if joint else 16)
     if dts is not None:
         assert not joint, "irregular grids are implemented for the per-treatment models"
         dp, dper = _dts_args(dts, rows, W)
@@ -429,7 +447,7 @@ def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, 
         fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
         rc = lib.b200i_insite_bfgs_dts(rows, W, int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
                                        int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
-                                       int(max_iter), dp, dper, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+                                       int(max_iter), mode, dp, dper, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
         _native.check(rc, "b200i_insite_bfgs_dts")
         return coefs, status, fval
     if joint:
@@ -438,7 +456,7 @@ def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, 
         fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
         rc = lib.b200i_insite_bfgs_joint(rows, W, float(dt), int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
                                          int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam),
-                                         float(gtol), int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+                                         float(gtol), int(max_iter), mode, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
         _native.check(rc, "b200i_insite_bfgs_joint")
         return coefs, status, fval
     coefs = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
@@ -446,7 +464,7 @@ def insite_bfgs(x, codes, sequence_lengths, projection_horizon, static_feature, 
     fval = torch.empty((rows, 2), dtype=torch.float64, device='cuda')
     rc = lib.b200i_insite_bfgs(rows, W, float(dt), int(substeps), _ptr(x), _ptr(codes), _ptr(sequence_lengths),
                                int(projection_horizon), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
-                               int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+                               int(max_iter), mode, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
     _native.check(rc, "b200i_insite_bfgs")
     return coefs, status, fval
 
@@ -536,18 +554,19 @@ def cf_eval_treatment_seq(factual, codes, cf, valid, n_steps, static_feature, co
     return sums
 
 
-def insite_bfgs_prefix(factual, codes, n_steps, static_feature, theta0, lam, fit_offset, gtol=1e-12, max_iter=200,
-                       dt=STANDARD_DT, substeps=STEPS_FOR_DT):
+def insite_bfgs_prefix(factual, codes, n_steps, static_feature, theta0, lam, fit_offset, gtol=None, max_iter=None,
+                       dt=STANDARD_DT, substeps=STEPS_FOR_DT, line_search='jax'):
     """K7 per (patient, t) of a compact cohort: fit window = the first t + fit_offset transitions of the factual
     trajectory.  Returns (coefs (n,T-1,4,4), status (n,T-1) int32, fval (n,T-1,2))."""
     lib = _native.load()
     n, T = factual.shape
+    mode, gtol, max_iter = _bfgs_options(line_search, gtol, max_iter, 16)
     coefs = torch.empty((n, T - 1, 4, 4), dtype=torch.float64, device='cuda')
     status = torch.empty((n, T - 1), dtype=torch.int32, device='cuda')
     fval = torch.empty((n, T - 1, 2), dtype=torch.float64, device='cuda')
     rc = lib.b200i_insite_bfgs_prefix(n, T, int(fit_offset), float(dt), int(substeps), _ptr(factual), _ptr(codes),
                                       _ptr(n_steps), _ptr(static_feature), _ptr(theta0), float(lam), float(gtol),
-                                      int(max_iter), _ptr(coefs), _ptr(status), _ptr(fval), _stream())
+                                      int(max_iter), mode, _ptr(coefs), _ptr(status), _ptr(fval), _stream())
     _native.check(rc, "b200i_insite_bfgs_prefix")
     return coefs, status, fval
 

@@ -80,13 +80,15 @@ class SINDY:
         self.sindy_quantize_global_model_round_to = m.sindy_quantize_global_model_round_to
         self.lam = m.lam
         self.joint_model = m.joint_model
-        # The reference discards a row's BFGS result when jax reports a failed zoom (status 3, sindy.py:628-631).  Which
-        # rows that hits is internal to jax's line search (un-vendored, parity unpinned at the iterate level); the rows
-        # where THIS line search is exhausted at the FP64 noise floor are the candidates.  Each model's default is the
-        # variant its own committed log line supports: per-treatment models keep the progress (RMSEs 7e-4 from
-        # final_with_insite.txt:2362; falling back would be 34 % off), the joint model falls back (5.5e-4 from the
-        # one_ode ablation log :6; keeping the progress gives 6 % lower errors than the reference reports).
-        self.zoom_failure_fallback = bool(m.get('insite_zoom_failure_fallback', bool(m.joint_model)))
+        # INSITE's optimiser = jax.scipy.optimize.minimize(method='BFGS', tol=1e-12) (sindy.py:627), restated in K7 with
+        # jax's own semantics: `tol` is not forwarded (gtol stays 1e-5, maxiter 200 * n), and a zoom that fails (signed
+        # bracket width <= 1e-10, or 30 trials) ends BFGS with status 3.  The reference's CURRENT code replaces those
+        # rows' coefficients by the population's (:628-631) -- the default here, which reproduces the joint-model log
+        # of 2023-05-16 (results/ablation/one_ode/...txt:6) to 2e-6.  The main-table log of 2023-05-14
+        # (results/2_main_table/final_with_insite.txt:2362) was written by the revision before that fallback existed (the
+        # commented-out line :632, `res.x` always): insite_zoom_failure_fallback=False reproduces it to 5e-15.
+        self.zoom_failure_fallback = bool(m.get('insite_zoom_failure_fallback', True))
+        self.insite_line_search = str(m.get('insite_line_search', 'jax'))
         self.insite = m.insite
         self.wsindy = m.wsindy
         self.use_smoothed_finite_difference = m.use_smoothed_finite_difference
@@ -95,6 +97,11 @@ class SINDY:
         self.insight_recover_parametric_dist = m.insight_recover_parametric_dist
         self.treatment_mode = args.dataset.treatment_mode
         self.dim_one_hot_treatments = self.dim_treatments
+        # counterfactual test sets of this package carry their device-resident compact cohort: the two RMSE methods then
+        # evaluate it directly (compact_eval.py; one fit per (patient, t), no dense rows) unless this is switched off
+        self.compact_evaluation = bool(m.get('compact_evaluation', True))
+        self.insite_gtol = m.get('insite_gtol', None)            # None = the line-search flavour's default
+        self.insite_max_iter = m.get('insite_max_iter', None)
         self.individualisation = getattr(m, 'individualisation', 'bfgs_rollout')
         self.ridge_prior_lam = getattr(m, 'ridge_prior_lam', 1e4)
         self.last_fit_info = {}
@@ -140,6 +147,9 @@ class SINDY:
             # one-hot encoding is built from (and drop it when 'current_treatments' is reassigned), so neither the
             # 1.2 GB one-hot array of a 10k/1k/1k collection nor its argmax (0.4 s) is needed here
             cached = getattr(dataset, 'treatment_codes_', None)
+            codes_fn = getattr(dataset, '_treatment_codes', None)
+            if cached is None and codes_fn is not None:
+                cached = codes_fn()
             if cached is not None and cached.shape == prev.shape:
                 codes = cached
             else:
@@ -230,7 +240,8 @@ class SINDY:
         W = prev.shape[1]
         if self.individualisation == 'bfgs_rollout':
             coefs, status, fval = dev.insite_bfgs(x, cd, dev.to_device(seq, dtype=torch.int32), projection_horizon,
-                                                  st, theta0, lam=self.lam, gtol=1e-12, joint=bool(self.joint_model))
+                                                  st, theta0, lam=self.lam, gtol=self.insite_gtol, max_iter=self.insite_max_iter,
+                                                  joint=bool(self.joint_model), line_search=self.insite_line_search)
             if self.zoom_failure_fallback:
                 # sindy.py:628-631: "if zoom fails, fall back to default value" (res.status == 3 -> population coefficients)
                 failed = (status & 255) == 3
@@ -279,7 +290,41 @@ class SINDY:
         return scaled[np.arange(R)[:, None], idx, :]
 
     # -- metrics (time_varying_model.py:236-313) -------------------------------------------------------
+    def _compact_metrics(self, dataset, kind):
+        """The RMSEs of a counterfactual test set from its compact cohort (None when the dense path has to run: no
+        compact cohort, switched off, or INSITE on the joint model)."""
+        compact = getattr(dataset, 'compact_', None) if self.compact_evaluation else None
+        if compact is None or compact[0].kind != kind or (self.joint_model and self.insite):
+            return None
+        from . import compact_eval as ce
+        cohort, static = compact
+        unscale = self.hparams.exp.unscale_rmse
+        scale = 1.0 if unscale else float(dataset.scaling_params['output_stds'])
+        theta0 = dev.to_device(self.rollout_coefs_ if self.joint_model else self.joint_coefs)
+        if self.insite:
+            coefs, diag = ce.individualise(cohort, static, theta0, self.individualisation, self.lam, self.ridge_prior_lam,
+                                           self.sindy_threshold, self.zoom_failure_fallback, self.dt, gtol=self.insite_gtol,
+                                           max_iter=self.insite_max_iter, line_search=self.insite_line_search)
+            if 'status' in diag:
+                st_np = diag['status'].cpu().numpy()
+                ok = st_np >= 0
+                self.last_fit_info = {'estimator': 'bfgs_rollout', 'fits': int(ok.sum()), 'rows_covered': int(cohort.total_rows),
+                                      'status_low_byte': np.bincount(st_np[ok] & 0xff, minlength=8),
+                                      'iterations_mean': float((st_np[ok] >> 8).mean()) if ok.any() else 0.0}
+            drop = -1.0
+        else:
+            coefs, drop = theta0, (-1.0 if self.joint_model else 1e-3)
+        sums = ce._finish(ce.evaluate(cohort, static, coefs, drop, self.dt))
+        pct = self.hparams.exp.percentage_rmse
+        if kind == 'one_step':
+            return ce.one_step_rmses(sums, cohort.T - 1, dataset.norm_const, pct, scale)
+        return ce.n_step_rmses(sums, cohort.H, dataset.norm_const, pct, scale)
+
     def get_normalised_masked_rmse(self, dataset, one_step_counterfactual=False):
+        if one_step_counterfactual:
+            fast = self._compact_metrics(dataset, 'one_step')
+            if fast is not None:
+                return fast
         outputs_scaled = self.get_predictions(dataset)
         unscale = self.hparams.exp.unscale_rmse
         percentage = self.hparams.exp.percentage_rmse
@@ -308,6 +353,10 @@ class SINDY:
 
     def get_normalised_n_step_rmses(self, dataset, datasets_mc=None):
         assert hasattr(dataset, 'data_processed_seq')
+        if datasets_mc is None:
+            fast = self._compact_metrics(dataset, 'treatment_seq')
+            if fast is not None:
+                return fast
         unscale = self.hparams.exp.unscale_rmse
         percentage = self.hparams.exp.percentage_rmse
         outputs_scaled = self.get_autoregressive_predictions(dataset if datasets_mc is None else datasets_mc)

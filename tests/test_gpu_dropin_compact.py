@@ -1,0 +1,114 @@
+"""GPU tests of the drop-in classes on device-resident counterfactual test sets (BASELINE config C1 without the dense
+round trip): the dictionaries of simulate_counterfactual_* keep their dense (R, width) arrays pending, every array
+process_data / process_sequential_test derive from them stays pending too, and SINDY's two RMSE methods evaluate the
+compact cohort.  Anything that reads a dense key gets the reference's arrays (bit-identical to the eager path); anything
+that reassigns one drops the compact cohort and the dense path runs."""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+RMSE_KEYS = ('encoder_test_rmse_all', 'encoder_test_rmse_orig', 'encoder_test_rmse_last') + \
+    tuple(f'decoder_test_rmse_{k}-step' for k in range(2, 7))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from b200_insite import device
+    device.require_cuda()
+    return device
+
+
+def _collection(seed=1, sizes=(1000, 100, 100), mode='multiclass'):
+    from b200_insite.dataset import SyntheticCancerDatasetCollection
+    col = SyntheticCancerDatasetCollection(2.0, 2.0, {'train': sizes[0], 'val': sizes[1], 'test': sizes[2]}, seed=seed,
+                                           treatment_mode=mode)
+    col.process_data_multi()
+    return col
+
+
+def test_lazy_dictionaries_hold_the_reference_arrays(dev):
+    import b200_insite.cancer_simulation as cs
+    for kind in ('one', 'seq'):
+        np.random.seed(5)
+        p = cs.generate_params(37, 2.0, 2.0, 15, 0)
+        state = np.random.get_state()
+        eager = cs.simulate_counterfactual_1_step(p, 60) if kind == 'one' else cs.simulate_counterfactuals_treatment_seq(p, 60, 5)
+        np.random.set_state(state)
+        lazy = cs.simulate_counterfactual_1_step(p, 60, lazy=True) if kind == 'one' else \
+            cs.simulate_counterfactuals_treatment_seq(p, 60, 5, lazy=True)
+        assert lazy.pending('cancer_volume') and lazy.attrs['compact'][0].total_rows == eager['cancer_volume'].shape[0]
+        for k in ('sequence_lengths', 'patient_types') + (() if kind == 'one' else ('patient_ids_all_trajectories', 'patient_current_t')):
+            assert not lazy.pending(k) and lazy[k].dtype == eager[k].dtype and np.array_equal(lazy[k], eager[k]), k
+        assert lazy.pending('chemo_application')
+        assert set(lazy.keys()) == set(eager.keys())            # enumerating builds the dense arrays (one expansion)
+        for k in eager:
+            assert np.array_equal(lazy[k], eager[k]), k
+        assert not lazy.pending('cancer_volume')
+
+
+def test_class_metrics_from_the_compact_cohorts_equal_the_dense_path(dev):
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    log = h.load_json('ref_log_seed1.json')['sindy']
+    col = _collection()
+    one, seq = col.test_cf_one_step, col.test_cf_treatment_seq
+    assert one.compact_ is not None and seq.compact_ is not None
+    assert len(one) == 22748 and len(seq) == 56239
+    res, model = run_experiment(default_config(insite=False), col)
+    # nothing on the way read a dense row
+    assert one.data.pending('cancer_volume') and one.data.pending('prev_outputs') and seq.data.pending('outputs')
+    assert seq.data_processed_seq.pending('unscaled_outputs')
+    ref = [log['encoder_test_rmse_all'], log['encoder_test_rmse_orig'], log['encoder_test_rmse_last']] + \
+        list(log['decoder_test_rmse_2_to_6_step'])
+    np.testing.assert_allclose([res[k] for k in RMSE_KEYS], ref, rtol=1e-9)
+    # the dense path on the same collection (materialises the rows)
+    res_d, _ = run_experiment(default_config(insite=False, compact_evaluation=False), col)
+    assert not one.data.pending('cancer_volume') and not seq.data_processed_seq.pending('unscaled_outputs')
+    np.testing.assert_allclose([res_d[k] for k in RMSE_KEYS], [res[k] for k in RMSE_KEYS], rtol=1e-10)
+    # reassigning a key of the processed dictionary makes the compact cohort stale: it is dropped
+    one.data['outputs'] = one.data['outputs'].copy()
+    assert one.compact_ is None and seq.compact_ is not None
+    res_t, _ = run_experiment(default_config(insite=False), col)
+    np.testing.assert_allclose([res_t[k] for k in RMSE_KEYS], [res[k] for k in RMSE_KEYS], rtol=1e-10)
+
+
+def test_insite_class_metrics_compact_vs_dense(dev):
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    ins = h.load_json('ref_log_seed1.json')['insite']
+    col = _collection()
+    res, model = run_experiment(default_config(insite=True, insite_zoom_failure_fallback=False), col)
+    assert col.test_cf_one_step.data.pending('cancer_volume')
+    assert model.last_fit_info['fits'] < 6000 and model.last_fit_info['rows_covered'] == 56239
+    ref = [ins['encoder_test_rmse_all'], ins['encoder_test_rmse_orig'], ins['encoder_test_rmse_last']] + \
+        list(ins['decoder_test_rmse_2_to_6_step'])
+    np.testing.assert_allclose([res[k] for k in RMSE_KEYS], ref, rtol=1e-9)
+    res_d, _ = run_experiment(default_config(insite=True, insite_zoom_failure_fallback=False, compact_evaluation=False), col)
+    # same estimator on the same fit problems; the dense rows carry the scaling round trip (x - mu) / sigma * sigma + mu
+    np.testing.assert_allclose([res_d[k] for k in RMSE_KEYS], [res[k] for k in RMSE_KEYS], rtol=1e-6)
+    for fb in (True, False):      # the fallback of the reference's current code, both paths
+        a, _ = run_experiment(default_config(insite=True, insite_zoom_failure_fallback=fb), col)
+        b, _ = run_experiment(default_config(insite=True, insite_zoom_failure_fallback=fb, compact_evaluation=False), col)
+        np.testing.assert_allclose([a[k] for k in RMSE_KEYS], [b[k] for k in RMSE_KEYS], rtol=1e-6)
+    # north-star estimator (ridge-to-prior STLSQ, one fit per (patient, t) by running sums)
+    cfg = default_config(insite=True, individualisation='ridge_prior_stlsq')
+    r1, _ = run_experiment(cfg, col)
+    r2, _ = run_experiment(default_config(insite=True, individualisation='ridge_prior_stlsq', compact_evaluation=False), col)
+    np.testing.assert_allclose([r1[k] for k in RMSE_KEYS], [r2[k] for k in RMSE_KEYS], rtol=1e-8)
+
+
+def test_joint_model_population_metrics_from_compact_cohorts(dev):
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    log = h.load_json('ref_log_joint_seed10.json')
+    col = _collection(seed=log['seed'], mode='multilabel')
+    res, model = run_experiment(default_config(insite=False, joint_model=True, treatment_mode='multilabel'), col)
+    assert col.test_cf_one_step.data.pending('cancer_volume')
+    res_d, _ = run_experiment(default_config(insite=False, joint_model=True, treatment_mode='multilabel',
+                                             compact_evaluation=False), col)
+    np.testing.assert_allclose([res[k] for k in RMSE_KEYS], [res_d[k] for k in RMSE_KEYS], rtol=1e-10)

@@ -149,7 +149,7 @@ def test_irregular_rollout_and_fits_match_the_numpy_restatement(dev, cohort, per
     coefs, status, fval = dev.insite_bfgs(x[:n7].contiguous(), cd[:n7].contiguous(),
                                           dev.to_device(c['seq'][:n7], dtype=torch.int32), 1, u[:n7].contiguous(),
                                           dev.to_device(theta0), 10.0,
-                                          dts=dts[:n7].contiguous() if per_row else dts)
+                                          dts=dts[:n7].contiguous() if per_row else dts, line_search='robust')
     coefs, fval = coefs.cpu().numpy(), fval.cpu().numpy()
     from scipy.optimize import minimize
     for r in range(n7):
