@@ -73,13 +73,12 @@ B200I_API int b200i_device_sms(int *sms_out);
  * out: nine (N,T) arrays + sequence_lengths (N,), keys of the dict at :356-367.  Every element of
  *      every output is written (zeros included) -- buffers need not be pre-zeroed.
  * variant: 0 = auto: the lean tiled kernel (csrc/sim_factual_ws.cuh) when T is even and all (N,T) pointers are
- *      16 B aligned -- one 16-column box per chunk when rows start on 128-byte lines (pitched entry point), two
- *      otherwise -- else the generic kernel; 1 = generic thread-per-patient kernel (odd T, assigned_actions);
- *      2-9 = first-generation TMA tile shapes; 10-13, 16, 17 = explicit shapes of the lean kernel; 14, 15 = its
- *      experimental line-aligned row-class mapping; 20-25 = data-movement-only builds (profiling aid: outputs are
- *      copies of the draws).  See csrc/sim_factual.cu::dispatch_tma.
+ *      16 B aligned -- one 16-column box per chunk when rows start on 128-byte lines (pitched entry point, = 12), two
+ *      otherwise (= 10) -- else the generic kernel; 1 = generic thread-per-patient kernel (odd T, assigned_actions);
+ *      2 = the first-generation TMA kernel (cross-check); 20, 21 = data-movement-only builds of 10 / 12 (profiling aid:
+ *      outputs are copies of the draws).  See csrc/sim_factual.cu::dispatch_tma.
  * gram_workspace: NULL, or a workspace of b200i_gram_workspace_bytes() bytes: the kernel then also
- *      accumulates the population statistics of K4 on the fly (fused theta_gram; variants 1-9, 10, 12, 16, 17) and
+ *      accumulates the population statistics of K4 on the fly (fused theta_gram; variants 1, 2, 10, 12) and
  *      leaves the reduced result in the first B200I_STATS_DOUBLES doubles of the workspace.  Measured slower than
  *      the two separate launches on B200 (2.0 vs 1.2 + 0.5 ms at 1M patients), so the pipeline does not use it.
  * ---------------------------------------------------------------------------------------------- */
@@ -469,6 +468,13 @@ B200I_API int b200i_stlsq_prefix(int64_t n, int32_t T, int32_t fit_offset, doubl
  * two-point grid, pkpd/utils.py:759-828).
  * b200i_stlsq_batched_dts also offers FP32 STORAGE of the volumes (x_f32 instead of x; arithmetic stays FP64,
  * SURVEY.md App. E.5): pass exactly one of x / x_f32; dts may be NULL (uniform fd_dt).
+ * estimator: 0 = ridge-to-prior (b200i_stlsq_batched); 1 = the ridge / threshold loop of the reference's dormant
+ * per-patient optimiser LSQIntialMask (pkpd/utils.py:244-327, used at pkpd_simulation.py:778-836): `prior` only
+ * supplies the initial support |prior| > support_tol (the reference: 1e-14, :251-253), every ridge step solves
+ * (Theta^T Theta + lam I) c = Theta^T xdot on the current support (sklearn ridge_regression, :228; lam = alpha), then
+ * thresholds.  That is the reference's estimator WITHOUT pysindy's unbias refit -- the branch pkpd_simulation.py:795-797
+ * keeps when the unbiased coefficients overflow; the refit itself is an OLS on a per-patient design that is rank
+ * deficient by construction (the static feature is constant within a patient) and is not offered.
  * ---------------------------------------------------------------------------------------------- */
 B200I_API int b200i_ode_rollout_dts(int64_t rows, int32_t W, int32_t substeps, const double *x0,
                            const double *static_feature, const uint8_t *codes, const double *coefs,
@@ -477,7 +483,7 @@ B200I_API int b200i_ode_rollout_dts(int64_t rows, int32_t W, int32_t substeps, c
 B200I_API int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x, const float *x_f32, const uint8_t *codes,
                            const int32_t *fit_len, const double *static_feature, const double *prior,
                            double support_tol, double lam, double threshold, int32_t max_iter, double fd_dt,
-                           const double *dts, int32_t dts_per_row, double *coefs_out, void *stream);
+                           const double *dts, int32_t dts_per_row, int32_t estimator, double *coefs_out, void *stream);
 B200I_API int b200i_insite_bfgs_dts(int64_t rows, int32_t W, int32_t substeps, const double *x, const uint8_t *codes,
                            const int32_t *sequence_lengths, int32_t projection_horizon, const double *static_feature,
                            const double *theta0, double lam, double gtol, int32_t max_iter, int32_t line_search,

@@ -77,7 +77,7 @@ SIGNATURES = {
     "b200i_stlsq_prefix": (ctypes.c_int, [c_i64, c_i32, c_i32, c_f64] + [c_vp] * 5 + [c_f64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "b200i_ode_rollout_dts": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f64, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "b200i_stlsq_batched_dts": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 6 + [c_f64, c_f64, c_f64, c_i32, c_f64, c_vp, c_i32,
-                                                                             c_vp, c_vp]),
+                                                                             c_i32, c_vp, c_vp]),
     "b200i_insite_bfgs_dts": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_f64, c_f64, c_i32,
                                              c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200i_theta_gram_dts": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 6 + [c_i32, c_vp, c_vp]),

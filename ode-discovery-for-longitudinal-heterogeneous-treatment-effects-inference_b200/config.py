@@ -39,4 +39,5 @@ def default_config(insite=True, gamma=2.0, seed=1, n_train=1000, n_val=100, n_te
                         num_patients=dict(train=n_train, val=n_val, test=n_test), window_size=15, lag=0,
                         max_seq_length=60, projection_horizon=5, cf_seq_mode='sliding_treatment',
                         val_batch_size=512, treatment_mode=treatment_mode),
-        'exp': dict(seed=seed, unscale_rmse=True, percentage_rmse=True, logging=False)})
+        'exp': dict(seed=seed, unscale_rmse=True, percentage_rmse=True, logging=False),
+        'force_recache': False, 'load_from_cache': False})

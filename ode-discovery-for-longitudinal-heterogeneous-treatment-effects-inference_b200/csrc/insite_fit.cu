@@ -30,8 +30,13 @@ namespace b200i {
 // K5b
 // ------------------------------------------------------------------------------------------------
 // ridge-to-prior STLSQ of one row from its per-treatment sums (see b200i_stlsq_batched in include/b200i.h)
+// estimator 0: ridge shrunk to the prior on mean-normalised normal equations (north-star estimator).
+// estimator 1: the ridge / threshold loop of the reference's dormant LSQIntialMask (pkpd/utils.py:244-327): the prior only
+//              supplies the initial support (:251-253), the ridge pulls towards ZERO on the un-normalised normal
+//              equations (sklearn ridge_regression, :228) -- i.e. what pkpd_simulation.py:795-797 keeps (unbias=False).
 __device__ __forceinline__ void ridge_prior_solve(const PatientGram &pg, double u, const double *s_prior, double support_tol,
-                                                  double lam, double threshold, int max_iter, double *__restrict__ out16)
+                                                  double lam, double threshold, int max_iter, double *__restrict__ out16,
+                                                  int estimator = 0)
 {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -45,12 +50,12 @@ __device__ __forceinline__ void ridge_prior_solve(const PatientGram &pg, double 
         }
         const double cnt = g15[14];
         if (cnt > 0.0 && ind != 0) {
-            const double inv = 1.0 / cnt;   // mean-normalised normal equations
+            const double inv = estimator == 1 ? 1.0 : 1.0 / cnt;   // mean-normalised normal equations
 #pragma unroll
             for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) g15[j] *= inv;
             unpack_gram(g15, G, b);
             for (int it = 0; it < max_iter; ++it) {
-                if (!solve_spd4(G, b, ind, lam, pr, c)) {
+                if (!solve_spd4(G, b, ind, lam, estimator == 1 ? nullptr : pr, c)) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) c[j] = ((ind >> j) & 1u) ? pr[j] : 0.0;
                     break;
@@ -80,7 +85,7 @@ __device__ __forceinline__ void ridge_prior_solve(const PatientGram &pg, double 
 // sums = the row's 4 x 5 per-treatment sums and out = its 16 coefficients, both in shared memory.
 __device__ __forceinline__ void ridge_prior_solve_rolled(const double *sums, double u, const double *s_prior,
                                                          double support_tol, double lam, double threshold, int max_iter,
-                                                         double *out)
+                                                         double *out, int estimator = 0)
 {
 #pragma unroll 1
     for (int a = 0; a < 4; ++a) {
@@ -96,12 +101,12 @@ __device__ __forceinline__ void ridge_prior_solve_rolled(const double *sums, dou
         }
         const double cnt = g15[14];
         if (cnt > 0.0 && ind != 0) {
-            const double inv = 1.0 / cnt;   // mean-normalised normal equations
+            const double inv = estimator == 1 ? 1.0 : 1.0 / cnt;   // mean-normalised normal equations
 #pragma unroll
             for (int j = 0; j < B200I_GRAM_PER_TREATMENT; ++j) g15[j] *= inv;
             unpack_gram(g15, G, b);
             for (int it = 0; it < max_iter; ++it) {
-                if (!solve_spd4(G, b, ind, lam, pr, c)) {
+                if (!solve_spd4(G, b, ind, lam, estimator == 1 ? nullptr : pr, c)) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) c[j] = ((ind >> j) & 1u) ? pr[j] : 0.0;
                     break;
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(128)
 stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict__ x, const uint8_t *__restrict__ codes,
                      const int *__restrict__ fit_len, const double *__restrict__ static_u,
                      const double *__restrict__ prior, double support_tol, double lam, double threshold, int max_iter,
-                     const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out)
+                     const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out, int estimator)
 {
     __shared__ double s_prior[16];
     if (threadIdx.x < 16) s_prior[threadIdx.x] = prior[threadIdx.x];
@@ -159,7 +164,7 @@ stlsq_batched_kernel(int64_t rows, int W, double fd_dt, const double *__restrict
             a0 = a1;
         }
     }
-    ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, coefs_out + r * 16);
+    ridge_prior_solve(pg, u, s_prior, support_tol, lam, threshold, max_iter, coefs_out + r * 16, estimator);
 }
 
 // Tiled K5b (W <= K5_MAXW): a warp owns 32 consecutive rows; their code bytes arrive by coalesced 16-byte loads, the
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(K5_WARPS * 32, 4)
 stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restrict__ x, const uint8_t *__restrict__ codes,
                            const int *__restrict__ fit_len, const double *__restrict__ static_u,
                            const double *__restrict__ prior, double support_tol, double lam, double threshold,
-                           int max_iter, const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out)
+                           int max_iter, const double *__restrict__ dts, int dts_per_row, double *__restrict__ coefs_out,
+                           int estimator)
 {
     extern __shared__ __align__(16) uint8_t smem5[];
     __shared__ double s_prior[16];
@@ -281,7 +287,7 @@ stlsq_batched_tiled_kernel(int64_t rows, int W, double fd_dt, const X *__restric
 #pragma unroll
             for (int m = 0; m < 5; ++m) s_pg[lane][a * 5 + m] = pg.s[a][m];
         __syncwarp();
-        if (live) ridge_prior_solve_rolled(s_pg[lane], u, s_prior, support_tol, lam, threshold, max_iter, s_x[lane]);
+        if (live) ridge_prior_solve_rolled(s_pg[lane], u, s_prior, support_tol, lam, threshold, max_iter, s_x[lane], estimator);
         __syncwarp();
         double *go = coefs_out + first * 16;
         for (int e = lane; e < nrows * 16; e += 32) go[e] = s_x[e >> 4][e & 15];
@@ -703,9 +709,10 @@ template <typename X>
 static int stlsq_batched_impl(int64_t rows, int32_t W, double fd_dt, const X *x, const uint8_t *codes,
                               const int32_t *fit_len, const double *static_feature, const double *prior,
                               double support_tol, double lam, double threshold, int32_t max_iter, const double *dts,
-                              int32_t dts_per_row, double *coefs_out, void *stream)
+                              int32_t dts_per_row, double *coefs_out, void *stream, int32_t estimator = 0)
 {
     B200I_REQUIRE(rows >= 0, B200I_E_ARG, "stlsq_batched: negative rows");
+    B200I_REQUIRE(estimator == 0 || estimator == 1, B200I_E_ARG, "stlsq_batched: estimator %d (0 ridge-to-prior, 1 LSQIntialMask)", estimator);
     if (rows == 0) return 0;
     B200I_REQUIRE(x && codes && fit_len && static_feature && prior && coefs_out, B200I_E_ARG, "stlsq_batched: NULL argument");
     B200I_REQUIRE(W >= 2 && (dts != nullptr || fd_dt > 0) && lam > 0 && threshold >= 0 && max_iter >= 1, B200I_E_ARG,
@@ -728,14 +735,14 @@ static int stlsq_batched_impl(int64_t rows, int32_t W, double fd_dt, const X *x,
         if (grid > cap) grid = cap;
         stlsq_batched_tiled_kernel<X><<<(unsigned)grid, K5_WARPS * 32, smem, st>>>(
             rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold, max_iter, dts, dts_per_row,
-            coefs_out);
+            coefs_out, estimator);
         return check_cuda(cudaGetLastError(), "stlsq_batched launch");
     }
     B200I_REQUIRE(sizeof(X) == sizeof(double), B200I_E_UNSUPPORTED, "stlsq_batched_f32: W=%d > %d", W, K5_MAXW);
     const unsigned grid = (unsigned)((rows + 127) / 128);
     stlsq_batched_kernel<<<grid, 128, 0, st>>>(rows, W, fd_dt, reinterpret_cast<const double *>(x), codes, fit_len,
                                                static_feature, prior, support_tol, lam, threshold, max_iter, dts, dts_per_row,
-                                               coefs_out);
+                                               coefs_out, estimator);
     return check_cuda(cudaGetLastError(), "stlsq_batched launch");
 }
 
@@ -751,14 +758,15 @@ extern "C" int b200i_stlsq_batched(int64_t rows, int32_t W, double fd_dt, const 
 extern "C" int b200i_stlsq_batched_dts(int64_t rows, int32_t W, const double *x, const float *x_f32, const uint8_t *codes,
                                        const int32_t *fit_len, const double *static_feature, const double *prior,
                                        double support_tol, double lam, double threshold, int32_t max_iter,
-                                       double fd_dt, const double *dts, int32_t dts_per_row, double *coefs_out, void *stream)
+                                       double fd_dt, const double *dts, int32_t dts_per_row, int32_t estimator,
+                                       double *coefs_out, void *stream)
 {
     B200I_REQUIRE((x != nullptr) != (x_f32 != nullptr), B200I_E_ARG, "stlsq_batched_dts: pass exactly one of x / x_f32");
     if (x_f32)
         return stlsq_batched_impl<float>(rows, W, fd_dt, x_f32, codes, fit_len, static_feature, prior, support_tol, lam,
-                                         threshold, max_iter, dts, dts_per_row, coefs_out, stream);
+                                         threshold, max_iter, dts, dts_per_row, coefs_out, stream, estimator);
     return stlsq_batched_impl<double>(rows, W, fd_dt, x, codes, fit_len, static_feature, prior, support_tol, lam, threshold,
-                                      max_iter, dts, dts_per_row, coefs_out, stream);
+                                      max_iter, dts, dts_per_row, coefs_out, stream, estimator);
 }
 
 static int insite_bfgs_impl(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x, const uint8_t *codes,

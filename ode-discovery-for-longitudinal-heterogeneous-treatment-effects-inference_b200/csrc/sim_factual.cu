@@ -382,27 +382,6 @@ static int launch_tma(int64_t n, int T, const SimC &c, const double *params, con
     return check_cuda(cudaGetLastError(), "sim_factual_tma launch");
 }
 
-// line-aligned row-class kernel for the full 128-row tiles, generic kernel for the last n % 128 rows;
-// T % 4 != 0 has no aligned mapping and uses the plain tiles
-template <int P, int NB, int MINB, int MODE>
-static int launch_ws_rows(int64_t n, int T, const SimC &c, const double *params, const double *const in[4],
-                          double *const out[9], double *seq_len, cudaStream_t st)
-{
-    if (T % 4 != 0) return launch_ws<P, NB, MINB, MODE, false>(n, n, T, T, c, params, in, out, seq_len, st);
-    const int64_t n_main = (n / 128) * 128, n_tail = n - n_main;
-    int rc = launch_ws<P, NB, MINB, MODE, true>(n_main, n, T, T, c, params, in, out, seq_len, st);
-    if (rc || n_tail == 0) return rc;
-    FactualPtrs io;
-    io.noise = in[0] + n_main * T; io.rec = in[1] + n_main * T; io.chemo_rvs = in[2] + n_main * T;
-    io.radio_rvs = in[3] + n_main * T;
-    io.assigned = nullptr;
-    for (int a = 0; a < 9; ++a) io.out[a] = out[a] + n_main * T;
-    io.seq_len = seq_len + n_main;
-    sim_factual_generic<false><<<(unsigned)((n_tail + 127) / 128), 128, 0, st>>>(n_tail, n, T, c, params + n_main, io,
-                                                                              nullptr, nullptr);
-    return check_cuda(cudaGetLastError(), "sim_factual_generic (tail) launch");
-}
-
 struct SideOut {
     uint8_t *codes;
     int64_t code_pitch;
@@ -423,32 +402,18 @@ static int dispatch_tma(int variant, int64_t n, int T, int64_t pitch, const SimC
         return launch_ws<32, 1, 11, 0, false, 2>(n, n, T, pitch, c, params, in, out, seq_len, st, nullptr, nullptr,
                                                  side.codes, side.code_pitch, side.pmom);
     }
-    B200I_REQUIRE(pitch == T || (variant >= 10 && variant <= 13) || variant == 16 || variant == 17 || (variant >= 20 && variant <= 22), B200I_E_UNSUPPORTED,
+    B200I_REQUIRE(pitch == T || variant == 10 || variant == 12 || variant == 20 || variant == 21, B200I_E_UNSUPPORTED,
                   "sim_factual: variant %d needs dense rows (row_pitch %lld, T %d)", variant, (long long)pitch, T);
     switch (variant) {
         case 2: return launch_tma<128, 8, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 3: return launch_tma<128, 4, 2, 3, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 4: return launch_tma<64, 16, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 5: return launch_tma<64, 8, 2, 3, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 6: return launch_tma<128, 4, 1, 4, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 7: return launch_tma<256, 4, 1, 2, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 8: return launch_tma<128, 16, 1, 1, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
-        case 9: return launch_tma<64, 4, 2, 6, GRAM>(n, T, c, params, in, out, seq_len, sf, ws, st);
         // generation 6 (sim_factual_ws.cuh): <patients per tile, 16-column boxes per chunk, CTAs per SM, mode>;
-        // launch_ws_rows = the experimental line-aligned row-class mapping; 2x = data movement only (profiling aid)
+        // 2x = data movement only (profiling aid).  The other tile shapes of generations 1-5 and the line-aligned
+        // row-class mapping (variants 3-9, 11, 13-17: parity-green but slower, profiles/r1_k1_sweep_gen2.json,
+        // r1_k1_skeleton.md) were removed in round 2; variant 2 stays as the first-generation cross-check.
         case 10: return launch_ws<32, 2, 6, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 11: if (!GRAM) return launch_ws<64, 2, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 12: return launch_ws<32, 1, 11, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 16: return launch_ws<32, 1, 8, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 17: return launch_ws<32, 1, 9, 0, false, GRAM ? 1 : 0>(n, n, T, pitch, c, params, in, out, seq_len, st, sf, ws);
-        case 13: if (!GRAM) return launch_ws<32, 4, 3, 0, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
-        case 14: if (!GRAM) return launch_ws_rows<32, 2, 1, 0>(n, T, c, params, in, out, seq_len, st); break;
-        case 15: if (!GRAM) return launch_ws_rows<32, 1, 3, 0>(n, T, c, params, in, out, seq_len, st); break;
         case 20: if (!GRAM) return launch_ws<32, 2, 6, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
         case 21: if (!GRAM) return launch_ws<32, 1, 11, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
-        case 22: if (!GRAM) return launch_ws<32, 4, 3, 1, false>(n, n, T, pitch, c, params, in, out, seq_len, st); break;
-        case 24: if (!GRAM) return launch_ws_rows<32, 2, 1, 1>(n, T, c, params, in, out, seq_len, st); break;
-        case 25: if (!GRAM) return launch_ws_rows<32, 1, 3, 1>(n, T, c, params, in, out, seq_len, st); break;
         default:
             break;
     }

@@ -393,19 +393,22 @@ def ode_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS
 
 
 def stlsq_batched(x, codes, fit_len, static_feature, prior, lam, threshold=1e-3, support_tol=1e-3, max_iter=10,
-                  fd_dt=STANDARD_DT, dts=None):
+                  fd_dt=STANDARD_DT, dts=None, estimator='ridge_prior'):
     """K5b.  x (R,W) float64 (or float32: FP32 storage, FP64 arithmetic), codes (R,W) uint8, fit_len (R,) int32 ->
-    per-row coefficients (R,4,4).  dts: interval lengths (W,) or (R,W) for an irregular time grid."""
+    per-row coefficients (R,4,4).  dts: interval lengths (W,) or (R,W) for an irregular time grid.
+    estimator: 'ridge_prior' (north star) or 'lsq_initial_mask' (the ridge / threshold loop of the reference's dormant
+    LSQIntialMask: prior = initial support only, lam = its alpha, pass support_tol=1e-14; see include/b200i.h)."""
     lib = _native.load()
     rows, W = x.shape
+    est = {'ridge_prior': 0, 'lsq_initial_mask': 1}[estimator]
     out = torch.empty((rows, 4, 4), dtype=torch.float64, device='cuda')
-    if dts is not None or x.dtype == torch.float32:
+    if dts is not None or x.dtype == torch.float32 or est != 0:
         dp, dper = (None, 0) if dts is None else _dts_args(dts, rows, W)
         f32 = x.dtype == torch.float32
         assert x.is_contiguous()
         rc = lib.b200i_stlsq_batched_dts(rows, W, None if f32 else _ptr(x), _ptr(x) if f32 else None, _ptr(codes),
                                          _ptr(fit_len), _ptr(static_feature), _ptr(prior), float(support_tol), float(lam),
-                                         float(threshold), int(max_iter), float(fd_dt), dp, dper, _ptr(out), _stream())
+                                         float(threshold), int(max_iter), float(fd_dt), dp, dper, est, _ptr(out), _stream())
         _native.check(rc, "b200i_stlsq_batched_dts")
         return out
     rc = lib.b200i_stlsq_batched(rows, W, float(fd_dt), _ptr(x), _ptr(codes), _ptr(fit_len), _ptr(static_feature),

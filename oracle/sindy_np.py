@@ -544,3 +544,48 @@ def normal_equations_irregular(vol, chemo, radio, seq_len, static, dts):
                 th = np.array([1.0, xv, u, xv * u])
                 G[a[k]] += np.outer(th, th); b[a[k]] += th * xd; cnt[a[k]] += 1
     return G, b, cnt
+
+
+def lsq_initial_mask(theta, xdot, initial_guess, threshold, alpha, max_iter=100, unbias=False):
+    """The reference's dormant per-patient optimiser LSQIntialMask._reduce (pkpd/utils.py:244-327, vendored copy of
+    pysindy's STLSQ with a warm start): the initial guess only sets the initial support ind = |guess| > 1e-14
+    (:251-253); every iteration ridge-regresses on the support (sklearn ridge_regression, :228) and thresholds (:213-219);
+    stop when no feature was dropped w.r.t. the initial support or the pattern repeats (:308).  unbias=True adds
+    pysindy's OLS refit on the final support (BaseOptimizer._unbias; the reference switches it off when the refit
+    overflows, pkpd_simulation.py:795-797)."""
+    from sklearn.linear_model import ridge_regression, LinearRegression
+    n_feat = theta.shape[1]
+    ind = np.abs(np.asarray(initial_guess, dtype=np.float64)) > 1e-14
+    n_sel0 = int(ind.sum())
+    coef = np.zeros(n_feat)
+    history = [np.asarray(initial_guess, dtype=np.float64).copy()]
+    for _ in range(max_iter):
+        if not ind.any():
+            coef = np.zeros(n_feat)
+            break
+        c = np.zeros(n_feat)
+        c[ind] = ridge_regression(theta[:, ind], xdot, alpha, tol=1e-6)
+        big = np.abs(c) >= threshold
+        c[~big] = 0
+        coef, ind = c, big
+        history.append(coef.copy())
+        if ind.sum() == n_sel0 or all(bool(a) == bool(b) for a, b in zip(history[-1], history[-2])):
+            break
+    if unbias and ind.any():
+        c = np.zeros(n_feat)
+        c[ind] = LinearRegression(fit_intercept=False).fit(theta[:, ind], xdot).coef_
+        coef = c
+    return coef, ind
+
+
+def row_design_matrices(x, codes, u, n_fit, dt=STANDARD_DT):
+    """Per-treatment design matrices of one row's fit window under the live path's rules (constant-treatment snippets,
+    order-1 finite differences, last point of a snippet backward; App. B): list of (Theta (m,4), xdot (m,)) for a = 0..3."""
+    W = len(x)
+    th = [[] for _ in range(4)]; xd = [[] for _ in range(4)]
+    for k in range(int(n_fit)):
+        a = int(codes[k]); a1 = int(codes[min(k + 1, W - 1)])
+        d = (x[k + 1] - x[k]) / dt
+        for xv in [x[k]] + ([x[k + 1]] if (k == n_fit - 1 or a1 != a) else []):
+            th[a].append([1.0, xv, u, xv * u]); xd[a].append(d)
+    return [(np.array(th[a]).reshape(-1, 4), np.array(xd[a])) for a in range(4)]

@@ -14,7 +14,7 @@ warnings.filterwarnings('ignore')
 from b200_insite import device as dev
 
 
-VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '2,5,10,11,12,13,14').split(',')]
+VARIANTS = [1, 2, 10, 12]
 FUSED = [bool(int(v)) for v in os.environ.get('FUSED', '0').split(',')]
 
 

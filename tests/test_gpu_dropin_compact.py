@@ -112,3 +112,64 @@ def test_joint_model_population_metrics_from_compact_cohorts(dev):
     res_d, _ = run_experiment(default_config(insite=False, joint_model=True, treatment_mode='multilabel',
                                              compact_evaluation=False), col)
     np.testing.assert_allclose([res[k] for k in RMSE_KEYS], [res_d[k] for k in RMSE_KEYS], rtol=1e-10)
+
+
+def _parse_equation(s):
+    """'Treatment k: x_dot = +c*1+c*x0+...' | ... -> list of [(coefficient, term name)] per treatment."""
+    import re
+    out = []
+    for part in s.split(' | '):
+        head, body = part.split(' = ')
+        assert re.fullmatch(r'Treatment \d: x_dot', head), head
+        out.append([(float(c), name) for c, name in re.findall(r'\+(-?[0-9.]+(?:e-?[0-9]+)?)\*([a-z0-9]+(?:\*[a-z0-9]+)*)', body)])
+        assert ''.join(f'+{repr(c)}*{name}' for c, name in out[-1]) == body     # nothing but '+repr(float)*term' pieces
+    return out
+
+
+def test_result_log_line_is_the_reference_wire_format(dev):
+    """run.py:119-121 / train_sindy.py:72-112: the '[Exp evaluation complete] {...}' line of the seed-1 SINDy and INSITE
+    runs parses (with the reference's own parser logic, utils/results_utils.py:126-131) to the dictionary of the
+    reference's committed log: same keys in the same order, RMSEs 1e-8 / 1e-9, and the WHOLE global_equation_string:
+    same terms in the same order, coefficients printed with repr(float), values 1e-9."""
+    import ast
+    from b200_insite import runner
+    gold = h.load_json('ref_logline_seed1.json')
+    for method, overrides, tol in (('sindy', {}, 1e-8), ('insite', dict(insite_zoom_failure_fallback=False), 1e-9)):
+        res = runner.run_exp_wrapper_outer(('cancer_sim', method, 1, 2.0), **overrides)
+        line = runner.result_log_line(res)
+        assert line.startswith('[Exp evaluation complete] {')
+        got = ast.literal_eval(line.split('[Exp evaluation complete] ')[1].strip())
+        ref = ast.literal_eval(gold[method])
+        assert list(got.keys()) == list(ref.keys())
+        for k, v in ref.items():
+            if k == 'seconds_taken':
+                assert got[k] < v                       # 13.1 s / 84.8 s in the reference's log
+            elif k == 'global_equation_string':
+                g, r = _parse_equation(got[k]), _parse_equation(v)
+                assert [[n for _, n in t] for t in g] == [[n for _, n in t] for t in r]
+                np.testing.assert_allclose([c for t in g for c, _ in t], [c for t in r for c, _ in t], rtol=1e-9)
+            elif isinstance(v, float):
+                np.testing.assert_allclose(got[k], v, rtol=tol, err_msg=k)
+            else:
+                assert got[k] == v, k
+    bad = runner.run_exp_wrapper_outer(('EQ_4_A', 'sindy', 1, 2.0))
+    assert bad['errored'] is True and bad['dataset_name'] == 'EQ_4_A'
+
+
+def test_dataset_cache_round_trip(dev, tmp_path):
+    """run_utils.get_dataset: shelve cache keyed by str(args.dataset); a cached collection gives the same results."""
+    from b200_insite import runner
+    from b200_insite.config import default_config
+    args = default_config(insite=False, n_train=300, n_val=30, n_test=30, seed=4)
+    args.force_recache = True
+    path = str(tmp_path / "ct_datasets")
+    col = runner.get_dataset(args, cache_path=path)
+    r1 = runner.main(args, col)
+    args.force_recache, args.load_from_cache = False, True
+    col2 = runner.get_dataset(args, cache_path=path)
+    assert col2 is not col
+    r2 = runner.main(args, col2)
+    for k in r1:
+        if isinstance(r1[k], float):
+            np.testing.assert_allclose(r2[k], r1[k], rtol=1e-10)
+    assert r1['global_equation_string'] == r2['global_equation_string']

@@ -95,6 +95,33 @@ def test_batched_ridge_prior_stlsq_matches_numpy(dev, collection):
                 np.testing.assert_allclose(got[r], ref, rtol=1e-7, atol=1e-10)
 
 
+def test_batched_fit_in_lsq_initial_mask_mode_equals_the_reference_optimiser_loop(dev, collection):
+    """K5b, estimator 'lsq_initial_mask': per row and treatment the ridge / threshold loop of the reference's dormant
+    per-patient optimiser (pkpd/utils.py:244-327 as used at pkpd_simulation.py:778-797 with unbias=False): warm-start
+    support from the population coefficients, sklearn ridge_regression(alpha) on the row's own design matrix."""
+    import torch
+    from oracle import sindy_np as sp
+    prior = np.array(h.load_json('ref_log_seed1.json')['sindy']['coefs'])
+    prior[3, 3] = 0.0           # one term outside the warm-start support
+    for which, ph in (('one', 1), ('seq', 5)):
+        x, u, codes, seq = _rows(collection, which, 200, seed=8)
+        W = x.shape[1]
+        fit_len = np.clip(seq - ph, 0, W - 1).astype(np.int32)
+        for alpha, thr in ((0.5, 1e-3), (50.0, 0.05)):
+            got = dev.stlsq_batched(dev.to_device(x), dev.to_device(codes, dtype=torch.uint8),
+                                    dev.to_device(fit_len, dtype=torch.int32), dev.to_device(u), dev.to_device(prior),
+                                    lam=alpha, threshold=thr, support_tol=1e-14, max_iter=100,
+                                    estimator='lsq_initial_mask').cpu().numpy()
+            for r in range(x.shape[0]):
+                for a, (th, xd) in enumerate(sp.row_design_matrices(x[r], codes[r], u[r], fit_len[r])):
+                    if th.shape[0] == 0:
+                        assert np.array_equal(got[r, a], prior[a])      # treatment not in the window: prior kept
+                        continue
+                    ref, ind = sp.lsq_initial_mask(th, xd, prior[a], thr, alpha, unbias=False)
+                    assert np.array_equal(got[r, a] != 0, ind), (which, r, a)
+                    np.testing.assert_allclose(got[r, a], ref, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(ref).max()))
+
+
 def test_bfgs_objective_and_optimum_vs_scipy(dev, collection):
     import torch
     from oracle import sindy_np as sp

@@ -45,7 +45,7 @@ def _check_factual(got, ref, tag):
         np.testing.assert_allclose(got[k], ref[k], rtol=FLOAT_RTOL, atol=1e-13, err_msg=f"{tag}: {k}")
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("variant", [1, 2, 10, 12])
 def test_factual_variants_match_oracle(dev, variant):
     from oracle import sim_oracle as so
     params, draws = h.random_cohort(3000, seed=5)   # ragged: last tile partial for every tile size
@@ -54,7 +54,7 @@ def test_factual_variants_match_oracle(dev, variant):
     _check_factual(got, ref, f"variant {variant}")
 
 
-@pytest.mark.parametrize("variant", [0, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("variant", [0, 10, 12])
 def test_factual_fast_path_preconditions_fall_back_per_tile(dev, variant):
     """Tiles whose patients break the lean kernel's preconditions (chemo and radio sigmoids differ, sigmoid
     argument beyond exp_fast's domain) are processed by the generic column function inside the same launch."""
@@ -70,7 +70,7 @@ def test_factual_fast_path_preconditions_fall_back_per_tile(dev, variant):
     _check_factual(got, ref, f"fallback variant {variant}")
 
 
-@pytest.mark.parametrize("variant,pitch", [(0, 64), (10, 64), (11, 64), (12, 64), (13, 64), (0, 62), (10, 72)])
+@pytest.mark.parametrize("variant,pitch", [(0, 64), (10, 64), (12, 64), (0, 62), (10, 72)])
 def test_factual_pitched_rows_bit_identical_to_dense(dev, variant, pitch):
     """cudaMallocPitch-style rows (b200i_sim_factual_pitched): same kernels, same bits, padding untouched."""
     import torch

@@ -243,3 +243,24 @@ def test_odeint_restatement_known_answers_of_the_reference():
     a = sp.rollout_unscaled(x0, cd, u, cc)
     b = sp.rollout_unscaled(x0, cd, u, cc, dts=np.full(20, sp.STANDARD_DT))
     assert np.array_equal(a, b)
+
+
+def test_lsq_initial_mask_restatement_is_pinned_by_the_reference_log(seed1):
+    """The restatement of the reference's dormant per-patient optimiser LSQIntialMask (pkpd/utils.py:244-327) with a
+    dense warm start and the unbias refit IS pysindy's STLSQ, so on the seed-1 training data it has to reproduce the 16
+    logged population coefficients (final_with_insite.txt:6); a sparse warm start only restricts the support."""
+    _, o = seed1
+    log = np.array(h.load_json('ref_log_seed1.json')['sindy']['coefs'])
+    means, stds = so.scaling_params(o['train'])
+    dtr, sc = sp.process_data(o['train'], means, stds)
+    buckets = sp.de_format_snippets(dtr, sc)
+    for a in range(4):
+        th, xd = sp.design_matrices(buckets[a])
+        c, ind = sp.lsq_initial_mask(th, xd, np.ones(4), 1e-3, 0.5, unbias=True)
+        np.testing.assert_allclose(c, log[a], rtol=1e-10)
+        assert ind.all()
+        guess = log[a].copy(); guess[3] = 0.0
+        c2, ind2 = sp.lsq_initial_mask(th, xd, guess, 1e-3, 0.5, unbias=False)
+        assert not ind2[3] and c2[3] == 0.0 and ind2[:3].all()
+        from sklearn.linear_model import ridge_regression
+        np.testing.assert_allclose(c2[:3], ridge_regression(th[:, :3], xd, 0.5, tol=1e-6), rtol=1e-12)
