@@ -291,7 +291,8 @@ def block_c4(gen, T, peak):
     ms7, (c7, status, fval) = _median_ms(lambda: dev.insite_bfgs(sub(xv), sub(cd), sub(fit_len), 1, sub(gen.static), prior, 10.0),
                                          reps=2)
     stn = status.cpu().numpy().astype(np.int64)
-    out["insite_bfgs"] = {"kernel": "insite_bfgs_kernel (K7, 16 lanes per row, BFGS over 16 coefficients, FP64)", "rows": nb,
+    out["insite_bfgs"] = {"kernel": "insite_bfgs_kernel (K7, 16 lanes per row, BFGS over 16 coefficients, FP64; jax line-search "
+                                    "semantics, gtol 1e-5)", "rows": nb,
                           "ms": ms7, "fits_per_s": nb / (ms7 / 1e3),
                           "status_hist": {"converged": int(((stn & 255) == 0).sum()), "max_iter": int(((stn & 255) == 1).sum()),
                                           "zoom_failed": int(((stn & 255) == 3).sum()),
@@ -405,7 +406,7 @@ def block_c3(params, block_dev, static_dev, n, T, H, rank, world, peak, insite_p
             st_sub = static_dev[:ni].contiguous()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
-            pc, diag = ce.individualise(sub, st_sub, coefs, estimator='bfgs_rollout', lam=10.0)
+            pc, diag = ce.individualise(sub, st_sub, coefs, estimator='bfgs_rollout', lam=10.0)   # jax semantics + fallback
             a1.record()
             ms_e2, s2 = _median_ms(lambda: ce.evaluate(sub, st_sub, pc, -1.0), reps=3)
             ms_fit = allmax(a0.elapsed_time(a1))
@@ -415,7 +416,8 @@ def block_c3(params, block_dev, static_dev, n, T, H, rank, world, peak, insite_p
             fits = allsum(int((stn >= 0).sum()))
             ins = {"patients_per_gpu": ni, "fits": fits, "fit_ms": ms_fit, "fits_per_s": fits / (ms_fit / 1e3),
                    "reference_rows_covered": allsum(int(sub.n_rows.sum().item())), "evaluation_ms": allmax(ms_e2),
-                   "line_search_exhausted_frac": float(((stn[stn >= 0] & 255) == 3).mean()) if (stn >= 0).any() else 0.0}
+                   "optimiser": "jax BFGS semantics (gtol 1e-5, zoom failure -> population coefficients, sindy.py:628-631)",
+                   "zoom_failed_frac": float(((stn[stn >= 0] & 255) == 3).mean()) if (stn >= 0).any() else 0.0}
             if kind == 'seq':
                 ins["rmse_tau_1_to_H_percent"] = [float(v) for v in ce.n_step_rmses(s2, H, dev.TUMOUR_DEATH_THRESHOLD)]
             else:
@@ -827,7 +829,7 @@ def main():
     ap.add_argument("--skip-c3", action="store_true", help="skip the counterfactual-cohort block (config C3)")
     ap.add_argument("--skip-c4", action="store_true", help="skip the individualisation block (config C4)")
     ap.add_argument("--skip-c5", action="store_true", help="skip the 16M-patient sweep (config C5)")
-    ap.add_argument("--insite-patients", type=int, default=100_000,
+    ap.add_argument("--insite-patients", type=int, default=1_000_000,
                     help="patients per GPU whose (patient, t) INSITE fits are run in the C3 block (118 fits per patient)")
     args = ap.parse_args()
     if args.impl == "reference":

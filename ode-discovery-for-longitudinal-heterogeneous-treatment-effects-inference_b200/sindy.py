@@ -107,8 +107,7 @@ class SINDY:
         self.last_fit_info = {}
         if self.dataset_name != 'CANCER_SIM':
             raise NotImplementedError(f"dataset {m.dataset_name!r}: only cancer_sim is on the accelerated path")
-        for flag in ('wsindy', 'smooth_input_data', 'use_smoothed_finite_difference', 'sindy_quantize',
-                     'ablation_more_complex_basis_functions'):
+        for flag in ('wsindy', 'smooth_input_data', 'use_smoothed_finite_difference', 'ablation_more_complex_basis_functions'):
             if getattr(self, flag):
                 raise NotImplementedError(f"model.{flag}=True is outside the accelerated INSITE path (SURVEY.md §8a/f)")
         if self.joint_model:
@@ -204,6 +203,17 @@ class SINDY:
         logger.info('[Model]: ' + self.global_equation_string)
         return self
 
+    def _population_rollout_coefs(self):
+        """(4,4) coefficients of the expression the reference integrates for population predictions: terms with
+        |c| > 1e-3, rounded to sindy_quantize_global_model_round_to decimals when sindy_quantize is set
+        (convert_sindy_model_to_sympyjax_model_core, pkpd/utils.py:386-391); the joint model's 11 terms restricted to each
+        treatment code.  The kernels take them with drop_below < 0 (nothing else to drop)."""
+        c = np.asarray(self.joint_coefs, dtype=np.float64)
+        e = np.where(np.abs(c) > 1e-3, np.round(c, self.sindy_quantize_global_model_round_to) if self.sindy_quantize else c, 0.0)
+        if self.joint_model:
+            return (_JOINT_TO_PER_TREATMENT @ e[0]).reshape(4, 4)
+        return e
+
     # -- predictions ---------------------------------------------------------------------------------
     def get_predictions(self, dataset):
         if not self.insite:
@@ -224,10 +234,7 @@ class SINDY:
         """Open-loop rollout of the population ODE (terms with |c| <= 1e-3 dropped, pkpd/utils.py:388)."""
         sp = dataset.scaling_params
         prev, static, codes, _ = self._unscaled_inputs(dataset)
-        if self.joint_model:
-            un = self._rollout(prev, static, codes, dev.to_device(self.rollout_coefs_), -1.0)
-        else:
-            un = self._rollout(prev, static, codes, dev.to_device(self.joint_coefs), 1e-3)
+        un = self._rollout(prev, static, codes, dev.to_device(self._population_rollout_coefs()), -1.0)
         return ((un - sp['output_means']) / sp['output_stds'])[..., None]
 
     def individualised_coefficients(self, dataset, projection_horizon=1):
@@ -300,7 +307,7 @@ class SINDY:
         cohort, static = compact
         unscale = self.hparams.exp.unscale_rmse
         scale = 1.0 if unscale else float(dataset.scaling_params['output_stds'])
-        theta0 = dev.to_device(self.rollout_coefs_ if self.joint_model else self.joint_coefs)
+        theta0 = dev.to_device(self.joint_coefs)       # not reached for the joint model with INSITE
         if self.insite:
             coefs, diag = ce.individualise(cohort, static, theta0, self.individualisation, self.lam, self.ridge_prior_lam,
                                            self.sindy_threshold, self.zoom_failure_fallback, self.dt, gtol=self.insite_gtol,
@@ -313,7 +320,7 @@ class SINDY:
                                       'iterations_mean': float((st_np[ok] >> 8).mean()) if ok.any() else 0.0}
             drop = -1.0
         else:
-            coefs, drop = theta0, (-1.0 if self.joint_model else 1e-3)
+            coefs, drop = dev.to_device(self._population_rollout_coefs()), -1.0
         sums = ce._finish(ce.evaluate(cohort, static, coefs, drop, self.dt))
         pct = self.hparams.exp.percentage_rmse
         if kind == 'one_step':

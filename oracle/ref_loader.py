@@ -52,3 +52,29 @@ def load_reference_sim():
     mod.tqdm = lambda it, **kw: it      # silence progress bars; iteration unchanged
     _cached = mod
     return mod
+
+
+REF_CONT = os.path.join(REF_ROOT, "libs_m/ct/src/data/continuous/continuous.py")
+
+
+def load_reference_continuous():
+    """The reference's EQ_5 simulators (continuous/continuous.py), unmodified.  Its only extra import is
+    ``src.data.pkpd.pkpd_simulation.Equation`` (:21), whose package pulls in jax: a stub module with the same IntEnum
+    (pkpd_simulation.py:51-60) is planted instead."""
+    import enum
+    if not os.path.isfile(REF_CONT):
+        raise FileNotFoundError(f"reference continuous simulator not found at {REF_CONT}")
+    _plant_stubs()
+    if "src.data.pkpd.pkpd_simulation" not in sys.modules:
+        class Equation(enum.IntEnum):
+            EQ_4_A = 1; EQ_4_B = 2; EQ_4_C = 3; EQ_4_D = 4; EQ_5_A = 5; EQ_5_B = 6; EQ_5_C = 7; EQ_5_D = 8; EQ_4_M = 9
+        for name in ("src", "src.data", "src.data.pkpd"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        m = types.ModuleType("src.data.pkpd.pkpd_simulation")
+        m.Equation = Equation
+        sys.modules["src.data.pkpd.pkpd_simulation"] = m
+    spec = importlib.util.spec_from_file_location("_insite_reference_continuous", REF_CONT)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.tqdm = lambda it, **kw: it
+    return mod

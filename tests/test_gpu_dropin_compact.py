@@ -173,3 +173,35 @@ def test_dataset_cache_round_trip(dev, tmp_path):
         if isinstance(r1[k], float):
             np.testing.assert_allclose(r2[k], r1[k], rtol=1e-10)
     assert r1['global_equation_string'] == r2['global_equation_string']
+
+
+def test_quantised_population_model(dev):
+    """model.sindy_quantize (pkpd/utils.py:389-390): the integrated expression and the logged string carry the
+    coefficients rounded to sindy_quantize_global_model_round_to decimals (terms are still selected by |c| > 1e-3 of
+    the un-rounded value)."""
+    from b200_insite.config import default_config
+    from b200_insite.sindy import run_experiment
+    from oracle import sindy_np as sp
+    col = _collection()
+    base, m0 = run_experiment(default_config(insite=False), col)
+    res, model = run_experiment(default_config(insite=False, sindy_quantize=True, sindy_quantize_global_model_round_to=2), col)
+    np.testing.assert_array_equal(model.joint_coefs, m0.joint_coefs)            # the fit itself is not quantised
+    for coef, name in [t for tr in _parse_equation(res['global_equation_string']) for t in tr]:
+        assert coef == round(coef, 2)
+    # dense restatement with the rounded coefficients
+    ds = col.test_cf_one_step
+    scp = ds.scaling_params
+    prev = np.squeeze(ds.data['prev_outputs'] * scp['output_stds'] + scp['output_means'], -1)
+    static = (ds.data['static_features'] * scp['inputs_stds'][1:2] + scp['input_means'][1:2])[:, 0]
+    codes = np.argmax(ds.data['current_treatments'], -1)
+    c = m0.joint_coefs
+    ce = np.where(np.abs(c) > 1e-3, np.round(c, 2), 0.0)
+    un = sp.rollout_unscaled(prev[:, 0], codes, static, ce)
+    scaled = ((un - scp['output_means']) / scp['output_stds'])[..., None]
+    orig, all_, last = sp.masked_rmse(scaled, ds.data, scp)
+    np.testing.assert_allclose([res['encoder_test_rmse_orig'], res['encoder_test_rmse_all'], res['encoder_test_rmse_last']],
+                               [orig, all_, last], rtol=1e-9)
+    dense, _ = run_experiment(default_config(insite=False, sindy_quantize=True, sindy_quantize_global_model_round_to=2,
+                                             compact_evaluation=False), col)
+    np.testing.assert_allclose([dense[k] for k in RMSE_KEYS], [res[k] for k in RMSE_KEYS], rtol=1e-10)
+    assert abs(res['encoder_test_rmse_all'] - base['encoder_test_rmse_all']) > 1e-6

@@ -179,3 +179,38 @@ def test_lazy_dataset_dictionary_behaves_like_a_dict():
         d['missing']
     del c['b']
     assert 'b' not in c
+
+
+def test_continuous_generate_params_bit_exact_and_rng_consumption():
+    """EQ_5 parameter generator (continuous/continuous.py:68-224) vs the committed vectors of the unmodified reference
+    (oracle/make_golden_continuous.py) and, where /root/reference exists, vs the live reference for all four equations:
+    every array bit-exact and the global RNG left in the same state."""
+    import hashlib
+    from b200_insite import continuous as ct
+    g = h.load_npz('ref_continuous_small.npz')
+    for eq in ('EQ_5_A', 'EQ_5_D'):
+        np.random.seed(17)
+        p = ct.generate_params(40, 2.0, 2.0, 15, 0, ct.Equation[eq])
+        for k, v in p.items():
+            ref = g[f'{eq}/factual/params/{k}']
+            assert np.array_equal(np.asarray(v), ref), (eq, k)
+        assert set(p) == {k.split('/')[-1] for k in g.files if k.startswith(f'{eq}/factual/params/')}
+    assert p['observation_noise'] == 0.01 and len(np.unique(p['beta_c'])) > 3
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        return
+    import sys
+    ref = ref_loader.load_reference_continuous()
+    Eq = sys.modules["src.data.pkpd.pkpd_simulation"].Equation
+    for eq in ('EQ_5_A', 'EQ_5_B', 'EQ_5_C', 'EQ_5_D'):
+        np.random.seed(3)
+        a = ref.generate_params(257, 3.0, 1.0, 15, 0, Eq[eq])
+        sa = hashlib.sha256(np.random.get_state()[1].tobytes()).hexdigest()
+        np.random.seed(3)
+        b = ct.generate_params(257, 3.0, 1.0, 15, 0, ct.Equation[eq])
+        sb = hashlib.sha256(np.random.get_state()[1].tobytes()).hexdigest()
+        assert sa == sb and set(a) == set(b)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (eq, k)
+    with pytest.raises(ValueError):
+        ct.generate_params(4, 2.0, 2.0, 15, 0, ct.Equation.EQ_4_A)

@@ -264,3 +264,4 @@ def test_lsq_initial_mask_restatement_is_pinned_by_the_reference_log(seed1):
         assert not ind2[3] and c2[3] == 0.0 and ind2[:3].all()
         from sklearn.linear_model import ridge_regression
         np.testing.assert_allclose(c2[:3], ridge_regression(th[:, :3], xd, 0.5, tol=1e-6), rtol=1e-12)
+
