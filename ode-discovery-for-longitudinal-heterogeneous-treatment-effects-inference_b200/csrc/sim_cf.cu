@@ -149,7 +149,16 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
     double self_F1 = 0.0;
     int steps = 0;
     bool alive = true;
+    // the four draws of step t + 1 are requested while step t computes (their addresses do not depend on the
+    // trajectory): the first version loaded them where they were used and spent 6.4 of 10 issue slots in
+    // long_scoreboard stalls (profiles/r2_k2_one_step_ncu.txt)
+    double nx_chemo = chemo_rvs[i * T], nx_radio = radio_rvs[i * T], nx_rec = rec[i * T], nx_noise = noise[i * T + 1];
     for (int t = 0; t < T - 1; ++t) {
+        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise;
+        if (alive && t + 1 < T - 1) {
+            nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
+            nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * T + t + 2];
+        }
         if (!alive) {   // steps after the last executed one: zeros (the compact arrays are fully defined)
             Fr[t + 1] = 0.0; cr[t] = 0;
             double2 *z = reinterpret_cast<double2 *>(cf_out + (i * (T - 1) + t) * 4);
@@ -165,9 +174,8 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
             w_t = w.at(t);
         }
         double C_t, D_t;
-        const int fo = cf_assign(c, p, s, w_t, chemo_rvs[i * T + t], radio_rvs[i * T + t], t, C_t, D_t);
+        const int fo = cf_assign(c, p, s, w_t, u_chemo, u_radio, t, C_t, D_t);
         const double lg = log(__ddiv_rn(p.K, s.F));
-        const double nz = noise[i * T + t + 1];
         const double prevC = (t == 0) ? 0.0 : s.Cprev;
         double Vf = 0.0;
 #pragma unroll
@@ -185,7 +193,7 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
         steps = t + 1;
         s.F = Fn;
         s.Cprev = C_t;
-        if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
+        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) alive = false;
     }
     cr[T - 1] = 0;
     n_steps[i] = steps;

@@ -254,7 +254,14 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
     for (int q = 0; q < PB_H; ++q) self_tail[q] = 0.0;
     int steps = 0;
     bool alive = !missing;
+    // draws of step t + 1 requested while step t computes (see cf_one_step_kernel)
+    double nx_chemo = chemo_rvs[i * T], nx_radio = radio_rvs[i * T], nx_rec = rec[i * T], nx_noise = noise[i * NW + 1];
     for (int t = 0; t < T - 1; ++t) {
+        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise;
+        if (alive && t + 1 < T - 1) {
+            nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
+            nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * NW + t + 2];
+        }
         if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; Cr[t] = 0.0; continue; }
         double w_t;
         if (w.self) {
@@ -267,9 +274,9 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
             w_t = w.at(t);
         }
         double C_t, D_t;
-        const int fo = cf_assign(c, p, s, w_t, chemo_rvs[i * T + t], radio_rvs[i * T + t], t, C_t, D_t);
+        const int fo = cf_assign(c, p, s, w_t, u_chemo, u_radio, t, C_t, D_t);
         const double lg = log(__ddiv_rn(p.K, s.F));
-        const double Fn = clip(growth(p, s.F, lg, C_t, D_t, noise[i * NW + t + 1]), 0.0, c.death);
+        const double Fn = clip(growth(p, s.F, lg, C_t, D_t, nz), 0.0, c.death);
         Fr[t + 1] = Fn;
         cr[t] = (uint8_t)fo;
         Cr[t] = C_t;
@@ -282,7 +289,7 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
         steps = t + 1;
         s.F = Fn;
         s.Cprev = C_t;
-        if (Fn >= c.death || recovery_test<false>(rec[i * T + t], Fn, c.density)) alive = false;
+        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) alive = false;
     }
     cr[T - 1] = 0;
     Cr[T - 1] = 0.0;

@@ -146,3 +146,56 @@ def test_sharded_counterfactual_cohort_equals_whole_cohort(tmp_path, kind, n_tot
     for k in ('cancer_volume', 'chemo_application', 'radio_application', 'sequence_lengths'):
         got = np.concatenate([p[k] for p in parts])
         assert np.array_equal(got, ref[k], equal_nan=True), k
+
+
+def _eval_worker(rank, world, port, out_dir):
+    """Sharded evaluation of a counterfactual test set: every rank holds the error sums of its patients (here from the
+    numpy restatement of the dense rows), the sums are all-reduced and every rank derives the same RMSEs."""
+    sys.path.insert(0, h.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200_insite import cohort, compact_eval as ce, counterfactual as cf
+    data = np.load(os.path.join(out_dir, "sums_in.npz"))
+    one = torch.from_numpy(data[f"one_{rank}"].copy())
+    seq = torch.from_numpy(data[f"seq_{rank}"].copy())
+    cohort.allreduce_stats(one)
+    cohort.allreduce_stats(seq)
+    base, total = cf.exchange_row_bases(int(data[f"rows_{rank}"]))
+    np.savez(os.path.join(out_dir, f"eval_{rank}.npz"), one=one.numpy(), seq=seq.numpy(), base=base, total=total,
+             r1=np.array(ce.one_step_rmses(one.numpy(), 59, 1150.0)), r5=ce.n_step_rmses(seq.numpy(), 5, 1150.0))
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_sums_and_row_bases(tmp_path):
+    """compact_eval on N > 1 ranks: additive error sums (all-reduce), row bases by an exclusive scan of the per-rank row
+    totals (counterfactual.exchange_row_bases) -- the two exchanges of a sharded config-C3 evaluation."""
+    from b200_insite import compact_eval as ce
+    rng = np.random.RandomState(5)
+    W, H, world = 59, 5, 2
+    parts = {}
+    rows = [4 * 1234, 4 * 987]
+    for r in range(world):
+        cnt = np.sort(rng.randint(1, rows[r], size=W))[::-1].astype(np.float64)
+        cnt[0] = rows[r]
+        se = rng.rand(W) * cnt * 100.0
+        last = rng.rand(W) * 50.0
+        parts[f"one_{r}"] = np.concatenate([se, cnt, last, [last.sum(), rows[r]]])
+        parts[f"seq_{r}"] = np.concatenate([rng.rand(H) * 1e4, np.full(H, 10.0 * rows[r])])
+        parts[f"rows_{r}"] = np.array(rows[r])
+    np.savez(tmp_path / "sums_in.npz", **parts)
+    mp.spawn(_eval_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"eval_{r}.npz") for r in range(world)]
+    tot_one = parts["one_0"] + parts["one_1"]
+    tot_seq = parts["seq_0"] + parts["seq_1"]
+    for r in range(world):
+        assert np.array_equal(got[r]["one"], tot_one) and np.array_equal(got[r]["seq"], tot_seq)
+        assert int(got[r]["total"]) == sum(rows) and int(got[r]["base"]) == sum(rows[:r])
+        np.testing.assert_allclose(got[r]["r1"], ce.one_step_rmses(tot_one, W, 1150.0), rtol=1e-15)
+        np.testing.assert_allclose(got[r]["r5"], ce.n_step_rmses(tot_seq, H, 1150.0), rtol=1e-15)
+    # the formulas themselves: time_varying_model.py:247-281 / :298-311 on the summed quantities
+    orig, all_, last = ce.one_step_rmses(tot_one, W, 1150.0)
+    se, cnt = tot_one[:W], tot_one[W:2 * W]
+    assert np.isclose(all_, np.sqrt(se.sum() / cnt.sum()) / 1150.0 * 100)
+    assert np.isclose(orig, np.sqrt((se / cnt).mean()) / 1150.0 * 100)
+    assert np.isclose(last, np.sqrt(tot_one[3 * W] / tot_one[3 * W + 1]) / 1150.0 * 100)
