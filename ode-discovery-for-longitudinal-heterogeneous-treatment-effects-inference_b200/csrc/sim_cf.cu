@@ -34,6 +34,29 @@ struct CfSrc {
 
 constexpr int MAXH = 8;
 
+// The factual step's three transcendental functions and its divisions: the lean versions of csrc/fastmath.cuh (the
+// ones K1 runs; <= 1 ulp, same class as libdevice's and numpy's own) wherever their domain allows -- positive, finite,
+// normal arguments, |sigmoid argument| <= 700 -- and the library functions otherwise (zero or negative window
+// entries, an eradicated tumour): 1300 -> ~500 warp instructions per patient step.
+__device__ __forceinline__ double cf_diameter(double v, double sphere)
+{
+    if (v >= 1e-30 && v <= 1e30) return __dmul_rn(fm::cbrt_fast(fm::div_fast(v, sphere)), 2.0);
+    if (v == 0.0) return 0.0;      // the part of the window row that was never written: ((0 / c) ** (1/3)) * 2 = 0
+    return calc_diameter(v, sphere);
+}
+__device__ __forceinline__ double cf_sigmoid(double beta, double metric, double intercept)
+{
+    // 1.0 / (1.0 + np.exp(-beta * (metric - intercept)))   cancer_simulation.py:322-323
+    const double z = __dmul_rn(-beta, __dsub_rn(metric, intercept));
+    if (fabs(z) <= 700.0) return fm::rcp_fast(__dadd_rn(1.0, fm::exp_fast(z)));
+    return __ddiv_rn(1.0, __dadd_rn(1.0, exp(z)));      // also the NaN route (negative volume in the window)
+}
+__device__ __forceinline__ double cf_log_ratio(double K, double F)
+{
+    if (F >= 1e-300 && F <= 1e300 && K >= 1e-300 && K <= 1e300) return fm::log_ratio(K, F);
+    return log(__ddiv_rn(K, F));
+}
+
 // owner j of global row g: off[j] <= g < off[j+1]; -1 if g is beyond the known rows
 __device__ __forceinline__ int64_t find_owner(const int64_t *__restrict__ off, int64_t n, int64_t g)
 {
@@ -76,10 +99,10 @@ struct CfFactual {
 __device__ __forceinline__ int cf_assign(const SimC2 &c, const Patient &p, CfFactual &s, double w_t, double uchemo,
                                          double uradio, int t, double &C_t, double &D_t)
 {
-    window_push(s.win, s.cnt, c.window + 1, calc_diameter(w_t, c.sphere));
+    window_push(s.win, s.cnt, c.window + 1, cf_diameter(w_t, c.sphere));
     const double metric = np_mean(s.win, s.cnt);
-    const double pr = sigmoid_prob(p.radio_beta, metric, p.radio_int);
-    const double pc = p.same_sigmoid ? pr : sigmoid_prob(p.chemo_beta, metric, p.chemo_int);
+    const double pr = cf_sigmoid(p.radio_beta, metric, p.radio_int);
+    const double pc = p.same_sigmoid ? pr : cf_sigmoid(p.chemo_beta, metric, p.chemo_int);
     const bool ra = uradio < pr;   // NaN probability (negative volume in the window) -> no treatment
     const bool ca = uchemo < pc;
     D_t = ra ? c.radio_amt : 0.0;
@@ -103,7 +126,7 @@ __device__ __forceinline__ double clip(double x, double lo, double hi) { return 
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const double *__restrict__ params,
                    const double *__restrict__ noise, const double *__restrict__ rec,
                    const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
@@ -153,11 +176,13 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
     // trajectory): the first version loaded them where they were used and spent 6.4 of 10 issue slots in
     // long_scoreboard stalls (profiles/r2_k2_one_step_ncu.txt)
     double nx_chemo = chemo_rvs[i * T], nx_radio = radio_rvs[i * T], nx_rec = rec[i * T], nx_noise = noise[i * T + 1];
+    double nx_w = w.self ? 0.0 : w.at(0);      // the window row's entry of the next step (owner's row: a remote read)
     for (int t = 0; t < T - 1; ++t) {
-        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise;
+        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise, w_pre = nx_w;
         if (alive && t + 1 < T - 1) {
             nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
             nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * T + t + 2];
+            if (!w.self) nx_w = w.at(t + 1);
         }
         if (!alive) {   // steps after the last executed one: zeros (the compact arrays are fully defined)
             Fr[t + 1] = 0.0; cr[t] = 0;
@@ -168,14 +193,14 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
         double w_t;
         if (w.self) {
             // row 0 is this patient's own t=0 snapshot [F0, F1, 0, ...]; before it exists the row is 0
-            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, calc_diameter(p.v0, c.sphere)); }
+            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, cf_diameter(p.v0, c.sphere)); }
             w_t = (t == 1) ? self_F1 : 0.0;
         } else {
-            w_t = w.at(t);
+            w_t = w_pre;
         }
         double C_t, D_t;
         const int fo = cf_assign(c, p, s, w_t, u_chemo, u_radio, t, C_t, D_t);
-        const double lg = log(__ddiv_rn(p.K, s.F));
+        const double lg = cf_log_ratio(p.K, s.F);
         const double prevC = (t == 0) ? 0.0 : s.Cprev;
         double Vf = 0.0;
 #pragma unroll
@@ -306,7 +331,7 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         double w_t;
         if (w.self) {
             // row 0 = first row this patient emits at t = 0: [F0, F1, projections of that option, 0, ...]
-            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, calc_diameter(p.v0, c.sphere)); }
+            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, cf_diameter(p.v0, c.sphere)); }
             w_t = 0.0;
             if (t == 1) w_t = self_F1;
 #pragma unroll
@@ -317,7 +342,7 @@ cf_treatment_seq_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const
         }
         double C_t, D_t;
         const int fo = cf_assign(c, p, s, w_t, chemo_rvs[i * T + t], radio_rvs[i * T + t], t, C_t, D_t);
-        const double lg = log(__ddiv_rn(p.K, s.F));
+        const double lg = cf_log_ratio(p.K, s.F);
         const double Fn = clip(growth(p, s.F, lg, C_t, D_t, noise[i * NW + t + 1]), 0.0, c.death);
         Fr[t + 1] = Fn;
         cr[t] = (uint8_t)fo;

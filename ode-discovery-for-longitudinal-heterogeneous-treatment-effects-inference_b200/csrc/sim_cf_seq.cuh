@@ -182,7 +182,7 @@ __global__ void cf_seq_self_kernel(int64_t n, int T, int H, SimC2 c, const __gri
     for (int q = 0; q < 16; ++q) s.win[q] = 0.0;
     double C_t, D_t;
     cf_assign(c, p, s, 0.0, chemo_rvs[0], radio_rvs[0], 0, C_t, D_t);     // the window row is still all zeros
-    const double lg = log(__ddiv_rn(p.K, s.F));
+    const double lg = cf_log_ratio(p.K, s.F);
     const double Fn = clip(growth(p, s.F, lg, C_t, D_t, noise[1]), 0.0, c.death);
     const ProjPatient pp = proj_patient(pk, c.radio_amt, params, n, 0);
     const ComputedLogTab tab;
@@ -198,7 +198,7 @@ __global__ void cf_seq_self_kernel(int64_t n, int T, int H, SimC2 c, const __gri
     for (int kk = 0; kk < PB_H; ++kk) self_row[kk] = opt[o][kk];
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, const double *__restrict__ params,
                       const double *__restrict__ noise, const double *__restrict__ rec,
                       const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
@@ -256,26 +256,28 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
     bool alive = !missing;
     // draws of step t + 1 requested while step t computes (see cf_one_step_kernel)
     double nx_chemo = chemo_rvs[i * T], nx_radio = radio_rvs[i * T], nx_rec = rec[i * T], nx_noise = noise[i * NW + 1];
+    double nx_w = (w.self || missing) ? 0.0 : w.at(0);
     for (int t = 0; t < T - 1; ++t) {
-        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise;
+        const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise, w_pre = nx_w;
         if (alive && t + 1 < T - 1) {
             nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
             nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * NW + t + 2];
+            if (!w.self) nx_w = w.at(t + 1);
         }
         if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; Cr[t] = 0.0; continue; }
         double w_t;
         if (w.self) {
-            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, calc_diameter(p.v0, c.sphere)); }
+            if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, cf_diameter(p.v0, c.sphere)); }
             w_t = (t == 1) ? self_F1 : 0.0;
 #pragma unroll
             for (int q = 0; q < PB_H; ++q)
                 if (t == q + 2) w_t = self_tail[q];
         } else {
-            w_t = w.at(t);
+            w_t = w_pre;
         }
         double C_t, D_t;
         const int fo = cf_assign(c, p, s, w_t, u_chemo, u_radio, t, C_t, D_t);
-        const double lg = log(__ddiv_rn(p.K, s.F));
+        const double lg = cf_log_ratio(p.K, s.F);
         const double Fn = clip(growth(p, s.F, lg, C_t, D_t, nz), 0.0, c.death);
         Fr[t + 1] = Fn;
         cr[t] = (uint8_t)fo;
