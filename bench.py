@@ -658,25 +658,35 @@ def run_b200(args):
     h_types = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.uint8)).pin_memory() if args.uniform_rows else None
     if args.uniform_rows:     # outside the timed region: the inputs really are what the reduced contract assumes
         assert np.array_equal(params['beta'], params['alpha'] / 10) and dev.uniform_param_rows(params) == uniform
-    for _ in range(max(1, min(args.warmup, 3))):
-        gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types)
-    barrier()
-    gen_e2e_steps = max(1, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(gen_e2e_steps):
-        gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types)
-    barrier()
-    gen_e2e_ms = 1e3 * (time.perf_counter() - t0) / gen_e2e_steps
+    def e2e_loop(graph):
+        for _ in range(max(1, min(args.warmup, 3))):
+            gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types, graph=graph)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            gen.step_host(h_block, h_static, h_result, uniform=uniform, types_u8=h_types, graph=graph)
+        barrier()
+        return 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    # eager: ~60 stream operations per step issued from Python; graph: the same step captured once and replayed with one
+    # launch (same copies, same kernels, same collective).  The headline e2e is the graph replay unless it is disabled.
+    gen_e2e_eager_ms = e2e_loop(False)
+    gen_e2e_ms = gen_e2e_eager_ms
+    e2e_graph_error = None
+    if args.e2e_graph:
+        try:
+            gen_e2e_ms = e2e_loop(True)
+        except Exception as e:      # noqa: BLE001
+            e2e_graph_error = repr(e)
     clocks.stop.set(); clocks.t.join(timeout=6)
     gen_coefs = h_result[:16].numpy().reshape(4, 4).copy()
-    tg = torch.tensor([gen_ms, gen_e2e_ms, -gen_exec], dtype=torch.float64, device='cuda')
+    tg = torch.tensor([gen_ms, gen_e2e_ms, gen_e2e_eager_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         tgs = torch.tensor([gen_exec], dtype=torch.float64, device='cuda'); dist.all_reduce(tgs, op=dist.ReduceOp.SUM)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gen_exec_all = float(tgs[0])
     else:
         gen_exec_all = gen_exec
-    gen_ms, gen_e2e_ms = float(tg[0]), float(tg[1])
+    gen_ms, gen_e2e_ms, gen_e2e_eager_ms = float(tg[0]), float(tg[1]), float(tg[2])
 
     # ---- the other BASELINE configurations (each block is guarded: a failure there must not cost the headline line) ----
     peak_hbm, _ = measured_peak_hbm()
@@ -738,6 +748,11 @@ def run_b200(args):
                         "h2d_bytes_per_patient": gen_h2d / n,
                         "rows_rebuilt_on_device": sorted(uniform) + ([3] if h_types is not None else []),
                         "d2h_bytes_per_step": int(h_result.numel() * 8), "ms_per_step": gen_e2e_ms,
+                        "launch": ("one CUDA-graph launch per step (the step's copies, kernels, collective and result copies "
+                                   "captured once for these pinned buffers)" if args.e2e_graph and e2e_graph_error is None
+                                   else "eager stream operations"),
+                        "eager": {"value": gen_exec_all / (gen_e2e_eager_ms / 1e3), "ms_per_step": gen_e2e_eager_ms,
+                                  "graph_error": e2e_graph_error},
                         "what": "GeneratedFitPipeline.step_host on the reduced input set: pinned host arrays of what "
                                 "get_standard_params draws per patient (initial volume, alpha, rho, beta_c as float64, the "
                                 "patient type as one byte) -> H2D in "
@@ -826,6 +841,7 @@ def main():
                     help="bounded CPU sample; 0 = the workload's patients per GPU for --impl reference, 400k for the "
                          "single-thread cpu_baseline leg of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-graph", type=int, default=1, help="e2e: replay the host step as one CUDA graph (0 = eager only)")
     ap.add_argument("--skip-c3", action="store_true", help="skip the counterfactual-cohort block (config C3)")
     ap.add_argument("--skip-c4", action="store_true", help="skip the individualisation block (config C4)")
     ap.add_argument("--skip-c5", action="store_true", help="skip the 16M-patient sweep (config C5)")

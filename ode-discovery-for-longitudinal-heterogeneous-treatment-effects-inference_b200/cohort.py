@@ -213,16 +213,8 @@ class GeneratedFitPipeline:
         self._simulate()
         return self._fit()
 
-    def step_host(self, params_block, static, result_host, uniform=None, types_u8=None):
-        """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.
-        types_u8: pinned uint8 (N,) patient types = the REDUCED input set (what get_standard_params draws: initial volume,
-        alpha, rho, beta_c, patient type); `static` is then ignored, beta = alpha / 10 and the static feature are rebuilt
-        on the device as generate_params builds them: 33 bytes per patient with the five scalar rows in `uniform`.
-        uniform: {row: value} of parameter rows that are one scalar for the cohort (device.uniform_param_rows): they
-        are filled on the device instead of being copied (88 -> 48 bytes per patient for the reference's cohorts).  The parameter
-        rows of chunk c+1 are copied on a second stream while chunk c is being simulated and reduced to its share of
-        the population statistics; the shares are summed in chunk order (bits depend on the chunk count only)."""
-        main = torch.cuda.current_stream()
+    def _enqueue_host_step(self, params_block, static, result_host, uniform, types_u8):
+        """Everything of step_host but the final synchronisation, on the current stream."""
         if types_u8 is not None:
             if getattr(self, 'types_u8_dev', None) is None:
                 self.types_u8_dev = torch.empty((self.n,), dtype=torch.uint8, device='cuda')
@@ -240,6 +232,35 @@ class GeneratedFitPipeline:
         result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
         result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
         result_host[32:32 + dev.STATS_DOUBLES].copy_(self.stats, non_blocking=True)
+
+    def step_host(self, params_block, static, result_host, uniform=None, types_u8=None, graph=False):
+        """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.
+        types_u8: pinned uint8 (N,) patient types = the REDUCED input set (what get_standard_params draws: initial volume,
+        alpha, rho, beta_c, patient type); `static` is then ignored, beta = alpha / 10 and the static feature are rebuilt
+        on the device as generate_params builds them: 33 bytes per patient with the five scalar rows in `uniform`.
+        uniform: {row: value} of parameter rows that are one scalar for the cohort (device.cohort_scalar_rows): they
+        are filled on the device instead of being copied.  The parameter rows of chunk c+1 are copied on a second stream
+        while chunk c is being simulated and reduced to its share of the population statistics; the shares are summed in
+        chunk order (bits depend on the chunk count only).
+        graph=True: the whole step (chunked copies on the copy stream, per-chunk kernels on two compute streams, the
+        all-reduce, STLSQ and the device->host copies of the result) is captured once into a CUDA graph for these host
+        buffers and replayed: one graph launch instead of ~60 stream operations per step (the copies read the same
+        pinned buffers every time, so the caller refreshes their CONTENT between steps)."""
+        main = torch.cuda.current_stream()
+        if not graph:
+            self._enqueue_host_step(params_block, static, result_host, uniform, types_u8)
+            main.synchronize()
+            return result_host
+        key = (params_block.data_ptr(), None if static is None else static.data_ptr(), result_host.data_ptr(),
+               None if types_u8 is None else types_u8.data_ptr(), tuple(sorted((uniform or {}).items())))
+        if getattr(self, '_graph_key', None) != key:
+            self._enqueue_host_step(params_block, static, result_host, uniform, types_u8)   # warm-up outside the capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_host_step(params_block, static, result_host, uniform, types_u8)
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
         main.synchronize()
         return result_host
 

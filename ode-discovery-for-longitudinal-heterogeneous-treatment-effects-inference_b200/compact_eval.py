@@ -48,11 +48,13 @@ def n_step_rmses(sums, H, norm_const, percentage=True, scale=1.0):
 
 
 def individualise(cohort, static, theta0, estimator='bfgs_rollout', lam=10.0, ridge_prior_lam=1e4, threshold=1e-3,
-                  zoom_failure_fallback=True, dt=dev.STANDARD_DT, gtol=None, max_iter=None, line_search='jax'):
+                  zoom_failure_fallback=None, dt=dev.STANDARD_DT, gtol=None, max_iter=None, line_search='jax'):
     """Per-(patient, t) coefficient matrices (n, T-1, 4, 4) of a compact cohort + diagnostics.
     The fit window of the one-step rows is their first t transitions (projection_horizon 1, sindy.py:433), of the
     sequence rows their first t+1 (projection_horizon H, :747)."""
     fit_offset = 0 if cohort.kind == 'one_step' else 1
+    if zoom_failure_fallback is None:      # the reference's rule (sindy.py:628-631) belongs to jax's failure semantics
+        zoom_failure_fallback = line_search == 'jax'
     if estimator == 'bfgs_rollout':
         coefs, status, fval = dev.insite_bfgs_prefix(cohort.factual, cohort.codes, cohort.n_steps, static, theta0, lam,
                                                      fit_offset, gtol=gtol, max_iter=max_iter, dt=dt, line_search=line_search)
@@ -77,7 +79,7 @@ def evaluate(cohort, static, coefs, drop_below, dt=dev.STANDARD_DT, substeps=dev
 
 
 def evaluate_model(one_step, static_one, seq, static_seq, population_coefs, insite=False, estimator='bfgs_rollout',
-                   lam=10.0, ridge_prior_lam=1e4, threshold=1e-3, zoom_failure_fallback=True,
+                   lam=10.0, ridge_prior_lam=1e4, threshold=1e-3, zoom_failure_fallback=None,
                    norm_const=dev.TUMOUR_DEATH_THRESHOLD, percentage=True, scale=1.0, dt=dev.STANDARD_DT, info=None):
     """The eight test metrics of train_sindy.main (:72-112) from two compact cohorts: encoder_test_rmse_{all,orig,last}
     and decoder_test_rmse_{2..H+1}-step.  population_coefs: (4,4) device tensor (SINDY.joint_coefs)."""

@@ -764,9 +764,12 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
         fill_uniform_rows_kernel<<<num_sms() * 4, 256, 0, st>>>(params, n, uniform_mask, u);
         B200I_CUDA(cudaGetLastError());
     }
-    // the previous work on `stream` may still read the parameter block / write the outputs
-    cudaEvent_t ev;
-    B200I_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // the previous work on `stream` may still read the parameter block / write the outputs.  One event per (thread,
+    // device), created once: the call creates and destroys nothing, so it can be captured into a CUDA graph
+    // (cohort.GeneratedFitPipeline.step_host(graph=True): one graph launch instead of ~60 stream operations per step)
+    static thread_local cudaEvent_t evs[16] = {};
+    if (evs[devid] == nullptr) B200I_CUDA(cudaEventCreateWithFlags(&evs[devid], cudaEventDisableTiming));
+    cudaEvent_t ev = evs[devid];
     int rc = check_cuda(cudaEventRecord(ev, st), "cudaEventRecord");
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(cs, ev, 0), "cudaStreamWaitEvent");
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(sx, ev, 0), "cudaStreamWaitEvent");
@@ -816,6 +819,5 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
         sum_chunk_stats_kernel<<<1, 96, 0, st>>>(static_cast<const uint8_t *>(chunk_gram_workspaces), ws_stride, c, stats_out);
         rc = check_cuda(cudaGetLastError(), "sum_chunk_stats launch");
     }
-    cudaEventDestroy(ev);   // deferred by the runtime until the recorded work has completed
     return rc;
 }

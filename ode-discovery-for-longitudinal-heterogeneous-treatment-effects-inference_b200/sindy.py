@@ -87,8 +87,9 @@ class SINDY:
         # of 2023-05-16 (results/ablation/one_ode/...txt:6) to 2e-6.  The main-table log of 2023-05-14
         # (results/2_main_table/final_with_insite.txt:2362) was written by the revision before that fallback existed (the
         # commented-out line :632, `res.x` always): insite_zoom_failure_fallback=False reproduces it to 5e-15.
-        self.zoom_failure_fallback = bool(m.get('insite_zoom_failure_fallback', True))
         self.insite_line_search = str(m.get('insite_line_search', 'jax'))
+        # the robust line search reports status 3 for "exhausted at the noise floor, best point kept": no fallback there
+        self.zoom_failure_fallback = bool(m.get('insite_zoom_failure_fallback', self.insite_line_search == 'jax'))
         self.insite = m.insite
         self.wsindy = m.wsindy
         self.use_smoothed_finite_difference = m.use_smoothed_finite_difference

@@ -205,3 +205,18 @@ def test_quantised_population_model(dev):
                                              compact_evaluation=False), col)
     np.testing.assert_allclose([dense[k] for k in RMSE_KEYS], [res[k] for k in RMSE_KEYS], rtol=1e-10)
     assert abs(res['encoder_test_rmse_all'] - base['encoder_test_rmse_all']) > 1e-6
+
+
+def test_second_population_known_answer_seed10(dev):
+    """results/2_main_table/final_with_insite.txt:2094: population SINDy on the collection seeded with 10 (the run's
+    dataset cache held that collection): the 8 RMSEs and the 16 coefficients of the logged equation string."""
+    import ast
+    from b200_insite import runner
+    ref = ast.literal_eval(h.load_json('ref_logline_seed1.json')['sindy_seed10'])
+    col = _collection(seed=10)
+    res = runner.main(__import__('b200_insite.config', fromlist=['default_config']).default_config(insite=False, seed=10), col)
+    for k in RMSE_KEYS:
+        np.testing.assert_allclose(res[k], ref[k], rtol=1e-8, err_msg=k)
+    g, r = _parse_equation(res['global_equation_string']), _parse_equation(ref['global_equation_string'])
+    assert [[n for _, n in t] for t in g] == [[n for _, n in t] for t in r]
+    np.testing.assert_allclose([c for t in g for c, _ in t], [c for t in r for c, _ in t], rtol=1e-8)

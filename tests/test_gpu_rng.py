@@ -175,6 +175,22 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     assert torch.equal(d.params, b.params) and torch.equal(d.static, b.static)
     assert torch.equal(d.volume, b.volume) and torch.equal(d.codes, b.codes) and torch.equal(d.stats, a.stats)
     assert d.h2d_bytes(uni, reduced=True) == 33 * n
+    # the same step captured into a CUDA graph and replayed: new CONTENT in the same pinned buffers, same bits as eager
+    hp = junk.pin_memory()
+    e = GeneratedFitPipeline(n, T, seed=3, patient_base=1000, chunks=chunks)
+    res2 = torch.zeros_like(res).pin_memory()
+    for rep in range(3):
+        if rep == 2:      # refresh the inputs between replays
+            params2 = _cohort(n, 86)
+            blk2 = torch.from_numpy(dev.pack_params(params2))
+            hp.copy_(blk2); types.copy_(torch.from_numpy(np.asarray(params2['patient_types'], dtype=np.uint8)))
+        e.step_host(hp, None, res2, uniform=dev.cohort_scalar_rows(2.0, 2.0), types_u8=types, graph=True)
+    f = GeneratedFitPipeline(n, T, seed=3, patient_base=1000, chunks=chunks)
+    res3 = torch.zeros_like(res).pin_memory()
+    f.step_host(hp, None, res3, uniform=dev.cohort_scalar_rows(2.0, 2.0), types_u8=types)
+    torch.cuda.synchronize()
+    assert torch.equal(e.volume, f.volume) and torch.equal(e.codes, f.codes) and torch.equal(e.stats, f.stats)
+    assert torch.equal(res2, res3) and not torch.equal(e.volume, d.volume)
 
 
 def test_generated_counterfactual_draws_and_cohort(dev):

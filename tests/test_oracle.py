@@ -265,3 +265,27 @@ def test_lsq_initial_mask_restatement_is_pinned_by_the_reference_log(seed1):
         from sklearn.linear_model import ridge_regression
         np.testing.assert_allclose(c2[:3], ridge_regression(th[:, :3], xd, 0.5, tol=1e-6), rtol=1e-12)
 
+
+
+def test_population_fit_second_known_answer_seed10():
+    """A second pin of the restated population path: final_with_insite.txt:2094 (SINDy on the collection seeded with 10):
+    coefficients parsed from the logged equation string and the 8 RMSEs."""
+    import ast
+    import re
+    ref = ast.literal_eval(h.load_json('ref_logline_seed1.json')['sindy_seed10'])
+    o = h.oracle_collection(h.collection_inputs(10, 2.0, 1000, 100, 100))
+    means, stds = so.scaling_params(o['train'])
+    dtr, sc = sp.process_data(o['train'], means, stds)
+    coefs, sup, _ = sp.fit_population(dtr, sc)
+    logged = [float(c) for c in re.findall(r'\+(-?[0-9.]+(?:e-?[0-9]+)?)\*', ref['global_equation_string'])]
+    assert len(logged) == 16
+    np.testing.assert_allclose(coefs.reshape(-1), logged, rtol=1e-9)
+    d1, _ = sp.process_data(o['one'], means, stds)
+    orig, all_, last = sp.masked_rmse(sp.predictions_population(d1, sc, coefs), d1, sc)
+    np.testing.assert_allclose([all_, orig, last], [ref['encoder_test_rmse_all'], ref['encoder_test_rmse_orig'],
+                                                    ref['encoder_test_rmse_last']], rtol=1e-10)
+    d2, _ = sp.process_data(o['seq'], means, stds)
+    d2s = sp.process_sequential_test(d2, sc, 5)
+    ps = sp.slice_autoregressive(sp.predictions_population(d2, sc, coefs), d2['sequence_lengths'], 5)
+    np.testing.assert_allclose(sp.n_step_rmses(ps, d2s, sc), [ref[f'decoder_test_rmse_{k}-step'] for k in range(2, 7)],
+                               rtol=1e-10)
