@@ -494,6 +494,19 @@ B200I_API int b200i_theta_gram_dts(int64_t n, int32_t T, const double *cancer_vo
                            const double *static_feature, const double *dts, int32_t dts_per_row,
                            void *gram_workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * model.use_smoothed_finite_difference (sindy.py:196-198): pysindy SmoothedFiniteDifference with scipy's
+ * savgol_filter(window_length=2, polyorder=1) run over every fitting trajectory before the order-1 finite difference.
+ * With an even window the filter is the half-sample two-point mean: interior samples become (x[i] + x[i+1]) / 2, the
+ * first and last sample of a trajectory keep their value (mode='interp' refits them through two points).  Trajectories
+ * as b200i_theta_gram cuts them (joint = 0: constant-treatment snippets, which share their end sample with the next
+ * snippet's first sample -- both edges; joint = 1: columns 1..L of a patient).  smoothed_out (N,T) then replaces
+ * cancer_volume in b200i_theta_gram / _mode / _dts.  Not in-place.
+ * ---------------------------------------------------------------------------------------------- */
+B200I_API int b200i_smooth_snippets(int64_t n, int32_t T, const double *cancer_volume, const double *chemo_application,
+                           const double *radio_application, const double *sequence_lengths, int32_t joint,
+                           double *smoothed_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

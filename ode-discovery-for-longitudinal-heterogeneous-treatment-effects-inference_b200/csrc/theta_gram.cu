@@ -619,3 +619,51 @@ extern "C" int b200i_theta_gram_dts(int64_t n, int32_t T, const double *cancer_v
                                            static_feature, ws, dts, dts_per_row);
     return check_cuda(cudaGetLastError(), "theta_gram_dts launch");
 }
+
+// ------------------------------------------------------------------------------------------------
+// SmoothedFiniteDifference(smoother_kws={'window_length': 2, 'polyorder': 1}) pre-pass (sindy.py:196-198).
+// scipy.signal.savgol_filter with an even window fits its line at the half-sample position: every interior sample of a
+// trajectory becomes (x[i] + x[i+1]) / 2, the first and last sample are refitted through their two neighbours and stay
+// x[i] (mode='interp').  The trajectories are the ones theta_gram cuts: per-treatment snippets share their end sample
+// with the next snippet's first sample, and both are edge samples, so one smoothed copy of the row serves every snippet;
+// joint model: one trajectory per patient over columns 1..L.  The smoothed row then goes through the ordinary
+// statistics kernels (pysindy >= 1.7.4 builds the library from the smoothed samples as well).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) smooth_snippets_kernel(int64_t n, int T, const double *__restrict__ vol,
+                                                              const double *__restrict__ chemo,
+                                                              const double *__restrict__ radio,
+                                                              const double *__restrict__ seq, int joint,
+                                                              double *__restrict__ out)
+{
+    const int64_t total = n * (int64_t)T;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = idx / T;
+        const int i = (int)(idx - p * T);
+        const int L = (int)seq[p];
+        const double x = vol[idx];
+        bool edge;
+        if (joint)
+            edge = i <= 1 || i >= L;
+        else
+            edge = i == 0 || i >= L || chemo[idx] != chemo[idx - 1] || radio[idx] != radio[idx - 1];
+        out[idx] = (edge || i + 1 >= T) ? x : 0.5 * x + 0.5 * vol[idx + 1];
+    }
+}
+
+extern "C" int b200i_smooth_snippets(int64_t n, int32_t T, const double *cancer_volume, const double *chemo_application,
+                                     const double *radio_application, const double *sequence_lengths, int32_t joint,
+                                     double *smoothed_out, void *stream)
+{
+    B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths && smoothed_out,
+                  B200I_E_ARG, "smooth_snippets: NULL argument or negative n");
+    B200I_REQUIRE(T >= 2, B200I_E_UNSUPPORTED, "smooth_snippets: T=%d < 2", T);
+    B200I_REQUIRE(smoothed_out != cancer_volume, B200I_E_ARG, "smooth_snippets: the pass is not in-place");
+    if (n == 0) return 0;
+    const int64_t total = n * (int64_t)T;
+    int64_t grid = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    smooth_snippets_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, T, cancer_volume, chemo_application, radio_application, sequence_lengths, joint, smoothed_out);
+    return check_cuda(cudaGetLastError(), "smooth_snippets launch");
+}

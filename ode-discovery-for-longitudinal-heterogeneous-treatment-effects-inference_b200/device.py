@@ -306,6 +306,21 @@ def theta_gram(cancer_volume, chemo_application, radio_application, sequence_len
     return ws[:STATS_DOUBLES]
 
 
+def smooth_snippets(cancer_volume, chemo_application, radio_application, sequence_lengths, joint=False):
+    """model.use_smoothed_finite_difference pre-pass (sindy.py:196-198): the half-sample two-point Savitzky-Golay mean
+    over every fitting trajectory, edges kept (see include/b200i.h).  Dense (N,T) float64 in, new (N,T) tensor out."""
+    lib = _native.load()
+    n, T = cancer_volume.shape
+    for a in (cancer_volume, chemo_application, radio_application):
+        if not a.is_contiguous() or a.shape != cancer_volume.shape:
+            raise ValueError("smooth_snippets takes dense (N,T) rows")
+    out = torch.empty_like(cancer_volume)
+    rc = lib.b200i_smooth_snippets(n, T, _ptr(cancer_volume), _ptr(chemo_application), _ptr(radio_application),
+                                   _ptr(sequence_lengths), 1 if joint else 0, _ptr(out), _stream())
+    _native.check(rc, "b200i_smooth_snippets")
+    return out
+
+
 def theta_gram_dts(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature, dts,
                    tag="default"):
     """K4 on an irregular time grid: dts (T-1,) or (N,T-1) interval lengths.  Returns the (68,) packed statistics

@@ -108,7 +108,7 @@ class SINDY:
         self.last_fit_info = {}
         if self.dataset_name != 'CANCER_SIM':
             raise NotImplementedError(f"dataset {m.dataset_name!r}: only cancer_sim is on the accelerated path")
-        for flag in ('wsindy', 'smooth_input_data', 'use_smoothed_finite_difference', 'ablation_more_complex_basis_functions'):
+        for flag in ('wsindy', 'smooth_input_data', 'ablation_more_complex_basis_functions'):
             if getattr(self, flag):
                 raise NotImplementedError(f"model.{flag}=True is outside the accelerated INSITE path (SURVEY.md §8a/f)")
         if self.joint_model:
@@ -170,8 +170,13 @@ class SINDY:
         chemo = np.zeros((n, T)); radio = np.zeros((n, T))
         chemo[:, :T - 1] = (codes & 1)
         radio[:, :T - 1] = (codes >> 1) & 1
-        stats = dev.theta_gram(dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio),
-                               dev.to_device(seq.astype(np.float64)), dev.to_device(static), fd_dt=self.dt,
+        vol_d, chemo_d, radio_d = dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio)
+        seq_d = dev.to_device(seq.astype(np.float64))
+        if self.use_smoothed_finite_difference:
+            # SmoothedFiniteDifference(window_length=2, polyorder=1), sindy.py:196-198: the trajectories are smoothed,
+            # then differentiated and expanded as usual
+            vol_d = dev.smooth_snippets(vol_d, chemo_d, radio_d, seq_d, joint=bool(self.joint_model))
+        stats = dev.theta_gram(vol_d, chemo_d, radio_d, seq_d, dev.to_device(static), fd_dt=self.dt,
                                joint=bool(self.joint_model))
         if self.joint_model:
             coefs11, support11, c44 = dev.stlsq_joint(stats, threshold=self.sindy_threshold, alpha=self.sindy_alpha,

@@ -137,12 +137,28 @@ def finite_difference_order1(x, dt):
     return xd
 
 
+def savgol_w2_p1(x):
+    """scipy.signal.savgol_filter(x, window_length=2, polyorder=1, axis=0) restated: pysindy's SmoothedFiniteDifference
+    with the reference's smoother_kws (sindy.py:196-198).  savgol_coeffs of an even window evaluates its line fit at the
+    half-sample position (pos = halflen - 0.5), i.e. weights [0.5, 0.5]; convolve1d places them on samples i and i+1;
+    mode='interp' refits the first and the last sample through the outermost two samples, which returns them unchanged
+    (up to lstsq rounding).  Pinned against scipy itself in tests/test_oracle.py."""
+    x = np.asarray(x, dtype=np.float64)
+    y = x.copy()
+    y[1:-1] = 0.5 * x[1:-1] + 0.5 * x[2:]
+    return y
+
+
 def library_p4(x, u):
     """PolynomialLibrary(degree=2, interaction_only=True) on [x0, u0] -> [1, x0, u0, x0 u0]."""
     return np.stack([np.ones_like(x), x, u, x * u], axis=1)
 
 
-def design_matrices(snippets, dt=STANDARD_DT):
+def design_matrices(snippets, dt=STANDARD_DT, smoothed=False):
+    """smoothed: SmoothedFiniteDifference -- pysindy (>= 1.7.4, FeatureLibrary.calc_trajectory) differentiates the
+    smoothed trajectory and builds the library from it as well."""
+    if smoothed:
+        snippets = [(savgol_w2_p1(x), u) for x, u in snippets]
     th = np.concatenate([library_p4(x, u) for x, u in snippets], axis=0)
     xd = np.concatenate([finite_difference_order1(x, dt) for x, _ in snippets], axis=0)
     return th, xd
@@ -179,13 +195,13 @@ def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True):
     return coef, ind
 
 
-def fit_population(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
+def fit_population(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT, smoothed=False):
     """sindy.py:160-213, 332-336 -> joint_coefs (4,4), support (4,4) bool."""
     buckets = de_format_snippets(data, scaling)
     coefs, sup = np.zeros((4, 4)), np.zeros((4, 4), dtype=bool)
     stats = []
     for a in range(4):
-        th, xd = design_matrices(buckets[a], dt)
+        th, xd = design_matrices(buckets[a], dt, smoothed)
         coefs[a], sup[a] = stlsq_fit(th, xd, threshold, alpha)
         stats.append((len(buckets[a]), th.shape[0]))
     return coefs, sup, stats
@@ -218,15 +234,17 @@ def library_p11(x, U):
     return np.stack([np.ones_like(x), x, u0, u1, u2, x * u0, x * u1, x * u2, u0 * u1, u0 * u2, u1 * u2], axis=1)
 
 
-def design_matrices_joint(trajs, dt=STANDARD_DT):
+def design_matrices_joint(trajs, dt=STANDARD_DT, smoothed=False):
+    if smoothed:
+        trajs = [(savgol_w2_p1(x), U) for x, U in trajs]
     th = np.concatenate([library_p11(x, U) for x, U in trajs], axis=0)
     xd = np.concatenate([finite_difference_order1(x, dt) for x, _ in trajs], axis=0)
     return th, xd
 
 
-def fit_population_joint(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
+def fit_population_joint(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT, smoothed=False):
     """sindy.py:185-204 with joint_model=True -> joint_coefs (1,11), support (11,), number of rows."""
-    th, xd = design_matrices_joint(de_format_joint(data, scaling), dt)
+    th, xd = design_matrices_joint(de_format_joint(data, scaling), dt, smoothed)
     coef, sup = stlsq_fit(th, xd, threshold, alpha)
     return coef[None, :], sup, th.shape[0]
 

@@ -289,3 +289,14 @@ def test_population_fit_second_known_answer_seed10():
     ps = sp.slice_autoregressive(sp.predictions_population(d2, sc, coefs), d2['sequence_lengths'], 5)
     np.testing.assert_allclose(sp.n_step_rmses(ps, d2s, sc), [ref[f'decoder_test_rmse_{k}-step'] for k in range(2, 7)],
                                rtol=1e-10)
+
+
+def test_savgol_window2_restatement_equals_scipy():
+    """pysindy SmoothedFiniteDifference(smoother_kws={'window_length': 2, 'polyorder': 1}) (sindy.py:196-198) calls
+    scipy.signal.savgol_filter(x, axis=0): scipy is installed here, so the restatement is pinned on the real thing."""
+    from scipy.signal import savgol_filter
+    rng = np.random.default_rng(3)
+    for L in (2, 3, 4, 5, 9, 31, 60):
+        x = rng.uniform(0.1, 1200.0, size=(L, 1))
+        np.testing.assert_allclose(sp.savgol_w2_p1(x[:, 0]), savgol_filter(x, window_length=2, polyorder=1, axis=0)[:, 0],
+                                   rtol=1e-13)
