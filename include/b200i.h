@@ -507,6 +507,35 @@ B200I_API int b200i_smooth_snippets(int64_t n, int32_t T, const double *cancer_v
                            const double *radio_application, const double *sequence_lengths, int32_t joint,
                            double *smoothed_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * model.ablation_more_complex_basis_functions (sindy.py:185-186): PolynomialLibrary(degree=4, interaction_only=False)
+ * over [x0 = volume, u0 = patient type] for the four per-treatment models -- 15 monomials x0^a u0^b in sklearn's
+ * order: 1, x0, u0, x0^2, x0 u0, u0^2, x0^3, x0^2 u0, x0 u0^2, u0^3, x0^4, x0^3 u0, x0^2 u0^2, x0 u0^3, u0^4.
+ * The library is rank deficient on every cancer_sim cohort (three patient types) and spans 13 orders of magnitude, so
+ * the statistics are the R factors of [Theta | xdot] (tall-skinny QR by Givens rotations), not normal equations, and
+ * the STLSQ passes solve through a one-sided Jacobi SVD of R[:, support]: ridge (Theta^T Theta + alpha I)^-1 Theta^T xdot
+ * as sklearn's ridge_regression, the final un-biasing as scipy.linalg.lstsq (minimum norm, singular values below
+ * rcond * s_max dropped; rcond <= 0 selects machine epsilon = scipy's cond=None).
+ *
+ * b200i_poly_tsqr: trajectories, finite differences and sample rows exactly as b200i_theta_gram (dense (N,T) rows).
+ *   r_out: 4 * 256 + 4 doubles = the four row-major 16x16 upper-triangular factors (columns 0..14 the monomials, 15 the
+ *   derivative) followed by the four sample counts.  workspace: b200i_poly_workspace_bytes().
+ * b200i_poly_stlsq: r_out -> coefs (4,15) float64, support (4,15) int32 (pysindy STLSQ + unbias, pkpd/utils.py:274-310).
+ * b200i_poly_rollout: b200i_ode_rollout for dx/dt = sum_j c[code][j] x^a_j u^b_j (terms with |c| <= drop_below dropped,
+ *   pkpd/utils.py:388), explicit Euler with `substeps` per interval (pkpd/utils.py:40,68-90); W <= 128.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200I_POLY_TERMS 15
+#define B200I_POLY_R_DOUBLES (4 * 256 + 4)
+B200I_API int64_t b200i_poly_workspace_bytes(void);
+B200I_API int b200i_poly_tsqr(int64_t n, int32_t T, double fd_dt, const double *cancer_volume,
+                     const double *chemo_application, const double *radio_application, const double *sequence_lengths,
+                     const double *static_feature, void *workspace, double *r_out, void *stream);
+B200I_API int b200i_poly_stlsq(const double *r_factors, double threshold, double alpha, int32_t max_iter, double rcond,
+                      double *coefs_out, int32_t *support_out, void *stream);
+B200I_API int b200i_poly_rollout(int64_t rows, int32_t W, double dt, int32_t substeps, const double *x0,
+                        const double *static_feature, const uint8_t *codes, const double *coefs, double drop_below,
+                        double *pred, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ SIGNATURES = {
                                                                              c_i32, c_vp, c_vp]),
     "b200i_insite_bfgs_dts": (ctypes.c_int, [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_f64, c_f64, c_i32,
                                              c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "b200i_poly_workspace_bytes": (c_i64, []),
+    "b200i_poly_tsqr": (ctypes.c_int, [c_i64, c_i32, ctypes.c_double] + [c_vp] * 8),
+    "b200i_poly_stlsq": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, c_i32, ctypes.c_double, c_vp, c_vp, c_vp]),
+    "b200i_poly_rollout": (ctypes.c_int, [c_i64, c_i32, ctypes.c_double, c_i32] + [c_vp] * 4 + [ctypes.c_double, c_vp, c_vp]),
     "b200i_smooth_snippets": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 4 + [c_i32, c_vp, c_vp]),
     "b200i_theta_gram_dts": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 6 + [c_i32, c_vp, c_vp]),
     "b200i_expand_cf_one_step": (ctypes.c_int, [c_i64, c_i32] + [c_vp] * 5 + [c_i64, c_i64] + [c_vp] * 5 + [c_vp]),

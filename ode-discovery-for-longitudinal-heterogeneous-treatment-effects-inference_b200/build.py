@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libb200insite.so")
-SOURCES = ["runtime.cu", "sim_factual.cu", "theta_gram.cu", "fit_rollout.cu", "sim_cf.cu", "insite_fit.cu", "cf_eval.cu"]  # missing files are skipped
+SOURCES = ["runtime.cu", "sim_factual.cu", "theta_gram.cu", "fit_rollout.cu", "sim_cf.cu", "insite_fit.cu", "cf_eval.cu", "poly_library.cu"]  # missing files are skipped
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

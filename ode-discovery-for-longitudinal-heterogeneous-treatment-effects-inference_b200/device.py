@@ -306,6 +306,53 @@ def theta_gram(cancer_volume, chemo_application, radio_application, sequence_len
     return ws[:STATS_DOUBLES]
 
 
+POLY_TERMS = 15
+# PolynomialLibrary(degree=4, interaction_only=False).get_feature_names() over [x0, u0] (sklearn's monomial order)
+POLY_FEATURE_LIBRARY_NAMES = ('1', 'x0', 'u0', 'x0^2', 'x0 u0', 'u0^2', 'x0^3', 'x0^2 u0', 'x0 u0^2', 'u0^3',
+                              'x0^4', 'x0^3 u0', 'x0^2 u0^2', 'x0 u0^3', 'u0^4')
+
+
+def poly_tsqr(cancer_volume, chemo_application, radio_application, sequence_lengths, static_feature, fd_dt=STANDARD_DT):
+    """Degree-4 library statistics (sindy.py:185-186): the four 16x16 R factors of [Theta | xdot] (tall-skinny QR) and
+    the four sample counts, (4*256 + 4,) float64 on the device.  Dense (N,T) rows."""
+    lib = _native.load()
+    n, T = cancer_volume.shape
+    for a in (cancer_volume, chemo_application, radio_application):
+        if not a.is_contiguous() or a.shape != cancer_volume.shape:
+            raise ValueError("poly_tsqr takes dense (N,T) rows")
+    key = (torch.cuda.current_device(), "poly")
+    if key not in _workspaces:
+        _workspaces[key] = torch.zeros((lib.b200i_poly_workspace_bytes() + 7) // 8, dtype=torch.float64, device='cuda')
+    out = torch.empty(4 * 256 + 4, dtype=torch.float64, device='cuda')
+    rc = lib.b200i_poly_tsqr(n, T, float(fd_dt), _ptr(cancer_volume), _ptr(chemo_application), _ptr(radio_application),
+                             _ptr(sequence_lengths), _ptr(static_feature), _ptr(_workspaces[key]), _ptr(out), _stream())
+    _native.check(rc, "b200i_poly_tsqr")
+    return out
+
+
+def poly_stlsq(r_factors, threshold=1e-3, alpha=0.5, max_iter=100, rcond=0.0):
+    """pysindy STLSQ + unbias on the R factors -> (coefs (4,15) float64, support (4,15) int32) on the device.
+    rcond <= 0: machine epsilon (scipy.linalg.lstsq's default cut-off)."""
+    lib = _native.load()
+    coefs = torch.empty((4, POLY_TERMS), dtype=torch.float64, device='cuda')
+    support = torch.empty((4, POLY_TERMS), dtype=torch.int32, device='cuda')
+    rc = lib.b200i_poly_stlsq(_ptr(r_factors), float(threshold), float(alpha), int(max_iter), float(rcond), _ptr(coefs),
+                              _ptr(support), _stream())
+    _native.check(rc, "b200i_poly_stlsq")
+    return coefs, support
+
+
+def poly_rollout(x0, static_feature, codes, coefs, dt=STANDARD_DT, substeps=STEPS_FOR_DT, drop_below=1e-3):
+    """K6 for the degree-4 library: codes (R,W) uint8, coefs (4,15) -> (R,W) un-scaled predictions."""
+    lib = _native.load()
+    rows, W = codes.shape
+    out = torch.empty((rows, W), dtype=torch.float64, device='cuda')
+    rc = lib.b200i_poly_rollout(rows, W, float(dt), int(substeps), _ptr(x0), _ptr(static_feature), _ptr(codes), _ptr(coefs),
+                                float(drop_below), _ptr(out), _stream())
+    _native.check(rc, "b200i_poly_rollout")
+    return out
+
+
 def smooth_snippets(cancer_volume, chemo_application, radio_application, sequence_lengths, joint=False):
     """model.use_smoothed_finite_difference pre-pass (sindy.py:196-198): the half-sample two-point Savitzky-Golay mean
     over every fitting trajectory, edges kept (see include/b200i.h).  Dense (N,T) float64 in, new (N,T) tensor out."""

@@ -12,8 +12,11 @@ What runs where
     tau-step slicing         get_autoregressive_predictions (sindy.py:717-760)
     metrics                  numpy on the host, formulas of time_varying_model.py:236-313
 
-Not implemented (outside the cancer_sim hot path): Weak-SINDy, EQ_4/EQ_5 datasets, smoothing /
-quantisation options, the degree-4 library, ray-tune finetune.  They raise NotImplementedError.
+Options: joint_model (11-term library), sindy_quantize, use_smoothed_finite_difference (smoothing pre-pass ahead of
+K4), ablation_more_complex_basis_functions (degree-4 library, population models: csrc/poly_library.cu).
+
+Not implemented (outside the cancer_sim hot path): Weak-SINDy, EQ_4/EQ_5 datasets, smooth_input_data,
+ray-tune finetune, the degree-4 library for the joint model or under INSITE.  They raise NotImplementedError.
 """
 import logging
 
@@ -108,9 +111,13 @@ class SINDY:
         self.last_fit_info = {}
         if self.dataset_name != 'CANCER_SIM':
             raise NotImplementedError(f"dataset {m.dataset_name!r}: only cancer_sim is on the accelerated path")
-        for flag in ('wsindy', 'smooth_input_data', 'ablation_more_complex_basis_functions'):
+        for flag in ('wsindy', 'smooth_input_data'):
             if getattr(self, flag):
                 raise NotImplementedError(f"model.{flag}=True is outside the accelerated INSITE path (SURVEY.md §8a/f)")
+        if self.ablation_more_complex_basis_functions and (self.joint_model or self.insite):
+            raise NotImplementedError("ablation_more_complex_basis_functions: the degree-4 library is built for the four "
+                                      "per-treatment population models (15 terms each); the joint model's 70 terms and "
+                                      "the INSITE step over up to 60 coefficients are not")
         if self.joint_model:
             # the "one ODE" ablation (results/ablation/one_ode): 11-term library, multilabel treatments
             if self.treatment_mode != 'multilabel':
@@ -176,6 +183,23 @@ class SINDY:
             # SmoothedFiniteDifference(window_length=2, polyorder=1), sindy.py:196-198: the trajectories are smoothed,
             # then differentiated and expanded as usual
             vol_d = dev.smooth_snippets(vol_d, chemo_d, radio_d, seq_d, joint=bool(self.joint_model))
+        if self.ablation_more_complex_basis_functions:
+            # PolynomialLibrary(degree=4, interaction_only=False), sindy.py:185-186: R factors instead of normal equations
+            rf = dev.poly_tsqr(vol_d, chemo_d, radio_d, seq_d, dev.to_device(static), fd_dt=self.dt)
+            coefs, support = dev.poly_stlsq(rf, threshold=self.sindy_threshold, alpha=self.sindy_alpha, max_iter=100)
+            torch.cuda.current_stream().synchronize()
+            self.joint_coefs = coefs.cpu().numpy()                             # (4, 15), sindy.py:334
+            self.support_ = support.cpu().numpy().astype(bool)
+            self.population_stats_ = rf.cpu().numpy().copy()
+            self.feature_library_names = list(dev.POLY_FEATURE_LIBRARY_NAMES)
+            self.feature_names = list(FEATURE_NAMES)
+            strs = [equation_string_core(self.feature_library_names, self.feature_names, self.joint_coefs[a],
+                                         quantize=self.sindy_quantize,
+                                         quantize_round_to=self.sindy_quantize_global_model_round_to) for a in range(4)]
+            self.global_equation_string = (f'Treatment 0: x_dot = {strs[0]} | Treatment 1: x_dot = {strs[1]} | '
+                                           f'Treatment 2: x_dot = {strs[2]} | Treatment 3: x_dot = {strs[3]}')
+            logger.info('[Model]: ' + self.global_equation_string)
+            return self
         stats = dev.theta_gram(vol_d, chemo_d, radio_d, seq_d, dev.to_device(static), fd_dt=self.dt,
                                joint=bool(self.joint_model))
         if self.joint_model:
@@ -230,6 +254,12 @@ class SINDY:
         return predictions
 
     def _rollout(self, prev, static, codes, coefs_dev, drop_below):
+        if self.ablation_more_complex_basis_functions:
+            pred = dev.poly_rollout(dev.to_device(np.ascontiguousarray(prev[:, 0])), dev.to_device(static),
+                                    dev.to_device(codes, dtype=torch.uint8), coefs_dev, dt=self.dt,
+                                    substeps=dev.STEPS_FOR_DT, drop_below=drop_below)
+            torch.cuda.current_stream().synchronize()
+            return pred.cpu().numpy()
         pred = dev.ode_rollout(dev.to_device(np.ascontiguousarray(prev[:, 0])), dev.to_device(static),
                                dev.to_device(codes, dtype=torch.uint8), coefs_dev, dt=self.dt,
                                substeps=dev.STEPS_FOR_DT, drop_below=drop_below)
@@ -307,7 +337,8 @@ class SINDY:
         """The RMSEs of a counterfactual test set from its compact cohort (None when the dense path has to run: no
         compact cohort, switched off, or INSITE on the joint model)."""
         compact = getattr(dataset, 'compact_', None) if self.compact_evaluation else None
-        if compact is None or compact[0].kind != kind or (self.joint_model and self.insite):
+        if compact is None or compact[0].kind != kind or (self.joint_model and self.insite) or \
+                self.ablation_more_complex_basis_functions:     # the compact kernels integrate the affine ODE
             return None
         from . import compact_eval as ce
         cohort, static = compact

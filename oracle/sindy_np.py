@@ -154,6 +154,23 @@ def library_p4(x, u):
     return np.stack([np.ones_like(x), x, u, x * u], axis=1)
 
 
+POLY4_EXPONENTS = tuple((d - b, b) for d in range(5) for b in range(d + 1))     # (a, b) of x0^a u0^b, sklearn's order
+POLY4_NAMES = ('1', 'x0', 'u0', 'x0^2', 'x0 u0', 'u0^2', 'x0^3', 'x0^2 u0', 'x0 u0^2', 'u0^3',
+               'x0^4', 'x0^3 u0', 'x0^2 u0^2', 'x0 u0^3', 'u0^4')
+
+
+def library_poly4(x, u):
+    """PolynomialLibrary(degree=4, interaction_only=False) on [x0, u0] (sindy.py:185-186): 15 monomials, by total degree
+    and lexicographic within a degree (sklearn PolynomialFeatures / pysindy get_feature_names order, POLY4_NAMES)."""
+    return np.stack([x ** a * u ** b for a, b in POLY4_EXPONENTS], axis=1)
+
+
+def design_matrices_poly4(snippets, dt=STANDARD_DT):
+    th = np.concatenate([library_poly4(x, u) for x, u in snippets], axis=0)
+    xd = np.concatenate([finite_difference_order1(x, dt) for x, _ in snippets], axis=0)
+    return th, xd
+
+
 def design_matrices(snippets, dt=STANDARD_DT, smoothed=False):
     """smoothed: SmoothedFiniteDifference -- pysindy (>= 1.7.4, FeatureLibrary.calc_trajectory) differentiates the
     smoothed trajectory and builds the library from it as well."""
@@ -164,9 +181,13 @@ def design_matrices(snippets, dt=STANDARD_DT, smoothed=False):
     return th, xd
 
 
-def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True):
+def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True, scipy_lstsq=False):
     """pysindy STLSQ.  Loop: pkpd/utils.py:274-310 (vendored copy); ridge: :228; unbias: pysindy
-    BaseOptimizer._unbias (LinearRegression without intercept on the final support)."""
+    BaseOptimizer._unbias (LinearRegression without intercept on the final support).
+    scipy_lstsq: un-bias with scipy.linalg.lstsq(X, y) directly -- what LinearRegression called in the scikit-learn of
+    the reference's time (<= 1.2: cut-off = machine epsilon); the one installed here passes cond=tol=1e-6, which matters
+    only for rank-deficient libraries (degree 4)."""
+    import warnings
     from sklearn.linear_model import ridge_regression, LinearRegression
     n_feat = theta.shape[1]
     ind = np.ones(n_feat, dtype=bool)
@@ -177,7 +198,9 @@ def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True):
         if np.count_nonzero(ind) == 0:
             coef = np.zeros(n_feat)
             break
-        c_i = ridge_regression(theta[:, ind], xdot, alpha, tol=1e-6)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')            # scipy's ill-conditioning warning on the degree-4 library
+            c_i = ridge_regression(theta[:, ind], xdot, alpha, tol=1e-6)
         c = np.zeros(n_feat)
         c[ind] = c_i
         big = np.abs(c) >= threshold
@@ -190,9 +213,50 @@ def stlsq_fit(theta, xdot, threshold, alpha, max_iter=100, unbias=True):
         n_sel = np.sum(ind)
     if unbias and np.any(ind):
         c = np.zeros(n_feat)
-        c[ind] = LinearRegression(fit_intercept=False).fit(theta[:, ind], xdot).coef_
+        if scipy_lstsq:
+            import scipy.linalg
+            c[ind] = scipy.linalg.lstsq(theta[:, ind], xdot)[0]
+        else:
+            c[ind] = LinearRegression(fit_intercept=False).fit(theta[:, ind], xdot).coef_
         coef = c
     return coef, ind
+
+
+def fit_population_poly4(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT):
+    """sindy.py:160-213 with ablation_more_complex_basis_functions -> joint_coefs (4,15), support (4,15) bool, and the
+    explicit design matrices per treatment (for the statistics checks)."""
+    buckets = de_format_snippets(data, scaling)
+    coefs, sup, mats = np.zeros((4, 15)), np.zeros((4, 15), dtype=bool), []
+    for a in range(4):
+        th, xd = design_matrices_poly4(buckets[a], dt)
+        coefs[a], sup[a] = stlsq_fit(th, xd, threshold, alpha, scipy_lstsq=True)
+        mats.append((th, xd))
+    return coefs, sup, mats
+
+
+def rollout_unscaled_poly4(x0, codes, u, coefs, dt=STANDARD_DT, steps=STEPS_FOR_DT):
+    """rollout_unscaled for dx/dt = sum_j coefs[code, j] x^a_j u^b_j (the sympy expression of the degree-4 model)."""
+    R, W = codes.shape
+    v = x0.astype(np.float64).copy()
+    out = np.empty((R, W))
+    h = dt / steps
+    for k in range(W):
+        c = coefs[codes[:, k]]
+        for _ in range(steps):
+            f = np.zeros(R)
+            for j, (a, b) in enumerate(POLY4_EXPONENTS):
+                f = f + c[:, j] * v ** a * u ** b
+            v = v + f * h
+        out[:, k] = v
+    return out
+
+
+def predictions_population_poly4(data, scaling, coefs):
+    prev = np.squeeze(data['prev_outputs'] * scaling['output_stds'] + scaling['output_means'], -1)
+    static = data['static_features'] * scaling['inputs_stds'][1:2] + scaling['input_means'][1:2]
+    codes = np.argmax(data['current_treatments'], axis=-1)
+    un = rollout_unscaled_poly4(prev[:, 0], codes, static[:, 0], effective_coefs(coefs))
+    return ((un - scaling['output_means']) / scaling['output_stds'])[..., None]
 
 
 def fit_population(data, scaling, threshold=1e-3, alpha=0.5, dt=STANDARD_DT, smoothed=False):
