@@ -515,7 +515,10 @@ B200I_API int b200i_smooth_snippets(int64_t n, int32_t T, const double *cancer_v
  * the statistics are the R factors of [Theta | xdot] (tall-skinny QR by Givens rotations), not normal equations, and
  * the STLSQ passes solve through a one-sided Jacobi SVD of R[:, support]: ridge (Theta^T Theta + alpha I)^-1 Theta^T xdot
  * as sklearn's ridge_regression, the final un-biasing as scipy.linalg.lstsq (minimum norm, singular values below
- * rcond * s_max dropped; rcond <= 0 selects machine epsilon = scipy's cond=None).
+ * rcond * s_max dropped; rcond <= 0 selects eps * max(samples, 15), numpy.linalg.lstsq's default.  On cancer_sim data
+ * the genuine singular values of a support stop at ~3e-4 * s_max and the three null directions sit at ~1e-17 * s_max,
+ * so every cut-off between scipy's own default of the reference's time -- machine epsilon, a factor 4 above that
+ * noise -- and today's scikit-learn (cond = 1e-6) gives the same solution).
  *
  * b200i_poly_tsqr: trajectories, finite differences and sample rows exactly as b200i_theta_gram (dense (N,T) rows).
  *   r_out: 4 * 256 + 4 doubles = the four row-major 16x16 upper-triangular factors (columns 0..14 the monomials, 15 the

@@ -9,11 +9,11 @@
 // the squared condition number buries the two smallest genuine singular values.  So the statistics here are the
 // R factor of [Theta | xdot] per treatment (16 x 16), built by a tall-skinny QR:
 //
-//   poly_tsqr_kernel      16-lane workers; lane j owns column j of the worker's four R factors (shared memory) and
-//                         element j of the incoming sample row; every sample row is rotated in with 16 Givens
-//                         rotations (column-wise backward stable, so graded columns keep their relative accuracy);
-//                         the workers of a CTA are merged the same way (rows of a triangular factor are sample rows
-//                         whose leading zeros are skipped), one CTA factor per treatment goes to scratch.
+//   poly_tsqr_kernel      16-lane workers, one treatment each; lane j owns column j of the worker's R factor
+//                         (registers) and element j of every sample row.  Rows are buffered 16 at a time in shared
+//                         memory and folded into R by 16 Householder reflections of [R; B] (column-wise backward
+//                         stable, so the graded columns keep their relative accuracy); the workers of a CTA and then
+//                         the CTAs are merged the same way (a triangular factor is a block of 16 sample rows).
 //   poly_tsqr_merge_kernel one CTA, one 16-lane group per treatment: merges the CTA factors in a fixed order.
 //   poly_stlsq_kernel     one warp per treatment: pysindy STLSQ on the R factor.  Ridge and minimum-norm solutions come
 //                         from a one-sided Jacobi SVD of R[:, support] (lane r owns row r):
@@ -31,8 +31,7 @@ namespace b200i {
 
 constexpr int PQ = 16;                 // 15 monomials + the derivative column
 constexpr int PT = B200I_POLY_TERMS;   // 15
-constexpr int TSQR_WORKERS = 8;        // 16-lane workers per CTA (256 threads would be 16; 128 threads = 8)
-constexpr int TSQR_MAX_CTAS = 296;
+constexpr int TSQR_MAX_CTAS = 444;
 
 // exponents (a, b) of x^a u^b in sklearn's PolynomialFeatures order: by total degree, then lexicographic with x first
 __constant__ int8_t c_poly_a[PT] = {0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0};
@@ -45,95 +44,166 @@ __device__ __forceinline__ double ipow4(double x, int e)
     return r;
 }
 
-// Rotate the row held across the 16 lanes of a group (lane j: v_j) into the upper-triangular R (row-major 16x16 in
-// shared memory, lane j touches column j only).  `first`: leading zeros of the row (rotations before it are skipped).
-__device__ __forceinline__ void givens_insert(double *R, double v, int lane16, int first, unsigned gmask)
+// Block update of a warp's R factor (shared memory, row-major 16 x 16).  Lane l owns column j = l & 15 of R and of one
+// 16-row block of the 32 buffered sample rows: b[r] = B[16 * (l >> 4) + r][j] (registers).  [R; B] (48 x 16) is brought
+// back to triangular form by 16 Householder reflections; reflection k only involves R[k][:] and B (R's other rows are
+// zero in column k); its vector (v0, B[:, k]) lives in lanes k and 16 + k, which publish it in shared memory (vk);
+// every lane updates its half column with fused multiply-add chains, the two halves of a dot product meet through one
+// shuffle.  ~50 warp instructions per sample row and ~75 registers (three CTAs per SM); the row-by-row Givens version
+// of the first cut needed ~2000 instructions per row of a 16-lane group, with a square root and two divisions per
+// rotation.
+constexpr int VK_HALF = PQ + 2;        // the halves' copies of the reflector sit in different banks
+__device__ __forceinline__ void householder_fold(double *Rs, const double *Bs, double *vk, int lane)
 {
-    for (int k = first; k < PQ; ++k) {
-        const double t = R[k * PQ + lane16];
-        const double rkk = __shfl_sync(gmask, t, k, 16);
-        const double vk = __shfl_sync(gmask, v, k, 16);
-        if (vk != 0.0) {                                  // uniform within the group
-            const double r = sqrt(rkk * rkk + vk * vk);
-            const double c = rkk / r, s = vk / r;
-            if (lane16 >= k) {
-                R[k * PQ + lane16] = c * t + s * v;
-                v = c * v - s * t;
-            }
-            if (lane16 == k) v = 0.0;
+    const int col = lane & 15, half = lane >> 4;
+    double b[PQ];
+#pragma unroll
+    for (int r = 0; r < PQ; ++r) b[r] = Bs[(half * PQ + r) * PQ + col];
+    double *myvk = vk + half * VK_HALF;
+#pragma unroll
+    for (int k = 0; k < PQ; ++k) {
+        double sg0 = 0.0, sg1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < PQ; r += 2) {
+            sg0 = fma(b[r], b[r], sg0);
+            sg1 = fma(b[r + 1], b[r + 1], sg1);
         }
+        double sig_k = __shfl_sync(0xffffffffu, sg0 + sg1, k, 16);
+        sig_k += __shfl_xor_sync(0xffffffffu, sig_k, 16);
+        if (sig_k == 0.0) continue;                       // nothing below the diagonal in column k (warp-uniform)
+        if (col == k) {
+#pragma unroll
+            for (int r = 0; r < PQ; ++r) myvk[r] = b[r];
+        }
+        const double rk = Rs[k * PQ + col], alpha = Rs[k * PQ + k];
+        __syncwarp();
+        const double nrm = sqrt(fma(alpha, alpha, sig_k));
+        const double beta = alpha >= 0.0 ? -nrm : nrm;
+        const double v0 = alpha - beta;                   // no cancellation: alpha and -beta share their sign
+        const double tau = 2.0 / fma(v0, v0, sig_k);
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < PQ; r += 2) {
+            d0 = fma(myvk[r], b[r], d0);
+            d1 = fma(myvk[r + 1], b[r + 1], d1);
+        }
+        double d = d0 + d1;
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        const double w = tau * fma(v0, rk, d);
+        if (col > k) {
+            if (half == 0) Rs[k * PQ + col] = fma(-w, v0, rk);
+#pragma unroll
+            for (int r = 0; r < PQ; ++r) b[r] = fma(-w, myvk[r], b[r]);
+        } else if (col == k) {
+            if (half == 0) Rs[k * PQ + col] = beta;
+#pragma unroll
+            for (int r = 0; r < PQ; ++r) b[r] = 0.0;
+        }
+        __syncwarp();                                     // vk and R[k][k] are free again
     }
 }
 
-__global__ void __launch_bounds__(TSQR_WORKERS * 16)
+constexpr int TSQR_WARPS = 8;
+// Warp -> (treatment, patient slot).  The untreated steps carry ~45 % of the sample rows of a cancer_sim cohort, chemo
+// only and radio only ~22 % each, both ~11 %: three, two, two and one warp keep the warps' row counts within 1.4x.
+__constant__ int8_t c_tsqr_a[TSQR_WARPS] = {0, 1, 2, 3, 0, 1, 2, 0};
+__constant__ int8_t c_tsqr_slot[TSQR_WARPS] = {0, 0, 0, 0, 1, 1, 1, 2};
+__constant__ int8_t c_tsqr_nslots[4] = {3, 2, 2, 1};
+constexpr int TSQR_ROWS = 32;          // buffered sample rows per fold
+constexpr int TSQR_WARP_DOUBLES = PQ * PQ + TSQR_ROWS * PQ + 2 * VK_HALF;   // R, B, vk
+
+// A warp serves one treatment on its share of the patients: it stages a patient's volumes
+// and treatment codes in shared memory, finds the steps of its treatment 32 at a time (ballot), buffers their sample
+// rows (32) and folds full buffers into its R factor.
+__global__ void __launch_bounds__(TSQR_WARPS * 32, 3)
 poly_tsqr_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol, const double *__restrict__ chemo,
                  const double *__restrict__ radio, const double *__restrict__ seq, const double *__restrict__ stat,
                  double *__restrict__ scratch, unsigned long long *__restrict__ counts)
 {
     extern __shared__ __align__(16) double s_tsqr[];
-    double(*s_R)[4][PQ * PQ] = reinterpret_cast<double(*)[4][PQ * PQ]>(s_tsqr);
-    __shared__ unsigned long long s_cnt[4];
-    const int tid = threadIdx.x, worker = tid >> 4, lane16 = tid & 15;
-    const unsigned gmask = 0xffffu << (16 * ((tid >> 4) & 1));
-    for (int e = tid; e < TSQR_WORKERS * 4 * PQ * PQ; e += blockDim.x) s_tsqr[e] = 0.0;
-    if (tid < 4) s_cnt[tid] = 0ull;
-    __syncthreads();
-    const int ea = lane16 < PT ? c_poly_a[lane16] : 0, eb = lane16 < PT ? c_poly_b[lane16] : 0;
-    unsigned long long my_cnt[4] = {0ull, 0ull, 0ull, 0ull};
-    const int64_t stride = (int64_t)gridDim.x * TSQR_WORKERS;
-    for (int64_t p = (int64_t)blockIdx.x * TSQR_WORKERS + worker; p < n; p += stride) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, col = lane & 15, half = lane >> 4;
+    const int a = c_tsqr_a[warp], nslots = c_tsqr_nslots[a];
+    double *Rs = s_tsqr + (size_t)warp * TSQR_WARP_DOUBLES;                              // [16][16]
+    double *Bs = Rs + PQ * PQ;                                                           // [32][16]
+    double *vk = Bs + TSQR_ROWS * PQ;
+    double *xs = s_tsqr + (size_t)TSQR_WARPS * TSQR_WARP_DOUBLES + (size_t)warp * (T + 1);   // volumes of the patient
+    uint8_t *cs = reinterpret_cast<uint8_t *>(s_tsqr + (size_t)TSQR_WARPS * (TSQR_WARP_DOUBLES + T + 1)) + (size_t)warp * (T + 1);
+    for (int e = lane; e < PQ * PQ; e += 32) Rs[e] = 0.0;
+    const int ea = col < PT ? c_poly_a[col] : 0, eb = col < PT ? c_poly_b[col] : 0;
+    const bool unit_dt = fd_dt == 1.0;
+    unsigned long long rows = 0ull;
+    int cnt = 0;
+    const int64_t stride = (int64_t)gridDim.x * nslots;
+    for (int64_t p = (int64_t)blockIdx.x * nslots + c_tsqr_slot[warp]; p < n; p += stride) {
         const double *x = vol + p * T, *ch = chemo + p * T, *ra = radio + p * T;
         const int L = min((int)seq[p], T - 1);
-        const double u = stat[p];
-        const double ub = ipow4(u, eb);
-        for (int i = 0; i < L; ++i) {
-            const int code = (ch[i] != 0.0 ? 1 : 0) + (ra[i] != 0.0 ? 2 : 0);
-            const double x0 = x[i], x1 = x[i + 1];
-            const double xd = (x1 - x0) / fd_dt;
-            double *R = &s_R[worker][code][0];
-            givens_insert(R, lane16 < PT ? ipow4(x0, ea) * ub : xd, lane16, 0, gmask);
-            int rows = 1;
-            const bool last = (i == L - 1) || (ch[i + 1] != ch[i]) || (ra[i + 1] != ra[i]);
-            if (last) {   // the snippet's end point with the backward difference
-                givens_insert(R, lane16 < PT ? ipow4(x1, ea) * ub : xd, lane16, 0, gmask);
-                rows = 2;
+        const double ub = ipow4(stat[p], eb);
+        __syncwarp();
+        for (int k = lane; k <= L; k += 32) xs[k] = x[k];
+        for (int k = lane; k < L; k += 32) cs[k] = (uint8_t)((ch[k] != 0.0 ? 1 : 0) + (ra[k] != 0.0 ? 2 : 0));
+        if (lane == 0) cs[L] = 0xff;                      // the last step always closes its snippet
+        __syncwarp();
+        for (int base = 0; base < L; base += 32) {
+            const int kk = base + lane;
+            unsigned m = __ballot_sync(0xffffffffu, kk < L && cs[kk] == a);
+            while (m) {
+                const int i = base + __ffs(m) - 1;
+                m &= m - 1;
+                const double x0 = xs[i], x1 = xs[i + 1];
+                const double xd = unit_dt ? (x1 - x0) : (x1 - x0) / fd_dt;
+                const int nrow = (cs[i + 1] != cs[i]) ? 2 : 1;   // the snippet's end point carries the backward difference
+                for (int e = 0; e < nrow; ++e) {
+                    if ((cnt >> 4) == half) Bs[cnt * PQ + col] = col < PT ? ipow4(e ? x1 : x0, ea) * ub : xd;
+                    if (++cnt == TSQR_ROWS) {
+                        __syncwarp();
+                        householder_fold(Rs, Bs, vk, lane);
+                        cnt = 0;
+                    }
+                }
+                rows += nrow;
             }
-            if (lane16 == 0) my_cnt[code] += rows;
         }
     }
-    if (lane16 == 0)
-        for (int a = 0; a < 4; ++a)
-            if (my_cnt[a]) atomicAdd(&s_cnt[a], my_cnt[a]);
+    if (cnt) {
+        for (int r = cnt; r < TSQR_ROWS; ++r)
+            if ((r >> 4) == half) Bs[r * PQ + col] = 0.0;
+        __syncwarp();
+        householder_fold(Rs, Bs, vk, lane);
+    }
+    if (lane == 0 && rows) atomicAdd(&counts[a], rows);
+    // merge the warps of a treatment: a parked factor is a block of 16 sample rows (rows 16..31 of the block zero)
+    __syncwarp();
+    if (warp >= 4)
+        for (int e = lane; e < PQ * PQ; e += 32) { Bs[e] = Rs[e]; Bs[PQ * PQ + e] = 0.0; }
     __syncthreads();
-    // merge the workers' factors: group a (a < 4) owns treatment a and folds the other workers' rows into its own
-    if (worker < 4) {
-        double *R = &s_R[worker][worker][0];
-        for (int o = 0; o < TSQR_WORKERS; ++o) {
-            if (o == worker) continue;
-            const double *S = &s_R[o][worker][0];
-            for (int k = 0; k < PQ; ++k) givens_insert(R, lane16 >= k ? S[k * PQ + lane16] : 0.0, lane16, k, gmask);
-        }
-        double *g = scratch + ((size_t)blockIdx.x * 4 + worker) * PQ * PQ;
-        for (int k = 0; k < PQ; ++k) g[k * PQ + lane16] = R[k * PQ + lane16];
+    if (warp < 4) {       // warps 0..3 lead treatments 0..3
+        for (int o = 4; o < TSQR_WARPS; ++o)
+            if (c_tsqr_a[o] == a) householder_fold(Rs, s_tsqr + (size_t)o * TSQR_WARP_DOUBLES + PQ * PQ, vk, lane);
+        double *g = scratch + ((size_t)blockIdx.x * 4 + warp) * PQ * PQ;
+        for (int e = lane; e < PQ * PQ; e += 32) g[e] = Rs[e];
     }
-    if (tid < 4 && s_cnt[tid]) atomicAdd(&counts[tid], s_cnt[tid]);
 }
 
-__global__ void __launch_bounds__(64)
+// one CTA, warp a = treatment a: folds the CTA factors two at a time (rows 0..15 and 16..31 of the block)
+__global__ void __launch_bounds__(128)
 poly_tsqr_merge_kernel(int nctas, const double *__restrict__ scratch, const unsigned long long *__restrict__ counts,
                        double *__restrict__ r_out)
 {
-    __shared__ double s_R[4][PQ * PQ];
-    const int tid = threadIdx.x, a = tid >> 4, lane16 = tid & 15;
-    const unsigned gmask = 0xffffu << (16 * (a & 1));
-    double *R = &s_R[a][0];
-    for (int k = 0; k < PQ; ++k) R[k * PQ + lane16] = scratch[(size_t)a * PQ * PQ + k * PQ + lane16];
-    __syncwarp(gmask);
-    for (int c = 1; c < nctas; ++c) {
-        const double *S = scratch + ((size_t)c * 4 + a) * PQ * PQ;
-        for (int k = 0; k < PQ; ++k) givens_insert(R, lane16 >= k ? S[k * PQ + lane16] : 0.0, lane16, k, gmask);
+    __shared__ double s_w[4][TSQR_WARP_DOUBLES];
+    const int tid = threadIdx.x, a = tid >> 5, lane = tid & 31;
+    double *Rs = s_w[a], *Bs = Rs + PQ * PQ, *vk = Bs + TSQR_ROWS * PQ;
+    for (int e = lane; e < PQ * PQ; e += 32) Rs[e] = scratch[(size_t)a * PQ * PQ + e];
+    for (int c = 1; c < nctas; c += 2) {
+        __syncwarp();
+        for (int e = lane; e < 2 * PQ * PQ; e += 32) {
+            const int cc = c + e / (PQ * PQ);
+            Bs[e] = (cc < nctas) ? scratch[((size_t)cc * 4 + a) * PQ * PQ + e % (PQ * PQ)] : 0.0;
+        }
+        __syncwarp();
+        householder_fold(Rs, Bs, vk, lane);
     }
-    for (int k = 0; k < PQ; ++k) r_out[(size_t)a * PQ * PQ + k * PQ + lane16] = R[k * PQ + lane16];
+    __syncwarp();
+    for (int e = lane; e < PQ * PQ; e += 32) r_out[(size_t)a * PQ * PQ + e] = Rs[e];
     if (tid < 4) r_out[4 * PQ * PQ + tid] = (double)counts[tid];
 }
 
@@ -221,7 +291,9 @@ poly_stlsq_kernel(const double *__restrict__ r_factors, double threshold, double
     __syncwarp();
     const double *R = s_R[a];
     double *coef = s_coef[a];
-    const bool empty = r_factors[4 * PQ * PQ + a] == 0.0;
+    const double count = r_factors[4 * PQ * PQ + a];
+    const bool empty = count == 0.0;
+    if (!(rcond > 0.0)) rcond = fmax(count, (double)PT) * 2.220446049250313e-16;   // numpy.linalg.lstsq's eps * max(M, N)
     // pkpd/utils.py:274-310 (pysindy STLSQ._reduce): ridge on the support, hard threshold, stop when nothing was dropped
     // in this pass or the support repeats
     unsigned ind = (1u << PT) - 1u, last = ind;
@@ -343,22 +415,23 @@ extern "C" int b200i_poly_tsqr(int64_t n, int32_t T, double fd_dt, const double 
     unsigned long long *counts = static_cast<unsigned long long *>(workspace);
     double *scratch = reinterpret_cast<double *>(static_cast<uint8_t *>(workspace) + 64);
     B200I_CUDA(cudaMemsetAsync(counts, 0, 64, st));
-    // a CTA's 8 workers take ~32 patients each before another CTA pays for its merge
-    int64_t grid = (n + TSQR_WORKERS * 32 - 1) / (TSQR_WORKERS * 32);
+    B200I_REQUIRE(T <= 1024, B200I_E_UNSUPPORTED, "poly_tsqr: T=%d > 1024", T);
+    // a CTA takes ~128 patients before another CTA pays for its merge
+    int64_t grid = (n + 127) / 128;
     if (grid < 1) grid = 1;
-    const int64_t cap = (2 * (int64_t)num_sms() < TSQR_MAX_CTAS) ? 2 * (int64_t)num_sms() : TSQR_MAX_CTAS;
+    const int64_t cap = (3 * (int64_t)num_sms() < TSQR_MAX_CTAS) ? 3 * (int64_t)num_sms() : TSQR_MAX_CTAS;
     if (grid > cap) grid = cap;
-    const int smem = TSQR_WORKERS * 4 * PQ * PQ * (int)sizeof(double);
+    const int smem = TSQR_WARPS * ((TSQR_WARP_DOUBLES + T + 1) * (int)sizeof(double) + ((T + 1 + 7) & ~7));
     {
         int per_sm = 1;
-        int rc0 = ensure_dyn_smem(reinterpret_cast<const void *>(poly_tsqr_kernel), smem, TSQR_WORKERS * 16, &per_sm);
+        int rc0 = ensure_dyn_smem(reinterpret_cast<const void *>(poly_tsqr_kernel), smem, TSQR_WARPS * 32, &per_sm);
         if (rc0) return rc0;
     }
-    poly_tsqr_kernel<<<(unsigned)grid, TSQR_WORKERS * 16, smem, st>>>(n, T, fd_dt, cancer_volume, chemo_application,
-                                                                   radio_application, sequence_lengths, static_feature,
-                                                                   scratch, counts);
+    poly_tsqr_kernel<<<(unsigned)grid, TSQR_WARPS * 32, smem, st>>>(n, T, fd_dt, cancer_volume, chemo_application,
+                                                                    radio_application, sequence_lengths, static_feature,
+                                                                    scratch, counts);
     B200I_CUDA(cudaGetLastError());
-    poly_tsqr_merge_kernel<<<1, 64, 0, st>>>((int)grid, scratch, counts, r_out);
+    poly_tsqr_merge_kernel<<<1, 128, 0, st>>>((int)grid, scratch, counts, r_out);
     return check_cuda(cudaGetLastError(), "poly_tsqr launch");
 }
 
@@ -367,7 +440,6 @@ extern "C" int b200i_poly_stlsq(const double *r_factors, double threshold, doubl
 {
     B200I_REQUIRE(r_factors && coefs_out && support_out, B200I_E_ARG, "poly_stlsq: NULL argument");
     B200I_REQUIRE(alpha >= 0.0 && max_iter >= 1, B200I_E_ARG, "poly_stlsq: alpha must be >= 0 and max_iter >= 1");
-    if (!(rcond > 0.0)) rcond = 2.220446049250313e-16;   // scipy.linalg.lstsq(cond=None): machine epsilon
     poly_stlsq_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(r_factors, threshold, alpha, max_iter, rcond,
                                                                         coefs_out, support_out);
     return check_cuda(cudaGetLastError(), "poly_stlsq launch");

@@ -332,7 +332,7 @@ def poly_tsqr(cancer_volume, chemo_application, radio_application, sequence_leng
 
 def poly_stlsq(r_factors, threshold=1e-3, alpha=0.5, max_iter=100, rcond=0.0):
     """pysindy STLSQ + unbias on the R factors -> (coefs (4,15) float64, support (4,15) int32) on the device.
-    rcond <= 0: machine epsilon (scipy.linalg.lstsq's default cut-off)."""
+    rcond <= 0: eps * max(samples, 15) (numpy.linalg.lstsq's default cut-off; see include/b200i.h)."""
     lib = _native.load()
     coefs = torch.empty((4, POLY_TERMS), dtype=torch.float64, device='cuda')
     support = torch.empty((4, POLY_TERMS), dtype=torch.int32, device='cuda')
