@@ -677,16 +677,40 @@ def run_b200(args):
             gen_e2e_ms = e2e_loop(True)
         except Exception as e:      # noqa: BLE001
             e2e_graph_error = repr(e)
+    # What the host->device path alone sustains with every rank copying at once (no kernels): the floor of the end-to-end
+    # step when the ranks' uploads share PCIe switches / host memory.  Same bytes, same chunking, same pinned buffers.
+    def h2d_probe():
+        rows = [r for r in range(10) if r not in (uniform or {})]
+        if h_types is not None:
+            rows = [r for r in rows if r != 3]           # beta is rebuilt on the device
+        for rep in range(3 + max(1, args.steps)):
+            if rep == 3:
+                barrier()
+                t0 = time.perf_counter()
+            for a, b in gen.bounds:
+                for r in rows:
+                    gen.params[r, a:b].copy_(h_block[r, a:b], non_blocking=True)
+                if h_types is not None:
+                    gen.types_u8_dev[a:b].copy_(h_types[a:b], non_blocking=True)
+                else:
+                    gen.static[a:b].copy_(h_static[a:b], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        barrier()
+        return 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    try:
+        h2d_only_ms = h2d_probe()
+    except Exception:      # noqa: BLE001
+        h2d_only_ms = None
     clocks.stop.set(); clocks.t.join(timeout=6)
     gen_coefs = h_result[:16].numpy().reshape(4, 4).copy()
-    tg = torch.tensor([gen_ms, gen_e2e_ms, gen_e2e_eager_ms], dtype=torch.float64, device='cuda')
+    tg = torch.tensor([gen_ms, gen_e2e_ms, gen_e2e_eager_ms, h2d_only_ms or 0.0], dtype=torch.float64, device='cuda')
     if world > 1:
         tgs = torch.tensor([gen_exec], dtype=torch.float64, device='cuda'); dist.all_reduce(tgs, op=dist.ReduceOp.SUM)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gen_exec_all = float(tgs[0])
     else:
         gen_exec_all = gen_exec
-    gen_ms, gen_e2e_ms, gen_e2e_eager_ms = float(tg[0]), float(tg[1]), float(tg[2])
+    gen_ms, gen_e2e_ms, gen_e2e_eager_ms, h2d_only_ms = float(tg[0]), float(tg[1]), float(tg[2]), float(tg[3])
 
     # ---- the other BASELINE configurations (each block is guarded: a failure there must not cost the headline line) ----
     peak_hbm, _ = measured_peak_hbm()
@@ -753,6 +777,11 @@ def run_b200(args):
                                    else "eager stream operations"),
                         "eager": {"value": gen_exec_all / (gen_e2e_eager_ms / 1e3), "ms_per_step": gen_e2e_eager_ms,
                                   "graph_error": e2e_graph_error},
+                        "h2d_only": {"ms_per_step": h2d_only_ms or None,
+                                     "gb_per_s_per_gpu": (gen_h2d / (h2d_only_ms * 1e6)) if h2d_only_ms else None,
+                                     "what": "the step's host->device copies alone (same pinned buffers, same chunks, no "
+                                             "kernels), all ranks copying at once, max over ranks: the floor the shared "
+                                             "host->device path puts under the end-to-end step"},
                         "what": "GeneratedFitPipeline.step_host on the reduced input set: pinned host arrays of what "
                                 "get_standard_params draws per patient (initial volume, alpha, rho, beta_c as float64, the "
                                 "patient type as one byte) -> H2D in "
