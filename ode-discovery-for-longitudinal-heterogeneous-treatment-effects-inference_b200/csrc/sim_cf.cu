@@ -33,6 +33,9 @@ struct CfSrc {
 };
 
 constexpr int MAXH = 8;
+#ifndef CF_FACTUAL_MINB
+#define CF_FACTUAL_MINB 3     // resident CTAs per SM the thread-per-patient factual kernels (K2, K3 phase A) are compiled for
+#endif
 
 // The factual step's three transcendental functions and its divisions: the lean versions of csrc/fastmath.cuh (the
 // ones K1 runs; <= 1 ulp, same class as libdevice's and numpy's own) wherever their domain allows -- positive, finite,
@@ -126,7 +129,7 @@ __device__ __forceinline__ double clip(double x, double lo, double hi) { return 
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, CF_FACTUAL_MINB)
 cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const double *__restrict__ params,
                    const double *__restrict__ noise, const double *__restrict__ rec,
                    const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
@@ -171,7 +174,6 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
     Fr[0] = p.v0;
     double self_F1 = 0.0;
     int steps = 0;
-    bool alive = true;
     // the four draws of step t + 1 are requested while step t computes (their addresses do not depend on the
     // trajectory): the first version loaded them where they were used and spent 6.4 of 10 issue slots in
     // long_scoreboard stalls (profiles/r2_k2_one_step_ncu.txt)
@@ -179,16 +181,10 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
     double nx_w = w.self ? 0.0 : w.at(0);      // the window row's entry of the next step (owner's row: a remote read)
     for (int t = 0; t < T - 1; ++t) {
         const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise, w_pre = nx_w;
-        if (alive && t + 1 < T - 1) {
+        if (t + 1 < T - 1) {
             nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
             nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * T + t + 2];
             if (!w.self) nx_w = w.at(t + 1);
-        }
-        if (!alive) {   // steps after the last executed one: zeros (the compact arrays are fully defined)
-            Fr[t + 1] = 0.0; cr[t] = 0;
-            double2 *z = reinterpret_cast<double2 *>(cf_out + (i * (T - 1) + t) * 4);
-            z[0] = make_double2(0.0, 0.0); z[1] = make_double2(0.0, 0.0);
-            continue;
         }
         double w_t;
         if (w.self) {
@@ -218,7 +214,12 @@ cf_one_step_kernel(int64_t lo, int64_t hi, int64_t n, int T, SimC2 c, const doub
         steps = t + 1;
         s.F = Fn;
         s.Cprev = C_t;
-        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) alive = false;
+        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) break;   // death / recovery ends the trajectory
+    }
+    for (int t = steps; t < T - 1; ++t) {   // steps after the last executed one: zeros (the compact arrays are fully defined)
+        Fr[t + 1] = 0.0; cr[t] = 0;
+        double2 *z = reinterpret_cast<double2 *>(cf_out + (i * (T - 1) + t) * 4);
+        z[0] = make_double2(0.0, 0.0); z[1] = make_double2(0.0, 0.0);
     }
     cr[T - 1] = 0;
     n_steps[i] = steps;

@@ -198,7 +198,7 @@ __global__ void cf_seq_self_kernel(int64_t n, int T, int H, SimC2 c, const __gri
     for (int kk = 0; kk < PB_H; ++kk) self_row[kk] = opt[o][kk];
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, CF_FACTUAL_MINB)
 cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, const double *__restrict__ params,
                       const double *__restrict__ noise, const double *__restrict__ rec,
                       const double *__restrict__ chemo_rvs, const double *__restrict__ radio_rvs, int64_t base,
@@ -253,18 +253,16 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
 #pragma unroll
     for (int q = 0; q < PB_H; ++q) self_tail[q] = 0.0;
     int steps = 0;
-    bool alive = !missing;
     // draws of step t + 1 requested while step t computes (see cf_one_step_kernel)
     double nx_chemo = chemo_rvs[i * T], nx_radio = radio_rvs[i * T], nx_rec = rec[i * T], nx_noise = noise[i * NW + 1];
     double nx_w = (w.self || missing) ? 0.0 : w.at(0);
-    for (int t = 0; t < T - 1; ++t) {
+    for (int t = 0; t < T - 1 && !missing; ++t) {
         const double u_chemo = nx_chemo, u_radio = nx_radio, u_rec = nx_rec, nz = nx_noise, w_pre = nx_w;
-        if (alive && t + 1 < T - 1) {
+        if (t + 1 < T - 1) {
             nx_chemo = chemo_rvs[i * T + t + 1]; nx_radio = radio_rvs[i * T + t + 1];
             nx_rec = rec[i * T + t + 1]; nx_noise = noise[i * NW + t + 2];
             if (!w.self) nx_w = w.at(t + 1);
         }
-        if (!alive) { Fr[t + 1] = 0.0; cr[t] = 0; Cr[t] = 0.0; continue; }
         double w_t;
         if (w.self) {
             if (t == 1) { s.cnt = 0; window_push(s.win, s.cnt, c.window + 1, cf_diameter(p.v0, c.sphere)); }
@@ -291,8 +289,9 @@ cf_seq_factual_kernel(int64_t lo, int64_t hi, int64_t n, int T, int H, SimC2 c, 
         steps = t + 1;
         s.F = Fn;
         s.Cprev = C_t;
-        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) alive = false;
+        if (Fn >= c.death || recovery_test<false>(u_rec, Fn, c.density)) break;   // death / recovery ends the trajectory
     }
+    for (int t = steps; t < T - 1; ++t) { Fr[t + 1] = 0.0; cr[t] = 0; Cr[t] = 0.0; }   // after the last executed step: zeros
     cr[T - 1] = 0;
     Cr[T - 1] = 0.0;
     n_steps[i] = steps;
