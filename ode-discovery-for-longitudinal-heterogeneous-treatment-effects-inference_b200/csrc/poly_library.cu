@@ -153,7 +153,12 @@ poly_tsqr_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol,
                 const double xd = unit_dt ? (x1 - x0) : (x1 - x0) / fd_dt;
                 const int nrow = (cs[i + 1] != cs[i]) ? 2 : 1;   // the snippet's end point carries the backward difference
                 for (int e = 0; e < nrow; ++e) {
-                    if ((cnt >> 4) == half) Bs[cnt * PQ + col] = col < PT ? ipow4(e ? x1 : x0, ea) * ub : xd;
+                    // this lane's monomial x^ea u^eb: the powers by repeated multiplication (1 * x * x ...), chosen by
+                    // selects -- a loop over the lane's exponent diverges inside the warp and cost 70 instructions a row
+                    const double x = e ? x1 : x0;
+                    const double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+                    const double pw = ea == 0 ? 1.0 : (ea == 1 ? x : (ea == 2 ? p2 : (ea == 3 ? p3 : p4)));
+                    if ((cnt >> 4) == half) Bs[cnt * PQ + col] = col < PT ? pw * ub : xd;
                     if (++cnt == TSQR_ROWS) {
                         __syncwarp();
                         householder_fold(Rs, Bs, vk, lane);
