@@ -411,9 +411,9 @@ extern "C" int b200i_poly_tsqr(int64_t n, int32_t T, double fd_dt, const double 
                                const double *sequence_lengths, const double *static_feature, void *workspace,
                                double *r_out, void *stream)
 {
-    B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths && static_feature &&
-                      workspace && r_out,
-                  B200I_E_ARG, "poly_tsqr: NULL argument or negative n");
+    B200I_REQUIRE(n >= 0 && workspace && r_out, B200I_E_ARG, "poly_tsqr: NULL workspace / output or negative n");
+    B200I_REQUIRE(n == 0 || (cancer_volume && chemo_application && radio_application && sequence_lengths && static_feature),
+                  B200I_E_ARG, "poly_tsqr: NULL argument");   // the arrays of an empty cohort may be NULL
     B200I_REQUIRE(T >= 2, B200I_E_UNSUPPORTED, "poly_tsqr: T=%d < 2", T);
     B200I_REQUIRE(fd_dt > 0.0, B200I_E_ARG, "poly_tsqr: fd_dt must be positive");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

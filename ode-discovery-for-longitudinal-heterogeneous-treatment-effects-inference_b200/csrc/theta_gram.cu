@@ -654,11 +654,12 @@ extern "C" int b200i_smooth_snippets(int64_t n, int32_t T, const double *cancer_
                                      const double *radio_application, const double *sequence_lengths, int32_t joint,
                                      double *smoothed_out, void *stream)
 {
-    B200I_REQUIRE(n >= 0 && cancer_volume && chemo_application && radio_application && sequence_lengths && smoothed_out,
-                  B200I_E_ARG, "smooth_snippets: NULL argument or negative n");
+    B200I_REQUIRE(n >= 0, B200I_E_ARG, "smooth_snippets: negative n");
+    if (n == 0) return 0;     // empty cohort: nothing to write (the arrays of an empty cohort may be NULL)
+    B200I_REQUIRE(cancer_volume && chemo_application && radio_application && sequence_lengths && smoothed_out,
+                  B200I_E_ARG, "smooth_snippets: NULL argument");
     B200I_REQUIRE(T >= 2, B200I_E_UNSUPPORTED, "smooth_snippets: T=%d < 2", T);
     B200I_REQUIRE(smoothed_out != cancer_volume, B200I_E_ARG, "smooth_snippets: the pass is not in-place");
-    if (n == 0) return 0;
     const int64_t total = n * (int64_t)T;
     int64_t grid = (total + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 8;

@@ -108,3 +108,57 @@ def test_degree4_is_refused_where_it_is_not_built(collection):
     with pytest.raises(NotImplementedError):
         SINDY(default_config(insite=False, ablation_more_complex_basis_functions=True, joint_model=True,
                              treatment_mode='multilabel'), collection)
+
+
+def test_edge_cases_empty_and_ragged_cohorts(dev):
+    """No patients, one patient, a treatment that never occurs, one-step trajectories: counts, zero factors and zero
+    coefficients where there is nothing to fit; the R factors still reproduce the explicit design matrix."""
+    import torch
+    from oracle import sindy_np as sp
+    T = 12
+    rng = np.random.default_rng(5)
+
+    def run(vol, chemo, radio, seq, static):
+        rf = dev.poly_tsqr(dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio), dev.to_device(seq),
+                           dev.to_device(static))
+        coefs, sup = dev.poly_stlsq(rf)
+        torch.cuda.synchronize()
+        return rf.cpu().numpy(), coefs.cpu().numpy(), sup.cpu().numpy()
+
+    z = np.zeros((0, T))
+    rf, coefs, sup = run(z, z, z, np.zeros(0), np.zeros(0))
+    assert not rf.any() and not coefs.any() and not sup.any()
+    # ragged cohort: radiotherapy never given, sequence lengths 1 .. T-1
+    n = 37
+    vol = rng.uniform(0.5, 30.0, size=(n, T))
+    chemo = (rng.uniform(size=(n, T)) < 0.4).astype(np.float64)
+    radio = np.zeros((n, T))
+    seq = rng.integers(1, T, size=n).astype(np.float64)
+    seq[0], seq[1] = 1, T - 1
+    static = rng.integers(1, 4, size=n).astype(np.float64)
+    rf, coefs, sup = run(vol, chemo, radio, seq, static)
+    # explicit design matrices from the same snippet rule (per-treatment runs, end point with the backward difference)
+    rows = {0: [], 1: []}
+    for p in range(n):
+        L, a = int(seq[p]), 0
+        for i in range(1, L + 1):
+            if i == L or chemo[p, i] != chemo[p, i - 1]:
+                x = vol[p, a:i + 1]
+                th = sp.library_poly4(x, np.full(len(x), static[p]))
+                xd = sp.finite_difference_order1(x, sp.STANDARD_DT)
+                rows[int(chemo[p, a])].append(np.concatenate([th, xd[:, None]], axis=1))
+                a = i
+    for a in (0, 1):
+        M = np.concatenate(rows[a], axis=0)
+        R = rf[a * 256:(a + 1) * 256].reshape(16, 16)
+        assert rf[4 * 256 + a] == M.shape[0]
+        G = M.T @ M
+        d = np.sqrt(np.diag(G))
+        np.testing.assert_allclose((R.T @ R) / np.outer(d, d), G / np.outer(d, d), atol=1e-11)
+    for a in (2, 3):     # radiotherapy never occurs
+        assert rf[4 * 256 + a] == 0 and not rf[a * 256:(a + 1) * 256].any()
+        assert not coefs[a].any() and not sup[a].any()
+    assert np.isfinite(coefs).all()
+    # one patient, one step
+    rf, coefs, sup = run(vol[:1], chemo[:1], radio[:1], np.ones(1), static[:1])
+    assert rf[4 * 256:].sum() == 2 and np.isfinite(coefs).all()

@@ -83,3 +83,21 @@ def test_fit_with_smoothed_finite_difference_equals_oracle(dev, joint):
     assert np.array_equal(model.support_.reshape(-1), np.asarray(sup).reshape(-1))
     np.testing.assert_allclose(model.joint_coefs, want, rtol=1e-7, atol=1e-12)
     assert np.abs(model.joint_coefs - plain.joint_coefs).max() > 1e-4      # the option does change the fit
+
+
+def test_smoothing_pass_edge_lengths(dev):
+    """Sequence length 1 (two samples: nothing to smooth), full length, empty cohort."""
+    import torch
+    T = 9
+    rng = np.random.default_rng(2)
+    vol = rng.uniform(1.0, 50.0, size=(3, T))
+    chemo = np.zeros((3, T)); radio = np.zeros((3, T))
+    seq = np.array([1.0, T - 1.0, 4.0])
+    out = dev.smooth_snippets(dev.to_device(vol), dev.to_device(chemo), dev.to_device(radio), dev.to_device(seq)).cpu().numpy()
+    np.testing.assert_array_equal(out[0], vol[0])
+    want = vol[1].copy(); want[1:T - 1] = 0.5 * vol[1, 1:T - 1] + 0.5 * vol[1, 2:]
+    np.testing.assert_array_equal(out[1], want)
+    want = vol[2].copy(); want[1:4] = 0.5 * vol[2, 1:4] + 0.5 * vol[2, 2:5]
+    np.testing.assert_array_equal(out[2], want)
+    z = torch.zeros((0, T), dtype=torch.float64, device='cuda')
+    assert dev.smooth_snippets(z, z, z, torch.zeros(0, dtype=torch.float64, device='cuda')).shape == (0, T)
