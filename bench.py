@@ -302,6 +302,26 @@ def block_c4(gen, T, peak):
                           "mean_iterations": float((stn[stn >= 0] >> 8).mean()),
                           "bound": "FP64 ALU / dependent-issue latency (16 forward sensitivities per Euler sub-step)",
                           "ncu": "profiles/r2_k7_insite_bfgs_ncu.txt"}
+    # the two fit options of SURVEY 8(f) F2 on the same cohort: degree-4 library (R factors by tall-skinny QR + SVD-based
+    # STLSQ + polynomial rollout) and the smoothing pass of use_smoothed_finite_difference
+    try:
+        chemo = (cd & 1).to(torch.float64); radio = ((cd >> 1) & 1).to(torch.float64)
+        ms_q, rf = _median_ms(lambda: dev.poly_tsqr(xv, chemo, radio, gen.sequence_lengths, gen.static), reps=3)
+        ms_s, (pcoef, psup) = _median_ms(lambda: dev.poly_stlsq(rf), reps=3)
+        ms_r, _ = _median_ms(lambda: dev.poly_rollout(x0, gen.static, cd1, pcoef), reps=3)
+        ms_sm, _ = _median_ms(lambda: dev.smooth_snippets(xv, chemo, radio, gen.sequence_lengths), reps=3)
+        rows_q = float(rf[4 * 256:].sum().item())
+        out["fit_options"] = {
+            "degree4_library": {"kernels": "poly_tsqr + poly_stlsq + poly_rollout (K4p / K5p / K6p)", "sample_rows": rows_q,
+                                "tsqr_ms": ms_q, "sample_rows_per_s": rows_q / (ms_q / 1e3), "stlsq_ms": ms_s,
+                                "rollout_ms": ms_r, "support_sizes": psup.sum(1).tolist(),
+                                "bound": "FP64 issue / latency (Householder folds of 32 sample rows)",
+                                "ncu": "profiles/r2_k4p_poly_tsqr_ncu.txt"},
+            "smoothed_finite_difference": {"kernel": "smooth_snippets", "ms": ms_sm,
+                                           "achieved_gb_per_s": n * T * 8 * 4 / (ms_sm / 1e3) / 1e9}}
+        del chemo, radio
+    except Exception as e:      # noqa: BLE001
+        out["fit_options"] = {"error": repr(e)}
     return out
 
 
