@@ -225,6 +225,19 @@ B200I_API int b200i_upload_simulate_rng_reduced(int64_t n, int32_t T, int64_t ro
                      double *cancer_volume, uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
                      double *patient_moments_out, int32_t chunks, double fd_dt, void *chunk_gram_workspaces,
                      double *stats_out, void *copy_stream, void *stream);
+/* b200i_upload_simulate_rng_reduced for a STREAM of cohorts: consecutive calls overlap.  The copies of a call do not wait
+ * for everything queued on `stream` before it (the previous step's all-reduce, STLSQ and result copies) but, chunk by
+ * chunk, only for the previous call's kernels that read that chunk's parameter rows; the kernels stay ordered behind
+ * `stream`.  The caller keeps the pinned inputs of a call unchanged until copy_stream has passed the call (record an
+ * event on copy_stream after it) and reads a call's results after an event recorded on `stream` behind it
+ * (cohort.GeneratedFitPipeline.submit / HostStep).  Same outputs, bit for bit, as the serial entry point. */
+B200I_API int b200i_upload_simulate_rng_pipelined(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *consts,
+                     const double *params_host, uint32_t uniform_mask, const double *uniform_values_host,
+                     int32_t derive_beta, const uint8_t *patient_types_host, uint8_t *patient_types_dev,
+                     double *params, double *static_feature, uint64_t seed, int64_t patient_base,
+                     double *cancer_volume, uint8_t *codes_out, int64_t code_pitch, double *sequence_lengths,
+                     double *patient_moments_out, int32_t chunks, double fd_dt, void *chunk_gram_workspaces,
+                     double *stats_out, void *copy_stream, void *stream);
 /* The same for (N,T) arrays with a row pitch (elements, even, >= T); see b200i_sim_factual_pitched. */
 B200I_API int b200i_theta_gram_pitched(int64_t n, int32_t T, int64_t row_pitch, double fd_dt,
                      const double *cancer_volume, const double *chemo_application,

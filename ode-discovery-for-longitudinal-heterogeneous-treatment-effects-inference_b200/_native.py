@@ -51,6 +51,10 @@ SIGNATURES = {
                                                          ctypes.POINTER(c_f64), c_i32, c_vp, c_vp, c_vp, c_vp,
                                                          ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_f64,
                                                          c_vp, c_vp, c_vp, c_vp]),
+    "b200i_upload_simulate_rng_pipelined": (ctypes.c_int, [c_i64, c_i32, c_i64, ctypes.POINTER(SimConsts), c_vp, ctypes.c_uint32,
+                                                           ctypes.POINTER(c_f64), c_i32, c_vp, c_vp, c_vp, c_vp,
+                                                           ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_f64,
+                                                           c_vp, c_vp, c_vp, c_vp]),
     "b200i_gram_workspace_bytes": (c_i64, []),
     "b200i_theta_gram": (ctypes.c_int, [c_i64, c_i32, c_f64] + [c_vp] * 9),
     "b200i_stlsq_population": (ctypes.c_int, [c_vp, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp]),

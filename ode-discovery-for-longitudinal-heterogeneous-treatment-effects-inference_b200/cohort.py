@@ -160,6 +160,17 @@ class FactualFitPipeline:
         return float((self.out['sequence_lengths'] - 1.0).sum().item())
 
 
+class HostStep:
+    """One submitted step of GeneratedFitPipeline.submit: its pinned result buffer and the two events of the protocol."""
+
+    def __init__(self, result_host, result_ready, inputs_consumed):
+        self.result_host, self.result_ready, self.inputs_consumed = result_host, result_ready, inputs_consumed
+
+    def wait(self):
+        self.result_ready.synchronize()
+        return self.result_host
+
+
 class GeneratedFitPipeline:
     """Factual cohort + population fit with device-generated draws (throughput mode).
 
@@ -213,25 +224,46 @@ class GeneratedFitPipeline:
         self._simulate()
         return self._fit()
 
-    def _enqueue_host_step(self, params_block, static, result_host, uniform, types_u8):
-        """Everything of step_host but the final synchronisation, on the current stream."""
+    def _enqueue_host_step(self, params_block, static, result_host, uniform, types_u8, pipelined=False):
+        """Everything of step_host but the final synchronisation, on the current stream.
+        pipelined (submit): the statistics of consecutive steps alternate between two buffers and the tail of the step --
+        all-reduce, STLSQ, result copies -- runs on a stream of its own, so the next step's simulation queues right behind
+        this step's and its upload (b200i_upload_simulate_rng_pipelined) under both.  Returns the stream the result copies
+        were queued on."""
+        stats, tail = self.stats, None
+        if pipelined:
+            if getattr(self, '_stats_ring', None) is None:
+                self._stats_ring = [torch.zeros_like(self.stats) for _ in range(2)]
+                self._tail_stream = torch.cuda.Stream()
+                self._submitted = 0
+            stats = self._stats_ring[self._submitted & 1]
+            self._submitted += 1
+            tail = self._tail_stream
         if types_u8 is not None:
             if getattr(self, 'types_u8_dev', None) is None:
                 self.types_u8_dev = torch.empty((self.n,), dtype=torch.uint8, device='cuda')
             dev.upload_simulate_rng(params_block, None, self.params, self.static, self.T, self.seed, self.patient_base,
                                     self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
-                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats,
-                                    uniform=uniform, derive_beta=True, types_u8_host=types_u8, types_u8_dev=self.types_u8_dev)
+                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=stats,
+                                    uniform=uniform, derive_beta=True, types_u8_host=types_u8, types_u8_dev=self.types_u8_dev,
+                                    pipelined=pipelined)
         else:
             dev.upload_simulate_rng(params_block, static, self.params, self.static, self.T, self.seed, self.patient_base,
                                     self.consts, self.volume, self.codes, self.sequence_lengths, self.patient_moments,
-                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=self.stats,
+                                    self.chunks, self.copy_stream, chunk_ws=self.chunk_ws, stats_out=stats,
                                     uniform=uniform)
-        allreduce_stats(self.stats)
-        self.coefs, self.support = dev.stlsq_population(self.stats, self.threshold, self.alpha, self.max_iter)
-        result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
-        result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
-        result_host[32:32 + dev.STATS_DOUBLES].copy_(self.stats, non_blocking=True)
+        main = torch.cuda.current_stream()
+        if tail is not None:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            tail.wait_event(ready)
+        with torch.cuda.stream(tail if tail is not None else main):
+            allreduce_stats(stats)
+            self.coefs, self.support = dev.stlsq_population(stats, self.threshold, self.alpha, self.max_iter)
+            result_host[:16].copy_(self.coefs.reshape(-1), non_blocking=True)
+            result_host[16:32].copy_(self.support.reshape(-1).to(torch.float64), non_blocking=True)
+            result_host[32:32 + dev.STATS_DOUBLES].copy_(stats, non_blocking=True)
+        return tail if tail is not None else main
 
     def step_host(self, params_block, static, result_host, uniform=None, types_u8=None, graph=False):
         """Pinned host parameters (10,N) + static feature (N,) in, pinned result (16 + 16 + 68,) out.
@@ -263,6 +295,16 @@ class GeneratedFitPipeline:
         self._graph.replay()
         main.synchronize()
         return result_host
+
+    def submit(self, params_block, result_host, types_u8, uniform=None):
+        """step_host for a stream of cohorts: queues the whole step (reduced input set) and returns at once with a
+        HostStep.  The upload of this step runs under the previous step's kernels and tail, and its simulation queues right
+        behind the previous step's simulation: the tail (all-reduce, STLSQ, result copies) has a stream of its own.  Protocol: keep `params_block` / `types_u8` unchanged until step.inputs_consumed has
+        passed, read `result_host` after step.wait().  Results are bit-identical to step_host's."""
+        tail = self._enqueue_host_step(params_block, None, result_host, uniform, types_u8, pipelined=True)
+        done = torch.cuda.Event(); done.record(tail)
+        consumed = torch.cuda.Event(); consumed.record(self.copy_stream)
+        return HostStep(result_host, done, consumed)
 
     def executed_steps(self):
         return float((self.sequence_lengths - 1.0).sum().item())

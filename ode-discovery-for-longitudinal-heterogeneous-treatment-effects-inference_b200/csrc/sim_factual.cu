@@ -687,7 +687,7 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
                                     double *sequence_lengths, double *patient_moments_out, int32_t chunks,
                                     double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                                     void *copy_stream, void *stream, int derive_beta, const uint8_t *types_u8_host,
-                                    uint8_t *types_u8_dev);
+                                    uint8_t *types_u8_dev, int overlap_prev = 0);
 
 extern "C" int b200i_upload_simulate_rng(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
                                          const double *params_host, uint32_t uniform_mask,
@@ -724,6 +724,26 @@ extern "C" int b200i_upload_simulate_rng_reduced(int64_t n, int32_t T, int64_t r
                                     copy_stream, stream, derive_beta ? 1 : 0, patient_types_host, patient_types_dev);
 }
 
+extern "C" int b200i_upload_simulate_rng_pipelined(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
+                                                   const double *params_host, uint32_t uniform_mask,
+                                                   const double *uniform_values_host, int32_t derive_beta,
+                                                   const uint8_t *patient_types_host, uint8_t *patient_types_dev,
+                                                   double *params, double *static_feature, uint64_t seed,
+                                                   int64_t patient_base, double *cancer_volume, uint8_t *codes_out,
+                                                   int64_t code_pitch, double *sequence_lengths, double *patient_moments_out,
+                                                   int32_t chunks, double fd_dt, void *chunk_gram_workspaces,
+                                                   double *stats_out, void *copy_stream, void *stream)
+{
+    B200I_REQUIRE(patient_types_host && patient_types_dev && static_feature, B200I_E_ARG,
+                  "upload_simulate_rng_pipelined: patient_types_host / patient_types_dev / static_feature is NULL");
+    B200I_REQUIRE(!derive_beta || !((uniform_mask >> 3) & 1u), B200I_E_ARG,
+                  "upload_simulate_rng_pipelined: beta cannot be both derived and uniform");
+    return upload_simulate_rng_impl(n, T, row_pitch, k, params_host, uniform_mask, uniform_values_host, nullptr, params,
+                                    static_feature, seed, patient_base, cancer_volume, codes_out, code_pitch,
+                                    sequence_lengths, patient_moments_out, chunks, fd_dt, chunk_gram_workspaces, stats_out,
+                                    copy_stream, stream, derive_beta ? 1 : 0, patient_types_host, patient_types_dev, 1);
+}
+
 static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, const b200i_sim_consts *k,
                                     const double *params_host, uint32_t uniform_mask,
                                     const double *uniform_values_host, const double *static_host, double *params,
@@ -732,7 +752,7 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
                                     double *sequence_lengths, double *patient_moments_out, int32_t chunks,
                                     double fd_dt, void *chunk_gram_workspaces, double *stats_out,
                                     void *copy_stream, void *stream, int derive_beta, const uint8_t *types_u8_host,
-                                    uint8_t *types_u8_dev)
+                                    uint8_t *types_u8_dev, int overlap_prev)
 {
     const bool fit = chunk_gram_workspaces != nullptr;
     B200I_REQUIRE(!fit || (stats_out && static_feature && codes_out && patient_moments_out && fd_dt > 0), B200I_E_ARG,
@@ -770,13 +790,20 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
     static thread_local cudaEvent_t evs[16] = {};
     if (evs[devid] == nullptr) B200I_CUDA(cudaEventCreateWithFlags(&evs[devid], cudaEventDisableTiming));
     cudaEvent_t ev = evs[devid];
+    // overlap_prev (b200i_upload_simulate_rng_pipelined): the copies of this call do not wait for everything queued on
+    // `stream` before it (the previous step's all-reduce, STLSQ and result copies) but, chunk by chunk, only for the
+    // kernels of the previous call that read that chunk's parameter rows -- the upload of step s+1 then runs under the
+    // tail of step s.  The kernels themselves stay ordered behind `stream` as before.
+    static thread_local cudaEvent_t chunk_done[16][64] = {};
     int rc = check_cuda(cudaEventRecord(ev, st), "cudaEventRecord");
-    if (!rc) rc = check_cuda(cudaStreamWaitEvent(cs, ev, 0), "cudaStreamWaitEvent");
+    if (!rc && !overlap_prev) rc = check_cuda(cudaStreamWaitEvent(cs, ev, 0), "cudaStreamWaitEvent");
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(sx, ev, 0), "cudaStreamWaitEvent");
     int c = 0;
     for (int64_t a = 0; a < n && !rc; a += step, ++c) {
         const int64_t b = (a + step < n) ? a + step : n;
         cudaStream_t run = (c & 1) ? sx : st;
+        if (overlap_prev && chunk_done[devid][c]) rc = check_cuda(cudaStreamWaitEvent(cs, chunk_done[devid][c], 0), "cudaStreamWaitEvent");
+        if (rc) break;
         const uint32_t skip = uniform_mask | (derive_beta ? (1u << 3) : 0u);   // rows that do not cross PCIe
         for (int r0 = 0; r0 < B200I_NUM_PARAMS && !rc;) {   // maximal runs of rows that are real arrays
             if ((skip >> r0) & 1u) { ++r0; continue; }
@@ -810,6 +837,11 @@ static int upload_simulate_rng_impl(int64_t n, int32_t T, int64_t row_pitch, con
             rc = b200i_theta_gram_codes(b - a, T, row_pitch, 0, fd_dt, cancer_volume + a * row_pitch, codes_out + a * code_pitch,
                                         code_pitch, sequence_lengths + a, static_feature + a, patient_moments_out + a, n,
                                         static_cast<uint8_t *>(chunk_gram_workspaces) + (size_t)c * ws_stride, run);
+        if (!rc && overlap_prev) {   // the readers of this chunk's rows are queued: the next call's copy of the chunk waits for them
+            if (chunk_done[devid][c] == nullptr)
+                rc = check_cuda(cudaEventCreateWithFlags(&chunk_done[devid][c], cudaEventDisableTiming), "cudaEventCreate");
+            if (!rc) rc = check_cuda(cudaEventRecord(chunk_done[devid][c], run), "cudaEventRecord");
+        }
     }
     if (!rc && c > 1) {   // `stream` continues after the chunks of the second stream
         rc = check_cuda(cudaEventRecord(ev, sx), "cudaEventRecord");

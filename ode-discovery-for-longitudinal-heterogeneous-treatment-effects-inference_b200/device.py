@@ -239,10 +239,13 @@ def cohort_scalar_rows(chemo_coeff, radio_coeff):
 
 def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, seed, patient_base, consts, volume, codes,
                         sequence_lengths, patient_moments, chunks, copy_stream, chunk_ws=None, stats_out=None,
-                        fd_dt=STANDARD_DT, uniform=None, derive_beta=False, types_u8_host=None, types_u8_dev=None):
+                        fd_dt=STANDARD_DT, uniform=None, derive_beta=False, types_u8_host=None, types_u8_dev=None,
+                        pipelined=False):
     """Pinned host parameters -> chunked H2D on copy_stream, each chunk simulated (K1L) on the current stream as soon
     as it has arrived (b200i_upload_simulate_rng).  chunk_ws (chunk_workspaces(chunks)) + stats_out (68,): each
-    chunk's share of the population statistics is computed right behind its simulation and summed in chunk order."""
+    chunk's share of the population statistics is computed right behind its simulation and summed in chunk order.
+    pipelined (reduced input set only): consecutive calls overlap -- this call's copies wait, chunk by chunk, only for
+    the previous call's readers of that chunk (b200i_upload_simulate_rng_pipelined)."""
     lib = _native.load()
     n = params_dev.shape[1]
     assert params_host.is_pinned() and params_host.is_contiguous() and tuple(params_host.shape) == (10, n)
@@ -256,7 +259,8 @@ def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, see
         # reduced parameter set: beta derived from alpha, patient types as bytes (b200i_upload_simulate_rng_reduced)
         assert types_u8_host.is_pinned() and types_u8_host.dtype == torch.uint8 and types_u8_host.numel() == n
         assert types_u8_dev is not None and types_u8_dev.is_cuda and types_u8_dev.numel() == n
-        rc = lib.b200i_upload_simulate_rng_reduced(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
+        fn = lib.b200i_upload_simulate_rng_pipelined if pipelined else lib.b200i_upload_simulate_rng_reduced
+        rc = fn(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
                                                    mask, vals if mask else None, 1 if derive_beta else 0,
                                                    ctypes.c_void_p(types_u8_host.data_ptr()), _ptr(types_u8_dev),
                                                    _ptr(params_dev), _ptr(static_dev), int(seed), int(patient_base),
@@ -264,8 +268,10 @@ def upload_simulate_rng(params_host, static_host, params_dev, static_dev, T, see
                                                    _ptr(sequence_lengths), _ptr(patient_moments), int(chunks), float(fd_dt),
                                                    _ptr(chunk_ws), _ptr(stats_out),
                                                    ctypes.c_void_p(copy_stream.cuda_stream), _stream())
-        _native.check(rc, "b200i_upload_simulate_rng_reduced")
+        _native.check(rc, "b200i_upload_simulate_rng_pipelined" if pipelined else "b200i_upload_simulate_rng_reduced")
         return
+    if pipelined:
+        raise ValueError("pipelined uploads take the reduced input set (types_u8_host)")
     rc = lib.b200i_upload_simulate_rng(n, T, vp, ctypes.byref(consts), ctypes.c_void_p(params_host.data_ptr()),
                                        mask, vals if mask else None,
                                        None if static_host is None else ctypes.c_void_p(static_host.data_ptr()),

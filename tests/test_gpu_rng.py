@@ -193,6 +193,45 @@ def test_generated_pipeline_host_step_equals_device_step(dev, chunks):
     assert torch.equal(res2, res3) and not torch.equal(e.volume, d.volume)
 
 
+@pytest.mark.parametrize("chunks", [3, 8])
+def test_submitted_steps_overlap_and_equal_the_serial_steps(dev, chunks):
+    """GeneratedFitPipeline.submit: a stream of cohorts whose uploads run under the previous step's tail.  Two different
+    cohorts alternate through two sets of pinned buffers; every result equals the serial step_host result of its cohort
+    bit for bit (a copy that overtook a reader of the previous step would show up here)."""
+    import torch
+    from b200_insite.cohort import GeneratedFitPipeline
+    n, T = 50021, 60
+    uni = dev.cohort_scalar_rows(2.0, 2.0)
+    sets, want = [], []
+    for seed in (85, 86):
+        params = _cohort(n, seed)
+        hp = torch.from_numpy(dev.pack_params(params)).pin_memory()
+        ty = torch.from_numpy(np.asarray(params['patient_types'], dtype=np.uint8)).pin_memory()
+        ref = GeneratedFitPipeline(n, T, seed=3, patient_base=7, chunks=chunks)
+        r = torch.zeros(32 + dev.STATS_DOUBLES, dtype=torch.float64).pin_memory()
+        ref.step_host(hp, None, r, uniform=uni, types_u8=ty)
+        sets.append((hp, ty)); want.append(r.clone())
+    assert not torch.equal(want[0], want[1])
+    pipe = GeneratedFitPipeline(n, T, seed=3, patient_base=7, chunks=chunks)
+    results = [torch.zeros(32 + dev.STATS_DOUBLES, dtype=torch.float64).pin_memory() for _ in range(2)]
+    pending, got = None, []
+    for s in range(7):
+        k = s & 1
+        step = pipe.submit(sets[k][0], results[k], sets[k][1], uniform=uni)
+        if pending is not None:
+            got.append((pending[0], pending[1].wait().clone()))
+        pending = (k, step)
+    got.append((pending[0], pending[1].wait().clone()))
+    pending[1].inputs_consumed.synchronize()
+    assert len(got) == 7
+    for k, r in got:
+        assert torch.equal(r, want[k])
+    # and a serial step after the stream still sees a quiescent pipeline
+    r = torch.zeros_like(results[0]).pin_memory()
+    pipe.step_host(sets[1][0], None, r, uniform=uni, types_u8=sets[1][1])
+    assert torch.equal(r, want[1])
+
+
 def test_generated_counterfactual_draws_and_cohort(dev):
     """counterfactual.generated_draws: the device generator's draws in the layout of the counterfactual simulators
     (noise (N, T+H) with odd width) equal the numpy restatement, and K3 on them equals the C oracle."""
