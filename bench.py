@@ -14,8 +14,12 @@ Keys of the JSON line beyond the contract:
                         the fit) -> K4 theta_gram_codes -> [all-reduce of 68 doubles] -> K5 STLSQ
   roofline              K1, HBM-bound: algorithmic bytes (6328 B/patient) / CUDA-event time of the launch alone
   roofline_theta_gram   K4, by SURVEY 8d's 1456 B/patient; read_gbs = bytes the lean launch actually reads
-  e2e                   host parameters in -> coefficients out (GeneratedFitPipeline.step_host): the draws come from
-                        the device generator inside the simulator kernel (K1L), chunked H2D overlapped with compute
+  e2e                   host parameters in -> coefficients out, as a stream of cohorts (GeneratedFitPipeline.submit: every
+                        step uploads its own pinned inputs and has its own result read back; the next step's upload is
+                        queued under the current step): the draws come from the device generator inside the simulator
+                        kernel (K1L), chunked H2D overlapped with compute.  e2e.one_step_at_a_time = step_host (a call
+                        returns with its result on the host before the next upload starts), e2e.eager the same without
+                        the CUDA graph, e2e.h2d_only the copies alone with all ranks uploading at once
   e2e_host_draws        the same through the pre-drawn-array contract (2 GB of draws per step over PCIe)
   device_rng            the generated-draws path with parameters resident (K1L -> K4 -> K5)
   individualisation     config C4: per-patient STLSQ fits/s (K5b) and discovered-ODE rollout steps/s (K6), uniform and
@@ -688,7 +692,7 @@ def run_b200(args):
         barrier()
         return 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
     # eager: ~60 stream operations per step issued from Python; graph: the same step captured once and replayed with one
-    # launch (same copies, same kernels, same collective).  The headline e2e is the graph replay unless it is disabled.
+    # launch (same copies, same kernels, same collective).  This is the one-step-at-a-time number (graph replay unless disabled); the headline e2e is the stream of cohorts below.
     gen_e2e_eager_ms = e2e_loop(False)
     gen_e2e_ms = gen_e2e_eager_ms
     e2e_graph_error = None
