@@ -137,6 +137,7 @@ poly_tsqr_kernel(int64_t n, int T, double fd_dt, const double *__restrict__ vol,
     for (int64_t p = (int64_t)blockIdx.x * nslots + c_tsqr_slot[warp]; p < n; p += stride) {
         const double *x = vol + p * T, *ch = chemo + p * T, *ra = radio + p * T;
         const int L = min((int)seq[p], T - 1);
+        if (L <= 0) continue;                             // no step, no sample (warp-uniform)
         const double ub = ipow4(stat[p], eb);
         __syncwarp();
         for (int k = lane; k <= L; k += 32) xs[k] = x[k];
