@@ -300,3 +300,41 @@ def test_savgol_window2_restatement_equals_scipy():
         x = rng.uniform(0.1, 1200.0, size=(L, 1))
         np.testing.assert_allclose(sp.savgol_w2_p1(x[:, 0]), savgol_filter(x, window_length=2, polyorder=1, axis=0)[:, 0],
                                    rtol=1e-13)
+
+
+def test_degree4_library_order_and_names_equal_sklearn():
+    """pysindy's PolynomialLibrary subclasses sklearn's PolynomialFeatures (sindy.py:185-186 passes degree=4,
+    interaction_only=False): the column order and the feature names of the restatement are pinned on the real class."""
+    from sklearn.preprocessing import PolynomialFeatures
+    rng = np.random.default_rng(11)
+    X = np.stack([rng.uniform(0.1, 30.0, 200), rng.integers(1, 4, 200).astype(np.float64)], axis=1)
+    pf = PolynomialFeatures(degree=4, interaction_only=False, include_bias=True).fit(X)
+    np.testing.assert_allclose(sp.library_poly4(X[:, 0], X[:, 1]), pf.transform(X), rtol=1e-14)
+    assert tuple(map(tuple, pf.powers_)) == sp.POLY4_EXPONENTS
+    assert tuple(pf.get_feature_names_out(['x0', 'u0'])) == sp.POLY4_NAMES
+    # degree 2, interaction only: the 4-term and 11-term libraries of the default and the joint model
+    pf2 = PolynomialFeatures(degree=2, interaction_only=True, include_bias=True).fit(X)
+    np.testing.assert_allclose(sp.library_p4(X[:, 0], X[:, 1]), pf2.transform(X), rtol=1e-15)
+    X4 = np.concatenate([X, rng.integers(0, 2, (200, 2)).astype(np.float64)], axis=1)[:, [0, 2, 3, 1]]
+    pf11 = PolynomialFeatures(degree=2, interaction_only=True, include_bias=True).fit(X4)
+    np.testing.assert_allclose(sp.library_p11(X4[:, 0], X4[:, 1:]), pf11.transform(X4), rtol=1e-15)
+    assert tuple(n.replace(' ', '*') for n in pf11.get_feature_names_out(['x0', 'u0', 'u1', 'u2'])) == sp.JOINT_NAMES
+
+
+def test_degree4_fit_is_insensitive_to_the_unbias_cutoff(seed1):
+    """The degree-4 library is rank 12 of 15 on cancer_sim data; the fit must not depend on which of the two historical
+    cut-offs of the un-bias step (scipy's machine epsilon / today's scikit-learn 1e-6) is used, nor on the row order."""
+    _, o = seed1
+    means, stds = so.scaling_params(o['train'])
+    dtr, sc = sp.process_data(o['train'], means, stds)
+    buckets = sp.de_format_snippets(dtr, sc)
+    th, xd = sp.design_matrices_poly4(buckets[3])
+    assert np.linalg.matrix_rank(th) == 12
+    c_eps, s_eps = sp.stlsq_fit(th, xd, 1e-3, 0.5, scipy_lstsq=True)
+    c_skl, s_skl = sp.stlsq_fit(th, xd, 1e-3, 0.5, scipy_lstsq=False)
+    assert np.array_equal(s_eps, s_skl) and 5 <= s_eps.sum() < 15
+    np.testing.assert_allclose(c_eps, c_skl, rtol=1e-9, atol=1e-14)
+    perm = np.random.default_rng(0).permutation(th.shape[0])
+    c_perm, s_perm = sp.stlsq_fit(th[perm], xd[perm], 1e-3, 0.5, scipy_lstsq=True)
+    assert np.array_equal(s_perm, s_eps)
+    np.testing.assert_allclose(c_perm, c_eps, rtol=1e-9, atol=1e-14)
