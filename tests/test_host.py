@@ -214,3 +214,25 @@ def test_continuous_generate_params_bit_exact_and_rng_consumption():
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (eq, k)
     with pytest.raises(ValueError):
         ct.generate_params(4, 2.0, 2.0, 15, 0, ct.Equation.EQ_4_A)
+
+
+def test_model_switches_outside_the_built_path_are_refused_up_front():
+    """The mirror of SINDY raises NotImplementedError in its constructor (no GPU needed) for the reference switches that
+    are not built, and accepts the ones that are (sindy.py:95-130 of the package)."""
+    import pytest
+    from b200_insite.config import default_config
+    from b200_insite.sindy import SINDY
+    ok = [dict(insite=False), dict(insite=True), dict(insite=False, use_smoothed_finite_difference=True),
+          dict(insite=True, use_smoothed_finite_difference=True), dict(insite=False, sindy_quantize=True),
+          dict(insite=False, ablation_more_complex_basis_functions=True),
+          dict(insite=True, joint_model=True, treatment_mode='multilabel')]
+    for kw in ok:
+        SINDY(default_config(**kw), None, autoregressive=True, has_vitals=False)
+    refused = [dict(wsindy=True), dict(smooth_input_data=True),
+               dict(insite=True, ablation_more_complex_basis_functions=True),
+               dict(insite=False, ablation_more_complex_basis_functions=True, joint_model=True, treatment_mode='multilabel'),
+               dict(insite=False, joint_model=True),                          # the joint model is multilabel
+               dict(insite=False, treatment_mode='multilabel')]
+    for kw in refused:
+        with pytest.raises(NotImplementedError):
+            SINDY(default_config(**kw), None, autoregressive=True, has_vitals=False)
